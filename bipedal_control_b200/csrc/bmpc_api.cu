@@ -1,0 +1,461 @@
+// libbmpc.so: C ABI (include/bmpc.h) + host orchestration of one batched MPC tick on one B200.
+//
+// Host-side mirror of ocs2::MPC_BASE::run / SolverBase::run / SqpSolver::runImpl [UPSTREAM] as driven by
+// MPC_MRT_Interface::advanceMpc (bipedal_controllers/src/BipedalController.cpp:332-351).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/bmpc.h"
+#include "bmpc_gait.h"
+#include "bmpc_kernels.cuh"
+
+namespace bmpc {
+void finalize_model(HostModel& m);
+}
+
+using namespace bmpc;
+
+namespace {
+std::string g_create_error;
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) throw CudaError(std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #call); } while (0)
+
+template <class T> T* dalloc(size_t n) { T* p = nullptr; CK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T))); CK(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T))); return p; }
+template <class T> T* halloc(size_t n) { T* p = nullptr; CK(cudaMallocHost(&p, std::max<size_t>(n, 1) * sizeof(T))); std::memset(p, 0, std::max<size_t>(n, 1) * sizeof(T)); return p; }
+}  // namespace
+
+struct bmpc_handle {
+  HostModel model;
+  int B = 0, NS = 0, ME = 0, TP = 0, nj = 0, nx = 0, nu = 0, device = 0, sqp_iterations = 1;
+  double dt = 0, horizon = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // inputs (device) and their pinned staging copies
+  double *d_t0 = nullptr, *d_x0 = nullptr, *d_tgt_t = nullptr, *d_tgt_x = nullptr, *d_ev_t = nullptr;
+  int *d_n_ev = nullptr, *d_ev_mode = nullptr;
+  double *h_t0 = nullptr, *h_x0 = nullptr, *h_tgt_t = nullptr, *h_tgt_x = nullptr, *h_ev_t = nullptr;
+  int *h_n_ev = nullptr, *h_ev_mode = nullptr;
+  bool obs_dirty = false, tgt_dirty = false, sched_dirty = false, have_obs = false, have_tgt = false, have_sched = false;
+  int npts = 0;
+  // node grid work arrays
+  double *d_st_t = nullptr, *d_st_dt = nullptr, *d_xref = nullptr, *d_zref = nullptr;
+  int* d_st_mode = nullptr;
+  // primal solutions (double buffered)
+  int* s_n[2] = {nullptr, nullptr}; int* s_ev[2] = {nullptr, nullptr};
+  double *s_t[2] = {nullptr, nullptr}, *s_x[2] = {nullptr, nullptr}, *s_u[2] = {nullptr, nullptr}, *s_uff[2] = {nullptr, nullptr}, *s_K[2] = {nullptr, nullptr};
+  int cur = 0; bool have_solution = false;
+  // work
+  double *d_lq = nullptr, *d_proj = nullptr, *d_ric = nullptr, *d_dx = nullptr, *d_du = nullptr, *d_perf_trial = nullptr, *d_perf = nullptr, *d_alpha = nullptr, *d_norms = nullptr;
+  int *d_done = nullptr, *d_status = nullptr, *d_counters = nullptr;
+  int* h_counters = nullptr;
+  size_t rec = 0, prec = 0, krec = 0;
+  // gait bookkeeping
+  std::vector<GaitSchedule> gaits; bool use_gait = false;
+  // stats
+  int launches = 0; bool timing = false; cudaEvent_t tev[9] = {}; float phase_ms[8] = {};
+  int linesearch_trials = 0;
+  // scratch for policy evaluation
+  double *d_eval_t = nullptr, *d_eval_x = nullptr, *d_eval_xo = nullptr, *d_eval_uo = nullptr; int* d_eval_m = nullptr;
+};
+
+namespace {
+
+Dev make_dev(bmpc_handle* h) {
+  const int w = 1 - h->cur;
+  Dev d;
+  d.B = h->B; d.NS = h->NS; d.ME = h->ME; d.TP = h->TP; d.npts = h->npts;
+  d.dt_nom = h->dt; d.horizon = h->horizon;
+  d.t0 = h->d_t0; d.x0 = h->d_x0; d.tgt_t = h->d_tgt_t; d.tgt_x = h->d_tgt_x;
+  d.n_ev = h->d_n_ev; d.ev_t = h->d_ev_t; d.ev_mode = h->d_ev_mode;
+  d.n_nodes = h->s_n[w]; d.node_t = h->s_t[w]; d.node_ev = h->s_ev[w];
+  d.st_t = h->d_st_t; d.st_dt = h->d_st_dt; d.st_mode = h->d_st_mode; d.xref = h->d_xref; d.zref = h->d_zref;
+  d.p_n = h->have_solution ? h->s_n[h->cur] : nullptr; d.p_t = h->s_t[h->cur]; d.p_x = h->s_x[h->cur]; d.p_u = h->s_u[h->cur];
+  d.s_x = h->s_x[w]; d.s_u = h->s_u[w]; d.s_uff = h->s_uff[w]; d.s_K = h->s_K[w];
+  d.lq = h->d_lq; d.proj = h->d_proj; d.ric = h->d_ric; d.dx = h->d_dx; d.du = h->d_du;
+  d.perf_trial = h->d_perf_trial; d.perf = h->d_perf; d.alpha = h->d_alpha; d.norms = h->d_norms; d.done = h->d_done; d.status = h->d_status; d.counters = h->d_counters;
+  return d;
+}
+
+template <int NJ>
+void tick(bmpc_handle* h) {
+  using D = Dims<NJ>; using R = RDims<NJ>;
+  cudaStream_t st = h->stream;
+  const int B = h->B, NS = h->NS;
+  auto mark = [&](int i) { if (h->timing) CK(cudaEventRecord(h->tev[i], st)); };
+  h->launches = 0;
+  CK(cudaMemcpyToSymbolAsync(c_model, &h->model.dev, sizeof(DevModel), 0, cudaMemcpyHostToDevice, st));
+  // stage inputs
+  if (h->obs_dirty) { CK(cudaMemcpyAsync(h->d_t0, h->h_t0, sizeof(double) * B, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(h->d_x0, h->h_x0, sizeof(double) * B * h->nx, cudaMemcpyHostToDevice, st)); h->obs_dirty = false; }
+  if (h->tgt_dirty) { CK(cudaMemcpyAsync(h->d_tgt_t, h->h_tgt_t, sizeof(double) * B * h->TP, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(h->d_tgt_x, h->h_tgt_x, sizeof(double) * B * h->TP * h->nx, cudaMemcpyHostToDevice, st)); h->tgt_dirty = false; }
+  if (h->sched_dirty) {
+    CK(cudaMemcpyAsync(h->d_n_ev, h->h_n_ev, sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_ev_t, h->h_ev_t, sizeof(double) * B * h->ME, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_ev_mode, h->h_ev_mode, sizeof(int) * B * (h->ME + 1), cudaMemcpyHostToDevice, st));
+    h->sched_dirty = false;
+  }
+  CK(cudaMemsetAsync(h->d_status, 0, sizeof(int) * B, st));
+  Dev d = make_dev(h);
+  const int nodes = B * NS;
+  mark(0);
+  k_time_grid<<<(B + 127) / 128, 128, 0, st>>>(d); ++h->launches;
+  k_node_setup<NJ><<<(nodes + 127) / 128, 128, 0, st>>>(d); ++h->launches;
+  mark(1);
+  CK(cudaFuncSetAttribute(k_riccati<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem<NJ>)));
+  h->linesearch_trials = 0;
+  for (int iter = 0; iter < h->sqp_iterations; ++iter) {
+    k_lq<NJ><<<(nodes + 63) / 64, 64, 0, st>>>(d); ++h->launches;
+    if (iter == 0) mark(2);
+    k_project<NJ><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches;
+    if (iter == 0) mark(3);
+    k_riccati<NJ><<<B, WS_THREADS, sizeof(RicSmem<NJ>), st>>>(d); ++h->launches;
+    if (iter == 0) mark(4);
+    k_forward<NJ><<<(B + 3) / 4, 128, 0, st>>>(d); ++h->launches;
+    if (iter == 0) mark(5);
+    // filter line search: all instances try alpha = 1 first; the rejected ones halve their step
+    for (int trial = 0; trial < 16; ++trial) {
+      CK(cudaMemsetAsync(h->d_counters, 0, sizeof(int), st));
+      k_linesearch_eval<NJ><<<(nodes + 63) / 64, 64, 0, st>>>(d); ++h->launches;
+      k_accept<NJ><<<(B + 3) / 4, 128, 0, st>>>(d); ++h->launches;
+      ++h->linesearch_trials;
+      CK(cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (h->h_counters[0] == 0) break;
+    }
+    if (iter == 0) mark(6);
+    k_update<NJ><<<(nodes + 127) / 128, 128, 0, st>>>(d); ++h->launches;
+  }
+  k_policy_fill<NJ><<<B, 128, 0, st>>>(d); ++h->launches;
+  mark(7);
+  CK(cudaGetLastError());
+  h->cur = 1 - h->cur; h->have_solution = true;
+  (void)sizeof(D); (void)sizeof(R);
+}
+
+void compute_gait_schedules(bmpc_handle* h) {
+  if (!h->have_obs) throw std::invalid_argument("[bmpc] gait schedule mode needs host observations (bmpc_set_observations)");
+  const int B = h->B, ME = h->ME;
+  for (int b = 0; b < B; ++b) {
+    const double t0 = h->h_t0[b], tf = t0 + h->horizon;
+    // SwitchedModelReferenceManager::modifyReferences (SwitchedModelReferenceManager.cpp:62-69)
+    const ModeSchedule& ms = h->gaits[b].getModeSchedule(t0 - h->horizon, tf + h->horizon);
+    const int ne = (int)ms.eventTimes.size();
+    if (ne > ME) throw std::length_error("[bmpc] mode schedule exceeds max_events");
+    h->h_n_ev[b] = ne;
+    for (int i = 0; i < ne; ++i) h->h_ev_t[(size_t)b * ME + i] = ms.eventTimes[i];
+    for (int i = 0; i <= ne; ++i) h->h_ev_mode[(size_t)b * (ME + 1) + i] = ms.modeSequence[i];
+  }
+  h->sched_dirty = true; h->have_sched = true;
+}
+
+int fail(bmpc_handle* h, int code, const std::string& msg) { if (h) h->err = msg; else g_create_error = msg; return code; }
+
+#define API_BEGIN try {
+#define API_END(h) } catch (const CudaError& e) { return fail(h, BMPC_ERR_CUDA, e.what()); } \
+  catch (const std::invalid_argument& e) { return fail(h, BMPC_ERR_INVALID, e.what()); } \
+  catch (const std::length_error& e) { return fail(h, BMPC_ERR_CAPACITY, e.what()); } \
+  catch (const std::exception& e) { return fail(h, BMPC_ERR_INVALID, e.what()); }
+
+}  // namespace
+
+extern "C" {
+
+const char* bmpc_last_error(const bmpc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
+  bmpc_handle* h = nullptr;
+  try {
+    if (!cfg || !out) throw std::invalid_argument("[bmpc] null config");
+    if (cfg->batch <= 0) throw std::invalid_argument("[bmpc] batch must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw CudaError("CUDA: no device available (libbmpc has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) throw std::invalid_argument("[bmpc] invalid device ordinal");
+    CK(cudaSetDevice(cfg->device));
+    h = new bmpc_handle();
+    if (cfg->model_file && cfg->model_file[0]) h->model = load_compact_model(cfg->model_file);
+    else if (cfg->task_file && cfg->urdf_file && cfg->reference_file)
+      h->model = load_reference_files(cfg->task_file, cfg->reference_file, cfg->gait_file ? cfg->gait_file : "", cfg->urdf_file);
+    else throw std::invalid_argument("[bmpc] either model_file or task_file + reference_file + urdf_file must be given");
+    h->device = cfg->device;
+    h->B = cfg->batch; h->nj = h->model.nj; h->nx = h->model.nx; h->nu = h->model.nu;
+    h->dt = cfg->dt > 0 ? cfg->dt : h->model.sqp_dt;
+    h->horizon = cfg->time_horizon > 0 ? cfg->time_horizon : h->model.time_horizon;
+    h->ME = cfg->max_events > 0 ? cfg->max_events : 40;
+    h->TP = cfg->max_target_points > 0 ? cfg->max_target_points : 4;
+    h->sqp_iterations = cfg->sqp_iterations > 0 ? cfg->sqp_iterations : h->model.sqp_iterations;
+    h->NS = (int)std::ceil(h->horizon / h->dt - 1e-9) + 1 + 16;   // nominal grid + up to 16 event nodes inside the horizon
+    const size_t B = h->B, NS = h->NS, nx = h->nx, nu = h->nu;
+    if (h->nj == 10) { h->rec = Dims<10>::REC; h->prec = Dims<10>::PREC; h->krec = RDims<10>::KREC; }
+    else { h->rec = Dims<12>::REC; h->prec = Dims<12>::PREC; h->krec = RDims<12>::KREC; }
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& e : h->tev) CK(cudaEventCreate(&e));
+    h->d_t0 = dalloc<double>(B); h->d_x0 = dalloc<double>(B * nx); h->d_tgt_t = dalloc<double>(B * h->TP); h->d_tgt_x = dalloc<double>(B * h->TP * nx);
+    h->d_n_ev = dalloc<int>(B); h->d_ev_t = dalloc<double>(B * h->ME); h->d_ev_mode = dalloc<int>(B * (h->ME + 1));
+    h->h_t0 = halloc<double>(B); h->h_x0 = halloc<double>(B * nx); h->h_tgt_t = halloc<double>(B * h->TP); h->h_tgt_x = halloc<double>(B * h->TP * nx);
+    h->h_n_ev = halloc<int>(B); h->h_ev_t = halloc<double>(B * h->ME); h->h_ev_mode = halloc<int>(B * (h->ME + 1));
+    h->d_st_t = dalloc<double>(B * NS); h->d_st_dt = dalloc<double>(B * NS); h->d_st_mode = dalloc<int>(B * NS);
+    h->d_xref = dalloc<double>(B * NS * nx); h->d_zref = dalloc<double>(B * NS * 2);
+    for (int i = 0; i < 2; ++i) {
+      h->s_n[i] = dalloc<int>(B); h->s_ev[i] = dalloc<int>(B * NS); h->s_t[i] = dalloc<double>(B * NS);
+      h->s_x[i] = dalloc<double>(B * NS * nx); h->s_u[i] = dalloc<double>(B * NS * nu); h->s_uff[i] = dalloc<double>(B * NS * nu);
+      h->s_K[i] = dalloc<double>(B * NS * nu * nx);
+    }
+    h->d_lq = dalloc<double>(B * NS * h->rec); h->d_proj = dalloc<double>(B * NS * h->prec); h->d_ric = dalloc<double>(B * NS * h->krec);
+    h->d_dx = dalloc<double>(B * NS * nx); h->d_du = dalloc<double>(B * NS * nu);
+    h->d_perf_trial = dalloc<double>(B * NS * 3); h->d_perf = dalloc<double>(B * 8); h->d_alpha = dalloc<double>(B); h->d_norms = dalloc<double>(B * 2);
+    h->d_done = dalloc<int>(B); h->d_status = dalloc<int>(B); h->d_counters = dalloc<int>(4); h->h_counters = halloc<int>(4);
+    h->d_eval_t = dalloc<double>(B); h->d_eval_x = dalloc<double>(B * nx); h->d_eval_xo = dalloc<double>(B * nx); h->d_eval_uo = dalloc<double>(B * nu); h->d_eval_m = dalloc<int>(B);
+    // per-instance gait schedules start from reference.info's initialModeSchedule / defaultModeSequenceTemplate (BipedalRobotInterface.cpp:209-234)
+    GaitSchedule g0; g0.ms.eventTimes = h->model.init_events; g0.ms.modeSequence = h->model.init_modes; g0.tmpl = h->model.default_template;
+    g0.phaseTransitionStanceTime = h->model.phase_transition_stance_time;
+    h->gaits.assign(B, g0);
+    *out = h;
+    return BMPC_OK;
+  } catch (const CudaError& e) { delete h; return fail(nullptr, BMPC_ERR_CUDA, e.what()); }
+  catch (const std::invalid_argument& e) { delete h; return fail(nullptr, BMPC_ERR_INVALID, e.what()); }
+  catch (const std::exception& e) { delete h; return fail(nullptr, BMPC_ERR_INVALID, e.what()); }
+}
+
+void bmpc_destroy(bmpc_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  void* dptrs[] = {h->d_t0, h->d_x0, h->d_tgt_t, h->d_tgt_x, h->d_ev_t, h->d_n_ev, h->d_ev_mode, h->d_st_t, h->d_st_dt, h->d_xref, h->d_zref, h->d_st_mode,
+                   h->s_n[0], h->s_n[1], h->s_ev[0], h->s_ev[1], h->s_t[0], h->s_t[1], h->s_x[0], h->s_x[1], h->s_u[0], h->s_u[1], h->s_uff[0], h->s_uff[1], h->s_K[0], h->s_K[1],
+                   h->d_lq, h->d_proj, h->d_ric, h->d_dx, h->d_du, h->d_perf_trial, h->d_perf, h->d_alpha, h->d_norms, h->d_done, h->d_status, h->d_counters,
+                   h->d_eval_t, h->d_eval_x, h->d_eval_xo, h->d_eval_uo, h->d_eval_m};
+  for (void* p : dptrs) if (p) cudaFree(p);
+  void* hptrs[] = {h->h_t0, h->h_x0, h->h_tgt_t, h->h_tgt_x, h->h_ev_t, h->h_n_ev, h->h_ev_mode, h->h_counters};
+  for (void* p : hptrs) if (p) cudaFreeHost(p);
+  for (auto& e : h->tev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int bmpc_get_dims(const bmpc_handle* h, int* nx, int* nu, int* batch, int* max_nodes) {
+  if (!h) return BMPC_ERR_INVALID;
+  if (nx) *nx = h->nx; if (nu) *nu = h->nu; if (batch) *batch = h->B; if (max_nodes) *max_nodes = h->NS;
+  return BMPC_OK;
+}
+int bmpc_get_initial_state(const bmpc_handle* h, double* x) { if (!h || !x) return BMPC_ERR_INVALID; for (int i = 0; i < h->nx; ++i) x[i] = h->model.initial_state[i]; return BMPC_OK; }
+int bmpc_export_model(const bmpc_handle* h, const char* path) {
+  bmpc_handle* hh = const_cast<bmpc_handle*>(h);
+  API_BEGIN if (!h || !path) throw std::invalid_argument("[bmpc] null argument"); save_compact_model(h->model, path); return BMPC_OK; API_END(hh)
+}
+
+int bmpc_reset(bmpc_handle* h) {
+  API_BEGIN if (!h) return BMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream));
+  h->have_solution = false;
+  GaitSchedule g0; g0.ms.eventTimes = h->model.init_events; g0.ms.modeSequence = h->model.init_modes; g0.tmpl = h->model.default_template;
+  g0.phaseTransitionStanceTime = h->model.phase_transition_stance_time;
+  h->gaits.assign(h->B, g0);
+  return BMPC_OK; API_END(h)
+}
+
+int bmpc_set_observations(bmpc_handle* h, const double* t, const double* x) {
+  API_BEGIN if (!h || !t || !x) throw std::invalid_argument("[bmpc] null argument");
+  std::memcpy(h->h_t0, t, sizeof(double) * h->B); std::memcpy(h->h_x0, x, sizeof(double) * h->B * h->nx);
+  h->obs_dirty = true; h->have_obs = true; return BMPC_OK; API_END(h)
+}
+int bmpc_set_observations_device(bmpc_handle* h, const double* t, const double* x) {
+  API_BEGIN if (!h || !t || !x) throw std::invalid_argument("[bmpc] null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->d_t0, t, sizeof(double) * h->B, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_x0, x, sizeof(double) * h->B * h->nx, cudaMemcpyDeviceToDevice, h->stream));
+  h->obs_dirty = false; h->have_obs = false; return BMPC_OK; API_END(h)
+}
+int bmpc_set_target_trajectories(bmpc_handle* h, int npts, const double* times, const double* states) {
+  API_BEGIN if (!h || !times || !states) throw std::invalid_argument("[bmpc] null argument");
+  if (npts < 1 || npts > h->TP) throw std::length_error("[bmpc] number of target points exceeds max_target_points");
+  for (int b = 0; b < h->B; ++b) {
+    std::memcpy(h->h_tgt_t + (size_t)b * h->TP, times + (size_t)b * npts, sizeof(double) * npts);
+    std::memcpy(h->h_tgt_x + (size_t)b * h->TP * h->nx, states + (size_t)b * npts * h->nx, sizeof(double) * npts * h->nx);
+  }
+  h->npts = npts; h->tgt_dirty = true; h->have_tgt = true; return BMPC_OK; API_END(h)
+}
+int bmpc_set_target_trajectories_device(bmpc_handle* h, int npts, const double* times, const double* states) {
+  API_BEGIN if (!h || !times || !states) throw std::invalid_argument("[bmpc] null argument");
+  if (npts < 1 || npts > h->TP) throw std::length_error("[bmpc] number of target points exceeds max_target_points");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy2DAsync(h->d_tgt_t, sizeof(double) * h->TP, times, sizeof(double) * npts, sizeof(double) * npts, h->B, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpy2DAsync(h->d_tgt_x, sizeof(double) * h->TP * h->nx, states, sizeof(double) * npts * h->nx, sizeof(double) * npts * h->nx, h->B, cudaMemcpyDeviceToDevice, h->stream));
+  h->npts = npts; h->tgt_dirty = false; h->have_tgt = true; return BMPC_OK; API_END(h)
+}
+// TargetTrajectoriesPublisher.cpp:41-99
+int bmpc_set_targets_from_cmd_vel(bmpc_handle* h, const double* cmd, double time_to_target) {
+  API_BEGIN if (!h || !cmd) throw std::invalid_argument("[bmpc] null argument");
+  if (!h->have_obs) throw std::invalid_argument("[bmpc] set observations (host) before bmpc_set_targets_from_cmd_vel");
+  if (h->TP < 2) throw std::length_error("[bmpc] max_target_points < 2");
+  const int nx = h->nx, nj = h->nj;
+  for (int b = 0; b < h->B; ++b) {
+    const double* x = h->h_x0 + (size_t)b * nx; const double* c = cmd + (size_t)b * 4;
+    const double z = x[9], y = x[10], r = x[11];
+    const double cz = std::cos(z), sz = std::sin(z), cy = std::cos(y), sy = std::sin(y), cx = std::cos(r), sx = std::sin(r);
+    const double R[9] = {cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx, sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx, -sy, cy * sx, cy * cx};
+    const double vr[3] = {R[0] * c[0] + R[1] * c[1] + R[2] * c[2], R[3] * c[0] + R[4] * c[1] + R[5] * c[2], R[6] * c[0] + R[7] * c[1] + R[8] * c[2]};
+    double* s0 = h->h_tgt_x + (size_t)b * h->TP * nx; double* s1 = s0 + nx;
+    std::fill(s0, s0 + 2 * nx, 0.0);
+    s0[0] = s1[0] = vr[0]; s0[1] = s1[1] = vr[1]; s0[2] = s1[2] = vr[2];
+    s0[6] = x[6]; s0[7] = x[7]; s0[8] = h->model.com_height; s0[9] = x[9];
+    s1[6] = x[6] + vr[0] * time_to_target; s1[7] = x[7] + vr[1] * time_to_target; s1[8] = h->model.com_height; s1[9] = x[9] + c[3] * time_to_target;
+    for (int j = 0; j < nj; ++j) { s0[12 + j] = h->model.default_joint_state[j]; s1[12 + j] = h->model.default_joint_state[j]; }
+    h->h_tgt_t[(size_t)b * h->TP] = h->h_t0[b]; h->h_tgt_t[(size_t)b * h->TP + 1] = h->h_t0[b] + time_to_target;
+  }
+  h->npts = 2; h->tgt_dirty = true; h->have_tgt = true; return BMPC_OK; API_END(h)
+}
+int bmpc_set_mode_schedules(bmpc_handle* h, int stride, const int* n_events, const double* event_times, const int* mode_sequence) {
+  API_BEGIN if (!h || !n_events || !event_times || !mode_sequence) throw std::invalid_argument("[bmpc] null argument");
+  for (int b = 0; b < h->B; ++b) {
+    const int ne = n_events[b];
+    if (ne < 0 || ne > h->ME || ne > stride) throw std::length_error("[bmpc] mode schedule exceeds max_events");
+    h->h_n_ev[b] = ne;
+    std::memcpy(h->h_ev_t + (size_t)b * h->ME, event_times + (size_t)b * stride, sizeof(double) * ne);
+    std::memcpy(h->h_ev_mode + (size_t)b * (h->ME + 1), mode_sequence + (size_t)b * (stride + 1), sizeof(int) * (ne + 1));
+  }
+  h->sched_dirty = true; h->have_sched = true; h->use_gait = false; return BMPC_OK; API_END(h)
+}
+int bmpc_set_mode_schedules_device(bmpc_handle* h, int stride, const int* n_events, const double* event_times, const int* mode_sequence) {
+  API_BEGIN if (!h || !n_events || !event_times || !mode_sequence) throw std::invalid_argument("[bmpc] null argument");
+  if (stride > h->ME) throw std::length_error("[bmpc] mode schedule stride exceeds max_events");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->d_n_ev, n_events, sizeof(int) * h->B, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpy2DAsync(h->d_ev_t, sizeof(double) * h->ME, event_times, sizeof(double) * stride, sizeof(double) * stride, h->B, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpy2DAsync(h->d_ev_mode, sizeof(int) * (h->ME + 1), mode_sequence, sizeof(int) * (stride + 1), sizeof(int) * (stride + 1), h->B, cudaMemcpyDeviceToDevice, h->stream));
+  h->sched_dirty = false; h->have_sched = true; h->use_gait = false; return BMPC_OK; API_END(h)
+}
+
+int bmpc_gait_insert(bmpc_handle* h, int instance, int n_modes, const int* modes, const double* switching_times, double start_time, double final_time) {
+  API_BEGIN if (!h || !modes || !switching_times || n_modes <= 0) throw std::invalid_argument("[bmpc] null argument");
+  if (instance >= h->B) throw std::invalid_argument("[bmpc] instance out of range");
+  GaitTemplate t; t.modes.assign(modes, modes + n_modes); t.times.assign(switching_times, switching_times + n_modes + 1);
+  const int b0 = instance < 0 ? 0 : instance, b1 = instance < 0 ? h->B : instance + 1;
+  for (int b = b0; b < b1; ++b) h->gaits[b].insertModeSequenceTemplate(t, start_time, final_time);
+  return BMPC_OK; API_END(h)
+}
+int bmpc_gait_insert_named(bmpc_handle* h, int instance, const char* gait_name, double start_time, double final_time) {
+  if (!h || !gait_name) return BMPC_ERR_INVALID;
+  for (const auto& g : h->model.gaits)
+    if (g.name == gait_name) return bmpc_gait_insert(h, instance, (int)g.modes.size(), g.modes.data(), g.times.data(), start_time, final_time);
+  return fail(h, BMPC_ERR_INVALID, std::string("[bmpc] unknown gait '") + gait_name + "'");
+}
+int bmpc_use_gait_schedule(bmpc_handle* h, int enable) { if (!h) return BMPC_ERR_INVALID; h->use_gait = enable != 0; return BMPC_OK; }
+int bmpc_gait_peek(const bmpc_handle* h, int instance, int cap, double* event_times, int* mode_sequence) {
+  if (!h || instance < 0 || instance >= h->B) return BMPC_ERR_INVALID;
+  const ModeSchedule& ms = h->gaits[instance].ms;
+  const int n = (int)ms.eventTimes.size();
+  if (n > cap) return BMPC_ERR_CAPACITY;
+  for (int i = 0; i < n; ++i) event_times[i] = ms.eventTimes[i];
+  for (int i = 0; i <= n; ++i) mode_sequence[i] = ms.modeSequence[i];
+  return n;
+}
+
+int bmpc_advance_async(bmpc_handle* h) {
+  API_BEGIN if (!h) return BMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  if (h->use_gait) compute_gait_schedules(h);
+  if (!h->have_tgt) throw std::invalid_argument("[bmpc] target trajectories not set");
+  if (!h->have_sched) throw std::invalid_argument("[bmpc] mode schedules not set (bmpc_set_mode_schedules or bmpc_use_gait_schedule)");
+  if (h->nj == 10) tick<10>(h); else tick<12>(h);
+  return BMPC_OK; API_END(h)
+}
+int bmpc_synchronize(bmpc_handle* h) {
+  API_BEGIN if (!h) return BMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream));
+  if (h->timing) for (int i = 0; i < 7; ++i) cudaEventElapsedTime(&h->phase_ms[i], h->tev[i], h->tev[i + 1]);
+  return BMPC_OK; API_END(h)
+}
+int bmpc_advance(bmpc_handle* h) { const int rc = bmpc_advance_async(h); return rc != BMPC_OK ? rc : bmpc_synchronize(h); }
+
+int bmpc_get_policy(bmpc_handle* h, int first, int count, int* n_nodes, double* times, int* events, double* x, double* u, double* uff, double* K) {
+  API_BEGIN if (!h) return BMPC_ERR_INVALID;
+  if (!h->have_solution) throw std::invalid_argument("[bmpc] no solution yet");
+  if (first < 0 || count < 0 || first + count > h->B) throw std::invalid_argument("[bmpc] instance range out of bounds");
+  CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream));
+  const int c = h->cur; const size_t NS = h->NS, nx = h->nx, nu = h->nu, f = first, n = count;
+  if (n_nodes) CK(cudaMemcpy(n_nodes, h->s_n[c] + f, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  if (times) CK(cudaMemcpy(times, h->s_t[c] + f * NS, sizeof(double) * n * NS, cudaMemcpyDeviceToHost));
+  if (events) CK(cudaMemcpy(events, h->s_ev[c] + f * NS, sizeof(int) * n * NS, cudaMemcpyDeviceToHost));
+  if (x) CK(cudaMemcpy(x, h->s_x[c] + f * NS * nx, sizeof(double) * n * NS * nx, cudaMemcpyDeviceToHost));
+  if (u) CK(cudaMemcpy(u, h->s_u[c] + f * NS * nu, sizeof(double) * n * NS * nu, cudaMemcpyDeviceToHost));
+  if (uff) CK(cudaMemcpy(uff, h->s_uff[c] + f * NS * nu, sizeof(double) * n * NS * nu, cudaMemcpyDeviceToHost));
+  if (K) CK(cudaMemcpy(K, h->s_K[c] + f * NS * nu * nx, sizeof(double) * n * NS * nu * nx, cudaMemcpyDeviceToHost));
+  return BMPC_OK; API_END(h)
+}
+int bmpc_get_device_view(bmpc_handle* h, bmpc_device_view* v) {
+  if (!h || !v || !h->have_solution) return BMPC_ERR_INVALID;
+  const int c = h->cur;
+  v->n_nodes = h->s_n[c]; v->times = h->s_t[c]; v->events = h->s_ev[c]; v->x = h->s_x[c]; v->u = h->s_u[c]; v->uff = h->s_uff[c]; v->K = h->s_K[c];
+  v->max_nodes = h->NS; v->nx = h->nx; v->nu = h->nu; v->batch = h->B;
+  return BMPC_OK;
+}
+int bmpc_get_performance(bmpc_handle* h, double* perf) {
+  API_BEGIN if (!h || !perf) return BMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(perf, h->d_perf, sizeof(double) * h->B * 8, cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream));
+  return BMPC_OK; API_END(h)
+}
+int bmpc_get_status(bmpc_handle* h, int* status) {
+  API_BEGIN if (!h || !status) return BMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(status, h->d_status, sizeof(int) * h->B, cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream));
+  return BMPC_OK; API_END(h)
+}
+int bmpc_evaluate_policy(bmpc_handle* h, const double* t, const double* x, double* x_opt, double* u_opt, int* mode) {
+  API_BEGIN if (!h || !t || !x) return BMPC_ERR_INVALID;
+  if (!h->have_solution) throw std::invalid_argument("[bmpc] no solution yet");
+  CK(cudaSetDevice(h->device));
+  const int c = h->cur, B = h->B; cudaStream_t st = h->stream;
+  CK(cudaMemcpyAsync(h->d_eval_t, t, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_eval_x, x, sizeof(double) * B * h->nx, cudaMemcpyHostToDevice, st));
+  if (h->nj == 10) k_evaluate_policy<10><<<B, 32, 0, st>>>(B, h->NS, h->ME, h->s_n[c], h->s_t[c], h->s_x[c], h->s_uff[c], h->s_K[c], h->d_n_ev, h->d_ev_t, h->d_ev_mode, h->d_eval_t, h->d_eval_x, h->d_eval_xo, h->d_eval_uo, h->d_eval_m);
+  else k_evaluate_policy<12><<<B, 32, 0, st>>>(B, h->NS, h->ME, h->s_n[c], h->s_t[c], h->s_x[c], h->s_uff[c], h->s_K[c], h->d_n_ev, h->d_ev_t, h->d_ev_mode, h->d_eval_t, h->d_eval_x, h->d_eval_xo, h->d_eval_uo, h->d_eval_m);
+  if (x_opt) CK(cudaMemcpyAsync(x_opt, h->d_eval_xo, sizeof(double) * B * h->nx, cudaMemcpyDeviceToHost, st));
+  if (u_opt) CK(cudaMemcpyAsync(u_opt, h->d_eval_uo, sizeof(double) * B * h->nu, cudaMemcpyDeviceToHost, st));
+  if (mode) CK(cudaMemcpyAsync(mode, h->d_eval_m, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+  return BMPC_OK; API_END(h)
+}
+
+int bmpc_get_launch_count(const bmpc_handle* h) { return h ? h->launches : 0; }
+int bmpc_enable_phase_timing(bmpc_handle* h, int enable) { if (!h) return BMPC_ERR_INVALID; h->timing = enable != 0; return BMPC_OK; }
+int bmpc_get_phase_times(bmpc_handle* h, float* ms) { if (!h || !ms) return BMPC_ERR_INVALID; for (int i = 0; i < 7; ++i) ms[i] = h->phase_ms[i]; ms[7] = (float)h->linesearch_trials; return BMPC_OK; }
+void* bmpc_get_stream(bmpc_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int bmpc_debug_record_sizes(const bmpc_handle* h, int* lq_rec, int* proj_rec, int* ric_rec) {
+  if (!h) return BMPC_ERR_INVALID;
+  if (lq_rec) *lq_rec = (int)h->rec; if (proj_rec) *proj_rec = (int)h->prec; if (ric_rec) *ric_rec = (int)h->krec;
+  return BMPC_OK;
+}
+int bmpc_debug_copy(bmpc_handle* h, const char* name, int instance, double* dst, int capacity) {
+  API_BEGIN if (!h || !name || !dst || instance < 0 || instance >= h->B) return BMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream));
+  const std::string n(name); const size_t NS = h->NS, b = instance;
+  const double* src = nullptr; size_t cnt = 0;
+  const int c = h->cur;
+  if (n == "lq_record") { src = h->d_lq + b * NS * h->rec; cnt = NS * h->rec; }
+  else if (n == "proj_record") { src = h->d_proj + b * NS * h->prec; cnt = NS * h->prec; }
+  else if (n == "riccati_record") { src = h->d_ric + b * NS * h->krec; cnt = NS * h->krec; }
+  else if (n == "dx") { src = h->d_dx + b * NS * h->nx; cnt = NS * h->nx; }
+  else if (n == "du") { src = h->d_du + b * NS * h->nu; cnt = NS * h->nu; }
+  else if (n == "xref") { src = h->d_xref + b * NS * h->nx; cnt = NS * h->nx; }
+  else if (n == "zref") { src = h->d_zref + b * NS * 2; cnt = NS * 2; }
+  else if (n == "st_t") { src = h->d_st_t + b * NS; cnt = NS; }
+  else if (n == "st_dt") { src = h->d_st_dt + b * NS; cnt = NS; }
+  else if (n == "x") { src = h->s_x[c] + b * NS * h->nx; cnt = NS * h->nx; }
+  else if (n == "u") { src = h->s_u[c] + b * NS * h->nu; cnt = NS * h->nu; }
+  else throw std::invalid_argument("[bmpc] unknown debug buffer " + n);
+  if ((size_t)capacity < cnt) throw std::length_error("[bmpc] debug buffer capacity too small");
+  CK(cudaMemcpy(dst, src, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
+  return (int)cnt; API_END(h)
+}
+
+}  // extern "C"

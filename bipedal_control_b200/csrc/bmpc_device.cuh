@@ -1,0 +1,380 @@
+// Thread-level model mathematics of the centroidal OCP (sm_100a, FP64).
+//
+// Hand-derived replacements for the CppADCodeGen libraries the reference dlopens:
+//   - PinocchioCentroidalDynamicsAD flow map + exact Jacobians (call site
+//     ocs2_bipedal_robot/src/dynamics/BipedalRobotDynamicsAD.cpp:46-56),
+//   - PinocchioEndEffectorKinematicsCppAd contact velocity + Jacobians (built at
+//     ocs2_bipedal_robot/src/BipedalRobotInterface.cpp:169-178, used by
+//     src/constraint/EndEffectorLinearConstraint.cpp:89-111).
+// The derivatives are analytic (spatial-algebra recursion over the kinematic tree), not dual numbers:
+//   d(A(q) v)/dq_k |v = S_k x* h_sub(k) - I_sub(k) (S_k x v_parent(k))      (momentum, about the world origin)
+//   d(pdot_i)/dq_k |v = a_k x u_w + w_k x (a_k x (p_i - o_k))                (contact point velocity)
+// and are checked against the oracle's forward-mode duals in tests/.
+#pragma once
+#include <cuda_runtime.h>
+#include "bmpc_model.h"
+
+namespace bmpc {
+
+__constant__ DevModel c_model;
+
+struct v3 { double x, y, z; };
+__device__ __forceinline__ v3 mk(double x, double y, double z) { v3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ v3 operator+(v3 a, v3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ v3 operator-(v3 a, v3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ v3 operator*(double s, v3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ v3 cross(v3 a, v3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ double dot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ double comp(v3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+struct m3 { double m[9]; };
+__device__ __forceinline__ v3 mul(const m3& R, v3 v) { return mk(R.m[0] * v.x + R.m[1] * v.y + R.m[2] * v.z, R.m[3] * v.x + R.m[4] * v.y + R.m[5] * v.z, R.m[6] * v.x + R.m[7] * v.y + R.m[8] * v.z); }
+__device__ __forceinline__ v3 mulc(const double* R, const double* v) { return mk(R[0] * v[0] + R[1] * v[1] + R[2] * v[2], R[3] * v[0] + R[4] * v[1] + R[5] * v[2], R[6] * v[0] + R[7] * v[1] + R[8] * v[2]); }
+__device__ __forceinline__ m3 mul(const m3& A, const m3& B) {
+  m3 C;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C.m[3 * i + j] = A.m[3 * i] * B.m[j] + A.m[3 * i + 1] * B.m[3 + j] + A.m[3 * i + 2] * B.m[6 + j];
+  return C;
+}
+__device__ __forceinline__ m3 mulc(const m3& A, const double* B) {
+  m3 C;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C.m[3 * i + j] = A.m[3 * i] * B[j] + A.m[3 * i + 1] * B[3 + j] + A.m[3 * i + 2] * B[6 + j];
+  return C;
+}
+// symmetric 3x3 stored as xx, xy, xz, yy, yz, zz
+struct s3 { double xx, xy, xz, yy, yz, zz; };
+__device__ __forceinline__ v3 mul(const s3& I, v3 v) { return mk(I.xx * v.x + I.xy * v.y + I.xz * v.z, I.xy * v.x + I.yy * v.y + I.yz * v.z, I.xz * v.x + I.yz * v.y + I.zz * v.z); }
+__device__ __forceinline__ s3 operator+(const s3& a, const s3& b) { s3 r; r.xx = a.xx + b.xx; r.xy = a.xy + b.xy; r.xz = a.xz + b.xz; r.yy = a.yy + b.yy; r.yz = a.yz + b.yz; r.zz = a.zz + b.zz; return r; }
+// R I R^T for a (symmetric) body inertia given row-major 3x3 in constant memory
+__device__ __forceinline__ s3 rotate_inertia(const m3& R, const double* I) {
+  m3 T = mulc(R, I);
+  s3 r;
+  r.xx = T.m[0] * R.m[0] + T.m[1] * R.m[1] + T.m[2] * R.m[2];
+  r.xy = T.m[0] * R.m[3] + T.m[1] * R.m[4] + T.m[2] * R.m[5];
+  r.xz = T.m[0] * R.m[6] + T.m[1] * R.m[7] + T.m[2] * R.m[8];
+  r.yy = T.m[3] * R.m[3] + T.m[4] * R.m[4] + T.m[5] * R.m[5];
+  r.yz = T.m[3] * R.m[6] + T.m[4] * R.m[7] + T.m[5] * R.m[8];
+  r.zz = T.m[6] * R.m[6] + T.m[7] * R.m[7] + T.m[8] * R.m[8];
+  return r;
+}
+// spatial inertia about the world origin: mass, first moment h = m c, inertia about the origin
+struct SI { double M; v3 h; s3 I; };
+__device__ __forceinline__ SI body_si(double m, v3 c, const s3& Ic) {
+  SI s; s.M = m; s.h = m * c;
+  const double cc = dot(c, c);
+  s.I.xx = Ic.xx + m * (cc - c.x * c.x); s.I.xy = Ic.xy - m * c.x * c.y; s.I.xz = Ic.xz - m * c.x * c.z;
+  s.I.yy = Ic.yy + m * (cc - c.y * c.y); s.I.yz = Ic.yz - m * c.y * c.z; s.I.zz = Ic.zz + m * (cc - c.z * c.z);
+  return s;
+}
+__device__ __forceinline__ SI operator+(const SI& a, const SI& b) { SI s; s.M = a.M + b.M; s.h = a.h + b.h; s.I = a.I + b.I; return s; }
+struct Mom { v3 n, p; };   // moment about the world origin, linear momentum
+__device__ __forceinline__ Mom operator+(const Mom& a, const Mom& b) { Mom r; r.n = a.n + b.n; r.p = a.p + b.p; return r; }
+// momentum of a composite body moving with twist (w, vO)
+__device__ __forceinline__ Mom si_apply(const SI& s, v3 w, v3 vO) { Mom r; r.p = s.M * vO + cross(w, s.h); r.n = mul(s.I, w) + cross(s.h, vO); return r; }
+
+__device__ __forceinline__ m3 rodrigues(const double* a, double ang) {
+  double s, c; sincos(ang, &s, &c);
+  const double t = 1.0 - c;
+  m3 r;
+  r.m[0] = c + t * a[0] * a[0]; r.m[1] = t * a[0] * a[1] - s * a[2]; r.m[2] = t * a[0] * a[2] + s * a[1];
+  r.m[3] = t * a[0] * a[1] + s * a[2]; r.m[4] = c + t * a[1] * a[1]; r.m[5] = t * a[1] * a[2] - s * a[0];
+  r.m[6] = t * a[0] * a[2] - s * a[1]; r.m[7] = t * a[1] * a[2] + s * a[0]; r.m[8] = c + t * a[2] * a[2];
+  return r;
+}
+__device__ __forceinline__ void inv3(const double* a, double* r) {
+  const double c00 = a[4] * a[8] - a[5] * a[7], c01 = a[5] * a[6] - a[3] * a[8], c02 = a[3] * a[7] - a[4] * a[6];
+  const double id = 1.0 / (a[0] * c00 + a[1] * c01 + a[2] * c02);
+  r[0] = c00 * id; r[1] = (a[2] * a[7] - a[1] * a[8]) * id; r[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+  r[3] = c01 * id; r[4] = (a[0] * a[8] - a[2] * a[6]) * id; r[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+  r[6] = c02 * id; r[7] = (a[1] * a[6] - a[0] * a[7]) * id; r[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+}
+
+// gait/MotionPhaseDefinition.h:57-76 : mode -> leg in stance (both sole points of a foot share the flag)
+__device__ __forceinline__ bool leg_in_stance(int mode, int leg) { return leg == 0 ? (mode == 1 || mode == 3) : (mode == 2 || mode == 3); }
+
+template <int NJ>
+struct Dims {
+  static constexpr int NX = 12 + NJ, NU = 12 + NJ, NXA = NX - 3, NL = NJ / 2;
+  // compact LQ record produced by the LQ kernel (doubles)
+  static constexpr int R_B = 0, R_AD = R_B + NX, R_BD = R_AD + 9 * NXA, R_Q = R_BD + 9 * NU, R_R = R_Q + NX, R_HB = R_R + NU,
+                       R_CV = R_HB + 24, R_DV = R_CV + 10 * NXA, R_EV = R_DV + 10 * NJ, R_MISC = R_EV + 10, R_FO = R_MISC + 12,
+                       REC = ((R_FO + 12 + 3) / 4) * 4;
+  // misc slots
+  static constexpr int M_DT = 0, M_DQ = 1, M_DR = 2, M_MODE = 3, M_NROWS = 4, M_TYPE = 5, M_PCOST = 6, M_PDYN = 7, M_PEQ = 8;
+  // projection record: Pxj[NJ][NXA], Pej[NJ], N[NJ][8], meta (mj, rank_flag)
+  static constexpr int P_PX = 0, P_PE = P_PX + NJ * NXA, P_N = P_PE + NJ, P_META = P_N + NJ * 8, PREC = ((P_META + 2 + 3) / 4) * 4;
+  // Riccati record per stage: K[NU][NX], kappa[NU], Phi[NX][NX], phi[NX], ghat[NX], misc(2)
+  static constexpr int K_K = 0, K_KAP = K_K + NU * NX, K_PHI = K_KAP + NU, K_SPHI = K_PHI + NX * NX, K_G = K_SPHI + NX, K_MISC = K_G + NX,
+                       KREC = ((K_MISC + 2 + 3) / 4) * 4;
+};
+
+// map a state index (0..NX-1, not 6..8) to its column in the "active x" set X = {0..5, 9..NX-1}
+__device__ __forceinline__ int xcol(int s) { return s < 6 ? s : s - 3; }
+
+// Result of one evaluation of the continuous-time model at (x, u).
+template <int NJ>
+struct ModelEval {
+  static constexpr int NX = Dims<NJ>::NX, NXA = Dims<NJ>::NXA;
+  double f[NX];
+  double Ac[9][NXA];   // rows 3..11 of df/dx, active columns
+  double Bf[3][12];    // rows 3..5 of df/dF
+  double Bj[6][NJ];    // rows 6..11 of df/dqd_j
+  v3 pc[NCON], vc[NCON];
+};
+template <int NJ>
+struct ContactJac {
+  static constexpr int NXA = Dims<NJ>::NXA;
+  double Jx[NCON][3][NXA];   // d v_i / d x (active columns)
+  double Ju[NCON][3][NJ];    // d v_i / d qd_j
+};
+
+// LEVEL 0: values only (flow map, contact positions / velocities);  LEVEL 1: + dynamics Jacobians;  LEVEL 2: + contact Jacobians
+template <int NJ, int LEVEL>
+__device__ __noinline__ void model_eval(const double* __restrict__ x, const double* __restrict__ u, ModelEval<NJ>& E, ContactJac<NJ>* CJ) {
+  constexpr int NX = Dims<NJ>::NX, NXA = Dims<NJ>::NXA, NL = Dims<NJ>::NL;
+  const DevModel& M = c_model;
+  const double mass = M.total_mass, imass = 1.0 / mass;
+  // ---------------- forward kinematics
+  double sz, cz, sy, cy, sx, cx;
+  sincos(x[9], &sz, &cz); sincos(x[10], &sy, &cy); sincos(x[11], &sx, &cx);
+  m3 Rb;
+  Rb.m[0] = cz * cy; Rb.m[1] = cz * sy * sx - sz * cx; Rb.m[2] = cz * sy * cx + sz * sx;
+  Rb.m[3] = sz * cy; Rb.m[4] = sz * sy * sx + cz * cx; Rb.m[5] = sz * sy * cx - cz * sx;
+  Rb.m[6] = -sy;     Rb.m[7] = cy * sx;                Rb.m[8] = cy * cx;
+  const v3 pb = mk(x[6], x[7], x[8]);
+  v3 bax[3];   // Euler-rate axes in world: e_z, Rz e_y, Rz Ry e_x
+  bax[0] = mk(0.0, 0.0, 1.0); bax[1] = mk(-sz, cz, 0.0); bax[2] = mk(cz * cy, sz * cy, -sy);
+  v3 o[NJ], a[NJ];
+  SI comp_si[NJ];                      // composite spatial inertia of the subtree rooted at joint j
+  v3 cb[NJ]; s3 Icb[NJ];               // body COM / inertia about own COM (world axes)
+  m3 Rtip[2];
+#pragma unroll 1
+  for (int leg = 0; leg < 2; ++leg) {
+    m3 Rp = Rb; v3 pp = pb;
+#pragma unroll 1
+    for (int i = 0; i < NL; ++i) {
+      const int j = leg * NL + i;
+      o[j] = mulc(Rp.m, M.pj[j]) + pp;
+      const m3 Rfix = mulc(Rp, M.Rj[j]);
+      a[j] = mulc(Rfix.m, M.axis[j]);
+      const m3 Rw = mul(Rfix, rodrigues(M.axis[j], x[12 + j]));
+      cb[j] = mulc(Rw.m, M.com[j]) + o[j];
+      Icb[j] = rotate_inertia(Rw, M.inertia[j]);
+      Rp = Rw; pp = o[j];
+    }
+    Rtip[leg] = Rp;
+  }
+#pragma unroll 1
+  for (int c = 0; c < NCON; ++c) E.pc[c] = mulc(Rtip[c / 2].m, M.coff[c]) + o[(c / 2) * NL + NL - 1];
+  const v3 cbase = mulc(Rb.m, M.base_com) + pb;
+  const s3 Ibase = rotate_inertia(Rb, M.base_inertia);
+  // ---------------- composite inertias (leaf -> root)
+#pragma unroll 1
+  for (int leg = 0; leg < 2; ++leg)
+#pragma unroll 1
+    for (int i = NL - 1; i >= 0; --i) {
+      const int j = leg * NL + i;
+      const SI b = body_si(M.mass[j], cb[j], Icb[j]);
+      comp_si[j] = (i == NL - 1) ? b : b + comp_si[j + 1];
+    }
+  const SI tot = body_si(M.base_mass, cbase, Ibase) + comp_si[0] + comp_si[NL];
+  const v3 com = imass * tot.h;
+  // ---------------- centroidal momentum matrix columns (about the COM)
+  v3 Alin_e[3], Aang_e[3], Alin[NJ], Aang[NJ];
+#pragma unroll 1
+  for (int k = 0; k < 3; ++k) { const Mom m = si_apply(tot, bax[k], cross(pb, bax[k])); Alin_e[k] = m.p; Aang_e[k] = m.n - cross(com, m.p); }
+#pragma unroll 1
+  for (int j = 0; j < NJ; ++j) { const Mom m = si_apply(comp_si[j], a[j], cross(o[j], a[j])); Alin[j] = m.p; Aang[j] = m.n - cross(com, m.p); }
+  double A22[9], A22i[9], A12[9];
+#pragma unroll 1
+  for (int k = 0; k < 3; ++k) { A22[k] = Aang_e[k].x; A22[3 + k] = Aang_e[k].y; A22[6 + k] = Aang_e[k].z; A12[k] = Alin_e[k].x; A12[3 + k] = Alin_e[k].y; A12[6 + k] = Alin_e[k].z; }
+  inv3(A22, A22i);
+  // ---------------- generalized velocity  v_b = A_b^-1 (m h - A_j qd)
+  v3 ml = mk(mass * x[0], mass * x[1], mass * x[2]), ma = mk(mass * x[3], mass * x[4], mass * x[5]);
+#pragma unroll 1
+  for (int j = 0; j < NJ; ++j) { const double qd = u[12 + j]; ml = ml - qd * Alin[j]; ma = ma - qd * Aang[j]; }
+  const v3 w = mk(A22i[0] * ma.x + A22i[1] * ma.y + A22i[2] * ma.z, A22i[3] * ma.x + A22i[4] * ma.y + A22i[5] * ma.z, A22i[6] * ma.x + A22i[7] * ma.y + A22i[8] * ma.z);
+  const v3 vlin = imass * (ml - mk(A12[0] * w.x + A12[1] * w.y + A12[2] * w.z, A12[3] * w.x + A12[4] * w.y + A12[5] * w.z, A12[6] * w.x + A12[7] * w.y + A12[8] * w.z));
+  // ---------------- flow map
+  v3 Ftot = mk(0.0, 0.0, 0.0), tau = mk(0.0, 0.0, 0.0);
+#pragma unroll 1
+  for (int c = 0; c < NCON; ++c) { const v3 F = mk(u[3 * c], u[3 * c + 1], u[3 * c + 2]); Ftot = Ftot + F; tau = tau + cross(E.pc[c] - com, F); }
+  E.f[0] = Ftot.x * imass; E.f[1] = Ftot.y * imass; E.f[2] = Ftot.z * imass - 9.81;
+  E.f[3] = tau.x * imass; E.f[4] = tau.y * imass; E.f[5] = tau.z * imass;
+  E.f[6] = vlin.x; E.f[7] = vlin.y; E.f[8] = vlin.z; E.f[9] = w.x; E.f[10] = w.y; E.f[11] = w.z;
+#pragma unroll 1
+  for (int j = 0; j < NJ; ++j) E.f[12 + j] = u[12 + j];
+  // ---------------- link twists (world origin referenced)
+  const double wr[3] = {w.x, w.y, w.z};
+  v3 we[4], ve[4];   // twist after the translation joints and after each Euler joint
+  we[0] = mk(0.0, 0.0, 0.0); ve[0] = vlin;
+#pragma unroll 1
+  for (int k = 0; k < 3; ++k) { we[k + 1] = we[k] + wr[k] * bax[k]; ve[k + 1] = ve[k] + wr[k] * cross(pb, bax[k]); }
+  v3 wj[NJ], vj[NJ];
+#pragma unroll 1
+  for (int leg = 0; leg < 2; ++leg) {
+    v3 wp = we[3], vp = ve[3];
+#pragma unroll 1
+    for (int i = 0; i < NL; ++i) { const int j = leg * NL + i; const double qd = u[12 + j]; wj[j] = wp + qd * a[j]; vj[j] = vp + qd * cross(o[j], a[j]); wp = wj[j]; vp = vj[j]; }
+  }
+#pragma unroll 1
+  for (int c = 0; c < NCON; ++c) { const int tip = (c / 2) * NL + NL - 1; E.vc[c] = cross(wj[tip], E.pc[c]) + vj[tip]; }
+  if (LEVEL == 0) return;
+
+  // ---------------- dynamics Jacobians
+#pragma unroll 1
+  for (int r = 0; r < 9; ++r)
+#pragma unroll 1
+    for (int c = 0; c < NXA; ++c) E.Ac[r][c] = 0.0;
+  double A12A22i[9];
+#pragma unroll 1
+  for (int r = 0; r < 3; ++r)
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) A12A22i[3 * r + c] = A12[3 * r] * A22i[c] + A12[3 * r + 1] * A22i[3 + c] + A12[3 * r + 2] * A22i[6 + c];
+  // d v_b / d h = m A_b^-1 = [I, -A12 A22^-1 ; 0, m A22^-1]
+#pragma unroll 1
+  for (int r = 0; r < 3; ++r) {
+    E.Ac[3 + r][r] = 1.0;
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) { E.Ac[3 + r][3 + c] = -A12A22i[3 * r + c]; E.Ac[6 + r][3 + c] = mass * A22i[3 * r + c]; }
+  }
+  // B: d f / d F_i (rows 3..5) = skew(p_i - c)/m ; d f / d qd_j (rows 6..11) = -A_b^-1 A_j
+#pragma unroll 1
+  for (int c = 0; c < NCON; ++c) {
+    const v3 r = imass * (E.pc[c] - com);
+    E.Bf[0][3 * c] = 0.0;  E.Bf[0][3 * c + 1] = -r.z; E.Bf[0][3 * c + 2] = r.y;
+    E.Bf[1][3 * c] = r.z;  E.Bf[1][3 * c + 1] = 0.0;  E.Bf[1][3 * c + 2] = -r.x;
+    E.Bf[2][3 * c] = -r.y; E.Bf[2][3 * c + 1] = r.x;  E.Bf[2][3 * c + 2] = 0.0;
+  }
+#pragma unroll 1
+  for (int j = 0; j < NJ; ++j) {
+    const v3 n = Aang[j], p = Alin[j];
+    const v3 e = mk(A22i[0] * n.x + A22i[1] * n.y + A22i[2] * n.z, A22i[3] * n.x + A22i[4] * n.y + A22i[5] * n.z, A22i[6] * n.x + A22i[7] * n.y + A22i[8] * n.z);
+    const v3 l = imass * (p - mk(A12[0] * e.x + A12[1] * e.y + A12[2] * e.z, A12[3] * e.x + A12[4] * e.y + A12[5] * e.z, A12[6] * e.x + A12[7] * e.y + A12[8] * e.z));
+    E.Bj[0][j] = -l.x; E.Bj[1][j] = -l.y; E.Bj[2][j] = -l.z; E.Bj[3][j] = -e.x; E.Bj[4][j] = -e.y; E.Bj[5][j] = -e.z;
+  }
+  // subtree momenta
+  Mom hs[NJ];
+#pragma unroll 1
+  for (int leg = 0; leg < 2; ++leg)
+#pragma unroll 1
+    for (int i = NL - 1; i >= 0; --i) {
+      const int j = leg * NL + i;
+      Mom b; b.p = M.mass[j] * (vj[j] + cross(wj[j], cb[j])); b.n = mul(Icb[j], wj[j]) + cross(cb[j], b.p);
+      hs[j] = (i == NL - 1) ? b : b + hs[j + 1];
+    }
+  Mom htot;
+  { Mom b; b.p = M.base_mass * (ve[3] + cross(we[3], cbase)); b.n = mul(Ibase, we[3]) + cross(cbase, b.p); htot = b + hs[0] + hs[NL]; }
+  // one column of d f / d q_k for a revolute "joint" (axis ak, origin ok, subtree inertia/momentum, parent twist)
+  auto dq_column = [&](int col, v3 ak, v3 ok, const SI& sub, const Mom& hsub, v3 wp, v3 vp, v3 AlinK, int leg_first, int leg_last) {
+    const v3 s = cross(ok, ak);
+    const v3 mom1 = cross(ak, hsub.n) + cross(s, hsub.p);
+    const v3 frc1 = cross(ak, hsub.p);
+    const v3 w1 = cross(ak, wp);
+    const v3 v1 = cross(ak, vp) + cross(s, wp);
+    const Mom m2 = si_apply(sub, w1, v1);
+    const v3 dlin = frc1 - m2.p;
+    const v3 dnO = mom1 - m2.n;
+    const v3 dcom = imass * AlinK;
+    const v3 dang = dnO - cross(dcom, htot.p) - cross(com, dlin);
+    const v3 e = mk(A22i[0] * dang.x + A22i[1] * dang.y + A22i[2] * dang.z, A22i[3] * dang.x + A22i[4] * dang.y + A22i[5] * dang.z, A22i[6] * dang.x + A22i[7] * dang.y + A22i[8] * dang.z);
+    const v3 l = imass * (dlin - mk(A12[0] * e.x + A12[1] * e.y + A12[2] * e.z, A12[3] * e.x + A12[4] * e.y + A12[5] * e.z, A12[6] * e.x + A12[7] * e.y + A12[8] * e.z));
+    E.Ac[3][col] = -l.x; E.Ac[4][col] = -l.y; E.Ac[5][col] = -l.z; E.Ac[6][col] = -e.x; E.Ac[7][col] = -e.y; E.Ac[8][col] = -e.z;
+    // rows 3..5: (1/m) [ sum_{contacts moved by k} (ak x (p_i - ok)) x F_i  -  dcom x Ftot ]
+    v3 t = mk(0.0, 0.0, 0.0);
+#pragma unroll 1
+    for (int c = 0; c < NCON; ++c)
+      if (c / 2 >= leg_first && c / 2 <= leg_last) t = t + cross(cross(ak, E.pc[c] - ok), mk(u[3 * c], u[3 * c + 1], u[3 * c + 2]));
+    t = imass * (t - cross(dcom, Ftot));
+    E.Ac[0][col] = t.x; E.Ac[1][col] = t.y; E.Ac[2][col] = t.z;
+  };
+#pragma unroll 1
+  for (int k = 0; k < 3; ++k) dq_column(6 + k, bax[k], pb, tot, htot, we[k], ve[k], Alin_e[k], 0, 1);
+#pragma unroll 1
+  for (int leg = 0; leg < 2; ++leg)
+#pragma unroll 1
+    for (int i = 0; i < NL; ++i) {
+      const int j = leg * NL + i;
+      const v3 wp = (i == 0) ? we[3] : wj[j - 1];
+      const v3 vp = (i == 0) ? ve[3] : vj[j - 1];
+      dq_column(9 + j, a[j], o[j], comp_si[j], hs[j], wp, vp, Alin[j], leg, leg);
+    }
+  if (LEVEL == 1) return;
+
+  // ---------------- contact velocity Jacobians
+#pragma unroll 1
+  for (int c = 0; c < NCON; ++c) {
+    const int leg = c / 2;
+    const v3 p = E.pc[c], vcp = E.vc[c];
+    v3 Jb[3];   // base Euler columns of the geometric Jacobian (translation columns are identity)
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) Jb[k] = cross(bax[k], p - pb);
+    // chain rule through v_b(x,u): rows 6..11 of df/dx and df/du
+#pragma unroll 1
+    for (int col = 0; col < NXA; ++col) {
+      const v3 t = mk(E.Ac[3][col], E.Ac[4][col], E.Ac[5][col]) + E.Ac[6][col] * Jb[0] + E.Ac[7][col] * Jb[1] + E.Ac[8][col] * Jb[2];
+      CJ->Jx[c][0][col] = t.x; CJ->Jx[c][1][col] = t.y; CJ->Jx[c][2][col] = t.z;
+    }
+#pragma unroll 1
+    for (int j = 0; j < NJ; ++j) {
+      v3 t = mk(E.Bj[0][j], E.Bj[1][j], E.Bj[2][j]) + E.Bj[3][j] * Jb[0] + E.Bj[4][j] * Jb[1] + E.Bj[5][j] * Jb[2];
+      if (j / NL == leg) t = t + cross(a[j], p - o[j]);
+      CJ->Ju[c][0][j] = t.x; CJ->Ju[c][1][j] = t.y; CJ->Ju[c][2][j] = t.z;
+    }
+    // direct dependence on the configuration at fixed generalized velocity
+    auto direct = [&](int col, v3 ak, v3 ok, v3 wk, v3 vk) {
+      const v3 uw = vcp - (cross(wk, p) + vk);
+      const v3 t = cross(ak, uw) + cross(wk, cross(ak, p - ok));
+      CJ->Jx[c][0][col] += t.x; CJ->Jx[c][1][col] += t.y; CJ->Jx[c][2][col] += t.z;
+    };
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) direct(6 + k, bax[k], pb, we[k + 1], ve[k + 1]);
+#pragma unroll 1
+    for (int i = 0; i < NL; ++i) { const int j = leg * NL + i; direct(9 + j, a[j], o[j], wj[j], vj[j]); }
+  }
+}
+
+// relaxed log barrier [UPSTREAM RelaxedBarrierPenalty], settings task.info:280-287
+__device__ __forceinline__ void barrier_penalty(double h, double& p, double& dp, double& ddp) {
+  const double mu = c_model.bar_mu, de = c_model.bar_delta;
+  if (h > de) { p = -mu * log(h); dp = -mu / h; ddp = mu / (h * h); }
+  else { const double dh = (h - 2.0 * de) / de; p = mu * (-log(de) + 0.5 * dh * dh - 0.5); dp = mu * (h - 2.0 * de) / (de * de); ddp = mu / (de * de); }
+}
+// friction cone value (constraint/FrictionConeConstraint.cpp:160-166)
+__device__ __forceinline__ double friction_cone(double fx, double fy, double fz) {
+  return c_model.mu_f * (fz + c_model.fr_grip) - sqrt(fx * fx + fy * fy + c_model.fr_reg);
+}
+
+// stage cost value (tracking + soft friction cones), cost/BipedalRobotQuadraticTrackingCost.h:57-63, common/utils.h:63-77
+template <int NJ>
+__device__ double stage_cost_value(int mode, const double* x, const double* u, const double* xref) {
+  constexpr int NX = Dims<NJ>::NX;
+  const DevModel& M = c_model;
+  const bool st0 = leg_in_stance(mode, 0), st1 = leg_in_stance(mode, 1);
+  const int nst = 2 * (int(st0) + int(st1));
+  const double fz = nst > 0 ? M.total_mass * 9.81 / nst : 0.0;
+  double c = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < NX; ++i) { const double d = x[i] - xref[i]; c += 0.5 * M.Qdiag[i] * d * d; }
+#pragma unroll 1
+  for (int k = 0; k < NCON; ++k) {
+    const bool st = (k / 2 == 0) ? st0 : st1;
+    const double dx = u[3 * k], dy = u[3 * k + 1], dz = u[3 * k + 2] - (st ? fz : 0.0);
+    c += 0.5 * (M.Rforce[3 * k] * dx * dx + M.Rforce[3 * k + 1] * dy * dy + M.Rforce[3 * k + 2] * dz * dz);
+    if (st) { double p, dp, ddp; barrier_penalty(friction_cone(u[3 * k], u[3 * k + 1], u[3 * k + 2]), p, dp, ddp); c += p; }
+  }
+#pragma unroll 1
+  for (int i = 0; i < NJ; ++i) {
+    double s = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < NJ; ++j) s += M.Rjoint[i * NJ + j] * u[12 + j];
+    c += 0.5 * u[12 + i] * s;
+  }
+  return c;
+}
+
+}  // namespace bmpc

@@ -1,0 +1,952 @@
+// CUDA kernels of one SQP tick (sm_100a, FP64).  Kernel <-> reference mapping:
+//   k_time_grid / k_node_setup : timeDiscretizationWithEvents, ModeSchedule::modeAtTime, TargetTrajectories::getDesiredState,
+//                                SwingTrajectoryPlanner::getZvelocityConstraint (foot_planner/SwingTrajectoryPlanner.cpp:50-118),
+//                                multiple_shooting::initializeStateInputTrajectories + BipedalRobotInitializer::compute [UPSTREAM / initializer]
+//   k_lq                       : multiple_shooting::setupIntermediateNode / setupEventNode (dynamics RK2 sensitivity, cost, soft friction cone,
+//                                zero-force / zero-velocity / normal-velocity constraints)  -> compact LQ record
+//   k_project                  : LinearAlgebra::luConstraintProjection replacement (Householder QR, min-norm particular solution)
+//   k_riccati                  : changeOfInputVariables + HPIPM backward Riccati + feedback gains (DMMA m8n8k4 tiles in shared memory)
+//   k_forward                  : HPIPM forward substitution, armijoDescentMetric, PerformanceIndex reduction
+//   k_linesearch_eval/k_accept : SqpSolver::computePerformance + FilterLinesearch::acceptStep
+//   k_update / k_policy_fill   : incrementTrajectory + multiple_shooting::toPrimalSolution (LinearController uff, K)
+#pragma once
+#include "bmpc_device.cuh"
+
+namespace bmpc {
+
+constexpr double WEAK_EPS = 1e-6;   // [UPSTREAM] numeric_traits::weakEpsilon
+constexpr int WS_THREADS = 128;     // threads per CTA of the Riccati kernel (one instance per CTA)
+
+// sizes of the Riccati record per stage (kappa, Phi, phi, ghat, misc)
+template <int NJ>
+struct RDims {
+  static constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU;
+  static constexpr int K_KAP = 0, K_PHI = K_KAP + NU, K_SPHI = K_PHI + NX * NX, K_G = K_SPHI + NX, K_MISC = K_G + NX, KREC = ((K_MISC + 2 + 3) / 4) * 4;
+};
+
+struct Dev {
+  int B, NS, ME, TP, npts;
+  double dt_nom, horizon;
+  const double* t0; const double* x0;
+  const double* tgt_t; const double* tgt_x;
+  const int* n_ev; const double* ev_t; const int* ev_mode;
+  int* n_nodes; double* node_t; int* node_ev; double* st_t; double* st_dt; int* st_mode;
+  double* xref; double* zref;
+  const int* p_n; const double* p_t; const double* p_x; const double* p_u;   // previous primal solution (warm start)
+  double* s_x; double* s_u; double* s_uff; double* s_K;                      // new primal solution / linearisation point
+  double* lq; double* proj; double* ric;
+  double* dx; double* du;
+  double* perf_trial; double* perf; double* alpha; double* norms; int* done; int* status; int* counters;
+};
+
+// ------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ int lower_bound_d(const double* a, int n, double t) {  // first index with a[i] >= t
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < t) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+// [UPSTREAM] LinearInterpolation::timeSegment
+__device__ __forceinline__ void time_segment(const double* ta, int n, double t, int& index, double& alpha) {
+  int idx = lower_bound_d(ta, n, t);
+  int iv = (idx == 0 && n > 0 && t == ta[0]) ? 0 : idx - 1;
+  const int last = n - 1;
+  if (iv >= 0) {
+    if (iv < last) {
+      const double len = ta[iv + 1] - ta[iv], till = ta[iv + 1] - t;
+      if (len > 2.0 * 2.220446049250313e-16) { index = iv; alpha = till / len; }
+      else { index = iv; alpha = (till < 0.5 * len) ? 0.0 : 1.0; }
+    } else { index = max(last - 1, 0); alpha = 0.0; }
+  } else { index = 0; alpha = 1.0; }
+}
+__device__ __forceinline__ void interp_vec(const double* ta, const double* data, int n, int dim, double t, double* out) {
+  if (n <= 1) { for (int i = 0; i < dim; ++i) out[i] = data[i]; return; }
+  int idx; double al; time_segment(ta, n, t, idx, al);
+  const double* a = data + (size_t)idx * dim; const double* b = a + dim;
+  for (int i = 0; i < dim; ++i) out[i] = al * a[i] + (1.0 - al) * b[i];
+}
+
+// ------------------------------------------------------------------------------------------------ K0a: time grid
+__global__ void k_time_grid(Dev d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  const double t0 = d.t0[b], tf = t0 + d.horizon, dt = d.dt_nom;
+  const double* ev = d.ev_t + (size_t)b * d.ME; const int ne = d.n_ev[b];
+  double* nt = d.node_t + (size_t)b * d.NS; int* nev = d.node_ev + (size_t)b * d.NS;
+  const double dt_min = 10.0 * WEAK_EPS;
+  int n = 0; bool overflow = false;
+  nt[0] = t0; nev[0] = 0; n = 1;
+  int nextEvent = lower_bound_d(ev, ne, t0);
+  double nextT = t0; int nextE = 0;
+  while (nt[n - 1] < tf) {
+    nextT = nextT + dt; nextE = 0;
+    if (nextEvent < ne && nextT >= ev[nextEvent]) { nextT = ev[nextEvent]; nextE = 1; ++nextEvent; }
+    if (nextT >= tf) { nextT = tf; nextE = 0; }
+    if (nextT > nt[n - 1] + dt_min) { if (n >= d.NS) { overflow = true; break; } nt[n] = nextT; nev[n] = nextE; ++n; }
+    else { nt[n - 1] = nextT; nev[n - 1] = nextE; }
+    if (nextE == 1) { if (n >= d.NS) { overflow = true; break; } nt[n] = nextT; nev[n] = 2; ++n; }
+  }
+  if (overflow) { atomicOr(&d.status[b], 32); nt[n - 1] = tf; nev[n - 1] = 0; }
+  d.n_nodes[b] = n;
+  double* stt = d.st_t + (size_t)b * d.NS; double* std_ = d.st_dt + (size_t)b * d.NS;
+  for (int i = 0; i + 1 < n; ++i) {
+    const double ts = nev[i] == 2 ? nt[i] + WEAK_EPS : nt[i];
+    const double te = nev[i + 1] == 1 ? nt[i + 1] - WEAK_EPS : nt[i + 1];
+    stt[i] = ts; std_[i] = (nev[i] == 1) ? 0.0 : te - ts;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K0b: per-node references + warm start
+// swing height velocity of leg `leg` at time t (foot_planner/SwingTrajectoryPlanner.cpp:50-118, SplineCpg.cpp:38-60, CubicSpline.cpp:38-75)
+__device__ inline double swing_zvel(const double* ev, const int* modes, int ne, int leg, double t, int* status) {
+  const int np = ne + 1;
+  const int p = lower_bound_d(ev, ne, t);
+  int start = -1;
+  for (int ip = p - 1; ip >= 0; --ip) if (leg_in_stance(modes[ip], leg)) { start = ip; break; }
+  int fin = np - 1;
+  for (int ip = p + 1; ip < np; ++ip) if (leg_in_stance(modes[ip], leg)) { fin = ip - 1; break; }
+  if (start < 0 || fin >= np - 1) { atomicOr(status, 4); return 0.0; }
+  const double ts = ev[start], tf = ev[fin];
+  const double scaling = fmin(1.0, (tf - ts) / c_model.swing_time_scale);
+  const double mid_t = 0.5 * (ts + tf), mid_h = scaling * c_model.swing_height;
+  double t_a, p_a, v_a, t_b, p_b, v_b;
+  if (t < mid_t) { t_a = ts; p_a = 0.0; v_a = scaling * c_model.liftoff_vel; t_b = mid_t; p_b = mid_h; v_b = 0.0; }
+  else { t_a = mid_t; p_a = mid_h; v_a = 0.0; t_b = tf; p_b = 0.0; v_b = scaling * c_model.touchdown_vel; }
+  const double dts = t_b - t_a, dp = p_b - p_a, dv = v_b - v_a;
+  const double c1 = v_a * dts, c2 = -(3.0 * v_a + dv) * dts + 3.0 * dp, c3 = (2.0 * v_a + dv) * dts - 2.0 * dp;
+  const double tn = (t - t_a) / dts;
+  return (3.0 * c3 * tn * tn + 2.0 * c2 * tn + c1) / dts;
+}
+
+template <int NJ>
+__global__ void k_node_setup(Dev d) {
+  constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = gid / d.NS, k = gid % d.NS;
+  if (b >= d.B) return;
+  const int n = d.n_nodes[b];
+  if (k >= n) return;
+  const int N = n - 1;
+  const size_t nb = (size_t)b * d.NS;
+  const double* ev = d.ev_t + (size_t)b * d.ME; const int* modes = d.ev_mode + (size_t)b * (d.ME + 1); const int ne = d.n_ev[b];
+  const int* nev = d.node_ev + nb;
+  const double* nt = d.node_t + nb;
+  const double* stt = d.st_t + nb; const double* std_ = d.st_dt + nb;
+  // ---- stage references
+  if (k < N) {
+    int mode = -1;
+    if (nev[k] != 1) {
+      const double t = stt[k];
+      mode = modes[lower_bound_d(ev, ne, t)];
+      interp_vec(d.tgt_t + (size_t)b * d.TP, d.tgt_x + (size_t)b * d.TP * NX, d.npts, NX, t, d.xref + (nb + k) * NX);
+      for (int leg = 0; leg < 2; ++leg)
+        d.zref[(nb + k) * 2 + leg] = leg_in_stance(mode, leg) ? 0.0 : swing_zvel(ev, modes, ne, leg, t, &d.status[b]);
+    }
+    d.st_mode[nb + k] = mode;
+  }
+  // ---- initial guess: [UPSTREAM] multiple_shooting::initializeStateInputTrajectories
+  const int pn = d.p_n ? d.p_n[b] : 0;
+  const double* pt = d.p_t + nb; const double* px = d.p_x + nb * NX; const double* pu = d.p_u + nb * NU;
+  double stateTill = nt[0], inputTill = nt[0];
+  if (pn >= 2) { stateTill = pt[pn - 1]; inputTill = pt[pn - 2]; }
+  auto interval_uses_initializer = [&](int i) {   // interval i = [node i, node i+1]; true also for event nodes (state copied)
+    if (nev[i] == 1) return true;
+    const double ti = stt[i], tn = stt[i] + std_[i];
+    return (ti > inputTill || tn > stateTill);
+  };
+  // state of node k
+  int j = k;
+  while (j > 0 && interval_uses_initializer(j - 1)) --j;
+  double* xo = d.s_x + (nb + k) * NX;
+  if (j == 0) {
+    const double tinit = nev[0] == 2 ? nt[0] + WEAK_EPS : nt[0];
+    if (tinit < stateTill) interp_vec(pt, px, pn, NX, tinit, xo);
+    else for (int i = 0; i < NX; ++i) xo[i] = d.x0[(size_t)b * NX + i];
+  } else {
+    interp_vec(pt, px, pn, NX, stt[j - 1] + std_[j - 1], xo);
+  }
+  // input of stage k
+  if (k < N) {
+    double* uo = d.s_u + (nb + k) * NU;
+    if (nev[k] == 1) { for (int i = 0; i < NU; ++i) uo[i] = 0.0; }
+    else if (interval_uses_initializer(k)) {   // initialization/BipedalRobotInitializer.cpp:56-63 + common/utils.h:63-77
+      const int mode = modes[lower_bound_d(ev, ne, stt[k])];
+      const bool s0 = leg_in_stance(mode, 0), s1 = leg_in_stance(mode, 1);
+      const int ns = 2 * (int(s0) + int(s1));
+      const double fz = ns > 0 ? c_model.total_mass * 9.81 / ns : 0.0;
+      for (int i = 0; i < NU; ++i) uo[i] = 0.0;
+      if (s0) { uo[2] = fz; uo[5] = fz; }
+      if (s1) { uo[8] = fz; uo[11] = fz; }
+    } else interp_vec(pt, pu, pn, NU, stt[k], uo);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K1: LQ approximation, one thread per (instance, stage)
+template <int NJ>
+__global__ void __launch_bounds__(64) k_lq(Dev d) {
+  using D = Dims<NJ>;
+  constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = gid / d.NS, k = gid % d.NS;
+  if (b >= d.B) return;
+  const int N = d.n_nodes[b] - 1;
+  if (k >= N) return;
+  const size_t nb = (size_t)b * d.NS;
+  const double* xg = d.s_x + (nb + k) * NX; const double* ug = d.s_u + (nb + k) * NU; const double* xng = xg + NX;
+  double* rec = d.lq + (nb + k) * D::REC;
+  double x[NX], u[NU];
+#pragma unroll 1
+  for (int i = 0; i < NX; ++i) x[i] = xg[i];
+  if (d.node_ev[nb + k] == 1) {   // [UPSTREAM] setupEventNode: identity jump map, no input
+    double s = 0.0;
+    for (int i = 0; i < NX; ++i) { const double bi = x[i] - xng[i]; rec[D::R_B + i] = bi; s += bi * bi; }
+    rec[D::R_MISC + D::M_TYPE] = 1.0; rec[D::R_MISC + D::M_DT] = 0.0; rec[D::R_MISC + D::M_MODE] = -1.0;
+    rec[D::R_MISC + D::M_PCOST] = 0.0; rec[D::R_MISC + D::M_PDYN] = s; rec[D::R_MISC + D::M_PEQ] = 0.0;
+    return;
+  }
+#pragma unroll 1
+  for (int i = 0; i < NU; ++i) u[i] = ug[i];
+  const double dt = d.st_dt[nb + k];
+  const int mode = d.st_mode[nb + k];
+  const DevModel& M = c_model;
+  // ---- dynamics: Heun / RK2 with sensitivities  [UPSTREAM SensitivityIntegrator RK2]
+  ModelEval<NJ> E1; ContactJac<NJ> CJ;
+  model_eval<NJ, 2>(x, u, E1, &CJ);
+  double x2[NX];
+#pragma unroll 1
+  for (int i = 0; i < NX; ++i) x2[i] = x[i] + dt * E1.f[i];
+  ModelEval<NJ> E2;
+  model_eval<NJ, 1>(x2, u, E2, nullptr);
+  const double hdt = 0.5 * dt, imass = 1.0 / M.total_mass;
+  double pdyn = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < NX; ++i) { const double bi = x[i] + hdt * (E1.f[i] + E2.f[i]) - xng[i]; rec[D::R_B + i] = bi; pdyn += bi * bi; }
+  // (A_d - I) rows 3..11, active columns: dt/2 (A1 + A2 + dt A2 A1); A1 rows that matter: states 3,4,5 (block rows 0..2) and 9,10,11 (block rows 6..8)
+  for (int r = 0; r < 9; ++r)
+    for (int c = 0; c < NXA; ++c) {
+      double s = 0.0;
+#pragma unroll 1
+      for (int t = 0; t < 3; ++t) s += E2.Ac[r][3 + t] * E1.Ac[t][c] + E2.Ac[r][6 + t] * E1.Ac[6 + t][c];
+      rec[D::R_AD + r * NXA + c] = hdt * (E1.Ac[r][c] + E2.Ac[r][c] + dt * s);
+    }
+  // B_d rows 3..11
+  for (int r = 0; r < 9; ++r) {
+    for (int c = 0; c < 12; ++c) {   // force columns
+      const int a = c % 3;
+      double s = E2.Ac[r][a] * imass;
+#pragma unroll 1
+      for (int t = 0; t < 3; ++t) s += E2.Ac[r][3 + t] * E1.Bf[t][c];
+      const double b12 = r < 3 ? (E1.Bf[r][c] + E2.Bf[r][c]) : 0.0;
+      rec[D::R_BD + r * NU + c] = hdt * (b12 + dt * s);
+    }
+    for (int l = 0; l < NJ; ++l) {   // joint-velocity columns
+      double s = E2.Ac[r][9 + l];
+#pragma unroll 1
+      for (int t = 0; t < 3; ++t) s += E2.Ac[r][6 + t] * E1.Bj[3 + t][l];
+      const double b12 = r >= 3 ? (E1.Bj[r - 3][l] + E2.Bj[r - 3][l]) : 0.0;
+      rec[D::R_BD + r * NU + 12 + l] = hdt * (b12 + dt * s);
+    }
+  }
+  // ---- cost (x dt): tracking cost + soft friction cones
+  const double* xr = d.xref + (nb + k) * NX;
+  const bool st0 = leg_in_stance(mode, 0), st1 = leg_in_stance(mode, 1);
+  const int nst = 2 * (int(st0) + int(st1));
+  const double fznom = nst > 0 ? M.total_mass * 9.81 / nst : 0.0;
+  for (int i = 0; i < NX; ++i) rec[D::R_Q + i] = dt * M.Qdiag[i] * (x[i] - xr[i]);
+  double shift = 0.0;
+  for (int c = 0; c < NCON; ++c) {
+    const bool st = (c / 2 == 0) ? st0 : st1;
+    double r3[3] = {M.Rforce[3 * c] * u[3 * c], M.Rforce[3 * c + 1] * u[3 * c + 1], M.Rforce[3 * c + 2] * (u[3 * c + 2] - (st ? fznom : 0.0))};
+    double hb[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (st) {  // constraint/FrictionConeConstraint.cpp:96-166 wrapped by StateInputSoftConstraint + RelaxedBarrierPenalty
+      const double fx = u[3 * c], fy = u[3 * c + 1], fz = u[3 * c + 2];
+      const double ts = fx * fx + fy * fy + M.fr_reg, tn = sqrt(ts), t32 = tn * ts;
+      const double h = M.mu_f * (fz + M.fr_grip) - tn;
+      double p, dp, ddp; barrier_penalty(h, p, dp, ddp);
+      const double g0 = -fx / tn, g1 = -fy / tn, g2 = M.mu_f;
+      const double H00 = -(fy * fy + M.fr_reg) / t32, H01 = fx * fy / t32, H11 = -(fx * fx + M.fr_reg) / t32;
+      r3[0] += dp * g0; r3[1] += dp * g1; r3[2] += dp * g2;
+      hb[0] = ddp * g0 * g0 + dp * H00; hb[1] = ddp * g0 * g1 + dp * H01; hb[2] = ddp * g0 * g2;
+      hb[3] = ddp * g1 * g1 + dp * H11; hb[4] = ddp * g1 * g2; hb[5] = ddp * g2 * g2;
+      shift += -dp * M.fr_shift;   // FrictionConeConstraint.cpp:192-206: whole uu / xx diagonals
+    }
+    for (int a = 0; a < 3; ++a) rec[D::R_R + 3 * c + a] = dt * r3[a];
+    for (int a = 0; a < 6; ++a) rec[D::R_HB + 6 * c + a] = dt * hb[a];
+    for (int a = 0; a < 3; ++a) rec[D::R_FO + 3 * c + a] = u[3 * c + a];
+  }
+  for (int i = 0; i < NJ; ++i) {
+    double s = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < NJ; ++j) s += M.Rjoint[i * NJ + j] * u[12 + j];
+    rec[D::R_R + 12 + i] = dt * s;
+  }
+  const double pcost = dt * stage_cost_value<NJ>(mode, x, u, xr);
+  // ---- equality constraints on the contact velocities (rows compressed per foot: the two sole points of a stance foot give
+  //      6 rows of rank 5; the sum / difference rotation below is orthogonal, the dropped row has an identically zero D part,
+  //      so the Moore-Penrose solution is unchanged)
+  int nrows = 0; double peq = 0.0;
+  const double is2 = 0.7071067811865476;
+  for (int leg = 0; leg < 2; ++leg) {
+    const int ca = 2 * leg, cb = 2 * leg + 1;
+    const bool st = leg == 0 ? st0 : st1;
+    if (st) {
+      const v3 va = E1.vc[ca], vb = E1.vc[cb];
+      peq += dot(va, va) + dot(vb, vb);
+      for (int i = 0; i < 3; ++i) {   // sum rows
+        double* Cr = rec + D::R_CV + (nrows + i) * NXA; double* Dr = rec + D::R_DV + (nrows + i) * NJ;
+        for (int c = 0; c < NXA; ++c) Cr[c] = is2 * (CJ.Jx[ca][i][c] + CJ.Jx[cb][i][c]);
+        for (int c = 0; c < NJ; ++c) Dr[c] = is2 * (CJ.Ju[ca][i][c] + CJ.Ju[cb][i][c]);
+        rec[D::R_EV + nrows + i] = is2 * (comp(va, i) + comp(vb, i));
+      }
+      nrows += 3;
+      v3 r = E1.pc[ca] - E1.pc[cb];
+      r = (1.0 / sqrt(dot(r, r))) * r;
+      const double ax = fabs(r.x), ay = fabs(r.y), az = fabs(r.z);
+      const v3 e = (ax <= ay && ax <= az) ? mk(1.0, 0.0, 0.0) : ((ay <= az) ? mk(0.0, 1.0, 0.0) : mk(0.0, 0.0, 1.0));
+      v3 n1 = cross(r, e); n1 = (1.0 / sqrt(dot(n1, n1))) * n1;
+      const v3 n2 = cross(r, n1);
+      for (int t = 0; t < 2; ++t) {   // difference rows projected on the plane normal to the foot axis
+        const v3 nn = t == 0 ? n1 : n2;
+        double* Cr = rec + D::R_CV + (nrows + t) * NXA; double* Dr = rec + D::R_DV + (nrows + t) * NJ;
+        for (int c = 0; c < NXA; ++c) Cr[c] = is2 * (nn.x * (CJ.Jx[ca][0][c] - CJ.Jx[cb][0][c]) + nn.y * (CJ.Jx[ca][1][c] - CJ.Jx[cb][1][c]) + nn.z * (CJ.Jx[ca][2][c] - CJ.Jx[cb][2][c]));
+        for (int c = 0; c < NJ; ++c) Dr[c] = is2 * (nn.x * (CJ.Ju[ca][0][c] - CJ.Ju[cb][0][c]) + nn.y * (CJ.Ju[ca][1][c] - CJ.Ju[cb][1][c]) + nn.z * (CJ.Ju[ca][2][c] - CJ.Ju[cb][2][c]));
+        rec[D::R_EV + nrows + t] = is2 * dot(nn, va - vb);
+      }
+      nrows += 2;
+    } else {
+      const double zr = d.zref[(nb + k) * 2 + leg];
+      for (int t = 0; t < 2; ++t) {   // normal velocity rows (NormalVelocityConstraintCppAd.cpp:59-84, BipedalRobotPreComputation.cpp:71-80)
+        const int c0 = t == 0 ? ca : cb;
+        double* Cr = rec + D::R_CV + nrows * NXA; double* Dr = rec + D::R_DV + nrows * NJ;
+        for (int c = 0; c < NXA; ++c) Cr[c] = CJ.Jx[c0][2][c];
+        for (int c = 0; c < NJ; ++c) Dr[c] = CJ.Ju[c0][2][c];
+        const double ev = E1.vc[c0].z - zr;
+        rec[D::R_EV + nrows] = ev;
+        peq += ev * ev + u[3 * c0] * u[3 * c0] + u[3 * c0 + 1] * u[3 * c0 + 1] + u[3 * c0 + 2] * u[3 * c0 + 2];   // + zero-force rows
+        ++nrows;
+      }
+    }
+  }
+  double* misc = rec + D::R_MISC;
+  misc[D::M_DT] = dt; misc[D::M_DQ] = dt * shift; misc[D::M_DR] = dt * shift; misc[D::M_MODE] = (double)mode; misc[D::M_NROWS] = (double)nrows;
+  misc[D::M_TYPE] = 0.0; misc[D::M_PCOST] = pcost; misc[D::M_PDYN] = dt * pdyn; misc[D::M_PEQ] = dt * peq;
+}
+
+// ------------------------------------------------------------------------------------------------ K1.5: constraint projection, one warp per (instance, stage)
+// Dv (r x NJ, full row rank after the per-foot compression) -> Householder QR of Dv^T = Q [R; 0]:
+//   Dv^+ = Q1 R^-T  (Moore-Penrose),  null(Dv) = span(Q2).   Outputs Pxj = -Dv^+ Cv, Pej = -Dv^+ ev, N = Q2.
+template <int NJ>
+__global__ void __launch_bounds__(128) k_project(Dev d) {
+  using D = Dims<NJ>;
+  constexpr int NXA = D::NXA;
+  constexpr int WPB = 4;
+  __shared__ double sM[WPB][NJ][12];     // Dv^T  (NJ x r), r <= 10
+  __shared__ double sV[WPB][10][NJ];     // Householder vectors (zero padded)
+  __shared__ double sBeta[WPB][10];
+  __shared__ double sG[WPB][10][NXA + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * WPB + warp;
+  const int b = gw / d.NS, k = gw % d.NS;
+  if (b >= d.B) return;
+  const int N = d.n_nodes[b] - 1;
+  if (k >= N) return;
+  const size_t nb = (size_t)b * d.NS;
+  if (d.node_ev[nb + k] == 1) return;
+  const double* rec = d.lq + (nb + k) * D::REC;
+  double* out = d.proj + (nb + k) * D::PREC;
+  const int r = (int)rec[D::R_MISC + D::M_NROWS];
+  double (*Mt)[12] = sM[warp]; double (*V)[NJ] = sV[warp]; double* beta = sBeta[warp]; double (*G)[NXA + 1] = sG[warp];
+  for (int i = lane; i < r * NJ; i += 32) { const int row = i / NJ, col = i % NJ; Mt[col][row] = rec[D::R_DV + i]; }
+  for (int i = lane; i < r * NXA; i += 32) { const int row = i / NXA, col = i % NXA; G[row][col] = rec[D::R_CV + i]; }
+  for (int i = lane; i < r; i += 32) G[i][NXA] = rec[D::R_EV + i];
+  for (int i = lane; i < 10 * NJ; i += 32) V[i / NJ][i % NJ] = 0.0;
+  __syncwarp();
+  bool anomaly = false;
+  double rmax = 0.0;
+  for (int kk = 0; kk < r; ++kk) {
+    // all lanes compute the reflector of column kk redundantly (identical arithmetic)
+    double nrm2 = 0.0;
+    for (int i = kk; i < NJ; ++i) nrm2 += Mt[i][kk] * Mt[i][kk];
+    const double x0 = Mt[kk][kk];
+    const double nrm = sqrt(nrm2);
+    const double alpha = x0 >= 0.0 ? -nrm : nrm;
+    const double v0 = x0 - alpha;
+    const double vtv = nrm2 - x0 * x0 + v0 * v0;
+    const double bta = vtv > 0.0 ? 2.0 / vtv : 0.0;
+    rmax = fmax(rmax, nrm);
+    if (!(nrm > 1e-9 * rmax)) anomaly = true;
+    __syncwarp();
+    // lanes kk+1..r-1 update their column
+    if (lane > kk && lane < r) {
+      double s = v0 * Mt[kk][lane];
+      for (int i = kk + 1; i < NJ; ++i) s += Mt[i][kk] * Mt[i][lane];
+      s *= bta;
+      Mt[kk][lane] -= s * v0;
+      for (int i = kk + 1; i < NJ; ++i) Mt[i][lane] -= s * Mt[i][kk];
+    }
+    __syncwarp();
+    if (lane == 0) {
+      V[kk][kk] = v0; for (int i = kk + 1; i < NJ; ++i) V[kk][i] = Mt[i][kk];
+      beta[kk] = bta; Mt[kk][kk] = alpha;
+    }
+    __syncwarp();
+  }
+  // lanes 0..NXA: right-hand sides (columns of [Cv | ev]); lanes NXA+1 .. NXA+mj: null-space columns
+  const int mj = NJ - r;
+  double y[NJ];
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) y[i] = 0.0;
+  const bool is_rhs = lane <= NXA, is_null = lane > NXA && lane <= NXA + mj;
+  if (is_rhs) {   // z = R^-T g  (R^T lower triangular: R[l][i] = Mt[l][i] for l <= i)
+    for (int i = 0; i < r; ++i) {
+      double s = G[i][lane];
+      for (int l = 0; l < i; ++l) s -= Mt[l][i] * y[l];
+      y[i] = s / Mt[i][i];
+    }
+  } else if (is_null) {
+    const int t = lane - NXA - 1;
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) if (i == r + t) y[i] = 1.0;
+  }
+  if (is_rhs || is_null) {
+    for (int kk = r - 1; kk >= 0; --kk) {   // y <- H_kk y
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) s += V[kk][i] * y[i];
+      s *= beta[kk];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) y[i] -= s * V[kk][i];
+    }
+    if (is_rhs) {
+      if (lane < NXA) { for (int i = 0; i < NJ; ++i) out[D::P_PX + i * NXA + lane] = -y[i]; }
+      else { for (int i = 0; i < NJ; ++i) out[D::P_PE + i] = -y[i]; }
+    } else {
+      const int t = lane - NXA - 1;
+      for (int i = 0; i < NJ; ++i) out[D::P_N + i * 8 + t] = y[i];
+    }
+  }
+  if (lane == 0) { out[D::P_META] = (double)mj; out[D::P_META + 1] = anomaly ? 1.0 : 0.0; if (anomaly) atomicOr(&d.status[b], 2); }
+}
+
+// ------------------------------------------------------------------------------------------------ DMMA tile GEMM in shared memory
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// C[8MT x 8NT] = (ACC ? C : 0) + op(A) op(B), K = 4 KT.  TA: A is given transposed (As[k][m]); TB: B is given transposed (Bs[n][k]).
+// Output tiles are distributed round-robin over the NW warps of the CTA.  All leading dimensions are == 4 or 12 (mod 16) doubles,
+// which makes every fragment load bank-conflict free.
+template <int MT, int NT, int KT, bool TA, bool TB, bool ACC, int NW>
+__device__ __forceinline__ void gemm_tiles(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, double* __restrict__ C, int ldc, int warp, int lane) {
+  const int lr = lane >> 2, lc = lane & 3;
+  for (int t = warp; t < MT * NT; t += NW) {
+    const int mt = t / NT, nt = t % NT;
+    double c0 = 0.0, c1 = 0.0;
+    double* cp = C + (8 * mt + lr) * ldc + 8 * nt + 2 * lc;
+    if (ACC) { c0 = cp[0]; c1 = cp[1]; }
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
+      const double a = TA ? A[(4 * kk + lc) * lda + 8 * mt + lr] : A[(8 * mt + lr) * lda + 4 * kk + lc];
+      const double bb = TB ? B[(8 * nt + lr) * ldb + 4 * kk + lc] : B[(4 * kk + lc) * ldb + 8 * nt + lr];
+      dmma884(c0, c1, a, bb);
+    }
+    cp[0] = c0; cp[1] = c1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K2: change of input variables + backward Riccati
+// One CTA (4 warps) per instance; all matrices of the recursion live in shared memory, padded to NXP = 24 states / MP = 16 reduced inputs.
+template <int NJ>
+struct RicSmem {
+  static constexpr int NXP = 24, MP = 16, LD = 28, LDM = 20;
+  double S[NXP * LD], At[NXP * LD], SA[NXP * LD];
+  double Bt[NXP * LDM], SB[NXP * LDM];
+  double H[MP * LD], Kt[MP * LD], G[MP * LDM];
+  double T1[NJ * LD];                 // Rj_eff * Pxj   (NJ x NXA)
+  double rec[Dims<NJ>::REC];
+  double prj[Dims<NJ>::PREC];
+  double s[NXP], sb[NXP], bt[NXP], qt[NXP], snew[NXP], phi[NXP], ghat[NXP];
+  double rt[MP], g[MP], kt[MP], t1[NJ < 16 ? 16 : NJ], linv[MP];
+  double xk[NXP], uk[NXP];
+  int redcol[MP];                      // reduced input -> original input column (forces) or -(1+t) for null-space column t
+};
+
+template <int NJ>
+__global__ void __launch_bounds__(WS_THREADS) k_riccati(Dev d) {
+  using D = Dims<NJ>; using R = RDims<NJ>; using SM = RicSmem<NJ>;
+  constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, NXP = SM::NXP, MP = SM::MP, LD = SM::LD, LDM = SM::LDM;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SM& sm = *reinterpret_cast<SM*>(smem_raw);
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = d.n_nodes[b] - 1;
+  const size_t nb = (size_t)b * d.NS;
+  const DevModel& M = c_model;
+  const double imass = 1.0 / M.total_mass;
+  // terminal value function: zero (no terminal cost installed)
+  for (int i = tid; i < NXP * LD; i += WS_THREADS) sm.S[i] = 0.0;
+  for (int i = tid; i < NXP; i += WS_THREADS) sm.s[i] = 0.0;
+  __syncthreads();
+  for (int k = N - 1; k >= 0; --k) {
+    const double* recg = d.lq + (nb + k) * D::REC;
+    double* ric = d.ric + (nb + k) * R::KREC;
+    double* Kg = d.s_K + (nb + k) * (size_t)(NU * NX);
+    double* uffg = d.s_uff + (nb + k) * NU;
+    const bool is_event = d.node_ev[nb + k] == 1;
+    if (is_event) {
+      // S unchanged (A = I, Q = 0); s <- s + S b;  K = 0, Phi = I, phi = b
+      for (int i = tid; i < NX; i += WS_THREADS) sm.bt[i] = recg[D::R_B + i];
+      __syncthreads();
+      if (tid < NX) { double a = sm.s[tid]; for (int c = 0; c < NX; ++c) a += sm.S[tid * LD + c] * sm.bt[c]; sm.snew[tid] = a; }
+      __syncthreads();
+      if (tid < NX) { sm.s[tid] = sm.snew[tid]; ric[R::K_SPHI + tid] = sm.bt[tid]; ric[R::K_G + tid] = 0.0; }
+      if (tid == 0) { ric[R::K_MISC] = 0.0; ric[R::K_MISC + 1] = 1.0; }
+      for (int i = tid; i < NU; i += WS_THREADS) { ric[R::K_KAP + i] = 0.0; uffg[i] = 0.0; }
+      for (int i = tid; i < NX * NX; i += WS_THREADS) ric[R::K_PHI + i] = (i / NX == i % NX) ? 1.0 : 0.0;
+      for (int i = tid; i < NU * NX; i += WS_THREADS) Kg[i] = 0.0;
+      __syncthreads();
+      continue;
+    }
+    // ---- phase 0: stage the records
+    const double* prjg = d.proj + (nb + k) * D::PREC;
+    for (int i = tid; i < D::REC; i += WS_THREADS) sm.rec[i] = recg[i];
+    for (int i = tid; i < D::PREC; i += WS_THREADS) sm.prj[i] = prjg[i];
+    for (int i = tid; i < NX; i += WS_THREADS) sm.xk[i] = d.s_x[(nb + k) * NX + i];
+    for (int i = tid; i < NU; i += WS_THREADS) sm.uk[i] = d.s_u[(nb + k) * NU + i];
+    __syncthreads();
+    const double dt = sm.rec[D::R_MISC + D::M_DT], dq = sm.rec[D::R_MISC + D::M_DQ], dr = sm.rec[D::R_MISC + D::M_DR];
+    const int mode = (int)sm.rec[D::R_MISC + D::M_MODE];
+    const int mj = (int)sm.prj[D::P_META];
+    const bool st[2] = {leg_in_stance(mode, 0), leg_in_stance(mode, 1)};
+    const int nclosed = 2 * (int(st[0]) + int(st[1]));
+    const int m = 3 * nclosed + mj;
+    const double* Pxj = sm.prj + D::P_PX; const double* Pej = sm.prj + D::P_PE; const double* Nn = sm.prj + D::P_N;
+    const double* AdI = sm.rec + D::R_AD; const double* Bd = sm.rec + D::R_BD;
+    // ---- phase 1a: T1 = Rj_eff Pxj, t1 = r_j + Rj_eff Pej, reduced-input column map
+    for (int i = tid; i < NJ * NXA; i += WS_THREADS) {
+      const int l = i / NXA, c = i % NXA;
+      double a = dr * Pxj[l * NXA + c];
+      for (int j = 0; j < NJ; ++j) a += dt * M.Rjoint[l * NJ + j] * Pxj[j * NXA + c];
+      sm.T1[l * LD + c] = a;
+    }
+    if (tid < NJ) {
+      double a = sm.rec[D::R_R + 12 + tid] + dr * Pej[tid];
+      for (int j = 0; j < NJ; ++j) a += dt * M.Rjoint[tid * NJ + j] * Pej[j];
+      sm.t1[tid] = a;
+    }
+    if (tid == 0) {
+      int col = 0;
+      for (int c = 0; c < NCON; ++c) if (st[c / 2]) { sm.redcol[col++] = 3 * c; sm.redcol[col++] = 3 * c + 1; sm.redcol[col++] = 3 * c + 2; }
+      for (int t = 0; t < mj; ++t) sm.redcol[col++] = -(1 + t);
+      for (; col < MP; ++col) sm.redcol[col] = 1000;
+    }
+    // zero the padded operand matrices
+    for (int i = tid; i < NXP * LD; i += WS_THREADS) sm.At[i] = 0.0;
+    for (int i = tid; i < NXP * LDM; i += WS_THREADS) sm.Bt[i] = 0.0;
+    for (int i = tid; i < MP * LD; i += WS_THREADS) sm.H[i] = 0.0;
+    for (int i = tid; i < MP * LDM; i += WS_THREADS) sm.G[i] = 0.0;
+    __syncthreads();
+    // ---- phase 1b: At = A_d + B_d Px ; Bt = B_d Pu ; bt = b + B_d Pe ; H <- Pt ; G <- Rt ; rt, qt
+    for (int i = tid; i < NX * NX; i += WS_THREADS) {   // At
+      const int r = i / NX, c = i % NX;
+      double a = (r == c) ? 1.0 : 0.0;
+      if (c < 6 || c >= 9) {
+        const int xc = xcol(c);
+        if (r >= 3 && r < 12) {
+          a += AdI[(r - 3) * NXA + xc];
+          for (int l = 0; l < NJ; ++l) a += Bd[(r - 3) * NU + 12 + l] * Pxj[l * NXA + xc];
+        } else if (r >= 12) a += dt * Pxj[(r - 12) * NXA + xc];
+      }
+      sm.At[r * LD + c] = a;
+    }
+    for (int i = tid; i < NX * MP; i += WS_THREADS) {   // Bt
+      const int r = i / MP, c = i % MP;
+      const int rc = sm.redcol[c];
+      double a = 0.0;
+      if (rc < 1000) {
+        if (rc >= 0) {   // force column rc of B_d: rows 0..2 = dt/m e_a, rows 3..11 stored, rows >= 12 zero
+          if (r < 3) a = (r == rc % 3) ? dt * imass : 0.0;
+          else if (r < 12) a = Bd[(r - 3) * NU + rc];
+        } else {         // null-space column t: B_d[:, joints] N[:, t]
+          const int t = -rc - 1;
+          if (r >= 3 && r < 12) { for (int l = 0; l < NJ; ++l) a += Bd[(r - 3) * NU + 12 + l] * Nn[l * 8 + t]; }
+          else if (r >= 12) a = dt * Nn[(r - 12) * 8 + t];
+        }
+      }
+      sm.Bt[r * LDM + c] = a;
+    }
+    if (tid < NX) {   // bt = b + B_d Pe   (Pe: open-contact forces -F, joints Pej)
+      const int r = tid;
+      double a = sm.rec[D::R_B + r];
+      for (int c = 0; c < NCON; ++c) if (!st[c / 2]) {
+        for (int q = 0; q < 3; ++q) {
+          const double pe = -sm.rec[D::R_FO + 3 * c + q];
+          if (r < 3) { if (r == q) a += dt * imass * pe; }
+          else if (r < 12) a += Bd[(r - 3) * NU + 3 * c + q] * pe;
+        }
+      }
+      if (r >= 3 && r < 12) { for (int l = 0; l < NJ; ++l) a += Bd[(r - 3) * NU + 12 + l] * Pej[l]; }
+      else if (r >= 12) a += dt * Pej[r - 12];
+      sm.bt[r] = a;
+      // qt = q + Pxj^T t1
+      double qv = sm.rec[D::R_Q + r];
+      if (r < 6 || r >= 9) { const int xc = xcol(r); for (int l = 0; l < NJ; ++l) qv += Pxj[l * NXA + xc] * sm.t1[l]; }
+      sm.qt[r] = qv;
+    }
+    if (tid >= 32 && tid < 32 + MP) {   // rt
+      const int c = tid - 32; const int rc = sm.redcol[c];
+      double a = 0.0;
+      if (rc < 1000) { if (rc >= 0) a = sm.rec[D::R_R + rc]; else { const int t = -rc - 1; for (int l = 0; l < NJ; ++l) a += Nn[l * 8 + t] * sm.t1[l]; } }
+      sm.rt[c] = a;
+    }
+    for (int i = tid; i < MP * NX; i += WS_THREADS) {   // H <- Pt = Pu^T R Px : only null-space rows, N^T T1
+      const int r = i / NX, c = i % NX; const int rc = sm.redcol[r];
+      double a = 0.0;
+      if (rc < 0 && (c < 6 || c >= 9)) { const int t = -rc - 1, xc = xcol(c); for (int l = 0; l < NJ; ++l) a += Nn[l * 8 + t] * sm.T1[l * LD + xc]; }
+      sm.H[r * LD + c] = a;
+    }
+    for (int i = tid; i < MP * MP; i += WS_THREADS) {   // G <- Rt = Pu^T R Pu
+      const int r = i / MP, c = i % MP; const int rr = sm.redcol[r], rc = sm.redcol[c];
+      double a = 0.0;
+      if (rr == 1000 || rc == 1000) a = (r == c) ? 1.0 : 0.0;
+      else if (rr >= 0 && rc >= 0) {
+        if (rr / 3 == rc / 3) {   // same contact: diag + barrier block
+          const int cn = rr / 3, p = rr % 3, q = rc % 3;
+          const int lo = p < q ? p : q, hi = p < q ? q : p;
+          const int idx = lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);
+          a = sm.rec[D::R_HB + 6 * cn + idx];
+          if (p == q) a += dt * M.Rforce[rr] + dr;
+        }
+      } else if (rr < 0 && rc < 0) {
+        const int t1i = -rr - 1, t2i = -rc - 1;
+        for (int l = 0; l < NJ; ++l) {
+          double s = dr * Nn[l * 8 + t2i];
+          for (int j = 0; j < NJ; ++j) s += dt * M.Rjoint[l * NJ + j] * Nn[j * 8 + t2i];
+          a += Nn[l * 8 + t1i] * s;
+        }
+      }
+      sm.G[r * LDM + c] = a;
+    }
+    __syncthreads();
+    // ---- phase 2: SA = S At, SB = S Bt, sb = s + S bt
+    gemm_tiles<3, 3, 6, false, false, false, 4>(sm.S, LD, sm.At, LD, sm.SA, LD, warp, lane);
+    gemm_tiles<3, 2, 6, false, false, false, 4>(sm.S, LD, sm.Bt, LDM, sm.SB, LDM, warp, lane);
+    if (tid < NX) { double a = sm.s[tid]; for (int c = 0; c < NX; ++c) a += sm.S[tid * LD + c] * sm.bt[c]; sm.sb[tid] = a; }
+    __syncthreads();
+    // ---- phase 3: H += Bt^T SA, G += Bt^T SB, g = rt + Bt^T sb
+    gemm_tiles<2, 3, 6, true, false, true, 4>(sm.Bt, LDM, sm.SA, LD, sm.H, LD, warp, lane);
+    gemm_tiles<2, 2, 6, true, false, true, 4>(sm.Bt, LDM, sm.SB, LDM, sm.G, LDM, warp, lane);
+    if (tid < MP) { double a = sm.rt[tid]; for (int r = 0; r < NX; ++r) a += sm.Bt[r * LDM + tid] * sm.sb[r]; sm.g[tid] = a; }
+    __syncthreads();
+    // ---- phase 4: Cholesky of G (lower), warp 0
+    if (warp == 0) {
+      for (int j = 0; j < MP; ++j) {
+        double dj = sm.G[j * LDM + j];
+        for (int kk = 0; kk < j; ++kk) dj -= sm.G[j * LDM + kk] * sm.G[j * LDM + kk];
+        if (!(dj > 0.0)) { if (lane == 0) atomicOr(&d.status[b], 1); dj = 1.0; }
+        const double ljj = sqrt(dj), il = 1.0 / ljj;
+        __syncwarp();
+        if (lane > j && lane < MP) { double a = sm.G[lane * LDM + j]; for (int kk = 0; kk < j; ++kk) a -= sm.G[lane * LDM + kk] * sm.G[j * LDM + kk]; sm.G[lane * LDM + j] = a * il; }
+        if (lane == 0) { sm.G[j * LDM + j] = ljj; sm.linv[j] = il; }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // ---- phase 5: Kt = -G^-1 H (one thread per column), kt = -G^-1 g
+    if (tid <= NX) {
+      double y[MP];
+      const bool isg = tid == NX;
+#pragma unroll
+      for (int i = 0; i < MP; ++i) {
+        double a = isg ? sm.g[i] : sm.H[i * LD + tid];
+#pragma unroll
+        for (int l = 0; l < i; ++l) a -= sm.G[i * LDM + l] * y[l];
+        y[i] = a * sm.linv[i];
+      }
+#pragma unroll
+      for (int i = MP - 1; i >= 0; --i) {
+        double a = y[i];
+#pragma unroll
+        for (int l = i + 1; l < MP; ++l) a -= sm.G[l * LDM + i] * y[l];
+        y[i] = a * sm.linv[i];
+      }
+      if (isg) { for (int i = 0; i < MP; ++i) sm.kt[i] = -y[i]; }
+      else { for (int i = 0; i < MP; ++i) sm.Kt[i * LD + tid] = -y[i]; }
+    } else if (tid >= 64) {
+      for (int i = tid - 64; i < MP * 2; i += 64) { sm.Kt[(i >> 1) * LD + NX + (i & 1)] = 0.0; }   // padded columns 22, 23
+    }
+    __syncthreads();
+    // ---- phase 6: S' = Qt + At^T SA + H^T Kt (into S), s' = qt + At^T sb + H^T kt
+    gemm_tiles<3, 3, 6, true, false, false, 4>(sm.At, LD, sm.SA, LD, sm.S, LD, warp, lane);
+    __syncthreads();
+    gemm_tiles<3, 3, 4, true, false, true, 4>(sm.H, LD, sm.Kt, LD, sm.S, LD, warp, lane);
+    if (tid < NX) {
+      double a = sm.qt[tid];
+      for (int r = 0; r < NX; ++r) a += sm.At[r * LD + tid] * sm.sb[r];
+      for (int r = 0; r < MP; ++r) a += sm.H[r * LD + tid] * sm.kt[r];
+      sm.snew[tid] = a;
+      // ghat = qt + Kt^T rt
+      double gh = sm.qt[tid];
+      for (int r = 0; r < MP; ++r) gh += sm.Kt[r * LD + tid] * sm.rt[r];
+      sm.ghat[tid] = gh;
+      // phi = bt + Bt kt
+      double ph = sm.bt[tid];
+      for (int c = 0; c < MP; ++c) ph += sm.Bt[tid * LDM + c] * sm.kt[c];
+      sm.phi[tid] = ph;
+    }
+    __syncthreads();
+    // Phi = At + Bt Kt  (into SA: copy At first, At is then reused as the staging buffer of the symmetrised S')
+    for (int i = tid; i < NXP * LD; i += WS_THREADS) sm.SA[i] = sm.At[i];
+    __syncthreads();
+    gemm_tiles<3, 3, 4, false, false, true, 4>(sm.Bt, LDM, sm.Kt, LD, sm.SA, LD, warp, lane);
+    // add Qt = diag(dt Q + dq) + Pxj^T T1 and symmetrise S' (upper triangle staged in At)
+    for (int i = tid; i < NX * NX; i += WS_THREADS) {
+      const int r = i / NX, c = i % NX;
+      if (c < r) continue;
+      double a = 0.5 * (sm.S[r * LD + c] + sm.S[c * LD + r]);
+      if (r == c) a += dt * M.Qdiag[r] + dq;
+      if ((r < 6 || r >= 9) && (c < 6 || c >= 9)) { const int xr = xcol(r), xc = xcol(c); for (int l = 0; l < NJ; ++l) a += Pxj[l * NXA + xr] * sm.T1[l * LD + xc]; }
+      sm.At[r * LD + c] = a;
+    }
+    __syncthreads();
+    for (int i = tid; i < NX * NX; i += WS_THREADS) { const int r = i / NX, c = i % NX; sm.S[r * LD + c] = (c >= r) ? sm.At[r * LD + c] : sm.At[c * LD + r]; }
+    if (tid < NX) sm.s[tid] = sm.snew[tid];
+    __syncthreads();
+    // ---- phase 7: outputs.  K = Px + Pu Kt, kappa = Pe + Pu kt, uff0 = u - K x
+    for (int i = tid; i < NU * NX; i += WS_THREADS) {
+      const int r = i / NX, c = i % NX;
+      double a = 0.0;
+      if (r < 12) {
+        const int cn = r / 3;
+        if (st[cn / 2]) { int red = 0; for (int q = 0; q < cn; ++q) if (st[q / 2]) red += 3; a = sm.Kt[(red + r % 3) * LD + c]; }
+      } else {
+        const int l = r - 12;
+        if (c < 6 || c >= 9) a = Pxj[l * NXA + xcol(c)];
+        for (int t = 0; t < mj; ++t) a += Nn[l * 8 + t] * sm.Kt[(3 * nclosed + t) * LD + c];
+      }
+      Kg[i] = a;
+    }
+    if (tid < NU) {
+      const int r = tid;
+      double a = 0.0;
+      if (r < 12) {
+        const int cn = r / 3;
+        if (st[cn / 2]) { int red = 0; for (int q = 0; q < cn; ++q) if (st[q / 2]) red += 3; a = sm.kt[red + r % 3]; }
+        else a = -sm.rec[D::R_FO + r];
+      } else {
+        const int l = r - 12;
+        a = Pej[l];
+        for (int t = 0; t < mj; ++t) a += Nn[l * 8 + t] * sm.kt[3 * nclosed + t];
+      }
+      ric[R::K_KAP + r] = a;
+    }
+    for (int i = tid; i < NX * NX; i += WS_THREADS) ric[R::K_PHI + i] = sm.SA[(i / NX) * LD + i % NX];
+    if (tid < NX) { ric[R::K_SPHI + tid] = sm.phi[tid]; ric[R::K_G + tid] = sm.ghat[tid]; }
+    if (tid == 0) { double a = 0.0; for (int r = 0; r < MP; ++r) a += sm.rt[r] * sm.kt[r]; ric[R::K_MISC] = a; ric[R::K_MISC + 1] = 0.0; }
+    __syncthreads();
+    // uff0 = u - K x needs the K just written: recompute the rows from shared memory instead of re-reading global
+    if (tid < NU) {
+      const int r = tid;
+      double a = sm.uk[r];
+      for (int c = 0; c < NX; ++c) {
+        double kv = 0.0;
+        if (r < 12) {
+          const int cn = r / 3;
+          if (st[cn / 2]) { int red = 0; for (int q = 0; q < cn; ++q) if (st[q / 2]) red += 3; kv = sm.Kt[(red + r % 3) * LD + c]; }
+        } else {
+          const int l = r - 12;
+          if (c < 6 || c >= 9) kv = Pxj[l * NXA + xcol(c)];
+          for (int t = 0; t < mj; ++t) kv += Nn[l * 8 + t] * sm.Kt[(3 * nclosed + t) * LD + c];
+        }
+        a -= kv * sm.xk[c];
+      }
+      uffg[r] = a;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K3: forward substitution, one warp per instance
+template <int NJ>
+__global__ void __launch_bounds__(128) k_forward(Dev d) {
+  using D = Dims<NJ>; using R = RDims<NJ>;
+  constexpr int NX = D::NX, NU = D::NU, WPB = 4, LDP = NX + 1;
+  __shared__ double sPhi[WPB][NX * LDP], sK[WPB][NU * LDP], sdx[WPB][NX], sv[WPB][3 * NX + NU];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * WPB + warp;
+  if (b >= d.B) return;
+  const int N = d.n_nodes[b] - 1;
+  const size_t nb = (size_t)b * d.NS;
+  double* Phi = sPhi[warp]; double* Kk = sK[warp]; double* dx = sdx[warp]; double* v = sv[warp];
+  // dx_0 = x0 - x[0]
+  double s0 = 0.0;
+  if (lane < NX) { const double e = d.x0[(size_t)b * NX + lane] - d.s_x[nb * NX + lane]; dx[lane] = e; d.dx[nb * NX + lane] = e; s0 = e * e; }
+  double armijo = 0.0, dxn = s0, dun = 0.0, pc = 0.0, pd = 0.0, pe = 0.0;
+  __syncwarp();
+  for (int k = 0; k < N; ++k) {
+    const double* ric = d.ric + (nb + k) * R::KREC;
+    const double* Kg = d.s_K + (nb + k) * (size_t)(NU * NX);
+    const double* rec = d.lq + (nb + k) * D::REC;
+    for (int i = lane; i < NX * NX; i += 32) Phi[(i / NX) * LDP + i % NX] = ric[R::K_PHI + i];
+    for (int i = lane; i < NU * NX; i += 32) Kk[(i / NX) * LDP + i % NX] = Kg[i];
+    for (int i = lane; i < NX; i += 32) { v[i] = ric[R::K_SPHI + i]; v[NX + i] = ric[R::K_G + i]; }
+    for (int i = lane; i < NU; i += 32) v[2 * NX + i] = ric[R::K_KAP + i];
+    const double misc = ric[R::K_MISC];
+    const bool is_event = ric[R::K_MISC + 1] != 0.0;
+    __syncwarp();
+    double nx_ = 0.0, du_ = 0.0, ga = 0.0;
+    if (lane < NX) {
+      double a = v[lane]; for (int c = 0; c < NX; ++c) a += Phi[lane * LDP + c] * dx[c]; nx_ = a;
+      ga = v[NX + lane] * dx[lane];
+    }
+    if (lane < NU) { double a = v[2 * NX + lane]; for (int c = 0; c < NX; ++c) a += Kk[lane * LDP + c] * dx[c]; du_ = is_event ? 0.0 : a; d.du[(nb + k) * NU + lane] = du_; }
+    __syncwarp();
+    if (lane < NX) { dx[lane] = nx_; d.dx[(nb + k + 1) * NX + lane] = nx_; }
+    armijo += ga + (lane == 0 ? misc : 0.0);
+    dxn += nx_ * nx_; dun += du_ * du_;
+    if (lane == 0) { pc += rec[D::R_MISC + D::M_PCOST]; pd += rec[D::R_MISC + D::M_PDYN]; pe += rec[D::R_MISC + D::M_PEQ]; }
+    __syncwarp();
+  }
+  for (int o = 16; o > 0; o >>= 1) { armijo += __shfl_xor_sync(0xffffffffu, armijo, o); dxn += __shfl_xor_sync(0xffffffffu, dxn, o); dun += __shfl_xor_sync(0xffffffffu, dun, o); s0 += __shfl_xor_sync(0xffffffffu, s0, o); }
+  if (lane == 0) {
+    double* pf = d.perf + (size_t)b * 8;
+    pf[0] = pc; pf[1] = pd + s0; pf[2] = pe; pf[7] = armijo;
+    d.norms[2 * b] = sqrt(dxn); d.norms[2 * b + 1] = sqrt(dun);
+    d.alpha[b] = 1.0; d.done[b] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K4: line-search trial evaluation, one thread per (instance, stage)
+template <int NJ>
+__global__ void __launch_bounds__(64) k_linesearch_eval(Dev d) {
+  using D = Dims<NJ>;
+  constexpr int NX = D::NX, NU = D::NU;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = gid / d.NS, k = gid % d.NS;
+  if (b >= d.B) return;
+  if (d.done[b]) return;
+  const int N = d.n_nodes[b] - 1;
+  if (k >= N) return;
+  const size_t nb = (size_t)b * d.NS;
+  const double al = d.alpha[b];
+  double* out = d.perf_trial + (nb + k) * 3;
+  double x[NX], xn[NX], u[NU];
+  for (int i = 0; i < NX; ++i) { x[i] = d.s_x[(nb + k) * NX + i] + al * d.dx[(nb + k) * NX + i]; xn[i] = d.s_x[(nb + k + 1) * NX + i] + al * d.dx[(nb + k + 1) * NX + i]; }
+  if (d.node_ev[nb + k] == 1) {
+    double s = 0.0; for (int i = 0; i < NX; ++i) { const double e = x[i] - xn[i]; s += e * e; }
+    out[0] = 0.0; out[1] = s; out[2] = 0.0; return;
+  }
+  for (int i = 0; i < NU; ++i) u[i] = d.s_u[(nb + k) * NU + i] + al * d.du[(nb + k) * NU + i];
+  const double dt = d.st_dt[nb + k]; const int mode = d.st_mode[nb + k];
+  ModelEval<NJ> E1;
+  model_eval<NJ, 0>(x, u, E1, nullptr);
+  double x2[NX], k1[NX];
+  for (int i = 0; i < NX; ++i) { k1[i] = E1.f[i]; x2[i] = x[i] + dt * k1[i]; }
+  v3 vc[NCON]; for (int c = 0; c < NCON; ++c) vc[c] = E1.vc[c];
+  model_eval<NJ, 0>(x2, u, E1, nullptr);
+  double s = 0.0;
+  for (int i = 0; i < NX; ++i) { const double e = x[i] + 0.5 * dt * (k1[i] + E1.f[i]) - xn[i]; s += e * e; }
+  double peq = 0.0;
+  for (int leg = 0; leg < 2; ++leg) {
+    const int ca = 2 * leg, cb = 2 * leg + 1;
+    if (leg_in_stance(mode, leg)) peq += dot(vc[ca], vc[ca]) + dot(vc[cb], vc[cb]);
+    else {
+      const double zr = d.zref[(nb + k) * 2 + leg];
+      for (int t = 0; t < 2; ++t) { const int c0 = t == 0 ? ca : cb; const double ev = vc[c0].z - zr; peq += ev * ev + u[3 * c0] * u[3 * c0] + u[3 * c0 + 1] * u[3 * c0 + 1] + u[3 * c0 + 2] * u[3 * c0 + 2]; }
+    }
+  }
+  out[0] = dt * stage_cost_value<NJ>(mode, x, u, d.xref + (nb + k) * NX);
+  out[1] = dt * s; out[2] = dt * peq;
+}
+
+// ------------------------------------------------------------------------------------------------ K5: filter line search acceptance, one warp per instance
+// [UPSTREAM] FilterLinesearch::acceptStep (g_max, g_min: task.info:72-73; gamma_c 1e-6, armijoFactor 1e-4, alpha_decay 0.5, alpha_min 1e-4)
+template <int NJ>
+__global__ void __launch_bounds__(128) k_accept(Dev d) {
+  constexpr int NX = Dims<NJ>::NX;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + warp;
+  if (b >= d.B) return;
+  if (d.done[b]) return;
+  const int N = d.n_nodes[b] - 1;
+  const size_t nb = (size_t)b * d.NS;
+  double pc = 0.0, pd = 0.0, pe = 0.0;
+  for (int k = lane; k < N; k += 32) { const double* p = d.perf_trial + (nb + k) * 3; pc += p[0]; pd += p[1]; pe += p[2]; }
+  const double al = d.alpha[b];
+  if (lane < NX) { const double e = d.x0[(size_t)b * NX + lane] - (d.s_x[nb * NX + lane] + al * d.dx[nb * NX + lane]); pd += e * e; }
+  for (int o = 16; o > 0; o >>= 1) { pc += __shfl_xor_sync(0xffffffffu, pc, o); pd += __shfl_xor_sync(0xffffffffu, pd, o); pe += __shfl_xor_sync(0xffffffffu, pe, o); }
+  if (lane == 0) {
+    double* pf = d.perf + (size_t)b * 8;
+    const double th0 = sqrt(pf[1] + pf[2]), th = sqrt(pd + pe);
+    const double gamma_c = 1e-6, armijoFactor = 1e-4, alpha_decay = 0.5, alpha_min = 1e-4;
+    const double armijo = pf[7];
+    bool acc;
+    if (th > c_model.g_max) acc = th < (1.0 - gamma_c) * th0;
+    else if (th < c_model.g_min && th0 < c_model.g_min && armijo < 0.0) acc = pc < pf[0] + armijoFactor * al * armijo;
+    else acc = (pc < pf[0] - gamma_c * th0) || (th < (1.0 - gamma_c) * th0);
+    if (!(pc == pc) || !(pd == pd) || !(pe == pe)) { acc = false; atomicOr(&d.status[b], 8); }
+    if (acc) { pf[3] = pc; pf[4] = pd; pf[5] = pe; pf[6] = al; d.done[b] = 1; }
+    else {
+      const double an = al * alpha_decay;
+      const bool small = an * d.norms[2 * b] < c_model.delta_tol && an * d.norms[2 * b + 1] < c_model.delta_tol;
+      if (small || an < alpha_min) { pf[3] = pf[0]; pf[4] = pf[1]; pf[5] = pf[2]; pf[6] = 0.0; d.alpha[b] = 0.0; d.done[b] = 1; atomicOr(&d.status[b], 16); }
+      else { d.alpha[b] = an; atomicAdd(&d.counters[0], 1); }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K6: take the step, finish the policy
+template <int NJ>
+__global__ void k_update(Dev d) {
+  using R = RDims<NJ>;
+  constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = gid / d.NS, k = gid % d.NS;
+  if (b >= d.B) return;
+  const int n = d.n_nodes[b];
+  if (k >= n) return;
+  const size_t nb = (size_t)b * d.NS;
+  const double al = d.alpha[b];
+  for (int i = 0; i < NX; ++i) d.s_x[(nb + k) * NX + i] += al * d.dx[(nb + k) * NX + i];
+  if (k < n - 1 && d.node_ev[nb + k] != 1) {
+    const double* kap = d.ric + (nb + k) * R::KREC + R::K_KAP;
+    for (int i = 0; i < NU; ++i) { d.s_u[(nb + k) * NU + i] += al * d.du[(nb + k) * NU + i]; d.s_uff[(nb + k) * NU + i] += al * kap[i]; }
+  }
+}
+// event nodes and the terminal node copy input / feedforward / gain of the previous node ([UPSTREAM] toPrimalSolution)
+template <int NJ>
+__global__ void k_policy_fill(Dev d) {
+  constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU;
+  const int b = blockIdx.x;
+  const int n = d.n_nodes[b];
+  const size_t nb = (size_t)b * d.NS;
+  for (int k = 1; k < n; ++k) {
+    const bool copy = (k == n - 1) || d.node_ev[nb + k] == 1;
+    if (!copy) continue;
+    for (int i = threadIdx.x; i < NU; i += blockDim.x) { d.s_u[(nb + k) * NU + i] = d.s_u[(nb + k - 1) * NU + i]; d.s_uff[(nb + k) * NU + i] = d.s_uff[(nb + k - 1) * NU + i]; }
+    for (int i = threadIdx.x; i < NU * NX; i += blockDim.x) d.s_K[(nb + k) * (size_t)(NU * NX) + i] = d.s_K[(nb + k - 1) * (size_t)(NU * NX) + i];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ batched policy evaluation
+// [UPSTREAM] MPC_MRT_Interface::evaluatePolicy + LinearController::computeInput (linear interpolation of uff and K in time)
+template <int NJ>
+__global__ void k_evaluate_policy(int B, int NS, int ME, const int* n_nodes, const double* times, const double* sx, const double* suff, const double* sK,
+                                  const int* n_ev, const double* ev_t, const int* ev_mode, const double* tq, const double* xq, double* xo, double* uo, int* mo) {
+  constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU;
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  const size_t nb = (size_t)b * NS;
+  const int n = n_nodes[b];
+  int idx; double al; time_segment(times + nb, n, tq[b], idx, al);
+  const int i1 = min(idx + 1, n - 1);
+  for (int i = threadIdx.x; i < NX; i += blockDim.x) xo[(size_t)b * NX + i] = al * sx[(nb + idx) * NX + i] + (1.0 - al) * sx[(nb + i1) * NX + i];
+  for (int r = threadIdx.x; r < NU; r += blockDim.x) {
+    double a = al * suff[(nb + idx) * NU + r] + (1.0 - al) * suff[(nb + i1) * NU + r];
+    const double* K0 = sK + (nb + idx) * (size_t)(NU * NX) + r * NX; const double* K1 = sK + (nb + i1) * (size_t)(NU * NX) + r * NX;
+    for (int c = 0; c < NX; ++c) a += (al * K0[c] + (1.0 - al) * K1[c]) * xq[(size_t)b * NX + c];
+    uo[(size_t)b * NU + r] = a;
+  }
+  if (threadIdx.x == 0) mo[b] = ev_mode[(size_t)b * (ME + 1) + lower_bound_d(ev_t + (size_t)b * ME, n_ev[b], tq[b])];
+}
+
+}  // namespace bmpc

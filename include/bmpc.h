@@ -1,0 +1,149 @@
+/* bmpc.h - C ABI of the B200-native batched bipedal MPC solver (libbmpc.so).
+ *
+ * Drop-in boundary for the hot path of zitongbai/bipedal_control: one multiple-shooting SQP iteration of the
+ * centroidal switched-system OCP that ocs2_bipedal_robot defines (BipedalRobotInterface), for a batch of B
+ * independent instances on one GPU.  Each entry point cites the reference interface it replaces
+ * (paths relative to the reference repository root; [UPSTREAM] = OCS2 class that the reference calls but does
+ * not vendor).  No exceptions cross this ABI: every call returns 0 on success or a negative bmpc_status, and
+ * bmpc_last_error() returns the message.
+ *
+ * Layout conventions: all matrices row-major, double precision.
+ *   state  x[nx]  = [h_lin/m (3), h_ang/m (3), base xyz (3), base ZYX Euler (3), leg joints (nj)]
+ *   input  u[nu]  = [contact forces 4x3 (world), leg joint velocities (nj)]      (task.info:181-277)
+ */
+#ifndef BMPC_H
+#define BMPC_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bmpc_handle bmpc_handle;
+
+enum bmpc_status {
+  BMPC_OK = 0,
+  BMPC_ERR_INVALID = -1,   /* bad argument (reference: std::invalid_argument in BipedalRobotInterface.cpp:71-90) */
+  BMPC_ERR_CUDA = -2,      /* CUDA runtime failure / no device: the library never falls back to the CPU */
+  BMPC_ERR_NUMERIC = -3,   /* at least one instance reported a numerical failure (see bmpc_get_status) */
+  BMPC_ERR_CAPACITY = -4   /* horizon / events exceed the capacities given at creation */
+};
+
+/* per-instance status bits returned by bmpc_get_status */
+enum bmpc_instance_status {
+  BMPC_INST_OK = 0,
+  BMPC_INST_RICCATI_NOT_PD = 1,   /* reduced Hessian lost positive definiteness (HPIPM would fail the QP) */
+  BMPC_INST_RANK_ANOMALY = 2,     /* constraint Jacobian lost rank beyond the structural stance-foot deficiency */
+  BMPC_INST_SWING_UNDEFINED = 4,  /* lift-off / touch-down time undefined (SwingTrajectoryPlanner.cpp:191-212 throws) */
+  BMPC_INST_NAN = 8,
+  BMPC_INST_STEP_REJECTED = 16    /* filter line search reached alpha_min: no step taken (informational) */
+};
+
+/* Construction: replaces `BipedalRobotInterface(taskFile, urdfFile, referenceFile)` +
+ * `std::make_shared<SqpMpc>(mpcSettings, sqpSettings, ocp, initializer)`
+ * (bipedal_controllers/src/BipedalController.cpp:282-306).  Either `model_file` (compact derived numbers written by
+ * tools/ingest.py or bmpc_export_model) or the reference's own task/reference/gait .info + URDF files are given. */
+typedef struct bmpc_config {
+  const char* model_file;
+  const char* task_file;
+  const char* reference_file;
+  const char* gait_file;
+  const char* urdf_file;
+  int batch;               /* number of independent OCP instances B */
+  int device;              /* CUDA device ordinal */
+  double dt;               /* <= 0: sqp.dt of the task file (task.info:69) */
+  double time_horizon;     /* <= 0: mpc.timeHorizon (task.info:171) */
+  int max_events;          /* capacity of each instance's mode schedule (0: default 40) */
+  int max_target_points;   /* capacity of each instance's TargetTrajectories (0: default 4) */
+  int sqp_iterations;      /* <= 0: sqp.sqpIteration (task.info:70) */
+} bmpc_config;
+
+int bmpc_create(const bmpc_config* cfg, bmpc_handle** out);
+void bmpc_destroy(bmpc_handle* h);
+const char* bmpc_last_error(const bmpc_handle* h); /* h may be NULL: error of the last failed bmpc_create */
+
+/* sizes: nx, nu, batch, maximum number of nodes per instance (N+1 including event nodes) */
+int bmpc_get_dims(const bmpc_handle* h, int* nx, int* nu, int* batch, int* max_nodes);
+int bmpc_get_initial_state(const bmpc_handle* h, double* x /* nx */);      /* task.info `initialState` */
+int bmpc_export_model(const bmpc_handle* h, const char* path);             /* writes the compact model file */
+
+/* MPC_MRT_Interface::reset / resetMpcNode (BipedalController.cpp:147-148): drops the warm start of all instances */
+int bmpc_reset(bmpc_handle* h);
+
+/* MPC_MRT_Interface::setCurrentObservation (BipedalController.cpp:191): SystemObservation{time, state} per instance.
+ * t[B], x[B*nx], host memory (copied).  The *_device variants take device pointers (inputs already in HBM). */
+int bmpc_set_observations(bmpc_handle* h, const double* t, const double* x);
+int bmpc_set_observations_device(bmpc_handle* h, const double* t_dev, const double* x_dev);
+
+/* ReferenceManager::setTargetTrajectories [UPSTREAM] (BipedalController.cpp:145,153): npts knots per instance,
+ * times[B*npts], states[B*npts*nx]; the cost interpolates linearly (BipedalRobotQuadraticTrackingCost.h:60). */
+int bmpc_set_target_trajectories(bmpc_handle* h, int npts, const double* times, const double* states);
+int bmpc_set_target_trajectories_device(bmpc_handle* h, int npts, const double* times_dev, const double* states_dev);
+
+/* Batched TargetTrajectoriesPublisher::cmdVelToTargetTrajectories (bipedal_controllers/src/TargetTrajectoriesPublisher.cpp:76-99):
+ * builds the 2-knot targets from the current observations and cmd[B*4] = (vx, vy, vz, yaw rate); host side. */
+int bmpc_set_targets_from_cmd_vel(bmpc_handle* h, const double* cmd, double time_to_target);
+
+/* ReferenceManager::setModeSchedule [UPSTREAM]: explicit ModeSchedule per instance; n_events[B],
+ * event_times[B*stride], mode_sequence[B*(stride+1)] (mode ids: 0 FLY, 1 LF, 2 RF, 3 STANCE;
+ * gait/MotionPhaseDefinition.h:47-52).  Disables the internal GaitSchedule for the next solves. */
+int bmpc_set_mode_schedules(bmpc_handle* h, int stride, const int* n_events, const double* event_times, const int* mode_sequence);
+int bmpc_set_mode_schedules_device(bmpc_handle* h, int stride, const int* n_events_dev, const double* event_times_dev, const int* mode_sequence_dev);
+
+/* GaitSchedule (ocs2_bipedal_robot/src/gait/GaitSchedule.cpp): per-instance gait bookkeeping on the host.
+ * bmpc_gait_insert == GaitSchedule::insertModeSequenceTemplate (GaitSchedule.cpp:46-73; called from
+ * GaitReceiver::preSolverRun, ocs2_bipedal_robot_ros/src/gait/GaitReceiver.cpp:49-59); instance < 0 applies to all.
+ * bmpc_use_gait_schedule(1) makes bmpc_advance derive each instance's ModeSchedule with
+ * GaitSchedule::getModeSchedule(t0 - T, tf + T) as SwitchedModelReferenceManager::modifyReferences does
+ * (SwitchedModelReferenceManager.cpp:62-69). */
+int bmpc_gait_insert(bmpc_handle* h, int instance, int n_modes, const int* modes, const double* switching_times, double start_time, double final_time);
+int bmpc_gait_insert_named(bmpc_handle* h, int instance, const char* gait_name, double start_time, double final_time);
+int bmpc_use_gait_schedule(bmpc_handle* h, int enable);
+int bmpc_gait_peek(const bmpc_handle* h, int instance, int cap, double* event_times, int* mode_sequence); /* returns n_events */
+
+/* MPC_MRT_Interface::advanceMpc -> MPC_BASE::run(t, x) -> SqpSolver::runImpl [UPSTREAM] (BipedalController.cpp:339):
+ * one MPC tick for all B instances: reference update, LQ approximation, projected Riccati QP, filter line search,
+ * feedback policy.  Synchronous; results are available to the getters when it returns. */
+int bmpc_advance(bmpc_handle* h);
+/* same, but only enqueues the work on the library's stream; bmpc_synchronize waits for it */
+int bmpc_advance_async(bmpc_handle* h);
+int bmpc_synchronize(bmpc_handle* h);
+
+/* PrimalSolution [UPSTREAM] of instances [first, first+count): any output pointer may be NULL.
+ * n_nodes[count]; times[count*max_nodes]; events[count*max_nodes] (0 none, 1 pre-event, 2 post-event);
+ * x[count*max_nodes*nx]; u[count*max_nodes*nu]; uff[count*max_nodes*nu]; K[count*max_nodes*nu*nx]
+ * (LinearController: u = uff + K x).  Host memory. */
+int bmpc_get_policy(bmpc_handle* h, int first, int count, int* n_nodes, double* times, int* events, double* x, double* u, double* uff, double* K);
+
+/* device pointers of the current policy buffers (valid until the next bmpc_advance*): for the multi-GPU all-gather */
+typedef struct bmpc_device_view {
+  const int* n_nodes; const double* times; const int* events;
+  const double* x; const double* u; const double* uff; const double* K;
+  int max_nodes, nx, nu, batch;
+} bmpc_device_view;
+int bmpc_get_device_view(bmpc_handle* h, bmpc_device_view* v);
+
+/* PerformanceIndex [UPSTREAM] per instance: perf[B*8] = {cost, dynamicsViolationSSE, equalityConstraintsSSE} before the
+ * step, the same three after the accepted step, step size alpha, armijo descent metric. */
+int bmpc_get_performance(bmpc_handle* h, double* perf);
+int bmpc_get_status(bmpc_handle* h, int* status /* B */);
+
+/* MPC_MRT_Interface::evaluatePolicy(t, x, &xOpt, &uOpt, &mode) (BipedalController.cpp:200), batched:
+ * t[B], x[B*nx] -> x_opt[B*nx], u_opt[B*nu], mode[B].  Host memory. */
+int bmpc_evaluate_policy(bmpc_handle* h, const double* t, const double* x, double* x_opt, double* u_opt, int* mode);
+
+/* number of kernels launched by the last bmpc_advance (for bench.py's gpu_launches) and per-phase device times in
+ * milliseconds of the last tick: {setup, lq, projection, riccati, forward, linesearch, finalize} */
+int bmpc_get_launch_count(const bmpc_handle* h);
+int bmpc_get_phase_times(bmpc_handle* h, float* ms /* 8 */);
+int bmpc_enable_phase_timing(bmpc_handle* h, int enable);
+void* bmpc_get_stream(bmpc_handle* h); /* cudaStream_t the library launches on */
+
+/* Test hooks (used by tests/ to compare intermediate device data with the oracle): copies the named device buffer of one
+ * instance to host.  names: "lq_record", "proj_record", "riccati_record", "dx", "du", "x_lin", "u_lin", "node_meta" */
+int bmpc_debug_copy(bmpc_handle* h, const char* name, int instance, double* dst, int capacity_doubles);
+int bmpc_debug_record_sizes(const bmpc_handle* h, int* lq_rec, int* proj_rec, int* ric_rec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BMPC_H */
