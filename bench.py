@@ -1,0 +1,380 @@
+#!/usr/bin/env python3
+"""bench.py - MPC solves/sec of the batched bipedal MPC hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload identical|randomized]
+
+A "step" is one MPC tick (one multiple-shooting SQP iteration: LQ approximation, projected Riccati QP, filter line
+search, feedback policy) for every instance of the batch, warm-started from the previous tick.  Default workload =
+BASELINE.json configs[1]: Unitree H1, 'trot', horizon 1.0 s at dt 0.01 (N = 100 intervals + 3 event nodes), batch 4096
+identical instances.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "MPC solves/sec (H1 centroidal, N=100) at batch 4096"
+UNIT = "solves/s"
+BATCH = 4096
+DT, HORIZON = 0.01, 1.0
+MPC_DT = 0.02  # mpcDesiredFrequency 50 Hz (task.info:177): the closed loop advances by one MPC period per tick
+MODEL = os.path.join(ROOT, "configs", "h1.model")
+# algorithmic bytes per node: LQ record 2024 doubles written once + read once, policy record 550 written,
+# K + uff (506) read by the forward sweep
+LQ_REC, POLICY_REC, FWD_READ = 2024, 550, 506
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def workload(kind, batch, rank=0):
+    import helpers
+    from tools.ingest import read_model
+    mdl = read_model(MODEL)
+    x_init = np.asarray(mdl["initial_state"])
+    nx = x_init.shape[0]
+    dj = np.asarray(mdl["default_joint_state"])
+    ME = 40
+    if kind == "identical":
+        # configs[1] schedule (events -0.95 + 0.35 j) continued so that the closed loop can advance for many ticks
+        et = -0.95 + 0.35 * np.arange(ME - 1)
+        ms = np.array([3] + [1, 2] * ((ME - 2) // 2) + [3], dtype=np.int32)[:len(et) + 1]
+        ms[-1] = 3
+        CMD = np.tile(np.array([0.3, 0.0, 0.0, 0.0]), (batch, 1))
+        X0 = np.tile(x_init, (batch, 1))
+        tt, ts = helpers.cmd_vel_target(x_init, 0.0, (0.3, 0.0, 0.0, 0.0), 1.0, mdl["com_height"], dj)
+        TT = np.tile(tt, (batch, 1))
+        TS = np.tile(ts, (batch, 1, 1))
+        ET = np.zeros((batch, ME))
+        MS = np.zeros((batch, ME + 1), dtype=np.int32)
+        ET[:, :len(et)] = et
+        MS[:, :len(ms)] = ms
+        NE = np.full(batch, len(et), dtype=np.int32)
+    else:
+        lo = np.array([mdl[f"joint{j}_limits"][0] for j in range(nx - 12)])
+        hi = np.array([mdl[f"joint{j}_limits"][1] for j in range(nx - 12)])
+        X0, cmd, gait, phase = helpers.randomized_instances(batch, x_init, dj, lo, hi, seed=rank)
+        CMD = cmd
+        TT = np.zeros((batch, 2))
+        TS = np.zeros((batch, 2, nx))
+        ET = np.zeros((batch, ME))
+        MS = np.zeros((batch, ME + 1), dtype=np.int32)
+        NE = np.zeros(batch, dtype=np.int32)
+        for b in range(batch):
+            TT[b], TS[b] = helpers.cmd_vel_target(X0[b], 0.0, cmd[b], 1.0, mdl["com_height"], dj)
+            et, ms = helpers.tiled_schedule(gait[b], phase[b], t_hi=4.2)
+            NE[b] = len(et)
+            ET[b, :len(et)] = et
+            MS[b, :len(ms)] = ms
+    return dict(X0=X0, T0=np.zeros(batch), TT=TT, TS=TS, ET=ET, MS=MS, NE=NE, CMD=CMD, mdl=mdl)
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_baseline_run(sample_instances, ticks, threads, kind="identical", march_native=True):
+    """Times the CPU oracle (restatement of the reference path; the reference's OCS2 stack cannot be built here) on host cores."""
+    from oracle import pyoracle
+    L = None
+    if march_native:
+        try:
+            out = os.path.join(ROOT, "oracle", "liboracle_native.so")
+            pyoracle.build(march="native", out=out)
+            L = pyoracle.lib(out)
+        except Exception:
+            L = None
+    if L is None:
+        pyoracle.build()
+        L = pyoracle.lib()
+    w = workload(kind, sample_instances)
+    ob = pyoracle.OracleBatch(MODEL, sample_instances, L=L)
+    for b, o in enumerate(ob.inst):
+        o.set_dt_horizon(DT, HORIZON)
+        o.set_mode_schedule(w["ET"][b, :w["NE"][b]], w["MS"][b, :w["NE"][b] + 1])
+        o.set_target(w["TT"][b], w["TS"][b])
+        ob.set_observation(b, 0.0, w["X0"][b])
+        ob.set_cmd_vel(b, w["CMD"][b], 1.0)
+    ob.run(threads=threads)  # cold tick (untimed)
+    ob.run(threads=threads, shift_dt=MPC_DT)  # first warm tick (untimed)
+    sec = 0.0
+    for _ in range(ticks):
+        sec += ob.run(threads=threads, shift_dt=MPC_DT)
+    nodes = ob.inst[0].info()["n_nodes"]
+    return sample_instances * ticks / sec, sec, nodes
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; OCS2 itself is unbuildable offline) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = max(threads * 4, 32)
+    for _ in range(max(args.warmup, 0)):
+        pass
+    t0 = time.time()
+    val, sec, nodes = cpu_baseline_run(sample, max(args.steps, 1), threads)
+    line = {
+        "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sec / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": "BASELINE configs[1]: H1 trot, horizon 1.0 s, dt 0.01 (N=100 + 3 event nodes), identical instances", "nodes": nodes,
+                   "note": "CPU oracle port of the reference path (OCS2/Pinocchio/HPIPM are un-vendored and unbuildable offline)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{sample} instances x {args.steps} warm ticks per step-set, one std::thread per core"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="identical", choices=["identical", "randomized"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="full", choices=["full", "window", "none"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from bipedal_control_b200 import BatchedMpcMrtInterface
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B = args.batch
+    w = workload(args.workload, B, rank)
+    mpc = BatchedMpcMrtInterface(B, model_file=MODEL, device=local_rank, dt=DT, time_horizon=HORIZON)
+    stream = torch.cuda.ExternalStream(mpc.stream(), device=local_rank)
+
+    # device-resident inputs for the kernel-only metric
+    dev = torch.device("cuda", local_rank)
+    d_t0 = torch.tensor(w["T0"], device=dev)
+    d_x0 = torch.tensor(w["X0"], device=dev)
+    d_tt = torch.tensor(w["TT"], device=dev)
+    d_ts = torch.tensor(w["TS"], device=dev)
+    d_ne = torch.tensor(w["NE"], device=dev, dtype=torch.int32)
+    d_et = torch.tensor(w["ET"], device=dev)
+    d_ms = torch.tensor(w["MS"], device=dev, dtype=torch.int32)
+    torch.cuda.synchronize()
+
+    gather_bufs = {}
+
+    def gather_policies():
+        """One NCCL all-gather of the solved feedback policies per tick (north star); 'window' = nodes the consumers read before the next tick."""
+        if world == 1 or args.gather == "none":
+            return 0
+        v = mpc.getDeviceView()
+        NS, nx, nu = v.max_nodes, v.nx, v.nu
+        nbytes = 0
+        with torch.cuda.stream(stream):
+            for name, ptr, per in (("K", v.K, NS * nu * nx), ("uff", v.uff, NS * nu), ("x", v.x, NS * nx), ("u", v.u, NS * nu), ("t", v.times, NS)):
+                src = _alias(ptr, B * per, dev)
+                if args.gather == "window":
+                    k = 4  # t0 .. t0 + 1/50 s is covered by the first 3 nodes at dt 0.01; 4 for interpolation
+                    src = src.view(B, NS, -1)[:, :k].contiguous()
+                key = (name, src.numel())
+                if key not in gather_bufs:
+                    gather_bufs[key] = torch.empty(world * src.numel(), device=dev, dtype=torch.float64)
+                dist.all_gather_into_tensor(gather_bufs[key], src.reshape(-1))
+                nbytes += src.numel() * 8 * world
+        return nbytes
+
+    d_cmd = torch.tensor(w["CMD"], device=dev)
+
+    def device_step():
+        # closed loop, everything resident in HBM: next observation from the current policy, cmd_vel target, one MPC tick
+        mpc.shiftObservations(MPC_DT)
+        mpc.setTargetsFromCmdVelDevice(d_cmd.data_ptr(), 1.0)
+        mpc.advanceMpcAsync()
+        return gather_policies()
+
+    perf_host = None
+
+    e2e_state = {}
+
+    def e2e_step():
+        # the call sequence a host-side user makes every tick, all buffers in host memory:
+        # policy evaluation -> new observation -> targets -> mode schedules -> solve -> performance indices back on the host
+        nonlocal perf_host
+        if "t" not in e2e_state:
+            e2e_state["t"], e2e_state["x"] = mpc.getObservations()
+        t_next = e2e_state["t"] + MPC_DT
+        x_next, _, _ = mpc.evaluatePolicy(t_next, e2e_state["x"])
+        e2e_state["t"], e2e_state["x"] = t_next, x_next
+        mpc.setCurrentObservation(t_next, x_next)
+        mpc.setTargetsFromCmdVel(w["CMD"], 1.0)
+        mpc.setModeSchedule(w["ET"], w["MS"], w["NE"])
+        mpc.advanceMpcAsync()
+        gather_policies()
+        perf_host = mpc.getPerformanceIndices()  # device -> host read of the step's result (PerformanceIndex per instance)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, collect_phases=False):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        phases = []
+        e0.record(stream)
+        t_wall = time.time()
+        for _ in range(steps):
+            fn()
+            if collect_phases:
+                mpc.synchronize()
+                phases.append(mpc.phaseTimes())
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        wall = (time.time() - t_wall) * 1e3
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, wall, phases
+
+    # cold start (t0 = 0) + warm-up ticks of the closed loop
+    mpc.reset()
+    mpc.setCurrentObservationDevice(d_t0.data_ptr(), d_x0.data_ptr())
+    mpc.setTargetsFromCmdVelDevice(d_cmd.data_ptr(), 1.0)
+    mpc.setModeScheduleDevice(d_et.shape[1], d_ne.data_ptr(), d_et.data_ptr(), d_ms.data_ptr())
+    mpc.advanceMpcAsync()
+    gather_policies()
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    mpc.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    mpc.enablePhaseTiming(True)
+    ms_dev, wall_dev, phases = timed(device_step, args.steps, collect_phases=True)
+    launches = (mpc.launchCount() + 2) * args.steps
+    mpc.enablePhaseTiming(False)
+    # un-instrumented kernel-only timing (no per-step phase readback)
+    ms_dev2, _, _ = timed(device_step, args.steps)
+    ms_dev = min(ms_dev, ms_dev2)
+    for _ in range(2):
+        e2e_step()
+    ms_e2e, wall_e2e, _ = timed(e2e_step, args.steps)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    status = mpc.getStatus()
+    pol_n = mpc.getPolicy(0, 1, with_gains=False)["n_nodes"][0]
+    nodes_stage = int(pol_n) - 1
+
+    value = world * B * args.steps / (ms_dev * 1e-3)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    peaks, peak_kind = measured_peaks()
+    ph = {k: float(np.mean([p[k] for p in phases])) for k in phases[0]} if phases else {}
+    ric_ms = ph.get("riccati", 0.0)
+    ric_bytes = B * nodes_stage * (LQ_REC + POLICY_REC) * 8
+    achieved = ric_bytes / (ric_ms * 1e-3) / 1e9 if ric_ms > 0 else 0.0
+    tick_bytes = B * nodes_stage * (2 * LQ_REC + POLICY_REC + FWD_READ) * 8
+    nx = mpc.nx
+    h2d = 2 * B * 8 * (1 + nx) + B * 2 * 8 * (1 + nx) + B * (4 + 40 * 8 + 41 * 4)   # evaluatePolicy query + observation, targets, mode schedules
+    d2h = B * 8 * 8 + B * 8 * (nx + mpc.nu) + B * 4 + 4 * int(ph.get("linesearch_trials", 1))  # performance indices + evaluatePolicy result
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": ("BASELINE configs[1]: H1 trot, horizon 1.0 s, dt 0.01 (N=100 intervals + 3 event nodes = 103 stages), batch 4096 identical instances per GPU; closed loop: every step advances t0 by 1/50 s, takes x0 from the previous policy and solves one warm-started tick"
+                                if args.workload == "identical" else "BASELINE configs[2]: H1 randomized states / velocity references / gaits (seed = rank), batch 4096 per GPU, warm-started tick"),
+                   "batch_per_gpu": B, "stages": nodes_stage, "l2": "per-tick working set (>5 GB of stage records) exceeds the 126 MB L2; no explicit flush",
+                   "policy_gather": args.gather if world > 1 else "n/a (1 GPU)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
+                "note": "host buffers every step: bmpc_evaluate_policy -> bmpc_set_observations -> bmpc_set_targets_from_cmd_vel -> bmpc_set_mode_schedules -> bmpc_advance -> bmpc_get_performance"},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "hbm", "kernel": "k_riccati", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"] if peaks["hbm_gbs"] else None,
+                     "traffic": None, "peak_kind": peak_kind, "kernel_ms": ric_ms,
+                     "whole_tick_frac": (tick_bytes / (ms_dev / args.steps * 1e-3) / 1e9) / peaks["hbm_gbs"]},
+        "phase_ms": ph,
+        "status_nonzero": int(np.count_nonzero(status & ~16)),
+    }
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        sample = max(threads * 4, 32)
+        val, sec, _ = cpu_baseline_run(sample, 4, threads, kind=args.workload)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{sample} instances x 4 warm ticks of the same workload, one std::thread per core ({sec:.1f} s)"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+_ALIAS_KEEP = []
+
+
+def _alias(ptr, numel, dev):
+    """torch tensor aliasing library-owned device memory (float64)."""
+    import torch
+
+    class _Arr:
+        pass
+
+    a = _Arr()
+    a.__cuda_array_interface__ = {"shape": (int(numel),), "typestr": "<f8", "data": (int(ptr), False), "version": 3, "strides": None}
+    t = torch.as_tensor(a, device=dev)
+    _ALIAS_KEEP.append(a)
+    if len(_ALIAS_KEEP) > 64:
+        del _ALIAS_KEEP[:32]
+    return t
+
+
+if __name__ == "__main__":
+    main()

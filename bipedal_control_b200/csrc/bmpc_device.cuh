@@ -106,10 +106,7 @@ struct Dims {
   // misc slots
   static constexpr int M_DT = 0, M_DQ = 1, M_DR = 2, M_MODE = 3, M_NROWS = 4, M_TYPE = 5, M_PCOST = 6, M_PDYN = 7, M_PEQ = 8;
   // projection record: Pxj[NJ][NXA], Pej[NJ], N[NJ][8], meta (mj, rank_flag)
-  static constexpr int P_PX = 0, P_PE = P_PX + NJ * NXA, P_N = P_PE + NJ, P_META = P_N + NJ * 8, PREC = ((P_META + 2 + 3) / 4) * 4;
-  // Riccati record per stage: K[NU][NX], kappa[NU], Phi[NX][NX], phi[NX], ghat[NX], misc(2)
-  static constexpr int K_K = 0, K_KAP = K_K + NU * NX, K_PHI = K_KAP + NU, K_SPHI = K_PHI + NX * NX, K_G = K_SPHI + NX, K_MISC = K_G + NX,
-                       KREC = ((K_MISC + 2 + 3) / 4) * 4;
+  static constexpr int P_PX = 0, P_PE = P_PX + NJ * NXA, P_N = P_PE + NJ, P_FO = P_N + NJ * 8, P_META = P_FO + 12, PREC = ((P_META + 4 + 3) / 4) * 4;
 };
 
 // map a state index (0..NX-1, not 6..8) to its column in the "active x" set X = {0..5, 9..NX-1}

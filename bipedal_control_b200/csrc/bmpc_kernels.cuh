@@ -17,12 +17,8 @@ namespace bmpc {
 constexpr double WEAK_EPS = 1e-6;   // [UPSTREAM] numeric_traits::weakEpsilon
 constexpr int WS_THREADS = 128;     // threads per CTA of the Riccati kernel (one instance per CTA)
 
-// sizes of the Riccati record per stage (kappa, Phi, phi, ghat, misc)
-template <int NJ>
-struct RDims {
-  static constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU;
-  static constexpr int K_KAP = 0, K_PHI = K_KAP + NU, K_SPHI = K_PHI + NX * NX, K_G = K_SPHI + NX, K_MISC = K_G + NX, KREC = ((K_MISC + 2 + 3) / 4) * 4;
-};
+template <int NJ> struct RDims;
+template <int NJ> struct SDims;
 
 struct Dev {
   int B, NS, ME, TP, npts;
@@ -34,7 +30,7 @@ struct Dev {
   double* xref; double* zref;
   const int* p_n; const double* p_t; const double* p_x; const double* p_u;   // previous primal solution (warm start)
   double* s_x; double* s_u; double* s_uff; double* s_K;                      // new primal solution / linearisation point
-  double* lq; double* proj; double* ric;
+  double* lq; double* proj; double* stage; double* ric;
   double* dx; double* du;
   double* perf_trial; double* perf; double* alpha; double* norms; int* done; int* status; int* counters;
 };
@@ -331,18 +327,35 @@ __global__ void __launch_bounds__(64) k_lq(Dev d) {
   misc[D::M_TYPE] = 0.0; misc[D::M_PCOST] = pcost; misc[D::M_PDYN] = dt * pdyn; misc[D::M_PEQ] = dt * peq;
 }
 
-// ------------------------------------------------------------------------------------------------ K1.5: constraint projection, one warp per (instance, stage)
-// Dv (r x NJ, full row rank after the per-foot compression) -> Householder QR of Dv^T = Q [R; 0]:
-//   Dv^+ = Q1 R^-T  (Moore-Penrose),  null(Dv) = span(Q2).   Outputs Pxj = -Dv^+ Cv, Pej = -Dv^+ ev, N = Q2.
+// ------------------------------------------------------------------------------------------------ K1.5: constraint projection + change of input variables
+// One warp per (instance, stage).
+//  (1) Dv (r x NJ, full row rank after the per-foot compression) -> Householder QR of Dv^T = Q [R; 0]:
+//      Dv^+ = Q1 R^-T (Moore-Penrose), null(Dv) = span(Q2):  Pxj = -Dv^+ Cv, Pej = -Dv^+ ev, N = Q2
+//      (replaces LinearAlgebra::luConstraintProjection [UPSTREAM]).
+//  (2) changeOfInputVariables [UPSTREAM] with du = Pe + Px dx + Pu dut, exploiting the block structure
+//      (forces of closed contacts stay free, forces of open contacts are fixed to -F, joint velocities = Pej + Pxj dx + N dut_null):
+//      writes the projected stage record (SDims) that the sequential Riccati kernel consumes.
+template <int NJ>
+struct SDims {
+  static constexpr int NX = Dims<NJ>::NX, NXA = Dims<NJ>::NXA, NXR = NX - 3, MP = 16;
+  static constexpr int S_AT = 0, S_BT = S_AT + NXR * NXA, S_QT = S_BT + NXR * MP, S_PT = S_QT + NXA * NXA, S_RN = S_PT + 8 * NXA, S_HB = S_RN + 64,
+                       S_RD = S_HB + 24, S_B = S_RD + 12, S_Q = S_B + NX, S_R = S_Q + NX, S_QD = S_R + MP, S_META = S_QD + NX, SREC = ((S_META + 8 + 3) / 4) * 4;
+  // meta slots
+  static constexpr int T_TYPE = 0, T_MODE = 1, T_M = 2, T_MJ = 3, T_NCLOSED = 4, T_DT = 5;
+};
+
 template <int NJ>
 __global__ void __launch_bounds__(128) k_project(Dev d) {
-  using D = Dims<NJ>;
-  constexpr int NXA = D::NXA;
+  using D = Dims<NJ>; using S = SDims<NJ>;
+  constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, NXR = S::NXR, MP = S::MP;
   constexpr int WPB = 4;
   __shared__ double sM[WPB][NJ][12];     // Dv^T  (NJ x r), r <= 10
   __shared__ double sV[WPB][10][NJ];     // Householder vectors (zero padded)
   __shared__ double sBeta[WPB][10];
   __shared__ double sG[WPB][10][NXA + 1];
+  __shared__ double sPx[WPB][NJ][NXA + 1];   // [Pxj | Pej]
+  __shared__ double sN[WPB][NJ][8];
+  __shared__ double sRN[WPB][NJ][8];         // Rj_eff N
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * WPB + warp;
   const int b = gw / d.NS, k = gw % d.NS;
@@ -350,15 +363,23 @@ __global__ void __launch_bounds__(128) k_project(Dev d) {
   const int N = d.n_nodes[b] - 1;
   if (k >= N) return;
   const size_t nb = (size_t)b * d.NS;
-  if (d.node_ev[nb + k] == 1) return;
   const double* rec = d.lq + (nb + k) * D::REC;
   double* out = d.proj + (nb + k) * D::PREC;
+  double* so = d.stage + (nb + k) * S::SREC;
+  if (d.node_ev[nb + k] == 1) {   // event stage: only b is needed
+    for (int i = lane; i < NX; i += 32) so[S::S_B + i] = rec[D::R_B + i];
+    if (lane == 0) { so[S::S_META + S::T_TYPE] = 1.0; so[S::S_META + S::T_M] = 0.0; so[S::S_META + S::T_MJ] = 0.0; so[S::S_META + S::T_NCLOSED] = 0.0; so[S::S_META + S::T_DT] = 0.0; so[S::S_META + S::T_MODE] = -1.0; }
+    return;
+  }
+  const DevModel& M = c_model;
   const int r = (int)rec[D::R_MISC + D::M_NROWS];
   double (*Mt)[12] = sM[warp]; double (*V)[NJ] = sV[warp]; double* beta = sBeta[warp]; double (*G)[NXA + 1] = sG[warp];
+  double (*Px)[NXA + 1] = sPx[warp]; double (*Nn)[8] = sN[warp]; double (*RN)[8] = sRN[warp];
   for (int i = lane; i < r * NJ; i += 32) { const int row = i / NJ, col = i % NJ; Mt[col][row] = rec[D::R_DV + i]; }
   for (int i = lane; i < r * NXA; i += 32) { const int row = i / NXA, col = i % NXA; G[row][col] = rec[D::R_CV + i]; }
   for (int i = lane; i < r; i += 32) G[i][NXA] = rec[D::R_EV + i];
   for (int i = lane; i < 10 * NJ; i += 32) V[i / NJ][i % NJ] = 0.0;
+  for (int i = lane; i < NJ * 8; i += 32) { Nn[i / 8][i % 8] = 0.0; RN[i / 8][i % 8] = 0.0; }
   __syncwarp();
   bool anomaly = false;
   double rmax = 0.0;
@@ -375,8 +396,7 @@ __global__ void __launch_bounds__(128) k_project(Dev d) {
     rmax = fmax(rmax, nrm);
     if (!(nrm > 1e-9 * rmax)) anomaly = true;
     __syncwarp();
-    // lanes kk+1..r-1 update their column
-    if (lane > kk && lane < r) {
+    if (lane > kk && lane < r) {   // lanes kk+1..r-1 update their column
       double s = v0 * Mt[kk][lane];
       for (int i = kk + 1; i < NJ; ++i) s += Mt[i][kk] * Mt[i][lane];
       s *= bta;
@@ -397,9 +417,11 @@ __global__ void __launch_bounds__(128) k_project(Dev d) {
   for (int i = 0; i < NJ; ++i) y[i] = 0.0;
   const bool is_rhs = lane <= NXA, is_null = lane > NXA && lane <= NXA + mj;
   if (is_rhs) {   // z = R^-T g  (R^T lower triangular: R[l][i] = Mt[l][i] for l <= i)
-    for (int i = 0; i < r; ++i) {
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) if (i < r) {
       double s = G[i][lane];
-      for (int l = 0; l < i; ++l) s -= Mt[l][i] * y[l];
+#pragma unroll
+      for (int l = 0; l < NJ; ++l) if (l < i) s -= Mt[l][i] * y[l];
       y[i] = s / Mt[i][i];
     }
   } else if (is_null) {
@@ -417,350 +439,460 @@ __global__ void __launch_bounds__(128) k_project(Dev d) {
       for (int i = 0; i < NJ; ++i) y[i] -= s * V[kk][i];
     }
     if (is_rhs) {
-      if (lane < NXA) { for (int i = 0; i < NJ; ++i) out[D::P_PX + i * NXA + lane] = -y[i]; }
-      else { for (int i = 0; i < NJ; ++i) out[D::P_PE + i] = -y[i]; }
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) { y[i] = -y[i]; Px[i][lane] = y[i]; }
+      if (lane < NXA) { for (int i = 0; i < NJ; ++i) out[D::P_PX + i * NXA + lane] = y[i]; }
+      else { for (int i = 0; i < NJ; ++i) out[D::P_PE + i] = y[i]; }
     } else {
       const int t = lane - NXA - 1;
-      for (int i = 0; i < NJ; ++i) out[D::P_N + i * 8 + t] = y[i];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) { Nn[i][t] = y[i]; out[D::P_N + i * 8 + t] = y[i]; }
     }
   }
-  if (lane == 0) { out[D::P_META] = (double)mj; out[D::P_META + 1] = anomaly ? 1.0 : 0.0; if (anomaly) atomicOr(&d.status[b], 2); }
+  const double dt = rec[D::R_MISC + D::M_DT], dq = rec[D::R_MISC + D::M_DQ], dr = rec[D::R_MISC + D::M_DR];
+  const int mode = (int)rec[D::R_MISC + D::M_MODE];
+  const bool st0 = leg_in_stance(mode, 0), st1 = leg_in_stance(mode, 1);
+  const int nclosed = 2 * (int(st0) + int(st1));
+  const int m = 3 * nclosed + mj;
+  if (lane < 12) out[D::P_FO + lane] = rec[D::R_FO + lane];
+  if (lane == 0) {
+    out[D::P_META] = (double)mj; out[D::P_META + 1] = anomaly ? 1.0 : 0.0; out[D::P_META + 2] = (double)mode; if (anomaly) atomicOr(&d.status[b], 2);
+    double* mt = so + S::S_META;
+    mt[S::T_TYPE] = 0.0; mt[S::T_MODE] = (double)mode; mt[S::T_M] = (double)m; mt[S::T_MJ] = (double)mj; mt[S::T_NCLOSED] = (double)nclosed; mt[S::T_DT] = dt;
+  }
+  __syncwarp();
+  // ---------------- change of input variables.  y[] = own column of [Pxj | Pej] (lanes <= NXA) or of N (null lanes)
+  const double* Bd = rec + D::R_BD;
+  // t[] = Rj_eff * (own column)  (+ r_j for the Pe column -> t1 = r_j + Rj_eff Pej)
+  double tcol[NJ];
+  if (is_rhs || is_null) {
+#pragma unroll
+    for (int l = 0; l < NJ; ++l) {
+      double a = dr * y[l];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) a += dt * M.Rjoint[l * NJ + j] * y[j];
+      if (lane == NXA) a += rec[D::R_R + 12 + l];
+      tcol[l] = a;
+    }
+    if (is_null) { const int t = lane - NXA - 1; for (int l = 0; l < NJ; ++l) RN[l][t] = tcol[l]; }
+  }
+  __syncwarp();
+  if (is_rhs) {
+    const int c = lane;   // X column (or the affine column NXA)
+    // (At - I) rows 3..11: AdI + Bd_j Pxj ; rows 12..: dt Pxj.   Affine column: contributes to bt
+    for (int rr = 0; rr < 9; ++rr) {
+      double a = 0.0;
+#pragma unroll
+      for (int l = 0; l < NJ; ++l) a += Bd[rr * NU + 12 + l] * y[l];
+      if (c < NXA) so[S::S_AT + rr * NXA + c] = rec[D::R_AD + rr * NXA + c] + a;
+      else {
+        double bb = rec[D::R_B + 3 + rr] + a;
+        for (int cn = 0; cn < NCON; ++cn) if (!(cn / 2 == 0 ? st0 : st1))
+          for (int q = 0; q < 3; ++q) bb -= Bd[rr * NU + 3 * cn + q] * rec[D::R_FO + 3 * cn + q];
+        so[S::S_B + 3 + rr] = bb;
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < NJ; ++l) {
+      if (c < NXA) so[S::S_AT + (9 + l) * NXA + c] = dt * y[l];
+      else so[S::S_B + 12 + l] = rec[D::R_B + 12 + l] + dt * y[l];
+    }
+    if (c == NXA) {   // rows 0..2 of bt: B_d rows 0..2 = dt/m on the force columns
+      const double f = dt / M.total_mass;
+      for (int q = 0; q < 3; ++q) {
+        double bb = rec[D::R_B + q];
+        for (int cn = 0; cn < NCON; ++cn) if (!(cn / 2 == 0 ? st0 : st1)) bb -= f * rec[D::R_FO + 3 * cn + q];
+        so[S::S_B + q] = bb;
+      }
+    }
+    // QtX[:, c] = Pxj^T tcol  (c < NXA) ; qt = q + Pxj^T t1 (affine column)
+    for (int xr = 0; xr < NXA; ++xr) {
+      double a = 0.0;
+#pragma unroll
+      for (int l = 0; l < NJ; ++l) a += Px[l][xr] * tcol[l];
+      if (c < NXA) so[S::S_QT + xr * NXA + c] = a;
+      else { const int sidx = xr < 6 ? xr : xr + 3; so[S::S_Q + sidx] = rec[D::R_Q + sidx] + a; }
+    }
+    if (c == NXA) for (int q = 6; q < 9; ++q) so[S::S_Q + q] = rec[D::R_Q + q];
+    // Pt null rows: N^T tcol ; affine column -> rt null entries
+    for (int t = 0; t < 8; ++t) {
+      double a = 0.0;
+      if (t < mj) {
+#pragma unroll
+        for (int l = 0; l < NJ; ++l) a += Nn[l][t] * tcol[l];
+      }
+      if (c < NXA) so[S::S_PT + t * NXA + c] = a;
+      else if (t < mj) so[S::S_R + 3 * nclosed + t] = a;
+    }
+  }
+  // Bt: closed-contact force columns are copied, null-space columns = B_d[:, joints] N
+  for (int i = lane; i < NXR * MP; i += 32) {
+    const int rr = i / MP, c = i % MP;   // rr = state row - 3
+    double a = 0.0;
+    if (c < 3 * nclosed) {
+      int fc;   // original force column of reduced column c
+      if (st0) fc = c; else fc = 6 + c;
+      if (rr < 9) a = Bd[rr * NU + fc];
+    } else if (c < m) {
+      const int t = c - 3 * nclosed;
+      if (rr < 9) { for (int l = 0; l < NJ; ++l) a += Bd[rr * NU + 12 + l] * Nn[l][t]; }
+      else a = dt * Nn[rr - 9][t];
+    }
+    so[S::S_BT + i] = a;
+  }
+  // Rt: null block N^T Rj_eff N, force blocks (barrier Hessians) and force diagonal; rt force entries; Q diagonal
+  for (int i = lane; i < 64; i += 32) {
+    const int t1 = i / 8, t2 = i % 8;
+    double a = 0.0;
+    if (t1 < mj && t2 < mj) for (int l = 0; l < NJ; ++l) a += Nn[l][t1] * RN[l][t2];
+    so[S::S_RN + i] = a;
+  }
+  if (lane < 24) so[S::S_HB + lane] = rec[D::R_HB + lane];
+  if (lane < 12) so[S::S_RD + lane] = dt * M.Rforce[lane] + dr;
+  if (lane < 3 * nclosed) { const int fc = st0 ? lane : 6 + lane; so[S::S_R + lane] = rec[D::R_R + fc]; }
+  if (lane >= m && lane < MP) so[S::S_R + lane] = 0.0;
+  for (int i = lane; i < NX; i += 32) so[S::S_QD + i] = dt * M.Qdiag[i] + dq;
+}
+
+// ------------------------------------------------------------------------------------------------ TMA bulk copy + mbarrier helpers (sm_90+/sm_100a PTX)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// one thread: arm the barrier with the byte count and launch the bulk copy global -> shared (UBLKCP in SASS)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ DMMA tile GEMM in shared memory
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
-// C[8MT x 8NT] = (ACC ? C : 0) + op(A) op(B), K = 4 KT.  TA: A is given transposed (As[k][m]); TB: B is given transposed (Bs[n][k]).
-// Output tiles are distributed round-robin over the NW warps of the CTA.  All leading dimensions are == 4 or 12 (mod 16) doubles,
-// which makes every fragment load bank-conflict free.
-template <int MT, int NT, int KT, bool TA, bool TB, bool ACC, int NW>
+// C[8MT x 8NT] = (ACC ? C : 0) + sign * op(A) op(B), K = 4 KT.  TA: A is given transposed (As[k][m]); TB: B is given transposed (Bs[n][k]).
+// Output tiles are distributed round-robin over warps [W0, W0 + NW) of the CTA; each warp interleaves the k-loops of its tiles
+// (independent accumulator chains).  All leading dimensions are == 4 or 12 (mod 16) doubles: every fragment load is bank-conflict free.
+template <int MT, int NT, int KT, bool TA, bool TB, bool ACC, bool NEG, int NW, int W0>
 __device__ __forceinline__ void gemm_tiles(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, double* __restrict__ C, int ldc, int warp, int lane) {
+  constexpr int TPW = (MT * NT + NW - 1) / NW;
   const int lr = lane >> 2, lc = lane & 3;
-  for (int t = warp; t < MT * NT; t += NW) {
-    const int mt = t / NT, nt = t % NT;
-    double c0 = 0.0, c1 = 0.0;
-    double* cp = C + (8 * mt + lr) * ldc + 8 * nt + 2 * lc;
-    if (ACC) { c0 = cp[0]; c1 = cp[1]; }
+  const int w = warp - W0;
+  if (w < 0 || w >= NW) return;
+  double c0[TPW], c1[TPW];
+  int mt[TPW], nt[TPW];
 #pragma unroll
-    for (int kk = 0; kk < KT; ++kk) {
-      const double a = TA ? A[(4 * kk + lc) * lda + 8 * mt + lr] : A[(8 * mt + lr) * lda + 4 * kk + lc];
-      const double bb = TB ? B[(8 * nt + lr) * ldb + 4 * kk + lc] : B[(4 * kk + lc) * ldb + 8 * nt + lr];
-      dmma884(c0, c1, a, bb);
-    }
-    cp[0] = c0; cp[1] = c1;
+  for (int i = 0; i < TPW; ++i) {
+    const int t = w + i * NW;
+    mt[i] = t / NT; nt[i] = t % NT;
+    c0[i] = 0.0; c1[i] = 0.0;
+    if (ACC && t < MT * NT) { const double* cp = C + (8 * mt[i] + lr) * ldc + 8 * nt[i] + 2 * lc; c0[i] = cp[0]; c1[i] = cp[1]; }
   }
+#pragma unroll
+  for (int kk = 0; kk < KT; ++kk) {
+#pragma unroll
+    for (int i = 0; i < TPW; ++i) {
+      if (w + i * NW < MT * NT) {
+        double a = TA ? A[(4 * kk + lc) * lda + 8 * mt[i] + lr] : A[(8 * mt[i] + lr) * lda + 4 * kk + lc];
+        const double bb = TB ? B[(8 * nt[i] + lr) * ldb + 4 * kk + lc] : B[(4 * kk + lc) * ldb + 8 * nt[i] + lr];
+        if (NEG) a = -a;
+        dmma884(c0[i], c1[i], a, bb);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TPW; ++i)
+    if (w + i * NW < MT * NT) { double* cp = C + (8 * mt[i] + lr) * ldc + 8 * nt[i] + 2 * lc; cp[0] = c0[i]; cp[1] = c1[i]; }
 }
 
-// ------------------------------------------------------------------------------------------------ K2: change of input variables + backward Riccati
-// One CTA (4 warps) per instance; all matrices of the recursion live in shared memory, padded to NXP = 24 states / MP = 16 reduced inputs.
+// ------------------------------------------------------------------------------------------------ K2: backward Riccati recursion
+// One CTA (4 warps) per instance; S, At, SA, Bt, SB, H, G live in shared memory, padded to NXP = 24 states / MP = 16 reduced inputs.
+//   SA = S At, SB = S Bt, sb = s + S bt;  H = Pt + Bt^T SA, G = Rt + Bt^T SB, g = rt + Bt^T sb
+//   G = L L^T, Y = L^-1 H, yg = L^-1 g                    (warp 0; warps 1-3 compute At^T SA meanwhile)
+//   S' = Qt + At^T SA - Y^T Y,  s' = qt + At^T sb - Y^T yg
+// The gains Kt = -L^-T Y are recovered off the critical path by k_policy_expand.
 template <int NJ>
 struct RicSmem {
   static constexpr int NXP = 24, MP = 16, LD = 28, LDM = 20;
   double S[NXP * LD], At[NXP * LD], SA[NXP * LD];
   double Bt[NXP * LDM], SB[NXP * LDM];
-  double H[MP * LD], Kt[MP * LD], G[MP * LDM];
-  double T1[NJ * LD];                 // Rj_eff * Pxj   (NJ x NXA)
-  double rec[Dims<NJ>::REC];
-  double prj[Dims<NJ>::PREC];
-  double s[NXP], sb[NXP], bt[NXP], qt[NXP], snew[NXP], phi[NXP], ghat[NXP];
-  double rt[MP], g[MP], kt[MP], t1[NJ < 16 ? 16 : NJ], linv[MP];
-  double xk[NXP], uk[NXP];
-  int redcol[MP];                      // reduced input -> original input column (forces) or -(1+t) for null-space column t
+  double H[MP * LD], G[MP * LDM];
+  double s[NXP], sb[NXP], bt[NXP], qt[NXP], snew[NXP], qd[NXP];
+  double rt[MP], g[MP];
+  double lcol[2][MP + 2];
+  alignas(16) double stage[2][SDims<NJ>::SREC];   // TMA-staged stage records (double buffered)
+  alignas(8) unsigned long long bar[2];
 };
 
 template <int NJ>
-__global__ void __launch_bounds__(WS_THREADS) k_riccati(Dev d) {
-  using D = Dims<NJ>; using R = RDims<NJ>; using SM = RicSmem<NJ>;
-  constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, NXP = SM::NXP, MP = SM::MP, LD = SM::LD, LDM = SM::LDM;
+struct RDims {
+  static constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU, MP = 16;
+  // written by k_riccati: Y[MP][NX], yg[MP], L[MP][MP];  written by k_policy_expand: kappa, Phi, phi, ghat, misc
+  static constexpr int K_Y = 0, K_YG = K_Y + MP * NX, K_L = K_YG + MP, K_KAP = K_L + MP * MP, K_PHI = K_KAP + NU, K_SPHI = K_PHI + NX * NX, K_G = K_SPHI + NX,
+                       K_MISC = K_G + NX, KREC = ((K_MISC + 2 + 3) / 4) * 4;
+};
+
+template <int NJ>
+__global__ void __launch_bounds__(WS_THREADS, 4) k_riccati(Dev d) {
+  using D = Dims<NJ>; using R = RDims<NJ>; using SM = RicSmem<NJ>; using S = SDims<NJ>;
+  constexpr int NX = D::NX, NXA = D::NXA, NXR = S::NXR, NXP = SM::NXP, MP = SM::MP, LD = SM::LD, LDM = SM::LDM;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
   const int b = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = d.n_nodes[b] - 1;
   const size_t nb = (size_t)b * d.NS;
-  const DevModel& M = c_model;
-  const double imass = 1.0 / M.total_mass;
+  const double imass = 1.0 / c_model.total_mass;
   // terminal value function: zero (no terminal cost installed)
-  for (int i = tid; i < NXP * LD; i += WS_THREADS) sm.S[i] = 0.0;
-  for (int i = tid; i < NXP; i += WS_THREADS) sm.s[i] = 0.0;
+  for (int i = tid; i < NXP * LD; i += WS_THREADS) { sm.S[i] = 0.0; sm.At[i] = 0.0; sm.SA[i] = 0.0; }
+  for (int i = tid; i < NXP * LDM; i += WS_THREADS) { sm.Bt[i] = 0.0; sm.SB[i] = 0.0; }
+  for (int i = tid; i < MP * LD; i += WS_THREADS) sm.H[i] = 0.0;   // padded columns must stay zero (shared memory is not cleared between CTAs)
+  for (int i = tid; i < MP * LDM; i += WS_THREADS) sm.G[i] = 0.0;
+  for (int i = tid; i < NXP; i += WS_THREADS) { sm.s[i] = 0.0; sm.sb[i] = 0.0; sm.bt[i] = 0.0; sm.qt[i] = 0.0; sm.snew[i] = 0.0; sm.qd[i] = 0.0; }
+  constexpr unsigned REC_BYTES = S::SREC * sizeof(double);
+  if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); fence_mbar_init(); }
   __syncthreads();
+  // prologue: stage records N-1 and N-2 are in flight before the loop starts
+  if (tid == 0) {
+    if (N >= 1) tma_load_1d(sm.stage[(N - 1) & 1], d.stage + (nb + N - 1) * S::SREC, REC_BYTES, &sm.bar[(N - 1) & 1]);
+    if (N >= 2) tma_load_1d(sm.stage[(N - 2) & 1], d.stage + (nb + N - 2) * S::SREC, REC_BYTES, &sm.bar[(N - 2) & 1]);
+  }
+  unsigned phase_bits = 0;   // per-buffer mbarrier phase parity
   for (int k = N - 1; k >= 0; --k) {
-    const double* recg = d.lq + (nb + k) * D::REC;
+    const int buf = k & 1;
+    mbar_wait(&sm.bar[buf], (phase_bits >> buf) & 1u);
+    phase_bits ^= 1u << buf;
+    const double* sr = sm.stage[buf];
     double* ric = d.ric + (nb + k) * R::KREC;
-    double* Kg = d.s_K + (nb + k) * (size_t)(NU * NX);
-    double* uffg = d.s_uff + (nb + k) * NU;
-    const bool is_event = d.node_ev[nb + k] == 1;
-    if (is_event) {
-      // S unchanged (A = I, Q = 0); s <- s + S b;  K = 0, Phi = I, phi = b
-      for (int i = tid; i < NX; i += WS_THREADS) sm.bt[i] = recg[D::R_B + i];
+    const double* meta = sr + S::S_META;
+    const bool is_event = meta[S::T_TYPE] != 0.0;
+    if (is_event) {   // S unchanged (A = I, Q = 0, no input); s <- s + S b
+      if (tid < NX) sm.bt[tid] = sr[S::S_B + tid];
       __syncthreads();
       if (tid < NX) { double a = sm.s[tid]; for (int c = 0; c < NX; ++c) a += sm.S[tid * LD + c] * sm.bt[c]; sm.snew[tid] = a; }
       __syncthreads();
-      if (tid < NX) { sm.s[tid] = sm.snew[tid]; ric[R::K_SPHI + tid] = sm.bt[tid]; ric[R::K_G + tid] = 0.0; }
-      if (tid == 0) { ric[R::K_MISC] = 0.0; ric[R::K_MISC + 1] = 1.0; }
-      for (int i = tid; i < NU; i += WS_THREADS) { ric[R::K_KAP + i] = 0.0; uffg[i] = 0.0; }
-      for (int i = tid; i < NX * NX; i += WS_THREADS) ric[R::K_PHI + i] = (i / NX == i % NX) ? 1.0 : 0.0;
-      for (int i = tid; i < NU * NX; i += WS_THREADS) Kg[i] = 0.0;
+      if (tid < NX) sm.s[tid] = sm.snew[tid];
       __syncthreads();
+      if (tid == 0 && k >= 2) { fence_proxy_async(); tma_load_1d(sm.stage[buf], d.stage + (nb + k - 2) * S::SREC, REC_BYTES, &sm.bar[buf]); }
       continue;
     }
-    // ---- phase 0: stage the records
-    const double* prjg = d.proj + (nb + k) * D::PREC;
-    for (int i = tid; i < D::REC; i += WS_THREADS) sm.rec[i] = recg[i];
-    for (int i = tid; i < D::PREC; i += WS_THREADS) sm.prj[i] = prjg[i];
-    for (int i = tid; i < NX; i += WS_THREADS) sm.xk[i] = d.s_x[(nb + k) * NX + i];
-    for (int i = tid; i < NU; i += WS_THREADS) sm.uk[i] = d.s_u[(nb + k) * NU + i];
-    __syncthreads();
-    const double dt = sm.rec[D::R_MISC + D::M_DT], dq = sm.rec[D::R_MISC + D::M_DQ], dr = sm.rec[D::R_MISC + D::M_DR];
-    const int mode = (int)sm.rec[D::R_MISC + D::M_MODE];
-    const int mj = (int)sm.prj[D::P_META];
-    const bool st[2] = {leg_in_stance(mode, 0), leg_in_stance(mode, 1)};
-    const int nclosed = 2 * (int(st[0]) + int(st[1]));
-    const int m = 3 * nclosed + mj;
-    const double* Pxj = sm.prj + D::P_PX; const double* Pej = sm.prj + D::P_PE; const double* Nn = sm.prj + D::P_N;
-    const double* AdI = sm.rec + D::R_AD; const double* Bd = sm.rec + D::R_BD;
-    // ---- phase 1a: T1 = Rj_eff Pxj, t1 = r_j + Rj_eff Pej, reduced-input column map
-    for (int i = tid; i < NJ * NXA; i += WS_THREADS) {
-      const int l = i / NXA, c = i % NXA;
-      double a = dr * Pxj[l * NXA + c];
-      for (int j = 0; j < NJ; ++j) a += dt * M.Rjoint[l * NJ + j] * Pxj[j * NXA + c];
-      sm.T1[l * LD + c] = a;
-    }
-    if (tid < NJ) {
-      double a = sm.rec[D::R_R + 12 + tid] + dr * Pej[tid];
-      for (int j = 0; j < NJ; ++j) a += dt * M.Rjoint[tid * NJ + j] * Pej[j];
-      sm.t1[tid] = a;
-    }
-    if (tid == 0) {
-      int col = 0;
-      for (int c = 0; c < NCON; ++c) if (st[c / 2]) { sm.redcol[col++] = 3 * c; sm.redcol[col++] = 3 * c + 1; sm.redcol[col++] = 3 * c + 2; }
-      for (int t = 0; t < mj; ++t) sm.redcol[col++] = -(1 + t);
-      for (; col < MP; ++col) sm.redcol[col] = 1000;
-    }
-    // zero the padded operand matrices
-    for (int i = tid; i < NXP * LD; i += WS_THREADS) sm.At[i] = 0.0;
-    for (int i = tid; i < NXP * LDM; i += WS_THREADS) sm.Bt[i] = 0.0;
-    for (int i = tid; i < MP * LD; i += WS_THREADS) sm.H[i] = 0.0;
-    for (int i = tid; i < MP * LDM; i += WS_THREADS) sm.G[i] = 0.0;
-    __syncthreads();
-    // ---- phase 1b: At = A_d + B_d Px ; Bt = B_d Pu ; bt = b + B_d Pe ; H <- Pt ; G <- Rt ; rt, qt
-    for (int i = tid; i < NX * NX; i += WS_THREADS) {   // At
+    const int m = (int)meta[S::T_M], mj = (int)meta[S::T_MJ], nclosed = (int)meta[S::T_NCLOSED], mode = (int)meta[S::T_MODE];
+    const double dt = meta[S::T_DT];
+    const bool st0 = leg_in_stance(mode, 0);
+    // ---- phase 1: scatter the projected stage record into the padded operand matrices
+    for (int i = tid; i < NX * NX; i += WS_THREADS) {   // At = I + [rows 3.., X cols]
       const int r = i / NX, c = i % NX;
       double a = (r == c) ? 1.0 : 0.0;
-      if (c < 6 || c >= 9) {
-        const int xc = xcol(c);
-        if (r >= 3 && r < 12) {
-          a += AdI[(r - 3) * NXA + xc];
-          for (int l = 0; l < NJ; ++l) a += Bd[(r - 3) * NU + 12 + l] * Pxj[l * NXA + xc];
-        } else if (r >= 12) a += dt * Pxj[(r - 12) * NXA + xc];
-      }
+      if (r >= 3 && (c < 6 || c >= 9)) a += sr[S::S_AT + (r - 3) * NXA + xcol(c)];
       sm.At[r * LD + c] = a;
     }
     for (int i = tid; i < NX * MP; i += WS_THREADS) {   // Bt
       const int r = i / MP, c = i % MP;
-      const int rc = sm.redcol[c];
       double a = 0.0;
-      if (rc < 1000) {
-        if (rc >= 0) {   // force column rc of B_d: rows 0..2 = dt/m e_a, rows 3..11 stored, rows >= 12 zero
-          if (r < 3) a = (r == rc % 3) ? dt * imass : 0.0;
-          else if (r < 12) a = Bd[(r - 3) * NU + rc];
-        } else {         // null-space column t: B_d[:, joints] N[:, t]
-          const int t = -rc - 1;
-          if (r >= 3 && r < 12) { for (int l = 0; l < NJ; ++l) a += Bd[(r - 3) * NU + 12 + l] * Nn[l * 8 + t]; }
-          else if (r >= 12) a = dt * Nn[(r - 12) * 8 + t];
-        }
-      }
+      if (r >= 3) a = sr[S::S_BT + (r - 3) * MP + c];
+      else if (c < 3 * nclosed) a = (c % 3 == r) ? dt * imass : 0.0;
       sm.Bt[r * LDM + c] = a;
     }
-    if (tid < NX) {   // bt = b + B_d Pe   (Pe: open-contact forces -F, joints Pej)
-      const int r = tid;
-      double a = sm.rec[D::R_B + r];
-      for (int c = 0; c < NCON; ++c) if (!st[c / 2]) {
-        for (int q = 0; q < 3; ++q) {
-          const double pe = -sm.rec[D::R_FO + 3 * c + q];
-          if (r < 3) { if (r == q) a += dt * imass * pe; }
-          else if (r < 12) a += Bd[(r - 3) * NU + 3 * c + q] * pe;
-        }
-      }
-      if (r >= 3 && r < 12) { for (int l = 0; l < NJ; ++l) a += Bd[(r - 3) * NU + 12 + l] * Pej[l]; }
-      else if (r >= 12) a += dt * Pej[r - 12];
-      sm.bt[r] = a;
-      // qt = q + Pxj^T t1
-      double qv = sm.rec[D::R_Q + r];
-      if (r < 6 || r >= 9) { const int xc = xcol(r); for (int l = 0; l < NJ; ++l) qv += Pxj[l * NXA + xc] * sm.t1[l]; }
-      sm.qt[r] = qv;
-    }
-    if (tid >= 32 && tid < 32 + MP) {   // rt
-      const int c = tid - 32; const int rc = sm.redcol[c];
+    for (int i = tid; i < MP * NX; i += WS_THREADS) {   // H <- Pt (null rows only)
+      const int r = i / NX, c = i % NX;
       double a = 0.0;
-      if (rc < 1000) { if (rc >= 0) a = sm.rec[D::R_R + rc]; else { const int t = -rc - 1; for (int l = 0; l < NJ; ++l) a += Nn[l * 8 + t] * sm.t1[l]; } }
-      sm.rt[c] = a;
-    }
-    for (int i = tid; i < MP * NX; i += WS_THREADS) {   // H <- Pt = Pu^T R Px : only null-space rows, N^T T1
-      const int r = i / NX, c = i % NX; const int rc = sm.redcol[r];
-      double a = 0.0;
-      if (rc < 0 && (c < 6 || c >= 9)) { const int t = -rc - 1, xc = xcol(c); for (int l = 0; l < NJ; ++l) a += Nn[l * 8 + t] * sm.T1[l * LD + xc]; }
+      const int t = r - 3 * nclosed;
+      if (t >= 0 && t < mj && (c < 6 || c >= 9)) a = sr[S::S_PT + t * NXA + xcol(c)];
       sm.H[r * LD + c] = a;
     }
-    for (int i = tid; i < MP * MP; i += WS_THREADS) {   // G <- Rt = Pu^T R Pu
-      const int r = i / MP, c = i % MP; const int rr = sm.redcol[r], rc = sm.redcol[c];
+    for (int i = tid; i < MP * MP; i += WS_THREADS) {   // G <- Rt
+      const int r = i / MP, c = i % MP;
       double a = 0.0;
-      if (rr == 1000 || rc == 1000) a = (r == c) ? 1.0 : 0.0;
-      else if (rr >= 0 && rc >= 0) {
-        if (rr / 3 == rc / 3) {   // same contact: diag + barrier block
-          const int cn = rr / 3, p = rr % 3, q = rc % 3;
+      if (r >= m || c >= m) a = (r == c) ? 1.0 : 0.0;
+      else if (r < 3 * nclosed && c < 3 * nclosed) {
+        if (r / 3 == c / 3) {
+          const int cn = (st0 ? 0 : 2) + r / 3, p = r % 3, q = c % 3;
           const int lo = p < q ? p : q, hi = p < q ? q : p;
-          const int idx = lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);
-          a = sm.rec[D::R_HB + 6 * cn + idx];
-          if (p == q) a += dt * M.Rforce[rr] + dr;
+          a = sr[S::S_HB + 6 * cn + (lo == 0 ? hi : (lo == 1 ? 2 + hi : 5))];
+          if (p == q) a += sr[S::S_RD + 3 * cn + p];
         }
-      } else if (rr < 0 && rc < 0) {
-        const int t1i = -rr - 1, t2i = -rc - 1;
-        for (int l = 0; l < NJ; ++l) {
-          double s = dr * Nn[l * 8 + t2i];
-          for (int j = 0; j < NJ; ++j) s += dt * M.Rjoint[l * NJ + j] * Nn[j * 8 + t2i];
-          a += Nn[l * 8 + t1i] * s;
-        }
-      }
+      } else if (r >= 3 * nclosed && c >= 3 * nclosed) a = sr[S::S_RN + (r - 3 * nclosed) * 8 + (c - 3 * nclosed)];
       sm.G[r * LDM + c] = a;
     }
+    if (tid < NX) { sm.bt[tid] = sr[S::S_B + tid]; sm.qt[tid] = sr[S::S_Q + tid]; sm.qd[tid] = sr[S::S_QD + tid]; }
+    if (tid >= 32 && tid < 32 + MP) sm.rt[tid - 32] = sr[S::S_R + tid - 32];
     __syncthreads();
     // ---- phase 2: SA = S At, SB = S Bt, sb = s + S bt
-    gemm_tiles<3, 3, 6, false, false, false, 4>(sm.S, LD, sm.At, LD, sm.SA, LD, warp, lane);
-    gemm_tiles<3, 2, 6, false, false, false, 4>(sm.S, LD, sm.Bt, LDM, sm.SB, LDM, warp, lane);
-    if (tid < NX) { double a = sm.s[tid]; for (int c = 0; c < NX; ++c) a += sm.S[tid * LD + c] * sm.bt[c]; sm.sb[tid] = a; }
+    gemm_tiles<3, 3, 6, false, false, false, false, 4, 0>(sm.S, LD, sm.At, LD, sm.SA, LD, warp, lane);
+    gemm_tiles<3, 2, 6, false, false, false, false, 4, 0>(sm.S, LD, sm.Bt, LDM, sm.SB, LDM, warp, lane);
+    if (tid >= 96 && tid < 96 + NX) { const int r = tid - 96; double a = sm.s[r]; for (int c = 0; c < NX; ++c) a += sm.S[r * LD + c] * sm.bt[c]; sm.sb[r] = a; }
     __syncthreads();
     // ---- phase 3: H += Bt^T SA, G += Bt^T SB, g = rt + Bt^T sb
-    gemm_tiles<2, 3, 6, true, false, true, 4>(sm.Bt, LDM, sm.SA, LD, sm.H, LD, warp, lane);
-    gemm_tiles<2, 2, 6, true, false, true, 4>(sm.Bt, LDM, sm.SB, LDM, sm.G, LDM, warp, lane);
-    if (tid < MP) { double a = sm.rt[tid]; for (int r = 0; r < NX; ++r) a += sm.Bt[r * LDM + tid] * sm.sb[r]; sm.g[tid] = a; }
+    gemm_tiles<2, 3, 6, true, false, true, false, 4, 0>(sm.Bt, LDM, sm.SA, LD, sm.H, LD, warp, lane);
+    gemm_tiles<2, 2, 6, true, false, true, false, 4, 0>(sm.Bt, LDM, sm.SB, LDM, sm.G, LDM, warp, lane);
+    if (tid >= 96 && tid < 96 + MP) { const int c = tid - 96; double a = sm.rt[c]; for (int r = 0; r < NX; ++r) a += sm.Bt[r * LDM + c] * sm.sb[r]; sm.g[c] = a; }
     __syncthreads();
-    // ---- phase 4: Cholesky of G (lower), warp 0
+    // ---- phase 4: warp 0: right-looking Cholesky of G fused with the forward substitution of [H | g];  warps 1-3: S <- At^T SA
     if (warp == 0) {
+      // lane l < MP owns column l of G (lower part) ; lane c < NX owns column c of H ; lane NX owns g
+      double gc[MP], hc[MP];
+#pragma unroll
+      for (int i = 0; i < MP; ++i) { gc[i] = (lane < MP) ? sm.G[i * LDM + lane] : 0.0; hc[i] = (lane < NX) ? sm.H[i * LD + lane] : ((lane == NX) ? sm.g[i] : 0.0); }
+#pragma unroll
       for (int j = 0; j < MP; ++j) {
-        double dj = sm.G[j * LDM + j];
-        for (int kk = 0; kk < j; ++kk) dj -= sm.G[j * LDM + kk] * sm.G[j * LDM + kk];
-        if (!(dj > 0.0)) { if (lane == 0) atomicOr(&d.status[b], 1); dj = 1.0; }
-        const double ljj = sqrt(dj), il = 1.0 / ljj;
-        __syncwarp();
-        if (lane > j && lane < MP) { double a = sm.G[lane * LDM + j]; for (int kk = 0; kk < j; ++kk) a -= sm.G[lane * LDM + kk] * sm.G[j * LDM + kk]; sm.G[lane * LDM + j] = a * il; }
-        if (lane == 0) { sm.G[j * LDM + j] = ljj; sm.linv[j] = il; }
-        __syncwarp();
+        if (j < m) {
+          double* lc = sm.lcol[j & 1];
+          if (lane == j) {
+            double dj = gc[j];
+            if (!(dj > 0.0)) { atomicOr(&d.status[b], 1); dj = 1.0; }
+            const double inv = rsqrt(dj);
+            lc[MP] = inv;
+#pragma unroll
+            for (int i = 0; i < MP; ++i) { const double v = (i == j) ? dj * inv : ((i > j) ? gc[i] * inv : 0.0); lc[i] = v; gc[i] = v; }
+          }
+          __syncwarp();
+          const double inv = lc[MP];
+          const double yj = hc[j] * inv;
+          hc[j] = yj;
+          const double ljl = (lane > j && lane < MP) ? lc[lane] : 0.0;   // L[lane][j]
+#pragma unroll
+          for (int i = 0; i < MP; ++i) if (i > j) { const double lij = lc[i]; hc[i] -= lij * yj; if (lane > j) gc[i] -= lij * ljl; }
+        }
       }
-    }
-    __syncthreads();
-    // ---- phase 5: Kt = -G^-1 H (one thread per column), kt = -G^-1 g
-    if (tid <= NX) {
-      double y[MP];
-      const bool isg = tid == NX;
 #pragma unroll
       for (int i = 0; i < MP; ++i) {
-        double a = isg ? sm.g[i] : sm.H[i * LD + tid];
-#pragma unroll
-        for (int l = 0; l < i; ++l) a -= sm.G[i * LDM + l] * y[l];
-        y[i] = a * sm.linv[i];
+        if (lane < MP) sm.G[i * LDM + lane] = (i >= lane) ? gc[i] : 0.0;
+        if (lane < NX) sm.H[i * LD + lane] = hc[i]; else if (lane == NX) sm.g[i] = hc[i];
       }
-#pragma unroll
-      for (int i = MP - 1; i >= 0; --i) {
-        double a = y[i];
-#pragma unroll
-        for (int l = i + 1; l < MP; ++l) a -= sm.G[l * LDM + i] * y[l];
-        y[i] = a * sm.linv[i];
-      }
-      if (isg) { for (int i = 0; i < MP; ++i) sm.kt[i] = -y[i]; }
-      else { for (int i = 0; i < MP; ++i) sm.Kt[i * LD + tid] = -y[i]; }
-    } else if (tid >= 64) {
-      for (int i = tid - 64; i < MP * 2; i += 64) { sm.Kt[(i >> 1) * LD + NX + (i & 1)] = 0.0; }   // padded columns 22, 23
+    } else {
+      gemm_tiles<3, 3, 6, true, false, false, false, 3, 1>(sm.At, LD, sm.SA, LD, sm.S, LD, warp, lane);
     }
     __syncthreads();
-    // ---- phase 6: S' = Qt + At^T SA + H^T Kt (into S), s' = qt + At^T sb + H^T kt
-    gemm_tiles<3, 3, 6, true, false, false, 4>(sm.At, LD, sm.SA, LD, sm.S, LD, warp, lane);
-    __syncthreads();
-    gemm_tiles<3, 3, 4, true, false, true, 4>(sm.H, LD, sm.Kt, LD, sm.S, LD, warp, lane);
-    if (tid < NX) {
-      double a = sm.qt[tid];
-      for (int r = 0; r < NX; ++r) a += sm.At[r * LD + tid] * sm.sb[r];
-      for (int r = 0; r < MP; ++r) a += sm.H[r * LD + tid] * sm.kt[r];
-      sm.snew[tid] = a;
-      // ghat = qt + Kt^T rt
-      double gh = sm.qt[tid];
-      for (int r = 0; r < MP; ++r) gh += sm.Kt[r * LD + tid] * sm.rt[r];
-      sm.ghat[tid] = gh;
-      // phi = bt + Bt kt
-      double ph = sm.bt[tid];
-      for (int c = 0; c < MP; ++c) ph += sm.Bt[tid * LDM + c] * sm.kt[c];
-      sm.phi[tid] = ph;
+    // ---- phase 5: S -= Y^T Y ; s' = qt + At^T sb - Y^T yg ; write Y, yg, L for the policy kernel
+    gemm_tiles<3, 3, 4, true, false, true, true, 4, 0>(sm.H, LD, sm.H, LD, sm.S, LD, warp, lane);
+    if (tid >= 96 && tid < 96 + NX) {
+      const int c = tid - 96;
+      double a = sm.qt[c];
+      for (int r = 0; r < NX; ++r) a += sm.At[r * LD + c] * sm.sb[r];
+      for (int r = 0; r < MP; ++r) a -= sm.H[r * LD + c] * sm.g[r];
+      sm.snew[c] = a;
     }
+    for (int i = tid; i < MP * NX; i += WS_THREADS) ric[R::K_Y + i] = sm.H[(i / NX) * LD + i % NX];
+    for (int i = tid; i < MP * MP; i += WS_THREADS) ric[R::K_L + i] = sm.G[(i / MP) * LDM + i % MP];
+    if (tid < MP) ric[R::K_YG + tid] = sm.g[tid];
     __syncthreads();
-    // Phi = At + Bt Kt  (into SA: copy At first, At is then reused as the staging buffer of the symmetrised S')
-    for (int i = tid; i < NXP * LD; i += WS_THREADS) sm.SA[i] = sm.At[i];
-    __syncthreads();
-    gemm_tiles<3, 3, 4, false, false, true, 4>(sm.Bt, LDM, sm.Kt, LD, sm.SA, LD, warp, lane);
-    // add Qt = diag(dt Q + dq) + Pxj^T T1 and symmetrise S' (upper triangle staged in At)
+    // ---- phase 6: add Qt and symmetrise (each unordered pair (r, c) is owned by one thread)
     for (int i = tid; i < NX * NX; i += WS_THREADS) {
       const int r = i / NX, c = i % NX;
       if (c < r) continue;
       double a = 0.5 * (sm.S[r * LD + c] + sm.S[c * LD + r]);
-      if (r == c) a += dt * M.Qdiag[r] + dq;
-      if ((r < 6 || r >= 9) && (c < 6 || c >= 9)) { const int xr = xcol(r), xc = xcol(c); for (int l = 0; l < NJ; ++l) a += Pxj[l * NXA + xr] * sm.T1[l * LD + xc]; }
-      sm.At[r * LD + c] = a;
+      if (r == c) a += sm.qd[r];
+      if ((r < 6 || r >= 9) && (c < 6 || c >= 9)) a += sr[S::S_QT + xcol(r) * NXA + xcol(c)];
+      sm.S[r * LD + c] = a; sm.S[c * LD + r] = a;
     }
-    __syncthreads();
-    for (int i = tid; i < NX * NX; i += WS_THREADS) { const int r = i / NX, c = i % NX; sm.S[r * LD + c] = (c >= r) ? sm.At[r * LD + c] : sm.At[c * LD + r]; }
     if (tid < NX) sm.s[tid] = sm.snew[tid];
     __syncthreads();
-    // ---- phase 7: outputs.  K = Px + Pu Kt, kappa = Pe + Pu kt, uff0 = u - K x
-    for (int i = tid; i < NU * NX; i += WS_THREADS) {
-      const int r = i / NX, c = i % NX;
-      double a = 0.0;
+    // the staging buffer of this stage is free again: prefetch stage k-2 into it (TMA, completes on the buffer's mbarrier)
+    if (tid == 0 && k >= 2) { fence_proxy_async(); tma_load_1d(sm.stage[buf], d.stage + (nb + k - 2) * S::SREC, REC_BYTES, &sm.bar[buf]); }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K2b: gains and closed-loop stage maps, one warp per (instance, stage)
+//   Kt = -L^-T Y, kt = -L^-T yg;  K = Px + Pu Kt, kappa = Pe + Pu kt, uff0 = u - K x   ([UPSTREAM] remapProjectedGain / toPrimalSolution)
+//   Phi = At + Bt Kt, phi = bt + Bt kt (forward substitution), ghat = qt + Kt^T rt, misc = rt^T kt (armijoDescentMetric)
+template <int NJ>
+__global__ void __launch_bounds__(128) k_policy_expand(Dev d) {
+  using D = Dims<NJ>; using R = RDims<NJ>; using S = SDims<NJ>;
+  constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, MP = S::MP, WPB = 4;
+  __shared__ double sL[WPB][MP][MP + 1];
+  __shared__ double sKt[WPB][MP][NX + 2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * WPB + warp;
+  const int b = gw / d.NS, k = gw % d.NS;
+  if (b >= d.B) return;
+  const int N = d.n_nodes[b] - 1;
+  if (k >= N) return;
+  const size_t nb = (size_t)b * d.NS;
+  const double* sr = d.stage + (nb + k) * S::SREC;
+  double* ric = d.ric + (nb + k) * R::KREC;
+  double* Kg = d.s_K + (nb + k) * (size_t)(NU * NX);
+  double* uffg = d.s_uff + (nb + k) * NU;
+  const double* meta = sr + S::S_META;
+  if (meta[S::T_TYPE] != 0.0) {   // event stage: K = 0, Phi = I, phi = b
+    for (int i = lane; i < NU; i += 32) { ric[R::K_KAP + i] = 0.0; uffg[i] = 0.0; }
+    for (int i = lane; i < NX; i += 32) { ric[R::K_SPHI + i] = sr[S::S_B + i]; ric[R::K_G + i] = 0.0; }
+    for (int i = lane; i < NX * NX; i += 32) ric[R::K_PHI + i] = (i / NX == i % NX) ? 1.0 : 0.0;
+    for (int i = lane; i < NU * NX; i += 32) Kg[i] = 0.0;
+    if (lane == 0) { ric[R::K_MISC] = 0.0; ric[R::K_MISC + 1] = 1.0; }
+    return;
+  }
+  const int m = (int)meta[S::T_M], mj = (int)meta[S::T_MJ], nclosed = (int)meta[S::T_NCLOSED], mode = (int)meta[S::T_MODE];
+  const double dt = meta[S::T_DT];
+  const bool st0 = leg_in_stance(mode, 0), st1 = leg_in_stance(mode, 1);
+  const double imass = 1.0 / c_model.total_mass;
+  const double* prj = d.proj + (nb + k) * D::PREC;
+  double (*L)[MP + 1] = sL[warp]; double (*Kt)[NX + 2] = sKt[warp];
+  for (int i = lane; i < MP * MP; i += 32) L[i / MP][i % MP] = ric[R::K_L + i];
+  __syncwarp();
+  // back substitution: lane c < NX: column c of Y ; lane NX: yg
+  const bool active = lane <= NX;
+  double z[MP];
+#pragma unroll
+  for (int i = 0; i < MP; ++i) z[i] = active ? (lane < NX ? ric[R::K_Y + i * NX + lane] : ric[R::K_YG + i]) : 0.0;
+#pragma unroll
+  for (int i = MP - 1; i >= 0; --i) {
+    double a = z[i];
+#pragma unroll
+    for (int l = i + 1; l < MP; ++l) a -= L[l][i] * z[l];
+    z[i] = (i < m) ? a / L[i][i] : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < MP; ++i) { z[i] = -z[i]; if (active) Kt[i][lane] = z[i]; }   // Kt[:, c] and kt (column NX)
+  __syncwarp();
+  // Phi / phi : lane c: At[r][c] + sum_j Bt[r][j] z[j]
+  if (active) {
+    const int c = lane;
+    for (int r = 0; r < NX; ++r) {
+      double a;
+      if (c < NX) { a = (r == c) ? 1.0 : 0.0; if (r >= 3 && (c < 6 || c >= 9)) a += sr[S::S_AT + (r - 3) * NXA + xcol(c)]; }
+      else a = sr[S::S_B + r];
+      if (r >= 3) {
+#pragma unroll
+        for (int j = 0; j < MP; ++j) a += sr[S::S_BT + (r - 3) * MP + j] * z[j];
+      } else {
+        for (int cn = 0; cn < nclosed; ++cn) a += dt * imass * z[3 * cn + r];
+      }
+      if (c < NX) ric[R::K_PHI + r * NX + c] = a; else ric[R::K_SPHI + r] = a;
+    }
+    // ghat = qt + Kt^T rt ; misc = rt^T kt
+    double gh = (c < NX) ? sr[S::S_Q + c] : 0.0;
+#pragma unroll
+    for (int j = 0; j < MP; ++j) gh += sr[S::S_R + j] * z[j];
+    if (c < NX) ric[R::K_G + c] = gh; else { ric[R::K_MISC] = gh; ric[R::K_MISC + 1] = 0.0; }
+  }
+  // K / kappa rows, uff0 = u - K x
+  const double xc = (lane < NX) ? d.s_x[(nb + k) * NX + lane] : 0.0;
+  for (int r = 0; r < NU; ++r) {
+    double a = 0.0;
+    if (active) {
       if (r < 12) {
-        const int cn = r / 3;
-        if (st[cn / 2]) { int red = 0; for (int q = 0; q < cn; ++q) if (st[q / 2]) red += 3; a = sm.Kt[(red + r % 3) * LD + c]; }
+        const int cn = r / 3; const bool cl = (cn / 2 == 0) ? st0 : st1;
+        if (cl) { const int red = (st0 ? cn : cn - 2) * 3 + r % 3; a = z[red]; }
+        else if (lane == NX) a = -prj[D::P_FO + r];
       } else {
         const int l = r - 12;
-        if (c < 6 || c >= 9) a = Pxj[l * NXA + xcol(c)];
-        for (int t = 0; t < mj; ++t) a += Nn[l * 8 + t] * sm.Kt[(3 * nclosed + t) * LD + c];
+        if (lane < NX) { if (lane < 6 || lane >= 9) a = prj[D::P_PX + l * NXA + xcol(lane)]; }
+        else a = prj[D::P_PE + l];
+        for (int t = 0; t < mj; ++t) a += prj[D::P_N + l * 8 + t] * z[3 * nclosed + t];
       }
-      Kg[i] = a;
+      if (lane < NX) Kg[r * NX + lane] = a; else ric[R::K_KAP + r] = a;
     }
-    if (tid < NU) {
-      const int r = tid;
-      double a = 0.0;
-      if (r < 12) {
-        const int cn = r / 3;
-        if (st[cn / 2]) { int red = 0; for (int q = 0; q < cn; ++q) if (st[q / 2]) red += 3; a = sm.kt[red + r % 3]; }
-        else a = -sm.rec[D::R_FO + r];
-      } else {
-        const int l = r - 12;
-        a = Pej[l];
-        for (int t = 0; t < mj; ++t) a += Nn[l * 8 + t] * sm.kt[3 * nclosed + t];
-      }
-      ric[R::K_KAP + r] = a;
-    }
-    for (int i = tid; i < NX * NX; i += WS_THREADS) ric[R::K_PHI + i] = sm.SA[(i / NX) * LD + i % NX];
-    if (tid < NX) { ric[R::K_SPHI + tid] = sm.phi[tid]; ric[R::K_G + tid] = sm.ghat[tid]; }
-    if (tid == 0) { double a = 0.0; for (int r = 0; r < MP; ++r) a += sm.rt[r] * sm.kt[r]; ric[R::K_MISC] = a; ric[R::K_MISC + 1] = 0.0; }
-    __syncthreads();
-    // uff0 = u - K x needs the K just written: recompute the rows from shared memory instead of re-reading global
-    if (tid < NU) {
-      const int r = tid;
-      double a = sm.uk[r];
-      for (int c = 0; c < NX; ++c) {
-        double kv = 0.0;
-        if (r < 12) {
-          const int cn = r / 3;
-          if (st[cn / 2]) { int red = 0; for (int q = 0; q < cn; ++q) if (st[q / 2]) red += 3; kv = sm.Kt[(red + r % 3) * LD + c]; }
-        } else {
-          const int l = r - 12;
-          if (c < 6 || c >= 9) kv = Pxj[l * NXA + xcol(c)];
-          for (int t = 0; t < mj; ++t) kv += Nn[l * 8 + t] * sm.Kt[(3 * nclosed + t) * LD + c];
-        }
-        a -= kv * sm.xk[c];
-      }
-      uffg[r] = a;
-    }
-    __syncthreads();
+    double kx = (lane < NX) ? a * xc : 0.0;
+    for (int o = 16; o > 0; o >>= 1) kx += __shfl_xor_sync(0xffffffffu, kx, o);
+    if (lane == 0) uffg[r] = d.s_u[(nb + k) * NU + r] - kx;
   }
 }
 
@@ -947,6 +1079,38 @@ __global__ void k_evaluate_policy(int B, int NS, int ME, const int* n_nodes, con
     uo[(size_t)b * NU + r] = a;
   }
   if (threadIdx.x == 0) mo[b] = ev_mode[(size_t)b * (ME + 1) + lower_bound_d(ev_t + (size_t)b * ME, n_ev[b], tq[b])];
+}
+
+// ------------------------------------------------------------------------------------------------ observation / target helpers (device-resident drivers)
+// Next observation under a perfect model: t0 += dt, x0 = optimized state trajectory interpolated at the new time
+// (what MRT_ROS_Dummy_Loop's policy rollout [UPSTREAM] provides between MPC ticks, without re-integration).
+template <int NJ>
+__global__ void k_shift_observations(int B, int NS, double dt, const int* n_nodes, const double* times, const double* sx, double* t0, double* x0) {
+  constexpr int NX = Dims<NJ>::NX;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double t = t0[b] + dt;
+  interp_vec(times + (size_t)b * NS, sx + (size_t)b * NS * NX, n_nodes[b], NX, t, x0 + (size_t)b * NX);
+  t0[b] = t;
+}
+// TargetTrajectoriesPublisher::cmdVelToTargetTrajectories (bipedal_controllers/src/TargetTrajectoriesPublisher.cpp:76-99) on device
+template <int NJ>
+__global__ void k_cmd_vel_targets(int B, int TP, const double* t0, const double* x0, const double* cmd, double ttt, double com_height, const double* default_joints, double* tgt_t, double* tgt_x) {
+  constexpr int NX = Dims<NJ>::NX;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* x = x0 + (size_t)b * NX; const double* c = cmd + (size_t)b * 4;
+  double sz, cz, sy, cy, sx, cx;
+  sincos(x[9], &sz, &cz); sincos(x[10], &sy, &cy); sincos(x[11], &sx, &cx);
+  const double R[9] = {cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx, sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx, -sy, cy * sx, cy * cx};
+  const double vr[3] = {R[0] * c[0] + R[1] * c[1] + R[2] * c[2], R[3] * c[0] + R[4] * c[1] + R[5] * c[2], R[6] * c[0] + R[7] * c[1] + R[8] * c[2]};
+  double* s0 = tgt_x + (size_t)b * TP * NX; double* s1 = s0 + NX;
+  for (int i = 0; i < 2 * NX; ++i) s0[i] = 0.0;
+  s0[0] = s1[0] = vr[0]; s0[1] = s1[1] = vr[1]; s0[2] = s1[2] = vr[2];
+  s0[6] = x[6]; s0[7] = x[7]; s0[8] = com_height; s0[9] = x[9];
+  s1[6] = x[6] + vr[0] * ttt; s1[7] = x[7] + vr[1] * ttt; s1[8] = com_height; s1[9] = x[9] + c[3] * ttt;
+  for (int j = 0; j < NJ; ++j) { s0[12 + j] = default_joints[j]; s1[12 + j] = default_joints[j]; }
+  tgt_t[(size_t)b * TP] = t0[b]; tgt_t[(size_t)b * TP + 1] = t0[b] + ttt;
 }
 
 }  // namespace bmpc

@@ -67,7 +67,7 @@ def load_library(path: str | None = None):
     L.bmpc_get_stream.restype = C.c_void_p
     L.bmpc_get_stream.argtypes = [C.c_void_p]
     for name in ("bmpc_get_dims", "bmpc_get_initial_state", "bmpc_export_model", "bmpc_reset", "bmpc_set_observations", "bmpc_set_observations_device",
-                 "bmpc_set_target_trajectories", "bmpc_set_target_trajectories_device", "bmpc_set_targets_from_cmd_vel", "bmpc_set_mode_schedules",
+                 "bmpc_set_target_trajectories", "bmpc_set_target_trajectories_device", "bmpc_set_targets_from_cmd_vel", "bmpc_set_targets_from_cmd_vel_device", "bmpc_shift_observations", "bmpc_get_observations", "bmpc_set_mode_schedules",
                  "bmpc_set_mode_schedules_device", "bmpc_gait_insert", "bmpc_gait_insert_named", "bmpc_use_gait_schedule", "bmpc_gait_peek",
                  "bmpc_advance", "bmpc_advance_async", "bmpc_synchronize", "bmpc_get_policy", "bmpc_get_device_view", "bmpc_get_performance",
                  "bmpc_get_status", "bmpc_evaluate_policy", "bmpc_get_launch_count", "bmpc_get_phase_times", "bmpc_enable_phase_timing",
@@ -166,6 +166,18 @@ class BatchedMpcMrtInterface:
     def setTargetsFromCmdVel(self, cmd, time_to_target):
         cmd = _d(np.broadcast_to(cmd, (self.batch, 4)))
         self._ck(self.L.bmpc_set_targets_from_cmd_vel(self.h, _p(cmd), C.c_double(time_to_target)))
+
+    def setTargetsFromCmdVelDevice(self, cmd_ptr: int, time_to_target: float):
+        self._ck(self.L.bmpc_set_targets_from_cmd_vel_device(self.h, C.c_void_p(cmd_ptr), C.c_double(time_to_target)))
+
+    def shiftObservations(self, dt: float):
+        """t0 += dt, x0 = optimized state at the new time (device side, perfect-model closed loop)."""
+        self._ck(self.L.bmpc_shift_observations(self.h, C.c_double(dt)))
+
+    def getObservations(self):
+        t, x = np.zeros(self.batch), np.zeros((self.batch, self.nx))
+        self._ck(self.L.bmpc_get_observations(self.h, _p(t), _p(x)))
+        return t, x
 
     def setModeSchedule(self, event_times, mode_sequence, n_events=None):
         """event_times [B, stride] (or [stride] for all), mode_sequence [B, stride+1]; n_events[B] optional."""

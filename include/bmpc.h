@@ -83,6 +83,14 @@ int bmpc_set_target_trajectories_device(bmpc_handle* h, int npts, const double* 
  * builds the 2-knot targets from the current observations and cmd[B*4] = (vx, vy, vz, yaw rate); host side. */
 int bmpc_set_targets_from_cmd_vel(bmpc_handle* h, const double* cmd, double time_to_target);
 
+int bmpc_set_targets_from_cmd_vel_device(bmpc_handle* h, const double* cmd_dev, double time_to_target); /* same, observations and cmd in HBM */
+
+/* Closed-loop driver for device-resident batches: t0 += dt and x0 = optimized state trajectory of the current policy
+ * interpolated at the new time (perfect-model stand-in for the MRT_ROS_Dummy_Loop rollout [UPSTREAM] that
+ * ocs2_bipedal_robot_ros/src/BipedalRobotDummyNode.cpp:72-86 runs between MPC ticks).  bmpc_get_observations reads them back. */
+int bmpc_shift_observations(bmpc_handle* h, double dt);
+int bmpc_get_observations(bmpc_handle* h, double* t, double* x);
+
 /* ReferenceManager::setModeSchedule [UPSTREAM]: explicit ModeSchedule per instance; n_events[B],
  * event_times[B*stride], mode_sequence[B*(stride+1)] (mode ids: 0 FLY, 1 LF, 2 RF, 3 STANCE;
  * gait/MotionPhaseDefinition.h:47-52).  Disables the internal GaitSchedule for the next solves. */

@@ -12,6 +12,7 @@ thread_local std::string g_err;
 struct Batch {
   std::vector<std::unique_ptr<Solver>> s;
   std::vector<double> t0; std::vector<std::vector<double>> x0;
+  std::vector<std::array<double, 4>> cmd; std::vector<char> has_cmd; double ttt = 1.0;
 };
 }  // namespace
 
@@ -223,19 +224,33 @@ int orc_riccati(int N, int nx, const int* m, const double* A, const double* B, c
 void* orc_batch_create(const char* model_path, int B) {
   ORC_TRY Model m = load_model(model_path); auto* b = new Batch();
   for (int i = 0; i < B; ++i) b->s.emplace_back(new Solver(m));
-  b->t0.assign(B, 0.0); b->x0.assign(B, m.initial_state); return b; ORC_CATCH(nullptr)
+  b->t0.assign(B, 0.0); b->x0.assign(B, m.initial_state); b->cmd.assign(B, std::array<double, 4>{0, 0, 0, 0}); b->has_cmd.assign(B, 0); return b; ORC_CATCH(nullptr)
 }
 void orc_batch_destroy(void* h) { delete static_cast<Batch*>(h); }
 void* orc_batch_instance(void* h, int i) { return static_cast<Batch*>(h)->s[i].get(); }
 void orc_batch_set_observation(void* h, int i, double t0, const double* x0) { auto* b = static_cast<Batch*>(h); b->t0[i] = t0; b->x0[i].assign(x0, x0 + b->s[i]->M.nx); }
-// runs one tick for instances [first, first+count) on `threads` threads; returns wall seconds, -1 on failure
-double orc_batch_run(void* h, int first, int count, int threads) {
+void orc_batch_set_cmd_vel(void* h, int i, const double* cmd, double ttt) { auto* b = static_cast<Batch*>(h); for (int k = 0; k < 4; ++k) b->cmd[i][k] = cmd[k]; b->has_cmd[i] = 1; b->ttt = ttt; }
+void orc_batch_get_observation(void* h, int i, double* t0, double* x0) { auto* b = static_cast<Batch*>(h); *t0 = b->t0[i]; for (size_t k = 0; k < b->x0[i].size(); ++k) x0[k] = b->x0[i][k]; }
+// runs one tick for instances [first, first+count) on `threads` threads; returns wall seconds, -1 on failure.
+// shift_dt > 0: closed loop under a perfect model: t0 += shift_dt, x0 = previous optimized state at the new time; a cmd_vel target
+// (if set) is rebuilt from the new observation (TargetTrajectoriesPublisher.cpp:76-99) before the solve.
+double orc_batch_run(void* h, int first, int count, int threads, double shift_dt) {
   auto* b = static_cast<Batch*>(h);
   std::atomic<int> next(first); std::atomic<int> fail(0);
   const auto t_begin = std::chrono::steady_clock::now();
   auto work = [&]() {
     for (;;) { const int i = next.fetch_add(1); if (i >= first + count) break;
-      try { b->s[i]->run(b->t0[i], b->x0[i]); if (b->s[i]->info.status != 0) fail++; } catch (...) { fail++; } }
+      try {
+        Solver& S = *b->s[i];
+        if (shift_dt > 0.0 && !S.sol.empty()) {
+          std::vector<double> xo(S.M.nx), uo(S.M.nu); int mode;
+          b->t0[i] += shift_dt;
+          S.evaluatePolicy(b->t0[i], b->x0[i].data(), xo.data(), uo.data(), &mode);
+          b->x0[i] = xo;
+        }
+        if (b->has_cmd[i]) S.P.target = cmd_vel_to_target(S.M, b->t0[i], b->x0[i].data(), b->cmd[i].data(), b->ttt);
+        S.run(b->t0[i], b->x0[i]); if (S.info.status != 0) fail++;
+      } catch (...) { fail++; } }
   };
   std::vector<std::thread> th; for (int t = 1; t < threads; ++t) th.emplace_back(work);
   work(); for (auto& t : th) t.join();

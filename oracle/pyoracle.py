@@ -44,9 +44,12 @@ def lib(path: str | None = None):
     L.orc_batch_instance.restype = C.c_void_p
     L.orc_batch_instance.argtypes = [C.c_void_p, C.c_int]
     L.orc_batch_run.restype = C.c_double
-    L.orc_batch_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.orc_batch_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]
+    L.orc_batch_set_cmd_vel.argtypes = [C.c_void_p, C.c_int, c_dp, C.c_double]
+    L.orc_batch_get_observation.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp]
     L.orc_batch_destroy.argtypes = [C.c_void_p]
     L.orc_batch_set_observation.argtypes = [C.c_void_p, C.c_int, C.c_double, c_dp]
+    L.orc_batch_get_observation.restype = None
     L.orc_total_mass.restype = C.c_double
     L.orc_total_mass.argtypes = [C.c_void_p]
     if path is None:
@@ -333,8 +336,18 @@ class OracleBatch:
         x = _d(x0)
         self.L.orc_batch_set_observation(self.h, C.c_int(i), C.c_double(t0), _p(x))
 
-    def run(self, first=0, count=None, threads=1):
-        sec = self.L.orc_batch_run(self.h, C.c_int(first), C.c_int(self.B - first if count is None else count), C.c_int(threads))
+    def set_cmd_vel(self, i, cmd, time_to_target):
+        c = _d(cmd)
+        self.L.orc_batch_set_cmd_vel(self.h, C.c_int(i), _p(c), C.c_double(time_to_target))
+
+    def get_observation(self, i):
+        t = C.c_double()
+        x = np.zeros(self.inst[i].nx)
+        self.L.orc_batch_get_observation(self.h, C.c_int(i), C.byref(t), _p(x))
+        return t.value, x
+
+    def run(self, first=0, count=None, threads=1, shift_dt=0.0):
+        sec = self.L.orc_batch_run(self.h, C.c_int(first), C.c_int(self.B - first if count is None else count), C.c_int(threads), C.c_double(shift_dt))
         if sec < 0:
             raise RuntimeError("oracle batch run failed")
         return sec

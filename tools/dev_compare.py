@@ -95,7 +95,7 @@ def run(config, ticks=2):
             Pxj = prj[k][:nj * nxa].reshape(nj, nxa)
             Pej = prj[k][nj * nxa:nj * nxa + nj]
             Nn = prj[k][nj * nxa + nj:nj * nxa + nj + nj * 8].reshape(nj, 8)
-            mj = int(prj[k][nj * nxa + nj + nj * 8])
+            mj = int(prj[k][nj * nxa + nj + nj * 8 + 12])
             worst["Px"] = max(worst["Px"], np.abs(Pxj - P["Px"][12:][:, X]).max(), np.abs(P["Px"][12:, 6:9]).max())
             worst["Pe"] = max(worst["Pe"], np.abs(Pej - P["Pe"][12:]).max())
             Pu_j = P["Pu"][12:, :]
