@@ -78,7 +78,7 @@ def workload(kind, batch, rank=0):
         NE = np.zeros(batch, dtype=np.int32)
         for b in range(batch):
             TT[b], TS[b] = helpers.cmd_vel_target(X0[b], 0.0, cmd[b], 1.0, mdl["com_height"], dj)
-            et, ms = helpers.tiled_schedule(gait[b], phase[b], t_hi=4.2)
+            et, ms = helpers.tiled_schedule(gait[b], phase[b], t_hi=3.6)
             NE[b] = len(et)
             ET[b, :len(et)] = et
             MS[b, :len(ms)] = ms

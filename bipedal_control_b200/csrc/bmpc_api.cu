@@ -255,6 +255,16 @@ int bmpc_export_model(const bmpc_handle* h, const char* path) {
   API_BEGIN if (!h || !path) throw std::invalid_argument("[bmpc] null argument"); save_compact_model(h->model, path); return BMPC_OK; API_END(hh)
 }
 
+// host-only: ingest the reference's own files and write the compact model file (no GPU needed)
+int bmpc_convert_model(const char* task_file, const char* reference_file, const char* gait_file, const char* urdf_file, const char* out_path) {
+  try {
+    if (!task_file || !reference_file || !urdf_file || !out_path) throw std::invalid_argument("[bmpc] null argument");
+    HostModel m = load_reference_files(task_file, reference_file, gait_file ? gait_file : "", urdf_file);
+    save_compact_model(m, out_path);
+    return BMPC_OK;
+  } catch (const std::exception& e) { return fail(nullptr, BMPC_ERR_INVALID, e.what()); }
+}
+
 int bmpc_reset(bmpc_handle* h) {
   API_BEGIN if (!h) return BMPC_ERR_INVALID;
   CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream));

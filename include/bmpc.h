@@ -65,6 +65,9 @@ const char* bmpc_last_error(const bmpc_handle* h); /* h may be NULL: error of th
 int bmpc_get_dims(const bmpc_handle* h, int* nx, int* nu, int* batch, int* max_nodes);
 int bmpc_get_initial_state(const bmpc_handle* h, double* x /* nx */);      /* task.info `initialState` */
 int bmpc_export_model(const bmpc_handle* h, const char* path);             /* writes the compact model file */
+/* host-only tool: reads task.info / reference.info / gait.info (may be NULL) / URDF exactly as BipedalRobotInterface does
+ * (BipedalRobotInterface.cpp:67-204) and writes the compact model file; needs no GPU */
+int bmpc_convert_model(const char* task_file, const char* reference_file, const char* gait_file, const char* urdf_file, const char* out_path);
 
 /* MPC_MRT_Interface::reset / resetMpcNode (BipedalController.cpp:147-148): drops the warm start of all instances */
 int bmpc_reset(bmpc_handle* h);

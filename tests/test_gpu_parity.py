@@ -1,0 +1,247 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI, against the CPU oracle.
+
+Tolerances (FP64 end to end): 1e-8 relative on trajectories / gains / performance indices for identical linearisation
+points (far inside the north star's 1e-4 on cost and constraint residuals); closed-loop sequences of several ticks
+accumulate rounding through re-linearisation and are held to 1e-6.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MODEL = os.path.join(ROOT, "configs", "h1.model")
+REL = 1e-8
+
+
+def _gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from bipedal_control_b200 import BatchedMpcMrtInterface
+    return BatchedMpcMrtInterface
+
+
+def _mdl():
+    from tools.ingest import read_model
+    return read_model(MODEL)
+
+
+def _close(a, b, rel=REL, what=""):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = max(1.0, np.abs(b).max())
+    err = np.abs(a - b).max()
+    assert err <= rel * scale, f"{what}: max|diff| {err:.3e} > {rel:.0e} * {scale:.3e}"
+
+
+def _compare_tick(g, o, inst, rel=REL):
+    pol = g.getPolicy(inst, 1)
+    so, io = o.solution(), o.info()
+    n = int(pol["n_nodes"][0])
+    assert n == len(so["t"])
+    _close(pol["t"][0][:n], so["t"], 1e-14, "node times")
+    assert list(pol["events"][0][:n]) == list(so["events"])
+    perf = g.getPerformanceIndices()[inst]
+    _close(perf[0:3], io["before"], rel, "performance before")
+    _close(perf[3:6], io["after"], rel, "performance after")
+    assert perf[6] == io["step"]
+    _close(perf[7], io["armijo"], rel, "armijo descent metric")
+    _close(pol["x"][0][:n], so["x"], rel, "x")
+    _close(pol["u"][0][:n], so["u"], rel, "u")
+    _close(pol["uff"][0][:n], so["uff"], rel, "uff")
+    _close(pol["K"][0][:n], so["K"], rel, "K")
+    return pol, so
+
+
+def test_config1_stance_plumbing(oracle_h1):
+    """BASELINE configs[0]: H1 'stance', N = 20, dt 0.015, batch 1, cold start then a warm tick."""
+    G = _gpu()
+    o = oracle_h1
+    x0 = o.initial_state()
+    o.reset(); o.set_dt_horizon(0.015, 0.3); o.set_mode_schedule([-1.0, 5.0], [3, 3, 3]); o.set_target([0.0, 1.0], [x0, x0])
+    g = G(1, model_file=MODEL, dt=0.015, time_horizon=0.3)
+    g.setCurrentObservation(0.0, x0); g.setTargetTrajectories([0.0, 1.0], [x0, x0]); g.setModeSchedule([-1.0, 5.0], [3, 3, 3])
+    for _ in range(2):
+        o.run(0.0, x0); g.advanceMpc()
+        assert g.getStatus()[0] == 0
+        pol, so = _compare_tick(g, o, 0)
+        assert pol["n_nodes"][0] == 21
+    xo, uo, mo = o.evaluate_policy(0.007, x0 + 0.01)
+    xg, ug, mg = g.evaluatePolicy(0.007, x0 + 0.01)
+    _close(xg[0], xo, REL, "evaluatePolicy x"); _close(ug[0], uo, REL, "evaluatePolicy u"); assert mg[0] == mo == 3
+    g.close()
+
+
+def test_config2_trot_identical_instances(oracle_h1):
+    """BASELINE configs[1] at full size: all 4096 outputs bit-identical to each other, instance 0 within tolerance of the oracle."""
+    import helpers
+    G = _gpu()
+    m = _mdl()
+    o = oracle_h1
+    x0 = o.initial_state()
+    et, ms = helpers.config2(o.nx, x0, None, None)
+    tt, ts = helpers.cmd_vel_target(x0, 0.0, (0.3, 0, 0, 0), 1.0, m["com_height"], m["default_joint_state"])
+    o.reset(); o.set_dt_horizon(0.01, 1.0); o.set_mode_schedule(et, ms); o.set_target(tt, ts)
+    B = 4096
+    g = G(B, model_file=MODEL, dt=0.01, time_horizon=1.0)
+    g.setCurrentObservation(0.0, x0); g.setTargetTrajectories(tt, ts); g.setModeSchedule(et, ms)
+    for tick in range(2):
+        o.run(0.0, x0); g.advanceMpc()
+        assert not g.getStatus().any()
+        pol, so = _compare_tick(g, o, 0)
+        assert pol["n_nodes"][0] == 104   # 100 intervals + 3 event nodes + terminal
+    # bit-identical across the batch (checks every wave of CTAs, not only the first 148 x occupancy instances)
+    perf = g.getPerformanceIndices()
+    assert (perf == perf[0]).all()
+    for first in (1, 700, 2047, 4095):
+        p = g.getPolicy(first, 1)
+        for k in ("x", "u", "uff", "K"):
+            assert np.array_equal(p[k][0], pol[k][0]), k
+    g.close()
+
+
+def test_config3_randomized_divergent_modes(h1_model_path):
+    """BASELINE configs[2] distributions (seed 0): divergent contact modes incl. FLY, non-zero momentum (inconsistent stance-foot rows)."""
+    import helpers
+    from oracle.pyoracle import Oracle
+    G = _gpu()
+    m = _mdl()
+    nj = m["nj"]
+    lo = np.array([m[f"joint{j}_limits"][0] for j in range(nj)]); hi = np.array([m[f"joint{j}_limits"][1] for j in range(nj)])
+    B = 640   # more than one wave of CTAs on 148 SMs
+    X0, cmd, gait, phase = helpers.randomized_instances(B, np.asarray(m["initial_state"]), np.asarray(m["default_joint_state"]), lo, hi, seed=0)
+    ME = 40
+    ET, MS, NE = np.zeros((B, ME)), np.zeros((B, ME + 1), dtype=np.int32), np.zeros(B, dtype=np.int32)
+    TT, TS = np.zeros((B, 2)), np.zeros((B, 2, 12 + nj))
+    for b in range(B):
+        et, ms = helpers.tiled_schedule(gait[b], phase[b], t_hi=3.0)
+        NE[b] = len(et); ET[b, :len(et)] = et; MS[b, :len(ms)] = ms
+        TT[b], TS[b] = helpers.cmd_vel_target(X0[b], 0.0, cmd[b], 1.0, m["com_height"], m["default_joint_state"])
+    g = G(B, model_file=MODEL, dt=0.01, time_horizon=1.0)
+    g.setCurrentObservation(np.zeros(B), X0); g.setTargetTrajectories(TT, TS); g.setModeSchedule(ET, MS, NE)
+    check = [0, 1, 2, 3, 5, 8, 13, 100, 333, 600, 639]
+    assert {"trot", "standing_trot", "flying_trot", "stance"} <= set(gait[check].tolist() + gait[:40].tolist())
+    oracles = {}
+    for b in check:
+        o = Oracle(h1_model_path)
+        o.set_dt_horizon(0.01, 1.0); o.set_mode_schedule(ET[b, :NE[b]], MS[b, :NE[b] + 1]); o.set_target(TT[b], TS[b])
+        oracles[b] = o
+    for tick in range(2):
+        g.advanceMpc()
+        st = g.getStatus()
+        assert not (st & ~16).any()
+        for b in check:
+            oracles[b].run(0.0, X0[b])
+            _compare_tick(g, oracles[b], b, rel=1e-7 if tick else REL)
+    g.close()
+
+
+def test_closed_loop_shift_and_gait_schedule(h1_model_path):
+    """Several closed-loop ticks (t0 += 1/50 s, x0 from the policy) with the library's GaitSchedule bookkeeping, vs the oracle."""
+    import helpers
+    from oracle.pyoracle import OracleBatch
+    G = _gpu()
+    m = _mdl()
+    B = 3
+    g = G(B, model_file=MODEL, dt=0.015, time_horizon=1.0)
+    ob = OracleBatch(h1_model_path, B)
+    cmds = np.array([[0.3, 0.0, 0.0, 0.0], [0.0, 0.1, 0.0, 0.2], [-0.2, 0.0, 0.0, -0.1]])
+    x0 = g.initialState()
+    gaits = ["trot", "flying_trot", "standing_trot"]
+    for b in range(B):
+        modes, times = helpers.GAITS[gaits[b]]
+        g.insertGait((modes, times), 1.0, 2.0, instance=b)          # GaitReceiver inserts the new gait at the end of the horizon
+        ob.inst[b].gait_insert(modes, times, 1.0, 2.0)
+        ob.inst[b].use_gait_schedule()
+        ob.set_observation(b, 0.0, x0); ob.set_cmd_vel(b, cmds[b], 1.0)
+    g.useGaitSchedule(True)
+    t = np.zeros(B); X = np.tile(x0, (B, 1))
+    for tick in range(8):
+        g.setCurrentObservation(t, X); g.setTargetsFromCmdVel(cmds, 1.0)
+        g.advanceMpc()
+        ob.run(threads=1, shift_dt=0.0 if tick == 0 else 0.05)
+        assert not (g.getStatus() & ~16).any()
+        for b in range(B):
+            _compare_tick(g, ob.inst[b], b, rel=1e-6)
+            eg, mg = g.gaitPeek(b); eo, mo = ob.inst[b].gait_peek()
+            np.testing.assert_allclose(eg, eo, atol=1e-12); assert list(mg) == list(mo)
+        # next observation: the optimized state 0.05 s ahead (device-side shift == host-side evaluatePolicy == oracle)
+        xo, _, _ = g.evaluatePolicy(t + 0.05, X)
+        g.shiftObservations(0.05)
+        t2, X2 = g.getObservations()
+        np.testing.assert_allclose(t2, t + 0.05); np.testing.assert_allclose(X2, xo, atol=1e-14)
+        for b in range(B):
+            xb, _, _ = ob.inst[b].evaluate_policy(t[b] + 0.05, X[b])
+            _close(X2[b], xb, 1e-6, "shifted observation")
+        t, X = t2, X2
+    g.close()
+
+
+def test_device_resident_inputs_match_host_inputs():
+    """The *_device entry points (inputs already in HBM) give bit-identical results to the host entry points."""
+    import torch
+    import helpers
+    G = _gpu()
+    m = _mdl()
+    B = 64
+    x0 = np.asarray(m["initial_state"])
+    et, ms = helpers.config2(22, x0, None, None)
+    cmd = np.tile([0.3, 0.0, 0.0, 0.1], (B, 1))
+    ga = G(B, model_file=MODEL, dt=0.01, time_horizon=0.5); gb = G(B, model_file=MODEL, dt=0.01, time_horizon=0.5)
+    ga.setCurrentObservation(0.0, x0); ga.setTargetsFromCmdVel(cmd, 1.0); ga.setModeSchedule(et, ms); ga.advanceMpc()
+    dev = torch.device("cuda", 0)
+    d_t = torch.zeros(B, dtype=torch.float64, device=dev); d_x = torch.tensor(np.tile(x0, (B, 1)), device=dev); d_c = torch.tensor(cmd, device=dev)
+    d_ne = torch.full((B,), len(et), dtype=torch.int32, device=dev)
+    d_et = torch.tensor(np.tile(et, (B, 1)), device=dev); d_ms = torch.tensor(np.tile(ms, (B, 1)), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    gb.setCurrentObservationDevice(d_t.data_ptr(), d_x.data_ptr()); gb.setTargetsFromCmdVelDevice(d_c.data_ptr(), 1.0)
+    gb.setModeScheduleDevice(len(et), d_ne.data_ptr(), d_et.data_ptr(), d_ms.data_ptr()); gb.advanceMpc()
+    pa, pb = ga.getPolicy(), gb.getPolicy()
+    for k in ("x", "u", "uff", "K", "t"):
+        assert np.array_equal(pa[k], pb[k]), k
+    ga.close(); gb.close()
+
+
+def test_error_paths():
+    G = _gpu()
+    from bipedal_control_b200 import BmpcError
+    with pytest.raises(BmpcError):
+        G(4, model_file="/nonexistent.model")
+    g = G(2, model_file=MODEL, dt=0.01, time_horizon=0.2)
+    with pytest.raises(BmpcError):
+        g.advanceMpc()                       # targets / schedules not set
+    with pytest.raises(BmpcError):
+        g.getPolicy()                        # no solution yet
+    x0 = g.initialState()
+    g.setCurrentObservation(0.0, x0); g.setTargetTrajectories([0.0], [x0])
+    # a swing phase without a lift-off time: the reference throws (SwingTrajectoryPlanner.cpp:191-212); here a status bit is raised
+    g.setModeSchedule([0.05], [1, 3])
+    g.advanceMpc()
+    assert (g.getStatus() & 4).all()
+    g.close()
+
+
+def test_line_search_rejects_and_halves(oracle_h1):
+    """A far-off initial state forces alpha < 1 for the first tick; the accepted step size must match the oracle's."""
+    import helpers
+    G = _gpu()
+    m = _mdl()
+    o = oracle_h1
+    x0 = o.initial_state().copy()
+    x0[8] -= 0.25; x0[10] += 0.5; x0[0:3] = [1.5, -1.0, 0.8]; x0[14] -= 0.6
+    et, ms = helpers.config2(22, x0, None, None)
+    tt, ts = helpers.cmd_vel_target(o.initial_state(), 0.0, (0.5, 0, 0, 0), 1.0, m["com_height"], m["default_joint_state"])
+    o.reset(); o.set_dt_horizon(0.01, 0.6); o.set_mode_schedule(et, ms); o.set_target(tt, ts)
+    g = G(2, model_file=MODEL, dt=0.01, time_horizon=0.6)
+    g.setCurrentObservation(0.0, x0); g.setTargetTrajectories(tt, ts); g.setModeSchedule(et, ms)
+    steps = []
+    for _ in range(3):
+        o.run(0.0, x0); g.advanceMpc()
+        perf = g.getPerformanceIndices()[0]
+        assert perf[6] == o.info()["step"]
+        steps.append(perf[6])
+        _close(perf[3:6], o.info()["after"], 1e-7, "performance after")
+    g.close()
+    o.reset()
