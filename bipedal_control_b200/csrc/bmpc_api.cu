@@ -111,6 +111,7 @@ void tick(bmpc_handle* h) {
   k_node_setup<NJ><<<(nodes + 127) / 128, 128, 0, st>>>(d); ++h->launches;
   mark(1);
   CK(cudaFuncSetAttribute(k_riccati<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem<NJ>)));
+  CK(cudaFuncSetAttribute(k_policy_expand<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(PolSmem<NJ>))));
   h->linesearch_trials = 0;
   for (int iter = 0; iter < h->sqp_iterations; ++iter) {
     k_lq<NJ><<<(nodes + 63) / 64, 64, 0, st>>>(d); ++h->launches;
@@ -118,7 +119,7 @@ void tick(bmpc_handle* h) {
     k_project<NJ><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches;
     if (iter == 0) mark(3);
     k_riccati<NJ><<<B, WS_THREADS, sizeof(RicSmem<NJ>), st>>>(d); ++h->launches;
-    k_policy_expand<NJ><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches;
+    k_policy_expand<NJ><<<(nodes + 3) / 4, 128, 4 * sizeof(PolSmem<NJ>), st>>>(d); ++h->launches;
     if (iter == 0) mark(4);
     k_forward<NJ><<<(B + 3) / 4, 128, 0, st>>>(d); ++h->launches;
     if (iter == 0) mark(5);

@@ -16,6 +16,9 @@ namespace bmpc {
 
 constexpr double WEAK_EPS = 1e-6;   // [UPSTREAM] numeric_traits::weakEpsilon
 constexpr int WS_THREADS = 128;     // threads per CTA of the Riccati kernel (one instance per CTA)
+#ifndef LQ_MIN_BLOCKS
+#define LQ_MIN_BLOCKS 8
+#endif
 
 template <int NJ> struct RDims;
 template <int NJ> struct SDims;
@@ -178,7 +181,7 @@ __global__ void k_node_setup(Dev d) {
 
 // ------------------------------------------------------------------------------------------------ K1: LQ approximation, one thread per (instance, stage)
 template <int NJ>
-__global__ void __launch_bounds__(64) k_lq(Dev d) {
+__global__ void __launch_bounds__(64, LQ_MIN_BLOCKS) k_lq(Dev d) {
   using D = Dims<NJ>;
   constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -356,6 +359,7 @@ __global__ void __launch_bounds__(128) k_project(Dev d) {
   __shared__ double sPx[WPB][NJ][NXA + 1];   // [Pxj | Pej]
   __shared__ double sN[WPB][NJ][8];
   __shared__ double sRN[WPB][NJ][8];         // Rj_eff N
+  __shared__ double sBd[WPB][9 * (12 + NJ)];  // B_d rows 3..11 (read many times with warp-uniform indices)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * WPB + warp;
   const int b = gw / d.NS, k = gw % d.NS;
@@ -380,6 +384,7 @@ __global__ void __launch_bounds__(128) k_project(Dev d) {
   for (int i = lane; i < r; i += 32) G[i][NXA] = rec[D::R_EV + i];
   for (int i = lane; i < 10 * NJ; i += 32) V[i / NJ][i % NJ] = 0.0;
   for (int i = lane; i < NJ * 8; i += 32) { Nn[i / 8][i % 8] = 0.0; RN[i / 8][i % 8] = 0.0; }
+  for (int i = lane; i < 9 * NU; i += 32) sBd[warp][i] = rec[D::R_BD + i];
   __syncwarp();
   bool anomaly = false;
   double rmax = 0.0;
@@ -462,7 +467,7 @@ __global__ void __launch_bounds__(128) k_project(Dev d) {
   }
   __syncwarp();
   // ---------------- change of input variables.  y[] = own column of [Pxj | Pej] (lanes <= NXA) or of N (null lanes)
-  const double* Bd = rec + D::R_BD;
+  const double* Bd = sBd[warp];
   // t[] = Rj_eff * (own column)  (+ r_j for the Pe column -> t1 = r_j + Rj_eff Pej)
   double tcol[NJ];
   if (is_rhs || is_null) {
@@ -804,22 +809,40 @@ __global__ void __launch_bounds__(WS_THREADS, 4) k_riccati(Dev d) {
 //   Kt = -L^-T Y, kt = -L^-T yg;  K = Px + Pu Kt, kappa = Pe + Pu kt, uff0 = u - K x   ([UPSTREAM] remapProjectedGain / toPrimalSolution)
 //   Phi = At + Bt Kt, phi = bt + Bt kt (forward substitution), ghat = qt + Kt^T rt, misc = rt^T kt (armijoDescentMetric)
 template <int NJ>
-__global__ void __launch_bounds__(128) k_policy_expand(Dev d) {
-  using D = Dims<NJ>; using R = RDims<NJ>; using S = SDims<NJ>;
+struct PolSmem {
+  static constexpr int NX = Dims<NJ>::NX, MP = 16;
+  double L[MP][MP + 1];
+  double Kt[MP * 28];            // [Kt | kt | 0], ld 28
+  double P[(12 + NJ) * 25];      // K[r][c] * x[c] (row sums give K x)
+  double rt[MP], xk[24], Nn[NJ * 8];
+};
+
+// value of the padded operand [At | bt | 0] (24 x 24) at (r, c), read from the compact stage record
+template <int NJ>
+__device__ __forceinline__ double stage_At_aug(const double* __restrict__ sr, int r, int c) {
+  using S = SDims<NJ>; constexpr int NX = Dims<NJ>::NX, NXA = Dims<NJ>::NXA;
+  if (r >= NX) return 0.0;
+  if (c < NX) { double a = (r == c) ? 1.0 : 0.0; if (r >= 3 && (c < 6 || c >= 9)) a += sr[S::S_AT + (r - 3) * NXA + xcol(c)]; return a; }
+  return c == NX ? sr[S::S_B + r] : 0.0;
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(128, 4) k_policy_expand(Dev d) {
+  using D = Dims<NJ>; using R = RDims<NJ>; using S = SDims<NJ>; using PS = PolSmem<NJ>;
   constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, MP = S::MP, WPB = 4;
-  __shared__ double sL[WPB][MP][MP + 1];
-  __shared__ double sKt[WPB][MP][NX + 2];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  PS& sm = reinterpret_cast<PS*>(smem_raw)[warp];
   const int gw = blockIdx.x * WPB + warp;
   const int b = gw / d.NS, k = gw % d.NS;
   if (b >= d.B) return;
   const int N = d.n_nodes[b] - 1;
   if (k >= N) return;
   const size_t nb = (size_t)b * d.NS;
-  const double* sr = d.stage + (nb + k) * S::SREC;
-  double* ric = d.ric + (nb + k) * R::KREC;
-  double* Kg = d.s_K + (nb + k) * (size_t)(NU * NX);
-  double* uffg = d.s_uff + (nb + k) * NU;
+  const double* __restrict__ sr = d.stage + (nb + k) * S::SREC;
+  double* __restrict__ ric = d.ric + (nb + k) * R::KREC;
+  double* __restrict__ Kg = d.s_K + (nb + k) * (size_t)(NU * NX);
+  double* __restrict__ uffg = d.s_uff + (nb + k) * NU;
   const double* meta = sr + S::S_META;
   if (meta[S::T_TYPE] != 0.0) {   // event stage: K = 0, Phi = I, phi = b
     for (int i = lane; i < NU; i += 32) { ric[R::K_KAP + i] = 0.0; uffg[i] = 0.0; }
@@ -833,66 +856,113 @@ __global__ void __launch_bounds__(128) k_policy_expand(Dev d) {
   const double dt = meta[S::T_DT];
   const bool st0 = leg_in_stance(mode, 0), st1 = leg_in_stance(mode, 1);
   const double imass = 1.0 / c_model.total_mass;
-  const double* prj = d.proj + (nb + k) * D::PREC;
-  double (*L)[MP + 1] = sL[warp]; double (*Kt)[NX + 2] = sKt[warp];
-  for (int i = lane; i < MP * MP; i += 32) L[i / MP][i % MP] = ric[R::K_L + i];
-  __syncwarp();
-  // back substitution: lane c < NX: column c of Y ; lane NX: yg
+  const double* __restrict__ prj = d.proj + (nb + k) * D::PREC;
+  const int lr = lane >> 2, lc = lane & 3;
+  // ---- issue every global load up front (independent: their latency overlaps with the back substitution below)
   const bool active = lane <= NX;
   double z[MP];
 #pragma unroll
   for (int i = 0; i < MP; ++i) z[i] = active ? (lane < NX ? ric[R::K_Y + i * NX + lane] : ric[R::K_YG + i]) : 0.0;
+  double lreg[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) lreg[i] = ric[R::K_L + lane + 32 * i];
+  // accumulators of the 9 output tiles initialised with [At | bt | 0]; A fragments of Bt (24 x 16)
+  double c0[9], c1[9], af[3][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) { const int r = 8 * (t / 3) + lr, c = 8 * (t % 3) + 2 * lc; c0[t] = stage_At_aug<NJ>(sr, r, c); c1[t] = stage_At_aug<NJ>(sr, r, c + 1); }
+#pragma unroll
+  for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int r = 8 * mt + lr, c = 4 * kk + lc;
+      double a = 0.0;
+      if (r >= 3 && r < NX) a = sr[S::S_BT + (r - 3) * MP + c]; else if (r < 3 && c < 3 * nclosed) a = (c % 3 == r) ? dt * imass : 0.0;
+      af[mt][kk] = a;
+    }
+  const double rt_l = (lane < MP) ? sr[S::S_R + lane] : 0.0;
+  const double xk_l = (lane < NX) ? d.s_x[(nb + k) * NX + lane] : 0.0;
+  const double qt_l = (lane < NX) ? sr[S::S_Q + lane] : 0.0;
+  double nn[(NJ * 8 + 31) / 32];
+#pragma unroll
+  for (int i = 0; i < (NJ * 8 + 31) / 32; ++i) nn[i] = (lane + 32 * i < NJ * 8) ? prj[D::P_N + lane + 32 * i] : 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const int e = lane + 32 * i; sm.L[e / MP][e % MP] = lreg[i]; }
+  if (lane < MP) sm.rt[lane] = rt_l;
+  if (lane < 24) sm.xk[lane] = xk_l;
+#pragma unroll
+  for (int i = 0; i < (NJ * 8 + 31) / 32; ++i) if (lane + 32 * i < NJ * 8) sm.Nn[lane + 32 * i] = nn[i];
+  __syncwarp();
+  // ---- back substitution Kt = -L^-T Y (lane c < NX: column c; lane NX: kt from yg)
 #pragma unroll
   for (int i = MP - 1; i >= 0; --i) {
     double a = z[i];
 #pragma unroll
-    for (int l = i + 1; l < MP; ++l) a -= L[l][i] * z[l];
-    z[i] = (i < m) ? a / L[i][i] : 0.0;
+    for (int l = i + 1; l < MP; ++l) a -= sm.L[l][i] * z[l];
+    z[i] = (i < m) ? a / sm.L[i][i] : 0.0;
   }
 #pragma unroll
-  for (int i = 0; i < MP; ++i) { z[i] = -z[i]; if (active) Kt[i][lane] = z[i]; }   // Kt[:, c] and kt (column NX)
+  for (int i = 0; i < MP; ++i) { z[i] = -z[i]; if (lane < 28) sm.Kt[i * 28 + lane] = z[i]; }
   __syncwarp();
-  // Phi / phi : lane c: At[r][c] + sum_j Bt[r][j] z[j]
-  if (active) {
-    const int c = lane;
-    for (int r = 0; r < NX; ++r) {
-      double a;
-      if (c < NX) { a = (r == c) ? 1.0 : 0.0; if (r >= 3 && (c < 6 || c >= 9)) a += sr[S::S_AT + (r - 3) * NXA + xcol(c)]; }
-      else a = sr[S::S_B + r];
-      if (r >= 3) {
+  // ---- [Phi | phi] = [At | bt] + Bt [Kt | kt] on the FP64 tensor cores: 9 tiles x 4 k-steps, results stored straight from the fragments
 #pragma unroll
-        for (int j = 0; j < MP; ++j) a += sr[S::S_BT + (r - 3) * MP + j] * z[j];
-      } else {
-        for (int cn = 0; cn < nclosed; ++cn) a += dt * imass * z[3 * cn + r];
-      }
-      if (c < NX) ric[R::K_PHI + r * NX + c] = a; else ric[R::K_SPHI + r] = a;
+  for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) dmma884(c0[t], c1[t], af[t / 3][kk], sm.Kt[(4 * kk + lc) * 28 + 8 * (t % 3) + lr]);
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int r = 8 * (t / 3) + lr, c = 8 * (t % 3) + 2 * lc;
+    if (r < NX) {
+      if (c < NX) ric[R::K_PHI + r * NX + c] = c0[t]; else if (c == NX) ric[R::K_SPHI + r] = c0[t];
+      if (c + 1 < NX) ric[R::K_PHI + r * NX + c + 1] = c1[t]; else if (c + 1 == NX) ric[R::K_SPHI + r] = c1[t];
     }
-    // ghat = qt + Kt^T rt ; misc = rt^T kt
-    double gh = (c < NX) ? sr[S::S_Q + c] : 0.0;
-#pragma unroll
-    for (int j = 0; j < MP; ++j) gh += sr[S::S_R + j] * z[j];
-    if (c < NX) ric[R::K_G + c] = gh; else { ric[R::K_MISC] = gh; ric[R::K_MISC + 1] = 0.0; }
   }
-  // K / kappa rows, uff0 = u - K x
-  const double xc = (lane < NX) ? d.s_x[(nb + k) * NX + lane] : 0.0;
-  for (int r = 0; r < NU; ++r) {
-    double a = 0.0;
-    if (active) {
-      if (r < 12) {
-        const int cn = r / 3; const bool cl = (cn / 2 == 0) ? st0 : st1;
-        if (cl) { const int red = (st0 ? cn : cn - 2) * 3 + r % 3; a = z[red]; }
-        else if (lane == NX) a = -prj[D::P_FO + r];
-      } else {
-        const int l = r - 12;
-        if (lane < NX) { if (lane < 6 || lane >= 9) a = prj[D::P_PX + l * NXA + xcol(lane)]; }
-        else a = prj[D::P_PE + l];
-        for (int t = 0; t < mj; ++t) a += prj[D::P_N + l * 8 + t] * z[3 * nclosed + t];
-      }
-      if (lane < NX) Kg[r * NX + lane] = a; else ric[R::K_KAP + r] = a;
+  // ---- ghat = qt + Kt^T rt ; misc = rt^T kt
+  if (active) {
+    double gh = qt_l;
+#pragma unroll
+    for (int j = 0; j < MP; ++j) gh += sm.rt[j] * z[j];
+    if (lane < NX) ric[R::K_G + lane] = gh; else { ric[R::K_MISC] = gh; ric[R::K_MISC + 1] = 0.0; }
+  }
+  // ---- K = Px + Pu Kt, kappa = Pe + Pu kt ; products K[r][c] x[c] staged in shared memory for uff0 = u - K x
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < 12; ++r) {
+      const int cn = r / 3; const bool cl = (cn / 2 == 0) ? st0 : st1;
+      double a = 0.0;
+      if (cl) {
+        const int red = (st0 ? cn : cn - 2) * 3 + r % 3;
+#pragma unroll
+        for (int q = 0; q < 12; ++q) if (q == red) a = z[q];
+      } else if (lane == NX) a = -prj[D::P_FO + r];
+      if (lane < NX) { Kg[r * NX + lane] = a; sm.P[r * 25 + lane] = a * xk_l; } else ric[R::K_KAP + r] = a;
     }
-    double kx = (lane < NX) ? a * xc : 0.0;
-    for (int o = 16; o > 0; o >>= 1) kx += __shfl_xor_sync(0xffffffffu, kx, o);
-    if (lane == 0) uffg[r] = d.s_u[(nb + k) * NU + r] - kx;
+    double zn[8];   // null-space part of the own column
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      zn[t] = 0.0;
+#pragma unroll
+      for (int q = 0; q < MP; ++q) if (q == 3 * nclosed + t && t < mj) zn[t] = z[q];
+    }
+    const bool xact = lane < 6 || (lane >= 9 && lane < NX);
+    const int xc = xcol(lane);
+    double pxv[NJ];
+#pragma unroll
+    for (int l = 0; l < NJ; ++l) pxv[l] = (lane < NX) ? (xact ? prj[D::P_PX + l * NXA + xc] : 0.0) : prj[D::P_PE + l];
+#pragma unroll
+    for (int l = 0; l < NJ; ++l) {
+      double a = pxv[l];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) a += sm.Nn[l * 8 + t] * zn[t];
+      const int r = 12 + l;
+      if (lane < NX) { Kg[r * NX + lane] = a; sm.P[r * 25 + lane] = a * xk_l; } else ric[R::K_KAP + r] = a;
+    }
+  }
+  __syncwarp();
+  if (lane < NU) {
+    double kx = 0.0;
+#pragma unroll
+    for (int c = 0; c < NX; ++c) kx += sm.P[lane * 25 + c];
+    uffg[lane] = d.s_u[(nb + k) * NU + lane] - kx;
   }
 }
 
