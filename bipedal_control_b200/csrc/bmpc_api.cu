@@ -54,10 +54,10 @@ struct bmpc_handle {
   double *s_t[2] = {nullptr, nullptr}, *s_x[2] = {nullptr, nullptr}, *s_u[2] = {nullptr, nullptr}, *s_uff[2] = {nullptr, nullptr}, *s_K[2] = {nullptr, nullptr};
   int cur = 0; bool have_solution = false;
   // work
-  double *d_lq = nullptr, *d_proj = nullptr, *d_stage = nullptr, *d_ric = nullptr, *d_dx = nullptr, *d_du = nullptr, *d_perf_trial = nullptr, *d_perf = nullptr, *d_alpha = nullptr, *d_norms = nullptr;
+  double *d_lq = nullptr, *d_proj = nullptr, *d_stage = nullptr, *d_ric = nullptr, *d_base = nullptr, *d_dx = nullptr, *d_du = nullptr, *d_perf_trial = nullptr, *d_perf = nullptr, *d_alpha = nullptr, *d_norms = nullptr;
   int *d_done = nullptr, *d_status = nullptr, *d_counters = nullptr;
   int* h_counters = nullptr;
-  size_t rec = 0, prec = 0, krec = 0, srec = 0;
+  size_t rec = 0, prec = 0, krec = 0, srec = 0, brec = 0; bool split_lq = true;
   // gait bookkeeping
   std::vector<GaitSchedule> gaits; bool use_gait = false;
   // stats
@@ -81,7 +81,7 @@ Dev make_dev(bmpc_handle* h) {
   d.st_t = h->d_st_t; d.st_dt = h->d_st_dt; d.st_mode = h->d_st_mode; d.xref = h->d_xref; d.zref = h->d_zref;
   d.p_n = h->have_solution ? h->s_n[h->cur] : nullptr; d.p_t = h->s_t[h->cur]; d.p_x = h->s_x[h->cur]; d.p_u = h->s_u[h->cur];
   d.s_x = h->s_x[w]; d.s_u = h->s_u[w]; d.s_uff = h->s_uff[w]; d.s_K = h->s_K[w];
-  d.lq = h->d_lq; d.proj = h->d_proj; d.stage = h->d_stage; d.ric = h->d_ric; d.dx = h->d_dx; d.du = h->d_du;
+  d.lq = h->d_lq; d.proj = h->d_proj; d.stage = h->d_stage; d.ric = h->d_ric; d.base = h->d_base; d.dx = h->d_dx; d.du = h->d_du;
   d.perf_trial = h->d_perf_trial; d.perf = h->d_perf; d.alpha = h->d_alpha; d.norms = h->d_norms; d.done = h->d_done; d.status = h->d_status; d.counters = h->d_counters;
   return d;
 }
@@ -114,7 +114,10 @@ void tick(bmpc_handle* h) {
   CK(cudaFuncSetAttribute(k_policy_expand<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(PolSmem<NJ>))));
   h->linesearch_trials = 0;
   for (int iter = 0; iter < h->sqp_iterations; ++iter) {
-    k_lq<NJ><<<(nodes + 63) / 64, 64, 0, st>>>(d); ++h->launches;
+    if (h->split_lq) {
+      k_model_base<NJ><<<(nodes + 63) / 64, 64, 0, st>>>(d); ++h->launches;
+      k_lq_assemble<NJ><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches;
+    } else { k_lq<NJ><<<(nodes + 63) / 64, 64, 0, st>>>(d); ++h->launches; }
     if (iter == 0) mark(2);
     k_project<NJ><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches;
     if (iter == 0) mark(3);
@@ -196,8 +199,8 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     h->sqp_iterations = cfg->sqp_iterations > 0 ? cfg->sqp_iterations : h->model.sqp_iterations;
     h->NS = (int)std::ceil(h->horizon / h->dt - 1e-9) + 1 + 16;   // nominal grid + up to 16 event nodes inside the horizon
     const size_t B = h->B, NS = h->NS, nx = h->nx, nu = h->nu;
-    if (h->nj == 10) { h->rec = Dims<10>::REC; h->prec = Dims<10>::PREC; h->krec = RDims<10>::KREC; h->srec = SDims<10>::SREC; }
-    else { h->rec = Dims<12>::REC; h->prec = Dims<12>::PREC; h->krec = RDims<12>::KREC; h->srec = SDims<12>::SREC; }
+    if (h->nj == 10) { h->rec = Dims<10>::REC; h->prec = Dims<10>::PREC; h->krec = RDims<10>::KREC; h->srec = SDims<10>::SREC; h->brec = 2 * BaseDims<10>::BASE; }
+    else { h->rec = Dims<12>::REC; h->prec = Dims<12>::PREC; h->krec = RDims<12>::KREC; h->srec = SDims<12>::SREC; h->brec = 2 * BaseDims<12>::BASE; }
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& e : h->tev) CK(cudaEventCreate(&e));
     h->d_t0 = dalloc<double>(B); h->d_x0 = dalloc<double>(B * nx); h->d_tgt_t = dalloc<double>(B * h->TP); h->d_tgt_x = dalloc<double>(B * h->TP * nx);
@@ -211,7 +214,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
       h->s_x[i] = dalloc<double>(B * NS * nx); h->s_u[i] = dalloc<double>(B * NS * nu); h->s_uff[i] = dalloc<double>(B * NS * nu);
       h->s_K[i] = dalloc<double>(B * NS * nu * nx);
     }
-    h->d_lq = dalloc<double>(B * NS * h->rec); h->d_proj = dalloc<double>(B * NS * h->prec); h->d_stage = dalloc<double>(B * NS * h->srec); h->d_ric = dalloc<double>(B * NS * h->krec);
+    h->d_lq = dalloc<double>(B * NS * h->rec); h->d_proj = dalloc<double>(B * NS * h->prec); h->d_stage = dalloc<double>(B * NS * h->srec); h->d_base = dalloc<double>(B * NS * h->brec); h->d_ric = dalloc<double>(B * NS * h->krec);
     h->d_dx = dalloc<double>(B * NS * nx); h->d_du = dalloc<double>(B * NS * nu);
     h->d_perf_trial = dalloc<double>(B * NS * 3); h->d_perf = dalloc<double>(B * 8); h->d_alpha = dalloc<double>(B); h->d_norms = dalloc<double>(B * 2);
     h->d_done = dalloc<int>(B); h->d_status = dalloc<int>(B); h->d_counters = dalloc<int>(4); h->h_counters = halloc<int>(4);
@@ -235,7 +238,7 @@ void bmpc_destroy(bmpc_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* dptrs[] = {h->d_t0, h->d_x0, h->d_tgt_t, h->d_tgt_x, h->d_ev_t, h->d_n_ev, h->d_ev_mode, h->d_st_t, h->d_st_dt, h->d_xref, h->d_zref, h->d_st_mode,
                    h->s_n[0], h->s_n[1], h->s_ev[0], h->s_ev[1], h->s_t[0], h->s_t[1], h->s_x[0], h->s_x[1], h->s_u[0], h->s_u[1], h->s_uff[0], h->s_uff[1], h->s_K[0], h->s_K[1],
-                   h->d_lq, h->d_proj, h->d_stage, h->d_ric, h->d_dx, h->d_du, h->d_perf_trial, h->d_perf, h->d_alpha, h->d_norms, h->d_done, h->d_status, h->d_counters,
+                   h->d_lq, h->d_proj, h->d_stage, h->d_ric, h->d_base, h->d_dx, h->d_du, h->d_perf_trial, h->d_perf, h->d_alpha, h->d_norms, h->d_done, h->d_status, h->d_counters,
                    h->d_eval_t, h->d_eval_x, h->d_eval_xo, h->d_eval_uo, h->d_eval_m, h->d_default_joints, h->d_cmd};
   for (void* p : dptrs) if (p) cudaFree(p);
   void* hptrs[] = {h->h_t0, h->h_x0, h->h_tgt_t, h->h_tgt_x, h->h_ev_t, h->h_n_ev, h->h_ev_mode, h->h_counters};
@@ -474,6 +477,11 @@ int bmpc_get_observations(bmpc_handle* h, double* t, double* x) {
 }
 
 int bmpc_get_launch_count(const bmpc_handle* h) { return h ? h->launches : 0; }
+int bmpc_debug_set_option(bmpc_handle* h, const char* name, int value) {
+  if (!h || !name) return BMPC_ERR_INVALID;
+  if (std::string(name) == "split_lq") { h->split_lq = value != 0; return BMPC_OK; }
+  return BMPC_ERR_INVALID;
+}
 int bmpc_enable_phase_timing(bmpc_handle* h, int enable) { if (!h) return BMPC_ERR_INVALID; h->timing = enable != 0; return BMPC_OK; }
 int bmpc_get_phase_times(bmpc_handle* h, float* ms) { if (!h || !ms) return BMPC_ERR_INVALID; for (int i = 0; i < 7; ++i) ms[i] = h->phase_ms[i]; ms[7] = (float)h->linesearch_trials; return BMPC_OK; }
 void* bmpc_get_stream(bmpc_handle* h) { return h ? (void*)h->stream : nullptr; }

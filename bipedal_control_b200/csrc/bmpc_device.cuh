@@ -335,6 +335,141 @@ __device__ __noinline__ void model_eval(const double* __restrict__ x, const doub
   }
 }
 
+// ------------------------------------------------------------------------------------------------ base record (values only)
+// Everything the Jacobian columns need, computed once per (stage, RK2 evaluation) by one thread and consumed by one warp
+// (k_lq_assemble: lane = column).  Layout in doubles:
+template <int NJ>
+struct BaseDims {
+  static constexpr int NX = Dims<NJ>::NX;
+  static constexpr int B_PB = 0, B_BAX = 3, B_WE = 12, B_VE = 24, B_TOT = 36, B_HTOT = 46, B_COM = 52, B_A22I = 55, B_A12 = 64, B_ALE = 73, B_AAE = 82,
+                       B_PC = 91, B_VC = 103, B_F = 115, B_FTOT = B_F + NX, B_J = B_FTOT + 3, JS = 34, BASE = ((B_J + JS * NJ + 3) / 4) * 4;
+  static constexpr int J_O = 0, J_A = 3, J_SI = 6, J_AL = 16, J_AA = 19, J_W = 22, J_V = 25, J_HN = 28, J_HP = 31;
+};
+__device__ __forceinline__ void st3(double* p, v3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
+__device__ __forceinline__ v3 ld3(const double* p) { return mk(p[0], p[1], p[2]); }
+__device__ __forceinline__ void st_si(double* p, const SI& s) { p[0] = s.M; st3(p + 1, s.h); p[4] = s.I.xx; p[5] = s.I.xy; p[6] = s.I.xz; p[7] = s.I.yy; p[8] = s.I.yz; p[9] = s.I.zz; }
+__device__ __forceinline__ SI ld_si(const double* p) { SI s; s.M = p[0]; s.h = ld3(p + 1); s.I.xx = p[4]; s.I.xy = p[5]; s.I.xz = p[6]; s.I.yy = p[7]; s.I.yz = p[8]; s.I.zz = p[9]; return s; }
+
+template <int NJ>
+__device__ __noinline__ void model_base(const double* __restrict__ x, const double* __restrict__ u, double* __restrict__ base) {
+  using BD = BaseDims<NJ>;
+  constexpr int NL = Dims<NJ>::NL;
+  const DevModel& M = c_model;
+  const double mass = M.total_mass, imass = 1.0 / mass;
+  double sz, cz, sy, cy, sx, cx;
+  sincos(x[9], &sz, &cz); sincos(x[10], &sy, &cy); sincos(x[11], &sx, &cx);
+  m3 Rb;
+  Rb.m[0] = cz * cy; Rb.m[1] = cz * sy * sx - sz * cx; Rb.m[2] = cz * sy * cx + sz * sx;
+  Rb.m[3] = sz * cy; Rb.m[4] = sz * sy * sx + cz * cx; Rb.m[5] = sz * sy * cx - cz * sx;
+  Rb.m[6] = -sy;     Rb.m[7] = cy * sx;                Rb.m[8] = cy * cx;
+  const v3 pb = mk(x[6], x[7], x[8]);
+  v3 bax[3];
+  bax[0] = mk(0.0, 0.0, 1.0); bax[1] = mk(-sz, cz, 0.0); bax[2] = mk(cz * cy, sz * cy, -sy);
+  st3(base + BD::B_PB, pb);
+  for (int k = 0; k < 3; ++k) st3(base + BD::B_BAX + 3 * k, bax[k]);
+  v3 o[NJ], a[NJ], cb[NJ]; s3 Icb[NJ]; SI comp_si[NJ];
+  m3 Rtip[2];
+#pragma unroll 1
+  for (int leg = 0; leg < 2; ++leg) {
+    m3 Rp = Rb; v3 pp = pb;
+#pragma unroll 1
+    for (int i = 0; i < NL; ++i) {
+      const int j = leg * NL + i;
+      o[j] = mulc(Rp.m, M.pj[j]) + pp;
+      const m3 Rfix = mulc(Rp, M.Rj[j]);
+      a[j] = mulc(Rfix.m, M.axis[j]);
+      const m3 Rw = mul(Rfix, rodrigues(M.axis[j], x[12 + j]));
+      cb[j] = mulc(Rw.m, M.com[j]) + o[j];
+      Icb[j] = rotate_inertia(Rw, M.inertia[j]);
+      Rp = Rw; pp = o[j];
+      st3(base + BD::B_J + BD::JS * j + BD::J_O, o[j]); st3(base + BD::B_J + BD::JS * j + BD::J_A, a[j]);
+    }
+    Rtip[leg] = Rp;
+  }
+  v3 pc[NCON];
+#pragma unroll 1
+  for (int c = 0; c < NCON; ++c) { pc[c] = mulc(Rtip[c / 2].m, M.coff[c]) + o[(c / 2) * NL + NL - 1]; st3(base + BD::B_PC + 3 * c, pc[c]); }
+  const v3 cbase = mulc(Rb.m, M.base_com) + pb;
+  const s3 Ibase = rotate_inertia(Rb, M.base_inertia);
+#pragma unroll 1
+  for (int leg = 0; leg < 2; ++leg)
+#pragma unroll 1
+    for (int i = NL - 1; i >= 0; --i) {
+      const int j = leg * NL + i;
+      const SI bsi = body_si(M.mass[j], cb[j], Icb[j]);
+      comp_si[j] = (i == NL - 1) ? bsi : bsi + comp_si[j + 1];
+      st_si(base + BD::B_J + BD::JS * j + BD::J_SI, comp_si[j]);
+    }
+  const SI tot = body_si(M.base_mass, cbase, Ibase) + comp_si[0] + comp_si[NL];
+  const v3 com = imass * tot.h;
+  st_si(base + BD::B_TOT, tot); st3(base + BD::B_COM, com);
+  v3 Alin_e[3], Aang_e[3];
+#pragma unroll 1
+  for (int k = 0; k < 3; ++k) {
+    const Mom m = si_apply(tot, bax[k], cross(pb, bax[k])); Alin_e[k] = m.p; Aang_e[k] = m.n - cross(com, m.p);
+    st3(base + BD::B_ALE + 3 * k, Alin_e[k]); st3(base + BD::B_AAE + 3 * k, Aang_e[k]);
+  }
+  double A22[9], A22i[9], A12[9];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { A22[k] = Aang_e[k].x; A22[3 + k] = Aang_e[k].y; A22[6 + k] = Aang_e[k].z; A12[k] = Alin_e[k].x; A12[3 + k] = Alin_e[k].y; A12[6 + k] = Alin_e[k].z; }
+  inv3(A22, A22i);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { base[BD::B_A22I + i] = A22i[i]; base[BD::B_A12 + i] = A12[i]; }
+  v3 ml = mk(mass * x[0], mass * x[1], mass * x[2]), ma = mk(mass * x[3], mass * x[4], mass * x[5]);
+#pragma unroll 1
+  for (int j = 0; j < NJ; ++j) {
+    const Mom m = si_apply(comp_si[j], a[j], cross(o[j], a[j]));
+    const v3 al = m.p, aa = m.n - cross(com, m.p);
+    st3(base + BD::B_J + BD::JS * j + BD::J_AL, al); st3(base + BD::B_J + BD::JS * j + BD::J_AA, aa);
+    const double qd = u[12 + j]; ml = ml - qd * al; ma = ma - qd * aa;
+  }
+  const v3 w = mk(A22i[0] * ma.x + A22i[1] * ma.y + A22i[2] * ma.z, A22i[3] * ma.x + A22i[4] * ma.y + A22i[5] * ma.z, A22i[6] * ma.x + A22i[7] * ma.y + A22i[8] * ma.z);
+  const v3 vlin = imass * (ml - mk(A12[0] * w.x + A12[1] * w.y + A12[2] * w.z, A12[3] * w.x + A12[4] * w.y + A12[5] * w.z, A12[6] * w.x + A12[7] * w.y + A12[8] * w.z));
+  v3 Ftot = mk(0.0, 0.0, 0.0), tau = mk(0.0, 0.0, 0.0);
+#pragma unroll 1
+  for (int c = 0; c < NCON; ++c) { const v3 F = mk(u[3 * c], u[3 * c + 1], u[3 * c + 2]); Ftot = Ftot + F; tau = tau + cross(pc[c] - com, F); }
+  double* f = base + BD::B_F;
+  f[0] = Ftot.x * imass; f[1] = Ftot.y * imass; f[2] = Ftot.z * imass - 9.81;
+  f[3] = tau.x * imass; f[4] = tau.y * imass; f[5] = tau.z * imass;
+  f[6] = vlin.x; f[7] = vlin.y; f[8] = vlin.z; f[9] = w.x; f[10] = w.y; f[11] = w.z;
+#pragma unroll 1
+  for (int j = 0; j < NJ; ++j) f[12 + j] = u[12 + j];
+  st3(base + BD::B_FTOT, Ftot);
+  const double wr[3] = {w.x, w.y, w.z};
+  v3 we = mk(0.0, 0.0, 0.0), ve = vlin;
+  st3(base + BD::B_WE, we); st3(base + BD::B_VE, ve);
+#pragma unroll 1
+  for (int k = 0; k < 3; ++k) { we = we + wr[k] * bax[k]; ve = ve + wr[k] * cross(pb, bax[k]); st3(base + BD::B_WE + 3 * (k + 1), we); st3(base + BD::B_VE + 3 * (k + 1), ve); }
+  v3 wj[NJ], vj[NJ];
+#pragma unroll 1
+  for (int leg = 0; leg < 2; ++leg) {
+    v3 wp = we, vp = ve;
+#pragma unroll 1
+    for (int i = 0; i < NL; ++i) {
+      const int j = leg * NL + i; const double qd = u[12 + j];
+      wj[j] = wp + qd * a[j]; vj[j] = vp + qd * cross(o[j], a[j]); wp = wj[j]; vp = vj[j];
+      st3(base + BD::B_J + BD::JS * j + BD::J_W, wj[j]); st3(base + BD::B_J + BD::JS * j + BD::J_V, vj[j]);
+    }
+  }
+#pragma unroll 1
+  for (int c = 0; c < NCON; ++c) { const int tip = (c / 2) * NL + NL - 1; st3(base + BD::B_VC + 3 * c, cross(wj[tip], pc[c]) + vj[tip]); }
+  Mom hsum; hsum.n = mk(0.0, 0.0, 0.0); hsum.p = mk(0.0, 0.0, 0.0);
+#pragma unroll 1
+  for (int leg = 0; leg < 2; ++leg) {
+    Mom acc; acc.n = mk(0.0, 0.0, 0.0); acc.p = mk(0.0, 0.0, 0.0);
+#pragma unroll 1
+    for (int i = NL - 1; i >= 0; --i) {
+      const int j = leg * NL + i;
+      Mom bm; bm.p = M.mass[j] * (vj[j] + cross(wj[j], cb[j])); bm.n = mul(Icb[j], wj[j]) + cross(cb[j], bm.p);
+      acc = bm + acc;
+      st3(base + BD::B_J + BD::JS * j + BD::J_HN, acc.n); st3(base + BD::B_J + BD::JS * j + BD::J_HP, acc.p);
+    }
+    hsum = hsum + acc;
+  }
+  { Mom bm; bm.p = M.base_mass * (ve + cross(we, cbase)); bm.n = mul(Ibase, we) + cross(cbase, bm.p); hsum = hsum + bm; }
+  st3(base + BD::B_HTOT, hsum.n); st3(base + BD::B_HTOT + 3, hsum.p);
+}
+
 // relaxed log barrier [UPSTREAM RelaxedBarrierPenalty], settings task.info:280-287
 __device__ __forceinline__ void barrier_penalty(double h, double& p, double& dp, double& ddp) {
   const double mu = c_model.bar_mu, de = c_model.bar_delta;

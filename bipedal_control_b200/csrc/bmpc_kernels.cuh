@@ -33,7 +33,7 @@ struct Dev {
   double* xref; double* zref;
   const int* p_n; const double* p_t; const double* p_x; const double* p_u;   // previous primal solution (warm start)
   double* s_x; double* s_u; double* s_uff; double* s_K;                      // new primal solution / linearisation point
-  double* lq; double* proj; double* stage; double* ric;
+  double* lq; double* proj; double* stage; double* ric; double* base;
   double* dx; double* du;
   double* perf_trial; double* perf; double* alpha; double* norms; int* done; int* status; int* counters;
 };
@@ -330,6 +330,309 @@ __global__ void __launch_bounds__(64, LQ_MIN_BLOCKS) k_lq(Dev d) {
   misc[D::M_TYPE] = 0.0; misc[D::M_PCOST] = pcost; misc[D::M_PDYN] = dt * pdyn; misc[D::M_PEQ] = dt * peq;
 }
 
+// ------------------------------------------------------------------------------------------------ K1a/K1b: LQ approximation split by parallelism
+// K1a k_model_base : one THREAD per stage, values only (FK, composite inertias, CMM, twists, subtree momenta) for both RK2 evaluations
+// K1b k_lq_assemble: one WARP per stage, lane = column: analytic Jacobian columns, RK2 sensitivities, cost, constraint rows -> compact LQ record
+// (same record as k_lq; k_lq is kept as the single-kernel reference implementation for cross-checks).
+template <int NJ>
+__global__ void __launch_bounds__(64, 6) k_model_base(Dev d) {
+  using D = Dims<NJ>; using BD = BaseDims<NJ>;
+  constexpr int NX = D::NX, NU = D::NU;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = gid / d.NS, k = gid % d.NS;
+  if (b >= d.B) return;
+  const int N = d.n_nodes[b] - 1;
+  if (k >= N) return;
+  const size_t nb = (size_t)b * d.NS;
+  if (d.node_ev[nb + k] == 1) return;
+  double x[NX], u[NU];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) x[i] = d.s_x[(nb + k) * NX + i];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) u[i] = d.s_u[(nb + k) * NU + i];
+  double* base0 = d.base + (nb + k) * (size_t)(2 * BD::BASE);
+  model_base<NJ>(x, u, base0);
+  const double dt = d.st_dt[nb + k];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) x[i] += dt * base0[BD::B_F + i];
+  model_base<NJ>(x, u, base0 + BD::BASE);
+}
+
+// one column (X index c >= 6) of d f / d x from the base record: rows 3..5 -> col[0..2], rows 6..8 -> col[3..5], rows 9..11 -> col[6..8]
+template <int NJ>
+__device__ __forceinline__ void lq_dq_column(const double* __restrict__ bs, const double* __restrict__ u, int c, double* col) {
+  using BD = BaseDims<NJ>; constexpr int NL = Dims<NJ>::NL;
+  const double imass = 1.0 / c_model.total_mass;
+  v3 ak, ok, wp, vp, AlinK; SI sub; Mom hsub; int leg_first, leg_last;
+  if (c < 9) {
+    const int k = c - 6;
+    ak = ld3(bs + BD::B_BAX + 3 * k); ok = ld3(bs + BD::B_PB); sub = ld_si(bs + BD::B_TOT);
+    hsub.n = ld3(bs + BD::B_HTOT); hsub.p = ld3(bs + BD::B_HTOT + 3);
+    wp = ld3(bs + BD::B_WE + 3 * k); vp = ld3(bs + BD::B_VE + 3 * k); AlinK = ld3(bs + BD::B_ALE + 3 * k); leg_first = 0; leg_last = 1;
+  } else {
+    const int j = c - 9; const double* J = bs + BD::B_J + BD::JS * j;
+    ak = ld3(J + BD::J_A); ok = ld3(J + BD::J_O); sub = ld_si(J + BD::J_SI); hsub.n = ld3(J + BD::J_HN); hsub.p = ld3(J + BD::J_HP);
+    if (j % NL == 0) { wp = ld3(bs + BD::B_WE + 9); vp = ld3(bs + BD::B_VE + 9); } else { wp = ld3(J - BD::JS + BD::J_W); vp = ld3(J - BD::JS + BD::J_V); }
+    AlinK = ld3(J + BD::J_AL); leg_first = leg_last = j / NL;
+  }
+  const v3 com = ld3(bs + BD::B_COM), ptot = ld3(bs + BD::B_HTOT + 3), Ftot = ld3(bs + BD::B_FTOT);
+  const double* A22i = bs + BD::B_A22I; const double* A12 = bs + BD::B_A12;
+  const v3 s = cross(ok, ak);
+  const v3 mom1 = cross(ak, hsub.n) + cross(s, hsub.p);
+  const v3 frc1 = cross(ak, hsub.p);
+  const v3 w1 = cross(ak, wp);
+  const v3 v1 = cross(ak, vp) + cross(s, wp);
+  const Mom m2 = si_apply(sub, w1, v1);
+  const v3 dlin = frc1 - m2.p;
+  const v3 dnO = mom1 - m2.n;
+  const v3 dcom = imass * AlinK;
+  const v3 dang = dnO - cross(dcom, ptot) - cross(com, dlin);
+  const v3 e = mk(A22i[0] * dang.x + A22i[1] * dang.y + A22i[2] * dang.z, A22i[3] * dang.x + A22i[4] * dang.y + A22i[5] * dang.z, A22i[6] * dang.x + A22i[7] * dang.y + A22i[8] * dang.z);
+  const v3 l = imass * (dlin - mk(A12[0] * e.x + A12[1] * e.y + A12[2] * e.z, A12[3] * e.x + A12[4] * e.y + A12[5] * e.z, A12[6] * e.x + A12[7] * e.y + A12[8] * e.z));
+  col[3] = -l.x; col[4] = -l.y; col[5] = -l.z; col[6] = -e.x; col[7] = -e.y; col[8] = -e.z;
+  v3 t = mk(0.0, 0.0, 0.0);
+#pragma unroll
+  for (int cc = 0; cc < NCON; ++cc)
+    if (cc / 2 >= leg_first && cc / 2 <= leg_last) t = t + cross(cross(ak, ld3(bs + BD::B_PC + 3 * cc) - ok), mk(u[3 * cc], u[3 * cc + 1], u[3 * cc + 2]));
+  t = imass * (t - cross(dcom, Ftot));
+  col[0] = t.x; col[1] = t.y; col[2] = t.z;
+}
+template <int NJ>
+__device__ __forceinline__ void lq_x_column(const double* __restrict__ bs, const double* __restrict__ u, int c, double* col) {
+  using BD = BaseDims<NJ>;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) col[i] = 0.0;
+  if (c < 3) col[3 + c] = 1.0;
+  else if (c < 6) {
+    const double* A22i = bs + BD::B_A22I; const double* A12 = bs + BD::B_A12; const int cc = c - 3;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { col[3 + r] = -(A12[3 * r] * A22i[cc] + A12[3 * r + 1] * A22i[3 + cc] + A12[3 * r + 2] * A22i[6 + cc]); col[6 + r] = c_model.total_mass * A22i[3 * r + cc]; }
+  } else lq_dq_column<NJ>(bs, u, c, col);
+}
+// column l of d f / d qd_j (rows 6..11)
+template <int NJ>
+__device__ __forceinline__ void lq_bj_column(const double* __restrict__ bs, int l, double* col) {
+  using BD = BaseDims<NJ>;
+  const double imass = 1.0 / c_model.total_mass;
+  const double* J = bs + BD::B_J + BD::JS * l; const double* A22i = bs + BD::B_A22I; const double* A12 = bs + BD::B_A12;
+  const v3 n = ld3(J + BD::J_AA), p = ld3(J + BD::J_AL);
+  const v3 e = mk(A22i[0] * n.x + A22i[1] * n.y + A22i[2] * n.z, A22i[3] * n.x + A22i[4] * n.y + A22i[5] * n.z, A22i[6] * n.x + A22i[7] * n.y + A22i[8] * n.z);
+  const v3 lv = imass * (p - mk(A12[0] * e.x + A12[1] * e.y + A12[2] * e.z, A12[3] * e.x + A12[4] * e.y + A12[5] * e.z, A12[6] * e.x + A12[7] * e.y + A12[8] * e.z));
+  col[0] = -lv.x; col[1] = -lv.y; col[2] = -lv.z; col[3] = -e.x; col[4] = -e.y; col[5] = -e.z;
+}
+// column c (force component) of d f / d F (rows 3..5): column (c % 3) of skew(p_i - com) / m
+template <int NJ>
+__device__ __forceinline__ void lq_bf_column(const double* __restrict__ bs, int c, double* col) {
+  using BD = BaseDims<NJ>;
+  const double imass = 1.0 / c_model.total_mass;
+  const v3 r = imass * (ld3(bs + BD::B_PC + 3 * (c / 3)) - ld3(bs + BD::B_COM));
+  const int a = c % 3;
+  col[0] = a == 0 ? 0.0 : (a == 1 ? -r.z : r.y);
+  col[1] = a == 0 ? r.z : (a == 1 ? 0.0 : -r.x);
+  col[2] = a == 0 ? -r.y : (a == 1 ? r.x : 0.0);
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(128, 4) k_lq_assemble(Dev d) {
+  using D = Dims<NJ>; using BD = BaseDims<NJ>;
+  constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, NL = D::NL, WPB = 4, BASE = BD::BASE;
+  __shared__ double sbase[WPB][2 * BASE];
+  __shared__ double sA2[WPB][9][NXA + 1];
+  __shared__ double sxu[WPB][4 * 24];   // x, u, xnext, xref
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * WPB + warp;
+  const int b = gw / d.NS, k = gw % d.NS;
+  if (b >= d.B) return;
+  const int N = d.n_nodes[b] - 1;
+  if (k >= N) return;
+  const size_t nb = (size_t)b * d.NS;
+  double* __restrict__ rec = d.lq + (nb + k) * D::REC;
+  const double* xg = d.s_x + (nb + k) * NX; const double* xng = xg + NX;
+  if (d.node_ev[nb + k] == 1) {   // [UPSTREAM] setupEventNode
+    double s = 0.0;
+    if (lane < NX) { const double bi = xg[lane] - xng[lane]; rec[D::R_B + lane] = bi; s = bi * bi; }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      rec[D::R_MISC + D::M_TYPE] = 1.0; rec[D::R_MISC + D::M_DT] = 0.0; rec[D::R_MISC + D::M_MODE] = -1.0;
+      rec[D::R_MISC + D::M_PCOST] = 0.0; rec[D::R_MISC + D::M_PDYN] = s; rec[D::R_MISC + D::M_PEQ] = 0.0;
+    }
+    return;
+  }
+  // ---- stage the two base records and the linearisation point
+  const double* __restrict__ bg = d.base + (nb + k) * (size_t)(2 * BASE);
+  constexpr int NIT = (2 * BASE + 31) / 32;
+  double tmp[NIT];
+#pragma unroll
+  for (int i = 0; i < NIT; ++i) tmp[i] = (lane + 32 * i < 2 * BASE) ? bg[lane + 32 * i] : 0.0;
+  double* xs = sxu[warp]; double* us = xs + 24; double* xns = xs + 48; double* xrs = xs + 72;
+  if (lane < NX) { xs[lane] = xg[lane]; xns[lane] = xng[lane]; xrs[lane] = d.xref[(nb + k) * NX + lane]; }
+  if (lane < NU) us[lane] = d.s_u[(nb + k) * NU + lane];
+#pragma unroll
+  for (int i = 0; i < NIT; ++i) if (lane + 32 * i < 2 * BASE) sbase[warp][lane + 32 * i] = tmp[i];
+  __syncwarp();
+  const double* b1 = sbase[warp]; const double* b2 = b1 + BASE;
+  const DevModel& M = c_model;
+  const double dt = d.st_dt[nb + k];
+  const int mode = d.st_mode[nb + k];
+  const double hdt = 0.5 * dt, imass = 1.0 / M.total_mass;
+  // ---- Jacobian columns (lane = column)
+  double a1[9], a2[9], bj1[6], bj2[6], bf1[3], bf2[3];
+  if (lane < NXA) { lq_x_column<NJ>(b1, us, lane, a1); lq_x_column<NJ>(b2, us, lane, a2); }
+  if (lane < NJ) { lq_bj_column<NJ>(b1, lane, bj1); lq_bj_column<NJ>(b2, lane, bj2); }
+  if (lane < 12) { lq_bf_column<NJ>(b1, lane, bf1); lq_bf_column<NJ>(b2, lane, bf2); }
+  if (lane < NXA) {
+#pragma unroll
+    for (int r = 0; r < 9; ++r) sA2[warp][r][lane] = a2[r];
+  }
+  __syncwarp();
+  // ---- dynamics: b, (A_d - I), B_d   [UPSTREAM SensitivityIntegrator RK2]
+  double pdyn = 0.0;
+  if (lane < NX) { const double bi = xs[lane] + hdt * (b1[BD::B_F + lane] + b2[BD::B_F + lane]) - xns[lane]; rec[D::R_B + lane] = bi; pdyn = bi * bi; }
+  for (int o = 16; o > 0; o >>= 1) pdyn += __shfl_xor_sync(0xffffffffu, pdyn, o);
+  if (lane < NXA) {
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      double s = 0.0;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) s += sA2[warp][r][3 + t] * a1[t] + sA2[warp][r][6 + t] * a1[6 + t];
+      rec[D::R_AD + r * NXA + lane] = hdt * (a1[r] + a2[r] + dt * s);
+    }
+  }
+  if (lane < 12) {
+    const int a = lane % 3;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      double s = sA2[warp][r][a] * imass;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) s += sA2[warp][r][3 + t] * bf1[t];
+      const double b12 = r < 3 ? (bf1[r] + bf2[r]) : 0.0;
+      rec[D::R_BD + r * NU + lane] = hdt * (b12 + dt * s);
+    }
+  }
+  if (lane < NJ) {
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      double s = sA2[warp][r][9 + lane];
+#pragma unroll
+      for (int t = 0; t < 3; ++t) s += sA2[warp][r][6 + t] * bj1[3 + t];
+      const double b12 = r >= 3 ? (bj1[r - 3] + bj2[r - 3]) : 0.0;
+      rec[D::R_BD + r * NU + 12 + lane] = hdt * (b12 + dt * s);
+    }
+  }
+  // ---- cost gradient / barrier blocks (one contact per lane 0..3, one joint per lane for the joint part)
+  const bool st0 = leg_in_stance(mode, 0), st1 = leg_in_stance(mode, 1);
+  const int nst = 2 * (int(st0) + int(st1));
+  const double fznom = nst > 0 ? M.total_mass * 9.81 / nst : 0.0;
+  if (lane < NX) rec[D::R_Q + lane] = dt * M.Qdiag[lane] * (xs[lane] - xrs[lane]);
+  double shift = 0.0;
+  if (lane < NCON) {
+    const int c = lane;
+    const bool st = (c / 2 == 0) ? st0 : st1;
+    double r3[3] = {M.Rforce[3 * c] * us[3 * c], M.Rforce[3 * c + 1] * us[3 * c + 1], M.Rforce[3 * c + 2] * (us[3 * c + 2] - (st ? fznom : 0.0))};
+    double hb[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (st) {
+      const double fx = us[3 * c], fy = us[3 * c + 1], fz = us[3 * c + 2];
+      const double ts = fx * fx + fy * fy + M.fr_reg, tn = sqrt(ts), t32 = tn * ts;
+      const double h = M.mu_f * (fz + M.fr_grip) - tn;
+      double p, dp, ddp; barrier_penalty(h, p, dp, ddp);
+      const double g0 = -fx / tn, g1 = -fy / tn, g2 = M.mu_f;
+      const double H00 = -(fy * fy + M.fr_reg) / t32, H01 = fx * fy / t32, H11 = -(fx * fx + M.fr_reg) / t32;
+      r3[0] += dp * g0; r3[1] += dp * g1; r3[2] += dp * g2;
+      hb[0] = ddp * g0 * g0 + dp * H00; hb[1] = ddp * g0 * g1 + dp * H01; hb[2] = ddp * g0 * g2;
+      hb[3] = ddp * g1 * g1 + dp * H11; hb[4] = ddp * g1 * g2; hb[5] = ddp * g2 * g2;
+      shift = -dp * M.fr_shift;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { rec[D::R_R + 3 * c + a] = dt * r3[a]; rec[D::R_FO + 3 * c + a] = us[3 * c + a]; }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) rec[D::R_HB + 6 * c + a] = dt * hb[a];
+  }
+  for (int o = 2; o > 0; o >>= 1) shift += __shfl_xor_sync(0xffffffffu, shift, o);   // lanes 0..3
+  shift = __shfl_sync(0xffffffffu, shift, 0);
+  if (lane < NJ) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) s += M.Rjoint[lane * NJ + j] * us[12 + j];
+    rec[D::R_R + 12 + lane] = dt * s;
+  }
+  // ---- contact velocity Jacobians of the first evaluation and the compressed constraint rows
+  v3 jx[NCON], ju[NCON];
+  {
+    const v3 pb = ld3(b1 + BD::B_PB);
+#pragma unroll
+    for (int c = 0; c < NCON; ++c) {
+      const int leg = c / 2;
+      const v3 p = ld3(b1 + BD::B_PC + 3 * c), vcp = ld3(b1 + BD::B_VC + 3 * c);
+      v3 Jb[3];
+#pragma unroll
+      for (int kk = 0; kk < 3; ++kk) Jb[kk] = cross(ld3(b1 + BD::B_BAX + 3 * kk), p - pb);
+      jx[c] = mk(0.0, 0.0, 0.0); ju[c] = mk(0.0, 0.0, 0.0);
+      if (lane < NXA) {
+        v3 t = mk(a1[3], a1[4], a1[5]) + a1[6] * Jb[0] + a1[7] * Jb[1] + a1[8] * Jb[2];
+        bool direct = false; v3 ak, ok, wk, vk;
+        if (lane >= 6 && lane < 9) { const int kk = lane - 6; direct = true; ak = ld3(b1 + BD::B_BAX + 3 * kk); ok = pb; wk = ld3(b1 + BD::B_WE + 3 * (kk + 1)); vk = ld3(b1 + BD::B_VE + 3 * (kk + 1)); }
+        else if (lane >= 9 && (lane - 9) / NL == leg) { const double* J = b1 + BD::B_J + BD::JS * (lane - 9); direct = true; ak = ld3(J + BD::J_A); ok = ld3(J + BD::J_O); wk = ld3(J + BD::J_W); vk = ld3(J + BD::J_V); }
+        if (direct) { const v3 uw = vcp - (cross(wk, p) + vk); t = t + cross(ak, uw) + cross(wk, cross(ak, p - ok)); }
+        jx[c] = t;
+      }
+      if (lane < NJ) {
+        v3 t = mk(bj1[0], bj1[1], bj1[2]) + bj1[3] * Jb[0] + bj1[4] * Jb[1] + bj1[5] * Jb[2];
+        if (lane / NL == leg) { const double* J = b1 + BD::B_J + BD::JS * lane; t = t + cross(ld3(J + BD::J_A), p - ld3(J + BD::J_O)); }
+        ju[c] = t;
+      }
+    }
+  }
+  int nrows = 0; double peq = 0.0;
+  const double is2 = 0.7071067811865476;
+#pragma unroll
+  for (int leg = 0; leg < 2; ++leg) {
+    const int ca = 2 * leg, cb = 2 * leg + 1;
+    const bool st = leg == 0 ? st0 : st1;
+    const v3 va = ld3(b1 + BD::B_VC + 3 * ca), vb = ld3(b1 + BD::B_VC + 3 * cb);
+    if (st) {
+      peq += dot(va, va) + dot(vb, vb);
+      v3 r = ld3(b1 + BD::B_PC + 3 * ca) - ld3(b1 + BD::B_PC + 3 * cb);
+      r = (1.0 / sqrt(dot(r, r))) * r;
+      const double ax = fabs(r.x), ay = fabs(r.y), az = fabs(r.z);
+      const v3 e = (ax <= ay && ax <= az) ? mk(1.0, 0.0, 0.0) : ((ay <= az) ? mk(0.0, 1.0, 0.0) : mk(0.0, 0.0, 1.0));
+      v3 n1 = cross(r, e); n1 = (1.0 / sqrt(dot(n1, n1))) * n1;
+      const v3 n2 = cross(r, n1);
+      const v3 sx_ = is2 * (jx[ca] + jx[cb]), dx_ = is2 * (jx[ca] - jx[cb]), su_ = is2 * (ju[ca] + ju[cb]), du_ = is2 * (ju[ca] - ju[cb]);
+      if (lane < NXA) {
+        rec[D::R_CV + (nrows + 0) * NXA + lane] = sx_.x; rec[D::R_CV + (nrows + 1) * NXA + lane] = sx_.y; rec[D::R_CV + (nrows + 2) * NXA + lane] = sx_.z;
+        rec[D::R_CV + (nrows + 3) * NXA + lane] = dot(n1, dx_); rec[D::R_CV + (nrows + 4) * NXA + lane] = dot(n2, dx_);
+      }
+      if (lane < NJ) {
+        rec[D::R_DV + (nrows + 0) * NJ + lane] = su_.x; rec[D::R_DV + (nrows + 1) * NJ + lane] = su_.y; rec[D::R_DV + (nrows + 2) * NJ + lane] = su_.z;
+        rec[D::R_DV + (nrows + 3) * NJ + lane] = dot(n1, du_); rec[D::R_DV + (nrows + 4) * NJ + lane] = dot(n2, du_);
+      }
+      if (lane == 0) {
+        const v3 sv = is2 * (va + vb), dv = is2 * (va - vb);
+        rec[D::R_EV + nrows] = sv.x; rec[D::R_EV + nrows + 1] = sv.y; rec[D::R_EV + nrows + 2] = sv.z; rec[D::R_EV + nrows + 3] = dot(n1, dv); rec[D::R_EV + nrows + 4] = dot(n2, dv);
+      }
+      nrows += 5;
+    } else {
+      const double zr = d.zref[(nb + k) * 2 + leg];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int c0 = t == 0 ? ca : cb;
+        if (lane < NXA) rec[D::R_CV + nrows * NXA + lane] = jx[c0].z;
+        if (lane < NJ) rec[D::R_DV + nrows * NJ + lane] = ju[c0].z;
+        const double ev = (t == 0 ? va.z : vb.z) - zr;
+        if (lane == 0) rec[D::R_EV + nrows] = ev;
+        peq += ev * ev + us[3 * c0] * us[3 * c0] + us[3 * c0 + 1] * us[3 * c0 + 1] + us[3 * c0 + 2] * us[3 * c0 + 2];
+        ++nrows;
+      }
+    }
+  }
+  if (lane == 0) {
+    const double pcost = dt * stage_cost_value<NJ>(mode, xs, us, xrs);
+    double* misc = rec + D::R_MISC;
+    misc[D::M_DT] = dt; misc[D::M_DQ] = dt * shift; misc[D::M_DR] = dt * shift; misc[D::M_MODE] = (double)mode; misc[D::M_NROWS] = (double)nrows;
+    misc[D::M_TYPE] = 0.0; misc[D::M_PCOST] = pcost; misc[D::M_PDYN] = dt * pdyn; misc[D::M_PEQ] = dt * peq;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ K1.5: constraint projection + change of input variables
 // One warp per (instance, stage).
 //  (1) Dv (r x NJ, full row rank after the per-foot compression) -> Householder QR of Dv^T = Q [R; 0]:
@@ -618,6 +921,35 @@ __device__ __forceinline__ void gemm_tiles(const double* __restrict__ A, int lda
     if (w + i * NW < MT * NT) { double* cp = C + (8 * mt[i] + lr) * ldc + 8 * nt[i] + 2 * lc; cp[0] = c0[i]; cp[1] = c1[i]; }
 }
 
+// Right-looking Cholesky of the (symmetric, fully stored) M x M matrix G fused with the forward substitution of [H | g], one warp,
+// shuffles only.  Lane l < MP holds column l of G in gc[], lane c holds column c of [H | g] in hc[].  On return lane j holds
+// column j of L in gc[] (rows >= j) and hc[] holds Y = L^-1 H (yg in the g lane).  Serial chain per pivot: shuffle -> rsqrt -> FMA.
+template <int M, int MP>
+__device__ __forceinline__ bool chol_forward(double (&gc)[MP], double (&hc)[MP], int lane) {
+  bool not_pd = false;
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    double dj = __shfl_sync(0xffffffffu, gc[j], j);
+    if (!(dj > 0.0)) { not_pd = true; dj = 1.0; }
+    const double inv = rsqrt(dj);
+    const double yj = hc[j] * inv;
+    const double gj = (lane > j) ? gc[j] * inv : 0.0;   // L[lane][j] by symmetry of the fully stored G (own column, row j); finished columns stay untouched
+    hc[j] = yj;
+#pragma unroll
+    for (int i = j + 1; i < M; ++i) {
+      const double li = __shfl_sync(0xffffffffu, gc[i], j) * inv;   // L[i][j]
+      hc[i] -= li * yj;
+      gc[i] -= li * gj;
+    }
+    if (lane == j) {
+      gc[j] = dj * inv;
+#pragma unroll
+      for (int i = j + 1; i < M; ++i) gc[i] *= inv;
+    }
+  }
+  return not_pd;
+}
+
 // ------------------------------------------------------------------------------------------------ K2: backward Riccati recursion
 // One CTA (4 warps) per instance; S, At, SA, Bt, SB, H, G live in shared memory, padded to NXP = 24 states / MP = 16 reduced inputs.
 //   SA = S At, SB = S Bt, sb = s + S bt;  H = Pt + Bt^T SA, G = Rt + Bt^T SB, g = rt + Bt^T sb
@@ -633,8 +965,8 @@ struct RicSmem {
   double s[NXP], sb[NXP], bt[NXP], qt[NXP], snew[NXP], qd[NXP];
   double rt[MP], g[MP];
   double lcol[2][MP + 2];
-  alignas(16) double stage[2][SDims<NJ>::SREC];   // TMA-staged stage records (double buffered)
-  alignas(8) unsigned long long bar[2];
+  alignas(16) double stage[SDims<NJ>::SREC];   // TMA-staged stage record (refilled right after the scatter phase)
+  alignas(8) unsigned long long bar;
 };
 
 template <int NJ>
@@ -656,6 +988,11 @@ __global__ void __launch_bounds__(WS_THREADS, 4) k_riccati(Dev d) {
   const int N = d.n_nodes[b] - 1;
   const size_t nb = (size_t)b * d.NS;
   const double imass = 1.0 / c_model.total_mass;
+  // warp w runs on SM sub-partition w % 4: rotate the serial roles (Cholesky, mat-vecs) over the CTAs so that co-resident CTAs
+  // do not pile their serial FP64 work onto the same sub-partition
+  const int cw = blockIdx.x & 3;            // Cholesky warp of this CTA
+  const int vw = (warp - cw - 1) & 3;       // 0..2 for the other three warps, 3 for the Cholesky warp
+  const int mw = (cw + 2) & 3;              // mat-vec warp
   // terminal value function: zero (no terminal cost installed)
   for (int i = tid; i < NXP * LD; i += WS_THREADS) { sm.S[i] = 0.0; sm.At[i] = 0.0; sm.SA[i] = 0.0; }
   for (int i = tid; i < NXP * LDM; i += WS_THREADS) { sm.Bt[i] = 0.0; sm.SB[i] = 0.0; }
@@ -663,145 +1000,137 @@ __global__ void __launch_bounds__(WS_THREADS, 4) k_riccati(Dev d) {
   for (int i = tid; i < MP * LDM; i += WS_THREADS) sm.G[i] = 0.0;
   for (int i = tid; i < NXP; i += WS_THREADS) { sm.s[i] = 0.0; sm.sb[i] = 0.0; sm.bt[i] = 0.0; sm.qt[i] = 0.0; sm.snew[i] = 0.0; sm.qd[i] = 0.0; }
   constexpr unsigned REC_BYTES = S::SREC * sizeof(double);
-  if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
   __syncthreads();
-  // prologue: stage records N-1 and N-2 are in flight before the loop starts
-  if (tid == 0) {
-    if (N >= 1) tma_load_1d(sm.stage[(N - 1) & 1], d.stage + (nb + N - 1) * S::SREC, REC_BYTES, &sm.bar[(N - 1) & 1]);
-    if (N >= 2) tma_load_1d(sm.stage[(N - 2) & 1], d.stage + (nb + N - 2) * S::SREC, REC_BYTES, &sm.bar[(N - 2) & 1]);
-  }
-  unsigned phase_bits = 0;   // per-buffer mbarrier phase parity
+  if (tid == 0 && N >= 1) tma_load_1d(sm.stage, d.stage + (nb + N - 1) * S::SREC, REC_BYTES, &sm.bar);
+  unsigned phase_bit = 0;
   for (int k = N - 1; k >= 0; --k) {
-    const int buf = k & 1;
-    mbar_wait(&sm.bar[buf], (phase_bits >> buf) & 1u);
-    phase_bits ^= 1u << buf;
-    const double* sr = sm.stage[buf];
+    mbar_wait(&sm.bar, phase_bit);
+    phase_bit ^= 1u;
+    const double* sr = sm.stage;
     double* ric = d.ric + (nb + k) * R::KREC;
     const double* meta = sr + S::S_META;
     const bool is_event = meta[S::T_TYPE] != 0.0;
     if (is_event) {   // S unchanged (A = I, Q = 0, no input); s <- s + S b
       if (tid < NX) sm.bt[tid] = sr[S::S_B + tid];
       __syncthreads();
+      if (tid == 0 && k >= 1) { fence_proxy_async(); tma_load_1d(sm.stage, d.stage + (nb + k - 1) * S::SREC, REC_BYTES, &sm.bar); }
       if (tid < NX) { double a = sm.s[tid]; for (int c = 0; c < NX; ++c) a += sm.S[tid * LD + c] * sm.bt[c]; sm.snew[tid] = a; }
       __syncthreads();
       if (tid < NX) sm.s[tid] = sm.snew[tid];
       __syncthreads();
-      if (tid == 0 && k >= 2) { fence_proxy_async(); tma_load_1d(sm.stage[buf], d.stage + (nb + k - 2) * S::SREC, REC_BYTES, &sm.bar[buf]); }
       continue;
     }
     const int m = (int)meta[S::T_M], mj = (int)meta[S::T_MJ], nclosed = (int)meta[S::T_NCLOSED], mode = (int)meta[S::T_MODE];
     const double dt = meta[S::T_DT];
     const bool st0 = leg_in_stance(mode, 0);
-    // ---- phase 1: scatter the projected stage record into the padded operand matrices
-    for (int i = tid; i < NX * NX; i += WS_THREADS) {   // At = I + [rows 3.., X cols]
-      const int r = i / NX, c = i % NX;
-      double a = (r == c) ? 1.0 : 0.0;
-      if (r >= 3 && (c < 6 || c >= 9)) a += sr[S::S_AT + (r - 3) * NXA + xcol(c)];
-      sm.At[r * LD + c] = a;
+    // ---- phase 1: scatter the projected stage record into the padded operand matrices (lane = column, warp = row stride: no div/mod)
+    {
+      const int xcl = lane < 6 ? lane : lane + 3;   // state column of active-x column `lane`
+      for (int r = warp; r < NX; r += 4) {           // At = I + [rows 3.., X cols]; columns 6..8 are identity columns
+        if (lane < NXA) sm.At[r * LD + xcl] = ((r == xcl) ? 1.0 : 0.0) + ((r >= 3) ? sr[S::S_AT + (r - 3) * NXA + lane] : 0.0);
+        if (lane >= 29) { const int c = lane - 23; sm.At[r * LD + c] = (r == c) ? 1.0 : 0.0; }
+      }
+      const int bc = lane & 15, bh = lane >> 4;
+      for (int r = 2 * warp + bh; r < NX; r += 8)    // Bt (two rows per warp pass)
+        sm.Bt[r * LDM + bc] = (r >= 3) ? sr[S::S_BT + (r - 3) * MP + bc] : ((bc < 3 * nclosed && bc % 3 == r) ? dt * imass : 0.0);
+      for (int r = warp; r < MP; r += 4) {           // H <- Pt (null rows only)
+        const int t = r - 3 * nclosed;
+        if (lane < NXA) sm.H[r * LD + xcl] = (t >= 0 && t < mj) ? sr[S::S_PT + t * NXA + lane] : 0.0;
+        if (lane >= 29) sm.H[r * LD + lane - 23] = 0.0;
+      }
+      for (int r = 2 * warp + bh; r < MP; r += 8) {  // G <- Rt
+        const int c = bc;
+        double a = 0.0;
+        if (r >= m || c >= m) a = (r == c) ? 1.0 : 0.0;
+        else if (r < 3 * nclosed && c < 3 * nclosed) {
+          if (r / 3 == c / 3) {
+            const int cn = (st0 ? 0 : 2) + r / 3, p = r % 3, q = c % 3;
+            const int lo = p < q ? p : q, hi = p < q ? q : p;
+            a = sr[S::S_HB + 6 * cn + (lo == 0 ? hi : (lo == 1 ? 2 + hi : 5))];
+            if (p == q) a += sr[S::S_RD + 3 * cn + p];
+          }
+        } else if (r >= 3 * nclosed && c >= 3 * nclosed) a = sr[S::S_RN + (r - 3 * nclosed) * 8 + (c - 3 * nclosed)];
+        sm.G[r * LDM + c] = a;
+      }
     }
-    for (int i = tid; i < NX * MP; i += WS_THREADS) {   // Bt
-      const int r = i / MP, c = i % MP;
-      double a = 0.0;
-      if (r >= 3) a = sr[S::S_BT + (r - 3) * MP + c];
-      else if (c < 3 * nclosed) a = (c % 3 == r) ? dt * imass : 0.0;
-      sm.Bt[r * LDM + c] = a;
-    }
-    for (int i = tid; i < MP * NX; i += WS_THREADS) {   // H <- Pt (null rows only)
-      const int r = i / NX, c = i % NX;
-      double a = 0.0;
-      const int t = r - 3 * nclosed;
-      if (t >= 0 && t < mj && (c < 6 || c >= 9)) a = sr[S::S_PT + t * NXA + xcol(c)];
-      sm.H[r * LD + c] = a;
-    }
-    for (int i = tid; i < MP * MP; i += WS_THREADS) {   // G <- Rt
-      const int r = i / MP, c = i % MP;
-      double a = 0.0;
-      if (r >= m || c >= m) a = (r == c) ? 1.0 : 0.0;
-      else if (r < 3 * nclosed && c < 3 * nclosed) {
-        if (r / 3 == c / 3) {
-          const int cn = (st0 ? 0 : 2) + r / 3, p = r % 3, q = c % 3;
-          const int lo = p < q ? p : q, hi = p < q ? q : p;
-          a = sr[S::S_HB + 6 * cn + (lo == 0 ? hi : (lo == 1 ? 2 + hi : 5))];
-          if (p == q) a += sr[S::S_RD + 3 * cn + p];
-        }
-      } else if (r >= 3 * nclosed && c >= 3 * nclosed) a = sr[S::S_RN + (r - 3 * nclosed) * 8 + (c - 3 * nclosed)];
-      sm.G[r * LDM + c] = a;
-    }
-    if (tid < NX) { sm.bt[tid] = sr[S::S_B + tid]; sm.qt[tid] = sr[S::S_Q + tid]; sm.qd[tid] = sr[S::S_QD + tid]; }
+    if (tid < NX) { sm.bt[tid] = sr[S::S_B + tid]; sm.qt[tid] = sr[S::S_Q + tid]; }
     if (tid >= 32 && tid < 32 + MP) sm.rt[tid - 32] = sr[S::S_R + tid - 32];
+    // Qt entries this thread adds in phase 6 (pairs r <= c), held in registers so that the staging buffer can be refilled now
+    constexpr int QPT = (NX + 3) / 4;
+    double qreg[QPT];
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+      const int r = warp + 4 * q, c = lane;
+      double a = 0.0;
+      if (r < NX && c < NX && c >= r) { if (r == c) a = sr[S::S_QD + r]; if ((r < 6 || r >= 9) && (c < 6 || c >= 9)) a += sr[S::S_QT + xcol(r) * NXA + xcol(c)]; }
+      qreg[q] = a;
+    }
     __syncthreads();
+    // the staging buffer is free: prefetch the next stage record while this stage is being processed (TMA, completes on the mbarrier)
+    if (tid == 0 && k >= 1) { fence_proxy_async(); tma_load_1d(sm.stage, d.stage + (nb + k - 1) * S::SREC, REC_BYTES, &sm.bar); }
     // ---- phase 2: SA = S At, SB = S Bt, sb = s + S bt
     gemm_tiles<3, 3, 6, false, false, false, false, 4, 0>(sm.S, LD, sm.At, LD, sm.SA, LD, warp, lane);
     gemm_tiles<3, 2, 6, false, false, false, false, 4, 0>(sm.S, LD, sm.Bt, LDM, sm.SB, LDM, warp, lane);
-    if (tid >= 96 && tid < 96 + NX) { const int r = tid - 96; double a = sm.s[r]; for (int c = 0; c < NX; ++c) a += sm.S[r * LD + c] * sm.bt[c]; sm.sb[r] = a; }
+    if (warp == mw && lane < NX) { const int r = lane; double a = sm.s[r]; for (int c = 0; c < NX; ++c) a += sm.S[r * LD + c] * sm.bt[c]; sm.sb[r] = a; }
     __syncthreads();
     // ---- phase 3: H += Bt^T SA, G += Bt^T SB, g = rt + Bt^T sb
     gemm_tiles<2, 3, 6, true, false, true, false, 4, 0>(sm.Bt, LDM, sm.SA, LD, sm.H, LD, warp, lane);
     gemm_tiles<2, 2, 6, true, false, true, false, 4, 0>(sm.Bt, LDM, sm.SB, LDM, sm.G, LDM, warp, lane);
-    if (tid >= 96 && tid < 96 + MP) { const int c = tid - 96; double a = sm.rt[c]; for (int r = 0; r < NX; ++r) a += sm.Bt[r * LDM + c] * sm.sb[r]; sm.g[c] = a; }
+    if (warp == mw && lane < MP) { const int c = lane; double a = sm.rt[c]; for (int r = 0; r < NX; ++r) a += sm.Bt[r * LDM + c] * sm.sb[r]; sm.g[c] = a; }
     __syncthreads();
     // ---- phase 4: warp 0: right-looking Cholesky of G fused with the forward substitution of [H | g];  warps 1-3: S <- At^T SA
-    if (warp == 0) {
-      // lane l < MP owns column l of G (lower part) ; lane c < NX owns column c of H ; lane NX owns g
+    if (warp == cw) {
+      // lane l < MP owns column l of G (lower part) ; lane c < NX owns column c of H ; lane NX owns g.
+      // Shuffle-only right-looking elimination: the raw pivot column is broadcast from lane j while every lane computes the
+      // reciprocal square root of the pivot redundantly, so the serial chain per pivot is shuffle -> rsqrt -> one FMA.
       double gc[MP], hc[MP];
 #pragma unroll
       for (int i = 0; i < MP; ++i) { gc[i] = (lane < MP) ? sm.G[i * LDM + lane] : 0.0; hc[i] = (lane < NX) ? sm.H[i * LD + lane] : ((lane == NX) ? sm.g[i] : 0.0); }
-#pragma unroll
-      for (int j = 0; j < MP; ++j) {
-        if (j < m) {
-          double* lc = sm.lcol[j & 1];
-          if (lane == j) {
-            double dj = gc[j];
-            if (!(dj > 0.0)) { atomicOr(&d.status[b], 1); dj = 1.0; }
-            const double inv = rsqrt(dj);
-            lc[MP] = inv;
-#pragma unroll
-            for (int i = 0; i < MP; ++i) { const double v = (i == j) ? dj * inv : ((i > j) ? gc[i] * inv : 0.0); lc[i] = v; gc[i] = v; }
-          }
-          __syncwarp();
-          const double inv = lc[MP];
-          const double yj = hc[j] * inv;
-          hc[j] = yj;
-          const double ljl = (lane > j && lane < MP) ? lc[lane] : 0.0;   // L[lane][j]
-#pragma unroll
-          for (int i = 0; i < MP; ++i) if (i > j) { const double lij = lc[i]; hc[i] -= lij * yj; if (lane > j) gc[i] -= lij * ljl; }
-        }
+      bool not_pd;
+      switch (m) {   // reduced input dimensions that occur: H1 6 / 9 / 12 (FLY / single stance / double stance), G1 8 / 11 / 14
+        case 6: not_pd = chol_forward<6, MP>(gc, hc, lane); break;
+        case 9: not_pd = chol_forward<9, MP>(gc, hc, lane); break;
+        case 12: not_pd = chol_forward<12, MP>(gc, hc, lane); break;
+        case 8: not_pd = chol_forward<8, MP>(gc, hc, lane); break;
+        case 11: not_pd = chol_forward<11, MP>(gc, hc, lane); break;
+        case 14: not_pd = chol_forward<14, MP>(gc, hc, lane); break;
+        default: not_pd = chol_forward<MP, MP>(gc, hc, lane); break;   // padded pivots are identity rows
       }
+      if (not_pd && lane == 0) atomicOr(&d.status[b], 1);
 #pragma unroll
       for (int i = 0; i < MP; ++i) {
         if (lane < MP) sm.G[i * LDM + lane] = (i >= lane) ? gc[i] : 0.0;
         if (lane < NX) sm.H[i * LD + lane] = hc[i]; else if (lane == NX) sm.g[i] = hc[i];
       }
     } else {
-      gemm_tiles<3, 3, 6, true, false, false, false, 3, 1>(sm.At, LD, sm.SA, LD, sm.S, LD, warp, lane);
+      gemm_tiles<3, 3, 6, true, false, false, false, 3, 0>(sm.At, LD, sm.SA, LD, sm.S, LD, vw, lane);
     }
     __syncthreads();
     // ---- phase 5: S -= Y^T Y ; s' = qt + At^T sb - Y^T yg ; write Y, yg, L for the policy kernel
     gemm_tiles<3, 3, 4, true, false, true, true, 4, 0>(sm.H, LD, sm.H, LD, sm.S, LD, warp, lane);
-    if (tid >= 96 && tid < 96 + NX) {
-      const int c = tid - 96;
+    if (warp == mw && lane < NX) {
+      const int c = lane;
       double a = sm.qt[c];
       for (int r = 0; r < NX; ++r) a += sm.At[r * LD + c] * sm.sb[r];
       for (int r = 0; r < MP; ++r) a -= sm.H[r * LD + c] * sm.g[r];
       sm.snew[c] = a;
     }
-    for (int i = tid; i < MP * NX; i += WS_THREADS) ric[R::K_Y + i] = sm.H[(i / NX) * LD + i % NX];
-    for (int i = tid; i < MP * MP; i += WS_THREADS) ric[R::K_L + i] = sm.G[(i / MP) * LDM + i % MP];
+    for (int r = warp; r < MP; r += 4) if (lane < NX) ric[R::K_Y + r * NX + lane] = sm.H[r * LD + lane];
+    for (int r = 2 * warp + (lane >> 4); r < MP; r += 8) ric[R::K_L + r * MP + (lane & 15)] = sm.G[r * LDM + (lane & 15)];
     if (tid < MP) ric[R::K_YG + tid] = sm.g[tid];
     __syncthreads();
     // ---- phase 6: add Qt and symmetrise (each unordered pair (r, c) is owned by one thread)
-    for (int i = tid; i < NX * NX; i += WS_THREADS) {
-      const int r = i / NX, c = i % NX;
-      if (c < r) continue;
-      double a = 0.5 * (sm.S[r * LD + c] + sm.S[c * LD + r]);
-      if (r == c) a += sm.qd[r];
-      if ((r < 6 || r >= 9) && (c < 6 || c >= 9)) a += sr[S::S_QT + xcol(r) * NXA + xcol(c)];
-      sm.S[r * LD + c] = a; sm.S[c * LD + r] = a;
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+      const int r = warp + 4 * q, c = lane;
+      if (r < NX && c < NX && c >= r) {
+        const double a = 0.5 * (sm.S[r * LD + c] + sm.S[c * LD + r]) + qreg[q];
+        sm.S[r * LD + c] = a; sm.S[c * LD + r] = a;
+      }
     }
     if (tid < NX) sm.s[tid] = sm.snew[tid];
     __syncthreads();
-    // the staging buffer of this stage is free again: prefetch stage k-2 into it (TMA, completes on the buffer's mbarrier)
-    if (tid == 0 && k >= 2) { fence_proxy_async(); tma_load_1d(sm.stage[buf], d.stage + (nb + k - 2) * S::SREC, REC_BYTES, &sm.bar[buf]); }
   }
 }
 

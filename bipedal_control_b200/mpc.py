@@ -71,7 +71,7 @@ def load_library(path: str | None = None):
                  "bmpc_set_mode_schedules_device", "bmpc_gait_insert", "bmpc_gait_insert_named", "bmpc_use_gait_schedule", "bmpc_gait_peek",
                  "bmpc_advance", "bmpc_advance_async", "bmpc_synchronize", "bmpc_get_policy", "bmpc_get_device_view", "bmpc_get_performance",
                  "bmpc_get_status", "bmpc_evaluate_policy", "bmpc_get_launch_count", "bmpc_get_phase_times", "bmpc_enable_phase_timing",
-                 "bmpc_debug_copy", "bmpc_debug_record_sizes"):
+                 "bmpc_debug_copy", "bmpc_debug_record_sizes", "bmpc_debug_set_option"):
         getattr(L, name).restype = C.c_int
     if path is None:
         _lib = L
@@ -274,6 +274,9 @@ class BatchedMpcMrtInterface:
 
     def stream(self) -> int:
         return int(self.L.bmpc_get_stream(self.h) or 0)
+
+    def setOption(self, name, value):
+        self._ck(self.L.bmpc_debug_set_option(self.h, name.encode(), C.c_int(int(value))))
 
     def recordSizes(self):
         a, b, c = C.c_int(), C.c_int(), C.c_int()

@@ -245,3 +245,33 @@ def test_line_search_rejects_and_halves(oracle_h1):
         _close(perf[3:6], o.info()["after"], 1e-7, "performance after")
     g.close()
     o.reset()
+
+
+def test_split_lq_kernels_match_single_kernel_reference():
+    """k_model_base + k_lq_assemble (thread-per-stage values, warp-per-stage columns) reproduce the single-kernel k_lq record."""
+    import helpers
+    G = _gpu()
+    m = _mdl()
+    nj = m["nj"]
+    lo = np.array([m[f"joint{j}_limits"][0] for j in range(nj)]); hi = np.array([m[f"joint{j}_limits"][1] for j in range(nj)])
+    B = 48
+    X0, cmd, gait, phase = helpers.randomized_instances(B, np.asarray(m["initial_state"]), np.asarray(m["default_joint_state"]), lo, hi, seed=3)
+    ME = 40
+    ET, MS, NE = np.zeros((B, ME)), np.zeros((B, ME + 1), dtype=np.int32), np.zeros(B, dtype=np.int32)
+    for b in range(B):
+        et, ms = helpers.tiled_schedule(gait[b], phase[b], t_hi=3.0)
+        NE[b] = len(et); ET[b, :len(et)] = et; MS[b, :len(ms)] = ms
+    recs = []
+    for split in (1, 0):
+        g = G(B, model_file=MODEL, dt=0.01, time_horizon=1.0)
+        g.setOption("split_lq", split)
+        g.setCurrentObservation(np.zeros(B), X0); g.setTargetsFromCmdVel(cmd, 1.0); g.setModeSchedule(ET, MS, NE)
+        g.advanceMpc(); g.advanceMpc()
+        n = g.getPolicy(0, B, with_gains=False)["n_nodes"]
+        recs.append([g.debugCopy("lq_record", b)[:n[b] - 1] for b in (0, 7, 19, 47)])
+        g.close()
+    for ra, rb in zip(*recs):
+        scale = np.maximum(1.0, np.abs(rb))
+        # rows beyond nrows of the constraint block are never written: compare only what both kernels define
+        assert np.abs((ra - rb) / scale)[:, :22 + 171 + 198 + 44 + 24].max() < 1e-10
+        assert np.abs((ra - rb) / scale)[:, -28:].max() < 1e-10   # ev rows in use, misc, forces
