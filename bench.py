@@ -30,6 +30,7 @@ BATCH = 4096
 DT, HORIZON = 0.01, 1.0
 MPC_DT = 0.02  # mpcDesiredFrequency 50 Hz (task.info:177): the closed loop advances by one MPC period per tick
 MODEL = os.path.join(ROOT, "configs", "h1.model")
+MODELS = {"h1": MODEL, "g1": os.path.join(ROOT, "configs", "g1.model")}
 # algorithmic bytes per node: LQ record 2024 doubles written once + read once, policy record 550 written,
 # K + uff (506) read by the forward sweep
 LQ_REC, POLICY_REC, FWD_READ = 2024, 550, 506
@@ -43,10 +44,10 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
-def workload(kind, batch, rank=0):
+def workload(kind, batch, rank=0, model=None):
     import helpers
     from tools.ingest import read_model
-    mdl = read_model(MODEL)
+    mdl = read_model(model or MODEL)
     x_init = np.asarray(mdl["initial_state"])
     nx = x_init.shape[0]
     dj = np.asarray(mdl["default_joint_state"])
@@ -70,6 +71,7 @@ def workload(kind, batch, rank=0):
         lo = np.array([mdl[f"joint{j}_limits"][0] for j in range(nx - 12)])
         hi = np.array([mdl[f"joint{j}_limits"][1] for j in range(nx - 12)])
         X0, cmd, gait, phase = helpers.randomized_instances(batch, x_init, dj, lo, hi, seed=rank)
+        X0[:, 8] = x_init[8] + (X0[:, 8] - 0.93)
         CMD = cmd
         TT = np.zeros((batch, 2))
         TS = np.zeros((batch, 2, nx))
@@ -115,7 +117,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_baseline_run(sample_instances, ticks, threads, kind="identical", march_native=True):
+def cpu_baseline_run(sample_instances, ticks, threads, kind="identical", march_native=True, model=None):
     """Times the CPU oracle (restatement of the reference path; the reference's OCS2 stack cannot be built here) on host cores."""
     from oracle import pyoracle
     L = None
@@ -129,8 +131,9 @@ def cpu_baseline_run(sample_instances, ticks, threads, kind="identical", march_n
     if L is None:
         pyoracle.build()
         L = pyoracle.lib()
-    w = workload(kind, sample_instances)
-    ob = pyoracle.OracleBatch(MODEL, sample_instances, L=L)
+    model = model or MODEL
+    w = workload(kind, sample_instances, 0, model)
+    ob = pyoracle.OracleBatch(model, sample_instances, L=L)
     for b, o in enumerate(ob.inst):
         o.set_dt_horizon(DT, HORIZON)
         o.set_mode_schedule(w["ET"][b, :w["NE"][b]], w["MS"][b, :w["NE"][b] + 1])
@@ -178,6 +181,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="identical", choices=["identical", "randomized"])
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--robot", default="h1", choices=["h1", "g1"], help="g1 = BASELINE configs[3] (use --batch 8192)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="full", choices=["full", "window", "none"])
     args = ap.parse_args()
@@ -197,8 +201,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = args.batch
-    w = workload(args.workload, B, rank)
-    mpc = BatchedMpcMrtInterface(B, model_file=MODEL, device=local_rank, dt=DT, time_horizon=HORIZON)
+    model = MODELS[args.robot]
+    w = workload(args.workload, B, rank, model)
+    mpc = BatchedMpcMrtInterface(B, model_file=model, device=local_rank, dt=DT, time_horizon=HORIZON)
     stream = torch.cuda.ExternalStream(mpc.stream(), device=local_rank)
 
     # device-resident inputs for the kernel-only metric
@@ -213,31 +218,47 @@ def main():
     torch.cuda.synchronize()
 
     gather_bufs = {}
+    gstream = torch.cuda.Stream(device=dev) if world > 1 else None
+    gather_events = []   # completion events of the in-flight all-gathers (policy buffers are double buffered in the library)
 
     def gather_policies():
-        """One NCCL all-gather of the solved feedback policies per tick (north star); 'window' = nodes the consumers read before the next tick."""
+        """One NCCL all-gather of the solved feedback policies per tick (north star).  The gather runs on a side stream and overlaps
+        with the next tick's compute: the library double-buffers its policies, so the buffer being gathered is only overwritten two
+        ticks later, and that tick first waits for this gather.  'window' = only the nodes consumers read before the next tick."""
         if world == 1 or args.gather == "none":
             return 0
         v = mpc.getDeviceView()
         NS, nx, nu = v.max_nodes, v.nx, v.nu
         nbytes = 0
-        with torch.cuda.stream(stream):
+        done = torch.cuda.Event()
+        ready = torch.cuda.Event()
+        ready.record(stream)
+        gstream.wait_event(ready)
+        with torch.cuda.stream(gstream):
             for name, ptr, per in (("K", v.K, NS * nu * nx), ("uff", v.uff, NS * nu), ("x", v.x, NS * nx), ("u", v.u, NS * nu), ("t", v.times, NS)):
                 src = _alias(ptr, B * per, dev)
                 if args.gather == "window":
                     k = 4  # t0 .. t0 + 1/50 s is covered by the first 3 nodes at dt 0.01; 4 for interpolation
                     src = src.view(B, NS, -1)[:, :k].contiguous()
-                key = (name, src.numel())
+                key = (name, src.numel(), len(gather_events) & 1)
                 if key not in gather_bufs:
                     gather_bufs[key] = torch.empty(world * src.numel(), device=dev, dtype=torch.float64)
                 dist.all_gather_into_tensor(gather_bufs[key], src.reshape(-1))
                 nbytes += src.numel() * 8 * world
+            done.record(gstream)
+        gather_events.append(done)
         return nbytes
+
+    def wait_for_old_gather():
+        # the tick about to start overwrites the policy buffer that was gathered two ticks ago
+        if len(gather_events) >= 2:
+            stream.wait_event(gather_events[-2])
 
     d_cmd = torch.tensor(w["CMD"], device=dev)
 
     def device_step():
         # closed loop, everything resident in HBM: next observation from the current policy, cmd_vel target, one MPC tick
+        wait_for_old_gather()
         mpc.shiftObservations(MPC_DT)
         mpc.setTargetsFromCmdVelDevice(d_cmd.data_ptr(), 1.0)
         mpc.advanceMpcAsync()
@@ -256,6 +277,7 @@ def main():
         t_next = e2e_state["t"] + MPC_DT
         x_next, _, _ = mpc.evaluatePolicy(t_next, e2e_state["x"])
         e2e_state["t"], e2e_state["x"] = t_next, x_next
+        wait_for_old_gather()
         mpc.setCurrentObservation(t_next, x_next)
         mpc.setTargetsFromCmdVel(w["CMD"], 1.0)
         mpc.setModeSchedule(w["ET"], w["MS"], w["NE"])
@@ -322,9 +344,11 @@ def main():
     peaks, peak_kind = measured_peaks()
     ph = {k: float(np.mean([p[k] for p in phases])) for k in phases[0]} if phases else {}
     ric_ms = ph.get("riccati", 0.0)
-    ric_bytes = B * nodes_stage * (LQ_REC + POLICY_REC) * 8
+    n_ = mpc.nx
+    lq_rec, pol_rec, fwd_rd = 3 * n_ * n_ + n_ * (n_ + 1) + 3 * n_, n_ * n_ + 3 * n_, n_ * n_ + n_   # SURVEY.md 8d general formula (H1: 2024, 550, 506)
+    ric_bytes = B * nodes_stage * (lq_rec + pol_rec) * 8
     achieved = ric_bytes / (ric_ms * 1e-3) / 1e9 if ric_ms > 0 else 0.0
-    tick_bytes = B * nodes_stage * (2 * LQ_REC + POLICY_REC + FWD_READ) * 8
+    tick_bytes = B * nodes_stage * (2 * lq_rec + pol_rec + fwd_rd) * 8
     nx = mpc.nx
     h2d = 2 * B * 8 * (1 + nx) + B * 2 * 8 * (1 + nx) + B * (4 + 40 * 8 + 41 * 4)   # evaluatePolicy query + observation, targets, mode schedules
     d2h = B * 8 * 8 + B * 8 * (nx + mpc.nu) + B * 4 + 4 * int(ph.get("linesearch_trials", 1))  # performance indices + evaluatePolicy result
@@ -333,8 +357,8 @@ def main():
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": ("BASELINE configs[1]: H1 trot, horizon 1.0 s, dt 0.01 (N=100 intervals + 3 event nodes = 103 stages), batch 4096 identical instances per GPU; closed loop: every step advances t0 by 1/50 s, takes x0 from the previous policy and solves one warm-started tick"
                                 if args.workload == "identical" else "BASELINE configs[2]: H1 randomized states / velocity references / gaits (seed = rank), batch 4096 per GPU, warm-started tick"),
-                   "batch_per_gpu": B, "stages": nodes_stage, "l2": "per-tick working set (>5 GB of stage records) exceeds the 126 MB L2; no explicit flush",
-                   "policy_gather": args.gather if world > 1 else "n/a (1 GPU)"},
+                   "robot": args.robot, "batch_per_gpu": B, "stages": nodes_stage, "l2": "per-tick working set (>5 GB of stage records) exceeds the 126 MB L2; no explicit flush",
+                   "policy_gather": (args.gather + ", one all-gather per tick on a side stream, overlapped with the next tick (double-buffered policies)") if world > 1 else "n/a (1 GPU)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
                 "note": "host buffers every step: bmpc_evaluate_policy -> bmpc_set_observations -> bmpc_set_targets_from_cmd_vel -> bmpc_set_mode_schedules -> bmpc_advance -> bmpc_get_performance"},
         "gpu_launches": int(launches),
@@ -348,7 +372,7 @@ def main():
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         sample = max(threads * 4, 32)
-        val, sec, _ = cpu_baseline_run(sample, 4, threads, kind=args.workload)
+        val, sec, _ = cpu_baseline_run(sample, 4, threads, kind=args.workload, model=model)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"{sample} instances x 4 warm ticks of the same workload, one std::thread per core ({sec:.1f} s)"}
     if rank == 0:

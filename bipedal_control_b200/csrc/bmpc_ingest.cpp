@@ -222,11 +222,21 @@ HostModel load_reference_files(const std::string& task_file, const std::string& 
   // ---- reduction: movable joints in DFS order
   struct Mov { std::string name; int parent; M3 R; V3 p; V3 axis; Lump body; double lo, hi; };
   std::vector<Mov> mov; Lump base; std::map<std::string, std::pair<int, V3>> contact_at;
+  // bmpc extension: `contact_frames { name { parent <link>  x ..  y ..  z .. } }` defines contact points that are not URDF links
+  struct CFrame { std::string name, parent; V3 xyz; };
+  std::vector<CFrame> cframes;
+  if (const Info* cf = task->child("contact_frames"))
+    for (auto& c : cf->children) {
+      const std::string* par = c.second->value("parent"); const std::string *sx = c.second->value("x"), *sy = c.second->value("y"), *sz = c.second->value("z");
+      if (!par || !sx || !sy || !sz) throw std::invalid_argument("[bmpc] contact_frames." + c.first + " needs parent, x, y, z");
+      cframes.push_back({c.first, *par, V3{{std::strtod(sx->c_str(), nullptr), std::strtod(sy->c_str(), nullptr), std::strtod(sz->c_str(), nullptr)}}});
+    }
   auto is_listed = [&](const std::string& n) { for (auto& s : joint_names) if (s == n) return true; return false; };
   std::function<void(const std::string&, int, const M3&, const V3&)> visit = [&](const std::string& link, int mi, const M3& Racc, const V3& pacc) {
     const ULink& L = links[link];
     if (L.mass > 0) { Lump& body = mi < 0 ? base : mov[mi].body; body.add(L.mass, add(mul(Racc, L.com), pacc), mul(Racc, mul(L.I, tr(Racc)))); }
     for (auto& c : contact_names) if (c == link) contact_at[link] = {mi, pacc};
+    for (auto& cfr : cframes) if (cfr.parent == link) contact_at[cfr.name] = {mi, add(mul(Racc, cfr.xyz), pacc)};
     auto it = children.find(link);
     if (it == children.end()) return;
     for (int ji : it->second) {

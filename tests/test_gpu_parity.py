@@ -275,3 +275,44 @@ def test_split_lq_kernels_match_single_kernel_reference():
         # rows beyond nrows of the constraint block are never written: compare only what both kernels define
         assert np.abs((ra - rb) / scale)[:, :22 + 171 + 198 + 44 + 24].max() < 1e-10
         assert np.abs((ra - rb) / scale)[:, -28:].max() < 1e-10   # ev rows in use, misc, forces
+
+
+def test_config4_g1_second_morphology():
+    """BASELINE configs[3]: Unitree G1 (12 leg joints, nx = nu = 24), trot, N = 100: authored config (configs/g1), vs the oracle."""
+    import helpers
+    from oracle.pyoracle import Oracle
+    from tools.ingest import read_model
+    G = _gpu()
+    model = os.path.join(ROOT, "configs", "g1.model")
+    m = read_model(model)
+    nj = m["nj"]
+    assert nj == 12
+    lo = np.array([m[f"joint{j}_limits"][0] for j in range(nj)]); hi = np.array([m[f"joint{j}_limits"][1] for j in range(nj)])
+    B = 800
+    X0, cmd, gait, phase = helpers.randomized_instances(B, np.asarray(m["initial_state"]), np.asarray(m["default_joint_state"]), lo, hi, seed=4)
+    X0[:, 8] = m["initial_state"][8] + (X0[:, 8] - 0.93)          # the helper draws heights around the H1 value
+    X0[:, 12:] = np.asarray(m["initial_state"])[12:] + 0.5 * (X0[:, 12:] - np.asarray(m["default_joint_state"]))
+    ME = 40
+    ET, MS, NE = np.zeros((B, ME)), np.zeros((B, ME + 1), dtype=np.int32), np.zeros(B, dtype=np.int32)
+    TT, TS = np.zeros((B, 2)), np.zeros((B, 2, 12 + nj))
+    for b in range(B):
+        g_ = "trot" if b % 4 else gait[b]
+        et, ms = helpers.tiled_schedule(g_, phase[b], t_hi=3.0)
+        NE[b] = len(et); ET[b, :len(et)] = et; MS[b, :len(ms)] = ms
+        TT[b], TS[b] = helpers.cmd_vel_target(X0[b], 0.0, cmd[b], 1.0, m["com_height"], m["default_joint_state"])
+    g = G(B, model_file=model, dt=0.01, time_horizon=1.0)
+    assert g.nx == 24 and g.nu == 24
+    g.setCurrentObservation(np.zeros(B), X0); g.setTargetTrajectories(TT, TS); g.setModeSchedule(ET, MS, NE)
+    check = [0, 1, 2, 4, 8, 401, 799]
+    oracles = {}
+    for b in check:
+        o = Oracle(model)
+        o.set_dt_horizon(0.01, 1.0); o.set_mode_schedule(ET[b, :NE[b]], MS[b, :NE[b] + 1]); o.set_target(TT[b], TS[b])
+        oracles[b] = o
+    for tick in range(2):
+        g.advanceMpc()
+        assert not (g.getStatus() & ~16).any()
+        for b in check:
+            oracles[b].run(0.0, X0[b])
+            _compare_tick(g, oracles[b], b, rel=1e-7 if tick else REL)
+    g.close()

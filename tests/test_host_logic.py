@@ -183,3 +183,40 @@ def test_shard_range_covers_batch():
             r = [shard_range(B, k, w) for k in range(w)]
             assert r[0][0] == 0 and r[-1][1] == B and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
             assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+G1_URDF = "/root/reference/bipedal_robot_example/unitree_g1/g1_description/g1.urdf"
+
+
+@pytest.mark.skipif(not os.path.exists(G1_URDF), reason="reference tree not mounted")
+def test_g1_model_ingestion_cpp_vs_python(lib, tmp_path):
+    """Second morphology: authored configs/g1/*.info + the reference's g1.urdf (sole points via the contact_frames extension)."""
+    from tools.ingest import read_model
+    out = str(tmp_path / "g1_cpp.model")
+    cfg = os.path.join(ROOT, "configs", "g1")
+    rc = lib.bmpc_convert_model(f"{cfg}/task.info".encode(), f"{cfg}/reference.info".encode(), f"{cfg}/gait.info".encode(), G1_URDF.encode(), out.encode())
+    assert rc == 0, lib.bmpc_last_error(None)
+    a, b = read_model(out), read_model(os.path.join(ROOT, "configs", "g1.model"))
+    for k, v in b.items():
+        if not isinstance(v, str):
+            np.testing.assert_allclose(np.asarray(a[k], dtype=float), np.asarray(v, dtype=float), atol=1e-12, err_msg=k)
+    assert b["nj"] == 12 and abs(b["total_mass"] - 32.239) < 1e-3     # SURVEY.md Appendix A: 32.239 kg over 44 links
+
+
+def test_g1_oracle_soles_on_ground_and_jacobians():
+    from oracle.pyoracle import Oracle
+    o = Oracle(os.path.join(ROOT, "configs", "g1.model"))
+    assert o.nx == 24 and o.nu == 24
+    x0 = o.initial_state()
+    _, pos, _ = o.flow_map(x0, np.zeros(o.nu))
+    assert np.abs(pos[:, 2]).max() < 1e-3
+    rng = np.random.default_rng(2)
+    x = x0 + rng.normal(0, 0.1, o.nx)
+    u = rng.normal(0, 1.0, o.nu)
+    L = o.linearize(x, u)
+    eps = 1e-6
+    for i in (3, 10, 13, 17, 23):
+        xp, xm = x.copy(), x.copy()
+        xp[i] += eps; xm[i] -= eps
+        fd = (o.flow_map(xp, u)[0] - o.flow_map(xm, u)[0]) / (2 * eps)
+        assert np.abs(fd - L["A"][:, i]).max() < 1e-6

@@ -207,7 +207,7 @@ class Body:
         return self.m, c, Ic
 
 
-def reduce_model(links, joints, joint_names, contact_names, root_link=None):
+def reduce_model(links, joints, joint_names, contact_names, root_link=None, contact_frames=None):
     """Tree with only `joint_names` movable; everything else lumped at angle zero."""
     children = {}
     child_links = set()
@@ -232,6 +232,9 @@ def reduce_model(links, joints, joint_names, contact_names, root_link=None):
             body.add(L["mass"], R_acc @ L["com"] + p_acc, R_acc @ L["I"] @ R_acc.T)
         if link in contact_names:
             contacts[link] = (mov_idx, p_acc.copy())
+        for cname, (cparent, cxyz) in (contact_frames or {}).items():   # bmpc extension: contact points that are not URDF links
+            if cparent == link:
+                contacts[cname] = (mov_idx, R_acc @ np.asarray(cxyz) + p_acc)
         for jn in children.get(link, []):
             j = joints[jn]
             Rj = R_acc @ j["R"]
@@ -313,7 +316,9 @@ def build_model(task_file, reference_file, gait_file, urdf_file, name):
     joint_names = info_list(task, "model_settings.jointNames")
     contact_names = info_list(task, "model_settings.contactNames3DoF")
     links, joints = parse_urdf(urdf_file)
-    base_body, mov, contacts = reduce_model(links, joints, joint_names, contact_names)
+    cf = info_get(task, "contact_frames")
+    contact_frames = {k: (v["parent"], [float(v["x"]), float(v["y"]), float(v["z"])]) for k, v in cf.items()} if isinstance(cf, dict) else {}
+    base_body, mov, contacts = reduce_model(links, joints, joint_names, contact_names, contact_frames=contact_frames)
     nj = len(mov)
     nc = len(contacts)
     nx = 12 + nj
@@ -443,6 +448,10 @@ def read_model(path):
 
 REF = "/root/reference/bipedal_robot_example"
 ROBOTS = {
+    "g1": dict(task=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs", "g1", "task.info"),
+               reference=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs", "g1", "reference.info"),
+               gait=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs", "g1", "gait.info"),
+               urdf=f"{REF}/unitree_g1/g1_description/g1.urdf"),
     "h1": dict(task=f"{REF}/unitree_h1/h1_ocs2_config/config/task/task.info",
                reference=f"{REF}/unitree_h1/h1_ocs2_config/config/command/reference.info",
                gait=f"{REF}/unitree_h1/h1_ocs2_config/config/command/gait.info",
