@@ -1140,8 +1140,9 @@ __global__ void __launch_bounds__(WS_THREADS, 4) k_riccati(Dev d) {
 template <int NJ>
 struct PolSmem {
   static constexpr int NX = Dims<NJ>::NX, MP = 16;
+  static constexpr int NT = (NX + 1 + 7) / 8, LDK = NT * 8 + 4;   // column tiles of [Kt | kt] (H1: 3, G1: 4); ld = 4 or 12 mod 16
   double L[MP][MP + 1];
-  double Kt[MP * 28];            // [Kt | kt | 0], ld 28
+  double Kt[MP * LDK];           // [Kt | kt | 0]
   double P[(12 + NJ) * 25];      // K[r][c] * x[c] (row sums give K x)
   double rt[MP], xk[24], Nn[NJ * 8];
 };
@@ -1158,7 +1159,7 @@ __device__ __forceinline__ double stage_At_aug(const double* __restrict__ sr, in
 template <int NJ>
 __global__ void __launch_bounds__(128, 4) k_policy_expand(Dev d) {
   using D = Dims<NJ>; using R = RDims<NJ>; using S = SDims<NJ>; using PS = PolSmem<NJ>;
-  constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, MP = S::MP, WPB = 4;
+  constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, MP = S::MP, WPB = 4, NT = PS::NT, LDK = PS::LDK, NTILES = 3 * NT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   PS& sm = reinterpret_cast<PS*>(smem_raw)[warp];
@@ -1196,9 +1197,9 @@ __global__ void __launch_bounds__(128, 4) k_policy_expand(Dev d) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) lreg[i] = ric[R::K_L + lane + 32 * i];
   // accumulators of the 9 output tiles initialised with [At | bt | 0]; A fragments of Bt (24 x 16)
-  double c0[9], c1[9], af[3][4];
+  double c0[NTILES], c1[NTILES], af[3][4];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) { const int r = 8 * (t / 3) + lr, c = 8 * (t % 3) + 2 * lc; c0[t] = stage_At_aug<NJ>(sr, r, c); c1[t] = stage_At_aug<NJ>(sr, r, c + 1); }
+  for (int t = 0; t < NTILES; ++t) { const int r = 8 * (t / NT) + lr, c = 8 * (t % NT) + 2 * lc; c0[t] = stage_At_aug<NJ>(sr, r, c); c1[t] = stage_At_aug<NJ>(sr, r, c + 1); }
 #pragma unroll
   for (int mt = 0; mt < 3; ++mt)
 #pragma unroll
@@ -1230,16 +1231,16 @@ __global__ void __launch_bounds__(128, 4) k_policy_expand(Dev d) {
     z[i] = (i < m) ? a / sm.L[i][i] : 0.0;
   }
 #pragma unroll
-  for (int i = 0; i < MP; ++i) { z[i] = -z[i]; if (lane < 28) sm.Kt[i * 28 + lane] = z[i]; }
+  for (int i = 0; i < MP; ++i) { z[i] = -z[i]; if (lane < LDK) sm.Kt[i * LDK + lane] = z[i]; }
   __syncwarp();
   // ---- [Phi | phi] = [At | bt] + Bt [Kt | kt] on the FP64 tensor cores: 9 tiles x 4 k-steps, results stored straight from the fragments
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-    for (int t = 0; t < 9; ++t) dmma884(c0[t], c1[t], af[t / 3][kk], sm.Kt[(4 * kk + lc) * 28 + 8 * (t % 3) + lr]);
+    for (int t = 0; t < NTILES; ++t) dmma884(c0[t], c1[t], af[t / NT][kk], sm.Kt[(4 * kk + lc) * LDK + 8 * (t % NT) + lr]);
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const int r = 8 * (t / 3) + lr, c = 8 * (t % 3) + 2 * lc;
+  for (int t = 0; t < NTILES; ++t) {
+    const int r = 8 * (t / NT) + lr, c = 8 * (t % NT) + 2 * lc;
     if (r < NX) {
       if (c < NX) ric[R::K_PHI + r * NX + c] = c0[t]; else if (c == NX) ric[R::K_SPHI + r] = c0[t];
       if (c + 1 < NX) ric[R::K_PHI + r * NX + c + 1] = c1[t]; else if (c + 1 == NX) ric[R::K_SPHI + r] = c1[t];
