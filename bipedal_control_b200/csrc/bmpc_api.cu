@@ -111,6 +111,7 @@ void tick(bmpc_handle* h) {
   k_node_setup<NJ><<<(nodes + 127) / 128, 128, 0, st>>>(d); ++h->launches;
   mark(1);
   CK(cudaFuncSetAttribute(k_riccati<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem<NJ>)));
+  CK(cudaFuncSetAttribute(k_riccati<NJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_policy_expand<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(PolSmem<NJ>))));
   h->linesearch_trials = 0;
   for (int iter = 0; iter < h->sqp_iterations; ++iter) {
