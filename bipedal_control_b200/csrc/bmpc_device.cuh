@@ -470,6 +470,135 @@ __device__ __noinline__ void model_base(const double* __restrict__ x, const doub
   st3(base + BD::B_HTOT, hsum.n); st3(base + BD::B_HTOT + 3, hsum.p);
 }
 
+// ------------------------------------------------------------------------------------------------ warp-cooperative base record
+// Same quantities as model_base, computed by one warp with lane j = leg joint j (two serial chains of NL joints): per-joint data stays in
+// the lane's registers, parents / children are reached with shuffles, level by level along each leg.  The record is written to shared memory.
+__device__ __forceinline__ v3 shfl_v3(v3 a, int src) { return mk(__shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src), __shfl_sync(0xffffffffu, a.z, src)); }
+__device__ __forceinline__ m3 shfl_m3(const m3& a, int src) { m3 r; for (int i = 0; i < 9; ++i) r.m[i] = __shfl_sync(0xffffffffu, a.m[i], src); return r; }
+__device__ __forceinline__ SI shfl_si(const SI& a, int src) {
+  SI r; r.M = __shfl_sync(0xffffffffu, a.M, src); r.h = shfl_v3(a.h, src);
+  r.I.xx = __shfl_sync(0xffffffffu, a.I.xx, src); r.I.xy = __shfl_sync(0xffffffffu, a.I.xy, src); r.I.xz = __shfl_sync(0xffffffffu, a.I.xz, src);
+  r.I.yy = __shfl_sync(0xffffffffu, a.I.yy, src); r.I.yz = __shfl_sync(0xffffffffu, a.I.yz, src); r.I.zz = __shfl_sync(0xffffffffu, a.I.zz, src);
+  return r;
+}
+__device__ __forceinline__ Mom shfl_mom(const Mom& a, int src) { Mom r; r.n = shfl_v3(a.n, src); r.p = shfl_v3(a.p, src); return r; }
+__device__ __forceinline__ double warp_sum(double v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
+
+// jc: per-joint constants of this lane's joint in shared memory, layout [Rj 9 | pj 3 | axis 3 | mass 1 | com 3 | inertia 9] (28 doubles)
+template <int NJ>
+__device__ __forceinline__ void warp_model_base(const double* __restrict__ x, const double* __restrict__ u, double* __restrict__ base, int lane, const double* __restrict__ jc) {
+  using BD = BaseDims<NJ>;
+  constexpr int NL = Dims<NJ>::NL;
+  const DevModel& M = c_model;
+  const double mass = M.total_mass, imass = 1.0 / mass;
+  const bool act = lane < NJ;
+  const int j = act ? lane : 0, lvl_own = j % NL;
+  double sz, cz, sy, cy, sx, cx;
+  sincos(x[9], &sz, &cz); sincos(x[10], &sy, &cy); sincos(x[11], &sx, &cx);
+  m3 Rb;
+  Rb.m[0] = cz * cy; Rb.m[1] = cz * sy * sx - sz * cx; Rb.m[2] = cz * sy * cx + sz * sx;
+  Rb.m[3] = sz * cy; Rb.m[4] = sz * sy * sx + cz * cx; Rb.m[5] = sz * sy * cx - cz * sx;
+  Rb.m[6] = -sy;     Rb.m[7] = cy * sx;                Rb.m[8] = cy * cx;
+  const v3 pb = mk(x[6], x[7], x[8]);
+  v3 bax[3];
+  bax[0] = mk(0.0, 0.0, 1.0); bax[1] = mk(-sz, cz, 0.0); bax[2] = mk(cz * cy, sz * cy, -sy);
+  // ---- forward kinematics, one level of both legs at a time
+  // local transform of the own joint (parallel over lanes), then the chain R = Rp Rloc, o = Rp pj + pp level by level (shuffles)
+  m3 Rloc = mul(*reinterpret_cast<const m3*>(jc), rodrigues(jc + 12, x[12 + j]));
+  m3 R = Rb; v3 o = pb;
+#pragma unroll 1
+  for (int lvl = 0; lvl < NL; ++lvl) {
+    m3 Rp = shfl_m3(R, lane - 1); v3 pp = shfl_v3(o, lane - 1);
+    if (lvl == 0) { Rp = Rb; pp = pb; }
+    if (act && lvl_own == lvl) { o = mulc(Rp.m, jc + 9) + pp; R = mul(Rp, Rloc); }
+  }
+  // joint axis in world = R * axis (the rotation about the axis leaves it invariant), body COM and inertia
+  const v3 a = mulc(R.m, jc + 12);
+  const v3 cb = mulc(R.m, jc + 16) + o;
+  const s3 Icb = rotate_inertia(R, jc + 19);
+  // contact points live on the tip joints of the legs
+  v3 pc[NCON];
+#pragma unroll
+  for (int c = 0; c < NCON; ++c) { const v3 local = mulc(R.m, M.coff[c]) + o; pc[c] = shfl_v3(local, (c / 2) * NL + NL - 1); }
+  const v3 cbase = mulc(Rb.m, M.base_com) + pb;
+  const s3 Ibase = rotate_inertia(Rb, M.base_inertia);
+  // ---- composite inertias, leaf to root
+  SI comp = body_si(act ? jc[15] : 0.0, cb, Icb);
+#pragma unroll 1
+  for (int lvl = NL - 2; lvl >= 0; --lvl) {
+    const SI child = shfl_si(comp, lane + 1);
+    if (act && lvl_own == lvl) comp = comp + child;
+  }
+  const SI tot = body_si(M.base_mass, cbase, Ibase) + shfl_si(comp, 0) + shfl_si(comp, NL);
+  const v3 com = imass * tot.h;
+  v3 Alin_e[3], Aang_e[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { const Mom m = si_apply(tot, bax[k], cross(pb, bax[k])); Alin_e[k] = m.p; Aang_e[k] = m.n - cross(com, m.p); }
+  double A22[9], A22i[9], A12[9];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { A22[k] = Aang_e[k].x; A22[3 + k] = Aang_e[k].y; A22[6 + k] = Aang_e[k].z; A12[k] = Alin_e[k].x; A12[3 + k] = Alin_e[k].y; A12[6 + k] = Alin_e[k].z; }
+  inv3(A22, A22i);
+  v3 Alin, Aang;
+  { const Mom m = si_apply(comp, a, cross(o, a)); Alin = m.p; Aang = m.n - cross(com, m.p); }
+  // ---- generalized velocity: v_b = A_b^-1 (m h - sum_j A_j qd_j)
+  const double qd = act ? u[12 + j] : 0.0;
+  v3 ml = mk(mass * x[0] - warp_sum(qd * Alin.x), mass * x[1] - warp_sum(qd * Alin.y), mass * x[2] - warp_sum(qd * Alin.z));
+  v3 ma = mk(mass * x[3] - warp_sum(qd * Aang.x), mass * x[4] - warp_sum(qd * Aang.y), mass * x[5] - warp_sum(qd * Aang.z));
+  const v3 w = mk(A22i[0] * ma.x + A22i[1] * ma.y + A22i[2] * ma.z, A22i[3] * ma.x + A22i[4] * ma.y + A22i[5] * ma.z, A22i[6] * ma.x + A22i[7] * ma.y + A22i[8] * ma.z);
+  const v3 vlin = imass * (ml - mk(A12[0] * w.x + A12[1] * w.y + A12[2] * w.z, A12[3] * w.x + A12[4] * w.y + A12[5] * w.z, A12[6] * w.x + A12[7] * w.y + A12[8] * w.z));
+  v3 Ftot = mk(0.0, 0.0, 0.0), tau = mk(0.0, 0.0, 0.0);
+#pragma unroll
+  for (int c = 0; c < NCON; ++c) { const v3 F = mk(u[3 * c], u[3 * c + 1], u[3 * c + 2]); Ftot = Ftot + F; tau = tau + cross(pc[c] - com, F); }
+  // ---- link twists, root to leaf
+  const double wr[3] = {w.x, w.y, w.z};
+  v3 we[4], ve[4];
+  we[0] = mk(0.0, 0.0, 0.0); ve[0] = vlin;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { we[k + 1] = we[k] + wr[k] * bax[k]; ve[k + 1] = ve[k] + wr[k] * cross(pb, bax[k]); }
+  v3 wj = we[3], vj = ve[3];
+#pragma unroll 1
+  for (int lvl = 0; lvl < NL; ++lvl) {
+    v3 wp = shfl_v3(wj, lane - 1), vp = shfl_v3(vj, lane - 1);
+    if (lvl == 0) { wp = we[3]; vp = ve[3]; }
+    if (act && lvl_own == lvl) { wj = wp + qd * a; vj = vp + qd * cross(o, a); }
+  }
+  v3 vc[NCON];
+#pragma unroll
+  for (int c = 0; c < NCON; ++c) { const v3 local = cross(wj, pc[c]) + vj; vc[c] = shfl_v3(local, (c / 2) * NL + NL - 1); }
+  // ---- subtree momenta, leaf to root
+  Mom hs;
+  { const double mj = act ? jc[15] : 0.0; hs.p = mj * (vj + cross(wj, cb)); hs.n = mul(Icb, wj) + cross(cb, hs.p); }
+#pragma unroll 1
+  for (int lvl = NL - 2; lvl >= 0; --lvl) {
+    const Mom child = shfl_mom(hs, lane + 1);
+    if (act && lvl_own == lvl) hs = hs + child;
+  }
+  Mom htot;
+  { Mom bm; bm.p = M.base_mass * (ve[3] + cross(we[3], cbase)); bm.n = mul(Ibase, we[3]) + cross(cbase, bm.p); htot = bm + shfl_mom(hs, 0) + shfl_mom(hs, NL); }
+  // ---- write the record: per-joint part by the joint's lane, shared part by lane 31 (idle otherwise)
+  if (act) {
+    double* J = base + BD::B_J + BD::JS * j;
+    st3(J + BD::J_O, o); st3(J + BD::J_A, a); st_si(J + BD::J_SI, comp); st3(J + BD::J_AL, Alin); st3(J + BD::J_AA, Aang);
+    st3(J + BD::J_W, wj); st3(J + BD::J_V, vj); st3(J + BD::J_HN, hs.n); st3(J + BD::J_HP, hs.p);
+    base[BD::B_F + 12 + j] = qd;
+  }
+  if (lane == 31) {
+    st3(base + BD::B_PB, pb);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { st3(base + BD::B_BAX + 3 * k, bax[k]); st3(base + BD::B_ALE + 3 * k, Alin_e[k]); st3(base + BD::B_AAE + 3 * k, Aang_e[k]); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { st3(base + BD::B_WE + 3 * k, we[k]); st3(base + BD::B_VE + 3 * k, ve[k]); st3(base + BD::B_PC + 3 * k, pc[k]); st3(base + BD::B_VC + 3 * k, vc[k]); }
+    st_si(base + BD::B_TOT, tot); st3(base + BD::B_HTOT, htot.n); st3(base + BD::B_HTOT + 3, htot.p); st3(base + BD::B_COM, com);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { base[BD::B_A22I + i] = A22i[i]; base[BD::B_A12 + i] = A12[i]; }
+    double* f = base + BD::B_F;
+    f[0] = Ftot.x * imass; f[1] = Ftot.y * imass; f[2] = Ftot.z * imass - 9.81;
+    f[3] = tau.x * imass; f[4] = tau.y * imass; f[5] = tau.z * imass;
+    f[6] = vlin.x; f[7] = vlin.y; f[8] = vlin.z; f[9] = w.x; f[10] = w.y; f[11] = w.z;
+    st3(base + BD::B_FTOT, Ftot);
+  }
+}
+
 // relaxed log barrier [UPSTREAM RelaxedBarrierPenalty], settings task.info:280-287
 __device__ __forceinline__ void barrier_penalty(double h, double& p, double& dp, double& ddp) {
   const double mu = c_model.bar_mu, de = c_model.bar_delta;

@@ -432,14 +432,23 @@ __device__ __forceinline__ void lq_bf_column(const double* __restrict__ bs, int 
   col[2] = a == 0 ? -r.y : (a == 1 ? r.x : 0.0);
 }
 
-template <int NJ>
-__global__ void __launch_bounds__(128, 4) k_lq_assemble(Dev d) {
+template <int NJ, bool FUSED>
+__global__ void __launch_bounds__(128, FUSED ? 3 : 4) k_lq_assemble(Dev d) {
   using D = Dims<NJ>; using BD = BaseDims<NJ>;
   constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, NL = D::NL, WPB = 4, BASE = BD::BASE;
   __shared__ double sbase[WPB][2 * BASE];
   __shared__ double sA2[WPB][9][NXA + 1];
   __shared__ double sxu[WPB][4 * 24];   // x, u, xnext, xref
+  __shared__ double sjc[FUSED ? NJ : 1][28];   // per-joint model constants (lane-indexed reads of __constant__ memory would serialise)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (FUSED) {
+    for (int i = threadIdx.x; i < NJ * 28; i += 128) {
+      const int jj = i / 28, e = i % 28;
+      const DevModel& Mm = c_model;
+      sjc[jj][e] = e < 9 ? Mm.Rj[jj][e] : (e < 12 ? Mm.pj[jj][e - 9] : (e < 15 ? Mm.axis[jj][e - 12] : (e == 15 ? Mm.mass[jj] : (e < 19 ? Mm.com[jj][e - 16] : Mm.inertia[jj][e - 19]))));
+    }
+    __syncthreads();
+  }
   const int gw = blockIdx.x * WPB + warp;
   const int b = gw / d.NS, k = gw % d.NS;
   if (b >= d.B) return;
@@ -458,17 +467,30 @@ __global__ void __launch_bounds__(128, 4) k_lq_assemble(Dev d) {
     }
     return;
   }
-  // ---- stage the two base records and the linearisation point
-  const double* __restrict__ bg = d.base + (nb + k) * (size_t)(2 * BASE);
-  constexpr int NIT = (2 * BASE + 31) / 32;
-  double tmp[NIT];
-#pragma unroll
-  for (int i = 0; i < NIT; ++i) tmp[i] = (lane + 32 * i < 2 * BASE) ? bg[lane + 32 * i] : 0.0;
+  // ---- the two base records (FUSED: computed here by the warp, lane = joint; otherwise staged from k_model_base's output) and the linearisation point
   double* xs = sxu[warp]; double* us = xs + 24; double* xns = xs + 48; double* xrs = xs + 72;
-  if (lane < NX) { xs[lane] = xg[lane]; xns[lane] = xng[lane]; xrs[lane] = d.xref[(nb + k) * NX + lane]; }
-  if (lane < NU) us[lane] = d.s_u[(nb + k) * NU + lane];
+  if (FUSED) {
+    double* x2 = &sA2[warp][0][0];   // scratch for the second RK2 evaluation point (sA2 is filled later)
+    if (lane < NX) { xs[lane] = xg[lane]; xns[lane] = xng[lane]; xrs[lane] = d.xref[(nb + k) * NX + lane]; }
+    if (lane < NU) us[lane] = d.s_u[(nb + k) * NU + lane];
+    __syncwarp();
+    const double* jc = sjc[lane < NJ ? lane : 0];
+    warp_model_base<NJ>(xs, us, sbase[warp], lane, jc);
+    __syncwarp();
+    if (lane < NX) x2[lane] = xs[lane] + d.st_dt[nb + k] * sbase[warp][BD::B_F + lane];
+    __syncwarp();
+    warp_model_base<NJ>(x2, us, sbase[warp] + BASE, lane, jc);
+  } else {
+    const double* __restrict__ bg = d.base + (nb + k) * (size_t)(2 * BASE);
+    constexpr int NIT = (2 * BASE + 31) / 32;
+    double tmp[NIT];
 #pragma unroll
-  for (int i = 0; i < NIT; ++i) if (lane + 32 * i < 2 * BASE) sbase[warp][lane + 32 * i] = tmp[i];
+    for (int i = 0; i < NIT; ++i) tmp[i] = (lane + 32 * i < 2 * BASE) ? bg[lane + 32 * i] : 0.0;
+    if (lane < NX) { xs[lane] = xg[lane]; xns[lane] = xng[lane]; xrs[lane] = d.xref[(nb + k) * NX + lane]; }
+    if (lane < NU) us[lane] = d.s_u[(nb + k) * NU + lane];
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) if (lane + 32 * i < 2 * BASE) sbase[warp][lane + 32 * i] = tmp[i];
+  }
   __syncwarp();
   const double* b1 = sbase[warp]; const double* b2 = b1 + BASE;
   const DevModel& M = c_model;

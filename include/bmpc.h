@@ -153,7 +153,8 @@ void* bmpc_get_stream(bmpc_handle* h); /* cudaStream_t the library launches on *
  * instance to host.  names: "lq_record", "proj_record", "riccati_record", "dx", "du", "x_lin", "u_lin", "node_meta" */
 int bmpc_debug_copy(bmpc_handle* h, const char* name, int instance, double* dst, int capacity_doubles);
 int bmpc_debug_record_sizes(const bmpc_handle* h, int* lq_rec, int* proj_rec, int* ric_rec);
-/* options: "split_lq" 1 (default: k_model_base + k_lq_assemble) / 0 (single-kernel reference implementation k_lq) */
+/* options: "lq_mode" 2 (default: fused warp-cooperative k_lq_assemble<FUSED>), 1 (k_model_base + k_lq_assemble), 0 (single-kernel k_lq);
+ * the three implementations of the LQ approximation are cross-checked against each other in tests/ */
 int bmpc_debug_set_option(bmpc_handle* h, const char* name, int value);
 
 #ifdef __cplusplus
