@@ -155,9 +155,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = max(threads * 4, 32)
-    for _ in range(max(args.warmup, 0)):
-        pass
+    sample = max(threads * 8, 64)
     t0 = time.time()
     val, sec, nodes = cpu_baseline_run(sample, max(args.steps, 1), threads)
     line = {
@@ -343,12 +341,27 @@ def main():
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
     peaks, peak_kind = measured_peaks()
     ph = {k: float(np.mean([p[k] for p in phases])) for k in phases[0]} if phases else {}
-    ric_ms = ph.get("riccati", 0.0)
     n_ = mpc.nx
     lq_rec, pol_rec, fwd_rd = 3 * n_ * n_ + n_ * (n_ + 1) + 3 * n_, n_ * n_ + 3 * n_, n_ * n_ + n_   # SURVEY.md 8d general formula (H1: 2024, 550, 506)
-    ric_bytes = B * nodes_stage * (lq_rec + pol_rec) * 8
-    achieved = ric_bytes / (ric_ms * 1e-3) / 1e9 if ric_ms > 0 else 0.0
-    tick_bytes = B * nodes_stage * (2 * lq_rec + pol_rec + fwd_rd) * 8
+    stages_total = B * nodes_stage
+    # algorithmic bytes per launch of the three heavy kernels: the LQ kernel writes the LQ record, the Riccati kernel
+    # reads it and produces the gains of the policy record, the forward sweep reads K + uff
+    kernels = {"k_lq_assemble": ("lq", lq_rec), "k_riccati": ("riccati", lq_rec + pol_rec), "k_project": ("projection", lq_rec), "k_forward": ("forward", fwd_rd)}
+    rl_all = {}
+    for kn, (phase, doubles) in kernels.items():
+        ms_k = ph.get(phase, 0.0)
+        if ms_k > 0:
+            a = stages_total * doubles * 8 / (ms_k * 1e-3) / 1e9
+            rl_all[kn] = {"kernel_ms": ms_k, "achieved": a, "frac": a / peaks["hbm_gbs"]}
+    dominant = max((k for k in rl_all if k in ("k_lq_assemble", "k_riccati", "k_project")), key=lambda k: rl_all[k]["kernel_ms"]) if rl_all else "k_riccati"
+    ric_ms = rl_all.get(dominant, {}).get("kernel_ms", 0.0)
+    achieved = rl_all.get(dominant, {}).get("achieved", 0.0)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get(args.robot, {}).get(dominant)
+    tick_bytes = stages_total * (2 * lq_rec + pol_rec + fwd_rd) * 8
     nx = mpc.nx
     h2d = 2 * B * 8 * (1 + nx) + B * 2 * 8 * (1 + nx) + B * (4 + 40 * 8 + 41 * 4)   # evaluatePolicy query + observation, targets, mode schedules
     d2h = B * 8 * 8 + B * 8 * (nx + mpc.nu) + B * 4 + 4 * int(ph.get("linesearch_trials", 1))  # performance indices + evaluatePolicy result
@@ -363,18 +376,19 @@ def main():
                 "note": "host buffers every step: bmpc_evaluate_policy -> bmpc_set_observations -> bmpc_set_targets_from_cmd_vel -> bmpc_set_mode_schedules -> bmpc_advance -> bmpc_get_performance"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
-        "roofline": {"bound": "hbm", "kernel": "k_riccati", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"] if peaks["hbm_gbs"] else None,
-                     "traffic": None, "peak_kind": peak_kind, "kernel_ms": ric_ms,
+        "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"] if peaks["hbm_gbs"] else None,
+                     "traffic": traffic, "peak_kind": peak_kind, "kernel_ms": ric_ms, "all_kernels": rl_all,
+                     "note": "FP64 small-matrix work: the dominant kernel is FP64-pipe/latency bound, not HBM bound (DESIGN.md section 4)",
                      "whole_tick_frac": (tick_bytes / (ms_dev / args.steps * 1e-3) / 1e9) / peaks["hbm_gbs"]},
         "phase_ms": ph,
         "status_nonzero": int(np.count_nonzero(status & ~16)),
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
-        sample = max(threads * 4, 32)
-        val, sec, _ = cpu_baseline_run(sample, 4, threads, kind=args.workload, model=model)
+        sample = max(threads * 16, 64)
+        val, sec, _ = cpu_baseline_run(sample, 16, threads, kind=args.workload, model=model)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{sample} instances x 4 warm ticks of the same workload, one std::thread per core ({sec:.1f} s)"}
+                                "sample": f"{sample} instances x 16 warm closed-loop ticks of the same workload, one std::thread per core ({sec:.1f} s)"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

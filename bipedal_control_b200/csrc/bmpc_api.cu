@@ -61,7 +61,7 @@ struct bmpc_handle {
   // gait bookkeeping
   std::vector<GaitSchedule> gaits; bool use_gait = false;
   // stats
-  int launches = 0; bool timing = false; cudaEvent_t tev[9] = {}; float phase_ms[8] = {};
+  int launches = 0; bool timing = false; cudaEvent_t tev[10] = {}; float phase_ms[9] = {};
   int linesearch_trials = 0;
   // scratch for policy evaluation
   double *d_default_joints = nullptr, *d_cmd = nullptr;
@@ -124,10 +124,11 @@ void tick(bmpc_handle* h) {
     k_project<NJ><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches;
     if (iter == 0) mark(3);
     k_riccati<NJ><<<B, WS_THREADS, sizeof(RicSmem<NJ>), st>>>(d); ++h->launches;
-    k_policy_expand<NJ><<<(nodes + 3) / 4, 128, 4 * sizeof(PolSmem<NJ>), st>>>(d); ++h->launches;
     if (iter == 0) mark(4);
-    k_forward<NJ><<<(B + 3) / 4, 128, 0, st>>>(d); ++h->launches;
+    k_policy_expand<NJ><<<(nodes + 3) / 4, 128, 4 * sizeof(PolSmem<NJ>), st>>>(d); ++h->launches;
     if (iter == 0) mark(5);
+    k_forward<NJ><<<(B + 3) / 4, 128, 0, st>>>(d); ++h->launches;
+    if (iter == 0) mark(6);
     // filter line search: all instances try alpha = 1 first; the rejected ones halve their step
     for (int trial = 0; trial < 16; ++trial) {
       CK(cudaMemsetAsync(h->d_counters, 0, sizeof(int), st));
@@ -138,11 +139,11 @@ void tick(bmpc_handle* h) {
       CK(cudaStreamSynchronize(st));
       if (h->h_counters[0] == 0) break;
     }
-    if (iter == 0) mark(6);
+    if (iter == 0) mark(7);
     k_update<NJ><<<(nodes + 127) / 128, 128, 0, st>>>(d); ++h->launches;
   }
   k_policy_fill<NJ><<<B, 128, 0, st>>>(d); ++h->launches;
-  mark(7);
+  mark(8);
   CK(cudaGetLastError());
   h->cur = 1 - h->cur; h->have_solution = true;
   (void)sizeof(D); (void)sizeof(R);
@@ -390,7 +391,7 @@ int bmpc_advance_async(bmpc_handle* h) {
 int bmpc_synchronize(bmpc_handle* h) {
   API_BEGIN if (!h) return BMPC_ERR_INVALID;
   CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream));
-  if (h->timing) for (int i = 0; i < 7; ++i) cudaEventElapsedTime(&h->phase_ms[i], h->tev[i], h->tev[i + 1]);
+  if (h->timing) for (int i = 0; i < 8; ++i) cudaEventElapsedTime(&h->phase_ms[i], h->tev[i], h->tev[i + 1]);
   return BMPC_OK; API_END(h)
 }
 int bmpc_advance(bmpc_handle* h) { const int rc = bmpc_advance_async(h); return rc != BMPC_OK ? rc : bmpc_synchronize(h); }
@@ -485,7 +486,7 @@ int bmpc_debug_set_option(bmpc_handle* h, const char* name, int value) {
   return BMPC_ERR_INVALID;
 }
 int bmpc_enable_phase_timing(bmpc_handle* h, int enable) { if (!h) return BMPC_ERR_INVALID; h->timing = enable != 0; return BMPC_OK; }
-int bmpc_get_phase_times(bmpc_handle* h, float* ms) { if (!h || !ms) return BMPC_ERR_INVALID; for (int i = 0; i < 7; ++i) ms[i] = h->phase_ms[i]; ms[7] = (float)h->linesearch_trials; return BMPC_OK; }
+int bmpc_get_phase_times(bmpc_handle* h, float* ms) { if (!h || !ms) return BMPC_ERR_INVALID; for (int i = 0; i < 8; ++i) ms[i] = h->phase_ms[i]; ms[8] = (float)h->linesearch_trials; return BMPC_OK; }
 void* bmpc_get_stream(bmpc_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 int bmpc_debug_record_sizes(const bmpc_handle* h, int* lq_rec, int* proj_rec, int* ric_rec) {

@@ -265,11 +265,11 @@ class BatchedMpcMrtInterface:
         self._ck(self.L.bmpc_enable_phase_timing(self.h, C.c_int(1 if enable else 0)))
 
     def phaseTimes(self):
-        ms = (C.c_float * 8)()
+        ms = (C.c_float * 9)()
         self._ck(self.L.bmpc_get_phase_times(self.h, ms))
-        names = ["setup", "lq", "projection", "riccati", "forward", "linesearch", "finalize"]
+        names = ["setup", "lq", "projection", "riccati", "policy_expand", "forward", "linesearch", "finalize"]
         out = {k: float(ms[i]) for i, k in enumerate(names)}
-        out["linesearch_trials"] = int(ms[7])
+        out["linesearch_trials"] = int(ms[8])
         return out
 
     def stream(self) -> int:
