@@ -113,6 +113,7 @@ void tick(bmpc_handle* h) {
   CK(cudaFuncSetAttribute(k_riccati<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem<NJ>)));
   CK(cudaFuncSetAttribute(k_riccati<NJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_policy_expand<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(PolSmem<NJ>))));
+  CK(cudaFuncSetAttribute(k_forward<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(FwdSmem<NJ>))));
   h->linesearch_trials = 0;
   for (int iter = 0; iter < h->sqp_iterations; ++iter) {
     if (h->lq_mode == 2) { k_lq_assemble<NJ, true><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches; }
@@ -127,7 +128,7 @@ void tick(bmpc_handle* h) {
     if (iter == 0) mark(4);
     k_policy_expand<NJ><<<(nodes + 3) / 4, 128, 4 * sizeof(PolSmem<NJ>), st>>>(d); ++h->launches;
     if (iter == 0) mark(5);
-    k_forward<NJ><<<(B + 3) / 4, 128, 0, st>>>(d); ++h->launches;
+    k_forward<NJ><<<(B + 3) / 4, 128, 4 * sizeof(FwdSmem<NJ>), st>>>(d); ++h->launches;
     if (iter == 0) mark(6);
     // filter line search: all instances try alpha = 1 first; the rejected ones halve their step
     for (int trial = 0; trial < 16; ++trial) {
@@ -140,7 +141,7 @@ void tick(bmpc_handle* h) {
       if (h->h_counters[0] == 0) break;
     }
     if (iter == 0) mark(7);
-    k_update<NJ><<<(nodes + 127) / 128, 128, 0, st>>>(d); ++h->launches;
+    k_update<NJ><<<(unsigned)(((size_t)nodes * Dims<NJ>::NX + 255) / 256), 256, 0, st>>>(d); ++h->launches;
   }
   k_policy_fill<NJ><<<B, 128, 0, st>>>(d); ++h->launches;
   mark(8);

@@ -1320,45 +1320,82 @@ __global__ void __launch_bounds__(128, 4) k_policy_expand(Dev d) {
 
 // ------------------------------------------------------------------------------------------------ K3: forward substitution, one warp per instance
 template <int NJ>
+struct FwdSmem {
+  static constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU, LDP = NX + 1;
+  double Phi[2][NX * LDP], K[2][NU * LDP], v[2][3 * NX + NU + 2];   // double buffered: stage k+1 is fetched while stage k is applied
+  double dx[NX];
+};
+
+template <int NJ>
 __global__ void __launch_bounds__(128) k_forward(Dev d) {
-  using D = Dims<NJ>; using R = RDims<NJ>;
-  constexpr int NX = D::NX, NU = D::NU, WPB = 4, LDP = NX + 1;
-  __shared__ double sPhi[WPB][NX * LDP], sK[WPB][NU * LDP], sdx[WPB][NX], sv[WPB][3 * NX + NU];
+  using D = Dims<NJ>; using R = RDims<NJ>; using FS = FwdSmem<NJ>;
+  constexpr int NX = D::NX, NU = D::NU, WPB = 4, LDP = FS::LDP;
+  constexpr int NPH = (NX * NX + 31) / 32, NK = (NU * NX + 31) / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  FS& sm = reinterpret_cast<FS*>(smem_raw)[warp];
   const int b = blockIdx.x * WPB + warp;
   if (b >= d.B) return;
   const int N = d.n_nodes[b] - 1;
   const size_t nb = (size_t)b * d.NS;
-  double* Phi = sPhi[warp]; double* Kk = sK[warp]; double* dx = sdx[warp]; double* v = sv[warp];
+  double* dx = sm.dx;
   // dx_0 = x0 - x[0]
   double s0 = 0.0;
   if (lane < NX) { const double e = d.x0[(size_t)b * NX + lane] - d.s_x[nb * NX + lane]; dx[lane] = e; d.dx[nb * NX + lane] = e; s0 = e * e; }
   double armijo = 0.0, dxn = s0, dun = 0.0, pc = 0.0, pd = 0.0, pe = 0.0;
-  __syncwarp();
-  for (int k = 0; k < N; ++k) {
+  double rphi[NPH], rk[NK], rv[4], rperf[3] = {0.0, 0.0, 0.0};
+  auto fetch = [&](int k) {   // global -> registers (all loads independent, in flight while the previous stage is applied)
     const double* ric = d.ric + (nb + k) * R::KREC;
     const double* Kg = d.s_K + (nb + k) * (size_t)(NU * NX);
-    const double* rec = d.lq + (nb + k) * D::REC;
-    for (int i = lane; i < NX * NX; i += 32) Phi[(i / NX) * LDP + i % NX] = ric[R::K_PHI + i];
-    for (int i = lane; i < NU * NX; i += 32) Kk[(i / NX) * LDP + i % NX] = Kg[i];
-    for (int i = lane; i < NX; i += 32) { v[i] = ric[R::K_SPHI + i]; v[NX + i] = ric[R::K_G + i]; }
-    for (int i = lane; i < NU; i += 32) v[2 * NX + i] = ric[R::K_KAP + i];
-    const double misc = ric[R::K_MISC];
-    const bool is_event = ric[R::K_MISC + 1] != 0.0;
-    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NPH; ++i) { const int e = lane + 32 * i; rphi[i] = e < NX * NX ? ric[R::K_PHI + e] : 0.0; }
+#pragma unroll
+    for (int i = 0; i < NK; ++i) { const int e = lane + 32 * i; rk[i] = e < NU * NX ? Kg[e] : 0.0; }
+    rv[0] = lane < NX ? ric[R::K_SPHI + lane] : 0.0; rv[1] = lane < NX ? ric[R::K_G + lane] : 0.0; rv[2] = lane < NU ? ric[R::K_KAP + lane] : 0.0;
+    rv[3] = lane < 2 ? ric[R::K_MISC + lane] : 0.0;
+    if (lane < 3) rperf[lane] = d.lq[(nb + k) * D::REC + D::R_MISC + D::M_PCOST + lane];
+  };
+  auto stash = [&](int buf) {   // registers -> shared memory buffer
+#pragma unroll
+    for (int i = 0; i < NPH; ++i) { const int e = lane + 32 * i; if (e < NX * NX) sm.Phi[buf][(e / NX) * LDP + e % NX] = rphi[i]; }
+#pragma unroll
+    for (int i = 0; i < NK; ++i) { const int e = lane + 32 * i; if (e < NU * NX) sm.K[buf][(e / NX) * LDP + e % NX] = rk[i]; }
+    double* v = sm.v[buf];
+    if (lane < NX) { v[lane] = rv[0]; v[NX + lane] = rv[1]; }
+    if (lane < NU) v[2 * NX + lane] = rv[2];
+    if (lane < 2) v[3 * NX + NU + lane] = rv[3];
+  };
+  if (N > 0) { fetch(0); stash(0); }
+  __syncwarp();
+  for (int k = 0; k < N; ++k) {
+    const int buf = k & 1;
+    if (lane == 0) { pc += rperf[0]; } if (lane == 1) pd += rperf[1]; if (lane == 2) pe += rperf[2];
+    if (k + 1 < N) fetch(k + 1);
+    const double* Phi = sm.Phi[buf]; const double* Kk = sm.K[buf]; const double* v = sm.v[buf];
+    const double misc = v[3 * NX + NU];
+    const bool is_event = v[3 * NX + NU + 1] != 0.0;
     double nx_ = 0.0, du_ = 0.0, ga = 0.0;
     if (lane < NX) {
-      double a = v[lane]; for (int c = 0; c < NX; ++c) a += Phi[lane * LDP + c] * dx[c]; nx_ = a;
+      double a = v[lane];
+#pragma unroll
+      for (int c = 0; c < NX; ++c) a += Phi[lane * LDP + c] * dx[c];
+      nx_ = a;
       ga = v[NX + lane] * dx[lane];
     }
-    if (lane < NU) { double a = v[2 * NX + lane]; for (int c = 0; c < NX; ++c) a += Kk[lane * LDP + c] * dx[c]; du_ = is_event ? 0.0 : a; d.du[(nb + k) * NU + lane] = du_; }
+    if (lane < NU) {
+      double a = v[2 * NX + lane];
+#pragma unroll
+      for (int c = 0; c < NX; ++c) a += Kk[lane * LDP + c] * dx[c];
+      du_ = is_event ? 0.0 : a; d.du[(nb + k) * NU + lane] = du_;
+    }
     __syncwarp();
     if (lane < NX) { dx[lane] = nx_; d.dx[(nb + k + 1) * NX + lane] = nx_; }
     armijo += ga + (lane == 0 ? misc : 0.0);
     dxn += nx_ * nx_; dun += du_ * du_;
-    if (lane == 0) { pc += rec[D::R_MISC + D::M_PCOST]; pd += rec[D::R_MISC + D::M_PDYN]; pe += rec[D::R_MISC + D::M_PEQ]; }
+    if (k + 1 < N) stash(buf ^ 1);
     __syncwarp();
   }
+  pc = __shfl_sync(0xffffffffu, pc, 0); pd = __shfl_sync(0xffffffffu, pd, 1); pe = __shfl_sync(0xffffffffu, pe, 2);
   for (int o = 16; o > 0; o >>= 1) { armijo += __shfl_xor_sync(0xffffffffu, armijo, o); dxn += __shfl_xor_sync(0xffffffffu, dxn, o); dun += __shfl_xor_sync(0xffffffffu, dun, o); s0 += __shfl_xor_sync(0xffffffffu, s0, o); }
   if (lane == 0) {
     double* pf = d.perf + (size_t)b * 8;
@@ -1449,20 +1486,21 @@ __global__ void __launch_bounds__(128) k_accept(Dev d) {
 
 // ------------------------------------------------------------------------------------------------ K6: take the step, finish the policy
 template <int NJ>
-__global__ void k_update(Dev d) {
+__global__ void k_update(Dev d) {   // one thread per (instance, node, component): coalesced x += alpha dx, u += alpha du, uff += alpha kappa
   using R = RDims<NJ>;
   constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU;
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = gid / d.NS, k = gid % d.NS;
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t node = gid / NX; const int i = (int)(gid % NX);
+  const int b = (int)(node / d.NS), k = (int)(node % d.NS);
   if (b >= d.B) return;
   const int n = d.n_nodes[b];
   if (k >= n) return;
   const size_t nb = (size_t)b * d.NS;
   const double al = d.alpha[b];
-  for (int i = 0; i < NX; ++i) d.s_x[(nb + k) * NX + i] += al * d.dx[(nb + k) * NX + i];
-  if (k < n - 1 && d.node_ev[nb + k] != 1) {
-    const double* kap = d.ric + (nb + k) * R::KREC + R::K_KAP;
-    for (int i = 0; i < NU; ++i) { d.s_u[(nb + k) * NU + i] += al * d.du[(nb + k) * NU + i]; d.s_uff[(nb + k) * NU + i] += al * kap[i]; }
+  d.s_x[(nb + k) * NX + i] += al * d.dx[(nb + k) * NX + i];
+  if (i < NU && k < n - 1 && d.node_ev[nb + k] != 1) {
+    d.s_u[(nb + k) * NU + i] += al * d.du[(nb + k) * NU + i];
+    d.s_uff[(nb + k) * NU + i] += al * d.ric[(nb + k) * R::KREC + R::K_KAP + i];
   }
 }
 // event nodes and the terminal node copy input / feedforward / gain of the previous node ([UPSTREAM] toPrimalSolution)
