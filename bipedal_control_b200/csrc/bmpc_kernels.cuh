@@ -713,33 +713,45 @@ __global__ void __launch_bounds__(128) k_project(Dev d) {
   __syncwarp();
   bool anomaly = false;
   double rmax = 0.0;
-  for (int kk = 0; kk < r; ++kk) {
-    // all lanes compute the reflector of column kk redundantly (identical arithmetic)
-    double nrm2 = 0.0;
-    for (int i = kk; i < NJ; ++i) nrm2 += Mt[i][kk] * Mt[i][kk];
-    const double x0 = Mt[kk][kk];
-    const double nrm = sqrt(nrm2);
-    const double alpha = x0 >= 0.0 ? -nrm : nrm;
-    const double v0 = x0 - alpha;
-    const double vtv = nrm2 - x0 * x0 + v0 * v0;
-    const double bta = vtv > 0.0 ? 2.0 / vtv : 0.0;
-    rmax = fmax(rmax, nrm);
-    if (!(nrm > 1e-9 * rmax)) anomaly = true;
-    __syncwarp();
-    if (lane > kk && lane < r) {   // lanes kk+1..r-1 update their column
-      double s = v0 * Mt[kk][lane];
-      for (int i = kk + 1; i < NJ; ++i) s += Mt[i][kk] * Mt[i][lane];
-      s *= bta;
-      Mt[kk][lane] -= s * v0;
-      for (int i = kk + 1; i < NJ; ++i) Mt[i][lane] -= s * Mt[i][kk];
+  // Householder QR with compile-time trip counts (rows beyond r are skipped by the warp-uniform test kk < r).  Lane c < r keeps its
+  // column of Dv^T in registers; the reflector of column kk is broadcast from lane kk with shuffles (no shared-memory round trips).
+  double colv[NJ];
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) colv[i] = (lane < r) ? Mt[i][lane] : 0.0;
+#pragma unroll
+  for (int kk = 0; kk < 10; ++kk) {
+    if (kk < r) {
+      double vk[NJ];
+      double nrm2 = 0.0;
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) { vk[i] = (i >= kk) ? __shfl_sync(0xffffffffu, colv[i], kk) : 0.0; nrm2 += vk[i] * vk[i]; }
+      const double x0 = vk[kk];
+      const double nrm = nrm2 > 0.0 ? nrm2 * rsqrt(nrm2) : 0.0;
+      const double alpha = x0 >= 0.0 ? -nrm : nrm;
+      const double v0 = x0 - alpha;
+      const double vtv = nrm2 - x0 * x0 + v0 * v0;
+      const double bta = vtv > 0.0 ? 2.0 / vtv : 0.0;
+      rmax = fmax(rmax, nrm);
+      if (!(nrm > 1e-9 * rmax)) anomaly = true;
+      vk[kk] = v0;
+      if (lane > kk && lane < r) {   // apply the reflector to the own column
+        double sdot = 0.0;
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) if (i >= kk) sdot += vk[i] * colv[i];
+        sdot *= bta;
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) if (i >= kk) colv[i] -= sdot * vk[i];
+      }
+      if (lane == kk) {
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) { colv[i] = (i == kk) ? alpha : ((i > kk) ? 0.0 : colv[i]); V[kk][i] = vk[i]; }
+        beta[kk] = bta;
+      }
     }
-    __syncwarp();
-    if (lane == 0) {
-      V[kk][kk] = v0; for (int i = kk + 1; i < NJ; ++i) V[kk][i] = Mt[i][kk];
-      beta[kk] = bta; Mt[kk][kk] = alpha;
-    }
-    __syncwarp();
   }
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) if (lane < r) Mt[i][lane] = colv[i];   // R (upper triangle) for the triangular solve below
+  __syncwarp();
   // lanes 0..NXA: right-hand sides (columns of [Cv | ev]); lanes NXA+1 .. NXA+mj: null-space columns
   const int mj = NJ - r;
   double y[NJ];

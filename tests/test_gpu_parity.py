@@ -316,3 +316,55 @@ def test_config4_g1_second_morphology():
             oracles[b].run(0.0, X0[b])
             _compare_tick(g, oracles[b], b, rel=1e-7 if tick else REL)
     g.close()
+
+
+def test_two_sqp_iterations_and_reset(oracle_h1):
+    """sqpIteration = 2 (task.info:70 allows any count): both iterations re-linearise on the GPU exactly as the oracle does; reset drops the warm start."""
+    import helpers
+    G = _gpu()
+    m = _mdl()
+    o = oracle_h1
+    x0 = o.initial_state().copy()
+    x0[0] = 0.2; x0[7] = 0.05
+    et, ms = helpers.config2(22, x0, None, None)
+    tt, ts = helpers.cmd_vel_target(x0, 0.0, (0.3, 0.1, 0, 0.1), 1.0, m["com_height"], m["default_joint_state"])
+    o.reset(); o.set_sqp_iterations(2); o.set_dt_horizon(0.01, 0.5); o.set_mode_schedule(et, ms); o.set_target(tt, ts)
+    g = G(5, model_file=MODEL, dt=0.01, time_horizon=0.5, sqp_iterations=2)
+    g.setCurrentObservation(0.0, x0); g.setTargetTrajectories(tt, ts); g.setModeSchedule(et, ms)
+    try:
+        for _ in range(2):
+            o.run(0.0, x0); g.advanceMpc()
+            pol = g.getPolicy(2, 1); so = o.solution(); n = int(pol["n_nodes"][0])
+            _close(pol["x"][0][:n], so["x"], 1e-7, "x after two iterations")
+            _close(pol["u"][0][:n], so["u"], 1e-7, "u after two iterations")
+            _close(pol["K"][0][:n], so["K"], 1e-7, "K after two iterations")
+            _close(g.getPerformanceIndices()[2][3:6], o.info()["after"], 1e-7, "performance after")
+        first = g.getPolicy(0, 1)["x"][0].copy()
+        g.reset(); o.reset()
+        o.run(0.0, x0); g.advanceMpc()   # cold start again: must reproduce a cold-start solve, not the warm one
+        pol = g.getPolicy(0, 1); so = o.solution(); n = int(pol["n_nodes"][0])
+        _close(pol["x"][0][:n], so["x"], 1e-7, "x after reset")
+        assert np.abs(pol["x"][0] - first).max() > 1e-6
+    finally:
+        o.set_sqp_iterations(1); o.reset()
+        g.close()
+
+
+def test_two_handles_with_different_robots_coexist():
+    """H1 and G1 handles in one process: the model constants are re-uploaded per tick, results must not interfere."""
+    import helpers
+    G = _gpu()
+    m = _mdl()
+    x0 = np.asarray(m["initial_state"])
+    et, ms = helpers.config2(22, x0, None, None)
+    gh = G(3, model_file=MODEL, dt=0.01, time_horizon=0.3)
+    gg = G(3, model_file=os.path.join(ROOT, "configs", "g1.model"), dt=0.01, time_horizon=0.3)
+    xg = gg.initialState()
+    gh.setCurrentObservation(0.0, x0); gh.setTargetTrajectories([0.0], [x0]); gh.setModeSchedule(et, ms)
+    gg.setCurrentObservation(0.0, xg); gg.setTargetTrajectories([0.0], [xg]); gg.setModeSchedule(et, ms)
+    gh.advanceMpc(); ref = gh.getPolicy(0, 1)["K"].copy()
+    gg.advanceMpc()
+    gh.reset(); gh.advanceMpc()
+    assert np.array_equal(gh.getPolicy(0, 1)["K"], ref)
+    assert not gg.getStatus().any() and not gh.getStatus().any()
+    gh.close(); gg.close()
