@@ -64,7 +64,7 @@ struct bmpc_handle {
   int launches = 0; bool timing = false; cudaEvent_t tev[10] = {}; float phase_ms[9] = {};
   int linesearch_trials = 0;
   // scratch for policy evaluation
-  double *d_default_joints = nullptr, *d_cmd = nullptr;
+  double *d_default_joints = nullptr, *d_cmd = nullptr, *d_jc = nullptr;
   double *d_eval_t = nullptr, *d_eval_x = nullptr, *d_eval_xo = nullptr, *d_eval_uo = nullptr; int* d_eval_m = nullptr;
 };
 
@@ -81,7 +81,7 @@ Dev make_dev(bmpc_handle* h) {
   d.st_t = h->d_st_t; d.st_dt = h->d_st_dt; d.st_mode = h->d_st_mode; d.xref = h->d_xref; d.zref = h->d_zref;
   d.p_n = h->have_solution ? h->s_n[h->cur] : nullptr; d.p_t = h->s_t[h->cur]; d.p_x = h->s_x[h->cur]; d.p_u = h->s_u[h->cur];
   d.s_x = h->s_x[w]; d.s_u = h->s_u[w]; d.s_uff = h->s_uff[w]; d.s_K = h->s_K[w];
-  d.lq = h->d_lq; d.proj = h->d_proj; d.stage = h->d_stage; d.ric = h->d_ric; d.base = h->d_base; d.dx = h->d_dx; d.du = h->d_du;
+  d.lq = h->d_lq; d.proj = h->d_proj; d.stage = h->d_stage; d.ric = h->d_ric; d.base = h->d_base; d.jc = h->d_jc; d.dx = h->d_dx; d.du = h->d_du;
   d.perf_trial = h->d_perf_trial; d.perf = h->d_perf; d.alpha = h->d_alpha; d.norms = h->d_norms; d.done = h->d_done; d.status = h->d_status; d.counters = h->d_counters;
   return d;
 }
@@ -224,6 +224,17 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     h->d_done = dalloc<int>(B); h->d_status = dalloc<int>(B); h->d_counters = dalloc<int>(4); h->h_counters = halloc<int>(4);
     h->d_default_joints = dalloc<double>(MAXJ); h->d_cmd = dalloc<double>(B * 4);
     CK(cudaMemcpy(h->d_default_joints, h->model.default_joint_state.data(), sizeof(double) * h->nj, cudaMemcpyHostToDevice));
+    {  // packed per-joint constants for the lane = joint kernels
+      std::vector<double> jc((size_t)MAXJ * 28, 0.0); const DevModel& dm = h->model.dev;
+      for (int j = 0; j < h->nj; ++j) {
+        double* p = jc.data() + (size_t)j * 28;
+        for (int i = 0; i < 9; ++i) { p[i] = dm.Rj[j][i]; p[19 + i] = dm.inertia[j][i]; }
+        for (int i = 0; i < 3; ++i) { p[9 + i] = dm.pj[j][i]; p[12 + i] = dm.axis[j][i]; p[16 + i] = dm.com[j][i]; }
+        p[15] = dm.mass[j];
+      }
+      h->d_jc = dalloc<double>((size_t)MAXJ * 28);
+      CK(cudaMemcpy(h->d_jc, jc.data(), sizeof(double) * jc.size(), cudaMemcpyHostToDevice));
+    }
     h->d_eval_t = dalloc<double>(B); h->d_eval_x = dalloc<double>(B * nx); h->d_eval_xo = dalloc<double>(B * nx); h->d_eval_uo = dalloc<double>(B * nu); h->d_eval_m = dalloc<int>(B);
     // per-instance gait schedules start from reference.info's initialModeSchedule / defaultModeSequenceTemplate (BipedalRobotInterface.cpp:209-234)
     GaitSchedule g0; g0.ms.eventTimes = h->model.init_events; g0.ms.modeSequence = h->model.init_modes; g0.tmpl = h->model.default_template;
@@ -243,7 +254,7 @@ void bmpc_destroy(bmpc_handle* h) {
   void* dptrs[] = {h->d_t0, h->d_x0, h->d_tgt_t, h->d_tgt_x, h->d_ev_t, h->d_n_ev, h->d_ev_mode, h->d_st_t, h->d_st_dt, h->d_xref, h->d_zref, h->d_st_mode,
                    h->s_n[0], h->s_n[1], h->s_ev[0], h->s_ev[1], h->s_t[0], h->s_t[1], h->s_x[0], h->s_x[1], h->s_u[0], h->s_u[1], h->s_uff[0], h->s_uff[1], h->s_K[0], h->s_K[1],
                    h->d_lq, h->d_proj, h->d_stage, h->d_ric, h->d_base, h->d_dx, h->d_du, h->d_perf_trial, h->d_perf, h->d_alpha, h->d_norms, h->d_done, h->d_status, h->d_counters,
-                   h->d_eval_t, h->d_eval_x, h->d_eval_xo, h->d_eval_uo, h->d_eval_m, h->d_default_joints, h->d_cmd};
+                   h->d_eval_t, h->d_eval_x, h->d_eval_xo, h->d_eval_uo, h->d_eval_m, h->d_default_joints, h->d_cmd, h->d_jc};
   for (void* p : dptrs) if (p) cudaFree(p);
   void* hptrs[] = {h->h_t0, h->h_x0, h->h_tgt_t, h->h_tgt_x, h->h_ev_t, h->h_n_ev, h->h_ev_mode, h->h_counters};
   for (void* p : hptrs) if (p) cudaFreeHost(p);

@@ -494,7 +494,12 @@ __device__ __forceinline__ void warp_model_base(const double* __restrict__ x, co
   const bool act = lane < NJ;
   const int j = act ? lane : 0, lvl_own = j % NL;
   double sz, cz, sy, cy, sx, cx;
-  sincos(x[9], &sz, &cz); sincos(x[10], &sy, &cy); sincos(x[11], &sx, &cx);
+  {   // one sincos per lane (lane % 3 picks the Euler angle), broadcast with shuffles instead of three evaluations on every lane
+    double s_, c_; sincos(x[9 + lane % 3], &s_, &c_);
+    sz = __shfl_sync(0xffffffffu, s_, 0); cz = __shfl_sync(0xffffffffu, c_, 0);
+    sy = __shfl_sync(0xffffffffu, s_, 1); cy = __shfl_sync(0xffffffffu, c_, 1);
+    sx = __shfl_sync(0xffffffffu, s_, 2); cx = __shfl_sync(0xffffffffu, c_, 2);
+  }
   m3 Rb;
   Rb.m[0] = cz * cy; Rb.m[1] = cz * sy * sx - sz * cx; Rb.m[2] = cz * sy * cx + sz * sx;
   Rb.m[3] = sz * cy; Rb.m[4] = sz * sy * sx + cz * cx; Rb.m[5] = sz * sy * cx - cz * sx;

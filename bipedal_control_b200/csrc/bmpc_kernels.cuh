@@ -33,7 +33,7 @@ struct Dev {
   double* xref; double* zref;
   const int* p_n; const double* p_t; const double* p_x; const double* p_u;   // previous primal solution (warm start)
   double* s_x; double* s_u; double* s_uff; double* s_K;                      // new primal solution / linearisation point
-  double* lq; double* proj; double* stage; double* ric; double* base;
+  double* lq; double* proj; double* stage; double* ric; double* base; const double* jc;
   double* dx; double* du;
   double* perf_trial; double* perf; double* alpha; double* norms; int* done; int* status; int* counters;
 };
@@ -442,11 +442,7 @@ __global__ void __launch_bounds__(128, FUSED ? 3 : 4) k_lq_assemble(Dev d) {
   __shared__ double sjc[FUSED ? NJ : 1][28];   // per-joint model constants (lane-indexed reads of __constant__ memory would serialise)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (FUSED) {
-    for (int i = threadIdx.x; i < NJ * 28; i += 128) {
-      const int jj = i / 28, e = i % 28;
-      const DevModel& Mm = c_model;
-      sjc[jj][e] = e < 9 ? Mm.Rj[jj][e] : (e < 12 ? Mm.pj[jj][e - 9] : (e < 15 ? Mm.axis[jj][e - 12] : (e == 15 ? Mm.mass[jj] : (e < 19 ? Mm.com[jj][e - 16] : Mm.inertia[jj][e - 19]))));
-    }
+    for (int i = threadIdx.x; i < NJ * 28; i += 128) (&sjc[0][0])[i] = d.jc[i];   // packed [Rj 9 | pj 3 | axis 3 | mass | com 3 | inertia 9] per joint
     __syncthreads();
   }
   const int gw = blockIdx.x * WPB + warp;
@@ -545,12 +541,14 @@ __global__ void __launch_bounds__(128, FUSED ? 3 : 4) k_lq_assemble(Dev d) {
   const bool st0 = leg_in_stance(mode, 0), st1 = leg_in_stance(mode, 1);
   const int nst = 2 * (int(st0) + int(st1));
   const double fznom = nst > 0 ? M.total_mass * 9.81 / nst : 0.0;
-  if (lane < NX) rec[D::R_Q + lane] = dt * M.Qdiag[lane] * (xs[lane] - xrs[lane]);
+  double cpart = 0.0;   // this lane's share of the stage cost value (tracking cost + barrier), summed over the warp below
+  if (lane < NX) { const double dq_ = xs[lane] - xrs[lane]; rec[D::R_Q + lane] = dt * M.Qdiag[lane] * dq_; cpart = 0.5 * M.Qdiag[lane] * dq_ * dq_; }
   double shift = 0.0;
   if (lane < NCON) {
     const int c = lane;
     const bool st = (c / 2 == 0) ? st0 : st1;
     double r3[3] = {M.Rforce[3 * c] * us[3 * c], M.Rforce[3 * c + 1] * us[3 * c + 1], M.Rforce[3 * c + 2] * (us[3 * c + 2] - (st ? fznom : 0.0))};
+    cpart += 0.5 * (r3[0] * us[3 * c] + r3[1] * us[3 * c + 1] + r3[2] * (us[3 * c + 2] - (st ? fznom : 0.0)));
     double hb[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (st) {
       const double fx = us[3 * c], fy = us[3 * c + 1], fz = us[3 * c + 2];
@@ -563,6 +561,7 @@ __global__ void __launch_bounds__(128, FUSED ? 3 : 4) k_lq_assemble(Dev d) {
       hb[0] = ddp * g0 * g0 + dp * H00; hb[1] = ddp * g0 * g1 + dp * H01; hb[2] = ddp * g0 * g2;
       hb[3] = ddp * g1 * g1 + dp * H11; hb[4] = ddp * g1 * g2; hb[5] = ddp * g2 * g2;
       shift = -dp * M.fr_shift;
+      cpart += p;
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a) { rec[D::R_R + 3 * c + a] = dt * r3[a]; rec[D::R_FO + 3 * c + a] = us[3 * c + a]; }
@@ -576,7 +575,9 @@ __global__ void __launch_bounds__(128, FUSED ? 3 : 4) k_lq_assemble(Dev d) {
 #pragma unroll
     for (int j = 0; j < NJ; ++j) s += M.Rjoint[lane * NJ + j] * us[12 + j];
     rec[D::R_R + 12 + lane] = dt * s;
+    cpart += 0.5 * us[12 + lane] * s;
   }
+  const double pcost = dt * warp_sum(cpart);
   // ---- contact velocity Jacobians of the first evaluation and the compressed constraint rows
   v3 jx[NCON], ju[NCON];
   {
@@ -648,7 +649,6 @@ __global__ void __launch_bounds__(128, FUSED ? 3 : 4) k_lq_assemble(Dev d) {
     }
   }
   if (lane == 0) {
-    const double pcost = dt * stage_cost_value<NJ>(mode, xs, us, xrs);
     double* misc = rec + D::R_MISC;
     misc[D::M_DT] = dt; misc[D::M_DQ] = dt * shift; misc[D::M_DR] = dt * shift; misc[D::M_MODE] = (double)mode; misc[D::M_NROWS] = (double)nrows;
     misc[D::M_TYPE] = 0.0; misc[D::M_PCOST] = pcost; misc[D::M_PDYN] = dt * pdyn; misc[D::M_PEQ] = dt * peq;
@@ -704,12 +704,27 @@ __global__ void __launch_bounds__(128) k_project(Dev d) {
   const int r = (int)rec[D::R_MISC + D::M_NROWS];
   double (*Mt)[12] = sM[warp]; double (*V)[NJ] = sV[warp]; double* beta = sBeta[warp]; double (*G)[NXA + 1] = sG[warp];
   double (*Px)[NXA + 1] = sPx[warp]; double (*Nn)[8] = sN[warp]; double (*RN)[8] = sRN[warp];
-  for (int i = lane; i < r * NJ; i += 32) { const int row = i / NJ, col = i % NJ; Mt[col][row] = rec[D::R_DV + i]; }
-  for (int i = lane; i < r * NXA; i += 32) { const int row = i / NXA, col = i % NXA; G[row][col] = rec[D::R_CV + i]; }
-  for (int i = lane; i < r; i += 32) G[i][NXA] = rec[D::R_EV + i];
+  {   // stage Dv^T, [Cv | ev] and B_d rows 3..11: all global loads are issued before the first shared-memory store (fixed trip counts;
+      // rows >= r hold stale but finite data and are never used)
+    constexpr int N1 = (10 * NJ + 31) / 32, N2 = (10 * NXA + 31) / 32, N3 = (9 * NU + 31) / 32;
+    double t1[N1], t2[N2], t3[N3];
+#pragma unroll
+    for (int i = 0; i < N1; ++i) { const int e = lane + 32 * i; t1[i] = e < 10 * NJ ? rec[D::R_DV + e] : 0.0; }
+#pragma unroll
+    for (int i = 0; i < N2; ++i) { const int e = lane + 32 * i; t2[i] = e < 10 * NXA ? rec[D::R_CV + e] : 0.0; }
+#pragma unroll
+    for (int i = 0; i < N3; ++i) { const int e = lane + 32 * i; t3[i] = e < 9 * NU ? rec[D::R_BD + e] : 0.0; }
+    const double tev = lane < 10 ? rec[D::R_EV + lane] : 0.0;
+#pragma unroll
+    for (int i = 0; i < N1; ++i) { const int e = lane + 32 * i; if (e < 10 * NJ) Mt[e % NJ][e / NJ] = t1[i]; }
+#pragma unroll
+    for (int i = 0; i < N2; ++i) { const int e = lane + 32 * i; if (e < 10 * NXA) G[e / NXA][e % NXA] = t2[i]; }
+#pragma unroll
+    for (int i = 0; i < N3; ++i) { const int e = lane + 32 * i; if (e < 9 * NU) sBd[warp][e] = t3[i]; }
+    if (lane < 10) G[lane][NXA] = tev;
+  }
   for (int i = lane; i < 10 * NJ; i += 32) V[i / NJ][i % NJ] = 0.0;
   for (int i = lane; i < NJ * 8; i += 32) { Nn[i / 8][i % 8] = 0.0; RN[i / 8][i % 8] = 0.0; }
-  for (int i = lane; i < 9 * NU; i += 32) sBd[warp][i] = rec[D::R_BD + i];
   __syncwarp();
   bool anomaly = false;
   double rmax = 0.0;
@@ -819,20 +834,22 @@ __global__ void __launch_bounds__(128) k_project(Dev d) {
     if (is_null) { const int t = lane - NXA - 1; for (int l = 0; l < NJ; ++l) RN[l][t] = tcol[l]; }
   }
   __syncwarp();
+  // contribution of the fixed open-contact forces (du_F = -F) to rows 3..11 of bt, one row per lane 0..8
+  double open_corr = 0.0;
+  if (lane < 9) {
+    for (int cn = 0; cn < NCON; ++cn) if (!(cn / 2 == 0 ? st0 : st1))
+      for (int q = 0; q < 3; ++q) open_corr -= Bd[lane * NU + 3 * cn + q] * rec[D::R_FO + 3 * cn + q];
+  }
   if (is_rhs) {
     const int c = lane;   // X column (or the affine column NXA)
     // (At - I) rows 3..11: AdI + Bd_j Pxj ; rows 12..: dt Pxj.   Affine column: contributes to bt
+#pragma unroll
     for (int rr = 0; rr < 9; ++rr) {
       double a = 0.0;
 #pragma unroll
       for (int l = 0; l < NJ; ++l) a += Bd[rr * NU + 12 + l] * y[l];
-      if (c < NXA) so[S::S_AT + rr * NXA + c] = rec[D::R_AD + rr * NXA + c] + a;
-      else {
-        double bb = rec[D::R_B + 3 + rr] + a;
-        for (int cn = 0; cn < NCON; ++cn) if (!(cn / 2 == 0 ? st0 : st1))
-          for (int q = 0; q < 3; ++q) bb -= Bd[rr * NU + 3 * cn + q] * rec[D::R_FO + 3 * cn + q];
-        so[S::S_B + 3 + rr] = bb;
-      }
+      const double base_v = (c < NXA) ? rec[D::R_AD + rr * NXA + c] : rec[D::R_B + 3 + rr] + __shfl_sync(__activemask(), open_corr, rr);
+      if (c < NXA) so[S::S_AT + rr * NXA + c] = base_v + a; else so[S::S_B + 3 + rr] = base_v + a;
     }
 #pragma unroll
     for (int l = 0; l < NJ; ++l) {
