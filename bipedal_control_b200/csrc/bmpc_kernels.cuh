@@ -974,7 +974,7 @@ __device__ __forceinline__ void gemm_tiles(const double* __restrict__ A, int lda
 
 // Right-looking Cholesky of the (symmetric, fully stored) M x M matrix G fused with the forward substitution of [H | g], one warp,
 // shuffles only.  Lane l < MP holds column l of G in gc[], lane c holds column c of [H | g] in hc[].  On return lane j holds
-// column j of L in gc[] (rows >= j) and hc[] holds Y = L^-1 H (yg in the g lane).  Serial chain per pivot: shuffle -> rsqrt -> FMA.
+// column j of L in gc[] (rows > j; the diagonal entry holds 1 / L[j][j]) and hc[] holds Y = L^-1 H (yg in the g lane).  Serial chain per pivot: shuffle -> rsqrt -> FMA.
 template <int M, int MP>
 __device__ __forceinline__ bool chol_forward(double (&gc)[MP], double (&hc)[MP], int lane) {
   bool not_pd = false;
@@ -993,7 +993,7 @@ __device__ __forceinline__ bool chol_forward(double (&gc)[MP], double (&hc)[MP],
       gc[i] -= li * gj;
     }
     if (lane == j) {
-      gc[j] = dj * inv;
+      gc[j] = inv;   // the reciprocal of the pivot is what the back substitution in k_policy_expand needs (no divisions there)
 #pragma unroll
       for (int i = j + 1; i < M; ++i) gc[i] *= inv;
     }
@@ -1279,7 +1279,7 @@ __global__ void __launch_bounds__(128, 4) k_policy_expand(Dev d) {
     double a = z[i];
 #pragma unroll
     for (int l = i + 1; l < MP; ++l) a -= sm.L[l][i] * z[l];
-    z[i] = (i < m) ? a / sm.L[i][i] : 0.0;
+    z[i] = (i < m) ? a * sm.L[i][i] : 0.0;   // the record stores 1 / L[i][i] on the diagonal
   }
 #pragma unroll
   for (int i = 0; i < MP; ++i) { z[i] = -z[i]; if (lane < LDK) sm.Kt[i * LDK + lane] = z[i]; }
@@ -1310,20 +1310,13 @@ __global__ void __launch_bounds__(128, 4) k_policy_expand(Dev d) {
     for (int r = 0; r < 12; ++r) {
       const int cn = r / 3; const bool cl = (cn / 2 == 0) ? st0 : st1;
       double a = 0.0;
-      if (cl) {
-        const int red = (st0 ? cn : cn - 2) * 3 + r % 3;
-#pragma unroll
-        for (int q = 0; q < 12; ++q) if (q == red) a = z[q];
-      } else if (lane == NX) a = -prj[D::P_FO + r];
+      if (cl) a = sm.Kt[((st0 ? cn : cn - 2) * 3 + r % 3) * LDK + lane];
+      else if (lane == NX) a = -prj[D::P_FO + r];
       if (lane < NX) { Kg[r * NX + lane] = a; sm.P[r * 25 + lane] = a * xk_l; } else ric[R::K_KAP + r] = a;
     }
     double zn[8];   // null-space part of the own column
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      zn[t] = 0.0;
-#pragma unroll
-      for (int q = 0; q < MP; ++q) if (q == 3 * nclosed + t && t < mj) zn[t] = z[q];
-    }
+    for (int t = 0; t < 8; ++t) zn[t] = (t < mj) ? sm.Kt[(3 * nclosed + t) * LDK + lane] : 0.0;
     const bool xact = lane < 6 || (lane >= 9 && lane < NX);
     const int xc = xcol(lane);
     double pxv[NJ];
