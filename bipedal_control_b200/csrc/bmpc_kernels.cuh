@@ -19,6 +19,9 @@ constexpr int WS_THREADS = 128;     // threads per CTA of the Riccati kernel (on
 #ifndef LQ_MIN_BLOCKS
 #define LQ_MIN_BLOCKS 8
 #endif
+#ifndef LQ_FUSED_BLOCKS
+#define LQ_FUSED_BLOCKS 2
+#endif
 
 template <int NJ> struct RDims;
 template <int NJ> struct SDims;
@@ -433,7 +436,7 @@ __device__ __forceinline__ void lq_bf_column(const double* __restrict__ bs, int 
 }
 
 template <int NJ, bool FUSED>
-__global__ void __launch_bounds__(128, FUSED ? 3 : 4) k_lq_assemble(Dev d) {
+__global__ void __launch_bounds__(128, FUSED ? LQ_FUSED_BLOCKS : 4) k_lq_assemble(Dev d) {
   using D = Dims<NJ>; using BD = BaseDims<NJ>;
   constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, NL = D::NL, WPB = 4, BASE = BD::BASE;
   __shared__ double sbase[WPB][2 * BASE];
