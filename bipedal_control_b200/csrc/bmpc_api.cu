@@ -57,7 +57,7 @@ struct bmpc_handle {
   double *d_lq = nullptr, *d_proj = nullptr, *d_stage = nullptr, *d_ric = nullptr, *d_base = nullptr, *d_dx = nullptr, *d_du = nullptr, *d_perf_trial = nullptr, *d_perf = nullptr, *d_alpha = nullptr, *d_norms = nullptr;
   int *d_done = nullptr, *d_status = nullptr, *d_counters = nullptr;
   int* h_counters = nullptr;
-  size_t rec = 0, prec = 0, krec = 0, srec = 0, brec = 0; int lq_mode = 2;   // 0: k_lq, 1: k_model_base + k_lq_assemble, 2: fused warp-cooperative
+  size_t rec = 0, prec = 0, krec = 0, srec = 0, brec = 0; int lq_mode = 3;   // 0: k_lq, 1: k_model_base + k_lq_assemble, 2: fused warp-cooperative, 3: pair-packed fused (default)
   // gait bookkeeping
   std::vector<GaitSchedule> gaits; bool use_gait = false;
   // stats
@@ -112,11 +112,15 @@ void tick(bmpc_handle* h) {
   mark(1);
   CK(cudaFuncSetAttribute(k_riccati<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem<NJ>)));
   CK(cudaFuncSetAttribute(k_riccati<NJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_lq_pair<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LqPairSmem<NJ>)));
   CK(cudaFuncSetAttribute(k_policy_expand<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(PolSmem<NJ>))));
   CK(cudaFuncSetAttribute(k_forward<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(FwdSmem<NJ>))));
   h->linesearch_trials = 0;
   for (int iter = 0; iter < h->sqp_iterations; ++iter) {
-    if (h->lq_mode == 2) { k_lq_assemble<NJ, true><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches; }
+    if (h->lq_mode == 3) {
+      const int NP = (NS + 1) / 2;
+      k_lq_pair<NJ><<<(B * NP + 3) / 4, 128, sizeof(LqPairSmem<NJ>), st>>>(d); ++h->launches;
+    } else if (h->lq_mode == 2) { k_lq_assemble<NJ, true><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches; }
     else if (h->lq_mode == 1) {
       k_model_base<NJ><<<(nodes + 63) / 64, 64, 0, st>>>(d); ++h->launches;
       k_lq_assemble<NJ, false><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches;
@@ -494,7 +498,7 @@ int bmpc_get_observations(bmpc_handle* h, double* t, double* x) {
 int bmpc_get_launch_count(const bmpc_handle* h) { return h ? h->launches : 0; }
 int bmpc_debug_set_option(bmpc_handle* h, const char* name, int value) {
   if (!h || !name) return BMPC_ERR_INVALID;
-  if (std::string(name) == "lq_mode") { if (value < 0 || value > 2) return BMPC_ERR_INVALID; h->lq_mode = value; return BMPC_OK; }
+  if (std::string(name) == "lq_mode") { if (value < 0 || value > 3) return BMPC_ERR_INVALID; h->lq_mode = value; return BMPC_OK; }
   return BMPC_ERR_INVALID;
 }
 int bmpc_enable_phase_timing(bmpc_handle* h, int enable) { if (!h) return BMPC_ERR_INVALID; h->timing = enable != 0; return BMPC_OK; }

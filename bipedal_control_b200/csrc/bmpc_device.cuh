@@ -485,20 +485,26 @@ __device__ __forceinline__ Mom shfl_mom(const Mom& a, int src) { Mom r; r.n = sh
 __device__ __forceinline__ double warp_sum(double v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
 
 // jc: per-joint constants of this lane's joint in shared memory, layout [Rj 9 | pj 3 | axis 3 | mass 1 | com 3 | inertia 9] (28 doubles)
-template <int NJ>
-__device__ __forceinline__ void warp_model_base(const double* __restrict__ x, const double* __restrict__ u, double* __restrict__ base, int lane, const double* __restrict__ jc) {
+// SEG = 32: one stage per warp (lane = joint).  SEG = 16: two stages per warp, one per half-warp (lane & 15 = joint); x, u, base and jc are
+// then per-half pointers and every shuffle stays inside the lane's 16-lane segment (segment base hb).
+template <int SEG>
+__device__ __forceinline__ double seg_sum(double v) { for (int o = SEG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
+template <int NJ, int SEG = 32>
+__device__ __forceinline__ void warp_model_base(const double* __restrict__ x, const double* __restrict__ u, double* __restrict__ base, int lane_w, const double* __restrict__ jc) {
   using BD = BaseDims<NJ>;
   constexpr int NL = Dims<NJ>::NL;
+  static_assert(NJ < SEG, "one idle lane per segment writes the shared part of the record");
   const DevModel& M = c_model;
   const double mass = M.total_mass, imass = 1.0 / mass;
+  const int lane = lane_w & (SEG - 1), hb = lane_w & ~(SEG - 1);   // lane: index inside the segment; lane_w +- 1 shuffles stay inside a leg
   const bool act = lane < NJ;
   const int j = act ? lane : 0, lvl_own = j % NL;
   double sz, cz, sy, cy, sx, cx;
   {   // one sincos per lane (lane % 3 picks the Euler angle), broadcast with shuffles instead of three evaluations on every lane
     double s_, c_; sincos(x[9 + lane % 3], &s_, &c_);
-    sz = __shfl_sync(0xffffffffu, s_, 0); cz = __shfl_sync(0xffffffffu, c_, 0);
-    sy = __shfl_sync(0xffffffffu, s_, 1); cy = __shfl_sync(0xffffffffu, c_, 1);
-    sx = __shfl_sync(0xffffffffu, s_, 2); cx = __shfl_sync(0xffffffffu, c_, 2);
+    sz = __shfl_sync(0xffffffffu, s_, hb + 0); cz = __shfl_sync(0xffffffffu, c_, hb + 0);
+    sy = __shfl_sync(0xffffffffu, s_, hb + 1); cy = __shfl_sync(0xffffffffu, c_, hb + 1);
+    sx = __shfl_sync(0xffffffffu, s_, hb + 2); cx = __shfl_sync(0xffffffffu, c_, hb + 2);
   }
   m3 Rb;
   Rb.m[0] = cz * cy; Rb.m[1] = cz * sy * sx - sz * cx; Rb.m[2] = cz * sy * cx + sz * sx;
@@ -513,7 +519,7 @@ __device__ __forceinline__ void warp_model_base(const double* __restrict__ x, co
   m3 R = Rb; v3 o = pb;
 #pragma unroll 1
   for (int lvl = 0; lvl < NL; ++lvl) {
-    m3 Rp = shfl_m3(R, lane - 1); v3 pp = shfl_v3(o, lane - 1);
+    m3 Rp = shfl_m3(R, lane_w - 1); v3 pp = shfl_v3(o, lane_w - 1);
     if (lvl == 0) { Rp = Rb; pp = pb; }
     if (act && lvl_own == lvl) { o = mulc(Rp.m, jc + 9) + pp; R = mul(Rp, Rloc); }
   }
@@ -524,17 +530,17 @@ __device__ __forceinline__ void warp_model_base(const double* __restrict__ x, co
   // contact points live on the tip joints of the legs
   v3 pc[NCON];
 #pragma unroll
-  for (int c = 0; c < NCON; ++c) { const v3 local = mulc(R.m, M.coff[c]) + o; pc[c] = shfl_v3(local, (c / 2) * NL + NL - 1); }
+  for (int c = 0; c < NCON; ++c) { const v3 local = mulc(R.m, M.coff[c]) + o; pc[c] = shfl_v3(local, hb + (c / 2) * NL + NL - 1); }
   const v3 cbase = mulc(Rb.m, M.base_com) + pb;
   const s3 Ibase = rotate_inertia(Rb, M.base_inertia);
   // ---- composite inertias, leaf to root
   SI comp = body_si(act ? jc[15] : 0.0, cb, Icb);
 #pragma unroll 1
   for (int lvl = NL - 2; lvl >= 0; --lvl) {
-    const SI child = shfl_si(comp, lane + 1);
+    const SI child = shfl_si(comp, lane_w + 1);
     if (act && lvl_own == lvl) comp = comp + child;
   }
-  const SI tot = body_si(M.base_mass, cbase, Ibase) + shfl_si(comp, 0) + shfl_si(comp, NL);
+  const SI tot = body_si(M.base_mass, cbase, Ibase) + shfl_si(comp, hb) + shfl_si(comp, hb + NL);
   const v3 com = imass * tot.h;
   v3 Alin_e[3], Aang_e[3];
 #pragma unroll
@@ -547,8 +553,8 @@ __device__ __forceinline__ void warp_model_base(const double* __restrict__ x, co
   { const Mom m = si_apply(comp, a, cross(o, a)); Alin = m.p; Aang = m.n - cross(com, m.p); }
   // ---- generalized velocity: v_b = A_b^-1 (m h - sum_j A_j qd_j)
   const double qd = act ? u[12 + j] : 0.0;
-  v3 ml = mk(mass * x[0] - warp_sum(qd * Alin.x), mass * x[1] - warp_sum(qd * Alin.y), mass * x[2] - warp_sum(qd * Alin.z));
-  v3 ma = mk(mass * x[3] - warp_sum(qd * Aang.x), mass * x[4] - warp_sum(qd * Aang.y), mass * x[5] - warp_sum(qd * Aang.z));
+  v3 ml = mk(mass * x[0] - seg_sum<SEG>(qd * Alin.x), mass * x[1] - seg_sum<SEG>(qd * Alin.y), mass * x[2] - seg_sum<SEG>(qd * Alin.z));
+  v3 ma = mk(mass * x[3] - seg_sum<SEG>(qd * Aang.x), mass * x[4] - seg_sum<SEG>(qd * Aang.y), mass * x[5] - seg_sum<SEG>(qd * Aang.z));
   const v3 w = mk(A22i[0] * ma.x + A22i[1] * ma.y + A22i[2] * ma.z, A22i[3] * ma.x + A22i[4] * ma.y + A22i[5] * ma.z, A22i[6] * ma.x + A22i[7] * ma.y + A22i[8] * ma.z);
   const v3 vlin = imass * (ml - mk(A12[0] * w.x + A12[1] * w.y + A12[2] * w.z, A12[3] * w.x + A12[4] * w.y + A12[5] * w.z, A12[6] * w.x + A12[7] * w.y + A12[8] * w.z));
   v3 Ftot = mk(0.0, 0.0, 0.0), tau = mk(0.0, 0.0, 0.0);
@@ -563,31 +569,31 @@ __device__ __forceinline__ void warp_model_base(const double* __restrict__ x, co
   v3 wj = we[3], vj = ve[3];
 #pragma unroll 1
   for (int lvl = 0; lvl < NL; ++lvl) {
-    v3 wp = shfl_v3(wj, lane - 1), vp = shfl_v3(vj, lane - 1);
+    v3 wp = shfl_v3(wj, lane_w - 1), vp = shfl_v3(vj, lane_w - 1);
     if (lvl == 0) { wp = we[3]; vp = ve[3]; }
     if (act && lvl_own == lvl) { wj = wp + qd * a; vj = vp + qd * cross(o, a); }
   }
   v3 vc[NCON];
 #pragma unroll
-  for (int c = 0; c < NCON; ++c) { const v3 local = cross(wj, pc[c]) + vj; vc[c] = shfl_v3(local, (c / 2) * NL + NL - 1); }
+  for (int c = 0; c < NCON; ++c) { const v3 local = cross(wj, pc[c]) + vj; vc[c] = shfl_v3(local, hb + (c / 2) * NL + NL - 1); }
   // ---- subtree momenta, leaf to root
   Mom hs;
   { const double mj = act ? jc[15] : 0.0; hs.p = mj * (vj + cross(wj, cb)); hs.n = mul(Icb, wj) + cross(cb, hs.p); }
 #pragma unroll 1
   for (int lvl = NL - 2; lvl >= 0; --lvl) {
-    const Mom child = shfl_mom(hs, lane + 1);
+    const Mom child = shfl_mom(hs, lane_w + 1);
     if (act && lvl_own == lvl) hs = hs + child;
   }
   Mom htot;
-  { Mom bm; bm.p = M.base_mass * (ve[3] + cross(we[3], cbase)); bm.n = mul(Ibase, we[3]) + cross(cbase, bm.p); htot = bm + shfl_mom(hs, 0) + shfl_mom(hs, NL); }
-  // ---- write the record: per-joint part by the joint's lane, shared part by lane 31 (idle otherwise)
+  { Mom bm; bm.p = M.base_mass * (ve[3] + cross(we[3], cbase)); bm.n = mul(Ibase, we[3]) + cross(cbase, bm.p); htot = bm + shfl_mom(hs, hb) + shfl_mom(hs, hb + NL); }
+  // ---- write the record: per-joint part by the joint's lane, shared part by the last lane of the segment (idle otherwise)
   if (act) {
     double* J = base + BD::B_J + BD::JS * j;
     st3(J + BD::J_O, o); st3(J + BD::J_A, a); st_si(J + BD::J_SI, comp); st3(J + BD::J_AL, Alin); st3(J + BD::J_AA, Aang);
     st3(J + BD::J_W, wj); st3(J + BD::J_V, vj); st3(J + BD::J_HN, hs.n); st3(J + BD::J_HP, hs.p);
     base[BD::B_F + 12 + j] = qd;
   }
-  if (lane == 31) {
+  if (lane == SEG - 1) {
     st3(base + BD::B_PB, pb);
 #pragma unroll
     for (int k = 0; k < 3; ++k) { st3(base + BD::B_BAX + 3 * k, bax[k]); st3(base + BD::B_ALE + 3 * k, Alin_e[k]); st3(base + BD::B_AAE + 3 * k, Aang_e[k]); }

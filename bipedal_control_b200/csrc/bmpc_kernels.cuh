@@ -435,63 +435,13 @@ __device__ __forceinline__ void lq_bf_column(const double* __restrict__ bs, int 
   col[2] = a == 0 ? -r.y : (a == 1 ? r.x : 0.0);
 }
 
-template <int NJ, bool FUSED>
-__global__ void __launch_bounds__(128, FUSED ? LQ_FUSED_BLOCKS : 4) k_lq_assemble(Dev d) {
+// Column pass of one stage (lane = column): analytic d f / d x, d f / d u from the two base records b1, b2 (Heun evaluations), RK2 sensitivities,
+// cost gradient, soft friction-cone barrier, compressed constraint rows -> compact LQ record `rec`.  xs/us/xns/xrs: x_k, u_k, x_{k+1}, x_ref.
+template <int NJ>
+__device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k, double* __restrict__ rec, const double* __restrict__ b1, const double* __restrict__ b2,
+                                                 const double* xs, const double* us, const double* xns, const double* xrs, double (*sA2w)[Dims<NJ>::NXA + 1], int lane) {
   using D = Dims<NJ>; using BD = BaseDims<NJ>;
-  constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, NL = D::NL, WPB = 4, BASE = BD::BASE;
-  __shared__ double sbase[WPB][2 * BASE];
-  __shared__ double sA2[WPB][9][NXA + 1];
-  __shared__ double sxu[WPB][4 * 24];   // x, u, xnext, xref
-  __shared__ double sjc[FUSED ? NJ : 1][28];   // per-joint model constants (lane-indexed reads of __constant__ memory would serialise)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (FUSED) {
-    for (int i = threadIdx.x; i < NJ * 28; i += 128) (&sjc[0][0])[i] = d.jc[i];   // packed [Rj 9 | pj 3 | axis 3 | mass | com 3 | inertia 9] per joint
-    __syncthreads();
-  }
-  const int gw = blockIdx.x * WPB + warp;
-  const int b = gw / d.NS, k = gw % d.NS;
-  if (b >= d.B) return;
-  const int N = d.n_nodes[b] - 1;
-  if (k >= N) return;
-  const size_t nb = (size_t)b * d.NS;
-  double* __restrict__ rec = d.lq + (nb + k) * D::REC;
-  const double* xg = d.s_x + (nb + k) * NX; const double* xng = xg + NX;
-  if (d.node_ev[nb + k] == 1) {   // [UPSTREAM] setupEventNode
-    double s = 0.0;
-    if (lane < NX) { const double bi = xg[lane] - xng[lane]; rec[D::R_B + lane] = bi; s = bi * bi; }
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
-      rec[D::R_MISC + D::M_TYPE] = 1.0; rec[D::R_MISC + D::M_DT] = 0.0; rec[D::R_MISC + D::M_MODE] = -1.0;
-      rec[D::R_MISC + D::M_PCOST] = 0.0; rec[D::R_MISC + D::M_PDYN] = s; rec[D::R_MISC + D::M_PEQ] = 0.0;
-    }
-    return;
-  }
-  // ---- the two base records (FUSED: computed here by the warp, lane = joint; otherwise staged from k_model_base's output) and the linearisation point
-  double* xs = sxu[warp]; double* us = xs + 24; double* xns = xs + 48; double* xrs = xs + 72;
-  if (FUSED) {
-    double* x2 = &sA2[warp][0][0];   // scratch for the second RK2 evaluation point (sA2 is filled later)
-    if (lane < NX) { xs[lane] = xg[lane]; xns[lane] = xng[lane]; xrs[lane] = d.xref[(nb + k) * NX + lane]; }
-    if (lane < NU) us[lane] = d.s_u[(nb + k) * NU + lane];
-    __syncwarp();
-    const double* jc = sjc[lane < NJ ? lane : 0];
-    warp_model_base<NJ>(xs, us, sbase[warp], lane, jc);
-    __syncwarp();
-    if (lane < NX) x2[lane] = xs[lane] + d.st_dt[nb + k] * sbase[warp][BD::B_F + lane];
-    __syncwarp();
-    warp_model_base<NJ>(x2, us, sbase[warp] + BASE, lane, jc);
-  } else {
-    const double* __restrict__ bg = d.base + (nb + k) * (size_t)(2 * BASE);
-    constexpr int NIT = (2 * BASE + 31) / 32;
-    double tmp[NIT];
-#pragma unroll
-    for (int i = 0; i < NIT; ++i) tmp[i] = (lane + 32 * i < 2 * BASE) ? bg[lane + 32 * i] : 0.0;
-    if (lane < NX) { xs[lane] = xg[lane]; xns[lane] = xng[lane]; xrs[lane] = d.xref[(nb + k) * NX + lane]; }
-    if (lane < NU) us[lane] = d.s_u[(nb + k) * NU + lane];
-#pragma unroll
-    for (int i = 0; i < NIT; ++i) if (lane + 32 * i < 2 * BASE) sbase[warp][lane + 32 * i] = tmp[i];
-  }
-  __syncwarp();
-  const double* b1 = sbase[warp]; const double* b2 = b1 + BASE;
+  constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, NL = D::NL;
   const DevModel& M = c_model;
   const double dt = d.st_dt[nb + k];
   const int mode = d.st_mode[nb + k];
@@ -503,7 +453,7 @@ __global__ void __launch_bounds__(128, FUSED ? LQ_FUSED_BLOCKS : 4) k_lq_assembl
   if (lane < 12) { lq_bf_column<NJ>(b1, lane, bf1); lq_bf_column<NJ>(b2, lane, bf2); }
   if (lane < NXA) {
 #pragma unroll
-    for (int r = 0; r < 9; ++r) sA2[warp][r][lane] = a2[r];
+    for (int r = 0; r < 9; ++r) sA2w[r][lane] = a2[r];
   }
   __syncwarp();
   // ---- dynamics: b, (A_d - I), B_d   [UPSTREAM SensitivityIntegrator RK2]
@@ -515,7 +465,7 @@ __global__ void __launch_bounds__(128, FUSED ? LQ_FUSED_BLOCKS : 4) k_lq_assembl
     for (int r = 0; r < 9; ++r) {
       double s = 0.0;
 #pragma unroll
-      for (int t = 0; t < 3; ++t) s += sA2[warp][r][3 + t] * a1[t] + sA2[warp][r][6 + t] * a1[6 + t];
+      for (int t = 0; t < 3; ++t) s += sA2w[r][3 + t] * a1[t] + sA2w[r][6 + t] * a1[6 + t];
       rec[D::R_AD + r * NXA + lane] = hdt * (a1[r] + a2[r] + dt * s);
     }
   }
@@ -523,9 +473,9 @@ __global__ void __launch_bounds__(128, FUSED ? LQ_FUSED_BLOCKS : 4) k_lq_assembl
     const int a = lane % 3;
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
-      double s = sA2[warp][r][a] * imass;
+      double s = sA2w[r][a] * imass;
 #pragma unroll
-      for (int t = 0; t < 3; ++t) s += sA2[warp][r][3 + t] * bf1[t];
+      for (int t = 0; t < 3; ++t) s += sA2w[r][3 + t] * bf1[t];
       const double b12 = r < 3 ? (bf1[r] + bf2[r]) : 0.0;
       rec[D::R_BD + r * NU + lane] = hdt * (b12 + dt * s);
     }
@@ -533,9 +483,9 @@ __global__ void __launch_bounds__(128, FUSED ? LQ_FUSED_BLOCKS : 4) k_lq_assembl
   if (lane < NJ) {
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
-      double s = sA2[warp][r][9 + lane];
+      double s = sA2w[r][9 + lane];
 #pragma unroll
-      for (int t = 0; t < 3; ++t) s += sA2[warp][r][6 + t] * bj1[3 + t];
+      for (int t = 0; t < 3; ++t) s += sA2w[r][6 + t] * bj1[3 + t];
       const double b12 = r >= 3 ? (bj1[r - 3] + bj2[r - 3]) : 0.0;
       rec[D::R_BD + r * NU + 12 + lane] = hdt * (b12 + dt * s);
     }
@@ -655,6 +605,141 @@ __global__ void __launch_bounds__(128, FUSED ? LQ_FUSED_BLOCKS : 4) k_lq_assembl
     double* misc = rec + D::R_MISC;
     misc[D::M_DT] = dt; misc[D::M_DQ] = dt * shift; misc[D::M_DR] = dt * shift; misc[D::M_MODE] = (double)mode; misc[D::M_NROWS] = (double)nrows;
     misc[D::M_TYPE] = 0.0; misc[D::M_PCOST] = pcost; misc[D::M_PDYN] = dt * pdyn; misc[D::M_PEQ] = dt * peq;
+  }
+}
+
+template <int NJ, bool FUSED>
+__global__ void __launch_bounds__(128, FUSED ? LQ_FUSED_BLOCKS : 4) k_lq_assemble(Dev d) {
+  using D = Dims<NJ>; using BD = BaseDims<NJ>;
+  constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, NL = D::NL, WPB = 4, BASE = BD::BASE;
+  __shared__ double sbase[WPB][2 * BASE];
+  __shared__ double sA2[WPB][9][NXA + 1];
+  __shared__ double sxu[WPB][4 * 24];   // x, u, xnext, xref
+  __shared__ double sjc[FUSED ? NJ : 1][28];   // per-joint model constants (lane-indexed reads of __constant__ memory would serialise)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (FUSED) {
+    for (int i = threadIdx.x; i < NJ * 28; i += 128) (&sjc[0][0])[i] = d.jc[i];   // packed [Rj 9 | pj 3 | axis 3 | mass | com 3 | inertia 9] per joint
+    __syncthreads();
+  }
+  const int gw = blockIdx.x * WPB + warp;
+  const int b = gw / d.NS, k = gw % d.NS;
+  if (b >= d.B) return;
+  const int N = d.n_nodes[b] - 1;
+  if (k >= N) return;
+  const size_t nb = (size_t)b * d.NS;
+  double* __restrict__ rec = d.lq + (nb + k) * D::REC;
+  const double* xg = d.s_x + (nb + k) * NX; const double* xng = xg + NX;
+  if (d.node_ev[nb + k] == 1) {   // [UPSTREAM] setupEventNode
+    double s = 0.0;
+    if (lane < NX) { const double bi = xg[lane] - xng[lane]; rec[D::R_B + lane] = bi; s = bi * bi; }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      rec[D::R_MISC + D::M_TYPE] = 1.0; rec[D::R_MISC + D::M_DT] = 0.0; rec[D::R_MISC + D::M_MODE] = -1.0;
+      rec[D::R_MISC + D::M_PCOST] = 0.0; rec[D::R_MISC + D::M_PDYN] = s; rec[D::R_MISC + D::M_PEQ] = 0.0;
+    }
+    return;
+  }
+  // ---- the two base records (FUSED: computed here by the warp, lane = joint; otherwise staged from k_model_base's output) and the linearisation point
+  double* xs = sxu[warp]; double* us = xs + 24; double* xns = xs + 48; double* xrs = xs + 72;
+  if (FUSED) {
+    double* x2 = &sA2[warp][0][0];   // scratch for the second RK2 evaluation point (sA2 is filled later)
+    if (lane < NX) { xs[lane] = xg[lane]; xns[lane] = xng[lane]; xrs[lane] = d.xref[(nb + k) * NX + lane]; }
+    if (lane < NU) us[lane] = d.s_u[(nb + k) * NU + lane];
+    __syncwarp();
+    const double* jc = sjc[lane < NJ ? lane : 0];
+    warp_model_base<NJ>(xs, us, sbase[warp], lane, jc);
+    __syncwarp();
+    if (lane < NX) x2[lane] = xs[lane] + d.st_dt[nb + k] * sbase[warp][BD::B_F + lane];
+    __syncwarp();
+    warp_model_base<NJ>(x2, us, sbase[warp] + BASE, lane, jc);
+  } else {
+    const double* __restrict__ bg = d.base + (nb + k) * (size_t)(2 * BASE);
+    constexpr int NIT = (2 * BASE + 31) / 32;
+    double tmp[NIT];
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) tmp[i] = (lane + 32 * i < 2 * BASE) ? bg[lane + 32 * i] : 0.0;
+    if (lane < NX) { xs[lane] = xg[lane]; xns[lane] = xng[lane]; xrs[lane] = d.xref[(nb + k) * NX + lane]; }
+    if (lane < NU) us[lane] = d.s_u[(nb + k) * NU + lane];
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) if (lane + 32 * i < 2 * BASE) sbase[warp][lane + 32 * i] = tmp[i];
+  }
+  __syncwarp();
+  lq_stage_columns<NJ>(d, nb, k, rec, sbase[warp], sbase[warp] + BASE, xs, us, xns, xrs, sA2[warp], lane);
+}
+
+// Pair-packed LQ kernel (default): one warp per TWO consecutive stages of an instance.  The base pass (lane & 15 = leg joint) runs for both
+// stages at once, one per half-warp, so 2 NJ of 32 lanes are busy instead of NJ; the column pass (lane = column) then handles the two stages
+// one after the other.  A half whose stage is an event node or beyond the horizon mirrors the other half's inputs (results discarded).
+template <int NJ>
+struct LqPairSmem {
+  static constexpr int BASE = BaseDims<NJ>::BASE, NXA = Dims<NJ>::NXA, WPB = 4;
+  double jc[NJ][28];
+  double base[WPB][2][2 * BASE];
+  double A2[WPB][9][NXA + 1];
+  double xu[WPB][2][4 * 24];   // per stage: x, u, xnext, xref
+};
+template <int NJ>
+__global__ void __launch_bounds__(128, 2) k_lq_pair(Dev d) {
+  using D = Dims<NJ>; using BD = BaseDims<NJ>; using SM = LqPairSmem<NJ>;
+  constexpr int NX = D::NX, NU = D::NU, WPB = SM::WPB, BASE = BD::BASE;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SM& sm = *reinterpret_cast<SM*>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < NJ * 28; i += 128) (&sm.jc[0][0])[i] = d.jc[i];
+  __syncthreads();
+  const int NP = (d.NS + 1) >> 1;
+  const int gw = blockIdx.x * WPB + warp;
+  const int b = gw / NP, k0 = 2 * (gw % NP);
+  if (b >= d.B) return;
+  const int N = d.n_nodes[b] - 1;
+  if (k0 >= N) return;
+  const size_t nb = (size_t)b * d.NS;
+  const bool has1 = k0 + 1 < N;
+  const bool ev0 = d.node_ev[nb + k0] == 1, ev1 = has1 && d.node_ev[nb + k0 + 1] == 1;
+  const bool comp0 = !ev0, comp1 = has1 && !ev1;   // stages that need the model
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    if (s == 1 && !has1) break;
+    const int k = k0 + s;
+    double* xs = sm.xu[warp][s];
+    if (lane < NX) { xs[lane] = d.s_x[(nb + k) * NX + lane]; xs[48 + lane] = d.s_x[(nb + k + 1) * NX + lane]; xs[72 + lane] = d.xref[(nb + k) * NX + lane]; }
+    if (lane < NU) xs[24 + lane] = d.s_u[(nb + k) * NU + lane];
+  }
+  __syncwarp();
+  if (comp0 || comp1) {
+    const int h = lane >> 4;
+    const int ms = (h == 0) ? (comp0 ? 0 : 1) : (comp1 ? 1 : 0);   // stage whose inputs this half evaluates
+    const double* xh = sm.xu[warp][ms]; const double* uh = xh + 24;
+    double* bh = sm.base[warp][h];
+    const double* jc = sm.jc[(lane & 15) < NJ ? (lane & 15) : 0];
+    double* x2 = &sm.A2[warp][0][0];   // scratch for the second RK2 evaluation points (A2 is filled later): 2 x 24 doubles
+    warp_model_base<NJ, 16>(xh, uh, bh, lane, jc);
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      if (lane < NX) x2[24 * s + lane] = sm.xu[warp][s][lane] + d.st_dt[nb + k0 + (s == 1 && !has1 ? 0 : s)] * sm.base[warp][s][BD::B_F + lane];
+    __syncwarp();
+    warp_model_base<NJ, 16>(x2 + 24 * ms, uh, bh + BASE, lane, jc);
+    __syncwarp();
+  }
+#pragma unroll 1
+  for (int s = 0; s < 2; ++s) {
+    if (s == 1 && !has1) break;
+    const int k = k0 + s;
+    double* __restrict__ rec = d.lq + (nb + k) * D::REC;
+    const double* xs = sm.xu[warp][s];
+    if (s == 0 ? ev0 : ev1) {   // [UPSTREAM] setupEventNode
+      double sq = 0.0;
+      if (lane < NX) { const double bi = xs[lane] - xs[48 + lane]; rec[D::R_B + lane] = bi; sq = bi * bi; }
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      if (lane == 0) {
+        rec[D::R_MISC + D::M_TYPE] = 1.0; rec[D::R_MISC + D::M_DT] = 0.0; rec[D::R_MISC + D::M_MODE] = -1.0;
+        rec[D::R_MISC + D::M_PCOST] = 0.0; rec[D::R_MISC + D::M_PDYN] = sq; rec[D::R_MISC + D::M_PEQ] = 0.0;
+      }
+      continue;
+    }
+    lq_stage_columns<NJ>(d, nb, k, rec, sm.base[warp][s], sm.base[warp][s] + BASE, xs, xs + 24, xs + 48, xs + 72, sm.A2[warp], lane);
+    __syncwarp();   // A2 is reused by the next stage
   }
 }
 
