@@ -226,6 +226,12 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     h->d_dx = dalloc<double>(B * NS * nx); h->d_du = dalloc<double>(B * NS * nu);
     h->d_perf_trial = dalloc<double>(B * NS * 3); h->d_perf = dalloc<double>(B * 8); h->d_alpha = dalloc<double>(B); h->d_norms = dalloc<double>(B * 2);
     h->d_done = dalloc<int>(B); h->d_status = dalloc<int>(B); h->d_counters = dalloc<int>(4); h->h_counters = halloc<int>(4);
+    {  // static entries of the projected stage records (identity rows / columns of At); everything else was zeroed by dalloc
+      const size_t nrec = B * NS;
+      if (h->nj == 10) k_stage_static<10><<<(unsigned)((nrec + 255) / 256), 256>>>(h->d_stage, nrec);
+      else k_stage_static<12><<<(unsigned)((nrec + 255) / 256), 256>>>(h->d_stage, nrec);
+      CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+    }
     h->d_default_joints = dalloc<double>(MAXJ); h->d_cmd = dalloc<double>(B * 4);
     CK(cudaMemcpy(h->d_default_joints, h->model.default_joint_state.data(), sizeof(double) * h->nj, cudaMemcpyHostToDevice));
     {  // packed per-joint constants for the lane = joint kernels

@@ -751,14 +751,36 @@ __global__ void __launch_bounds__(128, 2) k_lq_pair(Dev d) {
 //  (2) changeOfInputVariables [UPSTREAM] with du = Pe + Px dx + Pu dut, exploiting the block structure
 //      (forces of closed contacts stay free, forces of open contacts are fixed to -F, joint velocities = Pej + Pxj dx + N dut_null):
 //      writes the projected stage record (SDims) that the sequential Riccati kernel consumes.
+// Projected stage record (k_project -> k_riccati, k_policy_expand), padded to NXP = 24 states / MP = 16 reduced inputs:
+//   [AB | bt | qt | rt | meta]  one contiguous block that the Riccati kernel stages with a single TMA bulk copy:
+//       AB = [At | Bt] (24 x 42, row major; columns 0..23 = At incl. identity, 24..39 = Bt, 40..41 pad).  The leading dimension 42 = 2 mod 4
+//       makes the k-permuted transposed DMMA fragment loads of k_riccati bank-conflict free.
+//   QF  = Qt (24 x 24, full, diagonal included) in DMMA accumulator-fragment order: [tile 3x3][lane][2]
+//   PRF = [Pt | Rt] (16 x 40) in accumulator-fragment order: [tile 2x5][lane][2]   (Rt padded with the identity beyond m)
+// Entries that never change (identity rows 0..2 / columns 6..8 of At, padding) are written once by k_stage_static at bmpc_create.
 template <int NJ>
 struct SDims {
-  static constexpr int NX = Dims<NJ>::NX, NXA = Dims<NJ>::NXA, NXR = NX - 3, MP = 16;
-  static constexpr int S_AT = 0, S_BT = S_AT + NXR * NXA, S_QT = S_BT + NXR * MP, S_PT = S_QT + NXA * NXA, S_RN = S_PT + 8 * NXA, S_HB = S_RN + 64,
-                       S_RD = S_HB + 24, S_B = S_RD + 12, S_Q = S_B + NX, S_R = S_Q + NX, S_QD = S_R + MP, S_META = S_QD + NX, SREC = ((S_META + 8 + 3) / 4) * 4;
+  static constexpr int NX = Dims<NJ>::NX, NXA = Dims<NJ>::NXA, NXR = NX - 3, MP = 16, NXP = 24, LDA = 42;
+  static constexpr int S_AB = 0, S_B = S_AB + NXP * LDA, S_Q = S_B + NXP, S_R = S_Q + NXP, S_META = S_R + MP, TMA_DOUBLES = S_META + 8,
+                       S_QF = TMA_DOUBLES, S_PRF = S_QF + 9 * 64, SREC = S_PRF + 10 * 64;
+  static_assert((TMA_DOUBLES * 8) % 16 == 0 && (SREC * 8) % 16 == 0, "TMA bulk copies need 16-byte multiples");
   // meta slots
   static constexpr int T_TYPE = 0, T_MODE = 1, T_M = 2, T_MJ = 3, T_NCLOSED = 4, T_DT = 5;
+  // offset of element (r, c) of a matrix with ntn column tiles stored in accumulator-fragment order (mma.m8n8k4 C layout)
+  __host__ __device__ static constexpr int frag(int ntn, int r, int c) { return ((r >> 3) * ntn + (c >> 3)) * 64 + (((r & 7) << 2) + ((c & 7) >> 1)) * 2 + (c & 1); }
+  __host__ __device__ static constexpr int qf(int r, int c) { return S_QF + frag(3, r, c); }
+  __host__ __device__ static constexpr int prf(int r, int c) { return S_PRF + frag(5, r, c); }   // c < 24: Pt, c >= 24: Rt column c - 24
 };
+
+// one-time initialisation of the static entries of every stage record (the buffer is zeroed before)
+template <int NJ>
+__global__ void k_stage_static(double* stage, size_t nrec) {
+  using S = SDims<NJ>;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrec) return;
+  double* so = stage + i * S::SREC;
+  for (int r = 0; r < 3; ++r) { so[S::S_AB + r * S::LDA + r] = 1.0; so[S::S_AB + (6 + r) * S::LDA + 6 + r] = 1.0; }
+}
 
 template <int NJ>
 __global__ void __launch_bounds__(128) k_project(Dev d) {
@@ -930,18 +952,19 @@ __global__ void __launch_bounds__(128) k_project(Dev d) {
   }
   if (is_rhs) {
     const int c = lane;   // X column (or the affine column NXA)
-    // (At - I) rows 3..11: AdI + Bd_j Pxj ; rows 12..: dt Pxj.   Affine column: contributes to bt
+    // At rows 3..11: I + AdI + Bd_j Pxj ; rows 12..: I + dt Pxj.   Affine column: contributes to bt
+    const int xs_ = c < 6 ? c : c + 3;   // state column of active column c
 #pragma unroll
     for (int rr = 0; rr < 9; ++rr) {
       double a = 0.0;
 #pragma unroll
       for (int l = 0; l < NJ; ++l) a += Bd[rr * NU + 12 + l] * y[l];
       const double base_v = (c < NXA) ? rec[D::R_AD + rr * NXA + c] : rec[D::R_B + 3 + rr] + __shfl_sync(__activemask(), open_corr, rr);
-      if (c < NXA) so[S::S_AT + rr * NXA + c] = base_v + a; else so[S::S_B + 3 + rr] = base_v + a;
+      if (c < NXA) so[S::S_AB + (3 + rr) * S::LDA + xs_] = base_v + a + ((3 + rr == xs_) ? 1.0 : 0.0); else so[S::S_B + 3 + rr] = base_v + a;
     }
 #pragma unroll
     for (int l = 0; l < NJ; ++l) {
-      if (c < NXA) so[S::S_AT + (9 + l) * NXA + c] = dt * y[l];
+      if (c < NXA) so[S::S_AB + (12 + l) * S::LDA + xs_] = dt * y[l] + ((12 + l == xs_) ? 1.0 : 0.0);
       else so[S::S_B + 12 + l] = rec[D::R_B + 12 + l] + dt * y[l];
     }
     if (c == NXA) {   // rows 0..2 of bt: B_d rows 0..2 = dt/m on the force columns
@@ -952,31 +975,34 @@ __global__ void __launch_bounds__(128) k_project(Dev d) {
         so[S::S_B + q] = bb;
       }
     }
-    // QtX[:, c] = Pxj^T tcol  (c < NXA) ; qt = q + Pxj^T t1 (affine column)
+    // Qt[:, c] = Pxj^T tcol (+ the diagonal dt Q + dq) in fragment order (c < NXA) ; qt = q + Pxj^T t1 (affine column)
     for (int xr = 0; xr < NXA; ++xr) {
       double a = 0.0;
 #pragma unroll
       for (int l = 0; l < NJ; ++l) a += Px[l][xr] * tcol[l];
-      if (c < NXA) so[S::S_QT + xr * NXA + c] = a;
-      else { const int sidx = xr < 6 ? xr : xr + 3; so[S::S_Q + sidx] = rec[D::R_Q + sidx] + a; }
+      const int sidx = xr < 6 ? xr : xr + 3;
+      if (c < NXA) so[S::qf(sidx, xs_)] = a + ((xr == c) ? dt * M.Qdiag[sidx] + dq : 0.0);
+      else so[S::S_Q + sidx] = rec[D::R_Q + sidx] + a;
     }
-    if (c == NXA) for (int q = 6; q < 9; ++q) so[S::S_Q + q] = rec[D::R_Q + q];
-    // Pt null rows: N^T tcol ; affine column -> rt null entries
-    for (int t = 0; t < 8; ++t) {
+    if (c == NXA) for (int q = 6; q < 9; ++q) { so[S::S_Q + q] = rec[D::R_Q + q]; so[S::qf(q, q)] = dt * M.Qdiag[q] + dq; }
+    // Pt: rows 3 nclosed .. m-1 hold N^T tcol, every other row is zero (no state-input cross term on the force rows) ; affine column -> rt null entries
+    for (int r = 0; r < MP; ++r) {
+      const int t = r - 3 * nclosed;
       double a = 0.0;
-      if (t < mj) {
+      if (t >= 0 && t < mj) {
 #pragma unroll
         for (int l = 0; l < NJ; ++l) a += Nn[l][t] * tcol[l];
       }
-      if (c < NXA) so[S::S_PT + t * NXA + c] = a;
-      else if (t < mj) so[S::S_R + 3 * nclosed + t] = a;
+      if (c < NXA) so[S::prf(r, xs_)] = a;
+      else if (t >= 0 && t < mj) so[S::S_R + r] = a;
     }
   }
-  // Bt: closed-contact force columns are copied, null-space columns = B_d[:, joints] N
-  for (int i = lane; i < NXR * MP; i += 32) {
-    const int rr = i / MP, c = i % MP;   // rr = state row - 3
+  // Bt: rows 0..2 = dt/m on the closed-contact force columns; closed-contact force columns of B_d are copied, null-space columns = B_d[:, joints] N
+  for (int i = lane; i < NX * MP; i += 32) {
+    const int r = i / MP, c = i % MP, rr = r - 3;   // rr = state row - 3
     double a = 0.0;
-    if (c < 3 * nclosed) {
+    if (r < 3) { if (c < 3 * nclosed && c % 3 == r) a = dt / M.total_mass; }
+    else if (c < 3 * nclosed) {
       int fc;   // original force column of reduced column c
       if (st0) fc = c; else fc = 6 + c;
       if (rr < 9) a = Bd[rr * NU + fc];
@@ -985,20 +1011,37 @@ __global__ void __launch_bounds__(128) k_project(Dev d) {
       if (rr < 9) { for (int l = 0; l < NJ; ++l) a += Bd[rr * NU + 12 + l] * Nn[l][t]; }
       else a = dt * Nn[rr - 9][t];
     }
-    so[S::S_BT + i] = a;
+    so[S::S_AB + r * S::LDA + 24 + c] = a;
   }
-  // Rt: null block N^T Rj_eff N, force blocks (barrier Hessians) and force diagonal; rt force entries; Q diagonal
-  for (int i = lane; i < 64; i += 32) {
-    const int t1 = i / 8, t2 = i % 8;
+  // Rt (16 x 16): force blocks (barrier Hessians + diagonal), null block N^T Rj_eff N, identity beyond m
+  double rnn[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int i = lane + 32 * q, t1 = i / 8, t2 = i % 8;
     double a = 0.0;
     if (t1 < mj && t2 < mj) for (int l = 0; l < NJ; ++l) a += Nn[l][t1] * RN[l][t2];
-    so[S::S_RN + i] = a;
+    rnn[q] = a;
   }
-  if (lane < 24) so[S::S_HB + lane] = rec[D::R_HB + lane];
-  if (lane < 12) so[S::S_RD + lane] = dt * M.Rforce[lane] + dr;
+  __syncwarp();
+  double* rns = &RN[0][0];   // reuse: the 8 x 8 null block (NJ >= 8 rows of 8)
+  rns[lane] = rnn[0]; rns[lane + 32] = rnn[1];
+  __syncwarp();
+  for (int i = lane; i < MP * MP; i += 32) {
+    const int r = i / MP, c = i % MP;
+    double a = 0.0;
+    if (r >= m || c >= m) a = (r == c) ? 1.0 : 0.0;
+    else if (r < 3 * nclosed && c < 3 * nclosed) {
+      if (r / 3 == c / 3) {
+        const int cn = (st0 ? 0 : 2) + r / 3, p = r % 3, q = c % 3;
+        const int lo = p < q ? p : q, hi = p < q ? q : p;
+        a = rec[D::R_HB + 6 * cn + (lo == 0 ? hi : (lo == 1 ? 2 + hi : 5))];
+        if (p == q) a += dt * M.Rforce[3 * cn + p] + dr;
+      }
+    } else if (r >= 3 * nclosed && c >= 3 * nclosed) a = rns[(r - 3 * nclosed) * 8 + (c - 3 * nclosed)];
+    so[S::prf(r, 24 + c)] = a;
+  }
   if (lane < 3 * nclosed) { const int fc = st0 ? lane : 6 + lane; so[S::S_R + lane] = rec[D::R_R + fc]; }
   if (lane >= m && lane < MP) so[S::S_R + lane] = 0.0;
-  for (int i = lane; i < NX; i += 32) so[S::S_QD + i] = dt * M.Qdiag[i] + dq;
 }
 
 // ------------------------------------------------------------------------------------------------ TMA bulk copy + mbarrier helpers (sm_90+/sm_100a PTX)
@@ -1163,35 +1206,13 @@ __global__ void __launch_bounds__(WS_THREADS, 4) k_riccati(Dev d) {
     const int m = (int)meta[S::T_M], mj = (int)meta[S::T_MJ], nclosed = (int)meta[S::T_NCLOSED], mode = (int)meta[S::T_MODE];
     const double dt = meta[S::T_DT];
     const bool st0 = leg_in_stance(mode, 0);
-    // ---- phase 1: scatter the projected stage record into the padded operand matrices (lane = column, warp = row stride: no div/mod)
+    // ---- phase 1: copy the projected stage record into the padded operand matrices (lane = column, warp = row stride)
     {
-      const int xcl = lane < 6 ? lane : lane + 3;   // state column of active-x column `lane`
-      for (int r = warp; r < NX; r += 4) {           // At = I + [rows 3.., X cols]; columns 6..8 are identity columns
-        if (lane < NXA) sm.At[r * LD + xcl] = ((r == xcl) ? 1.0 : 0.0) + ((r >= 3) ? sr[S::S_AT + (r - 3) * NXA + lane] : 0.0);
-        if (lane >= 29) { const int c = lane - 23; sm.At[r * LD + c] = (r == c) ? 1.0 : 0.0; }
-      }
+      for (int r = warp; r < NX; r += 4) if (lane < NXP) sm.At[r * LD + lane] = sr[S::S_AB + r * S::LDA + lane];
       const int bc = lane & 15, bh = lane >> 4;
-      for (int r = 2 * warp + bh; r < NX; r += 8)    // Bt (two rows per warp pass)
-        sm.Bt[r * LDM + bc] = (r >= 3) ? sr[S::S_BT + (r - 3) * MP + bc] : ((bc < 3 * nclosed && bc % 3 == r) ? dt * imass : 0.0);
-      for (int r = warp; r < MP; r += 4) {           // H <- Pt (null rows only)
-        const int t = r - 3 * nclosed;
-        if (lane < NXA) sm.H[r * LD + xcl] = (t >= 0 && t < mj) ? sr[S::S_PT + t * NXA + lane] : 0.0;
-        if (lane >= 29) sm.H[r * LD + lane - 23] = 0.0;
-      }
-      for (int r = 2 * warp + bh; r < MP; r += 8) {  // G <- Rt
-        const int c = bc;
-        double a = 0.0;
-        if (r >= m || c >= m) a = (r == c) ? 1.0 : 0.0;
-        else if (r < 3 * nclosed && c < 3 * nclosed) {
-          if (r / 3 == c / 3) {
-            const int cn = (st0 ? 0 : 2) + r / 3, p = r % 3, q = c % 3;
-            const int lo = p < q ? p : q, hi = p < q ? q : p;
-            a = sr[S::S_HB + 6 * cn + (lo == 0 ? hi : (lo == 1 ? 2 + hi : 5))];
-            if (p == q) a += sr[S::S_RD + 3 * cn + p];
-          }
-        } else if (r >= 3 * nclosed && c >= 3 * nclosed) a = sr[S::S_RN + (r - 3 * nclosed) * 8 + (c - 3 * nclosed)];
-        sm.G[r * LDM + c] = a;
-      }
+      for (int r = 2 * warp + bh; r < NX; r += 8) sm.Bt[r * LDM + bc] = sr[S::S_AB + r * S::LDA + 24 + bc];
+      for (int r = warp; r < MP; r += 4) if (lane < NXP) sm.H[r * LD + lane] = sr[S::prf(r, lane)];           // H <- Pt
+      for (int r = 2 * warp + bh; r < MP; r += 8) sm.G[r * LDM + bc] = sr[S::prf(r, 24 + bc)];                // G <- Rt
     }
     if (tid < NX) { sm.bt[tid] = sr[S::S_B + tid]; sm.qt[tid] = sr[S::S_Q + tid]; }
     if (tid >= 32 && tid < 32 + MP) sm.rt[tid - 32] = sr[S::S_R + tid - 32];
@@ -1202,7 +1223,7 @@ __global__ void __launch_bounds__(WS_THREADS, 4) k_riccati(Dev d) {
     for (int q = 0; q < QPT; ++q) {
       const int r = warp + 4 * q, c = lane;
       double a = 0.0;
-      if (r < NX && c < NX && c >= r) { if (r == c) a = sr[S::S_QD + r]; if ((r < 6 || r >= 9) && (c < 6 || c >= 9)) a += sr[S::S_QT + xcol(r) * NXA + xcol(c)]; }
+      if (r < NX && c < NX && c >= r) a = sr[S::qf(r, c)];
       qreg[q] = a;
     }
     __syncthreads();
@@ -1286,12 +1307,11 @@ struct PolSmem {
   double rt[MP], xk[24], Nn[NJ * 8];
 };
 
-// value of the padded operand [At | bt | 0] (24 x 24) at (r, c), read from the compact stage record
+// value of the padded operand [At | bt | 0] (24 x 24) at (r, c), read from the stage record (rows >= NX of AB and bt are zero padding)
 template <int NJ>
 __device__ __forceinline__ double stage_At_aug(const double* __restrict__ sr, int r, int c) {
-  using S = SDims<NJ>; constexpr int NX = Dims<NJ>::NX, NXA = Dims<NJ>::NXA;
-  if (r >= NX) return 0.0;
-  if (c < NX) { double a = (r == c) ? 1.0 : 0.0; if (r >= 3 && (c < 6 || c >= 9)) a += sr[S::S_AT + (r - 3) * NXA + xcol(c)]; return a; }
+  using S = SDims<NJ>; constexpr int NX = Dims<NJ>::NX;
+  if (c < NX) return sr[S::S_AB + r * S::LDA + c];
   return c == NX ? sr[S::S_B + r] : 0.0;
 }
 
@@ -1344,9 +1364,7 @@ __global__ void __launch_bounds__(128, 4) k_policy_expand(Dev d) {
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       const int r = 8 * mt + lr, c = 4 * kk + lc;
-      double a = 0.0;
-      if (r >= 3 && r < NX) a = sr[S::S_BT + (r - 3) * MP + c]; else if (r < 3 && c < 3 * nclosed) a = (c % 3 == r) ? dt * imass : 0.0;
-      af[mt][kk] = a;
+      af[mt][kk] = sr[S::S_AB + r * S::LDA + 24 + c];
     }
   const double rt_l = (lane < MP) ? sr[S::S_R + lane] : 0.0;
   const double xk_l = (lane < NX) ? d.s_x[(nb + k) * NX + lane] : 0.0;
