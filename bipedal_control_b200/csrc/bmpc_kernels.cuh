@@ -1294,6 +1294,203 @@ __global__ void __launch_bounds__(WS_THREADS, 4) k_riccati(Dev d) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ K2 (default): backward Riccati recursion, ONE WARP PER INSTANCE
+// No block-level barrier anywhere: the 4 warps of a CTA run 4 independent instances.  The value function S (24 x 24) never leaves the
+// warp's registers: it is held as the 3 x 3 accumulator fragments of mma.sync.m8n8k4.f64 (lane (g, q) = (lane >> 2, lane & 3) owns
+// S[8a + g][8b + 2q + {0,1}]).  Two observations make every product chain register-to-register:
+//   (1) S is symmetric, so the accumulator fragment of tile (a, b) is at the same time the B-operand fragment of rows 8b + {2q, 2q+1},
+//       columns 8a + g, provided the k index of the A operand is permuted the same way (k = 2q + slot; two DMMAs cover 8 rows of k);
+//   (2) computing the TRANSPOSED products Z^T = [At | Bt]^T S leaves Z = S [At | Bt] in exactly that B-operand form again.
+//   Z^T  = AB^T S                       (A operand: AB from the TMA-staged record, k-permuted transposed loads, ld 42 -> conflict free)
+//   [H | G] = [Pt | Rt] + Bt^T Z        (accumulators initialised straight from the fragment-ordered record in global memory)
+//   S'   = Qt + At^T Z[:, :24] - Y^T Y  (Y = L^-1 H from the in-warp Cholesky; Y staged in shared memory for the last product)
+// The staged record is single buffered: the TMA for stage k-1 is issued as soon as the last AB fragment of stage k has been read, and
+// lands while the warp runs the Cholesky chain.
+template <int NJ>
+struct RicWarpSmem {
+  static constexpr int LDH = 44;
+  alignas(16) double rec[SDims<NJ>::TMA_DOUBLES];   // AB | bt | qt | rt | meta (TMA destination)
+  alignas(16) double HG[16 * LDH];                   // [H | G] fragments -> column layout for the Cholesky; afterwards [Y | L]
+  double sb[24], gv[16];
+  alignas(16) unsigned long long bar;
+};
+
+template <int NJ>
+__global__ void __launch_bounds__(128, 3) k_riccati_warp(Dev d) {
+  using D = Dims<NJ>; using R = RDims<NJ>; using S = SDims<NJ>; using SM = RicWarpSmem<NJ>;
+  constexpr int NX = D::NX, MP = S::MP, LDA = S::LDA, LDH = SM::LDH;
+  constexpr unsigned TMA_BYTES = S::TMA_DOUBLES * sizeof(double);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + warp;
+  if (b >= d.B) return;
+  SM& sm = reinterpret_cast<SM*>(smem_raw)[warp];
+  const int N = d.n_nodes[b] - 1;
+  const size_t nb = (size_t)b * d.NS;
+  const int g = lane >> 2, q = lane & 3;
+  double Sf[3][3][2];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { Sf[a][c][0] = 0.0; Sf[a][c][1] = 0.0; }   // terminal value function: zero (no terminal cost installed)
+  double s_l = 0.0;   // lane r < 24 holds s[r]
+  if (lane == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
+  __syncwarp();
+  if (lane == 0 && N >= 1) tma_load_1d(sm.rec, d.stage + (nb + N - 1) * S::SREC, TMA_BYTES, &sm.bar);
+  unsigned phase_bit = 0;
+  const double* sr = sm.rec;
+  const double* AB = sm.rec + S::S_AB;
+#pragma unroll 1
+  for (int k = N - 1; k >= 0; --k) {
+    mbar_wait(&sm.bar, phase_bit);
+    phase_bit ^= 1u;
+    const double* __restrict__ grec = d.stage + (nb + k) * S::SREC;
+    double* __restrict__ ric = d.ric + (nb + k) * R::KREC;
+    const bool is_event = sr[S::S_META + S::T_TYPE] != 0.0;
+    const int m = (int)sr[S::S_META + S::T_M];
+    // ---- sb = s + S bt  (lane-level on the fragments: partial row sums, reduced over the 4 lanes of a quad)
+    {
+      double p[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc += Sf[a][c][0] * sr[S::S_B + 8 * c + 2 * q] + Sf[a][c][1] * sr[S::S_B + 8 * c + 2 * q + 1];
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        p[a] = acc;
+      }
+      if (q == 0) { sm.sb[g] = p[0]; sm.sb[8 + g] = p[1]; sm.sb[16 + g] = p[2]; }
+      __syncwarp();
+      const double sbv = (lane < 24) ? s_l + sm.sb[lane] : 0.0;
+      __syncwarp();
+      if (lane < 24) sm.sb[lane] = sbv;
+      if (is_event) {   // A = I, Q = 0, no input: S unchanged, s <- s + S b
+        s_l = sbv;
+        __syncwarp();
+        if (lane == 0 && k >= 1) { fence_proxy_async(); tma_load_1d(sm.rec, d.stage + (nb + k - 1) * S::SREC, TMA_BYTES, &sm.bar); }
+        continue;
+      }
+    }
+    // accumulator initialisers, fragment ordered in global memory: [Pt | Rt] now, Qt below (in flight during the products)
+    double HGf[2][5][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 5; ++c) { const double2 v = *reinterpret_cast<const double2*>(grec + S::S_PRF + (a * 5 + c) * 64 + 2 * lane); HGf[a][c][0] = v.x; HGf[a][c][1] = v.y; }
+    // ---- step A: Z^T = AB^T S   (Z[mt][nt] holds (S AB)[8 nt + 2q + slot][8 mt + g])
+    double Z[5][3][2];
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { Z[a][c][0] = 0.0; Z[a][c][1] = 0.0; }
+#pragma unroll
+    for (int kb = 0; kb < 3; ++kb)
+#pragma unroll
+      for (int mt = 0; mt < 5; ++mt) {
+        const double a0 = AB[(8 * kb + 2 * q) * LDA + 8 * mt + g], a1 = AB[(8 * kb + 2 * q + 1) * LDA + 8 * mt + g];
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) { dmma884(Z[mt][nt][0], Z[mt][nt][1], a0, Sf[nt][kb][0]); dmma884(Z[mt][nt][0], Z[mt][nt][1], a1, Sf[nt][kb][1]); }
+      }
+    double Sn[3][3][2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { const double2 v = *reinterpret_cast<const double2*>(grec + S::S_QF + (a * 3 + c) * 64 + 2 * lane); Sn[a][c][0] = v.x; Sn[a][c][1] = v.y; }
+    __syncwarp();   // sb visible to every lane
+    // ---- step B: [H | G] += Bt^T Z ; g = rt + Bt^T sb
+#pragma unroll
+    for (int kb = 0; kb < 3; ++kb)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const double a0 = AB[(8 * kb + 2 * q) * LDA + 24 + 8 * mt + g], a1 = AB[(8 * kb + 2 * q + 1) * LDA + 24 + 8 * mt + g];
+#pragma unroll
+        for (int nt = 0; nt < 5; ++nt) { dmma884(HGf[mt][nt][0], HGf[mt][nt][1], a0, Z[nt][kb][0]); dmma884(HGf[mt][nt][0], HGf[mt][nt][1], a1, Z[nt][kb][1]); }
+      }
+    {
+      double gval = 0.0, sn = 0.0;
+      if (lane < MP) { gval = sr[S::S_R + lane]; for (int r = 0; r < 24; ++r) gval += AB[r * LDA + 24 + lane] * sm.sb[r]; }
+      // ---- step D1: S' = Qt + At^T Z[:, :24] ; s' = qt + At^T sb
+      if (lane < 24) { sn = sr[S::S_Q + lane]; for (int r = 0; r < 24; ++r) sn += AB[r * LDA + lane] * sm.sb[r]; }
+      s_l = sn;
+      if (lane < MP) sm.gv[lane] = gval;
+    }
+#pragma unroll
+    for (int kb = 0; kb < 3; ++kb)
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt) {
+        const double a0 = AB[(8 * kb + 2 * q) * LDA + 8 * mt + g], a1 = AB[(8 * kb + 2 * q + 1) * LDA + 8 * mt + g];
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) { dmma884(Sn[mt][nt][0], Sn[mt][nt][1], a0, Z[nt][kb][0]); dmma884(Sn[mt][nt][0], Sn[mt][nt][1], a1, Z[nt][kb][1]); }
+      }
+    // ---- the staged record is free: prefetch the next stage while the Cholesky chain runs
+    __syncwarp();
+    if (lane == 0 && k >= 1) { fence_proxy_async(); tma_load_1d(sm.rec, d.stage + (nb + k - 1) * S::SREC, TMA_BYTES, &sm.bar); }
+    // ---- step C: [H | G] fragments -> shared memory -> one column per lane ; Cholesky of G fused with the forward substitution of [H | g]
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 5; ++c) *reinterpret_cast<double2*>(&sm.HG[(8 * a + g) * LDH + 8 * c + 2 * q]) = make_double2(HGf[a][c][0], HGf[a][c][1]);
+    __syncwarp();
+    {
+      double gc[MP], hc[MP];
+#pragma unroll
+      for (int i = 0; i < MP; ++i) { gc[i] = (lane < MP) ? sm.HG[i * LDH + 24 + lane] : 0.0; hc[i] = (lane < 24) ? sm.HG[i * LDH + lane] : ((lane == 24) ? sm.gv[i] : 0.0); }
+      __syncwarp();
+      bool not_pd;
+      switch (m) {   // reduced input dimensions that occur: H1 6 / 9 / 12 (FLY / single stance / double stance), G1 8 / 11 / 14
+        case 6: not_pd = chol_forward<6, MP>(gc, hc, lane); break;
+        case 9: not_pd = chol_forward<9, MP>(gc, hc, lane); break;
+        case 12: not_pd = chol_forward<12, MP>(gc, hc, lane); break;
+        case 8: not_pd = chol_forward<8, MP>(gc, hc, lane); break;
+        case 11: not_pd = chol_forward<11, MP>(gc, hc, lane); break;
+        case 14: not_pd = chol_forward<14, MP>(gc, hc, lane); break;
+        default: not_pd = chol_forward<MP, MP>(gc, hc, lane); break;   // padded pivots are identity rows
+      }
+      if (not_pd && lane == 0) atomicOr(&d.status[b], 1);
+#pragma unroll
+      for (int i = 0; i < MP; ++i) {
+        if (lane < 24) sm.HG[i * LDH + lane] = hc[i];                       // Y
+        if (lane < NX) ric[R::K_Y + i * NX + lane] = hc[i];
+        if (lane < MP) ric[R::K_L + i * MP + lane] = (i >= lane) ? gc[i] : 0.0;   // L (reciprocal pivots on the diagonal)
+        if (lane == 24) { sm.gv[i] = hc[i]; ric[R::K_YG + i] = hc[i]; }       // yg
+      }
+      __syncwarp();
+      if (lane < 24) {   // s' -= Y^T yg
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < MP; ++i) a += hc[i] * sm.gv[i];
+        s_l -= a;
+      }
+    }
+    // ---- step E: S' -= Y^T Y  (natural k order: both operands come from the staged Y)
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+      if (4 * kb < m) {
+        double y[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) y[t] = sm.HG[(4 * kb + q) * LDH + 8 * t + g];
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 3; ++nt) dmma884(Sn[mt][nt][0], Sn[mt][nt][1], -y[mt], y[nt]);
+      }
+    }
+    // ---- symmetrise: S = (S' + S'^T) / 2.  Element (8 nt + 2q + s, 8 mt + g) of tile (nt, mt) lives in lane (2q + s) * 4 + g / 2, slot g & 1
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int src = (2 * q + sl) * 4 + (g >> 1);
+          const double t0 = __shfl_sync(0xffffffffu, Sn[nt][mt][0], src), t1 = __shfl_sync(0xffffffffu, Sn[nt][mt][1], src);
+          Sf[mt][nt][sl] = 0.5 * (Sn[mt][nt][sl] + ((g & 1) ? t1 : t0));
+        }
+    __syncwarp();   // HG / gv / sb are rewritten by the next stage
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ K2b: gains and closed-loop stage maps, one warp per (instance, stage)
 //   Kt = -L^-T Y, kt = -L^-T yg;  K = Px + Pu Kt, kappa = Pe + Pu kt, uff0 = u - K x   ([UPSTREAM] remapProjectedGain / toPrimalSolution)
 //   Phi = At + Bt Kt, phi = bt + Bt kt (forward substitution), ghat = qt + Kt^T rt, misc = rt^T kt (armijoDescentMetric)

@@ -278,6 +278,40 @@ def test_lq_kernel_variants_agree():
         assert np.abs((ra - rb) / scale)[:, -28:].max() < 1e-10   # ev rows in use, misc, forces
 
 
+def test_riccati_kernel_variants_agree():
+    """The warp-per-instance Riccati kernel (default: value function in DMMA accumulator fragments) and the CTA-per-instance kernel
+    (operands in shared memory) give the same policies on randomised instances with divergent contact modes, for both robots."""
+    import helpers
+    from tools.ingest import read_model
+    G = _gpu()
+    for robot in ("h1", "g1"):
+        model = os.path.join(ROOT, "configs", f"{robot}.model")
+        m = read_model(model)
+        nj = m["nj"]
+        lo = np.array([m[f"joint{j}_limits"][0] for j in range(nj)]); hi = np.array([m[f"joint{j}_limits"][1] for j in range(nj)])
+        B = 37   # not a multiple of the 4 instances per CTA
+        X0, cmd, gait, phase = helpers.randomized_instances(B, np.asarray(m["initial_state"]), np.asarray(m["default_joint_state"]), lo, hi, seed=5)
+        X0[:, 8] = m["initial_state"][8] + (X0[:, 8] - 0.93)
+        ME = 40
+        ET, MS, NE = np.zeros((B, ME)), np.zeros((B, ME + 1), dtype=np.int32), np.zeros(B, dtype=np.int32)
+        for b in range(B):
+            et, ms = helpers.tiled_schedule(gait[b], phase[b], t_hi=3.0)
+            NE[b] = len(et); ET[b, :len(et)] = et; MS[b, :len(ms)] = ms
+        pols, perfs = [], []
+        for mode in (1, 0):
+            g = G(B, model_file=model, dt=0.01, time_horizon=1.0)
+            g.setOption("riccati_mode", mode)
+            g.setCurrentObservation(np.zeros(B), X0); g.setTargetsFromCmdVel(cmd, 1.0); g.setModeSchedule(ET, MS, NE)
+            g.advanceMpc(); g.advanceMpc()
+            assert not (g.getStatus() & ~16).any()
+            pols.append(g.getPolicy(0, B)); perfs.append(g.getPerformanceIndices())
+            g.close()
+        for key in ("x", "u", "uff", "K"):
+            a, b_ = pols[0][key], pols[1][key]
+            assert np.abs(a - b_).max() <= 1e-9 * max(1.0, np.abs(b_).max()), (robot, key, np.abs(a - b_).max())
+        assert np.abs(perfs[0] - perfs[1]).max() <= 1e-9 * max(1.0, np.abs(perfs[1]).max())
+
+
 def test_config4_g1_second_morphology():
     """BASELINE configs[3]: Unitree G1 (12 leg joints, nx = nu = 24), trot, N = 100: authored config (configs/g1), vs the oracle."""
     import helpers
