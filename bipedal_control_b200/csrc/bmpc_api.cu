@@ -57,7 +57,7 @@ struct bmpc_handle {
   double *d_lq = nullptr, *d_proj = nullptr, *d_stage = nullptr, *d_ric = nullptr, *d_base = nullptr, *d_dx = nullptr, *d_du = nullptr, *d_perf_trial = nullptr, *d_perf = nullptr, *d_alpha = nullptr, *d_norms = nullptr;
   int *d_done = nullptr, *d_status = nullptr, *d_counters = nullptr;
   int* h_counters = nullptr;
-  size_t rec = 0, prec = 0, krec = 0, srec = 0, brec = 0; int lq_mode = 3, riccati_mode = 1;   // 0: k_lq, 1: k_model_base + k_lq_assemble, 2: fused warp-cooperative, 3: pair-packed fused (default)
+  size_t rec = 0, prec = 0, krec = 0, srec = 0, brec = 0; int lq_mode = 3, riccati_mode = 1, ls_mode = 1;   // 0: k_lq, 1: k_model_base + k_lq_assemble, 2: fused warp-cooperative, 3: pair-packed fused (default)
   // gait bookkeeping
   std::vector<GaitSchedule> gaits; bool use_gait = false;
   // stats
@@ -140,7 +140,8 @@ void tick(bmpc_handle* h) {
     // filter line search: all instances try alpha = 1 first; the rejected ones halve their step
     for (int trial = 0; trial < 16; ++trial) {
       CK(cudaMemsetAsync(h->d_counters, 0, sizeof(int), st));
-      k_linesearch_eval<NJ><<<(nodes + 63) / 64, 64, 0, st>>>(d); ++h->launches;
+      if (h->ls_mode == 1) { k_linesearch_eval2<NJ><<<(nodes + 63) / 64, 64, 0, st>>>(d); ++h->launches; }   // streaming register-only flow map (default)
+      else { k_linesearch_eval<NJ><<<(nodes + 63) / 64, 64, 0, st>>>(d); ++h->launches; }
       k_accept<NJ><<<(B + 3) / 4, 128, 0, st>>>(d); ++h->launches;
       ++h->linesearch_trials;
       CK(cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -507,6 +508,7 @@ int bmpc_get_observations(bmpc_handle* h, double* t, double* x) {
 int bmpc_get_launch_count(const bmpc_handle* h) { return h ? h->launches : 0; }
 int bmpc_debug_set_option(bmpc_handle* h, const char* name, int value) {
   if (!h || !name) return BMPC_ERR_INVALID;
+  if (std::string(name) == "ls_mode") { if (value < 0 || value > 1) return BMPC_ERR_INVALID; h->ls_mode = value; return BMPC_OK; }
   if (std::string(name) == "riccati_mode") { if (value < 0 || value > 1) return BMPC_ERR_INVALID; h->riccati_mode = value; return BMPC_OK; }
   if (std::string(name) == "lq_mode") { if (value < 0 || value > 3) return BMPC_ERR_INVALID; h->lq_mode = value; return BMPC_OK; }
   return BMPC_ERR_INVALID;

@@ -335,6 +335,74 @@ __device__ __noinline__ void model_eval(const double* __restrict__ x, const doub
   }
 }
 
+// ------------------------------------------------------------------------------------------------ streaming flow map (values only, registers only)
+// Same flow map / contact velocities as model_eval<NJ, 0>, restructured for the line search so that nothing per-joint is stored:
+//   sum_j A_j(q) qd_j = sum_i I_i (w_i^J, v_i^J),  (w_i^J, v_i^J) = sum_{j on the path to body i} qd_j S_j   (joint-induced link twist)
+// so one root-to-leaf pass per leg accumulates the total spatial inertia, the joint-induced momentum and the tip twists; no composite
+// inertias, no per-joint arrays, no local memory.  xb = x[0:12], qj = x[12:], uf = u[0:12], qd = u[12:]; f = rows 0..11 of the flow map
+// (rows 12.. are qd).  Fully unrolled: the model constants become immediate constant-bank operands.
+template <int NJ>
+__device__ __noinline__ void model_values(const double (&xb)[12], const double (&qj)[NJ], const double (&uf)[12], const double (&qd)[NJ], double (&f)[12], v3 (&vc)[NCON]) {
+  constexpr int NL = Dims<NJ>::NL;
+  const DevModel& M = c_model;
+  const double mass = M.total_mass, imass = 1.0 / mass;
+  double sz, cz, sy, cy, sx, cx;
+  sincos(xb[9], &sz, &cz); sincos(xb[10], &sy, &cy); sincos(xb[11], &sx, &cx);
+  m3 Rb;
+  Rb.m[0] = cz * cy; Rb.m[1] = cz * sy * sx - sz * cx; Rb.m[2] = cz * sy * cx + sz * sx;
+  Rb.m[3] = sz * cy; Rb.m[4] = sz * sy * sx + cz * cx; Rb.m[5] = sz * sy * cx - cz * sx;
+  Rb.m[6] = -sy;     Rb.m[7] = cy * sx;                Rb.m[8] = cy * cx;
+  const v3 pb = mk(xb[6], xb[7], xb[8]);
+  v3 bax[3];
+  bax[0] = mk(0.0, 0.0, 1.0); bax[1] = mk(-sz, cz, 0.0); bax[2] = mk(cz * cy, sz * cy, -sy);
+  SI tot = body_si(M.base_mass, mulc(Rb.m, M.base_com) + pb, rotate_inertia(Rb, M.base_inertia));
+  Mom hJ; hJ.n = mk(0.0, 0.0, 0.0); hJ.p = mk(0.0, 0.0, 0.0);
+  v3 pc[NCON], wtip[2], vtip[2];
+#pragma unroll
+  for (int leg = 0; leg < 2; ++leg) {
+    m3 Rp = Rb; v3 pp = pb;
+    v3 wJ = mk(0.0, 0.0, 0.0), vJ = mk(0.0, 0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const int j = leg * NL + i;
+      const v3 o = mulc(Rp.m, M.pj[j]) + pp;
+      const m3 Rfix = mulc(Rp, M.Rj[j]);
+      const v3 a = mulc(Rfix.m, M.axis[j]);
+      const m3 Rw = mul(Rfix, rodrigues(M.axis[j], qj[j]));
+      const SI bj = body_si(M.mass[j], mulc(Rw.m, M.com[j]) + o, rotate_inertia(Rw, M.inertia[j]));
+      tot = tot + bj;
+      wJ = wJ + qd[j] * a; vJ = vJ + qd[j] * cross(o, a);
+      hJ = hJ + si_apply(bj, wJ, vJ);
+      Rp = Rw; pp = o;
+    }
+    pc[2 * leg] = mulc(Rp.m, M.coff[2 * leg]) + pp; pc[2 * leg + 1] = mulc(Rp.m, M.coff[2 * leg + 1]) + pp;
+    wtip[leg] = wJ; vtip[leg] = vJ;
+  }
+  const v3 com = imass * tot.h;
+  double A22[9], A22i[9], A12[9];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const Mom m = si_apply(tot, bax[k], cross(pb, bax[k]));
+    const v3 an = m.n - cross(com, m.p);
+    A22[k] = an.x; A22[3 + k] = an.y; A22[6 + k] = an.z; A12[k] = m.p.x; A12[3 + k] = m.p.y; A12[6 + k] = m.p.z;
+  }
+  inv3(A22, A22i);
+  const v3 ml = mk(mass * xb[0], mass * xb[1], mass * xb[2]) - hJ.p;
+  const v3 ma = mk(mass * xb[3], mass * xb[4], mass * xb[5]) - (hJ.n - cross(com, hJ.p));
+  const v3 w = mk(A22i[0] * ma.x + A22i[1] * ma.y + A22i[2] * ma.z, A22i[3] * ma.x + A22i[4] * ma.y + A22i[5] * ma.z, A22i[6] * ma.x + A22i[7] * ma.y + A22i[8] * ma.z);
+  const v3 vlin = imass * (ml - mk(A12[0] * w.x + A12[1] * w.y + A12[2] * w.z, A12[3] * w.x + A12[4] * w.y + A12[5] * w.z, A12[6] * w.x + A12[7] * w.y + A12[8] * w.z));
+  v3 Ftot = mk(0.0, 0.0, 0.0), tau = mk(0.0, 0.0, 0.0);
+#pragma unroll
+  for (int c = 0; c < NCON; ++c) { const v3 F = mk(uf[3 * c], uf[3 * c + 1], uf[3 * c + 2]); Ftot = Ftot + F; tau = tau + cross(pc[c] - com, F); }
+  f[0] = Ftot.x * imass; f[1] = Ftot.y * imass; f[2] = Ftot.z * imass - 9.81;
+  f[3] = tau.x * imass; f[4] = tau.y * imass; f[5] = tau.z * imass;
+  f[6] = vlin.x; f[7] = vlin.y; f[8] = vlin.z; f[9] = w.x; f[10] = w.y; f[11] = w.z;
+  const v3 we3 = w.x * bax[0] + w.y * bax[1] + w.z * bax[2];
+  const v3 ve3 = vlin + w.x * cross(pb, bax[0]) + w.y * cross(pb, bax[1]) + w.z * cross(pb, bax[2]);
+#pragma unroll
+  for (int c = 0; c < NCON; ++c) vc[c] = cross(we3 + wtip[c / 2], pc[c]) + ve3 + vtip[c / 2];
+}
+
 // ------------------------------------------------------------------------------------------------ base record (values only)
 // Everything the Jacobian columns need, computed once per (stage, RK2 evaluation) by one thread and consumed by one warp
 // (k_lq_assemble: lane = column).  Layout in doubles:

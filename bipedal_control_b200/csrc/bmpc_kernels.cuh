@@ -19,6 +19,15 @@ constexpr int WS_THREADS = 128;     // threads per CTA of the Riccati kernel (on
 #ifndef LQ_MIN_BLOCKS
 #define LQ_MIN_BLOCKS 8
 #endif
+#ifndef LQ_PAIR_BLOCKS
+#define LQ_PAIR_BLOCKS 2
+#endif
+#ifndef LS_BLOCKS
+#define LS_BLOCKS 6
+#endif
+#ifndef LS2_BLOCKS
+#define LS2_BLOCKS 4
+#endif
 #ifndef LQ_FUSED_BLOCKS
 #define LQ_FUSED_BLOCKS 2
 #endif
@@ -679,7 +688,7 @@ struct LqPairSmem {
   double xu[WPB][2][4 * 24];   // per stage: x, u, xnext, xref
 };
 template <int NJ>
-__global__ void __launch_bounds__(128, 2) k_lq_pair(Dev d) {
+__global__ void __launch_bounds__(128, LQ_PAIR_BLOCKS) k_lq_pair(Dev d) {
   using D = Dims<NJ>; using BD = BaseDims<NJ>; using SM = LqPairSmem<NJ>;
   constexpr int NX = D::NX, NU = D::NU, WPB = SM::WPB, BASE = BD::BASE;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1732,7 +1741,7 @@ __global__ void __launch_bounds__(128) k_forward(Dev d) {
 
 // ------------------------------------------------------------------------------------------------ K4: line-search trial evaluation, one thread per (instance, stage)
 template <int NJ>
-__global__ void __launch_bounds__(64) k_linesearch_eval(Dev d) {
+__global__ void __launch_bounds__(64, LS_BLOCKS) k_linesearch_eval(Dev d) {
   using D = Dims<NJ>;
   constexpr int NX = D::NX, NU = D::NU;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1771,6 +1780,88 @@ __global__ void __launch_bounds__(64) k_linesearch_eval(Dev d) {
   }
   out[0] = dt * stage_cost_value<NJ>(mode, x, u, d.xref + (nb + k) * NX);
   out[1] = dt * s; out[2] = dt * peq;
+}
+
+// K4 (default): the same trial evaluation on the streaming, register-only flow map (model_values): no per-joint arrays, no local memory
+template <int NJ>
+__global__ void __launch_bounds__(64, LS2_BLOCKS) k_linesearch_eval2(Dev d) {
+  using D = Dims<NJ>;
+  constexpr int NX = D::NX, NU = D::NU;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = gid / d.NS, k = gid % d.NS;
+  if (b >= d.B) return;
+  if (d.done[b]) return;
+  const int N = d.n_nodes[b] - 1;
+  if (k >= N) return;
+  const size_t nb = (size_t)b * d.NS;
+  const double al = d.alpha[b];
+  double* out = d.perf_trial + (nb + k) * 3;
+  const double* __restrict__ gx = d.s_x + (nb + k) * NX; const double* __restrict__ gdx = d.dx + (nb + k) * NX;
+  const double* __restrict__ gu = d.s_u + (nb + k) * NU; const double* __restrict__ gdu = d.du + (nb + k) * NU;
+  if (d.node_ev[nb + k] == 1) {
+    double s = 0.0;
+    for (int i = 0; i < NX; ++i) { const double e = gx[i] + al * gdx[i] - (gx[NX + i] + al * gdx[NX + i]); s += e * e; }
+    out[0] = 0.0; out[1] = s; out[2] = 0.0; return;
+  }
+  const double dt = d.st_dt[nb + k]; const int mode = d.st_mode[nb + k];
+  double xb[12], qj[NJ], uf[12], qd[NJ];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { xb[i] = gx[i] + al * gdx[i]; uf[i] = gu[i] + al * gdu[i]; }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) { qj[j] = gx[12 + j] + al * gdx[12 + j]; qd[j] = gu[12 + j] + al * gdu[12 + j]; }
+  // stage cost at (x, u): tracking + soft friction cones (cost/BipedalRobotQuadraticTrackingCost.h:57-63, common/utils.h:63-77)
+  const DevModel& M = c_model;
+  const bool st0 = leg_in_stance(mode, 0), st1 = leg_in_stance(mode, 1);
+  double cost = 0.0;
+  {
+    const double* __restrict__ xr = d.xref + (nb + k) * NX;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { const double e = xb[i] - xr[i]; cost += 0.5 * M.Qdiag[i] * e * e; }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { const double e = qj[j] - xr[12 + j]; cost += 0.5 * M.Qdiag[12 + j] * e * e; }
+    const int nst = 2 * (int(st0) + int(st1));
+    const double fz = nst > 0 ? M.total_mass * 9.81 / nst : 0.0;
+#pragma unroll
+    for (int c = 0; c < NCON; ++c) {
+      const bool st = (c / 2 == 0) ? st0 : st1;
+      const double ex = uf[3 * c], ey = uf[3 * c + 1], ez = uf[3 * c + 2] - (st ? fz : 0.0);
+      cost += 0.5 * (M.Rforce[3 * c] * ex * ex + M.Rforce[3 * c + 1] * ey * ey + M.Rforce[3 * c + 2] * ez * ez);
+      if (st) { double p, dp, ddp; barrier_penalty(friction_cone(uf[3 * c], uf[3 * c + 1], uf[3 * c + 2]), p, dp, ddp); cost += p; }
+    }
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) s += M.Rjoint[i * NJ + j] * qd[j];
+      cost += 0.5 * qd[i] * s;
+    }
+  }
+  // RK2 (Heun) defect against the next node; rows 12.. of the flow map are qd, so their defect is x + dt qd - x_next
+  double sdef = 0.0;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) { const double e = qj[j] + dt * qd[j] - (gx[NX + 12 + j] + al * gdx[NX + 12 + j]); sdef += e * e; }
+  double k1[12], k2[12]; v3 vc[NCON], vc2[NCON];
+  model_values<NJ>(xb, qj, uf, qd, k1, vc);
+  double peq = 0.0;
+#pragma unroll
+  for (int leg = 0; leg < 2; ++leg) {
+    const int ca = 2 * leg, cb = 2 * leg + 1;
+    if (leg == 0 ? st0 : st1) peq += dot(vc[ca], vc[ca]) + dot(vc[cb], vc[cb]);
+    else {
+      const double zr = d.zref[(nb + k) * 2 + leg];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) { const int c0 = t == 0 ? ca : cb; const double ev = vc[c0].z - zr; peq += ev * ev + uf[3 * c0] * uf[3 * c0] + uf[3 * c0 + 1] * uf[3 * c0 + 1] + uf[3 * c0 + 2] * uf[3 * c0 + 2]; }
+    }
+  }
+  double xb2[12], qj2[NJ];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) xb2[i] = xb[i] + dt * k1[i];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) qj2[j] = qj[j] + dt * qd[j];
+  model_values<NJ>(xb2, qj2, uf, qd, k2, vc2);
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { const double e = xb[i] + 0.5 * dt * (k1[i] + k2[i]) - (gx[NX + i] + al * gdx[NX + i]); sdef += e * e; }
+  out[0] = dt * cost; out[1] = dt * sdef; out[2] = dt * peq;
 }
 
 // ------------------------------------------------------------------------------------------------ K5: filter line search acceptance, one warp per instance

@@ -298,9 +298,10 @@ def test_riccati_kernel_variants_agree():
             et, ms = helpers.tiled_schedule(gait[b], phase[b], t_hi=3.0)
             NE[b] = len(et); ET[b, :len(et)] = et; MS[b, :len(ms)] = ms
         pols, perfs = [], []
-        for mode in (1, 0):
+        for mode in (1, 0):   # the CTA-per-instance run also uses the thread-level line-search evaluation (model_eval) instead of the streaming one
             g = G(B, model_file=model, dt=0.01, time_horizon=1.0)
             g.setOption("riccati_mode", mode)
+            g.setOption("ls_mode", mode)
             g.setCurrentObservation(np.zeros(B), X0); g.setTargetsFromCmdVel(cmd, 1.0); g.setModeSchedule(ET, MS, NE)
             g.advanceMpc(); g.advanceMpc()
             assert not (g.getStatus() & ~16).any()
