@@ -28,6 +28,9 @@ constexpr int WS_THREADS = 128;     // threads per CTA of the Riccati kernel (on
 #ifndef LS2_BLOCKS
 #define LS2_BLOCKS 4
 #endif
+#ifndef PROJ_BLOCKS
+#define PROJ_BLOCKS 4
+#endif
 #ifndef LQ_FUSED_BLOCKS
 #define LQ_FUSED_BLOCKS 2
 #endif
@@ -51,6 +54,10 @@ struct Dev {
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
+// FP64 tensor-core tile: D(8x8) += A(8x4) B(4x8); lane (g, q) = (lane >> 2, lane & 3) supplies A[g][q], B[q][g] and owns D[g][2q], D[g][2q+1]  (SASS: DMMA)
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 __device__ __forceinline__ int lower_bound_d(const double* a, int n, double t) {  // first index with a[i] >= t
   int lo = 0, hi = n;
   while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < t) lo = mid + 1; else hi = mid; }
@@ -791,8 +798,13 @@ __global__ void k_stage_static(double* stage, size_t nrec) {
   for (int r = 0; r < 3; ++r) { so[S::S_AB + r * S::LDA + r] = 1.0; so[S::S_AB + (6 + r) * S::LDA + 6 + r] = 1.0; }
 }
 
-template <int NJ>
-__global__ void __launch_bounds__(128) k_project(Dev d) {
+// TC = true (default): the change of input variables runs on the FP64 tensor cores.  With W = [Pxj | Pej | N] (NJ x 32, one column per lane)
+//   M  = W^T (Rj_eff W)   holds Qt (x-x block), the qt / rt corrections (affine column), Pt (null-x block) and the null block of Rt at once,
+//   AJ = B_d[:, joints] W holds the joint part of At rows 3..11, bt and the null-space columns of Bt;
+// Z^T = W^T Rj is formed first and reused as the B operand of M (same register-chaining trick as k_riccati_warp: Rj is symmetric).
+// TC = false: the scalar lane-per-column version (kept for cross-checking, bmpc_debug_set_option("project_mode", 0)).
+template <int NJ, bool TC>
+__global__ void __launch_bounds__(128, TC ? PROJ_BLOCKS : 4) k_project(Dev d) {
   using D = Dims<NJ>; using S = SDims<NJ>;
   constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, NXR = S::NXR, MP = S::MP;
   constexpr int WPB = 4;
@@ -800,9 +812,19 @@ __global__ void __launch_bounds__(128) k_project(Dev d) {
   __shared__ double sV[WPB][10][NJ];     // Householder vectors (zero padded)
   __shared__ double sBeta[WPB][10];
   __shared__ double sG[WPB][10][NXA + 1];
-  __shared__ double sPx[WPB][NJ][NXA + 1];   // [Pxj | Pej]
-  __shared__ double sN[WPB][NJ][8];
-  __shared__ double sRN[WPB][NJ][8];         // Rj_eff N
+  __shared__ double sPx[TC ? 1 : WPB][TC ? 1 : NJ][NXA + 1];   // [Pxj | Pej]   (scalar version only)
+  __shared__ double sN[TC ? 1 : WPB][TC ? 1 : NJ][8];
+  __shared__ double sRN[TC ? 1 : WPB][TC ? 1 : NJ][8];         // Rj_eff N
+  constexpr int LDW = 34, LDR = 18, LDJ = 20, CA = NXA, CN = NXA + 1;   // leading dimensions = 2 mod 4: k-permuted fragment loads are conflict free
+  __shared__ double sW[TC ? WPB : 1][TC ? 16 : 1][LDW];        // W = [Pxj | Pej | N | 0], rows >= NJ zero
+  __shared__ double sMisc[TC ? WPB : 1][32];          // r_j (16) | open-contact correction of bt rows 3..11 (16)
+  __shared__ double sRjP[16][LDR];                    // joint block of R (model constant), zero padded
+  __shared__ double sQd[24];
+  if (TC) {
+    for (int i = threadIdx.x; i < 16 * LDR; i += 128) { const int rr_ = i / LDR, cc_ = i % LDR; sRjP[rr_][cc_] = (rr_ < NJ && cc_ < NJ) ? c_model.Rjoint[rr_ * NJ + cc_] : 0.0; }
+    if (threadIdx.x < 24) sQd[threadIdx.x] = threadIdx.x < NX ? c_model.Qdiag[threadIdx.x] : 0.0;
+    __syncthreads();
+  }
   __shared__ double sBd[WPB][9 * (12 + NJ)];  // B_d rows 3..11 (read many times with warp-uniform indices)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * WPB + warp;
@@ -822,7 +844,8 @@ __global__ void __launch_bounds__(128) k_project(Dev d) {
   const DevModel& M = c_model;
   const int r = (int)rec[D::R_MISC + D::M_NROWS];
   double (*Mt)[12] = sM[warp]; double (*V)[NJ] = sV[warp]; double* beta = sBeta[warp]; double (*G)[NXA + 1] = sG[warp];
-  double (*Px)[NXA + 1] = sPx[warp]; double (*Nn)[8] = sN[warp]; double (*RN)[8] = sRN[warp];
+  double (*Px)[NXA + 1] = sPx[TC ? 0 : warp]; double (*Nn)[8] = sN[TC ? 0 : warp]; double (*RN)[8] = sRN[TC ? 0 : warp];
+  double (*W)[LDW] = sW[TC ? warp : 0];
   {   // stage Dv^T, [Cv | ev] and B_d rows 3..11: all global loads are issued before the first shared-memory store (fixed trip counts;
       // rows >= r hold stale but finite data and are never used)
     constexpr int N1 = (10 * NJ + 31) / 32, N2 = (10 * NXA + 31) / 32, N3 = (9 * NU + 31) / 32;
@@ -843,8 +866,11 @@ __global__ void __launch_bounds__(128) k_project(Dev d) {
     if (lane < 10) G[lane][NXA] = tev;
   }
   for (int i = lane; i < 10 * NJ; i += 32) V[i / NJ][i % NJ] = 0.0;
-  for (int i = lane; i < NJ * 8; i += 32) { Nn[i / 8][i % 8] = 0.0; RN[i / 8][i % 8] = 0.0; }
+  if (!TC) for (int i = lane; i < NJ * 8; i += 32) { Nn[i / 8][i % 8] = 0.0; RN[i / 8][i % 8] = 0.0; }
   __syncwarp();
+  if (TC) {   // joint block of B_d rows 3..11, padded; r_j
+    if (lane < 16) sMisc[warp][lane] = lane < NJ ? rec[D::R_R + 12 + lane] : 0.0;
+  }
   bool anomaly = false;
   double rmax = 0.0;
   // Householder QR with compile-time trip counts (rows beyond r are skipped by the warp-uniform test kk < r).  Lane c < r keeps its
@@ -916,14 +942,18 @@ __global__ void __launch_bounds__(128) k_project(Dev d) {
     }
     if (is_rhs) {
 #pragma unroll
-      for (int i = 0; i < NJ; ++i) { y[i] = -y[i]; Px[i][lane] = y[i]; }
+      for (int i = 0; i < NJ; ++i) { y[i] = -y[i]; if (!TC) Px[i][lane] = y[i]; }
       if (lane < NXA) { for (int i = 0; i < NJ; ++i) out[D::P_PX + i * NXA + lane] = y[i]; }
       else { for (int i = 0; i < NJ; ++i) out[D::P_PE + i] = y[i]; }
     } else {
       const int t = lane - NXA - 1;
 #pragma unroll
-      for (int i = 0; i < NJ; ++i) { Nn[i][t] = y[i]; out[D::P_N + i * 8 + t] = y[i]; }
+      for (int i = 0; i < NJ; ++i) { if (!TC) Nn[i][t] = y[i]; out[D::P_N + i * 8 + t] = y[i]; }
     }
+  }
+  if (TC) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) W[i][lane] = (i < NJ && (is_rhs || is_null)) ? y[i < NJ ? i : 0] : 0.0;
   }
   const double dt = rec[D::R_MISC + D::M_DT], dq = rec[D::R_MISC + D::M_DQ], dr = rec[D::R_MISC + D::M_DR];
   const int mode = (int)rec[D::R_MISC + D::M_MODE];
@@ -937,6 +967,182 @@ __global__ void __launch_bounds__(128) k_project(Dev d) {
     mt[S::T_TYPE] = 0.0; mt[S::T_MODE] = (double)mode; mt[S::T_M] = (double)m; mt[S::T_MJ] = (double)mj; mt[S::T_NCLOSED] = (double)nclosed; mt[S::T_DT] = dt;
   }
   __syncwarp();
+  // ---------------- change of input variables on the tensor cores
+  if constexpr (TC) {
+    const int g = lane >> 2, q = lane & 3;
+    const double* Bd = sBd[warp];
+    // joint block of B_d rows 3..11 (columns zero padded to 16; fragment rows beyond 8 re-read row 8, results discarded).  It reuses the
+    // storage of [Cv | ev], which is dead after the triangular solves.
+    static_assert(9 * LDJ <= 10 * (NXA + 1), "Bj must fit into the [Cv | ev] buffer");
+    double (*Bj)[LDJ] = reinterpret_cast<double (*)[LDJ]>(&G[0][0]);
+    for (int i = lane; i < 9 * LDJ; i += 32) { const int rr_ = i / LDJ, cc_ = i % LDJ; Bj[rr_][cc_] = (cc_ < NJ) ? Bd[rr_ * NU + 12 + cc_] : 0.0; }
+    // contribution of the fixed open-contact forces (du_F = -F) to rows 3..11 of bt, one row per lane 0..8
+    if (lane < 16) {
+      double open_corr = 0.0;
+      if (lane < 9) {
+        for (int cn = 0; cn < NCON; ++cn) if (!(cn / 2 == 0 ? st0 : st1))
+          for (int qq = 0; qq < 3; ++qq) open_corr -= Bd[lane * NU + 3 * cn + qq] * rec[D::R_FO + 3 * cn + qq];
+      }
+      sMisc[warp][16 + lane] = open_corr;
+    }
+    __syncwarp();
+    // ---- element-wise parts (lane = column of W, values in y[]; done first so that y[] is dead during the tile products)
+    if (is_rhs) {
+      const int c = lane, xs_ = c < 6 ? c : c + 3;
+#pragma unroll
+      for (int l = 0; l < NJ; ++l) {   // At rows 12..: I + dt Pxj ; bt rows 12..
+        if (c < NXA) so[S::S_AB + (12 + l) * S::LDA + xs_] = dt * y[l] + ((12 + l == xs_) ? 1.0 : 0.0);
+        else so[S::S_B + 12 + l] = rec[D::R_B + 12 + l] + dt * y[l];
+      }
+      if (c == NXA) {   // rows 0..2 of bt: B_d rows 0..2 = dt/m on the force columns
+        const double f = dt / M.total_mass;
+        for (int qq = 0; qq < 3; ++qq) {
+          double bb = rec[D::R_B + qq];
+          for (int cn = 0; cn < NCON; ++cn) if (!(cn / 2 == 0 ? st0 : st1)) bb -= f * rec[D::R_FO + 3 * cn + qq];
+          so[S::S_B + qq] = bb;
+        }
+        for (int qq = 6; qq < 9; ++qq) { so[S::S_Q + qq] = rec[D::R_Q + qq]; so[S::qf(qq, qq)] = dt * sQd[qq] + dq; }
+      } else {
+        for (int r_ = 0; r_ < MP; ++r_) if (!(r_ >= 3 * nclosed && r_ < m)) so[S::prf(r_, xs_)] = 0.0;   // Pt rows that are not null-space rows
+      }
+    } else if (is_null) {
+      const int t = lane - CN;
+#pragma unroll
+      for (int l = 0; l < NJ; ++l) so[S::S_AB + (12 + l) * S::LDA + 24 + 3 * nclosed + t] = dt * y[l];   // Bt rows 12..: dt N
+    }
+    // accumulator initialisers of AJ (issued early): A_d - I rows 3..11 / b rows 3..11 + open-contact correction
+    double ad[2][4][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int rr = 8 * mt + g, C = 8 * nt + 2 * q + sl;
+          double v = 0.0;
+          if (rr < 9) { if (C < NXA) v = rec[D::R_AD + rr * NXA + C]; else if (C == CA) v = rec[D::R_B + 3 + rr] + sMisc[warp][16 + rr]; }
+          ad[mt][nt][sl] = v;
+        }
+    // ---- step 1: Z^T = W^T Rj (32 x 16), then Z = dt Z + dr W (+ r_j on the affine column): Z[mt][nt] holds (Rj_eff W)[8 nt + 2q + s][8 mt + g]
+    double a[2][2][4], Z[4][2][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) { Z[mt][nt][0] = 0.0; Z[mt][nt][1] = 0.0; }
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) a[kb][sl][mt] = W[8 * kb + 2 * q + sl][8 * mt + g];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const double bR = sRjP[8 * kb + 2 * q + sl][8 * nt + g];
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) dmma884(Z[mt][nt][0], Z[mt][nt][1], a[kb][sl][mt], bR);
+        }
+      }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          double v = dt * Z[mt][nt][sl] + dr * a[nt][sl][mt];
+          if (8 * mt + g == CA) v += sMisc[warp][8 * nt + 2 * q + sl];
+          Z[mt][nt][sl] = v;
+        }
+    // ---- step 2: M = W^T (Rj_eff W), tile by tile; each tile is scattered to its destinations straight from the accumulator fragment
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        if (!(mt >= nt || (nt == CA / 8 && mt < nt))) continue;   // lower triangle + the tiles above the diagonal that hold the affine column
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) dmma884(c0, c1, a[kb][sl][mt], Z[nt][kb][sl]);
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int R = 8 * mt + g, C = 8 * nt + 2 * q + sl;
+          const double v = sl ? c1 : c0;
+          const int sR = R < 6 ? R : R + 3, sC = C < 6 ? C : C + 3;
+          if (R < NXA) {
+            if (C < NXA) {
+              if (mt >= nt) {
+                const double vv = v + ((R == C) ? dt * sQd[sR < 24 ? sR : 0] + dq : 0.0);
+                so[S::qf(sR, sC)] = vv;
+                if (mt > nt) so[S::qf(sC, sR)] = vv;
+              }
+            } else if (C == CA) so[S::S_Q + sR] = rec[D::R_Q + sR] + v;
+          } else if (R >= CN && R - CN < mj) {
+            const int row = 3 * nclosed + R - CN;
+            if (C < NXA) so[S::prf(row, sC)] = v;
+            else if (C == CA) so[S::S_R + row] = v;
+            else if (C - CN < mj) {
+              const int col = 3 * nclosed + C - CN;
+              so[S::prf(row, 24 + col)] = v;
+              if (mt > nt) so[S::prf(col, 24 + row)] = v;
+            }
+          }
+        }
+      }
+    // ---- step 3: AJ = B_d[:, joints] W (16 x 32): joint part of At rows 3..11, bt rows 3..11, null-space columns of Bt rows 3..11
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      double bj[2][2];
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) bj[kb][sl] = Bj[(8 * mt + g) < 9 ? 8 * mt + g : 8][8 * kb + 2 * q + sl];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        double c0 = ad[mt][nt][0], c1 = ad[mt][nt][1];
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) dmma884(c0, c1, bj[kb][sl], a[kb][sl][nt]);
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int rr = 8 * mt + g, C = 8 * nt + 2 * q + sl;
+          const double v = sl ? c1 : c0;
+          if (rr < 9) {
+            const int sC = C < 6 ? C : C + 3;
+            if (C < NXA) so[S::S_AB + (3 + rr) * S::LDA + sC] = v + ((3 + rr == sC) ? 1.0 : 0.0);
+            else if (C == CA) so[S::S_B + 3 + rr] = v;
+            else if (C - CN < mj) so[S::S_AB + (3 + rr) * S::LDA + 24 + 3 * nclosed + C - CN] = v;
+          }
+        }
+      }
+    }
+    // Bt entries outside the null-space block: rows 0..2, closed-contact force columns, zero columns beyond m
+    for (int i = lane; i < NX * MP; i += 32) {
+      const int r_ = i / MP, c = i % MP, rr = r_ - 3;
+      if (r_ >= 3 && c >= 3 * nclosed && c < m) continue;
+      double v = 0.0;
+      if (r_ < 3) { if (c < 3 * nclosed && c % 3 == r_) v = dt / M.total_mass; }
+      else if (c < 3 * nclosed && rr < 9) v = Bd[rr * NU + (st0 ? c : 6 + c)];
+      so[S::S_AB + r_ * S::LDA + 24 + c] = v;
+    }
+    // Rt outside the null block: force blocks (barrier Hessians + diagonal), identity beyond m, zero cross blocks
+    for (int i = lane; i < MP * MP; i += 32) {
+      const int r_ = i / MP, c = i % MP;
+      if (r_ >= 3 * nclosed && c >= 3 * nclosed && r_ < m && c < m) continue;
+      double v = 0.0;
+      if (r_ >= m || c >= m) v = (r_ == c) ? 1.0 : 0.0;
+      else if (r_ < 3 * nclosed && c < 3 * nclosed && r_ / 3 == c / 3) {
+        const int cn = (st0 ? 0 : 2) + r_ / 3, p_ = r_ % 3, q_ = c % 3;
+        const int lo = p_ < q_ ? p_ : q_, hi = p_ < q_ ? q_ : p_;
+        v = rec[D::R_HB + 6 * cn + (lo == 0 ? hi : (lo == 1 ? 2 + hi : 5))];
+        if (p_ == q_) v += dt * M.Rforce[3 * cn + p_] + dr;
+      }
+      so[S::prf(r_, 24 + c)] = v;
+    }
+    if (lane < 3 * nclosed) { const int fc = st0 ? lane : 6 + lane; so[S::S_R + lane] = rec[D::R_R + fc]; }
+    if (lane >= m && lane < MP) so[S::S_R + lane] = 0.0;
+    return;
+  }
   // ---------------- change of input variables.  y[] = own column of [Pxj | Pej] (lanes <= NXA) or of N (null lanes)
   const double* Bd = sBd[warp];
   // t[] = Rj_eff * (own column)  (+ r_j for the Pe column -> t1 = r_j + Rj_eff Pej)
@@ -1074,9 +1280,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 
 // ------------------------------------------------------------------------------------------------ DMMA tile GEMM in shared memory
-__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 // C[8MT x 8NT] = (ACC ? C : 0) + sign * op(A) op(B), K = 4 KT.  TA: A is given transposed (As[k][m]); TB: B is given transposed (Bs[n][k]).
 // Output tiles are distributed round-robin over warps [W0, W0 + NW) of the CTA; each warp interleaves the k-loops of its tiles
 // (independent accumulator chains).  All leading dimensions are == 4 or 12 (mod 16) doubles: every fragment load is bank-conflict free.

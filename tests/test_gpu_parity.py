@@ -302,6 +302,7 @@ def test_riccati_kernel_variants_agree():
             g = G(B, model_file=model, dt=0.01, time_horizon=1.0)
             g.setOption("riccati_mode", mode)
             g.setOption("ls_mode", mode)
+            g.setOption("project_mode", mode)   # and the scalar change of input variables instead of the tensor-core one
             g.setCurrentObservation(np.zeros(B), X0); g.setTargetsFromCmdVel(cmd, 1.0); g.setModeSchedule(ET, MS, NE)
             g.advanceMpc(); g.advanceMpc()
             assert not (g.getStatus() & ~16).any()
