@@ -57,7 +57,7 @@ struct bmpc_handle {
   double *d_lq = nullptr, *d_proj = nullptr, *d_stage = nullptr, *d_ric = nullptr, *d_base = nullptr, *d_dx = nullptr, *d_du = nullptr, *d_perf_trial = nullptr, *d_perf = nullptr, *d_alpha = nullptr, *d_norms = nullptr;
   int *d_done = nullptr, *d_status = nullptr, *d_counters = nullptr;
   int* h_counters = nullptr;
-  size_t rec = 0, prec = 0, krec = 0, srec = 0, brec = 0; int lq_mode = 3, riccati_mode = 1, ls_mode = 1, project_mode = 1;   // 0: k_lq, 1: k_model_base + k_lq_assemble, 2: fused warp-cooperative, 3: pair-packed fused (default)
+  size_t rec = 0, prec = 0, krec = 0, srec = 0, brec = 0; int lq_mode = 3, riccati_mode = 1, ls_mode = 1, project_mode = 1;   // 0: k_lq, 1: k_model_base + k_lq_assemble, 2: fused warp-cooperative, 3: packed fused, 3 (H1) / 2 (G1) stages per warp (default)
   // gait bookkeeping
   std::vector<GaitSchedule> gaits; bool use_gait = false;
   // stats
@@ -114,14 +114,15 @@ void tick(bmpc_handle* h) {
   CK(cudaFuncSetAttribute(k_riccati<NJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_riccati_warp<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(RicWarpSmem<NJ>))));
   CK(cudaFuncSetAttribute(k_riccati_warp<NJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(k_lq_pair<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LqPairSmem<NJ>)));
+  CK(cudaFuncSetAttribute(k_lq_pack<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LqPackSmem<NJ>)));
   CK(cudaFuncSetAttribute(k_policy_expand<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(PolSmem<NJ>))));
   CK(cudaFuncSetAttribute(k_forward<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(FwdSmem<NJ>))));
   h->linesearch_trials = 0;
   for (int iter = 0; iter < h->sqp_iterations; ++iter) {
     if (h->lq_mode == 3) {
-      const int NP = (NS + 1) / 2;
-      k_lq_pair<NJ><<<(B * NP + 3) / 4, 128, sizeof(LqPairSmem<NJ>), st>>>(d); ++h->launches;
+      constexpr int G = LqPackSmem<NJ>::G;
+      const int NP = (NS + G - 1) / G;
+      k_lq_pack<NJ><<<(B * NP + 3) / 4, 128, sizeof(LqPackSmem<NJ>), st>>>(d); ++h->launches;
     } else if (h->lq_mode == 2) { k_lq_assemble<NJ, true><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches; }
     else if (h->lq_mode == 1) {
       k_model_base<NJ><<<(nodes + 63) / 64, 64, 0, st>>>(d); ++h->launches;

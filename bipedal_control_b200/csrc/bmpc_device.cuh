@@ -555,17 +555,31 @@ __device__ __forceinline__ double warp_sum(double v) { for (int o = 16; o > 0; o
 // jc: per-joint constants of this lane's joint in shared memory, layout [Rj 9 | pj 3 | axis 3 | mass 1 | com 3 | inertia 9] (28 doubles)
 // SEG = 32: one stage per warp (lane = joint).  SEG = 16: two stages per warp, one per half-warp (lane & 15 = joint); x, u, base and jc are
 // then per-half pointers and every shuffle stays inside the lane's 16-lane segment (segment base hb).
-template <int SEG>
-__device__ __forceinline__ double seg_sum(double v) { for (int o = SEG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
+// sum over the NJ joint lanes of a segment, result in every lane of the segment.  Power-of-two segments: xor butterfly (idle lanes hold 0).
+// Other segment sizes (SEG == NJ): suffix doubling along each leg (NL lanes), then the two leg totals are added.
+template <int SEG, int NL>
+__device__ __forceinline__ double seg_sum(double v, int lane_w) {
+  if constexpr ((SEG & (SEG - 1)) == 0) {
+    for (int o = SEG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  } else {
+    static_assert(SEG == 2 * NL, "non power-of-two segments hold exactly the two legs");
+    const int jl = lane_w % SEG, hb = lane_w - jl, li = jl % NL;
+#pragma unroll
+    for (int o = 1; o < NL; o <<= 1) { const double t = __shfl_sync(0xffffffffu, v, lane_w + o); if (li + o < NL) v += t; }
+    return __shfl_sync(0xffffffffu, v, hb) + __shfl_sync(0xffffffffu, v, hb + NL);
+  }
+}
 template <int NJ, int SEG = 32>
 __device__ __forceinline__ void warp_model_base(const double* __restrict__ x, const double* __restrict__ u, double* __restrict__ base, int lane_w, const double* __restrict__ jc) {
   using BD = BaseDims<NJ>;
   constexpr int NL = Dims<NJ>::NL;
-  static_assert(NJ < SEG, "one idle lane per segment writes the shared part of the record");
+  static_assert(NJ <= SEG, "one lane per joint");
   const DevModel& M = c_model;
   const double mass = M.total_mass, imass = 1.0 / mass;
-  const int lane = lane_w & (SEG - 1), hb = lane_w & ~(SEG - 1);   // lane: index inside the segment; lane_w +- 1 shuffles stay inside a leg
-  const bool act = lane < NJ;
+  const int lane = lane_w % SEG, hb = lane_w - lane;   // lane: index inside the segment; lane_w +- 1 shuffles stay inside a leg
+  const bool act = lane < NJ && hb + SEG <= 32;        // lanes beyond the last complete segment (SEG = 10: lanes 30, 31) only tag along
+  constexpr int WR = (SEG > NJ) ? SEG - 1 : 0;         // lane of the segment that writes the shared part of the record
   const int j = act ? lane : 0, lvl_own = j % NL;
   double sz, cz, sy, cy, sx, cx;
   {   // one sincos per lane (lane % 3 picks the Euler angle), broadcast with shuffles instead of three evaluations on every lane
@@ -621,8 +635,8 @@ __device__ __forceinline__ void warp_model_base(const double* __restrict__ x, co
   { const Mom m = si_apply(comp, a, cross(o, a)); Alin = m.p; Aang = m.n - cross(com, m.p); }
   // ---- generalized velocity: v_b = A_b^-1 (m h - sum_j A_j qd_j)
   const double qd = act ? u[12 + j] : 0.0;
-  v3 ml = mk(mass * x[0] - seg_sum<SEG>(qd * Alin.x), mass * x[1] - seg_sum<SEG>(qd * Alin.y), mass * x[2] - seg_sum<SEG>(qd * Alin.z));
-  v3 ma = mk(mass * x[3] - seg_sum<SEG>(qd * Aang.x), mass * x[4] - seg_sum<SEG>(qd * Aang.y), mass * x[5] - seg_sum<SEG>(qd * Aang.z));
+  v3 ml = mk(mass * x[0] - seg_sum<SEG, NL>(qd * Alin.x, lane_w), mass * x[1] - seg_sum<SEG, NL>(qd * Alin.y, lane_w), mass * x[2] - seg_sum<SEG, NL>(qd * Alin.z, lane_w));
+  v3 ma = mk(mass * x[3] - seg_sum<SEG, NL>(qd * Aang.x, lane_w), mass * x[4] - seg_sum<SEG, NL>(qd * Aang.y, lane_w), mass * x[5] - seg_sum<SEG, NL>(qd * Aang.z, lane_w));
   const v3 w = mk(A22i[0] * ma.x + A22i[1] * ma.y + A22i[2] * ma.z, A22i[3] * ma.x + A22i[4] * ma.y + A22i[5] * ma.z, A22i[6] * ma.x + A22i[7] * ma.y + A22i[8] * ma.z);
   const v3 vlin = imass * (ml - mk(A12[0] * w.x + A12[1] * w.y + A12[2] * w.z, A12[3] * w.x + A12[4] * w.y + A12[5] * w.z, A12[6] * w.x + A12[7] * w.y + A12[8] * w.z));
   v3 Ftot = mk(0.0, 0.0, 0.0), tau = mk(0.0, 0.0, 0.0);
@@ -654,14 +668,14 @@ __device__ __forceinline__ void warp_model_base(const double* __restrict__ x, co
   }
   Mom htot;
   { Mom bm; bm.p = M.base_mass * (ve[3] + cross(we[3], cbase)); bm.n = mul(Ibase, we[3]) + cross(cbase, bm.p); htot = bm + shfl_mom(hs, hb) + shfl_mom(hs, hb + NL); }
-  // ---- write the record: per-joint part by the joint's lane, shared part by the last lane of the segment (idle otherwise)
+  // ---- write the record: per-joint part by the joint's lane, shared part by lane WR of the segment (an idle lane when there is one)
   if (act) {
     double* J = base + BD::B_J + BD::JS * j;
     st3(J + BD::J_O, o); st3(J + BD::J_A, a); st_si(J + BD::J_SI, comp); st3(J + BD::J_AL, Alin); st3(J + BD::J_AA, Aang);
     st3(J + BD::J_W, wj); st3(J + BD::J_V, vj); st3(J + BD::J_HN, hs.n); st3(J + BD::J_HP, hs.p);
     base[BD::B_F + 12 + j] = qd;
   }
-  if (lane == SEG - 1) {
+  if (lane == WR && hb + SEG <= 32) {
     st3(base + BD::B_PB, pb);
 #pragma unroll
     for (int k = 0; k < 3; ++k) { st3(base + BD::B_BAX + 3 * k, bax[k]); st3(base + BD::B_ALE + 3 * k, Alin_e[k]); st3(base + BD::B_AAE + 3 * k, Aang_e[k]); }

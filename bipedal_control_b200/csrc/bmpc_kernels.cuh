@@ -683,68 +683,81 @@ __global__ void __launch_bounds__(128, FUSED ? LQ_FUSED_BLOCKS : 4) k_lq_assembl
   lq_stage_columns<NJ>(d, nb, k, rec, sbase[warp], sbase[warp] + BASE, xs, us, xns, xrs, sA2[warp], lane);
 }
 
-// Pair-packed LQ kernel (default): one warp per TWO consecutive stages of an instance.  The base pass (lane & 15 = leg joint) runs for both
-// stages at once, one per half-warp, so 2 NJ of 32 lanes are busy instead of NJ; the column pass (lane = column) then handles the two stages
-// one after the other.  A half whose stage is an event node or beyond the horizon mirrors the other half's inputs (results discarded).
+// Packed LQ kernel (default): one warp per G consecutive stages of an instance (H1: G = 3 segments of 10 lanes, G1: G = 2 segments of 16).
+// The base pass (lane inside the segment = leg joint) runs for the G stages at once, so G NJ of 32 lanes are busy instead of NJ; the
+// column pass (lane = column) then handles the stages one after the other.  A segment whose stage is an event node or beyond the horizon
+// mirrors the inputs of a stage that needs the model (results discarded).
 template <int NJ>
-struct LqPairSmem {
+struct LqPackSmem {
   static constexpr int BASE = BaseDims<NJ>::BASE, NXA = Dims<NJ>::NXA, WPB = 4;
+  static constexpr int SEG = (NJ <= 10) ? 10 : 16, G = 32 / SEG;
   double jc[NJ][28];
-  double base[WPB][2][2 * BASE];
+  double base[WPB][G][2 * BASE];
   double A2[WPB][9][NXA + 1];
-  double xu[WPB][2][4 * 24];   // per stage: x, u, xnext, xref
+  double xu[WPB][G][4 * 24];   // per stage: x, u, xnext, xref
 };
 template <int NJ>
-__global__ void __launch_bounds__(128, LQ_PAIR_BLOCKS) k_lq_pair(Dev d) {
-  using D = Dims<NJ>; using BD = BaseDims<NJ>; using SM = LqPairSmem<NJ>;
-  constexpr int NX = D::NX, NU = D::NU, WPB = SM::WPB, BASE = BD::BASE;
+__global__ void __launch_bounds__(128, LQ_PAIR_BLOCKS) k_lq_pack(Dev d) {
+  using D = Dims<NJ>; using BD = BaseDims<NJ>; using SM = LqPackSmem<NJ>;
+  constexpr int NX = D::NX, NU = D::NU, WPB = SM::WPB, BASE = BD::BASE, SEG = SM::SEG, G = SM::G;
+  static_assert(G * 24 <= 9 * (D::NXA + 1), "the second RK2 evaluation points are staged in the A2 buffer");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < NJ * 28; i += 128) (&sm.jc[0][0])[i] = d.jc[i];
   __syncthreads();
-  const int NP = (d.NS + 1) >> 1;
+  const int NP = (d.NS + G - 1) / G;
   const int gw = blockIdx.x * WPB + warp;
-  const int b = gw / NP, k0 = 2 * (gw % NP);
+  const int b = gw / NP, k0 = G * (gw % NP);
   if (b >= d.B) return;
   const int N = d.n_nodes[b] - 1;
   if (k0 >= N) return;
   const size_t nb = (size_t)b * d.NS;
-  const bool has1 = k0 + 1 < N;
-  const bool ev0 = d.node_ev[nb + k0] == 1, ev1 = has1 && d.node_ev[nb + k0 + 1] == 1;
-  const bool comp0 = !ev0, comp1 = has1 && !ev1;   // stages that need the model
+  bool has[G], ev[G], comp[G];   // stage exists / is an event node / needs the model
+  int first_comp = -1;
 #pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    if (s == 1 && !has1) break;
+  for (int s = 0; s < G; ++s) {
+    has[s] = k0 + s < N;
+    ev[s] = has[s] && d.node_ev[nb + k0 + s] == 1;
+    comp[s] = has[s] && !ev[s];
+    if (comp[s] && first_comp < 0) first_comp = s;
+  }
+#pragma unroll
+  for (int s = 0; s < G; ++s) {
+    if (!has[s]) continue;
     const int k = k0 + s;
     double* xs = sm.xu[warp][s];
     if (lane < NX) { xs[lane] = d.s_x[(nb + k) * NX + lane]; xs[48 + lane] = d.s_x[(nb + k + 1) * NX + lane]; xs[72 + lane] = d.xref[(nb + k) * NX + lane]; }
     if (lane < NU) xs[24 + lane] = d.s_u[(nb + k) * NU + lane];
   }
   __syncwarp();
-  if (comp0 || comp1) {
-    const int h = lane >> 4;
-    const int ms = (h == 0) ? (comp0 ? 0 : 1) : (comp1 ? 1 : 0);   // stage whose inputs this half evaluates
+  if (first_comp >= 0) {
+    const int h = lane / SEG;          // segment of this lane (lanes beyond the last complete segment tag along with segment 0's data)
+    int ms = first_comp;               // stage whose inputs this segment evaluates
+#pragma unroll
+    for (int s = 0; s < G; ++s) if (h == s && comp[s]) ms = s;
+    const int hs_ = h < G ? h : 0;
     const double* xh = sm.xu[warp][ms]; const double* uh = xh + 24;
-    double* bh = sm.base[warp][h];
-    const double* jc = sm.jc[(lane & 15) < NJ ? (lane & 15) : 0];
-    double* x2 = &sm.A2[warp][0][0];   // scratch for the second RK2 evaluation points (A2 is filled later): 2 x 24 doubles
-    warp_model_base<NJ, 16>(xh, uh, bh, lane, jc);
+    double* bh = sm.base[warp][hs_];
+    const int jl = lane % SEG;
+    const double* jc = sm.jc[jl < NJ ? jl : 0];
+    double* x2 = &sm.A2[warp][0][0];   // scratch for the second RK2 evaluation points (A2 is filled later): G x 24 doubles
+    warp_model_base<NJ, SEG>(xh, uh, bh, lane, jc);
     __syncwarp();
 #pragma unroll
-    for (int s = 0; s < 2; ++s)
-      if (lane < NX) x2[24 * s + lane] = sm.xu[warp][s][lane] + d.st_dt[nb + k0 + (s == 1 && !has1 ? 0 : s)] * sm.base[warp][s][BD::B_F + lane];
+    for (int s = 0; s < G; ++s)
+      if (lane < NX) x2[24 * s + lane] = comp[s] ? sm.xu[warp][s][lane] + d.st_dt[nb + k0 + s] * sm.base[warp][s][BD::B_F + lane] : 0.0;
     __syncwarp();
-    warp_model_base<NJ, 16>(x2 + 24 * ms, uh, bh + BASE, lane, jc);
+    warp_model_base<NJ, SEG>(x2 + 24 * ms, uh, bh + BASE, lane, jc);
     __syncwarp();
   }
 #pragma unroll 1
-  for (int s = 0; s < 2; ++s) {
-    if (s == 1 && !has1) break;
+  for (int s = 0; s < G; ++s) {
+    if (k0 + s >= N) break;
     const int k = k0 + s;
     double* __restrict__ rec = d.lq + (nb + k) * D::REC;
     const double* xs = sm.xu[warp][s];
-    if (s == 0 ? ev0 : ev1) {   // [UPSTREAM] setupEventNode
+    if (d.node_ev[nb + k] == 1) {   // [UPSTREAM] setupEventNode
       double sq = 0.0;
       if (lane < NX) { const double bi = xs[lane] - xs[48 + lane]; rec[D::R_B + lane] = bi; sq = bi * bi; }
       for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
