@@ -57,7 +57,7 @@ struct bmpc_handle {
   double *d_lq = nullptr, *d_proj = nullptr, *d_stage = nullptr, *d_ric = nullptr, *d_base = nullptr, *d_dx = nullptr, *d_du = nullptr, *d_perf_trial = nullptr, *d_perf = nullptr, *d_alpha = nullptr, *d_norms = nullptr;
   int *d_done = nullptr, *d_status = nullptr, *d_counters = nullptr;
   int* h_counters = nullptr;
-  size_t rec = 0, prec = 0, krec = 0, srec = 0, brec = 0; int lq_mode = 3, riccati_mode = 1, ls_mode = 1, project_mode = 1;   // 0: k_lq, 1: k_model_base + k_lq_assemble, 2: fused warp-cooperative, 3: packed fused, 3 (H1) / 2 (G1) stages per warp (default)
+  size_t rec = 0, prec = 0, krec = 0, srec = 0, brec = 0; int lq_mode = 3, riccati_mode = 1, ls_mode = 1;   // 0: k_lq, 1: k_model_base + k_lq_assemble, 2: fused warp-cooperative, 3: packed fused, 3 (H1) / 2 (G1) stages per warp (default)
   // gait bookkeeping
   std::vector<GaitSchedule> gaits; bool use_gait = false;
   // stats
@@ -129,8 +129,7 @@ void tick(bmpc_handle* h) {
       k_lq_assemble<NJ, false><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches;
     } else { k_lq<NJ><<<(nodes + 63) / 64, 64, 0, st>>>(d); ++h->launches; }
     if (iter == 0) mark(2);
-    if (h->project_mode == 1) { k_project<NJ, true><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches; }   // change of variables on the FP64 tensor cores (default)
-    else { k_project<NJ, false><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches; }
+    k_project<NJ><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches;
     if (iter == 0) mark(3);
     if (h->riccati_mode == 1) { k_riccati_warp<NJ><<<(B + 3) / 4, 128, 4 * sizeof(RicWarpSmem<NJ>), st>>>(d); ++h->launches; }   // one warp per instance (default)
     else { k_riccati<NJ><<<B, WS_THREADS, sizeof(RicSmem<NJ>), st>>>(d); ++h->launches; }                                        // one CTA per instance
@@ -510,7 +509,6 @@ int bmpc_get_observations(bmpc_handle* h, double* t, double* x) {
 int bmpc_get_launch_count(const bmpc_handle* h) { return h ? h->launches : 0; }
 int bmpc_debug_set_option(bmpc_handle* h, const char* name, int value) {
   if (!h || !name) return BMPC_ERR_INVALID;
-  if (std::string(name) == "project_mode") { if (value < 0 || value > 1) return BMPC_ERR_INVALID; h->project_mode = value; return BMPC_OK; }
   if (std::string(name) == "ls_mode") { if (value < 0 || value > 1) return BMPC_ERR_INVALID; h->ls_mode = value; return BMPC_OK; }
   if (std::string(name) == "riccati_mode") { if (value < 0 || value > 1) return BMPC_ERR_INVALID; h->riccati_mode = value; return BMPC_OK; }
   if (std::string(name) == "lq_mode") { if (value < 0 || value > 3) return BMPC_ERR_INVALID; h->lq_mode = value; return BMPC_OK; }

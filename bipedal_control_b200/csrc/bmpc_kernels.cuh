@@ -811,34 +811,33 @@ __global__ void k_stage_static(double* stage, size_t nrec) {
   for (int r = 0; r < 3; ++r) { so[S::S_AB + r * S::LDA + r] = 1.0; so[S::S_AB + (6 + r) * S::LDA + 6 + r] = 1.0; }
 }
 
-// TC = true (default): the change of input variables runs on the FP64 tensor cores.  With W = [Pxj | Pej | N] (NJ x 32, one column per lane)
-//   M  = W^T (Rj_eff W)   holds Qt (x-x block), the qt / rt corrections (affine column), Pt (null-x block) and the null block of Rt at once,
-//   AJ = B_d[:, joints] W holds the joint part of At rows 3..11, bt and the null-space columns of Bt;
-// Z^T = W^T Rj is formed first and reused as the B operand of M (same register-chaining trick as k_riccati_warp: Rj is symmetric).
-// TC = false: the scalar lane-per-column version (kept for cross-checking, bmpc_debug_set_option("project_mode", 0)).
-template <int NJ, bool TC>
-__global__ void __launch_bounds__(128, TC ? PROJ_BLOCKS : 4) k_project(Dev d) {
+// Lane roles after the QR (one column of W = [Px | Pe | N] per lane, in FULL-STATE column order so that the tensor-core tiles line up with
+// the stage record): lane L < 24 = state column L (L = 6 carries the affine column Pe: base-position columns 6..8 of Px are structurally
+// zero; 7, 8 and the padding lanes stay zero), lane 24 + t = null-space column t.  The reduced input is ordered [null-space (mj) | closed-contact
+// forces (3 nclosed)], so the null rows / columns are tile aligned as well.
+// The change of input variables runs on the FP64 tensor cores:
+//   M  = W^T (Rj_eff W) (32 x 32)  : tiles (a, b < 3) are Qt in accumulator-fragment order (stored with one 16-byte store per lane and tile),
+//                                    row 6 / column 6 hold the qt / rt corrections, tiles (3, b < 3) are Pt, tile (3, 3) the null block of Rt;
+//   AJ = B_d[:, joints] W (16 x 32): joint part of At rows 3..11 (stored as row-major pairs), bt, null-space columns of Bt.
+// Z^T = W^T Rj is formed first and reused from registers as the B operand of M (same register-chaining trick as k_riccati_warp).
+template <int NJ>
+__global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
   using D = Dims<NJ>; using S = SDims<NJ>;
-  constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, NXR = S::NXR, MP = S::MP;
+  constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, MP = S::MP, LDA = S::LDA;
   constexpr int WPB = 4;
+  constexpr int LDW = 34, LDR = 18, LDJ = 20;   // leading dimensions = 2 mod 4: k-permuted fragment loads are conflict free
   __shared__ double sM[WPB][NJ][12];     // Dv^T  (NJ x r), r <= 10
   __shared__ double sV[WPB][10][NJ];     // Householder vectors (zero padded)
   __shared__ double sBeta[WPB][10];
-  __shared__ double sG[WPB][10][NXA + 1];
-  __shared__ double sPx[TC ? 1 : WPB][TC ? 1 : NJ][NXA + 1];   // [Pxj | Pej]   (scalar version only)
-  __shared__ double sN[TC ? 1 : WPB][TC ? 1 : NJ][8];
-  __shared__ double sRN[TC ? 1 : WPB][TC ? 1 : NJ][8];         // Rj_eff N
-  constexpr int LDW = 34, LDR = 18, LDJ = 20, CA = NXA, CN = NXA + 1;   // leading dimensions = 2 mod 4: k-permuted fragment loads are conflict free
-  __shared__ double sW[TC ? WPB : 1][TC ? 16 : 1][LDW];        // W = [Pxj | Pej | N | 0], rows >= NJ zero
-  __shared__ double sMisc[TC ? WPB : 1][32];          // r_j (16) | open-contact correction of bt rows 3..11 (16)
-  __shared__ double sRjP[16][LDR];                    // joint block of R (model constant), zero padded
+  __shared__ double sG[WPB][10][NXA + 1];   // [Cv | ev]; after the triangular solves: the padded joint block of B_d
+  __shared__ double sBd[WPB][9 * (12 + NJ)];  // B_d rows 3..11
+  __shared__ double sW[WPB][16][LDW];        // W, rows >= NJ zero
+  __shared__ double sMisc[WPB][32];          // r_j (16) | open-contact correction of bt rows 3..11 (16)
+  __shared__ double sRjP[16][LDR];           // joint block of R (model constant), zero padded
   __shared__ double sQd[24];
-  if (TC) {
-    for (int i = threadIdx.x; i < 16 * LDR; i += 128) { const int rr_ = i / LDR, cc_ = i % LDR; sRjP[rr_][cc_] = (rr_ < NJ && cc_ < NJ) ? c_model.Rjoint[rr_ * NJ + cc_] : 0.0; }
-    if (threadIdx.x < 24) sQd[threadIdx.x] = threadIdx.x < NX ? c_model.Qdiag[threadIdx.x] : 0.0;
-    __syncthreads();
-  }
-  __shared__ double sBd[WPB][9 * (12 + NJ)];  // B_d rows 3..11 (read many times with warp-uniform indices)
+  for (int i = threadIdx.x; i < 16 * LDR; i += 128) { const int rr_ = i / LDR, cc_ = i % LDR; sRjP[rr_][cc_] = (rr_ < NJ && cc_ < NJ) ? c_model.Rjoint[rr_ * NJ + cc_] : 0.0; }
+  if (threadIdx.x < 24) sQd[threadIdx.x] = threadIdx.x < NX ? c_model.Qdiag[threadIdx.x] : 0.0;
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * WPB + warp;
   const int b = gw / d.NS, k = gw % d.NS;
@@ -857,8 +856,8 @@ __global__ void __launch_bounds__(128, TC ? PROJ_BLOCKS : 4) k_project(Dev d) {
   const DevModel& M = c_model;
   const int r = (int)rec[D::R_MISC + D::M_NROWS];
   double (*Mt)[12] = sM[warp]; double (*V)[NJ] = sV[warp]; double* beta = sBeta[warp]; double (*G)[NXA + 1] = sG[warp];
-  double (*Px)[NXA + 1] = sPx[TC ? 0 : warp]; double (*Nn)[8] = sN[TC ? 0 : warp]; double (*RN)[8] = sRN[TC ? 0 : warp];
-  double (*W)[LDW] = sW[TC ? warp : 0];
+  double (*W)[LDW] = sW[warp];
+  const double* Bd = sBd[warp];
   {   // stage Dv^T, [Cv | ev] and B_d rows 3..11: all global loads are issued before the first shared-memory store (fixed trip counts;
       // rows >= r hold stale but finite data and are never used)
     constexpr int N1 = (10 * NJ + 31) / 32, N2 = (10 * NXA + 31) / 32, N3 = (9 * NU + 31) / 32;
@@ -870,6 +869,7 @@ __global__ void __launch_bounds__(128, TC ? PROJ_BLOCKS : 4) k_project(Dev d) {
 #pragma unroll
     for (int i = 0; i < N3; ++i) { const int e = lane + 32 * i; t3[i] = e < 9 * NU ? rec[D::R_BD + e] : 0.0; }
     const double tev = lane < 10 ? rec[D::R_EV + lane] : 0.0;
+    const double trj = lane < NJ ? rec[D::R_R + 12 + lane] : 0.0;
 #pragma unroll
     for (int i = 0; i < N1; ++i) { const int e = lane + 32 * i; if (e < 10 * NJ) Mt[e % NJ][e / NJ] = t1[i]; }
 #pragma unroll
@@ -877,13 +877,10 @@ __global__ void __launch_bounds__(128, TC ? PROJ_BLOCKS : 4) k_project(Dev d) {
 #pragma unroll
     for (int i = 0; i < N3; ++i) { const int e = lane + 32 * i; if (e < 9 * NU) sBd[warp][e] = t3[i]; }
     if (lane < 10) G[lane][NXA] = tev;
+    if (lane < 16) sMisc[warp][lane] = trj;
   }
   for (int i = lane; i < 10 * NJ; i += 32) V[i / NJ][i % NJ] = 0.0;
-  if (!TC) for (int i = lane; i < NJ * 8; i += 32) { Nn[i / 8][i % 8] = 0.0; RN[i / 8][i % 8] = 0.0; }
   __syncwarp();
-  if (TC) {   // joint block of B_d rows 3..11, padded; r_j
-    if (lane < 16) sMisc[warp][lane] = lane < NJ ? rec[D::R_R + 12 + lane] : 0.0;
-  }
   bool anomaly = false;
   double rmax = 0.0;
   // Householder QR with compile-time trip counts (rows beyond r are skipped by the warp-uniform test kk < r).  Lane c < r keeps its
@@ -925,49 +922,49 @@ __global__ void __launch_bounds__(128, TC ? PROJ_BLOCKS : 4) k_project(Dev d) {
 #pragma unroll
   for (int i = 0; i < NJ; ++i) if (lane < r) Mt[i][lane] = colv[i];   // R (upper triangle) for the triangular solve below
   __syncwarp();
-  // lanes 0..NXA: right-hand sides (columns of [Cv | ev]); lanes NXA+1 .. NXA+mj: null-space columns
+  // lane roles (see the header comment)
   const int mj = NJ - r;
+  const bool is_x = lane < 6 || (lane >= 9 && lane < NX), is_aff = lane == 6, is_rhs = is_x || is_aff;
+  const bool is_null = lane >= 24 && lane - 24 < mj;
+  const int gc = is_aff ? NXA : (lane < 6 ? lane : lane - 3);   // column of [Cv | ev] / compressed column index of this lane
   double y[NJ];
 #pragma unroll
   for (int i = 0; i < NJ; ++i) y[i] = 0.0;
-  const bool is_rhs = lane <= NXA, is_null = lane > NXA && lane <= NXA + mj;
   if (is_rhs) {   // z = R^-T g  (R^T lower triangular: R[l][i] = Mt[l][i] for l <= i)
 #pragma unroll
     for (int i = 0; i < NJ; ++i) if (i < r) {
-      double s = G[i][lane];
+      double s_ = G[i][gc];
 #pragma unroll
-      for (int l = 0; l < NJ; ++l) if (l < i) s -= Mt[l][i] * y[l];
-      y[i] = s / Mt[i][i];
+      for (int l = 0; l < NJ; ++l) if (l < i) s_ -= Mt[l][i] * y[l];
+      y[i] = s_ / Mt[i][i];
     }
   } else if (is_null) {
-    const int t = lane - NXA - 1;
+    const int t = lane - 24;
 #pragma unroll
     for (int i = 0; i < NJ; ++i) if (i == r + t) y[i] = 1.0;
   }
   if (is_rhs || is_null) {
     for (int kk = r - 1; kk >= 0; --kk) {   // y <- H_kk y
-      double s = 0.0;
+      double s_ = 0.0;
 #pragma unroll
-      for (int i = 0; i < NJ; ++i) s += V[kk][i] * y[i];
-      s *= beta[kk];
+      for (int i = 0; i < NJ; ++i) s_ += V[kk][i] * y[i];
+      s_ *= beta[kk];
 #pragma unroll
-      for (int i = 0; i < NJ; ++i) y[i] -= s * V[kk][i];
+      for (int i = 0; i < NJ; ++i) y[i] -= s_ * V[kk][i];
     }
     if (is_rhs) {
 #pragma unroll
-      for (int i = 0; i < NJ; ++i) { y[i] = -y[i]; if (!TC) Px[i][lane] = y[i]; }
-      if (lane < NXA) { for (int i = 0; i < NJ; ++i) out[D::P_PX + i * NXA + lane] = y[i]; }
+      for (int i = 0; i < NJ; ++i) y[i] = -y[i];
+      if (is_x) { for (int i = 0; i < NJ; ++i) out[D::P_PX + i * NXA + gc] = y[i]; }
       else { for (int i = 0; i < NJ; ++i) out[D::P_PE + i] = y[i]; }
     } else {
-      const int t = lane - NXA - 1;
+      const int t = lane - 24;
 #pragma unroll
-      for (int i = 0; i < NJ; ++i) { if (!TC) Nn[i][t] = y[i]; out[D::P_N + i * 8 + t] = y[i]; }
+      for (int i = 0; i < NJ; ++i) out[D::P_N + i * 8 + t] = y[i];
     }
   }
-  if (TC) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) W[i][lane] = (i < NJ && (is_rhs || is_null)) ? y[i < NJ ? i : 0] : 0.0;
-  }
+  for (int i = 0; i < 16; ++i) W[i][lane] = (i < NJ) ? y[i < NJ ? i : 0] : 0.0;   // idle lanes hold y = 0
   const double dt = rec[D::R_MISC + D::M_DT], dq = rec[D::R_MISC + D::M_DQ], dr = rec[D::R_MISC + D::M_DR];
   const int mode = (int)rec[D::R_MISC + D::M_MODE];
   const bool st0 = leg_in_stance(mode, 0), st1 = leg_in_stance(mode, 1);
@@ -976,300 +973,196 @@ __global__ void __launch_bounds__(128, TC ? PROJ_BLOCKS : 4) k_project(Dev d) {
   if (lane < 12) out[D::P_FO + lane] = rec[D::R_FO + lane];
   if (lane == 0) {
     out[D::P_META] = (double)mj; out[D::P_META + 1] = anomaly ? 1.0 : 0.0; out[D::P_META + 2] = (double)mode; if (anomaly) atomicOr(&d.status[b], 2);
-    double* mt = so + S::S_META;
-    mt[S::T_TYPE] = 0.0; mt[S::T_MODE] = (double)mode; mt[S::T_M] = (double)m; mt[S::T_MJ] = (double)mj; mt[S::T_NCLOSED] = (double)nclosed; mt[S::T_DT] = dt;
+    double* mt_ = so + S::S_META;
+    mt_[S::T_TYPE] = 0.0; mt_[S::T_MODE] = (double)mode; mt_[S::T_M] = (double)m; mt_[S::T_MJ] = (double)mj; mt_[S::T_NCLOSED] = (double)nclosed; mt_[S::T_DT] = dt;
   }
+  __syncwarp();   // [Cv | ev] is dead from here on
+  // ---------------- change of input variables
+  const int g = lane >> 2, q = lane & 3;
+  // original force column of reduced force index cf (closed contacts only)
+  auto force_col = [&](int cf) { return st0 ? cf : 6 + cf; };
+  // joint block of B_d rows 3..11 (columns zero padded to 16; fragment rows beyond 8 re-read row 8, results discarded) in the storage of [Cv | ev]
+  static_assert(9 * LDJ <= 10 * (NXA + 1), "Bj must fit into the [Cv | ev] buffer");
+  double (*Bj)[LDJ] = reinterpret_cast<double (*)[LDJ]>(&G[0][0]);
+  for (int i = lane; i < 9 * LDJ; i += 32) { const int rr_ = i / LDJ, cc_ = i % LDJ; Bj[rr_][cc_] = (cc_ < NJ) ? Bd[rr_ * NU + 12 + cc_] : 0.0; }
+  // contribution of the fixed open-contact forces (du_F = -F) to rows 3..11 of bt, one row per lane 0..8
+  if (lane < 16) {
+    double open_corr = 0.0;
+    if (lane < 9) {
+      for (int cn = 0; cn < NCON; ++cn) if (!(cn / 2 == 0 ? st0 : st1))
+        for (int qq = 0; qq < 3; ++qq) open_corr -= Bd[lane * NU + 3 * cn + qq] * rec[D::R_FO + 3 * cn + qq];
+    }
+    sMisc[warp][16 + lane] = open_corr;
+  }
+  // ---- element-wise parts (lane = column of W, values in y[]; done first so that y[] is dead during the tile products)
+  if (is_x) {
+#pragma unroll
+    for (int l = 0; l < NJ; ++l) so[S::S_AB + (12 + l) * LDA + lane] = dt * y[l] + ((12 + l == lane) ? 1.0 : 0.0);   // At rows 12..: I + dt Pxj
+  } else if (is_aff) {
+#pragma unroll
+    for (int l = 0; l < NJ; ++l) so[S::S_B + 12 + l] = rec[D::R_B + 12 + l] + dt * y[l];                              // bt rows 12..
+    const double f = dt / M.total_mass;
+    for (int qq = 0; qq < 3; ++qq) {   // rows 0..2 of bt: B_d rows 0..2 = dt/m on the force columns
+      double bb = rec[D::R_B + qq];
+      for (int cn = 0; cn < NCON; ++cn) if (!(cn / 2 == 0 ? st0 : st1)) bb -= f * rec[D::R_FO + 3 * cn + qq];
+      so[S::S_B + qq] = bb;
+    }
+  } else if (lane >= 24) {
+#pragma unroll
+    for (int l = 0; l < NJ; ++l) so[S::S_AB + (12 + l) * LDA + lane] = dt * y[l];   // Bt rows 12.., reduced columns 0..7: dt N (zero beyond mj)
+  }
+  // Bt rows 0..2 (dt/m on the closed-contact force columns) and rows 3..11 of the reduced columns 8..15 (force columns or zero)
+  for (int i = lane; i < 3 * MP + 9 * 8; i += 32) {
+    int r_, c; double v = 0.0;
+    if (i < 3 * MP) { r_ = i / MP; c = i % MP; const int cf = c - mj; if (cf >= 0 && cf < 3 * nclosed && cf % 3 == r_) v = dt / M.total_mass; }
+    else { const int e = i - 3 * MP; r_ = 3 + e / 8; c = 8 + e % 8; const int cf = c - mj; if (cf >= 0 && cf < 3 * nclosed) v = Bd[(r_ - 3) * NU + force_col(cf)]; }
+    so[S::S_AB + r_ * LDA + 24 + c] = v;
+  }
+  // rt: closed-contact force entries, zero padding (the null-space entries come from the tile products)
+  if (lane < MP) { const int cf = lane - mj; if (cf >= 0) so[S::S_R + lane] = (cf < 3 * nclosed) ? rec[D::R_R + force_col(cf)] : 0.0; }
   __syncwarp();
-  // ---------------- change of input variables on the tensor cores
-  if constexpr (TC) {
-    const int g = lane >> 2, q = lane & 3;
-    const double* Bd = sBd[warp];
-    // joint block of B_d rows 3..11 (columns zero padded to 16; fragment rows beyond 8 re-read row 8, results discarded).  It reuses the
-    // storage of [Cv | ev], which is dead after the triangular solves.
-    static_assert(9 * LDJ <= 10 * (NXA + 1), "Bj must fit into the [Cv | ev] buffer");
-    double (*Bj)[LDJ] = reinterpret_cast<double (*)[LDJ]>(&G[0][0]);
-    for (int i = lane; i < 9 * LDJ; i += 32) { const int rr_ = i / LDJ, cc_ = i % LDJ; Bj[rr_][cc_] = (cc_ < NJ) ? Bd[rr_ * NU + 12 + cc_] : 0.0; }
-    // contribution of the fixed open-contact forces (du_F = -F) to rows 3..11 of bt, one row per lane 0..8
-    if (lane < 16) {
-      double open_corr = 0.0;
-      if (lane < 9) {
-        for (int cn = 0; cn < NCON; ++cn) if (!(cn / 2 == 0 ? st0 : st1))
-          for (int qq = 0; qq < 3; ++qq) open_corr -= Bd[lane * NU + 3 * cn + qq] * rec[D::R_FO + 3 * cn + qq];
-      }
-      sMisc[warp][16 + lane] = open_corr;
-    }
-    __syncwarp();
-    // ---- element-wise parts (lane = column of W, values in y[]; done first so that y[] is dead during the tile products)
-    if (is_rhs) {
-      const int c = lane, xs_ = c < 6 ? c : c + 3;
+  // accumulator initialisers of AJ (issued early): A_d - I rows 3..11 / b rows 3..11 + open-contact correction
+  double ad[2][4][2];
 #pragma unroll
-      for (int l = 0; l < NJ; ++l) {   // At rows 12..: I + dt Pxj ; bt rows 12..
-        if (c < NXA) so[S::S_AB + (12 + l) * S::LDA + xs_] = dt * y[l] + ((12 + l == xs_) ? 1.0 : 0.0);
-        else so[S::S_B + 12 + l] = rec[D::R_B + 12 + l] + dt * y[l];
-      }
-      if (c == NXA) {   // rows 0..2 of bt: B_d rows 0..2 = dt/m on the force columns
-        const double f = dt / M.total_mass;
-        for (int qq = 0; qq < 3; ++qq) {
-          double bb = rec[D::R_B + qq];
-          for (int cn = 0; cn < NCON; ++cn) if (!(cn / 2 == 0 ? st0 : st1)) bb -= f * rec[D::R_FO + 3 * cn + qq];
-          so[S::S_B + qq] = bb;
-        }
-        for (int qq = 6; qq < 9; ++qq) { so[S::S_Q + qq] = rec[D::R_Q + qq]; so[S::qf(qq, qq)] = dt * sQd[qq] + dq; }
-      } else {
-        for (int r_ = 0; r_ < MP; ++r_) if (!(r_ >= 3 * nclosed && r_ < m)) so[S::prf(r_, xs_)] = 0.0;   // Pt rows that are not null-space rows
-      }
-    } else if (is_null) {
-      const int t = lane - CN;
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int l = 0; l < NJ; ++l) so[S::S_AB + (12 + l) * S::LDA + 24 + 3 * nclosed + t] = dt * y[l];   // Bt rows 12..: dt N
-    }
-    // accumulator initialisers of AJ (issued early): A_d - I rows 3..11 / b rows 3..11 + open-contact correction
-    double ad[2][4][2];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          const int rr = 8 * mt + g, C = 8 * nt + 2 * q + sl;
-          double v = 0.0;
-          if (rr < 9) { if (C < NXA) v = rec[D::R_AD + rr * NXA + C]; else if (C == CA) v = rec[D::R_B + 3 + rr] + sMisc[warp][16 + rr]; }
-          ad[mt][nt][sl] = v;
-        }
-    // ---- step 1: Z^T = W^T Rj (32 x 16), then Z = dt Z + dr W (+ r_j on the affine column): Z[mt][nt] holds (Rj_eff W)[8 nt + 2q + s][8 mt + g]
-    double a[2][2][4], Z[4][2][2];
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) { Z[mt][nt][0] = 0.0; Z[mt][nt][1] = 0.0; }
-#pragma unroll
-    for (int kb = 0; kb < 2; ++kb)
+    for (int nt = 0; nt < 3; ++nt)
 #pragma unroll
       for (int sl = 0; sl < 2; ++sl) {
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt) a[kb][sl][mt] = W[8 * kb + 2 * q + sl][8 * mt + g];
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          const double bR = sRjP[8 * kb + 2 * q + sl][8 * nt + g];
-#pragma unroll
-          for (int mt = 0; mt < 4; ++mt) dmma884(Z[mt][nt][0], Z[mt][nt][1], a[kb][sl][mt], bR);
+        const int rr = 8 * mt + g, C = 8 * nt + 2 * q + sl;
+        double v = 0.0;
+        if (rr < 9) {
+          if (C < 6 || (C >= 9 && C < NX)) v = rec[D::R_AD + rr * NXA + (C < 6 ? C : C - 3)];
+          else if (C == 6) v = rec[D::R_B + 3 + rr] + sMisc[warp][16 + rr];
         }
+        ad[mt][nt][sl] = v;
       }
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
+  for (int mt = 0; mt < 2; ++mt) { ad[mt][3][0] = 0.0; ad[mt][3][1] = 0.0; }
+  // ---- step 1: Z^T = W^T Rj (32 x 16), then Z = dt Z + dr W (+ r_j on the affine column): Z[mt][nt] holds (Rj_eff W)[8 nt + 2q + s][8 mt + g]
+  double a[2][2][4], Z[4][2][2];
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
+  for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          double v = dt * Z[mt][nt][sl] + dr * a[nt][sl][mt];
-          if (8 * mt + g == CA) v += sMisc[warp][8 * nt + 2 * q + sl];
-          Z[mt][nt][sl] = v;
-        }
-    // ---- step 2: M = W^T (Rj_eff W), tile by tile; each tile is scattered to its destinations straight from the accumulator fragment
+    for (int nt = 0; nt < 2; ++nt) { Z[mt][nt][0] = 0.0; Z[mt][nt][1] = 0.0; }
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
+  for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        if (!(mt >= nt || (nt == CA / 8 && mt < nt))) continue;   // lower triangle + the tiles above the diagonal that hold the affine column
-        double c0 = 0.0, c1 = 0.0;
+    for (int sl = 0; sl < 2; ++sl) {
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb)
+      for (int mt = 0; mt < 4; ++mt) a[kb][sl][mt] = W[8 * kb + 2 * q + sl][8 * mt + g];
 #pragma unroll
-          for (int sl = 0; sl < 2; ++sl) dmma884(c0, c1, a[kb][sl][mt], Z[nt][kb][sl]);
+      for (int nt = 0; nt < 2; ++nt) {
+        const double bR = sRjP[8 * kb + 2 * q + sl][8 * nt + g];
 #pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          const int R = 8 * mt + g, C = 8 * nt + 2 * q + sl;
-          const double v = sl ? c1 : c0;
-          const int sR = R < 6 ? R : R + 3, sC = C < 6 ? C : C + 3;
-          if (R < NXA) {
-            if (C < NXA) {
-              if (mt >= nt) {
-                const double vv = v + ((R == C) ? dt * sQd[sR < 24 ? sR : 0] + dq : 0.0);
-                so[S::qf(sR, sC)] = vv;
-                if (mt > nt) so[S::qf(sC, sR)] = vv;
-              }
-            } else if (C == CA) so[S::S_Q + sR] = rec[D::R_Q + sR] + v;
-          } else if (R >= CN && R - CN < mj) {
-            const int row = 3 * nclosed + R - CN;
-            if (C < NXA) so[S::prf(row, sC)] = v;
-            else if (C == CA) so[S::S_R + row] = v;
-            else if (C - CN < mj) {
-              const int col = 3 * nclosed + C - CN;
-              so[S::prf(row, 24 + col)] = v;
-              if (mt > nt) so[S::prf(col, 24 + row)] = v;
-            }
-          }
-        }
+        for (int mt = 0; mt < 4; ++mt) dmma884(Z[mt][nt][0], Z[mt][nt][1], a[kb][sl][mt], bR);
       }
-    // ---- step 3: AJ = B_d[:, joints] W (16 x 32): joint part of At rows 3..11, bt rows 3..11, null-space columns of Bt rows 3..11
+    }
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      double bj[2][2];
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        double v = dt * Z[mt][nt][sl] + dr * a[nt][sl][mt];
+        if (mt == 0 && g == 6) v += sMisc[warp][8 * nt + 2 * q + sl];   // affine column 6: t1 = r_j + Rj_eff Pe
+        Z[mt][nt][sl] = v;
+      }
+  // ---- step 2: M = W^T (Rj_eff W), tile by tile, stored straight from the accumulator fragments
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      if (mt < 3 && nt == 3) continue;   // N-columns of the state rows: the transpose of Pt, not needed
+      double c0 = 0.0, c1 = 0.0;
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-        for (int sl = 0; sl < 2; ++sl) bj[kb][sl] = Bj[(8 * mt + g) < 9 ? 8 * mt + g : 8][8 * kb + 2 * q + sl];
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        double c0 = ad[mt][nt][0], c1 = ad[mt][nt][1];
-#pragma unroll
-        for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-          for (int sl = 0; sl < 2; ++sl) dmma884(c0, c1, bj[kb][sl], a[kb][sl][nt]);
+        for (int sl = 0; sl < 2; ++sl) dmma884(c0, c1, a[kb][sl][mt], Z[nt][kb][sl]);
+      const int R = 8 * mt + g, C0 = 8 * nt + 2 * q;
+      if (mt < 3 && nt < 3) {          // Qt tile (R, C0 .. C0+1): row / column 6 carry the affine terms, the diagonal gets dt Q + dq
+        if (nt == 0 && q == 3 && R < NX && R != 6) so[S::S_Q + R] = rec[D::R_Q + R] + ((R == 7 || R == 8) ? 0.0 : c0);   // qt = q + Px^T t1
+        double v0 = (R == 6 || C0 == 6) ? 0.0 : c0, v1 = (R == 6) ? 0.0 : c1;
+        if (R == C0 && R < NX) v0 += dt * sQd[R] + dq;
+        if (R == C0 + 1 && R < NX) v1 += dt * sQd[R] + dq;
+        *reinterpret_cast<double2*>(so + S::S_QF + (mt * 3 + nt) * 64 + 2 * lane) = make_double2(v0, v1);
+      } else if (nt < 3) {             // mt == 3: Pt rows t = g (zero beyond mj); column 6 is the rt correction of the null-space inputs
+        if (nt == 0 && q == 3 && g < mj) so[S::S_R + g] = c0;
+        *reinterpret_cast<double2*>(so + S::S_PRF + (0 * 5 + nt) * 64 + 2 * lane) = make_double2((C0 == 6) ? 0.0 : c0, c1);
+      } else {                         // mt == nt == 3: null block of Rt = rows / columns 0..7 of Rt; the force / identity part F is added
+        double v[2] = {c0, c1};
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl) {
-          const int rr = 8 * mt + g, C = 8 * nt + 2 * q + sl;
-          const double v = sl ? c1 : c0;
-          if (rr < 9) {
-            const int sC = C < 6 ? C : C + 3;
-            if (C < NXA) so[S::S_AB + (3 + rr) * S::LDA + sC] = v + ((3 + rr == sC) ? 1.0 : 0.0);
-            else if (C == CA) so[S::S_B + 3 + rr] = v;
-            else if (C - CN < mj) so[S::S_AB + (3 + rr) * S::LDA + 24 + 3 * nclosed + C - CN] = v;
+          const int r_ = g, c = 2 * q + sl;
+          if (r_ >= mj || c >= mj) {
+            double f = 0.0;
+            if (r_ >= m || c >= m) f = (r_ == c) ? 1.0 : 0.0;
+            else if (r_ >= mj && c >= mj && (r_ - mj) / 3 == (c - mj) / 3) {
+              const int cn = (st0 ? 0 : 2) + (r_ - mj) / 3, p_ = (r_ - mj) % 3, q_ = (c - mj) % 3;
+              const int lo = p_ < q_ ? p_ : q_, hi = p_ < q_ ? q_ : p_;
+              f = rec[D::R_HB + 6 * cn + (lo == 0 ? hi : (lo == 1 ? 2 + hi : 5))];
+              if (p_ == q_) f += dt * M.Rforce[3 * cn + p_] + dr;
+            }
+            v[sl] = f;
           }
+        }
+        *reinterpret_cast<double2*>(so + S::S_PRF + (0 * 5 + 3) * 64 + 2 * lane) = make_double2(v[0], v[1]);
+      }
+    }
+  // the other three tiles of Rt (rows or columns 8..15): force blocks / identity only
+#pragma unroll
+  for (int tt = 1; tt < 4; ++tt) {
+    const int ta = tt >> 1, tb = tt & 1;
+    double v[2];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      const int r_ = 8 * ta + g, c = 8 * tb + 2 * q + sl;
+      double f = 0.0;
+      if (r_ >= m || c >= m) f = (r_ == c) ? 1.0 : 0.0;
+      else if (r_ >= mj && c >= mj && (r_ - mj) / 3 == (c - mj) / 3) {
+        const int cn = (st0 ? 0 : 2) + (r_ - mj) / 3, p_ = (r_ - mj) % 3, q_ = (c - mj) % 3;
+        const int lo = p_ < q_ ? p_ : q_, hi = p_ < q_ ? q_ : p_;
+        f = rec[D::R_HB + 6 * cn + (lo == 0 ? hi : (lo == 1 ? 2 + hi : 5))];
+        if (p_ == q_) f += dt * M.Rforce[3 * cn + p_] + dr;
+      }
+      v[sl] = f;
+    }
+    *reinterpret_cast<double2*>(so + S::S_PRF + (ta * 5 + 3 + tb) * 64 + 2 * lane) = make_double2(v[0], v[1]);
+  }
+  // ---- step 3: AJ = B_d[:, joints] W (16 x 32): joint part of At rows 3..11, bt rows 3..11, null-space columns of Bt rows 3..11
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    double bj[2][2];
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) bj[kb][sl] = Bj[(8 * mt + g) < 9 ? 8 * mt + g : 8][8 * kb + 2 * q + sl];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      double c0 = ad[mt][nt][0], c1 = ad[mt][nt][1];
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) dmma884(c0, c1, bj[kb][sl], a[kb][sl][nt]);
+      const int rr = 8 * mt + g, C0 = 8 * nt + 2 * q;
+      if (rr < 9) {
+        const int sr_ = 3 + rr;
+        if (nt < 3) {     // At row 3 + rr, state columns C0, C0 + 1 (columns 6..8: identity entries; column 6 of the product is bt)
+          if (C0 == 6) so[S::S_B + sr_] = c0;
+          const double v0 = ((C0 >= 6 && C0 <= 8) ? 0.0 : c0) + ((sr_ == C0) ? 1.0 : 0.0);
+          const double v1 = ((C0 + 1 >= 6 && C0 + 1 <= 8) ? 0.0 : c1) + ((sr_ == C0 + 1) ? 1.0 : 0.0);
+          *reinterpret_cast<double2*>(so + S::S_AB + sr_ * LDA + C0) = make_double2(v0, v1);
+        } else {          // Bt row 3 + rr, reduced columns 2q, 2q + 1: null-space columns, then closed-contact force columns, then zero
+          double v[2] = {c0, c1};
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) { const int cf = 2 * q + sl - mj; if (cf >= 0) v[sl] = (cf < 3 * nclosed) ? Bd[rr * NU + force_col(cf)] : 0.0; }
+          *reinterpret_cast<double2*>(so + S::S_AB + sr_ * LDA + 24 + 2 * q) = make_double2(v[0], v[1]);
         }
       }
     }
-    // Bt entries outside the null-space block: rows 0..2, closed-contact force columns, zero columns beyond m
-    for (int i = lane; i < NX * MP; i += 32) {
-      const int r_ = i / MP, c = i % MP, rr = r_ - 3;
-      if (r_ >= 3 && c >= 3 * nclosed && c < m) continue;
-      double v = 0.0;
-      if (r_ < 3) { if (c < 3 * nclosed && c % 3 == r_) v = dt / M.total_mass; }
-      else if (c < 3 * nclosed && rr < 9) v = Bd[rr * NU + (st0 ? c : 6 + c)];
-      so[S::S_AB + r_ * S::LDA + 24 + c] = v;
-    }
-    // Rt outside the null block: force blocks (barrier Hessians + diagonal), identity beyond m, zero cross blocks
-    for (int i = lane; i < MP * MP; i += 32) {
-      const int r_ = i / MP, c = i % MP;
-      if (r_ >= 3 * nclosed && c >= 3 * nclosed && r_ < m && c < m) continue;
-      double v = 0.0;
-      if (r_ >= m || c >= m) v = (r_ == c) ? 1.0 : 0.0;
-      else if (r_ < 3 * nclosed && c < 3 * nclosed && r_ / 3 == c / 3) {
-        const int cn = (st0 ? 0 : 2) + r_ / 3, p_ = r_ % 3, q_ = c % 3;
-        const int lo = p_ < q_ ? p_ : q_, hi = p_ < q_ ? q_ : p_;
-        v = rec[D::R_HB + 6 * cn + (lo == 0 ? hi : (lo == 1 ? 2 + hi : 5))];
-        if (p_ == q_) v += dt * M.Rforce[3 * cn + p_] + dr;
-      }
-      so[S::prf(r_, 24 + c)] = v;
-    }
-    if (lane < 3 * nclosed) { const int fc = st0 ? lane : 6 + lane; so[S::S_R + lane] = rec[D::R_R + fc]; }
-    if (lane >= m && lane < MP) so[S::S_R + lane] = 0.0;
-    return;
   }
-  // ---------------- change of input variables.  y[] = own column of [Pxj | Pej] (lanes <= NXA) or of N (null lanes)
-  const double* Bd = sBd[warp];
-  // t[] = Rj_eff * (own column)  (+ r_j for the Pe column -> t1 = r_j + Rj_eff Pej)
-  double tcol[NJ];
-  if (is_rhs || is_null) {
-#pragma unroll
-    for (int l = 0; l < NJ; ++l) {
-      double a = dr * y[l];
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) a += dt * M.Rjoint[l * NJ + j] * y[j];
-      if (lane == NXA) a += rec[D::R_R + 12 + l];
-      tcol[l] = a;
-    }
-    if (is_null) { const int t = lane - NXA - 1; for (int l = 0; l < NJ; ++l) RN[l][t] = tcol[l]; }
-  }
-  __syncwarp();
-  // contribution of the fixed open-contact forces (du_F = -F) to rows 3..11 of bt, one row per lane 0..8
-  double open_corr = 0.0;
-  if (lane < 9) {
-    for (int cn = 0; cn < NCON; ++cn) if (!(cn / 2 == 0 ? st0 : st1))
-      for (int q = 0; q < 3; ++q) open_corr -= Bd[lane * NU + 3 * cn + q] * rec[D::R_FO + 3 * cn + q];
-  }
-  if (is_rhs) {
-    const int c = lane;   // X column (or the affine column NXA)
-    // At rows 3..11: I + AdI + Bd_j Pxj ; rows 12..: I + dt Pxj.   Affine column: contributes to bt
-    const int xs_ = c < 6 ? c : c + 3;   // state column of active column c
-#pragma unroll
-    for (int rr = 0; rr < 9; ++rr) {
-      double a = 0.0;
-#pragma unroll
-      for (int l = 0; l < NJ; ++l) a += Bd[rr * NU + 12 + l] * y[l];
-      const double base_v = (c < NXA) ? rec[D::R_AD + rr * NXA + c] : rec[D::R_B + 3 + rr] + __shfl_sync(__activemask(), open_corr, rr);
-      if (c < NXA) so[S::S_AB + (3 + rr) * S::LDA + xs_] = base_v + a + ((3 + rr == xs_) ? 1.0 : 0.0); else so[S::S_B + 3 + rr] = base_v + a;
-    }
-#pragma unroll
-    for (int l = 0; l < NJ; ++l) {
-      if (c < NXA) so[S::S_AB + (12 + l) * S::LDA + xs_] = dt * y[l] + ((12 + l == xs_) ? 1.0 : 0.0);
-      else so[S::S_B + 12 + l] = rec[D::R_B + 12 + l] + dt * y[l];
-    }
-    if (c == NXA) {   // rows 0..2 of bt: B_d rows 0..2 = dt/m on the force columns
-      const double f = dt / M.total_mass;
-      for (int q = 0; q < 3; ++q) {
-        double bb = rec[D::R_B + q];
-        for (int cn = 0; cn < NCON; ++cn) if (!(cn / 2 == 0 ? st0 : st1)) bb -= f * rec[D::R_FO + 3 * cn + q];
-        so[S::S_B + q] = bb;
-      }
-    }
-    // Qt[:, c] = Pxj^T tcol (+ the diagonal dt Q + dq) in fragment order (c < NXA) ; qt = q + Pxj^T t1 (affine column)
-    for (int xr = 0; xr < NXA; ++xr) {
-      double a = 0.0;
-#pragma unroll
-      for (int l = 0; l < NJ; ++l) a += Px[l][xr] * tcol[l];
-      const int sidx = xr < 6 ? xr : xr + 3;
-      if (c < NXA) so[S::qf(sidx, xs_)] = a + ((xr == c) ? dt * M.Qdiag[sidx] + dq : 0.0);
-      else so[S::S_Q + sidx] = rec[D::R_Q + sidx] + a;
-    }
-    if (c == NXA) for (int q = 6; q < 9; ++q) { so[S::S_Q + q] = rec[D::R_Q + q]; so[S::qf(q, q)] = dt * M.Qdiag[q] + dq; }
-    // Pt: rows 3 nclosed .. m-1 hold N^T tcol, every other row is zero (no state-input cross term on the force rows) ; affine column -> rt null entries
-    for (int r = 0; r < MP; ++r) {
-      const int t = r - 3 * nclosed;
-      double a = 0.0;
-      if (t >= 0 && t < mj) {
-#pragma unroll
-        for (int l = 0; l < NJ; ++l) a += Nn[l][t] * tcol[l];
-      }
-      if (c < NXA) so[S::prf(r, xs_)] = a;
-      else if (t >= 0 && t < mj) so[S::S_R + r] = a;
-    }
-  }
-  // Bt: rows 0..2 = dt/m on the closed-contact force columns; closed-contact force columns of B_d are copied, null-space columns = B_d[:, joints] N
-  for (int i = lane; i < NX * MP; i += 32) {
-    const int r = i / MP, c = i % MP, rr = r - 3;   // rr = state row - 3
-    double a = 0.0;
-    if (r < 3) { if (c < 3 * nclosed && c % 3 == r) a = dt / M.total_mass; }
-    else if (c < 3 * nclosed) {
-      int fc;   // original force column of reduced column c
-      if (st0) fc = c; else fc = 6 + c;
-      if (rr < 9) a = Bd[rr * NU + fc];
-    } else if (c < m) {
-      const int t = c - 3 * nclosed;
-      if (rr < 9) { for (int l = 0; l < NJ; ++l) a += Bd[rr * NU + 12 + l] * Nn[l][t]; }
-      else a = dt * Nn[rr - 9][t];
-    }
-    so[S::S_AB + r * S::LDA + 24 + c] = a;
-  }
-  // Rt (16 x 16): force blocks (barrier Hessians + diagonal), null block N^T Rj_eff N, identity beyond m
-  double rnn[2];
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int i = lane + 32 * q, t1 = i / 8, t2 = i % 8;
-    double a = 0.0;
-    if (t1 < mj && t2 < mj) for (int l = 0; l < NJ; ++l) a += Nn[l][t1] * RN[l][t2];
-    rnn[q] = a;
-  }
-  __syncwarp();
-  double* rns = &RN[0][0];   // reuse: the 8 x 8 null block (NJ >= 8 rows of 8)
-  rns[lane] = rnn[0]; rns[lane + 32] = rnn[1];
-  __syncwarp();
-  for (int i = lane; i < MP * MP; i += 32) {
-    const int r = i / MP, c = i % MP;
-    double a = 0.0;
-    if (r >= m || c >= m) a = (r == c) ? 1.0 : 0.0;
-    else if (r < 3 * nclosed && c < 3 * nclosed) {
-      if (r / 3 == c / 3) {
-        const int cn = (st0 ? 0 : 2) + r / 3, p = r % 3, q = c % 3;
-        const int lo = p < q ? p : q, hi = p < q ? q : p;
-        a = rec[D::R_HB + 6 * cn + (lo == 0 ? hi : (lo == 1 ? 2 + hi : 5))];
-        if (p == q) a += dt * M.Rforce[3 * cn + p] + dr;
-      }
-    } else if (r >= 3 * nclosed && c >= 3 * nclosed) a = rns[(r - 3 * nclosed) * 8 + (c - 3 * nclosed)];
-    so[S::prf(r, 24 + c)] = a;
-  }
-  if (lane < 3 * nclosed) { const int fc = st0 ? lane : 6 + lane; so[S::S_R + lane] = rec[D::R_R + fc]; }
-  if (lane >= m && lane < MP) so[S::S_R + lane] = 0.0;
+  // qt of the base-position rows and the rows the tiles do not reach
+  if (lane >= 6 && lane < 9) so[S::S_Q + lane] = rec[D::R_Q + lane];
 }
 
 // ------------------------------------------------------------------------------------------------ TMA bulk copy + mbarrier helpers (sm_90+/sm_100a PTX)
@@ -1838,13 +1731,13 @@ __global__ void __launch_bounds__(128, 4) k_policy_expand(Dev d) {
     for (int r = 0; r < 12; ++r) {
       const int cn = r / 3; const bool cl = (cn / 2 == 0) ? st0 : st1;
       double a = 0.0;
-      if (cl) a = sm.Kt[((st0 ? cn : cn - 2) * 3 + r % 3) * LDK + lane];
+      if (cl) a = sm.Kt[(mj + (st0 ? cn : cn - 2) * 3 + r % 3) * LDK + lane];   // reduced inputs: [null space (mj) | closed-contact forces]
       else if (lane == NX) a = -prj[D::P_FO + r];
       if (lane < NX) { Kg[r * NX + lane] = a; sm.P[r * 25 + lane] = a * xk_l; } else ric[R::K_KAP + r] = a;
     }
     double zn[8];   // null-space part of the own column
 #pragma unroll
-    for (int t = 0; t < 8; ++t) zn[t] = (t < mj) ? sm.Kt[(3 * nclosed + t) * LDK + lane] : 0.0;
+    for (int t = 0; t < 8; ++t) zn[t] = (t < mj) ? sm.Kt[t * LDK + lane] : 0.0;
     const bool xact = lane < 6 || (lane >= 9 && lane < NX);
     const int xc = xcol(lane);
     double pxv[NJ];
