@@ -695,8 +695,8 @@ __device__ __forceinline__ void warp_model_base(const double* __restrict__ x, co
 // relaxed log barrier [UPSTREAM RelaxedBarrierPenalty], settings task.info:280-287
 __device__ __forceinline__ void barrier_penalty(double h, double& p, double& dp, double& ddp) {
   const double mu = c_model.bar_mu, de = c_model.bar_delta;
-  if (h > de) { p = -mu * log(h); dp = -mu / h; ddp = mu / (h * h); }
-  else { const double dh = (h - 2.0 * de) / de; p = mu * (-log(de) + 0.5 * dh * dh - 0.5); dp = mu * (h - 2.0 * de) / (de * de); ddp = mu / (de * de); }
+  if (h > de) { const double ih = __drcp_rn(h); p = -mu * log(h); dp = -mu * ih; ddp = mu * ih * ih; }
+  else { const double ide = __drcp_rn(de), dh = (h - 2.0 * de) * ide; p = mu * (-log(de) + 0.5 * dh * dh - 0.5); dp = mu * dh * ide; ddp = mu * ide * ide; }
 }
 // friction cone value (constraint/FrictionConeConstraint.cpp:160-166)
 __device__ __forceinline__ double friction_cone(double fx, double fy, double fz) {

@@ -509,7 +509,7 @@ __device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k,
   // ---- cost gradient / barrier blocks (one contact per lane 0..3, one joint per lane for the joint part)
   const bool st0 = leg_in_stance(mode, 0), st1 = leg_in_stance(mode, 1);
   const int nst = 2 * (int(st0) + int(st1));
-  const double fznom = nst > 0 ? M.total_mass * 9.81 / nst : 0.0;
+  const double fznom = nst > 0 ? M.total_mass * 9.81 * (nst == 2 ? 0.5 : 0.25) : 0.0;
   double cpart = 0.0;   // this lane's share of the stage cost value (tracking cost + barrier), summed over the warp below
   if (lane < NX) { const double dq_ = xs[lane] - xrs[lane]; rec[D::R_Q + lane] = dt * M.Qdiag[lane] * dq_; cpart = 0.5 * M.Qdiag[lane] * dq_ * dq_; }
   double shift = 0.0;
@@ -521,11 +521,11 @@ __device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k,
     double hb[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (st) {
       const double fx = us[3 * c], fy = us[3 * c + 1], fz = us[3 * c + 2];
-      const double ts = fx * fx + fy * fy + M.fr_reg, tn = sqrt(ts), t32 = tn * ts;
+      const double ts = fx * fx + fy * fy + M.fr_reg, itn = rsqrt(ts), tn = ts * itn, it32 = itn * itn * itn;
       const double h = M.mu_f * (fz + M.fr_grip) - tn;
       double p, dp, ddp; barrier_penalty(h, p, dp, ddp);
-      const double g0 = -fx / tn, g1 = -fy / tn, g2 = M.mu_f;
-      const double H00 = -(fy * fy + M.fr_reg) / t32, H01 = fx * fy / t32, H11 = -(fx * fx + M.fr_reg) / t32;
+      const double g0 = -fx * itn, g1 = -fy * itn, g2 = M.mu_f;
+      const double H00 = -(fy * fy + M.fr_reg) * it32, H01 = fx * fy * it32, H11 = -(fx * fx + M.fr_reg) * it32;
       r3[0] += dp * g0; r3[1] += dp * g1; r3[2] += dp * g2;
       hb[0] = ddp * g0 * g0 + dp * H00; hb[1] = ddp * g0 * g1 + dp * H01; hb[2] = ddp * g0 * g2;
       hb[3] = ddp * g1 * g1 + dp * H11; hb[4] = ddp * g1 * g2; hb[5] = ddp * g2 * g2;
@@ -584,10 +584,10 @@ __device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k,
     if (st) {
       peq += dot(va, va) + dot(vb, vb);
       v3 r = ld3(b1 + BD::B_PC + 3 * ca) - ld3(b1 + BD::B_PC + 3 * cb);
-      r = (1.0 / sqrt(dot(r, r))) * r;
+      r = rsqrt(dot(r, r)) * r;
       const double ax = fabs(r.x), ay = fabs(r.y), az = fabs(r.z);
       const v3 e = (ax <= ay && ax <= az) ? mk(1.0, 0.0, 0.0) : ((ay <= az) ? mk(0.0, 1.0, 0.0) : mk(0.0, 0.0, 1.0));
-      v3 n1 = cross(r, e); n1 = (1.0 / sqrt(dot(n1, n1))) * n1;
+      v3 n1 = cross(r, e); n1 = rsqrt(dot(n1, n1)) * n1;
       const v3 n2 = cross(r, n1);
       const v3 sx_ = is2 * (jx[ca] + jx[cb]), dx_ = is2 * (jx[ca] - jx[cb]), su_ = is2 * (ju[ca] + ju[cb]), du_ = is2 * (ju[ca] - ju[cb]);
       if (lane < NXA) {
@@ -828,7 +828,7 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
   constexpr int LDW = 34, LDR = 18, LDJ = 20;   // leading dimensions = 2 mod 4: k-permuted fragment loads are conflict free
   __shared__ double sM[WPB][NJ][12];     // Dv^T  (NJ x r), r <= 10
   __shared__ double sV[WPB][10][NJ];     // Householder vectors (zero padded)
-  __shared__ double sBeta[WPB][10];
+  __shared__ double sBeta[WPB][20];      // beta (10) | 1 / R[k][k] (10)
   __shared__ double sG[WPB][10][NXA + 1];   // [Cv | ev]; after the triangular solves: the padded joint block of B_d
   __shared__ double sBd[WPB][9 * (12 + NJ)];  // B_d rows 3..11
   __shared__ double sW[WPB][16][LDW];        // W, rows >= NJ zero
@@ -855,7 +855,7 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
   }
   const DevModel& M = c_model;
   const int r = (int)rec[D::R_MISC + D::M_NROWS];
-  double (*Mt)[12] = sM[warp]; double (*V)[NJ] = sV[warp]; double* beta = sBeta[warp]; double (*G)[NXA + 1] = sG[warp];
+  double (*Mt)[12] = sM[warp]; double (*V)[NJ] = sV[warp]; double* beta = sBeta[warp]; double* rinv = sBeta[warp] + 10; double (*G)[NXA + 1] = sG[warp];
   double (*W)[LDW] = sW[warp];
   const double* Bd = sBd[warp];
   {   // stage Dv^T, [Cv | ev] and B_d rows 3..11: all global loads are issued before the first shared-memory store (fixed trip counts;
@@ -900,7 +900,7 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
       const double alpha = x0 >= 0.0 ? -nrm : nrm;
       const double v0 = x0 - alpha;
       const double vtv = nrm2 - x0 * x0 + v0 * v0;
-      const double bta = vtv > 0.0 ? 2.0 / vtv : 0.0;
+      const double bta = vtv > 0.0 ? 2.0 * __drcp_rn(vtv) : 0.0;
       rmax = fmax(rmax, nrm);
       if (!(nrm > 1e-9 * rmax)) anomaly = true;
       vk[kk] = v0;
@@ -915,7 +915,7 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
       if (lane == kk) {
 #pragma unroll
         for (int i = 0; i < NJ; ++i) { colv[i] = (i == kk) ? alpha : ((i > kk) ? 0.0 : colv[i]); V[kk][i] = vk[i]; }
-        beta[kk] = bta;
+        beta[kk] = bta; rinv[kk] = __drcp_rn(alpha);   // 1 / R[kk][kk] for the triangular solves (inf on a rank anomaly, which is flagged)
       }
     }
   }
@@ -936,7 +936,7 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
       double s_ = G[i][gc];
 #pragma unroll
       for (int l = 0; l < NJ; ++l) if (l < i) s_ -= Mt[l][i] * y[l];
-      y[i] = s_ / Mt[i][i];
+      y[i] = s_ * rinv[i];
     }
   } else if (is_null) {
     const int t = lane - 24;
