@@ -112,10 +112,8 @@ void tick(bmpc_handle* h) {
   mark(1);
   CK(cudaFuncSetAttribute(k_riccati<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem<NJ>)));
   CK(cudaFuncSetAttribute(k_riccati<NJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(k_riccati_warp<NJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(RicWarpSmem<NJ>))));
-  CK(cudaFuncSetAttribute(k_riccati_warp<NJ, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(k_riccati_warp<NJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(RicWarpSmem<NJ>))));
-  CK(cudaFuncSetAttribute(k_riccati_warp<NJ, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_riccati_warp<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(RicWarpSmem<NJ>))));
+  CK(cudaFuncSetAttribute(k_riccati_warp<NJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_lq_pack<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LqPackSmem<NJ>)));
   CK(cudaFuncSetAttribute(k_policy_expand<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(PolSmem<NJ>))));
   CK(cudaFuncSetAttribute(k_forward<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(FwdSmem<NJ>))));
@@ -133,11 +131,10 @@ void tick(bmpc_handle* h) {
     if (iter == 0) mark(2);
     k_project<NJ><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches;
     if (iter == 0) mark(3);
-    if (h->riccati_mode == 2) { k_riccati_warp<NJ, true><<<(B + 3) / 4, 128, 4 * sizeof(RicWarpSmem<NJ>), st>>>(d); ++h->launches; }   // one warp per instance, gains fused into the sweep (measured slower: 7.1 ms vs 2.9 + 2.5 ms; kept as a cross-check)
-    else if (h->riccati_mode == 1) { k_riccati_warp<NJ, false><<<(B + 3) / 4, 128, 4 * sizeof(RicWarpSmem<NJ>), st>>>(d); ++h->launches; }   // one warp per instance (default)
+    if (h->riccati_mode == 1) { k_riccati_warp<NJ><<<(B + 3) / 4, 128, 4 * sizeof(RicWarpSmem<NJ>), st>>>(d); ++h->launches; }   // one warp per instance (default)
     else { k_riccati<NJ><<<B, WS_THREADS, sizeof(RicSmem<NJ>), st>>>(d); ++h->launches; }                                        // one CTA per instance
     if (iter == 0) mark(4);
-    if (h->riccati_mode != 2) { k_policy_expand<NJ><<<(nodes + 3) / 4, 128, 4 * sizeof(PolSmem<NJ>), st>>>(d); ++h->launches; }
+    k_policy_expand<NJ><<<(nodes + 3) / 4, 128, 4 * sizeof(PolSmem<NJ>), st>>>(d); ++h->launches;
     if (iter == 0) mark(5);
     k_forward<NJ><<<(B + 3) / 4, 128, 4 * sizeof(FwdSmem<NJ>), st>>>(d); ++h->launches;
     if (iter == 0) mark(6);
@@ -513,7 +510,7 @@ int bmpc_get_launch_count(const bmpc_handle* h) { return h ? h->launches : 0; }
 int bmpc_debug_set_option(bmpc_handle* h, const char* name, int value) {
   if (!h || !name) return BMPC_ERR_INVALID;
   if (std::string(name) == "ls_mode") { if (value < 0 || value > 1) return BMPC_ERR_INVALID; h->ls_mode = value; return BMPC_OK; }
-  if (std::string(name) == "riccati_mode") { if (value < 0 || value > 2) return BMPC_ERR_INVALID; h->riccati_mode = value; return BMPC_OK; }
+  if (std::string(name) == "riccati_mode") { if (value < 0 || value > 1) return BMPC_ERR_INVALID; h->riccati_mode = value; return BMPC_OK; }
   if (std::string(name) == "lq_mode") { if (value < 0 || value > 3) return BMPC_ERR_INVALID; h->lq_mode = value; return BMPC_OK; }
   return BMPC_ERR_INVALID;
 }

@@ -1250,21 +1250,6 @@ __device__ __forceinline__ bool chol_forward(double (&gc)[MP], double (&hc)[MP],
   return not_pd;
 }
 
-// Back substitution z <- -L^-T z with the factor left by chol_forward (lane j holds column j of L in gc[], reciprocal pivot on the diagonal):
-// every lane solves for its own column; L[l][i] is broadcast from lane i with a shuffle.  Rows >= M are zeroed.
-template <int M, int MP>
-__device__ __forceinline__ void chol_backsub(const double (&gc)[MP], double (&z)[MP], int lane) {
-#pragma unroll
-  for (int i = M - 1; i >= 0; --i) {
-    double a = z[i];
-#pragma unroll
-    for (int l = i + 1; l < M; ++l) a -= __shfl_sync(0xffffffffu, gc[l], i) * z[l];
-    z[i] = a * __shfl_sync(0xffffffffu, gc[i], i);
-  }
-#pragma unroll
-  for (int i = 0; i < MP; ++i) z[i] = (i < M) ? -z[i] : 0.0;
-}
-
 // ------------------------------------------------------------------------------------------------ K2: backward Riccati recursion
 // One CTA (4 warps) per instance; S, At, SA, Bt, SB, H, G live in shared memory, padded to NXP = 24 states / MP = 16 reduced inputs.
 //   SA = S At, SB = S Bt, sb = s + S bt;  H = Pt + Bt^T SA, G = Rt + Bt^T SB, g = rt + Bt^T sb
@@ -1448,12 +1433,10 @@ struct RicWarpSmem {
   alignas(16) unsigned long long bar;
 };
 
-// FUSE = true (default): the gains and closed-loop stage maps (K = Px + Pu Kt, kappa, uff0, Phi = At + Bt Kt, phi, ghat: what k_policy_expand
-// computes from the Y / L record) are produced right here while Y, L and AB are still on chip, so Y and L never travel through HBM.
-template <int NJ, bool FUSE>
+template <int NJ>
 __global__ void __launch_bounds__(128, 3) k_riccati_warp(Dev d) {
   using D = Dims<NJ>; using R = RDims<NJ>; using S = SDims<NJ>; using SM = RicWarpSmem<NJ>;
-  constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, MP = S::MP, LDA = S::LDA, LDH = SM::LDH;
+  constexpr int NX = D::NX, MP = S::MP, LDA = S::LDA, LDH = SM::LDH;
   constexpr unsigned TMA_BYTES = S::TMA_DOUBLES * sizeof(double);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1502,14 +1485,6 @@ __global__ void __launch_bounds__(128, 3) k_riccati_warp(Dev d) {
       if (lane < 24) sm.sb[lane] = sbv;
       if (is_event) {   // A = I, Q = 0, no input: S unchanged, s <- s + S b
         s_l = sbv;
-        if (FUSE) {       // K = 0, Phi = I, phi = b
-          double* __restrict__ Kg = d.s_K + (nb + k) * (size_t)(NU * NX);
-          for (int i = lane; i < NU; i += 32) { ric[R::K_KAP + i] = 0.0; d.s_uff[(nb + k) * NU + i] = 0.0; }
-          for (int i = lane; i < NX; i += 32) { ric[R::K_SPHI + i] = sr[S::S_B + i]; ric[R::K_G + i] = 0.0; }
-          for (int i = lane; i < NX * NX; i += 32) ric[R::K_PHI + i] = (i / NX == i % NX) ? 1.0 : 0.0;
-          for (int i = lane; i < NU * NX; i += 32) Kg[i] = 0.0;
-          if (lane == 0) { ric[R::K_MISC] = 0.0; ric[R::K_MISC + 1] = 1.0; }
-        }
         __syncwarp();
         if (lane == 0 && k >= 1) { fence_proxy_async(); tma_load_1d(sm.rec, d.stage + (nb + k - 1) * S::SREC, TMA_BYTES, &sm.bar); }
         continue;
@@ -1566,22 +1541,17 @@ __global__ void __launch_bounds__(128, 3) k_riccati_warp(Dev d) {
 #pragma unroll
         for (int nt = 0; nt < 3; ++nt) { dmma884(Sn[mt][nt][0], Sn[mt][nt][1], a0, Z[nt][kb][0]); dmma884(Sn[mt][nt][0], Sn[mt][nt][1], a1, Z[nt][kb][1]); }
       }
-    // ---- not fused: the staged record is free, prefetch the next stage while the Cholesky chain runs.  Fused: AB is still needed for
-    //      Phi = At + Bt Kt; the next record is only pulled into L2 here and staged at the end of the stage.
+    // ---- the staged record is free: prefetch the next stage while the Cholesky chain runs
     __syncwarp();
-    if (!FUSE) { if (lane == 0 && k >= 1) { fence_proxy_async(); tma_load_1d(sm.rec, d.stage + (nb + k - 1) * S::SREC, TMA_BYTES, &sm.bar); } }
-    else if (k >= 1) {
-      const char* nxt = reinterpret_cast<const char*>(d.stage + (nb + k - 1) * S::SREC);
-      for (int i = lane; i < (int)((S::SREC * sizeof(double) + 127) / 128); i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128 * i));
-    }
+    if (lane == 0 && k >= 1) { fence_proxy_async(); tma_load_1d(sm.rec, d.stage + (nb + k - 1) * S::SREC, TMA_BYTES, &sm.bar); }
     // ---- step C: [H | G] fragments -> shared memory -> one column per lane ; Cholesky of G fused with the forward substitution of [H | g]
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
       for (int c = 0; c < 5; ++c) *reinterpret_cast<double2*>(&sm.HG[(8 * a + g) * LDH + 8 * c + 2 * q]) = make_double2(HGf[a][c][0], HGf[a][c][1]);
     __syncwarp();
-    double gc[MP], hc[MP];
     {
+      double gc[MP], hc[MP];
 #pragma unroll
       for (int i = 0; i < MP; ++i) { gc[i] = (lane < MP) ? sm.HG[i * LDH + 24 + lane] : 0.0; hc[i] = (lane < 24) ? sm.HG[i * LDH + lane] : ((lane == 24) ? sm.gv[i] : 0.0); }
       __syncwarp();
@@ -1599,11 +1569,9 @@ __global__ void __launch_bounds__(128, 3) k_riccati_warp(Dev d) {
 #pragma unroll
       for (int i = 0; i < MP; ++i) {
         if (lane < 24) sm.HG[i * LDH + lane] = hc[i];                       // Y
-        if (!FUSE) {
-          if (lane < NX) ric[R::K_Y + i * NX + lane] = hc[i];
-          if (lane < MP) ric[R::K_L + i * MP + lane] = (i >= lane) ? gc[i] : 0.0;   // L (reciprocal pivots on the diagonal)
-        }
-        if (lane == 24) { sm.gv[i] = hc[i]; if (!FUSE) ric[R::K_YG + i] = hc[i]; }       // yg
+        if (lane < NX) ric[R::K_Y + i * NX + lane] = hc[i];
+        if (lane < MP) ric[R::K_L + i * MP + lane] = (i >= lane) ? gc[i] : 0.0;   // L (reciprocal pivots on the diagonal)
+        if (lane == 24) { sm.gv[i] = hc[i]; ric[R::K_YG + i] = hc[i]; }       // yg
       }
       __syncwarp();
       if (lane < 24) {   // s' -= Y^T yg
@@ -1637,105 +1605,6 @@ __global__ void __launch_bounds__(128, 3) k_riccati_warp(Dev d) {
           const double t0 = __shfl_sync(0xffffffffu, Sn[nt][mt][0], src), t1 = __shfl_sync(0xffffffffu, Sn[nt][mt][1], src);
           Sf[mt][nt][sl] = 0.5 * (Sn[mt][nt][sl] + ((g & 1) ? t1 : t0));
         }
-    if constexpr (FUSE) {
-      // ---- gains: Kt = -L^-T Y (lane c < 24: column c of Kt; lane 24: kt), staged in the Y area of HG for the Phi product
-      switch (m) {
-        case 6: chol_backsub<6, MP>(gc, hc, lane); break;
-        case 9: chol_backsub<9, MP>(gc, hc, lane); break;
-        case 12: chol_backsub<12, MP>(gc, hc, lane); break;
-        case 8: chol_backsub<8, MP>(gc, hc, lane); break;
-        case 11: chol_backsub<11, MP>(gc, hc, lane); break;
-        case 14: chol_backsub<14, MP>(gc, hc, lane); break;
-        default: chol_backsub<MP, MP>(gc, hc, lane); break;
-      }
-      const double* __restrict__ prj = d.proj + (nb + k) * D::PREC;
-      double* __restrict__ Kg = d.s_K + (nb + k) * (size_t)(NU * NX);
-      const int mj = (int)sr[S::S_META + S::T_MJ], mode = (int)sr[S::S_META + S::T_MODE];
-      const bool st0 = leg_in_stance(mode, 0), st1 = leg_in_stance(mode, 1);
-      __syncwarp();   // every lane is done with Y (step E)
-#pragma unroll
-      for (int i = 0; i < MP; ++i) { if (lane < 24) sm.HG[i * LDH + lane] = hc[i]; else if (lane == 24) sm.gv[i] = hc[i]; }
-      for (int i = lane; i < NJ * 8; i += 32) sm.HG[(i >> 3) * LDH + 24 + (i & 7)] = prj[D::P_N + i];   // null-space basis N (NJ x 8) in the L area
-      __syncwarp();
-      {   // Phi = At + Bt Kt (accumulators initialised with At from the staged record), stored straight from the fragments
-        double Ph[3][3][2];
-#pragma unroll
-        for (int mt = 0; mt < 3; ++mt)
-#pragma unroll
-          for (int nt = 0; nt < 3; ++nt) { const double2 v = *reinterpret_cast<const double2*>(&AB[(8 * mt + g) * LDA + 8 * nt + 2 * q]); Ph[mt][nt][0] = v.x; Ph[mt][nt][1] = v.y; }
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          if (4 * kk < m) {
-            double a_[3], b_[3];
-#pragma unroll
-            for (int t = 0; t < 3; ++t) { a_[t] = AB[(8 * t + g) * LDA + 24 + 4 * kk + q]; b_[t] = sm.HG[(4 * kk + q) * LDH + 8 * t + g]; }
-#pragma unroll
-            for (int mt = 0; mt < 3; ++mt)
-#pragma unroll
-              for (int nt = 0; nt < 3; ++nt) dmma884(Ph[mt][nt][0], Ph[mt][nt][1], a_[mt], b_[nt]);
-          }
-        }
-#pragma unroll
-        for (int mt = 0; mt < 3; ++mt)
-#pragma unroll
-          for (int nt = 0; nt < 3; ++nt) {
-            const int r_ = 8 * mt + g, c = 8 * nt + 2 * q;
-            if (r_ < NX) { if (c < NX) ric[R::K_PHI + r_ * NX + c] = Ph[mt][nt][0]; if (c + 1 < NX) ric[R::K_PHI + r_ * NX + c + 1] = Ph[mt][nt][1]; }
-          }
-      }
-      // phi = bt + Bt kt ; ghat = qt + Kt^T rt ; misc = rt^T kt (armijoDescentMetric)
-      if (lane < NX) {
-        double ph = sr[S::S_B + lane];
-#pragma unroll
-        for (int j = 0; j < MP; ++j) ph += AB[lane * LDA + 24 + j] * sm.gv[j];
-        ric[R::K_SPHI + lane] = ph;
-      }
-      if (lane <= 24) {
-        double gh = (lane < 24) ? sr[S::S_Q + lane] : 0.0;
-#pragma unroll
-        for (int j = 0; j < MP; ++j) gh += sr[S::S_R + j] * hc[j];
-        if (lane < NX) ric[R::K_G + lane] = gh; else if (lane == 24) { ric[R::K_MISC] = gh; ric[R::K_MISC + 1] = 0.0; }
-      }
-      // K = Px + Pu Kt, kappa = Pe + Pu kt: all NU values of the own column in registers first (they are read from HG, which P overlays)
-      const bool kcol = lane < NX, kap = lane == 24;
-      const double xk_l = kcol ? d.s_x[(nb + k) * NX + lane] : 0.0;
-      double kf[12], kj[NJ];
-#pragma unroll
-      for (int r_ = 0; r_ < 12; ++r_) {
-        const int cn = r_ / 3; const bool cl = (cn / 2 == 0) ? st0 : st1;
-        double a = 0.0;
-        if (cl) { const int row = mj + (st0 ? cn : cn - 2) * 3 + r_ % 3; a = kcol ? sm.HG[row * LDH + lane] : (kap ? sm.gv[row] : 0.0); }
-        else if (kap) a = -prj[D::P_FO + r_];
-        kf[r_] = a;
-      }
-      {
-        const bool xact = lane < 6 || (lane >= 9 && lane < NX);
-        const int xc = lane < 6 ? lane : lane - 3;
-#pragma unroll
-        for (int l = 0; l < NJ; ++l) {
-          double a = kcol ? (xact ? prj[D::P_PX + l * NXA + xc] : 0.0) : (kap ? prj[D::P_PE + l] : 0.0);
-#pragma unroll
-          for (int t = 0; t < 8; ++t) if (t < mj) a += sm.HG[l * LDH + 24 + t] * hc[t];
-          kj[l] = a;
-        }
-      }
-      __syncwarp();   // HG (Kt, N) is dead: P[r][c] = K[r][c] x[c] overlays it (row sums give K x)
-      double* P = sm.HG;
-#pragma unroll
-      for (int r_ = 0; r_ < 12; ++r_) { if (kcol) { Kg[r_ * NX + lane] = kf[r_]; P[r_ * 25 + lane] = kf[r_] * xk_l; } else if (kap) ric[R::K_KAP + r_] = kf[r_]; }
-#pragma unroll
-      for (int l = 0; l < NJ; ++l) { if (kcol) { Kg[(12 + l) * NX + lane] = kj[l]; P[(12 + l) * 25 + lane] = kj[l] * xk_l; } else if (kap) ric[R::K_KAP + 12 + l] = kj[l]; }
-      __syncwarp();
-      if (lane < NU) {
-        double kx = 0.0;
-#pragma unroll
-        for (int c = 0; c < NX; ++c) kx += P[lane * 25 + c];
-        d.s_uff[(nb + k) * NU + lane] = d.s_u[(nb + k) * NU + lane] - kx;
-      }
-      // ---- the staged record is free now: stage the next one (it was pulled into L2 before the Cholesky)
-      __syncwarp();
-      if (lane == 0 && k >= 1) { fence_proxy_async(); tma_load_1d(sm.rec, d.stage + (nb + k - 1) * S::SREC, TMA_BYTES, &sm.bar); }
-    }
     __syncwarp();   // HG / gv / sb are rewritten by the next stage
   }
 }

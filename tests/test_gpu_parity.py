@@ -328,9 +328,9 @@ def test_riccati_kernel_variants_agree():
             et, ms = helpers.tiled_schedule(gait[b], phase[b], t_hi=3.0)
             NE[b] = len(et); ET[b, :len(et)] = et; MS[b, :len(ms)] = ms
         pols, perfs = [], []
-        # 2: warp per instance with the gains fused in, 1: warp per instance + k_policy_expand (default), 0: CTA per instance + k_policy_expand;
-        # the last run also uses the thread-level line-search evaluation (model_eval) instead of the streaming one
-        for mode in (2, 1, 0):
+        # 1: warp per instance (default), 0: CTA per instance; the latter run also uses the thread-level line-search evaluation (model_eval)
+        # instead of the streaming one
+        for mode in (1, 0):
             g = G(B, model_file=model, dt=0.01, time_horizon=1.0)
             g.setOption("riccati_mode", mode)
             g.setOption("ls_mode", 1 if mode else 0)
@@ -339,11 +339,10 @@ def test_riccati_kernel_variants_agree():
             assert not (g.getStatus() & ~16).any()
             pols.append(g.getPolicy(0, B)); perfs.append(g.getPerformanceIndices())
             g.close()
-        for i in (0, 1):
-            for key in ("x", "u", "uff", "K"):
-                a, b_ = pols[i][key], pols[2][key]
-                assert np.abs(a - b_).max() <= 1e-9 * max(1.0, np.abs(b_).max()), (robot, i, key, np.abs(a - b_).max())
-            assert np.abs(perfs[i] - perfs[2]).max() <= 1e-9 * max(1.0, np.abs(perfs[2]).max())
+        for key in ("x", "u", "uff", "K"):
+            a, b_ = pols[0][key], pols[1][key]
+            assert np.abs(a - b_).max() <= 1e-9 * max(1.0, np.abs(b_).max()), (robot, key, np.abs(a - b_).max())
+        assert np.abs(perfs[0] - perfs[1]).max() <= 1e-9 * max(1.0, np.abs(perfs[1]).max())
 
 
 def test_config4_g1_second_morphology():
