@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--robot", default="h1", choices=["h1", "g1"], help="g1 = BASELINE configs[3] (use --batch 8192)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="full", choices=["full", "window", "none"])
+    ap.add_argument("--opt", action="append", default=[], help="debug option name=value passed to bmpc_debug_set_option (kernel variants; not for reported numbers)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -210,6 +211,9 @@ def main():
     model = MODELS[args.robot]
     w = workload(args.workload, B, rank, model)
     mpc = BatchedMpcMrtInterface(B, model_file=model, device=local_rank, dt=DT, time_horizon=HORIZON)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        mpc.setOption(name, int(val))
     stream = torch.cuda.ExternalStream(mpc.stream(), device=local_rank)
 
     # device-resident inputs for the kernel-only metric

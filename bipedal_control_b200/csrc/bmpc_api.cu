@@ -123,6 +123,11 @@ void tick(bmpc_handle* h) {
       constexpr int G = LqPackSmem<NJ>::G;
       const int NP = (NS + G - 1) / G;
       k_lq_pack<NJ><<<(B * NP + 3) / 4, 128, sizeof(LqPackSmem<NJ>), st>>>(d); ++h->launches;
+    } else if (h->lq_mode == 4) {
+      constexpr int G = LqPackSmem<NJ>::G;
+      const int NP = (NS + G - 1) / G;
+      k_base_pack<NJ><<<(B * NP + 3) / 4, 128, 0, st>>>(d); ++h->launches;
+      k_lq_assemble<NJ, false><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches;
     } else if (h->lq_mode == 2) { k_lq_assemble<NJ, true><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches; }
     else if (h->lq_mode == 1) {
       k_model_base<NJ><<<(nodes + 63) / 64, 64, 0, st>>>(d); ++h->launches;
@@ -511,7 +516,7 @@ int bmpc_debug_set_option(bmpc_handle* h, const char* name, int value) {
   if (!h || !name) return BMPC_ERR_INVALID;
   if (std::string(name) == "ls_mode") { if (value < 0 || value > 1) return BMPC_ERR_INVALID; h->ls_mode = value; return BMPC_OK; }
   if (std::string(name) == "riccati_mode") { if (value < 0 || value > 1) return BMPC_ERR_INVALID; h->riccati_mode = value; return BMPC_OK; }
-  if (std::string(name) == "lq_mode") { if (value < 0 || value > 3) return BMPC_ERR_INVALID; h->lq_mode = value; return BMPC_OK; }
+  if (std::string(name) == "lq_mode") { if (value < 0 || value > 4) return BMPC_ERR_INVALID; h->lq_mode = value; return BMPC_OK; }
   return BMPC_ERR_INVALID;
 }
 int bmpc_enable_phase_timing(bmpc_handle* h, int enable) { if (!h) return BMPC_ERR_INVALID; h->timing = enable != 0; return BMPC_OK; }

@@ -571,7 +571,7 @@ __device__ __forceinline__ double seg_sum(double v, int lane_w) {
   }
 }
 template <int NJ, int SEG = 32>
-__device__ __forceinline__ void warp_model_base(const double* __restrict__ x, const double* __restrict__ u, double* __restrict__ base, int lane_w, const double* __restrict__ jc) {
+__device__ __forceinline__ void warp_model_base(const double* __restrict__ x, const double* __restrict__ u, double* __restrict__ base, int lane_w, const double* __restrict__ jc, bool do_write = true) {
   using BD = BaseDims<NJ>;
   constexpr int NL = Dims<NJ>::NL;
   static_assert(NJ <= SEG, "one lane per joint");
@@ -669,13 +669,13 @@ __device__ __forceinline__ void warp_model_base(const double* __restrict__ x, co
   Mom htot;
   { Mom bm; bm.p = M.base_mass * (ve[3] + cross(we[3], cbase)); bm.n = mul(Ibase, we[3]) + cross(cbase, bm.p); htot = bm + shfl_mom(hs, hb) + shfl_mom(hs, hb + NL); }
   // ---- write the record: per-joint part by the joint's lane, shared part by lane WR of the segment (an idle lane when there is one)
-  if (act) {
+  if (act && do_write) {
     double* J = base + BD::B_J + BD::JS * j;
     st3(J + BD::J_O, o); st3(J + BD::J_A, a); st_si(J + BD::J_SI, comp); st3(J + BD::J_AL, Alin); st3(J + BD::J_AA, Aang);
     st3(J + BD::J_W, wj); st3(J + BD::J_V, vj); st3(J + BD::J_HN, hs.n); st3(J + BD::J_HP, hs.p);
     base[BD::B_F + 12 + j] = qd;
   }
-  if (lane == WR && hb + SEG <= 32) {
+  if (lane == WR && hb + SEG <= 32 && do_write) {
     st3(base + BD::B_PB, pb);
 #pragma unroll
     for (int k = 0; k < 3; ++k) { st3(base + BD::B_BAX + 3 * k, bax[k]); st3(base + BD::B_ALE + 3 * k, Alin_e[k]); st3(base + BD::B_AAE + 3 * k, Aang_e[k]); }

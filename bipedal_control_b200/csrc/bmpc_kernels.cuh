@@ -31,6 +31,9 @@ constexpr int WS_THREADS = 128;     // threads per CTA of the Riccati kernel (on
 #ifndef PROJ_BLOCKS
 #define PROJ_BLOCKS 4
 #endif
+#ifndef BASE_BLOCKS
+#define BASE_BLOCKS 4
+#endif
 #ifndef LQ_FUSED_BLOCKS
 #define LQ_FUSED_BLOCKS 2
 #endif
@@ -770,6 +773,57 @@ __global__ void __launch_bounds__(128, LQ_PAIR_BLOCKS) k_lq_pack(Dev d) {
     lq_stage_columns<NJ>(d, nb, k, rec, sm.base[warp][s], sm.base[warp][s] + BASE, xs, xs + 24, xs + 48, xs + 72, sm.A2[warp], lane);
     __syncwarp();   // A2 is reused by the next stage
   }
+}
+
+// Split LQ variant ("lq_mode" 4): k_base_pack evaluates the two base records of every stage (same packed base pass as k_lq_pack) and writes them
+// to global memory; k_lq_assemble<NJ, false> then runs the column pass with 128 registers / 16 warps per SM instead of 255 / 8.
+template <int NJ>
+__global__ void __launch_bounds__(128, BASE_BLOCKS) k_base_pack(Dev d) {
+  using D = Dims<NJ>; using BD = BaseDims<NJ>;
+  constexpr int NX = D::NX, NU = D::NU, WPB = 4, BASE = BD::BASE, SEG = LqPackSmem<NJ>::SEG, G = LqPackSmem<NJ>::G;
+  __shared__ double sjc[NJ][28];
+  __shared__ double sxu[WPB][G][3 * 24];   // x, u, x2
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < NJ * 28; i += 128) (&sjc[0][0])[i] = d.jc[i];
+  __syncthreads();
+  const int NP = (d.NS + G - 1) / G;
+  const int gw = blockIdx.x * WPB + warp;
+  const int b = gw / NP, k0 = G * (gw % NP);
+  if (b >= d.B) return;
+  const int N = d.n_nodes[b] - 1;
+  if (k0 >= N) return;
+  const size_t nb = (size_t)b * d.NS;
+  bool comp[G];
+  int first_comp = -1;
+#pragma unroll
+  for (int s = 0; s < G; ++s) {
+    comp[s] = k0 + s < N && d.node_ev[nb + k0 + s] != 1;
+    if (comp[s] && first_comp < 0) first_comp = s;
+  }
+  if (first_comp < 0) return;
+#pragma unroll
+  for (int s = 0; s < G; ++s) {
+    if (!comp[s]) continue;
+    double* xs = sxu[warp][s];
+    if (lane < NX) xs[lane] = d.s_x[(nb + k0 + s) * NX + lane];
+    if (lane < NU) xs[24 + lane] = d.s_u[(nb + k0 + s) * NU + lane];
+  }
+  __syncwarp();
+  const int h = lane / SEG;
+  int ms = first_comp; bool own = false;
+#pragma unroll
+  for (int s = 0; s < G; ++s) if (h == s && comp[s]) { ms = s; own = true; }
+  const double* xh = sxu[warp][ms]; const double* uh = xh + 24;
+  double* bh = d.base + (nb + k0 + ms) * (size_t)(2 * BASE);
+  const int jl = lane % SEG;
+  const double* jc = sjc[jl < NJ ? jl : 0];
+  warp_model_base<NJ, SEG>(xh, uh, bh, lane, jc, own);
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < G; ++s)
+    if (comp[s] && lane < NX) sxu[warp][s][48 + lane] = sxu[warp][s][lane] + d.st_dt[nb + k0 + s] * d.base[(nb + k0 + s) * (size_t)(2 * BASE) + BD::B_F + lane];
+  __syncwarp();
+  warp_model_base<NJ, SEG>(xh + 48, uh, bh + BASE, lane, jc, own);
 }
 
 // ------------------------------------------------------------------------------------------------ K1.5: constraint projection + change of input variables

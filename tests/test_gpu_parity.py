@@ -293,7 +293,7 @@ def test_lq_kernel_variants_agree():
         et, ms = helpers.tiled_schedule(gait[b], phase[b], t_hi=3.0)
         NE[b] = len(et); ET[b, :len(et)] = et; MS[b, :len(ms)] = ms
     recs = []
-    for split in (3, 2, 1, 0):
+    for split in (4, 3, 2, 1, 0):   # 4 = packed base pass through global memory + column kernel, 3 = packed fused (default), ...
         g = G(B, model_file=MODEL, dt=0.01, time_horizon=1.0)
         g.setOption("lq_mode", split)
         g.setCurrentObservation(np.zeros(B), X0); g.setTargetsFromCmdVel(cmd, 1.0); g.setModeSchedule(ET, MS, NE)
@@ -301,7 +301,7 @@ def test_lq_kernel_variants_agree():
         n = g.getPolicy(0, B, with_gains=False)["n_nodes"]
         recs.append([g.debugCopy("lq_record", b)[:n[b] - 1] for b in (0, 7, 19, 47)])
         g.close()
-    for ra, rb in list(zip(recs[0], recs[3])) + list(zip(recs[1], recs[3])) + list(zip(recs[2], recs[3])):
+    for ra, rb in [p_ for i in range(4) for p_ in zip(recs[i], recs[4])]:
         scale = np.maximum(1.0, np.abs(rb))
         # rows beyond nrows of the constraint block are never written: compare only what both kernels define
         assert np.abs((ra - rb) / scale)[:, :22 + 171 + 198 + 44 + 24].max() < 1e-10

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 cp bipedal_control_b200/libbmpc.so /tmp/libbmpc_keep.so
 for f in variants/libbmpc_*.so; do
   cp $f bipedal_control_b200/libbmpc.so
-  timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/var.json 2> gpurun_out/var.err
+  timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline $BENCH_OPTS > gpurun_out/var.json 2> gpurun_out/var.err
   python - "$f" <<'PY'
 import json, sys
 try:
