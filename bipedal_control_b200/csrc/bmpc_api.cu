@@ -112,7 +112,7 @@ void tick(bmpc_handle* h) {
   mark(1);
   CK(cudaFuncSetAttribute(k_riccati<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem<NJ>)));
   CK(cudaFuncSetAttribute(k_riccati<NJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(k_riccati_warp<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(RicWarpSmem<NJ>))));
+  CK(cudaFuncSetAttribute(k_riccati_warp<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RIC_WPC * sizeof(RicWarpSmem<NJ>))));
   CK(cudaFuncSetAttribute(k_riccati_warp<NJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_lq_pack<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LqPackSmem<NJ>)));
   CK(cudaFuncSetAttribute(k_policy_expand<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(PolSmem<NJ>))));
@@ -136,7 +136,7 @@ void tick(bmpc_handle* h) {
     if (iter == 0) mark(2);
     k_project<NJ><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches;
     if (iter == 0) mark(3);
-    if (h->riccati_mode == 1) { k_riccati_warp<NJ><<<(B + 3) / 4, 128, 4 * sizeof(RicWarpSmem<NJ>), st>>>(d); ++h->launches; }   // one warp per instance (default)
+    if (h->riccati_mode == 1) { k_riccati_warp<NJ><<<(B + RIC_WPC - 1) / RIC_WPC, 32 * RIC_WPC, RIC_WPC * sizeof(RicWarpSmem<NJ>), st>>>(d); ++h->launches; }   // one warp per instance (default)
     else { k_riccati<NJ><<<B, WS_THREADS, sizeof(RicSmem<NJ>), st>>>(d); ++h->launches; }                                        // one CTA per instance
     if (iter == 0) mark(4);
     k_policy_expand<NJ><<<(nodes + 3) / 4, 128, 4 * sizeof(PolSmem<NJ>), st>>>(d); ++h->launches;

@@ -34,6 +34,12 @@ constexpr int WS_THREADS = 128;     // threads per CTA of the Riccati kernel (on
 #ifndef BASE_BLOCKS
 #define BASE_BLOCKS 4
 #endif
+#ifndef RIC_BLOCKS
+#define RIC_BLOCKS 3
+#endif
+#ifndef RIC_WPC
+#define RIC_WPC 4   // independent instances (warps) per CTA of k_riccati_warp
+#endif
 #ifndef LQ_FUSED_BLOCKS
 #define LQ_FUSED_BLOCKS 2
 #endif
@@ -1488,13 +1494,13 @@ struct RicWarpSmem {
 };
 
 template <int NJ>
-__global__ void __launch_bounds__(128, 3) k_riccati_warp(Dev d) {
+__global__ void __launch_bounds__(32 * RIC_WPC, RIC_BLOCKS) k_riccati_warp(Dev d) {
   using D = Dims<NJ>; using R = RDims<NJ>; using S = SDims<NJ>; using SM = RicWarpSmem<NJ>;
   constexpr int NX = D::NX, MP = S::MP, LDA = S::LDA, LDH = SM::LDH;
   constexpr unsigned TMA_BYTES = S::TMA_DOUBLES * sizeof(double);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 4 + warp;
+  const int b = blockIdx.x * RIC_WPC + warp;
   if (b >= d.B) return;
   SM& sm = reinterpret_cast<SM*>(smem_raw)[warp];
   const int N = d.n_nodes[b] - 1;
@@ -1655,9 +1661,13 @@ __global__ void __launch_bounds__(128, 3) k_riccati_warp(Dev d) {
       for (int nt = 0; nt < 3; ++nt)
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl) {
+#ifdef RIC_NOSYM
+          Sf[mt][nt][sl] = Sn[mt][nt][sl];
+#else
           const int src = (2 * q + sl) * 4 + (g >> 1);
           const double t0 = __shfl_sync(0xffffffffu, Sn[nt][mt][0], src), t1 = __shfl_sync(0xffffffffu, Sn[nt][mt][1], src);
           Sf[mt][nt][sl] = 0.5 * (Sn[mt][nt][sl] + ((g & 1) ? t1 : t0));
+#endif
         }
     __syncwarp();   // HG / gv / sb are rewritten by the next stage
   }
