@@ -751,14 +751,18 @@ __global__ void __launch_bounds__(128, LQ_PAIR_BLOCKS) k_lq_pack(Dev d) {
     const int jl = lane % SEG;
     const double* jc = sm.jc[jl < NJ ? jl : 0];
     double* x2 = &sm.A2[warp][0][0];   // scratch for the second RK2 evaluation points (A2 is filled later): G x 24 doubles
-    warp_model_base<NJ, SEG>(xh, uh, bh, lane, jc);
-    __syncwarp();
+    // the two Heun evaluations share one copy of the (large) base-pass code: the kernel is instruction-cache bound otherwise
+#pragma unroll 1
+    for (int ev_ = 0; ev_ < 2; ++ev_) {
+      warp_model_base<NJ, SEG>(ev_ == 0 ? xh : x2 + 24 * ms, uh, bh + ev_ * BASE, lane, jc);
+      __syncwarp();
+      if (ev_ == 0) {
 #pragma unroll
-    for (int s = 0; s < G; ++s)
-      if (lane < NX) x2[24 * s + lane] = comp[s] ? sm.xu[warp][s][lane] + d.st_dt[nb + k0 + s] * sm.base[warp][s][BD::B_F + lane] : 0.0;
-    __syncwarp();
-    warp_model_base<NJ, SEG>(x2 + 24 * ms, uh, bh + BASE, lane, jc);
-    __syncwarp();
+        for (int s = 0; s < G; ++s)
+          if (lane < NX) x2[24 * s + lane] = comp[s] ? sm.xu[warp][s][lane] + d.st_dt[nb + k0 + s] * sm.base[warp][s][BD::B_F + lane] : 0.0;
+        __syncwarp();
+      }
+    }
   }
 #pragma unroll 1
   for (int s = 0; s < G; ++s) {
