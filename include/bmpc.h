@@ -153,8 +153,11 @@ void* bmpc_get_stream(bmpc_handle* h); /* cudaStream_t the library launches on *
  * instance to host.  names: "lq_record", "proj_record", "riccati_record", "dx", "du", "x_lin", "u_lin", "node_meta" */
 int bmpc_debug_copy(bmpc_handle* h, const char* name, int instance, double* dst, int capacity_doubles);
 int bmpc_debug_record_sizes(const bmpc_handle* h, int* lq_rec, int* proj_rec, int* ric_rec);
-/* options: "lq_mode" 2 (default: fused warp-cooperative k_lq_assemble<FUSED>), 1 (k_model_base + k_lq_assemble), 0 (single-kernel k_lq);
- * the three implementations of the LQ approximation are cross-checked against each other in tests/ */
+/* kernel-variant options, cross-checked against each other in tests/ (defaults are the fastest measured):
+ *   "lq_mode"      4 (packed base pass through global memory + column kernel), 3 (default: packed fused k_lq_pack, 3 (H1) / 2 (G1) stages per warp),
+ *                  2 (one stage per warp, k_lq_assemble<FUSED>), 1 (k_model_base + k_lq_assemble), 0 (single-kernel k_lq)
+ *   "riccati_mode" 1 (default: one warp per instance, k_riccati_warp), 0 (one CTA per instance, k_riccati)
+ *   "ls_mode"      1 (default: streaming register-only flow map, k_linesearch_eval2), 0 (thread-level model_eval, k_linesearch_eval) */
 int bmpc_debug_set_option(bmpc_handle* h, const char* name, int value);
 
 #ifdef __cplusplus
