@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--robot", default="h1", choices=["h1", "g1"], help="g1 = BASELINE configs[3] (use --batch 8192)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="full", choices=["full", "window", "none"])
+    ap.add_argument("--gather-impl", default="nccl", choices=["ce", "nccl"], help="full-policy all-gather: ncclAllGather (default: fastest measured at 8 GPUs) or copy-engine pulls over peer-mapped (symmetric) memory, which keep the SMs free but do not reach NVLink speed")
     ap.add_argument("--opt", action="append", default=[], help="debug option name=value passed to bmpc_debug_set_option (kernel variants; not for reported numbers)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -229,33 +230,74 @@ def main():
 
     gather_bufs = {}
     gstream = torch.cuda.Stream(device=dev) if world > 1 else None
-    gather_events = []   # completion events of the in-flight all-gathers (policy buffers are double buffered in the library)
+    gather_events = []   # events after which the library's policy buffer of that tick may be overwritten (policy buffers are double buffered in the library)
+    symm = {}            # copy-engine all-gather: name -> (staging tensor in symmetric memory, rendezvous handle)
+    gather_impl = {"kind": "nccl"}
+
+    def policy_fields(v):
+        NS, nx, nu = mpc.max_nodes, mpc.nx, mpc.nu
+        ptr = (lambda n: getattr(v, n)) if v is not None else (lambda n: 0)
+        return (("K", ptr("K"), NS * nu * nx), ("uff", ptr("uff"), NS * nu), ("x", ptr("x"), NS * nx), ("u", ptr("u"), NS * nu), ("t", ptr("times"), NS))
+
+    def setup_copy_engine_gather():
+        """Peer-mapped staging buffers (torch symmetric memory: CUDA VMM handles exchanged inside the node).  The all-gather then is 7 pulls per
+        rank with copy engines over NVLink (no SMs, so the next tick's kernels keep the whole GPU); falls back to ncclAllGather if unavailable."""
+        if world == 1 or args.gather != "full" or args.gather_impl != "ce":
+            return
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            for name, _, per in policy_fields(None):
+                t = symm_mem.empty(B * per, dtype=torch.float64, device=dev)
+                symm[name] = (t, symm_mem.rendezvous(t, dist.group.WORLD.group_name))
+            gather_impl["kind"] = "copy-engine pulls over peer-mapped (symmetric) memory"
+        except Exception as e:   # noqa: BLE001
+            symm.clear()
+            gather_impl["kind"] = "nccl (symmetric memory unavailable: %s)" % str(e).splitlines()[0][:80]
 
     def gather_policies():
-        """One NCCL all-gather of the solved feedback policies per tick (north star).  The gather runs on a side stream and overlaps
-        with the next tick's compute: the library double-buffers its policies, so the buffer being gathered is only overwritten two
-        ticks later, and that tick first waits for this gather.  'window' = only the nodes consumers read before the next tick."""
+        """One all-gather of the solved feedback policies per tick (north star).  The gather runs on a side stream and overlaps with the next
+        tick's compute: the library double-buffers its policies, so the buffer being gathered is only overwritten two ticks later, and that tick
+        first waits until the buffer has been read.  'window' = only the nodes consumers read before the next tick."""
         if world == 1 or args.gather == "none":
             return 0
         v = mpc.getDeviceView()
-        NS, nx, nu = v.max_nodes, v.nx, v.nu
         nbytes = 0
         done = torch.cuda.Event()
         ready = torch.cuda.Event()
         ready.record(stream)
         gstream.wait_event(ready)
+        parity = len(gather_events) & 1
         with torch.cuda.stream(gstream):
-            for name, ptr, per in (("K", v.K, NS * nu * nx), ("uff", v.uff, NS * nu), ("x", v.x, NS * nx), ("u", v.u, NS * nu), ("t", v.times, NS)):
-                src = _alias(ptr, B * per, dev)
-                if args.gather == "window":
-                    k = 4  # t0 .. t0 + 1/50 s is covered by the first 3 nodes at dt 0.01; 4 for interpolation
-                    src = src.view(B, NS, -1)[:, :k].contiguous()
-                key = (name, src.numel(), len(gather_events) & 1)
-                if key not in gather_bufs:
-                    gather_bufs[key] = torch.empty(world * src.numel(), device=dev, dtype=torch.float64)
-                dist.all_gather_into_tensor(gather_bufs[key], src.reshape(-1))
-                nbytes += src.numel() * 8 * world
-            done.record(gstream)
+            if symm:
+                fields = policy_fields(v)
+                for name, ptr, per in fields:
+                    symm[name][0].copy_(_alias(ptr, B * per, dev))      # stage the shard where the peers can read it (local copy)
+                h0 = symm["K"][1]
+                h0.barrier(channel=0)                                    # every rank has staged this tick
+                for name, ptr, per in fields:
+                    key = (name, B * per, parity)
+                    if key not in gather_bufs:
+                        gather_bufs[key] = torch.empty(world * B * per, device=dev, dtype=torch.float64)
+                # pulls on one stream, one peer after the other (measured at 8 GPUs: 25.5 ms / tick; one stream per peer: 40 ms; ncclAllGather: 23.3 ms)
+                for step in range(world):
+                    r = (rank - step) % world
+                    for name, ptr, per in fields:
+                        gather_bufs[(name, B * per, parity)].chunk(world)[r].copy_(symm[name][1].get_buffer(r, (B * per,), torch.float64))
+                    nbytes += sum(per for _, _, per in fields) * B * 8
+                h0.barrier(channel=0)                                    # nobody restages before every pull has finished
+                done.record(gstream)
+            else:
+                for name, ptr, per in policy_fields(v):
+                    src = _alias(ptr, B * per, dev)
+                    if args.gather == "window":
+                        k = 4  # t0 .. t0 + 1/50 s is covered by the first 3 nodes at dt 0.01; 4 for interpolation
+                        src = src.view(B, mpc.max_nodes, -1)[:, :k].contiguous()
+                    key = (name, src.numel(), parity)
+                    if key not in gather_bufs:
+                        gather_bufs[key] = torch.empty(world * src.numel(), device=dev, dtype=torch.float64)
+                    dist.all_gather_into_tensor(gather_bufs[key], src.reshape(-1))
+                    nbytes += src.numel() * 8 * world
+                done.record(gstream)
         gather_events.append(done)
         return nbytes
 
@@ -311,6 +353,8 @@ def main():
             if collect_phases:
                 mpc.synchronize()
                 phases.append(mpc.phaseTimes())
+        if gstream is not None:
+            stream.wait_stream(gstream)   # the timed region ends when the last policy all-gather has finished, not only the last tick
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -322,6 +366,7 @@ def main():
         return ms, wall, phases
 
     # cold start (t0 = 0) + warm-up ticks of the closed loop
+    setup_copy_engine_gather()
     mpc.reset()
     mpc.setCurrentObservationDevice(d_t0.data_ptr(), d_x0.data_ptr())
     mpc.setTargetsFromCmdVelDevice(d_cmd.data_ptr(), 1.0)
@@ -383,7 +428,7 @@ def main():
         "config": {"workload": ("BASELINE configs[1]: H1 trot, horizon 1.0 s, dt 0.01 (N=100 intervals + 3 event nodes = 103 stages), batch 4096 identical instances per GPU; closed loop: every step advances t0 by 1/50 s, takes x0 from the previous policy and solves one warm-started tick"
                                 if args.workload == "identical" else "BASELINE configs[2]: H1 randomized states / velocity references / gaits (seed = rank), batch 4096 per GPU, warm-started tick"),
                    "robot": args.robot, "batch_per_gpu": B, "stages": nodes_stage, "l2": "per-tick working set (>5 GB of stage records) exceeds the 126 MB L2; no explicit flush",
-                   "policy_gather": (args.gather + ", one all-gather per tick on a side stream, overlapped with the next tick (double-buffered policies)") if world > 1 else "n/a (1 GPU)"},
+                   "policy_gather": (args.gather + ", one all-gather per tick on a side stream, overlapped with the next tick (double-buffered policies); " + gather_impl["kind"]) if world > 1 else "n/a (1 GPU)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
                 "note": "host buffers every step: bmpc_evaluate_policy -> bmpc_set_observations -> bmpc_set_targets_from_cmd_vel -> bmpc_set_mode_schedules -> bmpc_advance -> bmpc_get_performance"},
         "gpu_launches": int(launches),
