@@ -443,9 +443,9 @@ def main():
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         sample = max(threads * 16, 64)
-        val, sec, _ = cpu_baseline_run(sample, 16, threads, kind=args.workload, model=model)
+        val, sec, _ = cpu_baseline_run(sample, 24, threads, kind=args.workload, model=model)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{sample} instances x 16 warm closed-loop ticks of the same workload, one std::thread per core ({sec:.1f} s)"}
+                                "sample": f"{sample} instances x 24 warm closed-loop ticks of the same workload, one std::thread per core ({sec:.1f} s)"}
     if rank == 0:
         emit(line)
     if world > 1:
