@@ -1,0 +1,86 @@
+// shared declarations: tuning knobs, the Dev argument block, interpolation helpers, the DMMA tile instruction
+// (part of bmpc_kernels.cuh: include that header, not this file)
+#pragma once
+
+namespace bmpc {
+
+
+constexpr double WEAK_EPS = 1e-6;   // [UPSTREAM] numeric_traits::weakEpsilon
+constexpr int WS_THREADS = 128;     // threads per CTA of the Riccati kernel (one instance per CTA)
+#ifndef LQ_MIN_BLOCKS
+#define LQ_MIN_BLOCKS 8
+#endif
+#ifndef LQ_PAIR_BLOCKS
+#define LQ_PAIR_BLOCKS 2
+#endif
+#ifndef LS_BLOCKS
+#define LS_BLOCKS 6
+#endif
+#ifndef LS2_BLOCKS
+#define LS2_BLOCKS 4
+#endif
+#ifndef PROJ_BLOCKS
+#define PROJ_BLOCKS 4
+#endif
+#ifndef BASE_BLOCKS
+#define BASE_BLOCKS 4
+#endif
+#ifndef RIC_BLOCKS
+#define RIC_BLOCKS 3
+#endif
+#ifndef RIC_WPC
+#define RIC_WPC 4   // independent instances (warps) per CTA of k_riccati_warp
+#endif
+#ifndef LQ_FUSED_BLOCKS
+#define LQ_FUSED_BLOCKS 2
+#endif
+
+template <int NJ> struct RDims;
+template <int NJ> struct SDims;
+
+struct Dev {
+  int B, NS, ME, TP, npts;
+  double dt_nom, horizon;
+  const double* t0; const double* x0;
+  const double* tgt_t; const double* tgt_x;
+  const int* n_ev; const double* ev_t; const int* ev_mode;
+  int* n_nodes; double* node_t; int* node_ev; double* st_t; double* st_dt; int* st_mode;
+  double* xref; double* zref;
+  const int* p_n; const double* p_t; const double* p_x; const double* p_u;   // previous primal solution (warm start)
+  double* s_x; double* s_u; double* s_uff; double* s_K;                      // new primal solution / linearisation point
+  double* lq; double* proj; double* stage; double* ric; double* base; const double* jc;
+  double* dx; double* du;
+  double* perf_trial; double* perf; double* alpha; double* norms; int* done; int* status; int* counters;
+};
+
+// ------------------------------------------------------------------------------------------------ helpers
+// FP64 tensor-core tile: D(8x8) += A(8x4) B(4x8); lane (g, q) = (lane >> 2, lane & 3) supplies A[g][q], B[q][g] and owns D[g][2q], D[g][2q+1]  (SASS: DMMA)
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ int lower_bound_d(const double* a, int n, double t) {  // first index with a[i] >= t
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < t) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+// [UPSTREAM] LinearInterpolation::timeSegment
+__device__ __forceinline__ void time_segment(const double* ta, int n, double t, int& index, double& alpha) {
+  int idx = lower_bound_d(ta, n, t);
+  int iv = (idx == 0 && n > 0 && t == ta[0]) ? 0 : idx - 1;
+  const int last = n - 1;
+  if (iv >= 0) {
+    if (iv < last) {
+      const double len = ta[iv + 1] - ta[iv], till = ta[iv + 1] - t;
+      if (len > 2.0 * 2.220446049250313e-16) { index = iv; alpha = till / len; }
+      else { index = iv; alpha = (till < 0.5 * len) ? 0.0 : 1.0; }
+    } else { index = max(last - 1, 0); alpha = 0.0; }
+  } else { index = 0; alpha = 1.0; }
+}
+__device__ __forceinline__ void interp_vec(const double* ta, const double* data, int n, int dim, double t, double* out) {
+  if (n <= 1) { for (int i = 0; i < dim; ++i) out[i] = data[i]; return; }
+  int idx; double al; time_segment(ta, n, t, idx, al);
+  const double* a = data + (size_t)idx * dim; const double* b = a + dim;
+  for (int i = 0; i < dim; ++i) out[i] = al * a[i] + (1.0 - al) * b[i];
+}
+
+}  // namespace bmpc

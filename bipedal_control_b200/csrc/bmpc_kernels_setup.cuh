@@ -1,0 +1,122 @@
+// K0: time grid with event nodes, per-node references, warm start
+// (part of bmpc_kernels.cuh: include that header, not this file)
+#pragma once
+
+namespace bmpc {
+
+// ------------------------------------------------------------------------------------------------ K0a: time grid
+__global__ void k_time_grid(Dev d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  const double t0 = d.t0[b], tf = t0 + d.horizon, dt = d.dt_nom;
+  const double* ev = d.ev_t + (size_t)b * d.ME; const int ne = d.n_ev[b];
+  double* nt = d.node_t + (size_t)b * d.NS; int* nev = d.node_ev + (size_t)b * d.NS;
+  const double dt_min = 10.0 * WEAK_EPS;
+  int n = 0; bool overflow = false;
+  nt[0] = t0; nev[0] = 0; n = 1;
+  int nextEvent = lower_bound_d(ev, ne, t0);
+  double nextT = t0; int nextE = 0;
+  while (nt[n - 1] < tf) {
+    nextT = nextT + dt; nextE = 0;
+    if (nextEvent < ne && nextT >= ev[nextEvent]) { nextT = ev[nextEvent]; nextE = 1; ++nextEvent; }
+    if (nextT >= tf) { nextT = tf; nextE = 0; }
+    if (nextT > nt[n - 1] + dt_min) { if (n >= d.NS) { overflow = true; break; } nt[n] = nextT; nev[n] = nextE; ++n; }
+    else { nt[n - 1] = nextT; nev[n - 1] = nextE; }
+    if (nextE == 1) { if (n >= d.NS) { overflow = true; break; } nt[n] = nextT; nev[n] = 2; ++n; }
+  }
+  if (overflow) { atomicOr(&d.status[b], 32); nt[n - 1] = tf; nev[n - 1] = 0; }
+  d.n_nodes[b] = n;
+  double* stt = d.st_t + (size_t)b * d.NS; double* std_ = d.st_dt + (size_t)b * d.NS;
+  for (int i = 0; i + 1 < n; ++i) {
+    const double ts = nev[i] == 2 ? nt[i] + WEAK_EPS : nt[i];
+    const double te = nev[i + 1] == 1 ? nt[i + 1] - WEAK_EPS : nt[i + 1];
+    stt[i] = ts; std_[i] = (nev[i] == 1) ? 0.0 : te - ts;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K0b: per-node references + warm start
+// swing height velocity of leg `leg` at time t (foot_planner/SwingTrajectoryPlanner.cpp:50-118, SplineCpg.cpp:38-60, CubicSpline.cpp:38-75)
+__device__ inline double swing_zvel(const double* ev, const int* modes, int ne, int leg, double t, int* status) {
+  const int np = ne + 1;
+  const int p = lower_bound_d(ev, ne, t);
+  int start = -1;
+  for (int ip = p - 1; ip >= 0; --ip) if (leg_in_stance(modes[ip], leg)) { start = ip; break; }
+  int fin = np - 1;
+  for (int ip = p + 1; ip < np; ++ip) if (leg_in_stance(modes[ip], leg)) { fin = ip - 1; break; }
+  if (start < 0 || fin >= np - 1) { atomicOr(status, 4); return 0.0; }
+  const double ts = ev[start], tf = ev[fin];
+  const double scaling = fmin(1.0, (tf - ts) / c_model.swing_time_scale);
+  const double mid_t = 0.5 * (ts + tf), mid_h = scaling * c_model.swing_height;
+  double t_a, p_a, v_a, t_b, p_b, v_b;
+  if (t < mid_t) { t_a = ts; p_a = 0.0; v_a = scaling * c_model.liftoff_vel; t_b = mid_t; p_b = mid_h; v_b = 0.0; }
+  else { t_a = mid_t; p_a = mid_h; v_a = 0.0; t_b = tf; p_b = 0.0; v_b = scaling * c_model.touchdown_vel; }
+  const double dts = t_b - t_a, dp = p_b - p_a, dv = v_b - v_a;
+  const double c1 = v_a * dts, c2 = -(3.0 * v_a + dv) * dts + 3.0 * dp, c3 = (2.0 * v_a + dv) * dts - 2.0 * dp;
+  const double tn = (t - t_a) / dts;
+  return (3.0 * c3 * tn * tn + 2.0 * c2 * tn + c1) / dts;
+}
+
+template <int NJ>
+__global__ void k_node_setup(Dev d) {
+  constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = gid / d.NS, k = gid % d.NS;
+  if (b >= d.B) return;
+  const int n = d.n_nodes[b];
+  if (k >= n) return;
+  const int N = n - 1;
+  const size_t nb = (size_t)b * d.NS;
+  const double* ev = d.ev_t + (size_t)b * d.ME; const int* modes = d.ev_mode + (size_t)b * (d.ME + 1); const int ne = d.n_ev[b];
+  const int* nev = d.node_ev + nb;
+  const double* nt = d.node_t + nb;
+  const double* stt = d.st_t + nb; const double* std_ = d.st_dt + nb;
+  // ---- stage references
+  if (k < N) {
+    int mode = -1;
+    if (nev[k] != 1) {
+      const double t = stt[k];
+      mode = modes[lower_bound_d(ev, ne, t)];
+      interp_vec(d.tgt_t + (size_t)b * d.TP, d.tgt_x + (size_t)b * d.TP * NX, d.npts, NX, t, d.xref + (nb + k) * NX);
+      for (int leg = 0; leg < 2; ++leg)
+        d.zref[(nb + k) * 2 + leg] = leg_in_stance(mode, leg) ? 0.0 : swing_zvel(ev, modes, ne, leg, t, &d.status[b]);
+    }
+    d.st_mode[nb + k] = mode;
+  }
+  // ---- initial guess: [UPSTREAM] multiple_shooting::initializeStateInputTrajectories
+  const int pn = d.p_n ? d.p_n[b] : 0;
+  const double* pt = d.p_t + nb; const double* px = d.p_x + nb * NX; const double* pu = d.p_u + nb * NU;
+  double stateTill = nt[0], inputTill = nt[0];
+  if (pn >= 2) { stateTill = pt[pn - 1]; inputTill = pt[pn - 2]; }
+  auto interval_uses_initializer = [&](int i) {   // interval i = [node i, node i+1]; true also for event nodes (state copied)
+    if (nev[i] == 1) return true;
+    const double ti = stt[i], tn = stt[i] + std_[i];
+    return (ti > inputTill || tn > stateTill);
+  };
+  // state of node k
+  int j = k;
+  while (j > 0 && interval_uses_initializer(j - 1)) --j;
+  double* xo = d.s_x + (nb + k) * NX;
+  if (j == 0) {
+    const double tinit = nev[0] == 2 ? nt[0] + WEAK_EPS : nt[0];
+    if (tinit < stateTill) interp_vec(pt, px, pn, NX, tinit, xo);
+    else for (int i = 0; i < NX; ++i) xo[i] = d.x0[(size_t)b * NX + i];
+  } else {
+    interp_vec(pt, px, pn, NX, stt[j - 1] + std_[j - 1], xo);
+  }
+  // input of stage k
+  if (k < N) {
+    double* uo = d.s_u + (nb + k) * NU;
+    if (nev[k] == 1) { for (int i = 0; i < NU; ++i) uo[i] = 0.0; }
+    else if (interval_uses_initializer(k)) {   // initialization/BipedalRobotInitializer.cpp:56-63 + common/utils.h:63-77
+      const int mode = modes[lower_bound_d(ev, ne, stt[k])];
+      const bool s0 = leg_in_stance(mode, 0), s1 = leg_in_stance(mode, 1);
+      const int ns = 2 * (int(s0) + int(s1));
+      const double fz = ns > 0 ? c_model.total_mass * 9.81 / ns : 0.0;
+      for (int i = 0; i < NU; ++i) uo[i] = 0.0;
+      if (s0) { uo[2] = fz; uo[5] = fz; }
+      if (s1) { uo[8] = fz; uo[11] = fz; }
+    } else interp_vec(pt, pu, pn, NU, stt[k], uo);
+  }
+}
+
+}  // namespace bmpc
