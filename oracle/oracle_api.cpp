@@ -188,10 +188,12 @@ void orc_spline(double ts, double ps, double vs, double mid, double tf, double p
   SplineCpg sp(ts, ps, vs, mid, tf, pf, vf);
   for (int i = 0; i < n; ++i) { pos[i] = sp.position(tq[i]); vel[i] = sp.velocity(tq[i]); }
 }
+// 0: Moore-Penrose projection (default = the CUDA product), 1: emulation of upstream's Eigen::FullPivLU projection (process-wide switch, tests only)
+void orc_set_projection_mode(int mode) { projection_mode() = mode; }
 int orc_project(int nr, int nu, int nx, const double* C, const double* D, const double* e, double* Px, double* Pu, double* Pe) {
   ORC_TRY Mat Cm(nr, nx), Dm(nr, nu); Cm.a.assign(C, C + nr * nx); Dm.a.assign(D, D + nr * nu);
   std::vector<double> ev(e, e + nr), pe; Mat px, pu; int rank = 0;
-  project_constraints(Cm, Dm, ev, px, pu, pe, rank);
+  project_constraints_dispatch(Cm, Dm, ev, px, pu, pe, rank);
   for (size_t i = 0; i < px.a.size(); ++i) Px[i] = px.a[i];
   for (size_t i = 0; i < pu.a.size(); ++i) Pu[i] = pu.a[i];
   for (size_t i = 0; i < pe.size(); ++i) Pe[i] = pe[i];

@@ -412,6 +412,68 @@ inline void project_constraints(const Mat& C, const Mat& D, const std::vector<do
   }
 }
 
+// ---------------------------------------------------------------- [UPSTREAM] luConstraintProjection, emulated
+// What upstream does (ocs2_core LinearAlgebra::luConstraintProjection; the reference selects it with projectStateInputEqualityConstraints,
+// task.info:76):  lu = Eigen::FullPivLU(D);  Pu = lu.kernel();  Px = -lu.solve(C);  Pe = -lu.solve(e).
+// Restated from Eigen's documented algorithm: Gaussian elimination with complete pivoting; rank = number of pivots with
+// |pivot| > eps * min(rows, cols) * |largest pivot|; solve() forward-substitutes with the unit-lower factor, back-substitutes the leading
+// rank x rank block of U and sets the free unknowns to zero, i.e. it satisfies the first `rank` pivot rows and silently ignores the rest.
+// Used only to QUANTIFY the documented deviation of the default (Moore-Penrose) projection; never on the product path.
+inline void project_constraints_fullpivlu(const Mat& C, const Mat& D, const std::vector<double>& e, Mat& Px, Mat& Pu, std::vector<double>& Pe, int& rank) {
+  const int nr = D.r, nu = D.c, nx = C.c, sd = std::min(nr, nu);
+  Mat lu = D;
+  std::vector<int> rowp(nr), colp(nu);
+  for (int i = 0; i < nr; ++i) rowp[i] = i;
+  for (int j = 0; j < nu; ++j) colp[j] = j;
+  double maxpivot = 0.0; int nonzero = sd;
+  for (int k = 0; k < sd; ++k) {
+    int br = k, bc = k; double big = -1.0;
+    for (int i = k; i < nr; ++i) for (int j = k; j < nu; ++j) if (std::fabs(lu(i, j)) > big) { big = std::fabs(lu(i, j)); br = i; bc = j; }
+    if (big == 0.0) { nonzero = k; break; }
+    maxpivot = std::max(maxpivot, big);
+    if (br != k) { for (int j = 0; j < nu; ++j) std::swap(lu(k, j), lu(br, j)); std::swap(rowp[k], rowp[br]); }
+    if (bc != k) { for (int i = 0; i < nr; ++i) std::swap(lu(i, k), lu(i, bc)); std::swap(colp[k], colp[bc]); }
+    for (int i = k + 1; i < nr; ++i) {
+      const double f = lu(i, k) / lu(k, k);
+      lu(i, k) = f;
+      for (int j = k + 1; j < nu; ++j) lu(i, j) -= f * lu(k, j);
+    }
+  }
+  const double thr = std::numeric_limits<double>::epsilon() * sd * maxpivot;
+  rank = 0;
+  for (int k = 0; k < nonzero; ++k) if (std::fabs(lu(k, k)) > thr) ++rank;
+  // Eigen counts the pivots above the threshold; with complete pivoting they are the leading ones
+  auto solve = [&](const std::vector<double>& rhs, std::vector<double>& x) {
+    std::vector<double> c(nr);
+    for (int i = 0; i < nr; ++i) c[i] = rhs[rowp[i]];
+    for (int i = 0; i < sd; ++i) for (int l = 0; l < i; ++l) c[i] -= lu(i, l) * c[l];       // unit lower
+    for (int i = sd; i < nr; ++i) for (int l = 0; l < sd; ++l) c[i] -= lu(i, l) * c[l];
+    for (int i = rank - 1; i >= 0; --i) { for (int j = i + 1; j < rank; ++j) c[i] -= lu(i, j) * c[j]; c[i] /= lu(i, i); }
+    x.assign(nu, 0.0);
+    for (int i = 0; i < rank; ++i) x[colp[i]] = c[i];
+  };
+  Px = Mat(nu, nx); Pe.assign(nu, 0.0);
+  std::vector<double> g(nr), y;
+  for (int c = 0; c < nx; ++c) { for (int k = 0; k < nr; ++k) g[k] = C(k, c); solve(g, y); for (int j = 0; j < nu; ++j) Px(j, c) = -y[j]; }
+  solve(e, y); for (int j = 0; j < nu; ++j) Pe[j] = -y[j];
+  // kernel: one basis vector per free (non-pivot) column f: x_f = 1, U11 x_p = -U12 e_f
+  const int m = nu - rank;
+  Pu = Mat(nu, m);
+  for (int s_ = 0; s_ < m; ++s_) {
+    const int f = rank + s_;
+    std::vector<double> xp(rank);
+    for (int i = rank - 1; i >= 0; --i) { double v = -lu(i, f); for (int j = i + 1; j < rank; ++j) v -= lu(i, j) * xp[j]; xp[i] = v / lu(i, i); }
+    for (int i = 0; i < rank; ++i) Pu(colp[i], s_) = xp[i];
+    Pu(colp[f], s_) = 1.0;
+  }
+}
+// 0: Moore-Penrose (default, what the CUDA product implements), 1: FullPivLU emulation (upstream's choice)
+inline int& projection_mode() { static int mode = 0; return mode; }
+inline void project_constraints_dispatch(const Mat& C, const Mat& D, const std::vector<double>& e, Mat& Px, Mat& Pu, std::vector<double>& Pe, int& rank) {
+  if (projection_mode() == 1) project_constraints_fullpivlu(C, D, e, Px, Pu, Pe, rank);
+  else project_constraints(C, D, e, Px, Pu, Pe, rank);
+}
+
 // ---------------------------------------------------------------- node transcription [UPSTREAM multiple_shooting::setupIntermediateNode + projectTranscription]
 inline void setup_intermediate_node(const Problem& P, double t, double dt, int mode, const double* x, const double* u, const double* xnext, NodeLQ& n) {
   const Model& M = *P.M; const int nx = M.nx, nu = M.nu, nj = M.nj;
@@ -471,7 +533,7 @@ inline void setup_intermediate_node(const Problem& P, double t, double dt, int m
   n.perf_dyn = 0; for (int i = 0; i < nx; ++i) n.perf_dyn += n.b[i] * n.b[i]; n.perf_dyn *= dt;
   n.perf_eq = 0; for (double v : n.e) n.perf_eq += v * v; n.perf_eq *= dt;
   // --- projection + change of input variables
-  project_constraints(n.C, n.D, n.e, n.Px, n.Pu, n.Pe, n.rank);
+  project_constraints_dispatch(n.C, n.D, n.e, n.Px, n.Pu, n.Pe, n.rank);
   n.m = nu - n.rank;
   std::vector<double> RPe = matvec(n.R, n.Pe);
   std::vector<double> rr(nu); for (int i = 0; i < nu; ++i) rr[i] = n.r[i] + RPe[i];

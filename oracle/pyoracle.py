@@ -285,6 +285,11 @@ def spline(ts, ps, vs, mid, tf, pf, vf, tq):
     return pos, vel
 
 
+def set_projection_mode(mode: int):
+    """0: Moore-Penrose (default, what the CUDA product implements); 1: emulation of upstream's FullPivLU projection (process-wide)."""
+    lib().orc_set_projection_mode(C.c_int(mode))
+
+
 def project(Cm, D, e):
     L = lib()
     Cm, D, e = _d(Cm), _d(D), _d(e)

@@ -412,3 +412,77 @@ def test_cmd_vel_target_matches_numpy(o, h1_model_path):
     tt, ts = helpers.cmd_vel_target(x, 0.3, (0.3, 0.1, 0.0, 0.2), 1.0, m["com_height"], m["default_joint_state"])
     np.testing.assert_allclose(t, tt)
     np.testing.assert_allclose(s, ts, atol=1e-14)
+
+
+# ------------------------------------------------------------------------------------------------ upstream's FullPivLU projection, emulated
+def _random_stage_constraints(o, mode, seed):
+    """(C, D, e) of one stage at a random state / input, taken from the oracle's own transcription (node_lq)."""
+    rng = np.random.default_rng(seed)
+    x = o.initial_state().copy()
+    x[0:6] = rng.normal(0.0, 0.1, 6)
+    x[9:12] += rng.uniform(-0.1, 0.1, 3)
+    x[12:] += rng.uniform(-0.15, 0.15, o.nx - 12)
+    o.reset(); o.set_dt_horizon(0.01, 0.02)
+    o.set_mode_schedule([-1.0, 5.0], [3, mode, 3]); o.set_target([0.0, 1.0], [x, x])
+    o.run(0.0, x)
+    n = o.node_lq(0)
+    return n["C"], n["D"], n["e"]
+
+
+@pytest.mark.parametrize("mode,rank", [(3, 10), (1, 13), (2, 13)])
+def test_fullpivlu_emulation_properties(o, mode, rank):
+    """The emulation of upstream's luConstraintProjection (Eigen::FullPivLU: kernel + solve) finds the same rank as the default
+    Moore-Penrose projection, its kernel spans the same null space, and its particular solution satisfies a full-rank sub-system
+    exactly while ignoring the dependent stance-foot row."""
+    from oracle import pyoracle
+    Cm, D, e = _random_stage_constraints(o, mode, seed=11 + mode)
+    Px0, Pu0, Pe0, r0 = pyoracle.project(Cm, D, e)
+    pyoracle.set_projection_mode(1)
+    try:
+        Px1, Pu1, Pe1, r1 = pyoracle.project(Cm, D, e)
+    finally:
+        pyoracle.set_projection_mode(0)
+    assert r0 == r1 == rank == np.linalg.matrix_rank(D, tol=1e-9 * np.abs(D).max())
+    assert np.abs(D @ Pu1).max() < 1e-10 * max(1.0, np.abs(D).max())
+    # same null space: the orthogonal projector onto it is the same
+    Q1, _ = np.linalg.qr(Pu1)
+    assert np.abs(Pu0 @ Pu0.T - Q1 @ Q1.T).max() < 1e-9
+    # residual of the particular solutions: Moore-Penrose = least squares (smallest residual), FullPivLU = exact on `rank` rows
+    res0 = D @ Pe0 + e
+    res1 = D @ Pe1 + e
+    assert np.linalg.norm(res0) <= np.linalg.norm(res1) + 1e-12
+    assert np.sum(np.abs(res1) > 1e-9 * max(1.0, np.abs(e).max())) <= D.shape[0] - rank
+    # the two particular solutions differ only inside null(D) plus the part driven by the inconsistency
+    assert np.abs(D @ (Pe1 - Pe0) - (res1 - res0)).max() < 1e-10
+
+
+def test_projection_choice_identical_at_consistent_points_and_small_near_feasibility(h1_model_path):
+    """Quantifies deliberate deviation 1 of DESIGN.md: with the stance feet at rest (config 2, cold start from the initial state) the
+    equality constraints are consistent and both projections give the same solution to rounding; one warm tick later the stance-foot rows are
+    inconsistent at second order only (foot angular velocity x dx) and the solutions agree to 1e-4 relative on cost and to 1e-3 on the inputs."""
+    import helpers
+    from oracle import pyoracle
+    from tools.ingest import read_model
+    m = read_model(h1_model_path)
+    sols = {}
+    for pm in (0, 1):
+        pyoracle.set_projection_mode(pm)
+        try:
+            oo = Oracle(h1_model_path)
+            x0 = oo.initial_state()
+            et, ms = helpers.config2(oo.nx, x0, None, None)
+            tt, ts = helpers.cmd_vel_target(x0, 0.0, (0.3, 0, 0, 0), 1.0, m["com_height"], m["default_joint_state"])
+            oo.reset(); oo.set_dt_horizon(0.01, 1.0); oo.set_mode_schedule(et, ms); oo.set_target(tt, ts)
+            ticks = []
+            for _ in range(2):
+                oo.run(0.0, x0)
+                so, io = oo.solution(), oo.info()
+                ticks.append((np.array(so["x"]), np.array(so["u"]), np.array(so["K"]), np.array(io["after"])))
+            sols[pm] = ticks
+        finally:
+            pyoracle.set_projection_mode(0)
+    (xa, ua, Ka, pa), (xb, ub, Kb, pb) = sols[0][0], sols[1][0]
+    assert np.abs(xa - xb).max() < 1e-10 and np.abs(ua - ub).max() < 1e-9 * np.abs(ua).max() and np.abs(Ka - Kb).max() < 1e-9 * np.abs(Ka).max()
+    (xa, ua, Ka, pa), (xb, ub, Kb, pb) = sols[0][1], sols[1][1]
+    assert abs(pa[0] - pb[0]) < 1e-4 * abs(pa[0]) and abs(pa[2] - pb[2]) < 1e-4      # cost, equality-constraint SSE (the north star's 1e-4)
+    assert np.abs(xa - xb).max() < 1e-3 and np.abs(ua - ub).max() < 1e-3 * np.abs(ua).max()
