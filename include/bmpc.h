@@ -115,7 +115,10 @@ int bmpc_gait_peek(const bmpc_handle* h, int instance, int cap, double* event_ti
  * one MPC tick for all B instances: reference update, LQ approximation, projected Riccati QP, filter line search,
  * feedback policy.  Synchronous; results are available to the getters when it returns. */
 int bmpc_advance(bmpc_handle* h);
-/* same, but only enqueues the work on the library's stream; bmpc_synchronize waits for it */
+/* same, but only enqueues the work on the library's stream; bmpc_synchronize waits for it.
+ * Threading / multiple handles: one thread at a time per handle (as MPC_BASE::run).  All handles of a process share one constant-memory image
+ * of the robot model, refreshed at the start of every tick: ticks of handles that hold DIFFERENT robots must not overlap in time (finish one
+ * handle's tick with bmpc_synchronize before starting the other's); handles of the same robot may overlap freely. */
 int bmpc_advance_async(bmpc_handle* h);
 int bmpc_synchronize(bmpc_handle* h);
 
