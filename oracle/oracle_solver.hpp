@@ -428,7 +428,7 @@ inline void project_constraints_fullpivlu(const Mat& C, const Mat& D, const std:
   double maxpivot = 0.0; int nonzero = sd;
   for (int k = 0; k < sd; ++k) {
     int br = k, bc = k; double big = -1.0;
-    for (int i = k; i < nr; ++i) for (int j = k; j < nu; ++j) if (std::fabs(lu(i, j)) > big) { big = std::fabs(lu(i, j)); br = i; bc = j; }
+    for (int j = k; j < nu; ++j) for (int i = k; i < nr; ++i) if (std::fabs(lu(i, j)) > big) { big = std::fabs(lu(i, j)); br = i; bc = j; }   // first maximum in column-major order, as Eigen's maxCoeff visitor on a column-major matrix
     if (big == 0.0) { nonzero = k; break; }
     maxpivot = std::max(maxpivot, big);
     if (br != k) { for (int j = 0; j < nu; ++j) std::swap(lu(k, j), lu(br, j)); std::swap(rowp[k], rowp[br]); }
