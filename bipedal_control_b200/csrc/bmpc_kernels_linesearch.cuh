@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(64, LS2_BLOCKS) k_linesearch_eval2(Dev d) {
 template <int NJ>
 __global__ void __launch_bounds__(128) k_accept(Dev d) {
   constexpr int NX = Dims<NJ>::NX;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // broadcast: lets the compiler treat the warp index as warp-uniform
   const int b = blockIdx.x * 4 + warp;
   if (b >= d.B) return;
   if (d.done[b]) return;

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(128, 4) k_policy_expand(Dev d) {
   using D = Dims<NJ>; using R = RDims<NJ>; using S = SDims<NJ>; using PS = PolSmem<NJ>;
   constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, MP = S::MP, WPB = 4, NT = PS::NT, LDK = PS::LDK, NTILES = 3 * NT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // broadcast: lets the compiler treat the warp index as warp-uniform
   PS& sm = reinterpret_cast<PS*>(smem_raw)[warp];
   const int gw = blockIdx.x * WPB + warp;
   const int b = gw / d.NS, k = gw % d.NS;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(128) k_forward(Dev d) {
   constexpr int NX = D::NX, NU = D::NU, WPB = 4, LDP = FS::LDP;
   constexpr int NPH = (NX * NX + 31) / 32, NK = (NU * NX + 31) / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // broadcast: lets the compiler treat the warp index as warp-uniform
   FS& sm = reinterpret_cast<FS*>(smem_raw)[warp];
   const int b = blockIdx.x * WPB + warp;
   if (b >= d.B) return;

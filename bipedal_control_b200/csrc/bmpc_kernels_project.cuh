@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
   for (int i = threadIdx.x; i < 16 * LDR; i += 128) { const int rr_ = i / LDR, cc_ = i % LDR; sRjP[rr_][cc_] = (rr_ < NJ && cc_ < NJ) ? c_model.Rjoint[rr_ * NJ + cc_] : 0.0; }
   if (threadIdx.x < 24) sQd[threadIdx.x] = threadIdx.x < NX ? c_model.Qdiag[threadIdx.x] : 0.0;
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // broadcast: lets the compiler treat the warp index as warp-uniform
   const int gw = blockIdx.x * WPB + warp;
   const int b = gw / d.NS, k = gw % d.NS;
   if (b >= d.B) return;

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(WS_THREADS, 4) k_riccati(Dev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
   const int b = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int N = d.n_nodes[b] - 1;
   const size_t nb = (size_t)b * d.NS;
   const double imass = 1.0 / c_model.total_mass;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(32 * RIC_WPC, RIC_BLOCKS) k_riccati_warp(Dev d
   constexpr int NX = D::NX, MP = S::MP, LDA = S::LDA, LDH = SM::LDH;
   constexpr unsigned TMA_BYTES = S::TMA_DOUBLES * sizeof(double);
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // broadcast: lets the compiler treat the warp index as warp-uniform
   const int b = blockIdx.x * RIC_WPC + warp;
   if (b >= d.B) return;
   SM& sm = reinterpret_cast<SM*>(smem_raw)[warp];
