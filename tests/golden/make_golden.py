@@ -13,6 +13,7 @@ Cases (inputs are stored next to the outputs, so a test needs nothing but the .n
   h1_trot_n100       BASELINE configs[1]: H1 'trot', dt 0.01, horizon 1.0 (103 stages), cold tick + warm tick
   h1_random4         BASELINE configs[2] distributions, instances 0, 1, 4, 6 of seed 0 (one per gait), cold tick + warm tick
   g1_trot_n100       BASELINE configs[3]: G1 'trot', dt 0.01, horizon 1.0
+  h1_random4_fullpivlu  the h1_random4 instances solved with the oracle's emulation of upstream's FullPivLU projection (fixture for the next round)
 Gains are stored for a subset of nodes (first 4, every 10th, last) to keep the files small.
 """
 import os
@@ -102,6 +103,22 @@ def main():
         blob.update({f"i{b}_{k}": v for k, v in out.items()})
         print("h1_random4", b, gait[b], "nodes", len(out["t0_times"]), "step", out["t1_perf"][6])
     np.savez_compressed(os.path.join(HERE, "h1_random4.npz"), **blob)
+
+    # the same four instances with the emulation of upstream's FullPivLU projection (oracle test switch): fixtures for the CUDA
+    # implementation of that projection planned for the next round (deviation 1); first tick only, no gains
+    from oracle import pyoracle
+    pyoracle.set_projection_mode(1)
+    try:
+        blob = dict(instances=np.array(picks, dtype=np.int32), dt=0.01, horizon=1.0)
+        for b in picks:
+            et, ms = helpers.tiled_schedule(gait[b], phase[b])
+            tt, ts = helpers.cmd_vel_target(X0[b], 0.0, cmd[b], 1.0, m["com_height"], dj)
+            out = run_case(h1, 0.01, 1.0, et, ms, tt, ts, X0[b], ticks=1)
+            blob.update({f"i{b}_event_times": et, f"i{b}_mode_sequence": ms, f"i{b}_target_times": tt, f"i{b}_target_states": ts, f"i{b}_x0": X0[b]})
+            blob.update({f"i{b}_{k}": v for k, v in out.items() if not k.endswith("_K") and not k.endswith("gain_nodes")})
+        np.savez_compressed(os.path.join(HERE, "h1_random4_fullpivlu.npz"), **blob)
+    finally:
+        pyoracle.set_projection_mode(0)
 
 
 if __name__ == "__main__":
