@@ -486,3 +486,66 @@ def test_projection_choice_identical_at_consistent_points_and_small_near_feasibi
     (xa, ua, Ka, pa), (xb, ub, Kb, pb) = sols[0][1], sols[1][1]
     assert abs(pa[0] - pb[0]) < 1e-4 * abs(pa[0]) and abs(pa[2] - pb[2]) < 1e-4      # cost, equality-constraint SSE (the north star's 1e-4)
     assert np.abs(xa - xb).max() < 1e-3 and np.abs(ua - ub).max() < 1e-3 * np.abs(ua).max()
+
+
+@pytest.mark.parametrize("mode", [3, 1, 2, 0])
+def test_complete_pivoting_on_joint_block_equals_fullpivlu_on_stacked_rows(o, mode):
+    """Design check for the CUDA FullPivLU projection (tools/candidates/r2_fullpivlu.patch): the zero-force rows of open contacts are identity
+    rows on columns the velocity rows never touch, so Gaussian elimination with complete pivoting of the joint block Dv alone (what one warp does:
+    lane = joint column) gives the same Px / Pe joint rows as the oracle's FullPivLU emulation on the full stacked D of the stage."""
+    from oracle import pyoracle
+    Cm, D, e = _random_stage_constraints(o, mode, seed=5 + mode)
+    nu = D.shape[1]; nj = nu - 12
+    vel = [i for i in range(D.shape[0]) if np.abs(D[i, :12]).max() == 0.0]
+    n_open = (D.shape[0] - len(vel)) // 3
+    A = D[vel][:, 12:].copy(); Cv = Cm[vel]; ev = e[vel]
+    nr = A.shape[0]
+    rowid = list(range(nr)); colp = []; used = [False] * nj; piv = []
+    for k in range(min(nr, nj)):
+        best, bl, bi = -1.0, None, None
+        for l in range(nj):            # first maximum in column-major order over the columns that are not pivots yet
+            if used[l]:
+                continue
+            for i in range(k, nr):
+                if abs(A[i, l]) > best:
+                    best, bl, bi = abs(A[i, l]), l, i
+        if not best > 0.0:
+            break
+        A[[k, bi], :] = A[[bi, k], :]; rowid[k], rowid[bi] = rowid[bi], rowid[k]
+        p = A[k, bl]; piv.append(abs(p))
+        for i in range(k + 1, nr):
+            f = A[i, bl] / p
+            for l in range(nj):
+                if l == bl:
+                    A[i, l] = f
+                elif not used[l]:
+                    A[i, l] -= f * A[k, l]
+        used[bl] = True; colp.append(bl)
+    thr = np.finfo(float).eps * min(D.shape[0], nu) * max([1.0 if n_open else 0.0] + piv)
+    rank = sum(1 for p in piv if p > thr)
+
+    def solve(rhs):
+        g = np.array([rhs[rowid[i]] for i in range(nr)], dtype=float)
+        for i in range(1, rank):
+            for l in range(i):
+                g[i] -= A[i, colp[l]] * g[l]
+        for i in range(rank - 1, -1, -1):
+            s = g[i]
+            for j in range(i + 1, rank):
+                s -= A[i, colp[j]] * g[j]
+            g[i] = s / A[i, colp[i]]
+        x = np.zeros(nj)
+        for i in range(rank):
+            x[colp[i]] = g[i]
+        return x
+
+    Pxj = -np.stack([solve(Cv[:, c]) for c in range(Cm.shape[1])], axis=1)
+    Pej = -solve(ev)
+    pyoracle.set_projection_mode(1)
+    try:
+        Px1, Pu1, Pe1, r1 = pyoracle.project(Cm, D, e)
+    finally:
+        pyoracle.set_projection_mode(0)
+    assert r1 == rank + 3 * n_open
+    scale = max(1.0, np.abs(Px1).max())
+    assert np.abs(Px1[12:] - Pxj).max() < 1e-11 * scale and np.abs(Pe1[12:] - Pej).max() < 1e-11 * max(1.0, np.abs(Pe1).max())
