@@ -1,14 +1,26 @@
 // libbmpc.so: C ABI (include/bmpc.h) + host orchestration of one batched MPC tick on one B200.
 //
 // Host-side mirror of ocs2::MPC_BASE::run / SolverBase::run / SqpSolver::runImpl [UPSTREAM] as driven by
-// MPC_MRT_Interface::advanceMpc (bipedal_controllers/src/BipedalController.cpp:332-351).
+// MPC_MRT_Interface::advanceMpc (bipedal_controllers/src/BipedalController.cpp:332-351), and of the MRT side
+// (updatePolicy / evaluatePolicy, BipedalController.cpp:191-206) that reads the policy while the MPC thread solves.
+//
+// Threading model (mirrors MPC_MRT_Interface [UPSTREAM]: one MPC thread, one real-time reader, callback threads that set references):
+//   * a tick reads policy buffer `cur` (warm start) and writes buffer 1 - cur on the compute stream; nothing a getter can see changes
+//     until the tick is PUBLISHED (cur flips) -- by bmpc_synchronize, or lazily by the first getter that finds the tick finished
+//     (MRT_BASE::updatePolicy semantics);
+//   * getters (bmpc_get_policy, bmpc_evaluate_policy, bmpc_get_performance, bmpc_get_status) serve buffer `cur` on a second stream and never
+//     wait for a tick in flight; a reader count per buffer keeps the next tick from overwriting a buffer that is being copied;
+//   * set_* calls copy into pinned staging under the handle mutex; the tick uploads staging at its start and set_* waits for that upload
+//     (microseconds) before touching staging again.
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -25,20 +37,44 @@ using namespace bmpc;
 
 namespace {
 std::string g_create_error;
+std::mutex g_create_mtx;
 
 struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) throw CudaError(std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #call); } while (0)
 
-template <class T> T* dalloc(size_t n) { T* p = nullptr; CK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T))); CK(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T))); return p; }
-template <class T> T* halloc(size_t n) { T* p = nullptr; CK(cudaMallocHost(&p, std::max<size_t>(n, 1) * sizeof(T))); std::memset(p, 0, std::max<size_t>(n, 1) * sizeof(T)); return p; }
+// All handles of a process share ONE __constant__ image of the robot model per device.  The image is tagged with a hash of its content; a tick
+// whose model differs from the resident image first waits for every tick in flight on that device, then uploads its own (handles of the same
+// robot never wait; handles of different robots are serialised, not corrupted).
+std::mutex g_image_mtx;
+unsigned long long g_image_id[64] = {};
+
+unsigned long long fnv1a(const void* p, size_t n) {
+  const unsigned char* b = static_cast<const unsigned char*>(p);
+  unsigned long long h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return h ? h : 1ull;
+}
+
+struct DevPool {   // every device / pinned allocation of a handle, so that a failing bmpc_create cannot leak
+  std::vector<void*> dev, host;
+  template <class T> T* d(size_t n) { T* p = nullptr; n = std::max<size_t>(n, 1); CK(cudaMalloc(&p, n * sizeof(T))); dev.push_back(p); CK(cudaMemset(p, 0, n * sizeof(T))); return p; }
+  template <class T> T* h(size_t n) { T* p = nullptr; n = std::max<size_t>(n, 1); CK(cudaMallocHost(&p, n * sizeof(T))); host.push_back(p); std::memset(p, 0, n * sizeof(T)); return p; }
+  void release() { for (void* p : dev) cudaFree(p); for (void* p : host) cudaFreeHost(p); dev.clear(); host.clear(); }
+};
 }  // namespace
 
 struct bmpc_handle {
-  HostModel model;
+  HostModel model; unsigned long long model_id = 0;
   int B = 0, NS = 0, ME = 0, TP = 0, nj = 0, nx = 0, nu = 0, device = 0, sqp_iterations = 1;
   double dt = 0, horizon = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, io_stream = nullptr;
+  cudaEvent_t ev_done = nullptr, ev_inputs = nullptr;
   std::string err;
+  DevPool pool;
+  // synchronisation (see the header comment)
+  std::mutex mtx, eval_mtx; std::condition_variable cv; int readers[2] = {0, 0};
+  bool pending = false, upload_inflight = false;
+  int last_rc = BMPC_OK;
   // inputs (device) and their pinned staging copies
   double *d_t0 = nullptr, *d_x0 = nullptr, *d_tgt_t = nullptr, *d_tgt_x = nullptr, *d_ev_t = nullptr;
   int *d_n_ev = nullptr, *d_ev_mode = nullptr;
@@ -49,22 +85,25 @@ struct bmpc_handle {
   // node grid work arrays
   double *d_st_t = nullptr, *d_st_dt = nullptr, *d_xref = nullptr, *d_zref = nullptr;
   int* d_st_mode = nullptr;
-  // primal solutions (double buffered)
+  // primal solutions (double buffered), with the mode schedule and the performance / status of the tick that produced them
   int* s_n[2] = {nullptr, nullptr}; int* s_ev[2] = {nullptr, nullptr};
   double *s_t[2] = {nullptr, nullptr}, *s_x[2] = {nullptr, nullptr}, *s_u[2] = {nullptr, nullptr}, *s_uff[2] = {nullptr, nullptr}, *s_K[2] = {nullptr, nullptr};
+  int* s_nev[2] = {nullptr, nullptr}; double* s_evt[2] = {nullptr, nullptr}; int* s_evm[2] = {nullptr, nullptr};
+  double* s_perf[2] = {nullptr, nullptr}; int* s_status[2] = {nullptr, nullptr};
   int cur = 0; bool have_solution = false;
   // work
-  double *d_lq = nullptr, *d_proj = nullptr, *d_stage = nullptr, *d_ric = nullptr, *d_base = nullptr, *d_dx = nullptr, *d_du = nullptr, *d_perf_trial = nullptr, *d_perf = nullptr, *d_alpha = nullptr, *d_norms = nullptr;
-  int *d_done = nullptr, *d_status = nullptr, *d_counters = nullptr;
+  double *d_lq = nullptr, *d_proj = nullptr, *d_stage = nullptr, *d_ric = nullptr, *d_dx = nullptr, *d_du = nullptr, *d_norms = nullptr;
+  int* d_counters = nullptr;
   int* h_counters = nullptr;
-  size_t rec = 0, prec = 0, krec = 0, srec = 0, brec = 0; int lq_mode = 3, riccati_mode = 1, ls_mode = 1;   // 0: k_lq, 1: k_model_base + k_lq_assemble, 2: fused warp-cooperative, 3: packed fused, 3 (H1) / 2 (G1) stages per warp (default)
+  size_t rec = 0, prec = 0, krec = 0, srec = 0;
+  int projection_mode = 1;   // 1: upstream's FullPivLU projection (default), 0: Moore-Penrose (Householder QR on per-foot compressed rows)
   // gait bookkeeping
   std::vector<GaitSchedule> gaits; bool use_gait = false;
   // stats
   int launches = 0; bool timing = false; cudaEvent_t tev[10] = {}; float phase_ms[9] = {};
-  int linesearch_trials = 0;
-  // scratch for policy evaluation
-  double *d_default_joints = nullptr, *d_cmd = nullptr, *d_jc = nullptr;
+  int linesearch_trials = 0, max_trials = 0, failed_instances = 0, status_or = 0;
+  // scratch for policy evaluation / rollout
+  double *d_default_joints = nullptr, *d_jc = nullptr;
   double *d_eval_t = nullptr, *d_eval_x = nullptr, *d_eval_xo = nullptr, *d_eval_uo = nullptr; int* d_eval_m = nullptr;
 };
 
@@ -80,92 +119,135 @@ Dev make_dev(bmpc_handle* h) {
   d.n_nodes = h->s_n[w]; d.node_t = h->s_t[w]; d.node_ev = h->s_ev[w];
   d.st_t = h->d_st_t; d.st_dt = h->d_st_dt; d.st_mode = h->d_st_mode; d.xref = h->d_xref; d.zref = h->d_zref;
   d.p_n = h->have_solution ? h->s_n[h->cur] : nullptr; d.p_t = h->s_t[h->cur]; d.p_x = h->s_x[h->cur]; d.p_u = h->s_u[h->cur];
+  d.p_ev = h->s_ev[h->cur]; d.p_uff = h->s_uff[h->cur]; d.p_K = h->s_K[h->cur];
   d.s_x = h->s_x[w]; d.s_u = h->s_u[w]; d.s_uff = h->s_uff[w]; d.s_K = h->s_K[w];
-  d.lq = h->d_lq; d.proj = h->d_proj; d.stage = h->d_stage; d.ric = h->d_ric; d.base = h->d_base; d.jc = h->d_jc; d.dx = h->d_dx; d.du = h->d_du;
-  d.perf_trial = h->d_perf_trial; d.perf = h->d_perf; d.alpha = h->d_alpha; d.norms = h->d_norms; d.done = h->d_done; d.status = h->d_status; d.counters = h->d_counters;
+  d.lq = h->d_lq; d.proj = h->d_proj; d.stage = h->d_stage; d.ric = h->d_ric; d.jc = h->d_jc; d.dx = h->d_dx; d.du = h->d_du;
+  d.perf = h->s_perf[w]; d.norms = h->d_norms; d.status = h->s_status[w]; d.counters = h->d_counters;
   return d;
 }
 
-template <int NJ>
-void tick(bmpc_handle* h) {
-  using D = Dims<NJ>; using R = RDims<NJ>;
-  cudaStream_t st = h->stream;
-  const int B = h->B, NS = h->NS;
-  auto mark = [&](int i) { if (h->timing) CK(cudaEventRecord(h->tev[i], st)); };
-  h->launches = 0;
-  CK(cudaMemcpyToSymbolAsync(c_model, &h->model.dev, sizeof(DevModel), 0, cudaMemcpyHostToDevice, st));
-  // stage inputs
-  if (h->obs_dirty) { CK(cudaMemcpyAsync(h->d_t0, h->h_t0, sizeof(double) * B, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(h->d_x0, h->h_x0, sizeof(double) * B * h->nx, cudaMemcpyHostToDevice, st)); h->obs_dirty = false; }
-  if (h->tgt_dirty) { CK(cudaMemcpyAsync(h->d_tgt_t, h->h_tgt_t, sizeof(double) * B * h->TP, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(h->d_tgt_x, h->h_tgt_x, sizeof(double) * B * h->TP * h->nx, cudaMemcpyHostToDevice, st)); h->tgt_dirty = false; }
+void upload_inputs(bmpc_handle* h) {   // pinned staging -> device, on the compute stream; caller holds h->mtx
+  cudaStream_t st = h->stream; const int B = h->B;
+  bool any = false;
+  if (h->obs_dirty) { CK(cudaMemcpyAsync(h->d_t0, h->h_t0, sizeof(double) * B, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(h->d_x0, h->h_x0, sizeof(double) * B * h->nx, cudaMemcpyHostToDevice, st)); h->obs_dirty = false; any = true; }
+  if (h->tgt_dirty) { CK(cudaMemcpyAsync(h->d_tgt_t, h->h_tgt_t, sizeof(double) * B * h->TP, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(h->d_tgt_x, h->h_tgt_x, sizeof(double) * B * h->TP * h->nx, cudaMemcpyHostToDevice, st)); h->tgt_dirty = false; any = true; }
   if (h->sched_dirty) {
     CK(cudaMemcpyAsync(h->d_n_ev, h->h_n_ev, sizeof(int) * B, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_ev_t, h->h_ev_t, sizeof(double) * B * h->ME, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_ev_mode, h->h_ev_mode, sizeof(int) * B * (h->ME + 1), cudaMemcpyHostToDevice, st));
-    h->sched_dirty = false;
+    h->sched_dirty = false; any = true;
   }
-  CK(cudaMemsetAsync(h->d_status, 0, sizeof(int) * B, st));
+  if (any) { CK(cudaEventRecord(h->ev_inputs, st)); h->upload_inflight = true; }
+}
+// before the host overwrites pinned staging: the previous upload must have left it (caller holds h->mtx)
+void staging_ready(bmpc_handle* h) { if (h->upload_inflight) { CK(cudaEventSynchronize(h->ev_inputs)); h->upload_inflight = false; } }
+
+template <int NJ>
+void set_kernel_attributes() {
+  CK(cudaFuncSetAttribute(k_riccati_warp<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RIC_WPC * sizeof(RicWarpSmem<NJ>))));
+  CK(cudaFuncSetAttribute(k_riccati_warp<NJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_lq_pack<NJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LqPackSmem<NJ>)));
+  CK(cudaFuncSetAttribute(k_lq_pack<NJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LqPackSmem<NJ>)));
+  CK(cudaFuncSetAttribute(k_policy_expand<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(PolSmem<NJ>))));
+  CK(cudaFuncSetAttribute(k_forward<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(FwdSmem<NJ>))));
+}
+
+// the model image this handle's kernels read (see g_image_mtx)
+void ensure_model_image(bmpc_handle* h) {
+  std::lock_guard<std::mutex> lk(g_image_mtx);
+  const int dev = h->device & 63;
+  if (g_image_id[dev] == h->model_id) return;
+  CK(cudaDeviceSynchronize());   // ticks of handles that hold another robot finish on the old image first
+  CK(cudaMemcpyToSymbol(c_model, &h->model.dev, sizeof(DevModel), 0, cudaMemcpyHostToDevice));
+  g_image_id[dev] = h->model_id;
+}
+
+// enqueue one tick on the compute stream; caller holds h->mtx, no tick pending, no reader on the buffer about to be written
+template <int NJ>
+void tick(bmpc_handle* h) {
+  cudaStream_t st = h->stream;
+  const int B = h->B, NS = h->NS, w = 1 - h->cur;
+  auto mark = [&](int i) { if (h->timing) CK(cudaEventRecord(h->tev[i], st)); };
+  h->launches = 0;
+  ensure_model_image(h);
+  upload_inputs(h);
+  CK(cudaMemsetAsync(h->s_status[w], 0, sizeof(int) * B, st));
+  CK(cudaMemsetAsync(h->d_counters, 0, sizeof(int) * CNT_N, st));
+  // the mode schedule this policy is solved with travels with the policy buffer (evaluatePolicy reports the mode from it)
+  CK(cudaMemcpyAsync(h->s_nev[w], h->d_n_ev, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(h->s_evt[w], h->d_ev_t, sizeof(double) * B * h->ME, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(h->s_evm[w], h->d_ev_mode, sizeof(int) * B * (h->ME + 1), cudaMemcpyDeviceToDevice, st));
   Dev d = make_dev(h);
   const int nodes = B * NS;
   mark(0);
   k_time_grid<<<(B + 127) / 128, 128, 0, st>>>(d); ++h->launches;
   k_node_setup<NJ><<<(nodes + 127) / 128, 128, 0, st>>>(d); ++h->launches;
   mark(1);
-  CK(cudaFuncSetAttribute(k_riccati<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicSmem<NJ>)));
-  CK(cudaFuncSetAttribute(k_riccati<NJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(k_riccati_warp<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RIC_WPC * sizeof(RicWarpSmem<NJ>))));
-  CK(cudaFuncSetAttribute(k_riccati_warp<NJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(k_lq_pack<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LqPackSmem<NJ>)));
-  CK(cudaFuncSetAttribute(k_policy_expand<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(PolSmem<NJ>))));
-  CK(cudaFuncSetAttribute(k_forward<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(FwdSmem<NJ>))));
-  h->linesearch_trials = 0;
   for (int iter = 0; iter < h->sqp_iterations; ++iter) {
-    if (h->lq_mode == 3) {
-      constexpr int G = LqPackSmem<NJ>::G;
-      const int NP = (NS + G - 1) / G;
-      k_lq_pack<NJ><<<(B * NP + 3) / 4, 128, sizeof(LqPackSmem<NJ>), st>>>(d); ++h->launches;
-    } else if (h->lq_mode == 4) {
-      constexpr int G = LqPackSmem<NJ>::G;
-      const int NP = (NS + G - 1) / G;
-      k_base_pack<NJ><<<(B * NP + 3) / 4, 128, 0, st>>>(d); ++h->launches;
-      k_lq_assemble<NJ, false><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches;
-    } else if (h->lq_mode == 2) { k_lq_assemble<NJ, true><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches; }
-    else if (h->lq_mode == 1) {
-      k_model_base<NJ><<<(nodes + 63) / 64, 64, 0, st>>>(d); ++h->launches;
-      k_lq_assemble<NJ, false><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches;
-    } else { k_lq<NJ><<<(nodes + 63) / 64, 64, 0, st>>>(d); ++h->launches; }
+    constexpr int G = LqPackSmem<NJ>::G;
+    const int NP = (NS + G - 1) / G;
+    if (h->projection_mode == 1) k_lq_pack<NJ, true><<<(B * NP + 3) / 4, 128, sizeof(LqPackSmem<NJ>), st>>>(d);
+    else k_lq_pack<NJ, false><<<(B * NP + 3) / 4, 128, sizeof(LqPackSmem<NJ>), st>>>(d);
+    ++h->launches;
     if (iter == 0) mark(2);
-    k_project<NJ><<<(nodes + 3) / 4, 128, 0, st>>>(d); ++h->launches;
+    if (h->projection_mode == 1) k_project<NJ, true><<<(nodes + 3) / 4, 128, 0, st>>>(d);     // upstream's FullPivLU projection
+    else k_project<NJ, false><<<(nodes + 3) / 4, 128, 0, st>>>(d);                            // Moore-Penrose
+    ++h->launches;
     if (iter == 0) mark(3);
-    if (h->riccati_mode == 1) { k_riccati_warp<NJ><<<(B + RIC_WPC - 1) / RIC_WPC, 32 * RIC_WPC, RIC_WPC * sizeof(RicWarpSmem<NJ>), st>>>(d); ++h->launches; }   // one warp per instance (default)
-    else { k_riccati<NJ><<<B, WS_THREADS, sizeof(RicSmem<NJ>), st>>>(d); ++h->launches; }                                        // one CTA per instance
+    k_riccati_warp<NJ><<<(B + RIC_WPC - 1) / RIC_WPC, 32 * RIC_WPC, RIC_WPC * sizeof(RicWarpSmem<NJ>), st>>>(d); ++h->launches;
     if (iter == 0) mark(4);
     k_policy_expand<NJ><<<(nodes + 3) / 4, 128, 4 * sizeof(PolSmem<NJ>), st>>>(d); ++h->launches;
     if (iter == 0) mark(5);
     k_forward<NJ><<<(B + 3) / 4, 128, 4 * sizeof(FwdSmem<NJ>), st>>>(d); ++h->launches;
     if (iter == 0) mark(6);
-    // filter line search: all instances try alpha = 1 first; the rejected ones halve their step
-    for (int trial = 0; trial < 16; ++trial) {
-      CK(cudaMemsetAsync(h->d_counters, 0, sizeof(int), st));
-      if (h->ls_mode == 1) { k_linesearch_eval2<NJ><<<(nodes + 63) / 64, 64, 0, st>>>(d); ++h->launches; }   // streaming register-only flow map (default)
-      else { k_linesearch_eval<NJ><<<(nodes + 63) / 64, 64, 0, st>>>(d); ++h->launches; }
-      k_accept<NJ><<<(B + 3) / 4, 128, 0, st>>>(d); ++h->launches;
-      ++h->linesearch_trials;
-      CK(cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      if (h->h_counters[0] == 0) break;
-    }
+    // filter line search (device-side backtracking loop, one CTA per instance) + step + policy completion
+    k_linesearch<NJ><<<B, LS_THREADS, 0, st>>>(d, iter == h->sqp_iterations - 1 ? 1 : 0); ++h->launches;
     if (iter == 0) mark(7);
-    k_update<NJ><<<(unsigned)(((size_t)nodes * Dims<NJ>::NX + 255) / 256), 256, 0, st>>>(d); ++h->launches;
   }
-  k_policy_fill<NJ><<<B, 128, 0, st>>>(d); ++h->launches;
   mark(8);
+  CK(cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int) * CNT_N, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(h->ev_done, st));
   CK(cudaGetLastError());
-  h->cur = 1 - h->cur; h->have_solution = true;
-  (void)sizeof(D); (void)sizeof(R);
+  h->pending = true;
 }
+
+// the tick in flight has finished: make its policy the current one (caller holds h->mtx)
+void publish(bmpc_handle* h) {
+  h->cur = 1 - h->cur; h->have_solution = true; h->pending = false;
+  h->linesearch_trials = h->h_counters[CNT_TRIALS]; h->max_trials = h->h_counters[CNT_MAXTRIALS];
+  h->failed_instances = h->h_counters[CNT_FAIL]; h->status_or = h->h_counters[CNT_STATUS];
+  if (h->timing) for (int i = 0; i < 8; ++i) cudaEventElapsedTime(&h->phase_ms[i], h->tev[i], h->tev[i + 1]);
+  h->last_rc = BMPC_OK;
+  if (h->status_or & 32) { h->last_rc = BMPC_ERR_CAPACITY; h->err = "[bmpc] time grid overflow: more event nodes inside the horizon than max_event_nodes (status bit 32)"; }
+  else if (h->status_or & 4) { h->last_rc = BMPC_ERR_INVALID; h->err = "[bmpc] swing phase without lift-off / touch-down time in the mode schedule (status bit 4)"; }
+  else if (h->failed_instances > 0) { h->last_rc = BMPC_ERR_NUMERIC; h->err = "[bmpc] " + std::to_string(h->failed_instances) + " instance(s) failed numerically (see bmpc_get_status); their policies are open loop"; }
+}
+void try_publish(bmpc_handle* h) { if (h->pending && cudaEventQuery(h->ev_done) == cudaSuccess) publish(h); }
+// wait for the tick in flight (if any) and publish it; lk is released while waiting so that getters keep being served
+void wait_and_publish(bmpc_handle* h, std::unique_lock<std::mutex>& lk) {
+  while (h->pending) {
+    lk.unlock();
+    const cudaError_t e = cudaEventSynchronize(h->ev_done);
+    lk.lock();
+    if (e != cudaSuccess) { h->pending = false; throw CudaError(std::string("CUDA: ") + cudaGetErrorString(e) + " while waiting for the tick"); }
+    if (h->pending && cudaEventQuery(h->ev_done) == cudaSuccess) publish(h);
+  }
+}
+
+struct ReadGuard {   // pins the current policy buffer while a getter copies from it
+  bmpc_handle* h; int c;
+  explicit ReadGuard(bmpc_handle* h_) : h(h_) {
+    std::lock_guard<std::mutex> lk(h->mtx);
+    try_publish(h);
+    if (!h->have_solution) throw std::invalid_argument("[bmpc] no solution yet");
+    c = h->cur; ++h->readers[c];
+  }
+  ~ReadGuard() { { std::lock_guard<std::mutex> lk(h->mtx); --h->readers[c]; } h->cv.notify_all(); }
+};
 
 void compute_gait_schedules(bmpc_handle* h) {
   if (!h->have_obs) throw std::invalid_argument("[bmpc] gait schedule mode needs host observations (bmpc_set_observations)");
+  staging_ready(h);
   const int B = h->B, ME = h->ME;
   for (int b = 0; b < B; ++b) {
     const double t0 = h->h_t0[b], tf = t0 + h->horizon;
@@ -180,13 +262,37 @@ void compute_gait_schedules(bmpc_handle* h) {
   h->sched_dirty = true; h->have_sched = true;
 }
 
-int fail(bmpc_handle* h, int code, const std::string& msg) { if (h) h->err = msg; else g_create_error = msg; return code; }
+GaitSchedule initial_gait(const bmpc_handle* h) {
+  // per-instance gait schedules start from reference.info's initialModeSchedule / defaultModeSequenceTemplate (BipedalRobotInterface.cpp:209-234)
+  GaitSchedule g0; g0.ms.eventTimes = h->model.init_events; g0.ms.modeSequence = h->model.init_modes; g0.tmpl = h->model.default_template;
+  g0.phaseTransitionStanceTime = h->model.phase_transition_stance_time;
+  return g0;
+}
+
+int fail(bmpc_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else { std::lock_guard<std::mutex> lk(g_create_mtx); g_create_error = msg; }
+  return code;
+}
 
 #define API_BEGIN try {
 #define API_END(h) } catch (const CudaError& e) { return fail(h, BMPC_ERR_CUDA, e.what()); } \
   catch (const std::invalid_argument& e) { return fail(h, BMPC_ERR_INVALID, e.what()); } \
   catch (const std::length_error& e) { return fail(h, BMPC_ERR_CAPACITY, e.what()); } \
   catch (const std::exception& e) { return fail(h, BMPC_ERR_INVALID, e.what()); }
+
+void destroy_impl(bmpc_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->io_stream) cudaStreamSynchronize(h->io_stream);
+  h->pool.release();
+  for (auto& e : h->tev) if (e) cudaEventDestroy(e);
+  if (h->ev_done) cudaEventDestroy(h->ev_done);
+  if (h->ev_inputs) cudaEventDestroy(h->ev_inputs);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->io_stream) cudaStreamDestroy(h->io_stream);
+  delete h;
+}
 
 }  // namespace
 
@@ -208,6 +314,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     else if (cfg->task_file && cfg->urdf_file && cfg->reference_file)
       h->model = load_reference_files(cfg->task_file, cfg->reference_file, cfg->gait_file ? cfg->gait_file : "", cfg->urdf_file);
     else throw std::invalid_argument("[bmpc] either model_file or task_file + reference_file + urdf_file must be given");
+    h->model_id = fnv1a(&h->model.dev, sizeof(DevModel));
     h->device = cfg->device;
     h->B = cfg->batch; h->nj = h->model.nj; h->nx = h->model.nx; h->nu = h->model.nu;
     h->dt = cfg->dt > 0 ? cfg->dt : h->model.sqp_dt;
@@ -215,34 +322,41 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     h->ME = cfg->max_events > 0 ? cfg->max_events : 40;
     h->TP = cfg->max_target_points > 0 ? cfg->max_target_points : 4;
     h->sqp_iterations = cfg->sqp_iterations > 0 ? cfg->sqp_iterations : h->model.sqp_iterations;
-    h->NS = (int)std::ceil(h->horizon / h->dt - 1e-9) + 1 + 16;   // nominal grid + up to 16 event nodes inside the horizon
+    const int max_event_nodes = cfg->max_event_nodes > 0 ? cfg->max_event_nodes : 16;
+    h->NS = (int)std::ceil(h->horizon / h->dt - 1e-9) + 1 + max_event_nodes;   // nominal grid + event nodes inside the horizon (two per event off the grid, one per event on it)
     const size_t B = h->B, NS = h->NS, nx = h->nx, nu = h->nu;
-    if (h->nj == 10) { h->rec = Dims<10>::REC; h->prec = Dims<10>::PREC; h->krec = RDims<10>::KREC; h->srec = SDims<10>::SREC; h->brec = 2 * BaseDims<10>::BASE; }
-    else { h->rec = Dims<12>::REC; h->prec = Dims<12>::PREC; h->krec = RDims<12>::KREC; h->srec = SDims<12>::SREC; h->brec = 2 * BaseDims<12>::BASE; }
+    if (h->nj == 10) { h->rec = Dims<10>::REC; h->prec = Dims<10>::PREC; h->krec = RDims<10>::KREC; h->srec = SDims<10>::SREC; set_kernel_attributes<10>(); }
+    else { h->rec = Dims<12>::REC; h->prec = Dims<12>::PREC; h->krec = RDims<12>::KREC; h->srec = SDims<12>::SREC; set_kernel_attributes<12>(); }
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->io_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_inputs, cudaEventDisableTiming));
     for (auto& e : h->tev) CK(cudaEventCreate(&e));
-    h->d_t0 = dalloc<double>(B); h->d_x0 = dalloc<double>(B * nx); h->d_tgt_t = dalloc<double>(B * h->TP); h->d_tgt_x = dalloc<double>(B * h->TP * nx);
-    h->d_n_ev = dalloc<int>(B); h->d_ev_t = dalloc<double>(B * h->ME); h->d_ev_mode = dalloc<int>(B * (h->ME + 1));
-    h->h_t0 = halloc<double>(B); h->h_x0 = halloc<double>(B * nx); h->h_tgt_t = halloc<double>(B * h->TP); h->h_tgt_x = halloc<double>(B * h->TP * nx);
-    h->h_n_ev = halloc<int>(B); h->h_ev_t = halloc<double>(B * h->ME); h->h_ev_mode = halloc<int>(B * (h->ME + 1));
-    h->d_st_t = dalloc<double>(B * NS); h->d_st_dt = dalloc<double>(B * NS); h->d_st_mode = dalloc<int>(B * NS);
-    h->d_xref = dalloc<double>(B * NS * nx); h->d_zref = dalloc<double>(B * NS * 2);
+    DevPool& P = h->pool;
+    h->d_t0 = P.d<double>(B); h->d_x0 = P.d<double>(B * nx); h->d_tgt_t = P.d<double>(B * h->TP); h->d_tgt_x = P.d<double>(B * h->TP * nx);
+    h->d_n_ev = P.d<int>(B); h->d_ev_t = P.d<double>(B * h->ME); h->d_ev_mode = P.d<int>(B * (h->ME + 1));
+    h->h_t0 = P.h<double>(B); h->h_x0 = P.h<double>(B * nx); h->h_tgt_t = P.h<double>(B * h->TP); h->h_tgt_x = P.h<double>(B * h->TP * nx);
+    h->h_n_ev = P.h<int>(B); h->h_ev_t = P.h<double>(B * h->ME); h->h_ev_mode = P.h<int>(B * (h->ME + 1));
+    h->d_st_t = P.d<double>(B * NS); h->d_st_dt = P.d<double>(B * NS); h->d_st_mode = P.d<int>(B * NS);
+    h->d_xref = P.d<double>(B * NS * nx); h->d_zref = P.d<double>(B * NS * 2);
     for (int i = 0; i < 2; ++i) {
-      h->s_n[i] = dalloc<int>(B); h->s_ev[i] = dalloc<int>(B * NS); h->s_t[i] = dalloc<double>(B * NS);
-      h->s_x[i] = dalloc<double>(B * NS * nx); h->s_u[i] = dalloc<double>(B * NS * nu); h->s_uff[i] = dalloc<double>(B * NS * nu);
-      h->s_K[i] = dalloc<double>(B * NS * nu * nx);
+      h->s_n[i] = P.d<int>(B); h->s_ev[i] = P.d<int>(B * NS); h->s_t[i] = P.d<double>(B * NS);
+      h->s_x[i] = P.d<double>(B * NS * nx); h->s_u[i] = P.d<double>(B * NS * nu); h->s_uff[i] = P.d<double>(B * NS * nu);
+      h->s_K[i] = P.d<double>(B * NS * nu * nx);
+      h->s_nev[i] = P.d<int>(B); h->s_evt[i] = P.d<double>(B * h->ME); h->s_evm[i] = P.d<int>(B * (h->ME + 1));
+      h->s_perf[i] = P.d<double>(B * 8); h->s_status[i] = P.d<int>(B);
     }
-    h->d_lq = dalloc<double>(B * NS * h->rec); h->d_proj = dalloc<double>(B * NS * h->prec); h->d_stage = dalloc<double>(B * NS * h->srec); h->d_base = dalloc<double>(B * NS * h->brec); h->d_ric = dalloc<double>(B * NS * h->krec);
-    h->d_dx = dalloc<double>(B * NS * nx); h->d_du = dalloc<double>(B * NS * nu);
-    h->d_perf_trial = dalloc<double>(B * NS * 3); h->d_perf = dalloc<double>(B * 8); h->d_alpha = dalloc<double>(B); h->d_norms = dalloc<double>(B * 2);
-    h->d_done = dalloc<int>(B); h->d_status = dalloc<int>(B); h->d_counters = dalloc<int>(4); h->h_counters = halloc<int>(4);
-    {  // static entries of the projected stage records (identity rows / columns of At); everything else was zeroed by dalloc
+    h->d_lq = P.d<double>(B * NS * h->rec); h->d_proj = P.d<double>(B * NS * h->prec); h->d_stage = P.d<double>(B * NS * h->srec); h->d_ric = P.d<double>(B * NS * h->krec);
+    h->d_dx = P.d<double>(B * NS * nx); h->d_du = P.d<double>(B * NS * nu);
+    h->d_norms = P.d<double>(B * 2);
+    h->d_counters = P.d<int>(CNT_N); h->h_counters = P.h<int>(CNT_N);
+    {  // static entries of the projected stage records (identity rows / columns of At); everything else was zeroed by the pool
       const size_t nrec = B * NS;
       if (h->nj == 10) k_stage_static<10><<<(unsigned)((nrec + 255) / 256), 256>>>(h->d_stage, nrec);
       else k_stage_static<12><<<(unsigned)((nrec + 255) / 256), 256>>>(h->d_stage, nrec);
       CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
     }
-    h->d_default_joints = dalloc<double>(MAXJ); h->d_cmd = dalloc<double>(B * 4);
+    h->d_default_joints = P.d<double>(MAXJ);
     CK(cudaMemcpy(h->d_default_joints, h->model.default_joint_state.data(), sizeof(double) * h->nj, cudaMemcpyHostToDevice));
     {  // packed per-joint constants for the lane = joint kernels
       std::vector<double> jc((size_t)MAXJ * 28, 0.0); const DevModel& dm = h->model.dev;
@@ -252,36 +366,19 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
         for (int i = 0; i < 3; ++i) { p[9 + i] = dm.pj[j][i]; p[12 + i] = dm.axis[j][i]; p[16 + i] = dm.com[j][i]; }
         p[15] = dm.mass[j];
       }
-      h->d_jc = dalloc<double>((size_t)MAXJ * 28);
+      h->d_jc = P.d<double>((size_t)MAXJ * 28);
       CK(cudaMemcpy(h->d_jc, jc.data(), sizeof(double) * jc.size(), cudaMemcpyHostToDevice));
     }
-    h->d_eval_t = dalloc<double>(B); h->d_eval_x = dalloc<double>(B * nx); h->d_eval_xo = dalloc<double>(B * nx); h->d_eval_uo = dalloc<double>(B * nu); h->d_eval_m = dalloc<int>(B);
-    // per-instance gait schedules start from reference.info's initialModeSchedule / defaultModeSequenceTemplate (BipedalRobotInterface.cpp:209-234)
-    GaitSchedule g0; g0.ms.eventTimes = h->model.init_events; g0.ms.modeSequence = h->model.init_modes; g0.tmpl = h->model.default_template;
-    g0.phaseTransitionStanceTime = h->model.phase_transition_stance_time;
-    h->gaits.assign(B, g0);
+    h->d_eval_t = P.d<double>(B); h->d_eval_x = P.d<double>(B * nx); h->d_eval_xo = P.d<double>(B * nx); h->d_eval_uo = P.d<double>(B * nu); h->d_eval_m = P.d<int>(B);
+    h->gaits.assign(B, initial_gait(h));
     *out = h;
     return BMPC_OK;
-  } catch (const CudaError& e) { delete h; return fail(nullptr, BMPC_ERR_CUDA, e.what()); }
-  catch (const std::invalid_argument& e) { delete h; return fail(nullptr, BMPC_ERR_INVALID, e.what()); }
-  catch (const std::exception& e) { delete h; return fail(nullptr, BMPC_ERR_INVALID, e.what()); }
+  } catch (const CudaError& e) { destroy_impl(h); return fail(nullptr, BMPC_ERR_CUDA, e.what()); }
+  catch (const std::invalid_argument& e) { destroy_impl(h); return fail(nullptr, BMPC_ERR_INVALID, e.what()); }
+  catch (const std::exception& e) { destroy_impl(h); return fail(nullptr, BMPC_ERR_INVALID, e.what()); }
 }
 
-void bmpc_destroy(bmpc_handle* h) {
-  if (!h) return;
-  cudaSetDevice(h->device);
-  if (h->stream) cudaStreamSynchronize(h->stream);
-  void* dptrs[] = {h->d_t0, h->d_x0, h->d_tgt_t, h->d_tgt_x, h->d_ev_t, h->d_n_ev, h->d_ev_mode, h->d_st_t, h->d_st_dt, h->d_xref, h->d_zref, h->d_st_mode,
-                   h->s_n[0], h->s_n[1], h->s_ev[0], h->s_ev[1], h->s_t[0], h->s_t[1], h->s_x[0], h->s_x[1], h->s_u[0], h->s_u[1], h->s_uff[0], h->s_uff[1], h->s_K[0], h->s_K[1],
-                   h->d_lq, h->d_proj, h->d_stage, h->d_ric, h->d_base, h->d_dx, h->d_du, h->d_perf_trial, h->d_perf, h->d_alpha, h->d_norms, h->d_done, h->d_status, h->d_counters,
-                   h->d_eval_t, h->d_eval_x, h->d_eval_xo, h->d_eval_uo, h->d_eval_m, h->d_default_joints, h->d_cmd, h->d_jc};
-  for (void* p : dptrs) if (p) cudaFree(p);
-  void* hptrs[] = {h->h_t0, h->h_x0, h->h_tgt_t, h->h_tgt_x, h->h_ev_t, h->h_n_ev, h->h_ev_mode, h->h_counters};
-  for (void* p : hptrs) if (p) cudaFreeHost(p);
-  for (auto& e : h->tev) if (e) cudaEventDestroy(e);
-  if (h->stream) cudaStreamDestroy(h->stream);
-  delete h;
-}
+void bmpc_destroy(bmpc_handle* h) { destroy_impl(h); }
 
 int bmpc_get_dims(const bmpc_handle* h, int* nx, int* nu, int* batch, int* max_nodes) {
   if (!h) return BMPC_ERR_INVALID;
@@ -304,24 +401,32 @@ int bmpc_convert_model(const char* task_file, const char* reference_file, const 
   } catch (const std::exception& e) { return fail(nullptr, BMPC_ERR_INVALID, e.what()); }
 }
 
-int bmpc_reset(bmpc_handle* h) {
+int bmpc_reset(bmpc_handle* h, int instance) {
   API_BEGIN if (!h) return BMPC_ERR_INVALID;
-  CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream));
-  h->have_solution = false;
-  GaitSchedule g0; g0.ms.eventTimes = h->model.init_events; g0.ms.modeSequence = h->model.init_modes; g0.tmpl = h->model.default_template;
-  g0.phaseTransitionStanceTime = h->model.phase_transition_stance_time;
-  h->gaits.assign(h->B, g0);
+  if (instance >= h->B) throw std::invalid_argument("[bmpc] instance out of range");
+  CK(cudaSetDevice(h->device));
+  std::unique_lock<std::mutex> lk(h->mtx);
+  wait_and_publish(h, lk);
+  if (instance < 0) { h->have_solution = false; h->gaits.assign(h->B, initial_gait(h)); }
+  else {
+    // one instance: its warm start is dropped by emptying its previous solution (the initializer is used for every node of the next tick)
+    if (h->have_solution) { CK(cudaMemsetAsync(h->s_n[h->cur] + instance, 0, sizeof(int), h->stream)); CK(cudaStreamSynchronize(h->stream)); }
+    h->gaits[instance] = initial_gait(h);
+  }
   return BMPC_OK; API_END(h)
 }
 
 int bmpc_set_observations(bmpc_handle* h, const double* t, const double* x) {
   API_BEGIN if (!h || !t || !x) throw std::invalid_argument("[bmpc] null argument");
+  std::lock_guard<std::mutex> lk(h->mtx);
+  staging_ready(h);
   std::memcpy(h->h_t0, t, sizeof(double) * h->B); std::memcpy(h->h_x0, x, sizeof(double) * h->B * h->nx);
   h->obs_dirty = true; h->have_obs = true; return BMPC_OK; API_END(h)
 }
 int bmpc_set_observations_device(bmpc_handle* h, const double* t, const double* x) {
   API_BEGIN if (!h || !t || !x) throw std::invalid_argument("[bmpc] null argument");
   CK(cudaSetDevice(h->device));
+  std::lock_guard<std::mutex> lk(h->mtx);
   CK(cudaMemcpyAsync(h->d_t0, t, sizeof(double) * h->B, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_x0, x, sizeof(double) * h->B * h->nx, cudaMemcpyDeviceToDevice, h->stream));
   h->obs_dirty = false; h->have_obs = false; return BMPC_OK; API_END(h)
@@ -329,6 +434,8 @@ int bmpc_set_observations_device(bmpc_handle* h, const double* t, const double* 
 int bmpc_set_target_trajectories(bmpc_handle* h, int npts, const double* times, const double* states) {
   API_BEGIN if (!h || !times || !states) throw std::invalid_argument("[bmpc] null argument");
   if (npts < 1 || npts > h->TP) throw std::length_error("[bmpc] number of target points exceeds max_target_points");
+  std::lock_guard<std::mutex> lk(h->mtx);
+  staging_ready(h);
   for (int b = 0; b < h->B; ++b) {
     std::memcpy(h->h_tgt_t + (size_t)b * h->TP, times + (size_t)b * npts, sizeof(double) * npts);
     std::memcpy(h->h_tgt_x + (size_t)b * h->TP * h->nx, states + (size_t)b * npts * h->nx, sizeof(double) * npts * h->nx);
@@ -339,6 +446,7 @@ int bmpc_set_target_trajectories_device(bmpc_handle* h, int npts, const double* 
   API_BEGIN if (!h || !times || !states) throw std::invalid_argument("[bmpc] null argument");
   if (npts < 1 || npts > h->TP) throw std::length_error("[bmpc] number of target points exceeds max_target_points");
   CK(cudaSetDevice(h->device));
+  std::lock_guard<std::mutex> lk(h->mtx);
   CK(cudaMemcpy2DAsync(h->d_tgt_t, sizeof(double) * h->TP, times, sizeof(double) * npts, sizeof(double) * npts, h->B, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemcpy2DAsync(h->d_tgt_x, sizeof(double) * h->TP * h->nx, states, sizeof(double) * npts * h->nx, sizeof(double) * npts * h->nx, h->B, cudaMemcpyDeviceToDevice, h->stream));
   h->npts = npts; h->tgt_dirty = false; h->have_tgt = true; return BMPC_OK; API_END(h)
@@ -346,8 +454,10 @@ int bmpc_set_target_trajectories_device(bmpc_handle* h, int npts, const double* 
 // TargetTrajectoriesPublisher.cpp:41-99
 int bmpc_set_targets_from_cmd_vel(bmpc_handle* h, const double* cmd, double time_to_target) {
   API_BEGIN if (!h || !cmd) throw std::invalid_argument("[bmpc] null argument");
+  std::lock_guard<std::mutex> lk(h->mtx);
   if (!h->have_obs) throw std::invalid_argument("[bmpc] set observations (host) before bmpc_set_targets_from_cmd_vel");
   if (h->TP < 2) throw std::length_error("[bmpc] max_target_points < 2");
+  staging_ready(h);
   const int nx = h->nx, nj = h->nj;
   for (int b = 0; b < h->B; ++b) {
     const double* x = h->h_x0 + (size_t)b * nx; const double* c = cmd + (size_t)b * 4;
@@ -367,9 +477,11 @@ int bmpc_set_targets_from_cmd_vel(bmpc_handle* h, const double* cmd, double time
 }
 int bmpc_set_mode_schedules(bmpc_handle* h, int stride, const int* n_events, const double* event_times, const int* mode_sequence) {
   API_BEGIN if (!h || !n_events || !event_times || !mode_sequence) throw std::invalid_argument("[bmpc] null argument");
+  std::lock_guard<std::mutex> lk(h->mtx);
+  for (int b = 0; b < h->B; ++b) if (n_events[b] < 0 || n_events[b] > h->ME || n_events[b] > stride) throw std::length_error("[bmpc] mode schedule exceeds max_events");
+  staging_ready(h);
   for (int b = 0; b < h->B; ++b) {
     const int ne = n_events[b];
-    if (ne < 0 || ne > h->ME || ne > stride) throw std::length_error("[bmpc] mode schedule exceeds max_events");
     h->h_n_ev[b] = ne;
     std::memcpy(h->h_ev_t + (size_t)b * h->ME, event_times + (size_t)b * stride, sizeof(double) * ne);
     std::memcpy(h->h_ev_mode + (size_t)b * (h->ME + 1), mode_sequence + (size_t)b * (stride + 1), sizeof(int) * (ne + 1));
@@ -380,6 +492,7 @@ int bmpc_set_mode_schedules_device(bmpc_handle* h, int stride, const int* n_even
   API_BEGIN if (!h || !n_events || !event_times || !mode_sequence) throw std::invalid_argument("[bmpc] null argument");
   if (stride > h->ME) throw std::length_error("[bmpc] mode schedule stride exceeds max_events");
   CK(cudaSetDevice(h->device));
+  std::lock_guard<std::mutex> lk(h->mtx);
   CK(cudaMemcpyAsync(h->d_n_ev, n_events, sizeof(int) * h->B, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemcpy2DAsync(h->d_ev_t, sizeof(double) * h->ME, event_times, sizeof(double) * stride, sizeof(double) * stride, h->B, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemcpy2DAsync(h->d_ev_mode, sizeof(int) * (h->ME + 1), mode_sequence, sizeof(int) * (stride + 1), sizeof(int) * (stride + 1), h->B, cudaMemcpyDeviceToDevice, h->stream));
@@ -390,6 +503,7 @@ int bmpc_gait_insert(bmpc_handle* h, int instance, int n_modes, const int* modes
   API_BEGIN if (!h || !modes || !switching_times || n_modes <= 0) throw std::invalid_argument("[bmpc] null argument");
   if (instance >= h->B) throw std::invalid_argument("[bmpc] instance out of range");
   GaitTemplate t; t.modes.assign(modes, modes + n_modes); t.times.assign(switching_times, switching_times + n_modes + 1);
+  std::lock_guard<std::mutex> lk(h->mtx);   // GaitReceiver's receivedGaitMutex_ (GaitReceiver.cpp:52,65)
   const int b0 = instance < 0 ? 0 : instance, b1 = instance < 0 ? h->B : instance + 1;
   for (int b = b0; b < b1; ++b) h->gaits[b].insertModeSequenceTemplate(t, start_time, final_time);
   return BMPC_OK; API_END(h)
@@ -400,9 +514,11 @@ int bmpc_gait_insert_named(bmpc_handle* h, int instance, const char* gait_name, 
     if (g.name == gait_name) return bmpc_gait_insert(h, instance, (int)g.modes.size(), g.modes.data(), g.times.data(), start_time, final_time);
   return fail(h, BMPC_ERR_INVALID, std::string("[bmpc] unknown gait '") + gait_name + "'");
 }
-int bmpc_use_gait_schedule(bmpc_handle* h, int enable) { if (!h) return BMPC_ERR_INVALID; h->use_gait = enable != 0; return BMPC_OK; }
-int bmpc_gait_peek(const bmpc_handle* h, int instance, int cap, double* event_times, int* mode_sequence) {
+int bmpc_use_gait_schedule(bmpc_handle* h, int enable) { if (!h) return BMPC_ERR_INVALID; std::lock_guard<std::mutex> lk(h->mtx); h->use_gait = enable != 0; return BMPC_OK; }
+int bmpc_gait_peek(const bmpc_handle* hc, int instance, int cap, double* event_times, int* mode_sequence) {
+  bmpc_handle* h = const_cast<bmpc_handle*>(hc);
   if (!h || instance < 0 || instance >= h->B) return BMPC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mtx);
   const ModeSchedule& ms = h->gaits[instance].ms;
   const int n = (int)ms.eventTimes.size();
   if (n > cap) return BMPC_ERR_CAPACITY;
@@ -414,38 +530,65 @@ int bmpc_gait_peek(const bmpc_handle* h, int instance, int cap, double* event_ti
 int bmpc_advance_async(bmpc_handle* h) {
   API_BEGIN if (!h) return BMPC_ERR_INVALID;
   CK(cudaSetDevice(h->device));
+  std::unique_lock<std::mutex> lk(h->mtx);
+  wait_and_publish(h, lk);                                         // one tick at a time (MPC_BASE::run is not re-entrant either)
   if (h->use_gait) compute_gait_schedules(h);
   if (!h->have_tgt) throw std::invalid_argument("[bmpc] target trajectories not set");
   if (!h->have_sched) throw std::invalid_argument("[bmpc] mode schedules not set (bmpc_set_mode_schedules or bmpc_use_gait_schedule)");
+  const int w = 1 - h->cur;
+  h->cv.wait(lk, [&] { return h->readers[w] == 0; });              // nobody is still copying the buffer this tick overwrites
   if (h->nj == 10) tick<10>(h); else tick<12>(h);
   return BMPC_OK; API_END(h)
 }
 int bmpc_synchronize(bmpc_handle* h) {
   API_BEGIN if (!h) return BMPC_ERR_INVALID;
-  CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream));
-  if (h->timing) for (int i = 0; i < 8; ++i) cudaEventElapsedTime(&h->phase_ms[i], h->tev[i], h->tev[i + 1]);
-  return BMPC_OK; API_END(h)
+  CK(cudaSetDevice(h->device));
+  std::unique_lock<std::mutex> lk(h->mtx);
+  wait_and_publish(h, lk);
+  return h->last_rc; API_END(h)
 }
 int bmpc_advance(bmpc_handle* h) { const int rc = bmpc_advance_async(h); return rc != BMPC_OK ? rc : bmpc_synchronize(h); }
+int bmpc_poll(bmpc_handle* h) {
+  if (!h) return BMPC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mtx);
+  try_publish(h);
+  return h->pending ? 1 : 0;
+}
 
 int bmpc_get_policy(bmpc_handle* h, int first, int count, int* n_nodes, double* times, int* events, double* x, double* u, double* uff, double* K) {
   API_BEGIN if (!h) return BMPC_ERR_INVALID;
-  if (!h->have_solution) throw std::invalid_argument("[bmpc] no solution yet");
   if (first < 0 || count < 0 || first + count > h->B) throw std::invalid_argument("[bmpc] instance range out of bounds");
-  CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream));
-  const int c = h->cur; const size_t NS = h->NS, nx = h->nx, nu = h->nu, f = first, n = count;
-  if (n_nodes) CK(cudaMemcpy(n_nodes, h->s_n[c] + f, sizeof(int) * n, cudaMemcpyDeviceToHost));
-  if (times) CK(cudaMemcpy(times, h->s_t[c] + f * NS, sizeof(double) * n * NS, cudaMemcpyDeviceToHost));
-  if (events) CK(cudaMemcpy(events, h->s_ev[c] + f * NS, sizeof(int) * n * NS, cudaMemcpyDeviceToHost));
-  if (x) CK(cudaMemcpy(x, h->s_x[c] + f * NS * nx, sizeof(double) * n * NS * nx, cudaMemcpyDeviceToHost));
-  if (u) CK(cudaMemcpy(u, h->s_u[c] + f * NS * nu, sizeof(double) * n * NS * nu, cudaMemcpyDeviceToHost));
-  if (uff) CK(cudaMemcpy(uff, h->s_uff[c] + f * NS * nu, sizeof(double) * n * NS * nu, cudaMemcpyDeviceToHost));
-  if (K) CK(cudaMemcpy(K, h->s_K[c] + f * NS * nu * nx, sizeof(double) * n * NS * nu * nx, cudaMemcpyDeviceToHost));
+  CK(cudaSetDevice(h->device));
+  ReadGuard g(h);
+  const int c = g.c; const size_t NS = h->NS, nx = h->nx, nu = h->nu, f = first, n = count;
+  std::lock_guard<std::mutex> io(h->eval_mtx);   // one user of the io stream at a time
+  cudaStream_t st = h->io_stream;
+  if (n_nodes) CK(cudaMemcpyAsync(n_nodes, h->s_n[c] + f, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+  if (times) CK(cudaMemcpyAsync(times, h->s_t[c] + f * NS, sizeof(double) * n * NS, cudaMemcpyDeviceToHost, st));
+  if (events) CK(cudaMemcpyAsync(events, h->s_ev[c] + f * NS, sizeof(int) * n * NS, cudaMemcpyDeviceToHost, st));
+  if (x) CK(cudaMemcpyAsync(x, h->s_x[c] + f * NS * nx, sizeof(double) * n * NS * nx, cudaMemcpyDeviceToHost, st));
+  if (u) CK(cudaMemcpyAsync(u, h->s_u[c] + f * NS * nu, sizeof(double) * n * NS * nu, cudaMemcpyDeviceToHost, st));
+  if (uff) CK(cudaMemcpyAsync(uff, h->s_uff[c] + f * NS * nu, sizeof(double) * n * NS * nu, cudaMemcpyDeviceToHost, st));
+  if (K) CK(cudaMemcpyAsync(K, h->s_K[c] + f * NS * nu * nx, sizeof(double) * n * NS * nu * nx, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return BMPC_OK; API_END(h)
 }
 int bmpc_get_device_view(bmpc_handle* h, bmpc_device_view* v) {
-  if (!h || !v || !h->have_solution) return BMPC_ERR_INVALID;
+  if (!h || !v) return BMPC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mtx);
+  try_publish(h);
+  if (!h->have_solution) return BMPC_ERR_INVALID;
   const int c = h->cur;
+  v->n_nodes = h->s_n[c]; v->times = h->s_t[c]; v->events = h->s_ev[c]; v->x = h->s_x[c]; v->u = h->s_u[c]; v->uff = h->s_uff[c]; v->K = h->s_K[c];
+  v->max_nodes = h->NS; v->nx = h->nx; v->nu = h->nu; v->batch = h->B;
+  return BMPC_OK;
+}
+int bmpc_get_device_view_inflight(bmpc_handle* h, bmpc_device_view* v) {
+  if (!h || !v) return BMPC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mtx);
+  try_publish(h);
+  if (!h->have_solution && !h->pending) return BMPC_ERR_INVALID;
+  const int c = h->pending ? 1 - h->cur : h->cur;
   v->n_nodes = h->s_n[c]; v->times = h->s_t[c]; v->events = h->s_ev[c]; v->x = h->s_x[c]; v->u = h->s_u[c]; v->uff = h->s_uff[c]; v->K = h->s_K[c];
   v->max_nodes = h->NS; v->nx = h->nx; v->nu = h->nu; v->batch = h->B;
   return BMPC_OK;
@@ -453,24 +596,29 @@ int bmpc_get_device_view(bmpc_handle* h, bmpc_device_view* v) {
 int bmpc_get_performance(bmpc_handle* h, double* perf) {
   API_BEGIN if (!h || !perf) return BMPC_ERR_INVALID;
   CK(cudaSetDevice(h->device));
-  CK(cudaMemcpyAsync(perf, h->d_perf, sizeof(double) * h->B * 8, cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream));
+  ReadGuard g(h);
+  std::lock_guard<std::mutex> io(h->eval_mtx);
+  CK(cudaMemcpyAsync(perf, h->s_perf[g.c], sizeof(double) * h->B * 8, cudaMemcpyDeviceToHost, h->io_stream)); CK(cudaStreamSynchronize(h->io_stream));
   return BMPC_OK; API_END(h)
 }
 int bmpc_get_status(bmpc_handle* h, int* status) {
   API_BEGIN if (!h || !status) return BMPC_ERR_INVALID;
   CK(cudaSetDevice(h->device));
-  CK(cudaMemcpyAsync(status, h->d_status, sizeof(int) * h->B, cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream));
+  ReadGuard g(h);
+  std::lock_guard<std::mutex> io(h->eval_mtx);
+  CK(cudaMemcpyAsync(status, h->s_status[g.c], sizeof(int) * h->B, cudaMemcpyDeviceToHost, h->io_stream)); CK(cudaStreamSynchronize(h->io_stream));
   return BMPC_OK; API_END(h)
 }
 int bmpc_evaluate_policy(bmpc_handle* h, const double* t, const double* x, double* x_opt, double* u_opt, int* mode) {
   API_BEGIN if (!h || !t || !x) return BMPC_ERR_INVALID;
-  if (!h->have_solution) throw std::invalid_argument("[bmpc] no solution yet");
   CK(cudaSetDevice(h->device));
-  const int c = h->cur, B = h->B; cudaStream_t st = h->stream;
+  ReadGuard g(h);
+  std::lock_guard<std::mutex> io(h->eval_mtx);   // the query / result scratch buffers are shared
+  const int c = g.c, B = h->B; cudaStream_t st = h->io_stream;
   CK(cudaMemcpyAsync(h->d_eval_t, t, sizeof(double) * B, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(h->d_eval_x, x, sizeof(double) * B * h->nx, cudaMemcpyHostToDevice, st));
-  if (h->nj == 10) k_evaluate_policy<10><<<B, 32, 0, st>>>(B, h->NS, h->ME, h->s_n[c], h->s_t[c], h->s_x[c], h->s_uff[c], h->s_K[c], h->d_n_ev, h->d_ev_t, h->d_ev_mode, h->d_eval_t, h->d_eval_x, h->d_eval_xo, h->d_eval_uo, h->d_eval_m);
-  else k_evaluate_policy<12><<<B, 32, 0, st>>>(B, h->NS, h->ME, h->s_n[c], h->s_t[c], h->s_x[c], h->s_uff[c], h->s_K[c], h->d_n_ev, h->d_ev_t, h->d_ev_mode, h->d_eval_t, h->d_eval_x, h->d_eval_xo, h->d_eval_uo, h->d_eval_m);
+  if (h->nj == 10) k_evaluate_policy<10><<<B, 32, 0, st>>>(B, h->NS, h->ME, h->s_n[c], h->s_t[c], h->s_x[c], h->s_uff[c], h->s_K[c], h->s_nev[c], h->s_evt[c], h->s_evm[c], h->d_eval_t, h->d_eval_x, h->d_eval_xo, h->d_eval_uo, h->d_eval_m);
+  else k_evaluate_policy<12><<<B, 32, 0, st>>>(B, h->NS, h->ME, h->s_n[c], h->s_t[c], h->s_x[c], h->s_uff[c], h->s_K[c], h->s_nev[c], h->s_evt[c], h->s_evm[c], h->d_eval_t, h->d_eval_x, h->d_eval_xo, h->d_eval_uo, h->d_eval_m);
   if (x_opt) CK(cudaMemcpyAsync(x_opt, h->d_eval_xo, sizeof(double) * B * h->nx, cudaMemcpyDeviceToHost, st));
   if (u_opt) CK(cudaMemcpyAsync(u_opt, h->d_eval_uo, sizeof(double) * B * h->nu, cudaMemcpyDeviceToHost, st));
   if (mode) CK(cudaMemcpyAsync(mode, h->d_eval_m, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
@@ -478,13 +626,15 @@ int bmpc_evaluate_policy(bmpc_handle* h, const double* t, const double* x, doubl
   return BMPC_OK; API_END(h)
 }
 
-// Device-resident drivers for closed-loop batches (observations and targets never leave HBM).
+// Device-resident drivers for closed-loop batches (observations and targets never leave HBM).  They run on the compute stream, i.e. after
+// the tick in flight, and use the policy that tick produces.
 int bmpc_shift_observations(bmpc_handle* h, double dt) {
   API_BEGIN if (!h) return BMPC_ERR_INVALID;
-  if (!h->have_solution) throw std::invalid_argument("[bmpc] no solution yet");
   CK(cudaSetDevice(h->device));
-  if (h->obs_dirty) { CK(cudaMemcpyAsync(h->d_t0, h->h_t0, sizeof(double) * h->B, cudaMemcpyHostToDevice, h->stream)); CK(cudaMemcpyAsync(h->d_x0, h->h_x0, sizeof(double) * h->B * h->nx, cudaMemcpyHostToDevice, h->stream)); h->obs_dirty = false; }
-  const int c = h->cur, B = h->B;
+  std::lock_guard<std::mutex> lk(h->mtx);
+  if (!h->have_solution && !h->pending) throw std::invalid_argument("[bmpc] no solution yet");
+  upload_inputs(h);
+  const int c = h->pending ? 1 - h->cur : h->cur, B = h->B;   // stream order: the pending tick has written buffer 1 - cur by the time this kernel runs
   if (h->nj == 10) k_shift_observations<10><<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->NS, dt, h->s_n[c], h->s_t[c], h->s_x[c], h->d_t0, h->d_x0);
   else k_shift_observations<12><<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->NS, dt, h->s_n[c], h->s_t[c], h->s_x[c], h->d_t0, h->d_x0);
   h->have_obs = false; CK(cudaGetLastError());
@@ -494,7 +644,8 @@ int bmpc_set_targets_from_cmd_vel_device(bmpc_handle* h, const double* cmd_dev, 
   API_BEGIN if (!h || !cmd_dev) return BMPC_ERR_INVALID;
   if (h->TP < 2) throw std::length_error("[bmpc] max_target_points < 2");
   CK(cudaSetDevice(h->device));
-  if (h->obs_dirty) { CK(cudaMemcpyAsync(h->d_t0, h->h_t0, sizeof(double) * h->B, cudaMemcpyHostToDevice, h->stream)); CK(cudaMemcpyAsync(h->d_x0, h->h_x0, sizeof(double) * h->B * h->nx, cudaMemcpyHostToDevice, h->stream)); h->obs_dirty = false; }
+  std::lock_guard<std::mutex> lk(h->mtx);
+  upload_inputs(h);
   const int B = h->B;
   if (h->nj == 10) k_cmd_vel_targets<10><<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->TP, h->d_t0, h->d_x0, cmd_dev, time_to_target, h->model.com_height, h->d_default_joints, h->d_tgt_t, h->d_tgt_x);
   else k_cmd_vel_targets<12><<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->TP, h->d_t0, h->d_x0, cmd_dev, time_to_target, h->model.com_height, h->d_default_joints, h->d_tgt_t, h->d_tgt_x);
@@ -504,9 +655,11 @@ int bmpc_set_targets_from_cmd_vel_device(bmpc_handle* h, const double* cmd_dev, 
 int bmpc_get_observations(bmpc_handle* h, double* t, double* x) {
   API_BEGIN if (!h) return BMPC_ERR_INVALID;
   CK(cudaSetDevice(h->device));
-  if (h->obs_dirty) { CK(cudaMemcpyAsync(h->d_t0, h->h_t0, sizeof(double) * h->B, cudaMemcpyHostToDevice, h->stream)); CK(cudaMemcpyAsync(h->d_x0, h->h_x0, sizeof(double) * h->B * h->nx, cudaMemcpyHostToDevice, h->stream)); h->obs_dirty = false; }
+  std::unique_lock<std::mutex> lk(h->mtx);
+  upload_inputs(h);
   if (t) CK(cudaMemcpyAsync(t, h->d_t0, sizeof(double) * h->B, cudaMemcpyDeviceToHost, h->stream));
   if (x) CK(cudaMemcpyAsync(x, h->d_x0, sizeof(double) * h->B * h->nx, cudaMemcpyDeviceToHost, h->stream));
+  lk.unlock();
   CK(cudaStreamSynchronize(h->stream));
   return BMPC_OK; API_END(h)
 }
@@ -514,13 +667,26 @@ int bmpc_get_observations(bmpc_handle* h, double* t, double* x) {
 int bmpc_get_launch_count(const bmpc_handle* h) { return h ? h->launches : 0; }
 int bmpc_debug_set_option(bmpc_handle* h, const char* name, int value) {
   if (!h || !name) return BMPC_ERR_INVALID;
-  if (std::string(name) == "ls_mode") { if (value < 0 || value > 1) return BMPC_ERR_INVALID; h->ls_mode = value; return BMPC_OK; }
-  if (std::string(name) == "riccati_mode") { if (value < 0 || value > 1) return BMPC_ERR_INVALID; h->riccati_mode = value; return BMPC_OK; }
-  if (std::string(name) == "lq_mode") { if (value < 0 || value > 4) return BMPC_ERR_INVALID; h->lq_mode = value; return BMPC_OK; }
+  std::lock_guard<std::mutex> lk(h->mtx);
+  if (std::string(name) == "projection_mode") { if (value < 0 || value > 1) return BMPC_ERR_INVALID; h->projection_mode = value; return BMPC_OK; }
   return BMPC_ERR_INVALID;
 }
-int bmpc_enable_phase_timing(bmpc_handle* h, int enable) { if (!h) return BMPC_ERR_INVALID; h->timing = enable != 0; return BMPC_OK; }
-int bmpc_get_phase_times(bmpc_handle* h, float* ms) { if (!h || !ms) return BMPC_ERR_INVALID; for (int i = 0; i < 8; ++i) ms[i] = h->phase_ms[i]; ms[8] = (float)h->linesearch_trials; return BMPC_OK; }
+int bmpc_enable_phase_timing(bmpc_handle* h, int enable) { if (!h) return BMPC_ERR_INVALID; std::lock_guard<std::mutex> lk(h->mtx); h->timing = enable != 0; return BMPC_OK; }
+int bmpc_get_phase_times(bmpc_handle* h, float* ms) {
+  if (!h || !ms) return BMPC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mtx);
+  for (int i = 0; i < 8; ++i) ms[i] = h->phase_ms[i];
+  ms[8] = (float)h->max_trials;
+  return BMPC_OK;
+}
+int bmpc_get_tick_stats(bmpc_handle* h, int* total_trials, int* max_trials, int* failed_instances, int* status_or) {
+  if (!h) return BMPC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mtx);
+  try_publish(h);
+  if (total_trials) *total_trials = h->linesearch_trials; if (max_trials) *max_trials = h->max_trials;
+  if (failed_instances) *failed_instances = h->failed_instances; if (status_or) *status_or = h->status_or;
+  return BMPC_OK;
+}
 void* bmpc_get_stream(bmpc_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 int bmpc_debug_record_sizes(const bmpc_handle* h, int* lq_rec, int* proj_rec, int* ric_rec) {
@@ -530,7 +696,10 @@ int bmpc_debug_record_sizes(const bmpc_handle* h, int* lq_rec, int* proj_rec, in
 }
 int bmpc_debug_copy(bmpc_handle* h, const char* name, int instance, double* dst, int capacity) {
   API_BEGIN if (!h || !name || !dst || instance < 0 || instance >= h->B) return BMPC_ERR_INVALID;
-  CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream));
+  CK(cudaSetDevice(h->device));
+  std::unique_lock<std::mutex> lk(h->mtx);
+  wait_and_publish(h, lk);
+  CK(cudaStreamSynchronize(h->stream));
   const std::string n(name); const size_t NS = h->NS, b = instance;
   const double* src = nullptr; size_t cnt = 0;
   const int c = h->cur;

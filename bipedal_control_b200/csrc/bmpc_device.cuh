@@ -100,8 +100,12 @@ template <int NJ>
 struct Dims {
   static constexpr int NX = 12 + NJ, NU = 12 + NJ, NXA = NX - 3, NL = NJ / 2;
   // compact LQ record produced by the LQ kernel (doubles)
+  // constraint rows of the contact velocities, MAXROWS = 12: either the raw rows in upstream's stacking order (two sole points per foot:
+  // 3 zero-velocity rows per closed contact, 1 normal-velocity row per open contact; consumed by the FullPivLU projection) or the per-foot
+  // orthogonally compressed rows (<= 10, consumed by the Moore-Penrose projection)
+  static constexpr int MAXROWS = 12;
   static constexpr int R_B = 0, R_AD = R_B + NX, R_BD = R_AD + 9 * NXA, R_Q = R_BD + 9 * NU, R_R = R_Q + NX, R_HB = R_R + NU,
-                       R_CV = R_HB + 24, R_DV = R_CV + 10 * NXA, R_EV = R_DV + 10 * NJ, R_MISC = R_EV + 10, R_FO = R_MISC + 12,
+                       R_CV = R_HB + 24, R_DV = R_CV + MAXROWS * NXA, R_EV = R_DV + MAXROWS * NJ, R_MISC = R_EV + MAXROWS, R_FO = R_MISC + 12,
                        REC = ((R_FO + 12 + 3) / 4) * 4;
   // misc slots
   static constexpr int M_DT = 0, M_DQ = 1, M_DR = 2, M_MODE = 3, M_NROWS = 4, M_TYPE = 5, M_PCOST = 6, M_PDYN = 7, M_PEQ = 8;
@@ -112,231 +116,8 @@ struct Dims {
 // map a state index (0..NX-1, not 6..8) to its column in the "active x" set X = {0..5, 9..NX-1}
 __device__ __forceinline__ int xcol(int s) { return s < 6 ? s : s - 3; }
 
-// Result of one evaluation of the continuous-time model at (x, u).
-template <int NJ>
-struct ModelEval {
-  static constexpr int NX = Dims<NJ>::NX, NXA = Dims<NJ>::NXA;
-  double f[NX];
-  double Ac[9][NXA];   // rows 3..11 of df/dx, active columns
-  double Bf[3][12];    // rows 3..5 of df/dF
-  double Bj[6][NJ];    // rows 6..11 of df/dqd_j
-  v3 pc[NCON], vc[NCON];
-};
-template <int NJ>
-struct ContactJac {
-  static constexpr int NXA = Dims<NJ>::NXA;
-  double Jx[NCON][3][NXA];   // d v_i / d x (active columns)
-  double Ju[NCON][3][NJ];    // d v_i / d qd_j
-};
-
-// LEVEL 0: values only (flow map, contact positions / velocities);  LEVEL 1: + dynamics Jacobians;  LEVEL 2: + contact Jacobians
-template <int NJ, int LEVEL>
-__device__ __noinline__ void model_eval(const double* __restrict__ x, const double* __restrict__ u, ModelEval<NJ>& E, ContactJac<NJ>* CJ) {
-  constexpr int NX = Dims<NJ>::NX, NXA = Dims<NJ>::NXA, NL = Dims<NJ>::NL;
-  const DevModel& M = c_model;
-  const double mass = M.total_mass, imass = 1.0 / mass;
-  // ---------------- forward kinematics
-  double sz, cz, sy, cy, sx, cx;
-  sincos(x[9], &sz, &cz); sincos(x[10], &sy, &cy); sincos(x[11], &sx, &cx);
-  m3 Rb;
-  Rb.m[0] = cz * cy; Rb.m[1] = cz * sy * sx - sz * cx; Rb.m[2] = cz * sy * cx + sz * sx;
-  Rb.m[3] = sz * cy; Rb.m[4] = sz * sy * sx + cz * cx; Rb.m[5] = sz * sy * cx - cz * sx;
-  Rb.m[6] = -sy;     Rb.m[7] = cy * sx;                Rb.m[8] = cy * cx;
-  const v3 pb = mk(x[6], x[7], x[8]);
-  v3 bax[3];   // Euler-rate axes in world: e_z, Rz e_y, Rz Ry e_x
-  bax[0] = mk(0.0, 0.0, 1.0); bax[1] = mk(-sz, cz, 0.0); bax[2] = mk(cz * cy, sz * cy, -sy);
-  v3 o[NJ], a[NJ];
-  SI comp_si[NJ];                      // composite spatial inertia of the subtree rooted at joint j
-  v3 cb[NJ]; s3 Icb[NJ];               // body COM / inertia about own COM (world axes)
-  m3 Rtip[2];
-#pragma unroll 1
-  for (int leg = 0; leg < 2; ++leg) {
-    m3 Rp = Rb; v3 pp = pb;
-#pragma unroll 1
-    for (int i = 0; i < NL; ++i) {
-      const int j = leg * NL + i;
-      o[j] = mulc(Rp.m, M.pj[j]) + pp;
-      const m3 Rfix = mulc(Rp, M.Rj[j]);
-      a[j] = mulc(Rfix.m, M.axis[j]);
-      const m3 Rw = mul(Rfix, rodrigues(M.axis[j], x[12 + j]));
-      cb[j] = mulc(Rw.m, M.com[j]) + o[j];
-      Icb[j] = rotate_inertia(Rw, M.inertia[j]);
-      Rp = Rw; pp = o[j];
-    }
-    Rtip[leg] = Rp;
-  }
-#pragma unroll 1
-  for (int c = 0; c < NCON; ++c) E.pc[c] = mulc(Rtip[c / 2].m, M.coff[c]) + o[(c / 2) * NL + NL - 1];
-  const v3 cbase = mulc(Rb.m, M.base_com) + pb;
-  const s3 Ibase = rotate_inertia(Rb, M.base_inertia);
-  // ---------------- composite inertias (leaf -> root)
-#pragma unroll 1
-  for (int leg = 0; leg < 2; ++leg)
-#pragma unroll 1
-    for (int i = NL - 1; i >= 0; --i) {
-      const int j = leg * NL + i;
-      const SI b = body_si(M.mass[j], cb[j], Icb[j]);
-      comp_si[j] = (i == NL - 1) ? b : b + comp_si[j + 1];
-    }
-  const SI tot = body_si(M.base_mass, cbase, Ibase) + comp_si[0] + comp_si[NL];
-  const v3 com = imass * tot.h;
-  // ---------------- centroidal momentum matrix columns (about the COM)
-  v3 Alin_e[3], Aang_e[3], Alin[NJ], Aang[NJ];
-#pragma unroll 1
-  for (int k = 0; k < 3; ++k) { const Mom m = si_apply(tot, bax[k], cross(pb, bax[k])); Alin_e[k] = m.p; Aang_e[k] = m.n - cross(com, m.p); }
-#pragma unroll 1
-  for (int j = 0; j < NJ; ++j) { const Mom m = si_apply(comp_si[j], a[j], cross(o[j], a[j])); Alin[j] = m.p; Aang[j] = m.n - cross(com, m.p); }
-  double A22[9], A22i[9], A12[9];
-#pragma unroll 1
-  for (int k = 0; k < 3; ++k) { A22[k] = Aang_e[k].x; A22[3 + k] = Aang_e[k].y; A22[6 + k] = Aang_e[k].z; A12[k] = Alin_e[k].x; A12[3 + k] = Alin_e[k].y; A12[6 + k] = Alin_e[k].z; }
-  inv3(A22, A22i);
-  // ---------------- generalized velocity  v_b = A_b^-1 (m h - A_j qd)
-  v3 ml = mk(mass * x[0], mass * x[1], mass * x[2]), ma = mk(mass * x[3], mass * x[4], mass * x[5]);
-#pragma unroll 1
-  for (int j = 0; j < NJ; ++j) { const double qd = u[12 + j]; ml = ml - qd * Alin[j]; ma = ma - qd * Aang[j]; }
-  const v3 w = mk(A22i[0] * ma.x + A22i[1] * ma.y + A22i[2] * ma.z, A22i[3] * ma.x + A22i[4] * ma.y + A22i[5] * ma.z, A22i[6] * ma.x + A22i[7] * ma.y + A22i[8] * ma.z);
-  const v3 vlin = imass * (ml - mk(A12[0] * w.x + A12[1] * w.y + A12[2] * w.z, A12[3] * w.x + A12[4] * w.y + A12[5] * w.z, A12[6] * w.x + A12[7] * w.y + A12[8] * w.z));
-  // ---------------- flow map
-  v3 Ftot = mk(0.0, 0.0, 0.0), tau = mk(0.0, 0.0, 0.0);
-#pragma unroll 1
-  for (int c = 0; c < NCON; ++c) { const v3 F = mk(u[3 * c], u[3 * c + 1], u[3 * c + 2]); Ftot = Ftot + F; tau = tau + cross(E.pc[c] - com, F); }
-  E.f[0] = Ftot.x * imass; E.f[1] = Ftot.y * imass; E.f[2] = Ftot.z * imass - 9.81;
-  E.f[3] = tau.x * imass; E.f[4] = tau.y * imass; E.f[5] = tau.z * imass;
-  E.f[6] = vlin.x; E.f[7] = vlin.y; E.f[8] = vlin.z; E.f[9] = w.x; E.f[10] = w.y; E.f[11] = w.z;
-#pragma unroll 1
-  for (int j = 0; j < NJ; ++j) E.f[12 + j] = u[12 + j];
-  // ---------------- link twists (world origin referenced)
-  const double wr[3] = {w.x, w.y, w.z};
-  v3 we[4], ve[4];   // twist after the translation joints and after each Euler joint
-  we[0] = mk(0.0, 0.0, 0.0); ve[0] = vlin;
-#pragma unroll 1
-  for (int k = 0; k < 3; ++k) { we[k + 1] = we[k] + wr[k] * bax[k]; ve[k + 1] = ve[k] + wr[k] * cross(pb, bax[k]); }
-  v3 wj[NJ], vj[NJ];
-#pragma unroll 1
-  for (int leg = 0; leg < 2; ++leg) {
-    v3 wp = we[3], vp = ve[3];
-#pragma unroll 1
-    for (int i = 0; i < NL; ++i) { const int j = leg * NL + i; const double qd = u[12 + j]; wj[j] = wp + qd * a[j]; vj[j] = vp + qd * cross(o[j], a[j]); wp = wj[j]; vp = vj[j]; }
-  }
-#pragma unroll 1
-  for (int c = 0; c < NCON; ++c) { const int tip = (c / 2) * NL + NL - 1; E.vc[c] = cross(wj[tip], E.pc[c]) + vj[tip]; }
-  if (LEVEL == 0) return;
-
-  // ---------------- dynamics Jacobians
-#pragma unroll 1
-  for (int r = 0; r < 9; ++r)
-#pragma unroll 1
-    for (int c = 0; c < NXA; ++c) E.Ac[r][c] = 0.0;
-  double A12A22i[9];
-#pragma unroll 1
-  for (int r = 0; r < 3; ++r)
-#pragma unroll 1
-    for (int c = 0; c < 3; ++c) A12A22i[3 * r + c] = A12[3 * r] * A22i[c] + A12[3 * r + 1] * A22i[3 + c] + A12[3 * r + 2] * A22i[6 + c];
-  // d v_b / d h = m A_b^-1 = [I, -A12 A22^-1 ; 0, m A22^-1]
-#pragma unroll 1
-  for (int r = 0; r < 3; ++r) {
-    E.Ac[3 + r][r] = 1.0;
-#pragma unroll 1
-    for (int c = 0; c < 3; ++c) { E.Ac[3 + r][3 + c] = -A12A22i[3 * r + c]; E.Ac[6 + r][3 + c] = mass * A22i[3 * r + c]; }
-  }
-  // B: d f / d F_i (rows 3..5) = skew(p_i - c)/m ; d f / d qd_j (rows 6..11) = -A_b^-1 A_j
-#pragma unroll 1
-  for (int c = 0; c < NCON; ++c) {
-    const v3 r = imass * (E.pc[c] - com);
-    E.Bf[0][3 * c] = 0.0;  E.Bf[0][3 * c + 1] = -r.z; E.Bf[0][3 * c + 2] = r.y;
-    E.Bf[1][3 * c] = r.z;  E.Bf[1][3 * c + 1] = 0.0;  E.Bf[1][3 * c + 2] = -r.x;
-    E.Bf[2][3 * c] = -r.y; E.Bf[2][3 * c + 1] = r.x;  E.Bf[2][3 * c + 2] = 0.0;
-  }
-#pragma unroll 1
-  for (int j = 0; j < NJ; ++j) {
-    const v3 n = Aang[j], p = Alin[j];
-    const v3 e = mk(A22i[0] * n.x + A22i[1] * n.y + A22i[2] * n.z, A22i[3] * n.x + A22i[4] * n.y + A22i[5] * n.z, A22i[6] * n.x + A22i[7] * n.y + A22i[8] * n.z);
-    const v3 l = imass * (p - mk(A12[0] * e.x + A12[1] * e.y + A12[2] * e.z, A12[3] * e.x + A12[4] * e.y + A12[5] * e.z, A12[6] * e.x + A12[7] * e.y + A12[8] * e.z));
-    E.Bj[0][j] = -l.x; E.Bj[1][j] = -l.y; E.Bj[2][j] = -l.z; E.Bj[3][j] = -e.x; E.Bj[4][j] = -e.y; E.Bj[5][j] = -e.z;
-  }
-  // subtree momenta
-  Mom hs[NJ];
-#pragma unroll 1
-  for (int leg = 0; leg < 2; ++leg)
-#pragma unroll 1
-    for (int i = NL - 1; i >= 0; --i) {
-      const int j = leg * NL + i;
-      Mom b; b.p = M.mass[j] * (vj[j] + cross(wj[j], cb[j])); b.n = mul(Icb[j], wj[j]) + cross(cb[j], b.p);
-      hs[j] = (i == NL - 1) ? b : b + hs[j + 1];
-    }
-  Mom htot;
-  { Mom b; b.p = M.base_mass * (ve[3] + cross(we[3], cbase)); b.n = mul(Ibase, we[3]) + cross(cbase, b.p); htot = b + hs[0] + hs[NL]; }
-  // one column of d f / d q_k for a revolute "joint" (axis ak, origin ok, subtree inertia/momentum, parent twist)
-  auto dq_column = [&](int col, v3 ak, v3 ok, const SI& sub, const Mom& hsub, v3 wp, v3 vp, v3 AlinK, int leg_first, int leg_last) {
-    const v3 s = cross(ok, ak);
-    const v3 mom1 = cross(ak, hsub.n) + cross(s, hsub.p);
-    const v3 frc1 = cross(ak, hsub.p);
-    const v3 w1 = cross(ak, wp);
-    const v3 v1 = cross(ak, vp) + cross(s, wp);
-    const Mom m2 = si_apply(sub, w1, v1);
-    const v3 dlin = frc1 - m2.p;
-    const v3 dnO = mom1 - m2.n;
-    const v3 dcom = imass * AlinK;
-    const v3 dang = dnO - cross(dcom, htot.p) - cross(com, dlin);
-    const v3 e = mk(A22i[0] * dang.x + A22i[1] * dang.y + A22i[2] * dang.z, A22i[3] * dang.x + A22i[4] * dang.y + A22i[5] * dang.z, A22i[6] * dang.x + A22i[7] * dang.y + A22i[8] * dang.z);
-    const v3 l = imass * (dlin - mk(A12[0] * e.x + A12[1] * e.y + A12[2] * e.z, A12[3] * e.x + A12[4] * e.y + A12[5] * e.z, A12[6] * e.x + A12[7] * e.y + A12[8] * e.z));
-    E.Ac[3][col] = -l.x; E.Ac[4][col] = -l.y; E.Ac[5][col] = -l.z; E.Ac[6][col] = -e.x; E.Ac[7][col] = -e.y; E.Ac[8][col] = -e.z;
-    // rows 3..5: (1/m) [ sum_{contacts moved by k} (ak x (p_i - ok)) x F_i  -  dcom x Ftot ]
-    v3 t = mk(0.0, 0.0, 0.0);
-#pragma unroll 1
-    for (int c = 0; c < NCON; ++c)
-      if (c / 2 >= leg_first && c / 2 <= leg_last) t = t + cross(cross(ak, E.pc[c] - ok), mk(u[3 * c], u[3 * c + 1], u[3 * c + 2]));
-    t = imass * (t - cross(dcom, Ftot));
-    E.Ac[0][col] = t.x; E.Ac[1][col] = t.y; E.Ac[2][col] = t.z;
-  };
-#pragma unroll 1
-  for (int k = 0; k < 3; ++k) dq_column(6 + k, bax[k], pb, tot, htot, we[k], ve[k], Alin_e[k], 0, 1);
-#pragma unroll 1
-  for (int leg = 0; leg < 2; ++leg)
-#pragma unroll 1
-    for (int i = 0; i < NL; ++i) {
-      const int j = leg * NL + i;
-      const v3 wp = (i == 0) ? we[3] : wj[j - 1];
-      const v3 vp = (i == 0) ? ve[3] : vj[j - 1];
-      dq_column(9 + j, a[j], o[j], comp_si[j], hs[j], wp, vp, Alin[j], leg, leg);
-    }
-  if (LEVEL == 1) return;
-
-  // ---------------- contact velocity Jacobians
-#pragma unroll 1
-  for (int c = 0; c < NCON; ++c) {
-    const int leg = c / 2;
-    const v3 p = E.pc[c], vcp = E.vc[c];
-    v3 Jb[3];   // base Euler columns of the geometric Jacobian (translation columns are identity)
-#pragma unroll 1
-    for (int k = 0; k < 3; ++k) Jb[k] = cross(bax[k], p - pb);
-    // chain rule through v_b(x,u): rows 6..11 of df/dx and df/du
-#pragma unroll 1
-    for (int col = 0; col < NXA; ++col) {
-      const v3 t = mk(E.Ac[3][col], E.Ac[4][col], E.Ac[5][col]) + E.Ac[6][col] * Jb[0] + E.Ac[7][col] * Jb[1] + E.Ac[8][col] * Jb[2];
-      CJ->Jx[c][0][col] = t.x; CJ->Jx[c][1][col] = t.y; CJ->Jx[c][2][col] = t.z;
-    }
-#pragma unroll 1
-    for (int j = 0; j < NJ; ++j) {
-      v3 t = mk(E.Bj[0][j], E.Bj[1][j], E.Bj[2][j]) + E.Bj[3][j] * Jb[0] + E.Bj[4][j] * Jb[1] + E.Bj[5][j] * Jb[2];
-      if (j / NL == leg) t = t + cross(a[j], p - o[j]);
-      CJ->Ju[c][0][j] = t.x; CJ->Ju[c][1][j] = t.y; CJ->Ju[c][2][j] = t.z;
-    }
-    // direct dependence on the configuration at fixed generalized velocity
-    auto direct = [&](int col, v3 ak, v3 ok, v3 wk, v3 vk) {
-      const v3 uw = vcp - (cross(wk, p) + vk);
-      const v3 t = cross(ak, uw) + cross(wk, cross(ak, p - ok));
-      CJ->Jx[c][0][col] += t.x; CJ->Jx[c][1][col] += t.y; CJ->Jx[c][2][col] += t.z;
-    };
-#pragma unroll 1
-    for (int k = 0; k < 3; ++k) direct(6 + k, bax[k], pb, we[k + 1], ve[k + 1]);
-#pragma unroll 1
-    for (int i = 0; i < NL; ++i) { const int j = leg * NL + i; direct(9 + j, a[j], o[j], wj[j], vj[j]); }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ streaming flow map (values only, registers only)
-// Same flow map / contact velocities as model_eval<NJ, 0>, restructured for the line search so that nothing per-joint is stored:
+// Flow map / contact velocities for the line search and the rollout, structured so that nothing per-joint is stored:
 //   sum_j A_j(q) qd_j = sum_i I_i (w_i^J, v_i^J),  (w_i^J, v_i^J) = sum_{j on the path to body i} qd_j S_j   (joint-induced link twist)
 // so one root-to-leaf pass per leg accumulates the total spatial inertia, the joint-induced momentum and the tip twists; no composite
 // inertias, no per-joint arrays, no local memory.  xb = x[0:12], qj = x[12:], uf = u[0:12], qd = u[12:]; f = rows 0..11 of the flow map
@@ -404,8 +185,8 @@ __device__ __noinline__ void model_values(const double (&xb)[12], const double (
 }
 
 // ------------------------------------------------------------------------------------------------ base record (values only)
-// Everything the Jacobian columns need, computed once per (stage, RK2 evaluation) by one thread and consumed by one warp
-// (k_lq_assemble: lane = column).  Layout in doubles:
+// Everything the Jacobian columns need, computed once per (stage, RK2 evaluation) by the base pass (lane = joint) and consumed by the
+// column pass (lane = column) of k_lq_pack.  Layout in doubles:
 template <int NJ>
 struct BaseDims {
   static constexpr int NX = Dims<NJ>::NX;
@@ -418,128 +199,8 @@ __device__ __forceinline__ v3 ld3(const double* p) { return mk(p[0], p[1], p[2])
 __device__ __forceinline__ void st_si(double* p, const SI& s) { p[0] = s.M; st3(p + 1, s.h); p[4] = s.I.xx; p[5] = s.I.xy; p[6] = s.I.xz; p[7] = s.I.yy; p[8] = s.I.yz; p[9] = s.I.zz; }
 __device__ __forceinline__ SI ld_si(const double* p) { SI s; s.M = p[0]; s.h = ld3(p + 1); s.I.xx = p[4]; s.I.xy = p[5]; s.I.xz = p[6]; s.I.yy = p[7]; s.I.yz = p[8]; s.I.zz = p[9]; return s; }
 
-template <int NJ>
-__device__ __noinline__ void model_base(const double* __restrict__ x, const double* __restrict__ u, double* __restrict__ base) {
-  using BD = BaseDims<NJ>;
-  constexpr int NL = Dims<NJ>::NL;
-  const DevModel& M = c_model;
-  const double mass = M.total_mass, imass = 1.0 / mass;
-  double sz, cz, sy, cy, sx, cx;
-  sincos(x[9], &sz, &cz); sincos(x[10], &sy, &cy); sincos(x[11], &sx, &cx);
-  m3 Rb;
-  Rb.m[0] = cz * cy; Rb.m[1] = cz * sy * sx - sz * cx; Rb.m[2] = cz * sy * cx + sz * sx;
-  Rb.m[3] = sz * cy; Rb.m[4] = sz * sy * sx + cz * cx; Rb.m[5] = sz * sy * cx - cz * sx;
-  Rb.m[6] = -sy;     Rb.m[7] = cy * sx;                Rb.m[8] = cy * cx;
-  const v3 pb = mk(x[6], x[7], x[8]);
-  v3 bax[3];
-  bax[0] = mk(0.0, 0.0, 1.0); bax[1] = mk(-sz, cz, 0.0); bax[2] = mk(cz * cy, sz * cy, -sy);
-  st3(base + BD::B_PB, pb);
-  for (int k = 0; k < 3; ++k) st3(base + BD::B_BAX + 3 * k, bax[k]);
-  v3 o[NJ], a[NJ], cb[NJ]; s3 Icb[NJ]; SI comp_si[NJ];
-  m3 Rtip[2];
-#pragma unroll 1
-  for (int leg = 0; leg < 2; ++leg) {
-    m3 Rp = Rb; v3 pp = pb;
-#pragma unroll 1
-    for (int i = 0; i < NL; ++i) {
-      const int j = leg * NL + i;
-      o[j] = mulc(Rp.m, M.pj[j]) + pp;
-      const m3 Rfix = mulc(Rp, M.Rj[j]);
-      a[j] = mulc(Rfix.m, M.axis[j]);
-      const m3 Rw = mul(Rfix, rodrigues(M.axis[j], x[12 + j]));
-      cb[j] = mulc(Rw.m, M.com[j]) + o[j];
-      Icb[j] = rotate_inertia(Rw, M.inertia[j]);
-      Rp = Rw; pp = o[j];
-      st3(base + BD::B_J + BD::JS * j + BD::J_O, o[j]); st3(base + BD::B_J + BD::JS * j + BD::J_A, a[j]);
-    }
-    Rtip[leg] = Rp;
-  }
-  v3 pc[NCON];
-#pragma unroll 1
-  for (int c = 0; c < NCON; ++c) { pc[c] = mulc(Rtip[c / 2].m, M.coff[c]) + o[(c / 2) * NL + NL - 1]; st3(base + BD::B_PC + 3 * c, pc[c]); }
-  const v3 cbase = mulc(Rb.m, M.base_com) + pb;
-  const s3 Ibase = rotate_inertia(Rb, M.base_inertia);
-#pragma unroll 1
-  for (int leg = 0; leg < 2; ++leg)
-#pragma unroll 1
-    for (int i = NL - 1; i >= 0; --i) {
-      const int j = leg * NL + i;
-      const SI bsi = body_si(M.mass[j], cb[j], Icb[j]);
-      comp_si[j] = (i == NL - 1) ? bsi : bsi + comp_si[j + 1];
-      st_si(base + BD::B_J + BD::JS * j + BD::J_SI, comp_si[j]);
-    }
-  const SI tot = body_si(M.base_mass, cbase, Ibase) + comp_si[0] + comp_si[NL];
-  const v3 com = imass * tot.h;
-  st_si(base + BD::B_TOT, tot); st3(base + BD::B_COM, com);
-  v3 Alin_e[3], Aang_e[3];
-#pragma unroll 1
-  for (int k = 0; k < 3; ++k) {
-    const Mom m = si_apply(tot, bax[k], cross(pb, bax[k])); Alin_e[k] = m.p; Aang_e[k] = m.n - cross(com, m.p);
-    st3(base + BD::B_ALE + 3 * k, Alin_e[k]); st3(base + BD::B_AAE + 3 * k, Aang_e[k]);
-  }
-  double A22[9], A22i[9], A12[9];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { A22[k] = Aang_e[k].x; A22[3 + k] = Aang_e[k].y; A22[6 + k] = Aang_e[k].z; A12[k] = Alin_e[k].x; A12[3 + k] = Alin_e[k].y; A12[6 + k] = Alin_e[k].z; }
-  inv3(A22, A22i);
-#pragma unroll
-  for (int i = 0; i < 9; ++i) { base[BD::B_A22I + i] = A22i[i]; base[BD::B_A12 + i] = A12[i]; }
-  v3 ml = mk(mass * x[0], mass * x[1], mass * x[2]), ma = mk(mass * x[3], mass * x[4], mass * x[5]);
-#pragma unroll 1
-  for (int j = 0; j < NJ; ++j) {
-    const Mom m = si_apply(comp_si[j], a[j], cross(o[j], a[j]));
-    const v3 al = m.p, aa = m.n - cross(com, m.p);
-    st3(base + BD::B_J + BD::JS * j + BD::J_AL, al); st3(base + BD::B_J + BD::JS * j + BD::J_AA, aa);
-    const double qd = u[12 + j]; ml = ml - qd * al; ma = ma - qd * aa;
-  }
-  const v3 w = mk(A22i[0] * ma.x + A22i[1] * ma.y + A22i[2] * ma.z, A22i[3] * ma.x + A22i[4] * ma.y + A22i[5] * ma.z, A22i[6] * ma.x + A22i[7] * ma.y + A22i[8] * ma.z);
-  const v3 vlin = imass * (ml - mk(A12[0] * w.x + A12[1] * w.y + A12[2] * w.z, A12[3] * w.x + A12[4] * w.y + A12[5] * w.z, A12[6] * w.x + A12[7] * w.y + A12[8] * w.z));
-  v3 Ftot = mk(0.0, 0.0, 0.0), tau = mk(0.0, 0.0, 0.0);
-#pragma unroll 1
-  for (int c = 0; c < NCON; ++c) { const v3 F = mk(u[3 * c], u[3 * c + 1], u[3 * c + 2]); Ftot = Ftot + F; tau = tau + cross(pc[c] - com, F); }
-  double* f = base + BD::B_F;
-  f[0] = Ftot.x * imass; f[1] = Ftot.y * imass; f[2] = Ftot.z * imass - 9.81;
-  f[3] = tau.x * imass; f[4] = tau.y * imass; f[5] = tau.z * imass;
-  f[6] = vlin.x; f[7] = vlin.y; f[8] = vlin.z; f[9] = w.x; f[10] = w.y; f[11] = w.z;
-#pragma unroll 1
-  for (int j = 0; j < NJ; ++j) f[12 + j] = u[12 + j];
-  st3(base + BD::B_FTOT, Ftot);
-  const double wr[3] = {w.x, w.y, w.z};
-  v3 we = mk(0.0, 0.0, 0.0), ve = vlin;
-  st3(base + BD::B_WE, we); st3(base + BD::B_VE, ve);
-#pragma unroll 1
-  for (int k = 0; k < 3; ++k) { we = we + wr[k] * bax[k]; ve = ve + wr[k] * cross(pb, bax[k]); st3(base + BD::B_WE + 3 * (k + 1), we); st3(base + BD::B_VE + 3 * (k + 1), ve); }
-  v3 wj[NJ], vj[NJ];
-#pragma unroll 1
-  for (int leg = 0; leg < 2; ++leg) {
-    v3 wp = we, vp = ve;
-#pragma unroll 1
-    for (int i = 0; i < NL; ++i) {
-      const int j = leg * NL + i; const double qd = u[12 + j];
-      wj[j] = wp + qd * a[j]; vj[j] = vp + qd * cross(o[j], a[j]); wp = wj[j]; vp = vj[j];
-      st3(base + BD::B_J + BD::JS * j + BD::J_W, wj[j]); st3(base + BD::B_J + BD::JS * j + BD::J_V, vj[j]);
-    }
-  }
-#pragma unroll 1
-  for (int c = 0; c < NCON; ++c) { const int tip = (c / 2) * NL + NL - 1; st3(base + BD::B_VC + 3 * c, cross(wj[tip], pc[c]) + vj[tip]); }
-  Mom hsum; hsum.n = mk(0.0, 0.0, 0.0); hsum.p = mk(0.0, 0.0, 0.0);
-#pragma unroll 1
-  for (int leg = 0; leg < 2; ++leg) {
-    Mom acc; acc.n = mk(0.0, 0.0, 0.0); acc.p = mk(0.0, 0.0, 0.0);
-#pragma unroll 1
-    for (int i = NL - 1; i >= 0; --i) {
-      const int j = leg * NL + i;
-      Mom bm; bm.p = M.mass[j] * (vj[j] + cross(wj[j], cb[j])); bm.n = mul(Icb[j], wj[j]) + cross(cb[j], bm.p);
-      acc = bm + acc;
-      st3(base + BD::B_J + BD::JS * j + BD::J_HN, acc.n); st3(base + BD::B_J + BD::JS * j + BD::J_HP, acc.p);
-    }
-    hsum = hsum + acc;
-  }
-  { Mom bm; bm.p = M.base_mass * (ve + cross(we, cbase)); bm.n = mul(Ibase, we) + cross(cbase, bm.p); hsum = hsum + bm; }
-  st3(base + BD::B_HTOT, hsum.n); st3(base + BD::B_HTOT + 3, hsum.p);
-}
-
 // ------------------------------------------------------------------------------------------------ warp-cooperative base record
-// Same quantities as model_base, computed by one warp with lane j = leg joint j (two serial chains of NL joints): per-joint data stays in
+// Computed by one warp with lane j = leg joint j (two serial chains of NL joints): per-joint data stays in
 // the lane's registers, parents / children are reached with shuffles, level by level along each leg.  The record is written to shared memory.
 __device__ __forceinline__ v3 shfl_v3(v3 a, int src) { return mk(__shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src), __shfl_sync(0xffffffffu, a.z, src)); }
 __device__ __forceinline__ m3 shfl_m3(const m3& a, int src) { m3 r; for (int i = 0; i < 9; ++i) r.m[i] = __shfl_sync(0xffffffffu, a.m[i], src); return r; }

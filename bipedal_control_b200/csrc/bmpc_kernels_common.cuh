@@ -6,24 +6,16 @@ namespace bmpc {
 
 
 constexpr double WEAK_EPS = 1e-6;   // [UPSTREAM] numeric_traits::weakEpsilon
-constexpr int WS_THREADS = 128;     // threads per CTA of the Riccati kernel (one instance per CTA)
-#ifndef LQ_MIN_BLOCKS
-#define LQ_MIN_BLOCKS 8
-#endif
+// per-tick counters (ints) read back by the host after the tick: total / maximum line-search trials, failed instances, OR of all status bits
+constexpr int CNT_TRIALS = 0, CNT_MAXTRIALS = 1, CNT_FAIL = 2, CNT_STATUS = 3, CNT_N = 8;
 #ifndef LQ_PAIR_BLOCKS
 #define LQ_PAIR_BLOCKS 2
 #endif
-#ifndef LS_BLOCKS
-#define LS_BLOCKS 6
-#endif
 #ifndef LS2_BLOCKS
-#define LS2_BLOCKS 4
+#define LS2_BLOCKS 2   // CTAs (128 threads) per SM of k_linesearch
 #endif
 #ifndef PROJ_BLOCKS
 #define PROJ_BLOCKS 4
-#endif
-#ifndef BASE_BLOCKS
-#define BASE_BLOCKS 4
 #endif
 #ifndef RIC_BLOCKS
 #define RIC_BLOCKS 3
@@ -31,15 +23,12 @@ constexpr int WS_THREADS = 128;     // threads per CTA of the Riccati kernel (on
 #ifndef RIC_WPC
 #define RIC_WPC 4   // independent instances (warps) per CTA of k_riccati_warp
 #endif
-#ifndef LQ_FUSED_BLOCKS
-#define LQ_FUSED_BLOCKS 2
-#endif
 
 template <int NJ> struct RDims;
 template <int NJ> struct SDims;
 
 struct Dev {
-  int B, NS, ME, TP, npts;
+  int B, NS, ME, TP, npts;   // NS: node slots per instance = nominal grid + 1 + max_event_nodes
   double dt_nom, horizon;
   const double* t0; const double* x0;
   const double* tgt_t; const double* tgt_x;
@@ -47,10 +36,11 @@ struct Dev {
   int* n_nodes; double* node_t; int* node_ev; double* st_t; double* st_dt; int* st_mode;
   double* xref; double* zref;
   const int* p_n; const double* p_t; const double* p_x; const double* p_u;   // previous primal solution (warm start)
+  const int* p_ev; const double* p_uff; const double* p_K;                   // rest of the previous policy (kept by an instance whose solve fails)
   double* s_x; double* s_u; double* s_uff; double* s_K;                      // new primal solution / linearisation point
-  double* lq; double* proj; double* stage; double* ric; double* base; const double* jc;
+  double* lq; double* proj; double* stage; double* ric; const double* jc;
   double* dx; double* du;
-  double* perf_trial; double* perf; double* alpha; double* norms; int* done; int* status; int* counters;
+  double* perf; double* norms; int* status; int* counters;
 };
 
 // ------------------------------------------------------------------------------------------------ helpers

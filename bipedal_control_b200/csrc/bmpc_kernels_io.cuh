@@ -14,6 +14,12 @@ __global__ void k_evaluate_policy(int B, int NS, int ME, const int* n_nodes, con
   if (b >= B) return;
   const size_t nb = (size_t)b * NS;
   const int n = n_nodes[b];
+  if (n < 1) {   // no policy (the instance was reset, or its only solve so far failed): state echoed, zero input
+    for (int i = threadIdx.x; i < NX; i += blockDim.x) xo[(size_t)b * NX + i] = xq[(size_t)b * NX + i];
+    for (int r = threadIdx.x; r < NU; r += blockDim.x) uo[(size_t)b * NU + r] = 0.0;
+    if (threadIdx.x == 0) mo[b] = ev_mode[(size_t)b * (ME + 1) + lower_bound_d(ev_t + (size_t)b * ME, n_ev[b], tq[b])];
+    return;
+  }
   int idx; double al; time_segment(times + nb, n, tq[b], idx, al);
   const int i1 = min(idx + 1, n - 1);
   for (int i = threadIdx.x; i < NX; i += blockDim.x) xo[(size_t)b * NX + i] = al * sx[(nb + idx) * NX + i] + (1.0 - al) * sx[(nb + i1) * NX + i];
@@ -35,6 +41,7 @@ __global__ void k_shift_observations(int B, int NS, double dt, const int* n_node
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const double t = t0[b] + dt;
+  if (n_nodes[b] < 1) { t0[b] = t; return; }   // no policy: the observation only advances in time
   interp_vec(times + (size_t)b * NS, sx + (size_t)b * NS * NX, n_nodes[b], NX, t, x0 + (size_t)b * NX);
   t0[b] = t;
 }

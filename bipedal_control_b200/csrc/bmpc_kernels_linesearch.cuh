@@ -4,63 +4,27 @@
 
 namespace bmpc {
 
-// ------------------------------------------------------------------------------------------------ K4: line-search trial evaluation, one thread per (instance, stage)
-template <int NJ>
-__global__ void __launch_bounds__(64, LS_BLOCKS) k_linesearch_eval(Dev d) {
-  using D = Dims<NJ>;
-  constexpr int NX = D::NX, NU = D::NU;
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = gid / d.NS, k = gid % d.NS;
-  if (b >= d.B) return;
-  if (d.done[b]) return;
-  const int N = d.n_nodes[b] - 1;
-  if (k >= N) return;
-  const size_t nb = (size_t)b * d.NS;
-  const double al = d.alpha[b];
-  double* out = d.perf_trial + (nb + k) * 3;
-  double x[NX], xn[NX], u[NU];
-  for (int i = 0; i < NX; ++i) { x[i] = d.s_x[(nb + k) * NX + i] + al * d.dx[(nb + k) * NX + i]; xn[i] = d.s_x[(nb + k + 1) * NX + i] + al * d.dx[(nb + k + 1) * NX + i]; }
-  if (d.node_ev[nb + k] == 1) {
-    double s = 0.0; for (int i = 0; i < NX; ++i) { const double e = x[i] - xn[i]; s += e * e; }
-    out[0] = 0.0; out[1] = s; out[2] = 0.0; return;
-  }
-  for (int i = 0; i < NU; ++i) u[i] = d.s_u[(nb + k) * NU + i] + al * d.du[(nb + k) * NU + i];
-  const double dt = d.st_dt[nb + k]; const int mode = d.st_mode[nb + k];
-  ModelEval<NJ> E1;
-  model_eval<NJ, 0>(x, u, E1, nullptr);
-  double x2[NX], k1[NX];
-  for (int i = 0; i < NX; ++i) { k1[i] = E1.f[i]; x2[i] = x[i] + dt * k1[i]; }
-  v3 vc[NCON]; for (int c = 0; c < NCON; ++c) vc[c] = E1.vc[c];
-  model_eval<NJ, 0>(x2, u, E1, nullptr);
-  double s = 0.0;
-  for (int i = 0; i < NX; ++i) { const double e = x[i] + 0.5 * dt * (k1[i] + E1.f[i]) - xn[i]; s += e * e; }
-  double peq = 0.0;
-  for (int leg = 0; leg < 2; ++leg) {
-    const int ca = 2 * leg, cb = 2 * leg + 1;
-    if (leg_in_stance(mode, leg)) peq += dot(vc[ca], vc[ca]) + dot(vc[cb], vc[cb]);
-    else {
-      const double zr = d.zref[(nb + k) * 2 + leg];
-      for (int t = 0; t < 2; ++t) { const int c0 = t == 0 ? ca : cb; const double ev = vc[c0].z - zr; peq += ev * ev + u[3 * c0] * u[3 * c0] + u[3 * c0 + 1] * u[3 * c0 + 1] + u[3 * c0 + 2] * u[3 * c0 + 2]; }
-    }
-  }
-  out[0] = dt * stage_cost_value<NJ>(mode, x, u, d.xref + (nb + k) * NX);
-  out[1] = dt * s; out[2] = dt * peq;
-}
+// ------------------------------------------------------------------------------------------------ K4-K6: filter line search + step + policy completion
+// ONE CTA PER INSTANCE: thread = stage.  The backtracking loop of FilterLinesearch runs inside the CTA (instances are independent, so no
+// global synchronisation, no host round trip, no per-trial launches): every trial evaluates the RK2 defect, the cost and the constraint
+// violation at (x + alpha dx, u + alpha du) for all stages of the instance on the streaming, register-only flow map (model_values: no per-joint
+// arrays, no local memory), reduces them over the block and lets thread 0 take the accept / halve decision.  The accepted step is then applied
+// (x += alpha dx, u += alpha du, uff = uff0 + alpha kappa) and, on the last SQP iteration, event nodes and the terminal node copy the policy of
+// the previous node ([UPSTREAM] incrementTrajectory + multiple_shooting::toPrimalSolution).
+// [UPSTREAM] FilterLinesearch::acceptStep (g_max, g_min: task.info:72-73; gamma_c 1e-6, armijoFactor 1e-4, alpha_decay 0.5, alpha_min 1e-4)
+//
+// Instances whose solve failed numerically (Riccati lost positive definiteness, rank anomaly of the constraint Jacobian, NaN) store nothing of
+// this tick: they keep their previous policy, or none (n_nodes = 0) if there is no previous one, so the next tick starts from valid data (upstream
+// throws in these cases and the controller stops, BipedalController.cpp:344-348; here bmpc_advance / bmpc_synchronize return BMPC_ERR_NUMERIC and
+// the other instances of the batch are unaffected).
+constexpr int FAIL_MASK = 1 | 2 | 8;
+constexpr int LS_THREADS = 128;
 
-// K4 (default): the same trial evaluation on the streaming, register-only flow map (model_values): no per-joint arrays, no local memory
+// performance of one stage at step size al: out = {dt cost, dt |defect|^2, dt |equality constraints|^2}
 template <int NJ>
-__global__ void __launch_bounds__(64, LS2_BLOCKS) k_linesearch_eval2(Dev d) {
+__device__ __forceinline__ void stage_trial(const Dev& d, size_t nb, int k, double al, double (&out)[3]) {
   using D = Dims<NJ>;
   constexpr int NX = D::NX, NU = D::NU;
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = gid / d.NS, k = gid % d.NS;
-  if (b >= d.B) return;
-  if (d.done[b]) return;
-  const int N = d.n_nodes[b] - 1;
-  if (k >= N) return;
-  const size_t nb = (size_t)b * d.NS;
-  const double al = d.alpha[b];
-  double* out = d.perf_trial + (nb + k) * 3;
   const double* __restrict__ gx = d.s_x + (nb + k) * NX; const double* __restrict__ gdx = d.dx + (nb + k) * NX;
   const double* __restrict__ gu = d.s_u + (nb + k) * NU; const double* __restrict__ gdu = d.du + (nb + k) * NU;
   if (d.node_ev[nb + k] == 1) {
@@ -129,73 +93,95 @@ __global__ void __launch_bounds__(64, LS2_BLOCKS) k_linesearch_eval2(Dev d) {
   out[0] = dt * cost; out[1] = dt * sdef; out[2] = dt * peq;
 }
 
-// ------------------------------------------------------------------------------------------------ K5: filter line search acceptance, one warp per instance
-// [UPSTREAM] FilterLinesearch::acceptStep (g_max, g_min: task.info:72-73; gamma_c 1e-6, armijoFactor 1e-4, alpha_decay 0.5, alpha_min 1e-4)
 template <int NJ>
-__global__ void __launch_bounds__(128) k_accept(Dev d) {
-  constexpr int NX = Dims<NJ>::NX;
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // broadcast: lets the compiler treat the warp index as warp-uniform
-  const int b = blockIdx.x * 4 + warp;
-  if (b >= d.B) return;
-  if (d.done[b]) return;
-  const int N = d.n_nodes[b] - 1;
+__global__ void __launch_bounds__(LS_THREADS, LS2_BLOCKS) k_linesearch(Dev d, int last_iteration) {
+  using R = RDims<NJ>;
+  constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU, NWARP = LS_THREADS / 32;
+  __shared__ double sred[NWARP][3];
+  __shared__ double s_alpha;
+  __shared__ int s_done;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = d.n_nodes[b], N = n - 1;
   const size_t nb = (size_t)b * d.NS;
-  double pc = 0.0, pd = 0.0, pe = 0.0;
-  for (int k = lane; k < N; k += 32) { const double* p = d.perf_trial + (nb + k) * 3; pc += p[0]; pd += p[1]; pe += p[2]; }
-  const double al = d.alpha[b];
-  if (lane < NX) { const double e = d.x0[(size_t)b * NX + lane] - (d.s_x[nb * NX + lane] + al * d.dx[nb * NX + lane]); pd += e * e; }
-  for (int o = 16; o > 0; o >>= 1) { pc += __shfl_xor_sync(0xffffffffu, pc, o); pd += __shfl_xor_sync(0xffffffffu, pd, o); pe += __shfl_xor_sync(0xffffffffu, pe, o); }
-  if (lane == 0) {
-    double* pf = d.perf + (size_t)b * 8;
-    const double th0 = sqrt(pf[1] + pf[2]), th = sqrt(pd + pe);
-    const double gamma_c = 1e-6, armijoFactor = 1e-4, alpha_decay = 0.5, alpha_min = 1e-4;
-    const double armijo = pf[7];
-    bool acc;
-    if (th > c_model.g_max) acc = th < (1.0 - gamma_c) * th0;
-    else if (th < c_model.g_min && th0 < c_model.g_min && armijo < 0.0) acc = pc < pf[0] + armijoFactor * al * armijo;
-    else acc = (pc < pf[0] - gamma_c * th0) || (th < (1.0 - gamma_c) * th0);
-    if (!(pc == pc) || !(pd == pd) || !(pe == pe)) { acc = false; atomicOr(&d.status[b], 8); }
-    if (acc) { pf[3] = pc; pf[4] = pd; pf[5] = pe; pf[6] = al; d.done[b] = 1; }
-    else {
-      const double an = al * alpha_decay;
-      const bool small = an * d.norms[2 * b] < c_model.delta_tol && an * d.norms[2 * b + 1] < c_model.delta_tol;
-      if (small || an < alpha_min) { pf[3] = pf[0]; pf[4] = pf[1]; pf[5] = pf[2]; pf[6] = 0.0; d.alpha[b] = 0.0; d.done[b] = 1; atomicOr(&d.status[b], 16); }
-      else { d.alpha[b] = an; atomicAdd(&d.counters[0], 1); }
+  double* pf = d.perf + (size_t)b * 8;
+  double al = 1.0;
+  int trials = 0;
+  const bool pre_fail = (d.status[b] & FAIL_MASK) != 0;
+  for (;;) {
+    double acc3[3] = {0.0, 0.0, 0.0};
+    for (int k = tid; k < N; k += LS_THREADS) {
+      double o[3]; stage_trial<NJ>(d, nb, k, al, o);
+      acc3[0] += o[0]; acc3[1] += o[1]; acc3[2] += o[2];
+    }
+    if (tid < NX) { const double e = d.x0[(size_t)b * NX + tid] - (d.s_x[nb * NX + tid] + al * d.dx[nb * NX + tid]); acc3[1] += e * e; }   // initial-state defect
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { acc3[0] += __shfl_xor_sync(0xffffffffu, acc3[0], o); acc3[1] += __shfl_xor_sync(0xffffffffu, acc3[1], o); acc3[2] += __shfl_xor_sync(0xffffffffu, acc3[2], o); }
+    if (lane == 0) { sred[wid][0] = acc3[0]; sred[wid][1] = acc3[1]; sred[wid][2] = acc3[2]; }
+    __syncthreads();
+    ++trials;
+    if (tid == 0) {
+      double pc = 0.0, pd = 0.0, pe = 0.0;
+#pragma unroll
+      for (int w = 0; w < NWARP; ++w) { pc += sred[w][0]; pd += sred[w][1]; pe += sred[w][2]; }
+      const double th0 = sqrt(pf[1] + pf[2]), th = sqrt(pd + pe);
+      const double gamma_c = 1e-6, armijoFactor = 1e-4, alpha_decay = 0.5, alpha_min = 1e-4;
+      const double armijo = pf[7];
+      bool acc;
+      if (th > c_model.g_max) acc = th < (1.0 - gamma_c) * th0;
+      else if (th < c_model.g_min && th0 < c_model.g_min && armijo < 0.0) acc = pc < pf[0] + armijoFactor * al * armijo;
+      else acc = (pc < pf[0] - gamma_c * th0) || (th < (1.0 - gamma_c) * th0);
+      const bool nan_ = !(pc == pc) || !(pd == pd) || !(pe == pe) || !(armijo == armijo);
+      int done = 0; double anext = al;
+      if (nan_ || pre_fail) { pf[3] = pf[0]; pf[4] = pf[1]; pf[5] = pf[2]; pf[6] = 0.0; anext = 0.0; done = 1; if (nan_) atomicOr(&d.status[b], 8); }
+      else if (acc) { pf[3] = pc; pf[4] = pd; pf[5] = pe; pf[6] = al; done = 1; }
+      else {
+        const double an = al * alpha_decay;
+        const bool small = an * d.norms[2 * b] < c_model.delta_tol && an * d.norms[2 * b + 1] < c_model.delta_tol;
+        if (small || an < alpha_min) { pf[3] = pf[0]; pf[4] = pf[1]; pf[5] = pf[2]; pf[6] = 0.0; anext = 0.0; done = 1; atomicOr(&d.status[b], 16); }
+        else anext = an;
+      }
+      s_alpha = anext; s_done = done;
+    }
+    __syncthreads();
+    al = s_alpha;
+    if (s_done) break;
+  }
+  // ---- take the step
+  const int st = d.status[b];   // written by thread 0 before the barrier above (same CTA) or by earlier kernels
+  const bool fail = (st & FAIL_MASK) != 0;
+  if (tid == 0) {
+    atomicAdd(&d.counters[CNT_TRIALS], trials); atomicMax(&d.counters[CNT_MAXTRIALS], trials);
+    if (st) atomicOr(&d.counters[CNT_STATUS], st);
+    if (fail) atomicAdd(&d.counters[CNT_FAIL], 1);
+  }
+  if (fail) {
+    // the instance keeps its previous policy (time grid included), or has none (n_nodes = 0) if there is no previous one: the next tick then
+    // cold-starts it from the initializer.  Nothing computed by this tick is stored.
+    const int pn = d.p_n ? d.p_n[b] : 0;
+    for (int i = tid; i < pn; i += LS_THREADS) { d.node_t[nb + i] = d.p_t[nb + i]; d.node_ev[nb + i] = d.p_ev[nb + i]; }
+    for (int i = tid; i < pn * NX; i += LS_THREADS) d.s_x[nb * NX + i] = d.p_x[nb * NX + i];
+    for (int i = tid; i < pn * NU; i += LS_THREADS) { d.s_u[nb * NU + i] = d.p_u[nb * NU + i]; d.s_uff[nb * NU + i] = d.p_uff[nb * NU + i]; }
+    for (size_t i = tid; i < (size_t)pn * NU * NX; i += LS_THREADS) d.s_K[nb * (size_t)(NU * NX) + i] = d.p_K[nb * (size_t)(NU * NX) + i];
+    __syncthreads();
+    if (tid == 0) d.n_nodes[b] = pn;
+    return;
+  }
+  if (al != 0.0) {
+    for (int i = tid; i < n * NX; i += LS_THREADS) d.s_x[nb * NX + i] += al * d.dx[nb * NX + i];
+    for (int i = tid; i < N * NU; i += LS_THREADS) {
+      const int k = i / NU, c = i - k * NU;
+      if (d.node_ev[nb + k] == 1) continue;
+      d.s_u[nb * NU + i] += al * d.du[nb * NU + i]; d.s_uff[nb * NU + i] += al * d.ric[(nb + k) * R::KREC + R::K_KAP + c];
     }
   }
-}
-
-// ------------------------------------------------------------------------------------------------ K6: take the step, finish the policy
-template <int NJ>
-__global__ void k_update(Dev d) {   // one thread per (instance, node, component): coalesced x += alpha dx, u += alpha du, uff += alpha kappa
-  using R = RDims<NJ>;
-  constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU;
-  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t node = gid / NX; const int i = (int)(gid % NX);
-  const int b = (int)(node / d.NS), k = (int)(node % d.NS);
-  if (b >= d.B) return;
-  const int n = d.n_nodes[b];
-  if (k >= n) return;
-  const size_t nb = (size_t)b * d.NS;
-  const double al = d.alpha[b];
-  d.s_x[(nb + k) * NX + i] += al * d.dx[(nb + k) * NX + i];
-  if (i < NU && k < n - 1 && d.node_ev[nb + k] != 1) {
-    d.s_u[(nb + k) * NU + i] += al * d.du[(nb + k) * NU + i];
-    d.s_uff[(nb + k) * NU + i] += al * d.ric[(nb + k) * R::KREC + R::K_KAP + i];
-  }
-}
-// event nodes and the terminal node copy input / feedforward / gain of the previous node ([UPSTREAM] toPrimalSolution)
-template <int NJ>
-__global__ void k_policy_fill(Dev d) {
-  constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU;
-  const int b = blockIdx.x;
-  const int n = d.n_nodes[b];
-  const size_t nb = (size_t)b * d.NS;
+  if (!last_iteration) return;
+  __syncthreads();
+  // ---- event nodes and the terminal node copy input / feedforward / gain of the previous node
   for (int k = 1; k < n; ++k) {
     const bool copy = (k == n - 1) || d.node_ev[nb + k] == 1;
     if (!copy) continue;
-    for (int i = threadIdx.x; i < NU; i += blockDim.x) { d.s_u[(nb + k) * NU + i] = d.s_u[(nb + k - 1) * NU + i]; d.s_uff[(nb + k) * NU + i] = d.s_uff[(nb + k - 1) * NU + i]; }
-    for (int i = threadIdx.x; i < NU * NX; i += blockDim.x) d.s_K[(nb + k) * (size_t)(NU * NX) + i] = d.s_K[(nb + k - 1) * (size_t)(NU * NX) + i];
+    for (int i = tid; i < NU; i += LS_THREADS) { d.s_u[(nb + k) * NU + i] = d.s_u[(nb + k - 1) * NU + i]; d.s_uff[(nb + k) * NU + i] = d.s_uff[(nb + k - 1) * NU + i]; }
+    for (int i = tid; i < NU * NX; i += LS_THREADS) d.s_K[(nb + k) * (size_t)(NU * NX) + i] = d.s_K[(nb + k - 1) * (size_t)(NU * NX) + i];
     __syncthreads();
   }
 }

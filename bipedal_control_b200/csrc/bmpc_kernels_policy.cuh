@@ -239,7 +239,6 @@ __global__ void __launch_bounds__(128) k_forward(Dev d) {
     double* pf = d.perf + (size_t)b * 8;
     pf[0] = pc; pf[1] = pd + s0; pf[2] = pe; pf[7] = armijo;
     d.norms[2 * b] = sqrt(dxn); d.norms[2 * b + 1] = sqrt(dun);
-    d.alpha[b] = 1.0; d.done[b] = 0;
   }
 }
 

@@ -43,7 +43,112 @@ __global__ void k_stage_static(double* stage, size_t nrec) {
   for (int r = 0; r < 3; ++r) { so[S::S_AB + r * S::LDA + r] = 1.0; so[S::S_AB + (6 + r) * S::LDA + 6 + r] = 1.0; }
 }
 
-// Lane roles after the QR (one column of W = [Px | Pe | N] per lane, in FULL-STATE column order so that the tensor-core tiles line up with
+// ------------------------------------------------------------------------------------------------ upstream's projection: Eigen::FullPivLU
+// LinearAlgebra::luConstraintProjection [UPSTREAM] (selected by projectStateInputEqualityConstraints, task.info:76):
+//   lu = FullPivLU(D);  Pu = lu.kernel();  Px = -lu.solve(C);  Pe = -lu.solve(e)
+// i.e. Gaussian elimination with complete pivoting, rank = #pivots above eps * min(rows, cols) * |largest pivot|, solve() satisfies the
+// `rank` pivot rows exactly, ignores the dependent ones (the sixth row of every stance foot) and sets the free unknowns to zero, kernel()
+// is [-U11^-1 U12; I] in the pivot ordering.  Restated here for the structure of this problem: the zero-force rows of open contacts are
+// identity rows on force columns that no other row touches, so they are pivots whose elimination changes nothing; the closed-contact force
+// columns are zero and stay free; what remains is the complete-pivoting elimination of the joint block Dv (NR x NJ raw velocity rows), with
+// the identity pivots only entering the rank threshold (largest pivot >= 1, min(rows, cols) of the full matrix).
+// (tests/test_oracle_kat.py::test_complete_pivoting_on_joint_block_equals_fullpivlu_on_stacked_rows checks this reduction on the CPU.)
+// Implementation: Gauss-Jordan on the augmented columns [Dv | Cv | ev], one column per lane (G1: 34 columns, lanes 0 and 1 carry a second
+// one), rows in registers and never swapped physically.  Per pivot: lane-local maximum over the unused rows, exact warp arg-max of the
+// 64-bit pattern with two REDUX steps + ballot (first maximum in column order, as Eigen's column-major visitor), the multipliers of the pivot
+// column are broadcast through a double-buffered shared-memory vector, every lane eliminates its own column (above AND below the pivot, so
+// no back substitution is needed: afterwards row r of column c holds U11^-1 L^-1 P c up to the pivot scale).  The result columns
+// -col[row(k)] / pivot(k) are scattered into W (shared memory) at the pivot column's joint index.
+template <int NJ, int NR>
+__device__ __forceinline__ int lu_project(const double* __restrict__ rec, double* __restrict__ W, int ldw, double* __restrict__ sF, int* __restrict__ sPc, double* __restrict__ sIp,
+                                          int lane, int n_open) {
+  using D = Dims<NJ>;
+  constexpr int NXA = D::NXA, NU = D::NU, NCOLS = NJ + NXA + 1, SD = NR < NJ ? NR : NJ;
+  constexpr bool TWO = NCOLS > 32;
+  static_assert(NCOLS <= 64 && NR % 2 == 0 && NR <= D::MAXROWS, "column / row capacity of the in-warp elimination");
+  double c0[NR], c1[TWO ? NR : 1];
+  {
+    const int j = lane;
+#pragma unroll
+    for (int i = 0; i < NR; ++i) c0[i] = j < NJ ? rec[D::R_DV + i * NJ + j] : (j < NJ + NXA ? rec[D::R_CV + i * NXA + (j - NJ)] : (j == NJ + NXA ? rec[D::R_EV + i] : 0.0));
+    if constexpr (TWO) {
+      const int j2 = lane + 32;
+#pragma unroll
+      for (int i = 0; i < NR; ++i) c1[i] = j2 < NJ + NXA ? rec[D::R_CV + i * NXA + (j2 - NJ)] : (j2 == NJ + NXA ? rec[D::R_EV + i] : 0.0);
+    }
+  }
+  if (lane < NR) sPc[lane] = -1;
+  unsigned rowdone = 0u; bool used = false, stop = false; int rank = 0;
+  double maxpiv = n_open > 0 ? 1.0 : 0.0;
+  const int sdfull = (NR + 3 * n_open) < NU ? (NR + 3 * n_open) : NU;
+  const double epsd = 2.220446049250313e-16 * (double)sdfull;
+#pragma unroll
+  for (int kk = 0; kk < SD; ++kk) {
+    if (!stop) {   // warp uniform
+      double best = -1.0; int bi = 0;
+#pragma unroll
+      for (int i = 0; i < NR; ++i) { const double a_ = fabs(c0[i]); if (!((rowdone >> i) & 1u) && a_ > best) { best = a_; bi = i; } }
+      const bool cand = lane < NJ && !used;
+      const unsigned long long key = cand ? (unsigned long long)__double_as_longlong(best) : 0ull;
+      const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+      const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+      const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+      if ((mhi | mlo) == 0u) stop = true;   // the remaining block is exactly zero (Eigen: m_nonzero_pivots = k)
+      else {
+        const unsigned win = __ballot_sync(0xffffffffu, cand && hi == mhi && lo == mlo);
+        const int bl = __ffs(win) - 1;
+        const int prow = __shfl_sync(0xffffffffu, bi, bl);
+        double cp0 = 0.0, cp1 = 0.0;   // own elements of the pivot row (dynamic row index -> predicated moves)
+#pragma unroll
+        for (int i = 0; i < NR; ++i) if (i == prow) { cp0 = c0[i]; if constexpr (TWO) cp1 = c1[i]; }
+        const double p = __shfl_sync(0xffffffffu, cp0, bl);
+        const double ap = fabs(p), mp = fmax(maxpiv, ap);
+        if (!(ap > epsd * mp)) stop = true;   // below Eigen's rank threshold: with complete pivoting everything that follows is, too
+        else {
+          maxpiv = mp;
+          const double ip = 1.0 / p;
+          double* F = sF + (kk & 1) * 16;
+          if (lane == bl) {
+#pragma unroll
+            for (int i = 0; i < NR; i += 2) reinterpret_cast<double2*>(F)[i >> 1] = make_double2(i == prow ? 0.0 : c0[i] * ip, i + 1 == prow ? 0.0 : c0[i + 1] * ip);
+            used = true;
+          }
+          if (lane == 0) { sPc[prow] = bl; sIp[prow] = ip; }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < NR; i += 2) {
+            const double2 f = reinterpret_cast<const double2*>(F)[i >> 1];
+            c0[i] = fma(-f.x, cp0, c0[i]); c0[i + 1] = fma(-f.y, cp0, c0[i + 1]);
+            if constexpr (TWO) { c1[i] = fma(-f.x, cp1, c1[i]); c1[i + 1] = fma(-f.y, cp1, c1[i + 1]); }
+          }
+          rowdone |= 1u << prow; ++rank;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // scatter: W column of this lane's column (full-state order, affine column 6, kernel columns 24 + t in the order of the free joint columns)
+  const unsigned free_mask = __ballot_sync(0xffffffffu, lane < NJ && !used);
+  auto wcol = [&](int j) {
+    if (j < NJ) { const int w = 24 + __popc(free_mask & ((1u << j) - 1u)); return (used || w >= 32) ? -1 : w; }
+    if (j < NJ + NXA) { const int c = j - NJ; return c < 6 ? c : c + 3; }
+    return j == NJ + NXA ? 6 : -1;
+  };
+  const int wl0 = wcol(lane);
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    const int pc = sPc[i];
+    if (pc >= 0) {
+      const double s_ = -sIp[i];
+      if (wl0 >= 0) W[pc * ldw + wl0] = c0[i] * s_;
+      if constexpr (TWO) { const int wl1 = (lane + 32 < NCOLS) ? wcol(lane + 32) : -1; if (wl1 >= 0) W[pc * ldw + wl1] = c1[i] * s_; }
+    }
+  }
+  if (lane < NJ && !used && wl0 >= 0) W[lane * ldw + wl0] = 1.0;
+  return rank;
+}
+
+// Lane roles after the projection (one column of W = [Px | Pe | N] per lane, in FULL-STATE column order so that the tensor-core tiles line up with
 // the stage record): lane L < 24 = state column L (L = 6 carries the affine column Pe: base-position columns 6..8 of Px are structurally
 // zero; 7, 8 and the padding lanes stay zero), lane 24 + t = null-space column t.  The reduced input is ordered [null-space (mj) | closed-contact
 // forces (3 nclosed)], so the null rows / columns are tile aligned as well.
@@ -52,18 +157,20 @@ __global__ void k_stage_static(double* stage, size_t nrec) {
 //                                    row 6 / column 6 hold the qt / rt corrections, tiles (3, b < 3) are Pt, tile (3, 3) the null block of Rt;
 //   AJ = B_d[:, joints] W (16 x 32): joint part of At rows 3..11 (stored as row-major pairs), bt, null-space columns of Bt.
 // Z^T = W^T Rj is formed first and reused from registers as the B operand of M (same register-chaining trick as k_riccati_warp).
-template <int NJ>
+template <int NJ, bool LU>
 __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
   using D = Dims<NJ>; using S = SDims<NJ>;
   constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, MP = S::MP, LDA = S::LDA;
   constexpr int WPB = 4;
   constexpr int LDW = 34, LDR = 18, LDJ = 20;   // leading dimensions = 2 mod 4: k-permuted fragment loads are conflict free
-  __shared__ double sM[WPB][NJ][12];     // Dv^T  (NJ x r), r <= 10
-  __shared__ double sV[WPB][10][NJ];     // Householder vectors (zero padded)
-  __shared__ double sBeta[WPB][20];      // beta (10) | 1 / R[k][k] (10)
-  __shared__ double sG[WPB][10][NXA + 1];   // [Cv | ev]; after the triangular solves: the padded joint block of B_d
+  __shared__ double sM[LU ? 1 : WPB][NJ][12];     // QR: Dv^T  (NJ x r), r <= 10
+  __shared__ double sV[LU ? 1 : WPB][10][NJ];     // QR: Householder vectors (zero padded)
+  __shared__ __align__(16) double sBeta[WPB][32]; // QR: beta (10) | 1 / R[k][k] (10);  LU: multipliers of the pivot column, double buffered (2 x 16)
+  __shared__ double sIpv[WPB][12];                // LU: reciprocal pivot of the step that used row i
+  __shared__ int sPcl[WPB][12];                   // LU: joint column of the pivot that used row i (-1: dependent row, ignored as by FullPivLU::solve)
+  __shared__ double sG[WPB][10][NXA + 1];   // QR: [Cv | ev]; afterwards (both variants): the padded joint block of B_d
   __shared__ double sBd[WPB][9 * (12 + NJ)];  // B_d rows 3..11
-  __shared__ double sW[WPB][16][LDW];        // W, rows >= NJ zero
+  __shared__ __align__(16) double sW[WPB][16][LDW];        // W, rows >= NJ zero
   __shared__ double sMisc[WPB][32];          // r_j (16) | open-contact correction of bt rows 3..11 (16)
   __shared__ double sRjP[16][LDR];           // joint block of R (model constant), zero padded
   __shared__ double sQd[24];
@@ -87,9 +194,49 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
   }
   const DevModel& M = c_model;
   const int r = (int)rec[D::R_MISC + D::M_NROWS];
-  double (*Mt)[12] = sM[warp]; double (*V)[NJ] = sV[warp]; double* beta = sBeta[warp]; double* rinv = sBeta[warp] + 10; double (*G)[NXA + 1] = sG[warp];
+  const int mode = (int)rec[D::R_MISC + D::M_MODE];
+  const bool st0 = leg_in_stance(mode, 0), st1 = leg_in_stance(mode, 1);
+  double (*G)[NXA + 1] = sG[warp];
   double (*W)[LDW] = sW[warp];
   const double* Bd = sBd[warp];
+  bool anomaly = false;
+  int mj = 0;
+  // lane roles (see the header comment)
+  const bool is_x = lane < 6 || (lane >= 9 && lane < NX), is_aff = lane == 6, is_rhs = is_x || is_aff;
+  const int gc = is_aff ? NXA : (lane < 6 ? lane : lane - 3);   // column of [Cv | ev] / compressed column index of this lane
+  double y[NJ];
+  if constexpr (LU) {
+    {   // stage B_d rows 3..11 and r_j; zero W
+      constexpr int N3 = (9 * NU + 31) / 32;
+      double t3[N3];
+#pragma unroll
+      for (int i = 0; i < N3; ++i) { const int e = lane + 32 * i; t3[i] = e < 9 * NU ? rec[D::R_BD + e] : 0.0; }
+      const double trj = lane < NJ ? rec[D::R_R + 12 + lane] : 0.0;
+      for (int i = lane; i < 16 * LDW / 2; i += 32) reinterpret_cast<double2*>(&W[0][0])[i] = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int i = 0; i < N3; ++i) { const int e = lane + 32 * i; if (e < 9 * NU) sBd[warp][e] = t3[i]; }
+      if (lane < 16) sMisc[warp][lane] = trj;
+    }
+    const int n_open = 4 - 2 * (int(st0) + int(st1));
+    int rank;
+    switch (r) {   // raw velocity rows: 3 per closed contact, 1 per open contact
+      case 4: rank = lu_project<NJ, 4>(rec, &W[0][0], LDW, sBeta[warp], sPcl[warp], sIpv[warp], lane, n_open); break;
+      case 8: rank = lu_project<NJ, 8>(rec, &W[0][0], LDW, sBeta[warp], sPcl[warp], sIpv[warp], lane, n_open); break;
+      default: rank = lu_project<NJ, 12>(rec, &W[0][0], LDW, sBeta[warp], sPcl[warp], sIpv[warp], lane, n_open); break;
+    }
+    const int expect = (st0 ? 5 : 2) + (st1 ? 5 : 2);
+    anomaly = rank < (expect < NJ ? expect : NJ);
+    mj = NJ - rank;
+    if (mj > 8) { mj = 8; anomaly = true; }   // the null-space lanes / record hold 8 directions (H1 FLY: 6, G1 FLY: 8)
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) y[i] = W[i][lane];
+    const bool is_null = lane >= 24 && lane - 24 < mj;
+    if (is_x) { for (int i = 0; i < NJ; ++i) out[D::P_PX + i * NXA + gc] = y[i]; }
+    else if (is_aff) { for (int i = 0; i < NJ; ++i) out[D::P_PE + i] = y[i]; }
+    else if (is_null) { for (int i = 0; i < NJ; ++i) out[D::P_N + i * 8 + lane - 24] = y[i]; }
+  } else {
+  double (*Mt)[12] = sM[warp]; double (*V)[NJ] = sV[warp]; double* beta = sBeta[warp]; double* rinv = sBeta[warp] + 10;
   {   // stage Dv^T, [Cv | ev] and B_d rows 3..11: all global loads are issued before the first shared-memory store (fixed trip counts;
       // rows >= r hold stale but finite data and are never used)
     constexpr int N1 = (10 * NJ + 31) / 32, N2 = (10 * NXA + 31) / 32, N3 = (9 * NU + 31) / 32;
@@ -113,7 +260,6 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
   }
   for (int i = lane; i < 10 * NJ; i += 32) V[i / NJ][i % NJ] = 0.0;
   __syncwarp();
-  bool anomaly = false;
   double rmax = 0.0;
   // Householder QR with compile-time trip counts (rows beyond r are skipped by the warp-uniform test kk < r).  Lane c < r keeps its
   // column of Dv^T in registers; the reflector of column kk is broadcast from lane kk with shuffles (no shared-memory round trips).
@@ -154,12 +300,8 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
 #pragma unroll
   for (int i = 0; i < NJ; ++i) if (lane < r) Mt[i][lane] = colv[i];   // R (upper triangle) for the triangular solve below
   __syncwarp();
-  // lane roles (see the header comment)
-  const int mj = NJ - r;
-  const bool is_x = lane < 6 || (lane >= 9 && lane < NX), is_aff = lane == 6, is_rhs = is_x || is_aff;
+  mj = NJ - r;
   const bool is_null = lane >= 24 && lane - 24 < mj;
-  const int gc = is_aff ? NXA : (lane < 6 ? lane : lane - 3);   // column of [Cv | ev] / compressed column index of this lane
-  double y[NJ];
 #pragma unroll
   for (int i = 0; i < NJ; ++i) y[i] = 0.0;
   if (is_rhs) {   // z = R^-T g  (R^T lower triangular: R[l][i] = Mt[l][i] for l <= i)
@@ -197,9 +339,8 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) W[i][lane] = (i < NJ) ? y[i < NJ ? i : 0] : 0.0;   // idle lanes hold y = 0
+  }
   const double dt = rec[D::R_MISC + D::M_DT], dq = rec[D::R_MISC + D::M_DQ], dr = rec[D::R_MISC + D::M_DR];
-  const int mode = (int)rec[D::R_MISC + D::M_MODE];
-  const bool st0 = leg_in_stance(mode, 0), st1 = leg_in_stance(mode, 1);
   const int nclosed = 2 * (int(st0) + int(st1));
   const int m = 3 * nclosed + mj;
   if (lane < 12) out[D::P_FO + lane] = rec[D::R_FO + lane];

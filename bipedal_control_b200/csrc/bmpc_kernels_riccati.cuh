@@ -24,42 +24,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-// ------------------------------------------------------------------------------------------------ DMMA tile GEMM in shared memory
-// C[8MT x 8NT] = (ACC ? C : 0) + sign * op(A) op(B), K = 4 KT.  TA: A is given transposed (As[k][m]); TB: B is given transposed (Bs[n][k]).
-// Output tiles are distributed round-robin over warps [W0, W0 + NW) of the CTA; each warp interleaves the k-loops of its tiles
-// (independent accumulator chains).  All leading dimensions are == 4 or 12 (mod 16) doubles: every fragment load is bank-conflict free.
-template <int MT, int NT, int KT, bool TA, bool TB, bool ACC, bool NEG, int NW, int W0>
-__device__ __forceinline__ void gemm_tiles(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, double* __restrict__ C, int ldc, int warp, int lane) {
-  constexpr int TPW = (MT * NT + NW - 1) / NW;
-  const int lr = lane >> 2, lc = lane & 3;
-  const int w = warp - W0;
-  if (w < 0 || w >= NW) return;
-  double c0[TPW], c1[TPW];
-  int mt[TPW], nt[TPW];
-#pragma unroll
-  for (int i = 0; i < TPW; ++i) {
-    const int t = w + i * NW;
-    mt[i] = t / NT; nt[i] = t % NT;
-    c0[i] = 0.0; c1[i] = 0.0;
-    if (ACC && t < MT * NT) { const double* cp = C + (8 * mt[i] + lr) * ldc + 8 * nt[i] + 2 * lc; c0[i] = cp[0]; c1[i] = cp[1]; }
-  }
-#pragma unroll
-  for (int kk = 0; kk < KT; ++kk) {
-#pragma unroll
-    for (int i = 0; i < TPW; ++i) {
-      if (w + i * NW < MT * NT) {
-        double a = TA ? A[(4 * kk + lc) * lda + 8 * mt[i] + lr] : A[(8 * mt[i] + lr) * lda + 4 * kk + lc];
-        const double bb = TB ? B[(8 * nt[i] + lr) * ldb + 4 * kk + lc] : B[(4 * kk + lc) * ldb + 8 * nt[i] + lr];
-        if (NEG) a = -a;
-        dmma884(c0[i], c1[i], a, bb);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < TPW; ++i)
-    if (w + i * NW < MT * NT) { double* cp = C + (8 * mt[i] + lr) * ldc + 8 * nt[i] + 2 * lc; cp[0] = c0[i]; cp[1] = c1[i]; }
-}
-
 // Right-looking Cholesky of the (symmetric, fully stored) M x M matrix G fused with the forward substitution of [H | g], one warp,
 // shuffles only.  Lane l < MP holds column l of G in gc[], lane c holds column c of [H | g] in hc[].  On return lane j holds
 // column j of L in gc[] (rows > j; the diagonal entry holds 1 / L[j][j]) and hc[] holds Y = L^-1 H (yg in the g lane).  Serial chain per pivot: shuffle -> rsqrt -> FMA.
@@ -89,25 +53,6 @@ __device__ __forceinline__ bool chol_forward(double (&gc)[MP], double (&hc)[MP],
   return not_pd;
 }
 
-// ------------------------------------------------------------------------------------------------ K2: backward Riccati recursion
-// One CTA (4 warps) per instance; S, At, SA, Bt, SB, H, G live in shared memory, padded to NXP = 24 states / MP = 16 reduced inputs.
-//   SA = S At, SB = S Bt, sb = s + S bt;  H = Pt + Bt^T SA, G = Rt + Bt^T SB, g = rt + Bt^T sb
-//   G = L L^T, Y = L^-1 H, yg = L^-1 g                    (warp 0; warps 1-3 compute At^T SA meanwhile)
-//   S' = Qt + At^T SA - Y^T Y,  s' = qt + At^T sb - Y^T yg
-// The gains Kt = -L^-T Y are recovered off the critical path by k_policy_expand.
-template <int NJ>
-struct RicSmem {
-  static constexpr int NXP = 24, MP = 16, LD = 28, LDM = 20;
-  double S[NXP * LD], At[NXP * LD], SA[NXP * LD];
-  double Bt[NXP * LDM], SB[NXP * LDM];
-  double H[MP * LD], G[MP * LDM];
-  double s[NXP], sb[NXP], bt[NXP], qt[NXP], snew[NXP], qd[NXP];
-  double rt[MP], g[MP];
-  double lcol[2][MP + 2];
-  alignas(16) double stage[SDims<NJ>::SREC];   // TMA-staged stage record (refilled right after the scatter phase)
-  alignas(8) unsigned long long bar;
-};
-
 template <int NJ>
 struct RDims {
   static constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU, MP = 16;
@@ -115,141 +60,6 @@ struct RDims {
   static constexpr int K_Y = 0, K_YG = K_Y + MP * NX, K_L = K_YG + MP, K_KAP = K_L + MP * MP, K_PHI = K_KAP + NU, K_SPHI = K_PHI + NX * NX, K_G = K_SPHI + NX,
                        K_MISC = K_G + NX, KREC = ((K_MISC + 2 + 3) / 4) * 4;
 };
-
-template <int NJ>
-__global__ void __launch_bounds__(WS_THREADS, 4) k_riccati(Dev d) {
-  using D = Dims<NJ>; using R = RDims<NJ>; using SM = RicSmem<NJ>; using S = SDims<NJ>;
-  constexpr int NX = D::NX, NXA = D::NXA, NXR = S::NXR, NXP = SM::NXP, MP = SM::MP, LD = SM::LD, LDM = SM::LDM;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  SM& sm = *reinterpret_cast<SM*>(smem_raw);
-  const int b = blockIdx.x;
-  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-  const int N = d.n_nodes[b] - 1;
-  const size_t nb = (size_t)b * d.NS;
-  const double imass = 1.0 / c_model.total_mass;
-  // warp w runs on SM sub-partition w % 4: rotate the serial roles (Cholesky, mat-vecs) over the CTAs so that co-resident CTAs
-  // do not pile their serial FP64 work onto the same sub-partition
-  const int cw = blockIdx.x & 3;            // Cholesky warp of this CTA
-  const int vw = (warp - cw - 1) & 3;       // 0..2 for the other three warps, 3 for the Cholesky warp
-  const int mw = (cw + 2) & 3;              // mat-vec warp
-  // terminal value function: zero (no terminal cost installed)
-  for (int i = tid; i < NXP * LD; i += WS_THREADS) { sm.S[i] = 0.0; sm.At[i] = 0.0; sm.SA[i] = 0.0; }
-  for (int i = tid; i < NXP * LDM; i += WS_THREADS) { sm.Bt[i] = 0.0; sm.SB[i] = 0.0; }
-  for (int i = tid; i < MP * LD; i += WS_THREADS) sm.H[i] = 0.0;   // padded columns must stay zero (shared memory is not cleared between CTAs)
-  for (int i = tid; i < MP * LDM; i += WS_THREADS) sm.G[i] = 0.0;
-  for (int i = tid; i < NXP; i += WS_THREADS) { sm.s[i] = 0.0; sm.sb[i] = 0.0; sm.bt[i] = 0.0; sm.qt[i] = 0.0; sm.snew[i] = 0.0; sm.qd[i] = 0.0; }
-  constexpr unsigned REC_BYTES = S::SREC * sizeof(double);
-  if (tid == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
-  __syncthreads();
-  if (tid == 0 && N >= 1) tma_load_1d(sm.stage, d.stage + (nb + N - 1) * S::SREC, REC_BYTES, &sm.bar);
-  unsigned phase_bit = 0;
-  for (int k = N - 1; k >= 0; --k) {
-    mbar_wait(&sm.bar, phase_bit);
-    phase_bit ^= 1u;
-    const double* sr = sm.stage;
-    double* ric = d.ric + (nb + k) * R::KREC;
-    const double* meta = sr + S::S_META;
-    const bool is_event = meta[S::T_TYPE] != 0.0;
-    if (is_event) {   // S unchanged (A = I, Q = 0, no input); s <- s + S b
-      if (tid < NX) sm.bt[tid] = sr[S::S_B + tid];
-      __syncthreads();
-      if (tid == 0 && k >= 1) { fence_proxy_async(); tma_load_1d(sm.stage, d.stage + (nb + k - 1) * S::SREC, REC_BYTES, &sm.bar); }
-      if (tid < NX) { double a = sm.s[tid]; for (int c = 0; c < NX; ++c) a += sm.S[tid * LD + c] * sm.bt[c]; sm.snew[tid] = a; }
-      __syncthreads();
-      if (tid < NX) sm.s[tid] = sm.snew[tid];
-      __syncthreads();
-      continue;
-    }
-    const int m = (int)meta[S::T_M], mj = (int)meta[S::T_MJ], nclosed = (int)meta[S::T_NCLOSED], mode = (int)meta[S::T_MODE];
-    const double dt = meta[S::T_DT];
-    const bool st0 = leg_in_stance(mode, 0);
-    // ---- phase 1: copy the projected stage record into the padded operand matrices (lane = column, warp = row stride)
-    {
-      for (int r = warp; r < NX; r += 4) if (lane < NXP) sm.At[r * LD + lane] = sr[S::S_AB + r * S::LDA + lane];
-      const int bc = lane & 15, bh = lane >> 4;
-      for (int r = 2 * warp + bh; r < NX; r += 8) sm.Bt[r * LDM + bc] = sr[S::S_AB + r * S::LDA + 24 + bc];
-      for (int r = warp; r < MP; r += 4) if (lane < NXP) sm.H[r * LD + lane] = sr[S::prf(r, lane)];           // H <- Pt
-      for (int r = 2 * warp + bh; r < MP; r += 8) sm.G[r * LDM + bc] = sr[S::prf(r, 24 + bc)];                // G <- Rt
-    }
-    if (tid < NX) { sm.bt[tid] = sr[S::S_B + tid]; sm.qt[tid] = sr[S::S_Q + tid]; }
-    if (tid >= 32 && tid < 32 + MP) sm.rt[tid - 32] = sr[S::S_R + tid - 32];
-    // Qt entries this thread adds in phase 6 (pairs r <= c), held in registers so that the staging buffer can be refilled now
-    constexpr int QPT = (NX + 3) / 4;
-    double qreg[QPT];
-#pragma unroll
-    for (int q = 0; q < QPT; ++q) {
-      const int r = warp + 4 * q, c = lane;
-      double a = 0.0;
-      if (r < NX && c < NX && c >= r) a = sr[S::qf(r, c)];
-      qreg[q] = a;
-    }
-    __syncthreads();
-    // the staging buffer is free: prefetch the next stage record while this stage is being processed (TMA, completes on the mbarrier)
-    if (tid == 0 && k >= 1) { fence_proxy_async(); tma_load_1d(sm.stage, d.stage + (nb + k - 1) * S::SREC, REC_BYTES, &sm.bar); }
-    // ---- phase 2: SA = S At, SB = S Bt, sb = s + S bt
-    gemm_tiles<3, 3, 6, false, false, false, false, 4, 0>(sm.S, LD, sm.At, LD, sm.SA, LD, warp, lane);
-    gemm_tiles<3, 2, 6, false, false, false, false, 4, 0>(sm.S, LD, sm.Bt, LDM, sm.SB, LDM, warp, lane);
-    if (warp == mw && lane < NX) { const int r = lane; double a = sm.s[r]; for (int c = 0; c < NX; ++c) a += sm.S[r * LD + c] * sm.bt[c]; sm.sb[r] = a; }
-    __syncthreads();
-    // ---- phase 3: H += Bt^T SA, G += Bt^T SB, g = rt + Bt^T sb
-    gemm_tiles<2, 3, 6, true, false, true, false, 4, 0>(sm.Bt, LDM, sm.SA, LD, sm.H, LD, warp, lane);
-    gemm_tiles<2, 2, 6, true, false, true, false, 4, 0>(sm.Bt, LDM, sm.SB, LDM, sm.G, LDM, warp, lane);
-    if (warp == mw && lane < MP) { const int c = lane; double a = sm.rt[c]; for (int r = 0; r < NX; ++r) a += sm.Bt[r * LDM + c] * sm.sb[r]; sm.g[c] = a; }
-    __syncthreads();
-    // ---- phase 4: warp 0: right-looking Cholesky of G fused with the forward substitution of [H | g];  warps 1-3: S <- At^T SA
-    if (warp == cw) {
-      // lane l < MP owns column l of G (lower part) ; lane c < NX owns column c of H ; lane NX owns g.
-      // Shuffle-only right-looking elimination: the raw pivot column is broadcast from lane j while every lane computes the
-      // reciprocal square root of the pivot redundantly, so the serial chain per pivot is shuffle -> rsqrt -> one FMA.
-      double gc[MP], hc[MP];
-#pragma unroll
-      for (int i = 0; i < MP; ++i) { gc[i] = (lane < MP) ? sm.G[i * LDM + lane] : 0.0; hc[i] = (lane < NX) ? sm.H[i * LD + lane] : ((lane == NX) ? sm.g[i] : 0.0); }
-      bool not_pd;
-      switch (m) {   // reduced input dimensions that occur: H1 6 / 9 / 12 (FLY / single stance / double stance), G1 8 / 11 / 14
-        case 6: not_pd = chol_forward<6, MP>(gc, hc, lane); break;
-        case 9: not_pd = chol_forward<9, MP>(gc, hc, lane); break;
-        case 12: not_pd = chol_forward<12, MP>(gc, hc, lane); break;
-        case 8: not_pd = chol_forward<8, MP>(gc, hc, lane); break;
-        case 11: not_pd = chol_forward<11, MP>(gc, hc, lane); break;
-        case 14: not_pd = chol_forward<14, MP>(gc, hc, lane); break;
-        default: not_pd = chol_forward<MP, MP>(gc, hc, lane); break;   // padded pivots are identity rows
-      }
-      if (not_pd && lane == 0) atomicOr(&d.status[b], 1);
-#pragma unroll
-      for (int i = 0; i < MP; ++i) {
-        if (lane < MP) sm.G[i * LDM + lane] = (i >= lane) ? gc[i] : 0.0;
-        if (lane < NX) sm.H[i * LD + lane] = hc[i]; else if (lane == NX) sm.g[i] = hc[i];
-      }
-    } else {
-      gemm_tiles<3, 3, 6, true, false, false, false, 3, 0>(sm.At, LD, sm.SA, LD, sm.S, LD, vw, lane);
-    }
-    __syncthreads();
-    // ---- phase 5: S -= Y^T Y ; s' = qt + At^T sb - Y^T yg ; write Y, yg, L for the policy kernel
-    gemm_tiles<3, 3, 4, true, false, true, true, 4, 0>(sm.H, LD, sm.H, LD, sm.S, LD, warp, lane);
-    if (warp == mw && lane < NX) {
-      const int c = lane;
-      double a = sm.qt[c];
-      for (int r = 0; r < NX; ++r) a += sm.At[r * LD + c] * sm.sb[r];
-      for (int r = 0; r < MP; ++r) a -= sm.H[r * LD + c] * sm.g[r];
-      sm.snew[c] = a;
-    }
-    for (int r = warp; r < MP; r += 4) if (lane < NX) ric[R::K_Y + r * NX + lane] = sm.H[r * LD + lane];
-    for (int r = 2 * warp + (lane >> 4); r < MP; r += 8) ric[R::K_L + r * MP + (lane & 15)] = sm.G[r * LDM + (lane & 15)];
-    if (tid < MP) ric[R::K_YG + tid] = sm.g[tid];
-    __syncthreads();
-    // ---- phase 6: add Qt and symmetrise (each unordered pair (r, c) is owned by one thread)
-#pragma unroll
-    for (int q = 0; q < QPT; ++q) {
-      const int r = warp + 4 * q, c = lane;
-      if (r < NX && c < NX && c >= r) {
-        const double a = 0.5 * (sm.S[r * LD + c] + sm.S[c * LD + r]) + qreg[q];
-        sm.S[r * LD + c] = a; sm.S[c * LD + r] = a;
-      }
-    }
-    if (tid < NX) sm.s[tid] = sm.snew[tid];
-    __syncthreads();
-  }
-}
 
 // ------------------------------------------------------------------------------------------------ K2 (default): backward Riccati recursion, ONE WARP PER INSTANCE
 // No block-level barrier anywhere: the 4 warps of a CTA run 4 independent instances.  The value function S (24 x 24) never leaves the

@@ -38,7 +38,7 @@ class BmpcError(RuntimeError):
 class _Config(C.Structure):
     _fields_ = [("model_file", C.c_char_p), ("task_file", C.c_char_p), ("reference_file", C.c_char_p), ("gait_file", C.c_char_p),
                 ("urdf_file", C.c_char_p), ("batch", C.c_int), ("device", C.c_int), ("dt", C.c_double), ("time_horizon", C.c_double),
-                ("max_events", C.c_int), ("max_target_points", C.c_int), ("sqp_iterations", C.c_int)]
+                ("max_events", C.c_int), ("max_target_points", C.c_int), ("sqp_iterations", C.c_int), ("max_event_nodes", C.c_int)]
 
 
 class DeviceView(C.Structure):
@@ -71,6 +71,7 @@ def load_library(path: str | None = None):
                  "bmpc_set_mode_schedules_device", "bmpc_gait_insert", "bmpc_gait_insert_named", "bmpc_use_gait_schedule", "bmpc_gait_peek",
                  "bmpc_advance", "bmpc_advance_async", "bmpc_synchronize", "bmpc_get_policy", "bmpc_get_device_view", "bmpc_get_performance",
                  "bmpc_get_status", "bmpc_evaluate_policy", "bmpc_get_launch_count", "bmpc_get_phase_times", "bmpc_enable_phase_timing",
+                 "bmpc_poll", "bmpc_get_device_view_inflight", "bmpc_get_tick_stats",
                  "bmpc_debug_copy", "bmpc_debug_record_sizes", "bmpc_debug_set_option"):
         getattr(L, name).restype = C.c_int
     if path is None:
@@ -99,13 +100,13 @@ class BatchedMpcMrtInterface:
 
     def __init__(self, batch: int, model_file: str | None = None, robot: str = "h1", device: int = 0, dt: float = 0.0, time_horizon: float = 0.0,
                  max_events: int = 0, max_target_points: int = 0, sqp_iterations: int = 0, task_file: str | None = None,
-                 reference_file: str | None = None, gait_file: str | None = None, urdf_file: str | None = None):
+                 reference_file: str | None = None, gait_file: str | None = None, urdf_file: str | None = None, max_event_nodes: int = 0):
         self.L = load_library()
         enc = lambda s: s.encode() if s else None
         if model_file is None and task_file is None:
             model_file = DEFAULT_MODELS[robot]
         cfg = _Config(enc(model_file), enc(task_file), enc(reference_file), enc(gait_file), enc(urdf_file), int(batch), int(device), float(dt),
-                      float(time_horizon), int(max_events), int(max_target_points), int(sqp_iterations))
+                      float(time_horizon), int(max_events), int(max_target_points), int(sqp_iterations), int(max_event_nodes))
         h = C.c_void_p()
         rc = self.L.bmpc_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -141,8 +142,9 @@ class BatchedMpcMrtInterface:
     def exportModel(self, path):
         self._ck(self.L.bmpc_export_model(self.h, path.encode()))
 
-    def reset(self):
-        self._ck(self.L.bmpc_reset(self.h))
+    def reset(self, instance: int = -1):
+        """MPC_MRT_Interface::reset: drops warm start, policy and gait bookkeeping of one instance (all if instance < 0)."""
+        self._ck(self.L.bmpc_reset(self.h, C.c_int(instance)))
 
     def setCurrentObservation(self, t, x):
         t = _d(np.broadcast_to(t, (self.batch,)))
@@ -220,6 +222,15 @@ class BatchedMpcMrtInterface:
     def synchronize(self):
         self._ck(self.L.bmpc_synchronize(self.h))
 
+    def poll(self) -> bool:
+        """True while a tick is still running; publishes it (makes its policy the current one) once it has finished."""
+        return self._ck(self.L.bmpc_poll(self.h)) == 1
+
+    def tickStats(self):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.L.bmpc_get_tick_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(total_trials=a.value, max_trials=b.value, failed_instances=c.value, status_or=d.value)
+
     # ------------------------------------------------------------------ outputs
     def getPolicy(self, first=0, count=None, with_gains=True):
         count = self.batch - first if count is None else count
@@ -234,9 +245,10 @@ class BatchedMpcMrtInterface:
         self._ck(self.L.bmpc_get_policy(self.h, C.c_int(first), C.c_int(count), _pi(n), _p(t), _pi(ev), _p(x), _p(u), _p(uff), _p(K) if with_gains else None))
         return dict(n_nodes=n, t=t, events=ev, x=x, u=u, uff=uff, K=K)
 
-    def getDeviceView(self) -> DeviceView:
+    def getDeviceView(self, inflight: bool = False) -> DeviceView:
+        """Device pointers of the published policy; inflight=True: of the policy the tick in flight is writing (valid in stream order)."""
         v = DeviceView()
-        self._ck(self.L.bmpc_get_device_view(self.h, C.byref(v)))
+        self._ck((self.L.bmpc_get_device_view_inflight if inflight else self.L.bmpc_get_device_view)(self.h, C.byref(v)))
         return v
 
     def getPerformanceIndices(self):
@@ -267,9 +279,9 @@ class BatchedMpcMrtInterface:
     def phaseTimes(self):
         ms = (C.c_float * 9)()
         self._ck(self.L.bmpc_get_phase_times(self.h, ms))
-        names = ["setup", "lq", "projection", "riccati", "policy_expand", "forward", "linesearch", "finalize"]
+        names = ["setup", "lq", "projection", "riccati", "policy_expand", "forward", "linesearch"]
         out = {k: float(ms[i]) for i, k in enumerate(names)}
-        out["linesearch_trials"] = int(ms[8])
+        out["linesearch_trials"] = int(ms[8])   # largest number of trials any instance needed
         return out
 
     def stream(self) -> int:

@@ -35,8 +35,15 @@ enum bmpc_instance_status {
   BMPC_INST_RANK_ANOMALY = 2,     /* constraint Jacobian lost rank beyond the structural stance-foot deficiency */
   BMPC_INST_SWING_UNDEFINED = 4,  /* lift-off / touch-down time undefined (SwingTrajectoryPlanner.cpp:191-212 throws) */
   BMPC_INST_NAN = 8,
-  BMPC_INST_STEP_REJECTED = 16    /* filter line search reached alpha_min: no step taken (informational) */
+  BMPC_INST_STEP_REJECTED = 16,   /* filter line search reached alpha_min: no step taken (informational) */
+  BMPC_INST_GRID_OVERFLOW = 32    /* more event nodes inside the horizon than max_event_nodes: the time grid was truncated */
 };
+/* Failure semantics.  Upstream throws (HPIPM failure, SwingTrajectoryPlanner.cpp:191-212, ...) and BipedalController stops the controller
+ * (BipedalController.cpp:344-348).  Here the tick always completes for the whole batch; bmpc_advance / bmpc_synchronize then return
+ *   BMPC_ERR_NUMERIC  if any instance has bit 1, 2 or 8: that instance took no step and its policy is open loop (K = 0, uff = warm-start input),
+ *                     so nothing non-finite is stored and the next tick warm-starts from valid data;
+ *   BMPC_ERR_INVALID  if any instance has bit 4;   BMPC_ERR_CAPACITY if any instance has bit 32.
+ * The other instances are unaffected and every getter keeps working after such a return. */
 
 /* Construction: replaces `BipedalRobotInterface(taskFile, urdfFile, referenceFile)` +
  * `std::make_shared<SqpMpc>(mpcSettings, sqpSettings, ocp, initializer)`
@@ -55,6 +62,7 @@ typedef struct bmpc_config {
   int max_events;          /* capacity of each instance's mode schedule (0: default 40) */
   int max_target_points;   /* capacity of each instance's TargetTrajectories (0: default 4) */
   int sqp_iterations;      /* <= 0: sqp.sqpIteration (task.info:70) */
+  int max_event_nodes;     /* extra grid nodes for mode switches inside the horizon: 2 per switch off the nominal grid, 1 per switch on it (0: default 16) */
 } bmpc_config;
 
 int bmpc_create(const bmpc_config* cfg, bmpc_handle** out);
@@ -69,8 +77,9 @@ int bmpc_export_model(const bmpc_handle* h, const char* path);             /* wr
  * (BipedalRobotInterface.cpp:67-204) and writes the compact model file; needs no GPU */
 int bmpc_convert_model(const char* task_file, const char* reference_file, const char* gait_file, const char* urdf_file, const char* out_path);
 
-/* MPC_MRT_Interface::reset / resetMpcNode (BipedalController.cpp:147-148): drops the warm start of all instances */
-int bmpc_reset(bmpc_handle* h);
+/* MPC_MRT_Interface::reset / resetMpcNode (BipedalController.cpp:147-148): drops the warm start, the policy and the gait bookkeeping of one
+ * instance, or of all instances if instance < 0.  Waits for a tick in flight. */
+int bmpc_reset(bmpc_handle* h, int instance);
 
 /* MPC_MRT_Interface::setCurrentObservation (BipedalController.cpp:191): SystemObservation{time, state} per instance.
  * t[B], x[B*nx], host memory (copied).  The *_device variants take device pointers (inputs already in HBM). */
@@ -88,8 +97,8 @@ int bmpc_set_targets_from_cmd_vel(bmpc_handle* h, const double* cmd, double time
 
 int bmpc_set_targets_from_cmd_vel_device(bmpc_handle* h, const double* cmd_dev, double time_to_target); /* same, observations and cmd in HBM */
 
-/* Closed-loop driver for device-resident batches: t0 += dt and x0 = optimized state trajectory of the current policy
- * interpolated at the new time (perfect-model stand-in for the MRT_ROS_Dummy_Loop rollout [UPSTREAM] that
+/* Closed-loop driver for device-resident batches: t0 += dt and x0 = optimized state trajectory of the newest policy (the one of the tick in
+ * flight, in stream order) interpolated at the new time (perfect-model stand-in for the MRT_ROS_Dummy_Loop rollout [UPSTREAM] that
  * ocs2_bipedal_robot_ros/src/BipedalRobotDummyNode.cpp:72-86 runs between MPC ticks).  bmpc_get_observations reads them back. */
 int bmpc_shift_observations(bmpc_handle* h, double dt);
 int bmpc_get_observations(bmpc_handle* h, double* t, double* x);
@@ -113,14 +122,19 @@ int bmpc_gait_peek(const bmpc_handle* h, int instance, int cap, double* event_ti
 
 /* MPC_MRT_Interface::advanceMpc -> MPC_BASE::run(t, x) -> SqpSolver::runImpl [UPSTREAM] (BipedalController.cpp:339):
  * one MPC tick for all B instances: reference update, LQ approximation, projected Riccati QP, filter line search,
- * feedback policy.  Synchronous; results are available to the getters when it returns. */
+ * feedback policy.  Synchronous: the new policy is current when it returns. */
 int bmpc_advance(bmpc_handle* h);
-/* same, but only enqueues the work on the library's stream; bmpc_synchronize waits for it.
- * Threading / multiple handles: one thread at a time per handle (as MPC_BASE::run).  All handles of a process share one constant-memory image
- * of the robot model, refreshed at the start of every tick: ticks of handles that hold DIFFERENT robots must not overlap in time (finish one
- * handle's tick with bmpc_synchronize before starting the other's); handles of the same robot may overlap freely. */
+/* The same tick, only ENQUEUED on the library's stream: the call returns as soon as the kernels are queued (no host synchronisation inside the
+ * tick -- the line-search loop runs on the device).  The policy the getters serve stays the previous one until the tick is published:
+ * by bmpc_synchronize (waits), or by the first getter / bmpc_poll that finds the tick finished (MRT_BASE::updatePolicy semantics).
+ * Threading (MPC_MRT_Interface [UPSTREAM], BipedalController.cpp:191-200 vs :332-351): one thread at a time calls bmpc_advance* on a handle; any
+ * other thread may call the set_* functions and the getters (bmpc_get_policy, bmpc_evaluate_policy, bmpc_get_performance, bmpc_get_status,
+ * bmpc_get_device_view) concurrently: they never wait for a tick in flight.  A second bmpc_advance* first waits for the previous tick.
+ * Handles of different robots may be used concurrently; their ticks are serialised on the device's shared model image, handles of the same
+ * robot overlap freely. */
 int bmpc_advance_async(bmpc_handle* h);
-int bmpc_synchronize(bmpc_handle* h);
+int bmpc_synchronize(bmpc_handle* h);   /* waits for the tick in flight, publishes it, returns its status (see "Failure semantics") */
+int bmpc_poll(bmpc_handle* h);          /* publishes the tick in flight if it has finished; returns 1 while a tick is still running, else 0 */
 
 /* PrimalSolution [UPSTREAM] of instances [first, first+count): any output pointer may be NULL.
  * n_nodes[count]; times[count*max_nodes]; events[count*max_nodes] (0 none, 1 pre-event, 2 post-event);
@@ -128,13 +142,16 @@ int bmpc_synchronize(bmpc_handle* h);
  * (LinearController: u = uff + K x).  Host memory. */
 int bmpc_get_policy(bmpc_handle* h, int first, int count, int* n_nodes, double* times, int* events, double* x, double* u, double* uff, double* K);
 
-/* device pointers of the current policy buffers (valid until the next bmpc_advance*): for the multi-GPU all-gather */
+/* device pointers of the current (published) policy buffers; they stay untouched until the tick AFTER the next one starts (double buffering).
+ * bmpc_get_device_view_inflight: the buffers the tick in flight is writing (or the current ones if none is in flight) -- valid for work that
+ * is ordered after the tick on bmpc_get_stream(), e.g. the multi-GPU policy exchange. */
 typedef struct bmpc_device_view {
   const int* n_nodes; const double* times; const int* events;
   const double* x; const double* u; const double* uff; const double* K;
   int max_nodes, nx, nu, batch;
 } bmpc_device_view;
 int bmpc_get_device_view(bmpc_handle* h, bmpc_device_view* v);
+int bmpc_get_device_view_inflight(bmpc_handle* h, bmpc_device_view* v);
 
 /* PerformanceIndex [UPSTREAM] per instance: perf[B*8] = {cost, dynamicsViolationSSE, equalityConstraintsSSE} before the
  * step, the same three after the accepted step, step size alpha, armijo descent metric. */
@@ -146,21 +163,23 @@ int bmpc_get_status(bmpc_handle* h, int* status /* B */);
 int bmpc_evaluate_policy(bmpc_handle* h, const double* t, const double* x, double* x_opt, double* u_opt, int* mode);
 
 /* number of kernels launched by the last bmpc_advance (for bench.py's gpu_launches) and per-phase device times in
- * milliseconds of the last tick: ms[0..7] = {setup, lq, projection, riccati, policy_expand, forward, linesearch, finalize}, ms[8] = line-search trials */
+ * milliseconds of the last tick: ms[0..7] = {setup, lq, projection, riccati, policy_expand, forward, linesearch+step, (unused)}, ms[8] = largest number of
+ * line-search trials any instance needed */
 int bmpc_get_launch_count(const bmpc_handle* h);
 int bmpc_get_phase_times(bmpc_handle* h, float* ms /* 9 */);
 int bmpc_enable_phase_timing(bmpc_handle* h, int enable);
+/* statistics of the last published tick: line-search trials summed over the batch, their maximum, number of failed instances, OR of all status bits */
+int bmpc_get_tick_stats(bmpc_handle* h, int* total_trials, int* max_trials, int* failed_instances, int* status_or);
 void* bmpc_get_stream(bmpc_handle* h); /* cudaStream_t the library launches on */
 
 /* Test hooks (used by tests/ to compare intermediate device data with the oracle): copies the named device buffer of one
- * instance to host.  names: "lq_record", "proj_record", "riccati_record", "dx", "du", "x_lin", "u_lin", "node_meta" */
+ * instance to host.  names: "lq_record", "proj_record", "stage_record", "riccati_record", "dx", "du", "xref", "zref", "st_t", "st_dt", "x", "u" */
 int bmpc_debug_copy(bmpc_handle* h, const char* name, int instance, double* dst, int capacity_doubles);
 int bmpc_debug_record_sizes(const bmpc_handle* h, int* lq_rec, int* proj_rec, int* ric_rec);
-/* kernel-variant options, cross-checked against each other in tests/ (defaults are the fastest measured):
- *   "lq_mode"      4 (packed base pass through global memory + column kernel), 3 (default: packed fused k_lq_pack, 3 (H1) / 2 (G1) stages per warp),
- *                  2 (one stage per warp, k_lq_assemble<FUSED>), 1 (k_model_base + k_lq_assemble), 0 (single-kernel k_lq)
- *   "riccati_mode" 1 (default: one warp per instance, k_riccati_warp), 0 (one CTA per instance, k_riccati)
- *   "ls_mode"      1 (default: streaming register-only flow map, k_linesearch_eval2), 0 (thread-level model_eval, k_linesearch_eval) */
+/* options:
+ *   "projection_mode"  1 (default): upstream's constraint projection, Eigen::FullPivLU kernel() / solve() (LinearAlgebra::luConstraintProjection
+ *                      [UPSTREAM], task.info:76);  0: Moore-Penrose projection (Householder QR, minimum-norm particular solution, orthonormal
+ *                      null-space basis).  The two give the same QP whenever the stance feet are at rest at the linearisation point. */
 int bmpc_debug_set_option(bmpc_handle* h, const char* name, int value);
 
 #ifdef __cplusplus

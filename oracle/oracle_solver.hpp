@@ -352,9 +352,10 @@ inline void linearize(const Model& M, const double* x, const double* u, Lin& L, 
 
 // ---------------------------------------------------------------- constraint projection
 // du = Pe + Px dx + Pu dut with D Pu = 0, Px = -D^+ C, Pe = -D^+ e (D^+ = Moore-Penrose pseudo-inverse).
-// [UPSTREAM] luConstraintProjection uses Eigen::FullPivLU; its particular solution differs from the min-norm
-// one only inside null(D) (which the QP re-optimises) except for the rank-deficient stance-foot rows
-// (SURVEY.md Appendix B.6).  Algorithm (shared with the CUDA product): row-space orthonormalisation by
+// Moore-Penrose alternative to upstream's projection (selectable: projection_mode() = 0, product option "projection_mode" 0).
+// [UPSTREAM] luConstraintProjection uses Eigen::FullPivLU (project_constraints_fullpivlu below, the default); its particular solution
+// differs from the min-norm one only inside null(D) (which the QP re-optimises) except for the rank-deficient stance-foot rows
+// (SURVEY.md Appendix B.6).  Algorithm: row-space orthonormalisation by
 // modified Gram-Schmidt in natural row order with a relative rank tolerance, D = T W, D^+ = W^T (T^T T)^-1 T^T;
 // null-space basis by pivoted Gram-Schmidt of the unit vectors against W.
 constexpr double RANK_TOL = 1e-9;
@@ -418,7 +419,7 @@ inline void project_constraints(const Mat& C, const Mat& D, const std::vector<do
 // Restated from Eigen's documented algorithm: Gaussian elimination with complete pivoting; rank = number of pivots with
 // |pivot| > eps * min(rows, cols) * |largest pivot|; solve() forward-substitutes with the unit-lower factor, back-substitutes the leading
 // rank x rank block of U and sets the free unknowns to zero, i.e. it satisfies the first `rank` pivot rows and silently ignores the rest.
-// Used only to QUANTIFY the documented deviation of the default (Moore-Penrose) projection; never on the product path.
+// This is the oracle's default since round 2 (the CUDA product implements the same elimination in-warp, k_project<NJ, true>).
 inline void project_constraints_fullpivlu(const Mat& C, const Mat& D, const std::vector<double>& e, Mat& Px, Mat& Pu, std::vector<double>& Pe, int& rank) {
   const int nr = D.r, nu = D.c, nx = C.c, sd = std::min(nr, nu);
   Mat lu = D;
@@ -467,8 +468,8 @@ inline void project_constraints_fullpivlu(const Mat& C, const Mat& D, const std:
     Pu(colp[f], s_) = 1.0;
   }
 }
-// 0: Moore-Penrose (default, what the CUDA product implements), 1: FullPivLU emulation (upstream's choice)
-inline int& projection_mode() { static int mode = 0; return mode; }
+// 1 (default): FullPivLU emulation = upstream's luConstraintProjection (what the CUDA product implements by default), 0: Moore-Penrose (the product's "projection_mode" 0)
+inline int& projection_mode() { static int mode = 1; return mode; }
 inline void project_constraints_dispatch(const Mat& C, const Mat& D, const std::vector<double>& e, Mat& Px, Mat& Pu, std::vector<double>& Pe, int& rank) {
   if (projection_mode() == 1) project_constraints_fullpivlu(C, D, e, Px, Pu, Pe, rank);
   else project_constraints(C, D, e, Px, Pu, Pe, rank);

@@ -285,8 +285,11 @@ def spline(ts, ps, vs, mid, tf, pf, vf, tq):
     return pos, vel
 
 
+DEFAULT_PROJECTION_MODE = 1
+
+
 def set_projection_mode(mode: int):
-    """0: Moore-Penrose (default, what the CUDA product implements); 1: emulation of upstream's FullPivLU projection (process-wide)."""
+    """1 (default): emulation of upstream's FullPivLU projection (luConstraintProjection); 0: Moore-Penrose (process-wide switch)."""
     lib().orc_set_projection_mode(C.c_int(mode))
 
 

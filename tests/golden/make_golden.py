@@ -13,7 +13,8 @@ Cases (inputs are stored next to the outputs, so a test needs nothing but the .n
   h1_trot_n100       BASELINE configs[1]: H1 'trot', dt 0.01, horizon 1.0 (103 stages), cold tick + warm tick
   h1_random4         BASELINE configs[2] distributions, instances 0, 1, 4, 6 of seed 0 (one per gait), cold tick + warm tick
   g1_trot_n100       BASELINE configs[3]: G1 'trot', dt 0.01, horizon 1.0
-  h1_random4_fullpivlu  the h1_random4 instances solved with the oracle's emulation of upstream's FullPivLU projection (fixture for the next round)
+  h1_random4_pinv    the h1_random4 instances solved with the selectable Moore-Penrose projection ("projection_mode" 0), first tick
+All other fixtures use the default projection = upstream's luConstraintProjection (Eigen::FullPivLU, emulated by the oracle).
 Gains are stored for a subset of nodes (first 4, every 10th, last) to keep the files small.
 """
 import os
@@ -104,10 +105,9 @@ def main():
         print("h1_random4", b, gait[b], "nodes", len(out["t0_times"]), "step", out["t1_perf"][6])
     np.savez_compressed(os.path.join(HERE, "h1_random4.npz"), **blob)
 
-    # the same four instances with the emulation of upstream's FullPivLU projection (oracle test switch): fixtures for the CUDA
-    # implementation of that projection planned for the next round (deviation 1); first tick only, no gains
+    # the same four instances with the selectable Moore-Penrose projection (oracle switch / product option "projection_mode" 0): first tick only, no gains
     from oracle import pyoracle
-    pyoracle.set_projection_mode(1)
+    pyoracle.set_projection_mode(0)
     try:
         blob = dict(instances=np.array(picks, dtype=np.int32), dt=0.01, horizon=1.0)
         for b in picks:
@@ -116,9 +116,9 @@ def main():
             out = run_case(h1, 0.01, 1.0, et, ms, tt, ts, X0[b], ticks=1)
             blob.update({f"i{b}_event_times": et, f"i{b}_mode_sequence": ms, f"i{b}_target_times": tt, f"i{b}_target_states": ts, f"i{b}_x0": X0[b]})
             blob.update({f"i{b}_{k}": v for k, v in out.items() if not k.endswith("_K") and not k.endswith("gain_nodes")})
-        np.savez_compressed(os.path.join(HERE, "h1_random4_fullpivlu.npz"), **blob)
+        np.savez_compressed(os.path.join(HERE, "h1_random4_pinv.npz"), **blob)
     finally:
-        pyoracle.set_projection_mode(0)
+        pyoracle.set_projection_mode(pyoracle.DEFAULT_PROJECTION_MODE)
 
 
 if __name__ == "__main__":

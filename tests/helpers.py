@@ -76,9 +76,9 @@ def expand_lq_record(rec, nj, total_mass):
     o_r = o_q + nx
     o_hb = o_r + nu
     o_cv = o_hb + 24
-    o_dv = o_cv + 10 * nxa
-    o_ev = o_dv + 10 * nj
-    o_misc = o_ev + 10
+    o_dv = o_cv + 12 * nxa   # 12 row slots: raw rows (default, FullPivLU projection) or <= 10 compressed rows ("projection_mode" 0)
+    o_ev = o_dv + 12 * nj
+    o_misc = o_ev + 12
     o_fo = o_misc + 12
     misc = rec[o_misc:o_misc + 12]
     dt = misc[0]

@@ -102,40 +102,69 @@ def test_config2_trot_identical_instances(oracle_h1):
     g.close()
 
 
-def test_config3_randomized_divergent_modes(h1_model_path):
-    """BASELINE configs[2] distributions (seed 0): divergent contact modes incl. FLY, non-zero momentum (inconsistent stance-foot rows)."""
+def _randomized_batch(model, B, seed, all_gaits):
+    """BASELINE configs[2] / configs[3] distributions for `model` (seeded), as arrays ready for the C ABI."""
     import helpers
-    from oracle.pyoracle import Oracle
-    G = _gpu()
-    m = _mdl()
+    from tools.ingest import read_model
+    m = read_model(model)
     nj = m["nj"]
     lo = np.array([m[f"joint{j}_limits"][0] for j in range(nj)]); hi = np.array([m[f"joint{j}_limits"][1] for j in range(nj)])
-    B = 640   # more than one wave of CTAs on 148 SMs
-    X0, cmd, gait, phase = helpers.randomized_instances(B, np.asarray(m["initial_state"]), np.asarray(m["default_joint_state"]), lo, hi, seed=0)
+    X0, cmd, gait, phase = helpers.randomized_instances(B, np.asarray(m["initial_state"]), np.asarray(m["default_joint_state"]), lo, hi, seed=seed)
+    if m["name"] != "h1" and nj == 12:   # the helper draws around the H1 stance: re-centre heights / joints on this robot's initial state
+        X0[:, 8] = m["initial_state"][8] + (X0[:, 8] - 0.93)
+        X0[:, 12:] = np.asarray(m["initial_state"])[12:] + 0.5 * (X0[:, 12:] - np.asarray(m["default_joint_state"]))
     ME = 40
     ET, MS, NE = np.zeros((B, ME)), np.zeros((B, ME + 1), dtype=np.int32), np.zeros(B, dtype=np.int32)
     TT, TS = np.zeros((B, 2)), np.zeros((B, 2, 12 + nj))
     for b in range(B):
-        et, ms = helpers.tiled_schedule(gait[b], phase[b], t_hi=3.0)
+        g_ = gait[b] if (all_gaits or b % 4 == 0) else "trot"
+        gait[b] = g_
+        et, ms = helpers.tiled_schedule(g_, phase[b], t_hi=3.0)
         NE[b] = len(et); ET[b, :len(et)] = et; MS[b, :len(ms)] = ms
         TT[b], TS[b] = helpers.cmd_vel_target(X0[b], 0.0, cmd[b], 1.0, m["com_height"], m["default_joint_state"])
-    g = G(B, model_file=MODEL, dt=0.01, time_horizon=1.0)
+    return m, X0, gait, ET, MS, NE, TT, TS
+
+
+def _full_size_randomized(model, B, seed, all_gaits, n_check=64):
+    """Full-size randomised batch on the GPU; n_check instances (spread over the batch = over every wave of CTAs, every gait represented) are
+    solved by the oracle as well (one thread per host core): trajectories, gains, performance indices of two ticks within tolerance, identical
+    accepted step sizes, and the same number of line-search failures (alpha_min reached, status bit 16)."""
+    from oracle.pyoracle import OracleBatch
+    G = _gpu()
+    m, X0, gait, ET, MS, NE, TT, TS = _randomized_batch(model, B, seed, all_gaits)
+    check = set(np.linspace(0, B - 1, n_check - 12).astype(int).tolist() + [1, 2, 3, 5, 8, 13, B // 2 + 1, B - 2])
+    for kind in ("trot", "standing_trot", "flying_trot", "stance"):   # every gait is represented
+        check.add(int(np.flatnonzero(gait == kind)[len(check) % 7]))
+    check = sorted(check)
+    kinds = set(gait[check].tolist())
+    assert {"trot", "standing_trot", "flying_trot", "stance"} <= kinds
+    assert any(0 in MS[b, :NE[b] + 1] for b in check)          # FLY phases are among the checked instances
+    g = G(B, model_file=model, dt=0.01, time_horizon=1.0)
     g.setCurrentObservation(np.zeros(B), X0); g.setTargetTrajectories(TT, TS); g.setModeSchedule(ET, MS, NE)
-    check = [0, 1, 2, 3, 5, 8, 13, 100, 333, 600, 639]
-    assert {"trot", "standing_trot", "flying_trot", "stance"} <= set(gait[check].tolist() + gait[:40].tolist())
-    oracles = {}
-    for b in check:
-        o = Oracle(h1_model_path)
+    ob = OracleBatch(model, len(check))
+    for i, b in enumerate(check):
+        o = ob.inst[i]
         o.set_dt_horizon(0.01, 1.0); o.set_mode_schedule(ET[b, :NE[b]], MS[b, :NE[b] + 1]); o.set_target(TT[b], TS[b])
-        oracles[b] = o
+        ob.set_observation(i, 0.0, X0[b])
     for tick in range(2):
         g.advanceMpc()
         st = g.getStatus()
         assert not (st & ~16).any()
-        for b in check:
-            oracles[b].run(0.0, X0[b])
-            _compare_tick(g, oracles[b], b, rel=1e-7 if tick else REL)
+        ob.run(threads=os.cpu_count() or 1)
+        rejected_oracle = 0
+        for i, b in enumerate(check):
+            _compare_tick(g, ob.inst[i], b, rel=1e-7 if tick else REL)
+            rejected_oracle += int(ob.inst[i].info()["step"] == 0.0)
+        assert int(np.count_nonzero(st[check] & 16)) == rejected_oracle
+        stats = g.tickStats()
+        assert stats["failed_instances"] == 0 and stats["max_trials"] >= 1 and stats["total_trials"] >= B
     g.close()
+
+
+def test_config3_randomized_divergent_modes():
+    """BASELINE configs[2] at full size: H1, batch 4096, seed-0 distributions: divergent contact modes incl. FLY, non-zero momentum (rotating
+    stance feet: the dependent sixth row of each stance foot is inconsistent, which is where upstream's FullPivLU projection and a pseudo-inverse differ)."""
+    _full_size_randomized(MODEL, 4096, 0, all_gaits=True)
 
 
 def test_closed_loop_shift_and_gait_schedule(h1_model_path):
@@ -218,8 +247,11 @@ def test_error_paths():
     g.setCurrentObservation(0.0, x0); g.setTargetTrajectories([0.0], [x0])
     # a swing phase without a lift-off time: the reference throws (SwingTrajectoryPlanner.cpp:191-212); here a status bit is raised
     g.setModeSchedule([0.05], [1, 3])
-    g.advanceMpc()
+    with pytest.raises(BmpcError) as ei:
+        g.advanceMpc()
+    assert ei.value.code == -1           # BMPC_ERR_INVALID; the tick itself completed and every getter keeps working
     assert (g.getStatus() & 4).all()
+    assert g.tickStats()["status_or"] & 4
     g.close()
 
 
@@ -277,113 +309,14 @@ def test_line_search_rejects_and_halves(oracle_h1):
     o.reset()
 
 
-def test_lq_kernel_variants_agree():
-    """The pair-packed LQ kernel (default), the one-stage-per-warp fused kernel, the split k_model_base + k_lq_assemble pair and the
-    single-kernel k_lq agree."""
-    import helpers
-    G = _gpu()
-    m = _mdl()
-    nj = m["nj"]
-    lo = np.array([m[f"joint{j}_limits"][0] for j in range(nj)]); hi = np.array([m[f"joint{j}_limits"][1] for j in range(nj)])
-    B = 48
-    X0, cmd, gait, phase = helpers.randomized_instances(B, np.asarray(m["initial_state"]), np.asarray(m["default_joint_state"]), lo, hi, seed=3)
-    ME = 40
-    ET, MS, NE = np.zeros((B, ME)), np.zeros((B, ME + 1), dtype=np.int32), np.zeros(B, dtype=np.int32)
-    for b in range(B):
-        et, ms = helpers.tiled_schedule(gait[b], phase[b], t_hi=3.0)
-        NE[b] = len(et); ET[b, :len(et)] = et; MS[b, :len(ms)] = ms
-    recs = []
-    for split in (4, 3, 2, 1, 0):   # 4 = packed base pass through global memory + column kernel, 3 = packed fused (default), ...
-        g = G(B, model_file=MODEL, dt=0.01, time_horizon=1.0)
-        g.setOption("lq_mode", split)
-        g.setCurrentObservation(np.zeros(B), X0); g.setTargetsFromCmdVel(cmd, 1.0); g.setModeSchedule(ET, MS, NE)
-        g.advanceMpc(); g.advanceMpc()
-        n = g.getPolicy(0, B, with_gains=False)["n_nodes"]
-        recs.append([g.debugCopy("lq_record", b)[:n[b] - 1] for b in (0, 7, 19, 47)])
-        g.close()
-    for ra, rb in [p_ for i in range(4) for p_ in zip(recs[i], recs[4])]:
-        scale = np.maximum(1.0, np.abs(rb))
-        # rows beyond nrows of the constraint block are never written: compare only what both kernels define
-        assert np.abs((ra - rb) / scale)[:, :22 + 171 + 198 + 44 + 24].max() < 1e-10
-        assert np.abs((ra - rb) / scale)[:, -28:].max() < 1e-10   # ev rows in use, misc, forces
-
-
-def test_riccati_kernel_variants_agree():
-    """The warp-per-instance Riccati kernel (default: value function in DMMA accumulator fragments) and the CTA-per-instance kernel
-    (operands in shared memory) give the same policies on randomised instances with divergent contact modes, for both robots."""
-    import helpers
-    from tools.ingest import read_model
-    G = _gpu()
-    for robot in ("h1", "g1"):
-        model = os.path.join(ROOT, "configs", f"{robot}.model")
-        m = read_model(model)
-        nj = m["nj"]
-        lo = np.array([m[f"joint{j}_limits"][0] for j in range(nj)]); hi = np.array([m[f"joint{j}_limits"][1] for j in range(nj)])
-        B = 37   # not a multiple of the 4 instances per CTA
-        X0, cmd, gait, phase = helpers.randomized_instances(B, np.asarray(m["initial_state"]), np.asarray(m["default_joint_state"]), lo, hi, seed=5)
-        X0[:, 8] = m["initial_state"][8] + (X0[:, 8] - 0.93)
-        ME = 40
-        ET, MS, NE = np.zeros((B, ME)), np.zeros((B, ME + 1), dtype=np.int32), np.zeros(B, dtype=np.int32)
-        for b in range(B):
-            et, ms = helpers.tiled_schedule(gait[b], phase[b], t_hi=3.0)
-            NE[b] = len(et); ET[b, :len(et)] = et; MS[b, :len(ms)] = ms
-        pols, perfs = [], []
-        # 1: warp per instance (default), 0: CTA per instance; the latter run also uses the thread-level line-search evaluation (model_eval)
-        # instead of the streaming one
-        for mode in (1, 0):
-            g = G(B, model_file=model, dt=0.01, time_horizon=1.0)
-            g.setOption("riccati_mode", mode)
-            g.setOption("ls_mode", 1 if mode else 0)
-            g.setCurrentObservation(np.zeros(B), X0); g.setTargetsFromCmdVel(cmd, 1.0); g.setModeSchedule(ET, MS, NE)
-            g.advanceMpc(); g.advanceMpc()
-            assert not (g.getStatus() & ~16).any()
-            pols.append(g.getPolicy(0, B)); perfs.append(g.getPerformanceIndices())
-            g.close()
-        for key in ("x", "u", "uff", "K"):
-            a, b_ = pols[0][key], pols[1][key]
-            assert np.abs(a - b_).max() <= 1e-9 * max(1.0, np.abs(b_).max()), (robot, key, np.abs(a - b_).max())
-        assert np.abs(perfs[0] - perfs[1]).max() <= 1e-9 * max(1.0, np.abs(perfs[1]).max())
-
-
 def test_config4_g1_second_morphology():
-    """BASELINE configs[3]: Unitree G1 (12 leg joints, nx = nu = 24), trot, N = 100: authored config (configs/g1), vs the oracle."""
-    import helpers
-    from oracle.pyoracle import Oracle
-    from tools.ingest import read_model
+    """BASELINE configs[3] at full size: Unitree G1 (12 leg joints, nx = nu = 24), N = 100, batch 8192: authored config (configs/g1); three
+    quarters of the instances trot, the rest draw from all gaits."""
     G = _gpu()
-    model = os.path.join(ROOT, "configs", "g1.model")
-    m = read_model(model)
-    nj = m["nj"]
-    assert nj == 12
-    lo = np.array([m[f"joint{j}_limits"][0] for j in range(nj)]); hi = np.array([m[f"joint{j}_limits"][1] for j in range(nj)])
-    B = 800
-    X0, cmd, gait, phase = helpers.randomized_instances(B, np.asarray(m["initial_state"]), np.asarray(m["default_joint_state"]), lo, hi, seed=4)
-    X0[:, 8] = m["initial_state"][8] + (X0[:, 8] - 0.93)          # the helper draws heights around the H1 value
-    X0[:, 12:] = np.asarray(m["initial_state"])[12:] + 0.5 * (X0[:, 12:] - np.asarray(m["default_joint_state"]))
-    ME = 40
-    ET, MS, NE = np.zeros((B, ME)), np.zeros((B, ME + 1), dtype=np.int32), np.zeros(B, dtype=np.int32)
-    TT, TS = np.zeros((B, 2)), np.zeros((B, 2, 12 + nj))
-    for b in range(B):
-        g_ = "trot" if b % 4 else gait[b]
-        et, ms = helpers.tiled_schedule(g_, phase[b], t_hi=3.0)
-        NE[b] = len(et); ET[b, :len(et)] = et; MS[b, :len(ms)] = ms
-        TT[b], TS[b] = helpers.cmd_vel_target(X0[b], 0.0, cmd[b], 1.0, m["com_height"], m["default_joint_state"])
-    g = G(B, model_file=model, dt=0.01, time_horizon=1.0)
+    g = G(2, model_file=os.path.join(ROOT, "configs", "g1.model"))
     assert g.nx == 24 and g.nu == 24
-    g.setCurrentObservation(np.zeros(B), X0); g.setTargetTrajectories(TT, TS); g.setModeSchedule(ET, MS, NE)
-    check = [0, 1, 2, 4, 8, 401, 799]
-    oracles = {}
-    for b in check:
-        o = Oracle(model)
-        o.set_dt_horizon(0.01, 1.0); o.set_mode_schedule(ET[b, :NE[b]], MS[b, :NE[b] + 1]); o.set_target(TT[b], TS[b])
-        oracles[b] = o
-    for tick in range(2):
-        g.advanceMpc()
-        assert not (g.getStatus() & ~16).any()
-        for b in check:
-            oracles[b].run(0.0, X0[b])
-            _compare_tick(g, oracles[b], b, rel=1e-7 if tick else REL)
     g.close()
+    _full_size_randomized(os.path.join(ROOT, "configs", "g1.model"), 8192, 4, all_gaits=False)
 
 
 def test_two_sqp_iterations_and_reset(oracle_h1):
@@ -436,3 +369,202 @@ def test_two_handles_with_different_robots_coexist():
     assert np.array_equal(gh.getPolicy(0, 1)["K"], ref)
     assert not gg.getStatus().any() and not gh.getStatus().any()
     gh.close(); gg.close()
+
+
+def test_moore_penrose_option_matches_oracle_variant(h1_model_path):
+    """"projection_mode" 0 (Householder QR on per-foot compressed rows) against the oracle switched to its Moore-Penrose projection, on
+    randomised instances whose stance feet rotate (where the two projections are different QPs)."""
+    from oracle import pyoracle
+    from oracle.pyoracle import Oracle
+    G = _gpu()
+    B = 16
+    m, X0, gait, ET, MS, NE, TT, TS = _randomized_batch(MODEL, B, 7, True)
+    g = G(B, model_file=MODEL, dt=0.01, time_horizon=1.0)
+    g.setOption("projection_mode", 0)
+    g.setCurrentObservation(np.zeros(B), X0); g.setTargetTrajectories(TT, TS); g.setModeSchedule(ET, MS, NE)
+    pyoracle.set_projection_mode(0)
+    try:
+        oracles = {}
+        for b in (0, 3, 9, 15):
+            o = Oracle(h1_model_path)
+            o.set_dt_horizon(0.01, 1.0); o.set_mode_schedule(ET[b, :NE[b]], MS[b, :NE[b] + 1]); o.set_target(TT[b], TS[b])
+            oracles[b] = o
+        for tick in range(2):
+            g.advanceMpc()
+            assert not (g.getStatus() & ~16).any()
+            for b, o in oracles.items():
+                o.run(0.0, X0[b])
+                _compare_tick(g, o, b, rel=1e-7 if tick else REL)
+    finally:
+        pyoracle.set_projection_mode(pyoracle.DEFAULT_PROJECTION_MODE)
+    g.close()
+
+
+def test_numerical_failure_is_contained_and_reported():
+    """A non-finite observation in one instance: the tick completes, bmpc_advance returns BMPC_ERR_NUMERIC, that instance is flagged, stores
+    nothing non-finite (it keeps its previous policy; none on a cold start) and recovers on the next tick; the other instances are bit-identical to a clean run."""
+    import helpers
+    from bipedal_control_b200 import BmpcError
+    G = _gpu()
+    m = _mdl()
+    x0 = np.asarray(m["initial_state"])
+    et, ms = helpers.config2(22, x0, None, None)
+    tt, ts = helpers.cmd_vel_target(x0, 0.0, (0.3, 0, 0, 0), 1.0, m["com_height"], m["default_joint_state"])
+    B, bad = 6, 4
+    clean = G(B, model_file=MODEL, dt=0.01, time_horizon=0.5); dirty = G(B, model_file=MODEL, dt=0.01, time_horizon=0.5)
+    for g in (clean, dirty):
+        g.setCurrentObservation(0.0, x0); g.setTargetTrajectories(tt, ts); g.setModeSchedule(et, ms)
+    clean.advanceMpc(); dirty.advanceMpc()                 # tick 1: both fine
+    X = np.tile(x0, (B, 1)); X[:, 6] += 0.01
+    Xbad = X.copy(); Xbad[bad, 3] = np.nan
+    clean.setCurrentObservation(0.0, X); dirty.setCurrentObservation(0.0, Xbad)
+    before = dirty.getPolicy(bad, 1)
+    clean.advanceMpc()
+    with pytest.raises(BmpcError) as ei:
+        dirty.advanceMpc()                                  # tick 2: instance `bad` fails
+    assert ei.value.code == -3
+    st = dirty.getStatus()
+    assert st[bad] & 8 and not (np.delete(st, bad) & ~16).any()
+    assert dirty.tickStats()["failed_instances"] == 1
+    pc, pd = clean.getPolicy(), dirty.getPolicy()
+    for k in ("x", "u", "uff", "K", "t"):
+        assert np.array_equal(np.delete(pc[k], bad, axis=0), np.delete(pd[k], bad, axis=0)), k
+        assert np.isfinite(pd[k][bad]).all()
+        assert np.array_equal(pd[k][bad], before[k][0]), k      # the failed instance kept its previous policy
+    clean.setCurrentObservation(0.0, X); dirty.setCurrentObservation(0.0, X)
+    clean.advanceMpc(); dirty.advanceMpc()                 # tick 3: the instance solves again from valid data
+    assert not (dirty.getStatus() & ~16).any()
+    assert np.isfinite(dirty.getPolicy(bad, 1)["K"]).all()
+    # a failure on the very first tick leaves the instance without a policy; it cold-starts on the next one
+    g = G(3, model_file=MODEL, dt=0.01, time_horizon=0.3)
+    Xn = np.tile(x0, (3, 1)); Xn[1, 12] = np.inf
+    g.setCurrentObservation(0.0, Xn); g.setTargetTrajectories(tt, ts); g.setModeSchedule(et, ms)
+    with pytest.raises(BmpcError):
+        g.advanceMpc()
+    assert list(g.getPolicy(0, 3, with_gains=False)["n_nodes"] > 0) == [True, False, True]
+    g.setCurrentObservation(0.0, np.tile(x0, (3, 1)))
+    g.advanceMpc()
+    fresh = G(1, model_file=MODEL, dt=0.01, time_horizon=0.3)
+    fresh.setCurrentObservation(0.0, x0); fresh.setTargetTrajectories(tt, ts); fresh.setModeSchedule(et, ms); fresh.advanceMpc()
+    p, pf = g.getPolicy(1, 1), fresh.getPolicy(0, 1)
+    assert not g.getStatus().any()
+    for k in ("x", "u", "uff", "K"):
+        assert np.array_equal(p[k][0], pf[k][0]), k          # instance 1 solved a cold-start tick
+    g.close(); fresh.close(); clean.close(); dirty.close()
+
+
+def test_async_tick_publishes_on_completion_and_getters_do_not_tear():
+    """MRT semantics (BipedalController.cpp:191-200 vs :332-351): while a tick is in flight the getters keep serving the previous policy; a second
+    thread hammering evaluatePolicy / getPolicy during a closed loop only ever sees complete policies of one tick."""
+    import threading
+    import helpers
+    G = _gpu()
+    m = _mdl()
+    x0 = np.asarray(m["initial_state"])
+    et, ms = helpers.config2(22, x0, None, None)
+    B = 512
+    cmd = np.tile([0.3, 0.0, 0.0, 0.0], (B, 1))
+
+    def make():
+        g = G(B, model_file=MODEL, dt=0.01, time_horizon=1.0)
+        g.setCurrentObservation(0.0, x0); g.setTargetsFromCmdVel(cmd, 1.0); g.setModeSchedule(et, ms)
+        return g
+    # serial reference run: policy of instance 3 after every tick
+    g = make()
+    ref = []
+    for tick in range(6):
+        g.advanceMpc()
+        p = g.getPolicy(3, 1, with_gains=True)
+        ref.append({k: p[k][0].copy() for k in ("t", "x", "u", "uff", "K")})
+        g.shiftObservations(0.02)
+    g.close()
+    g = make()
+    g.advanceMpc()
+    first = g.getPolicy(3, 1)
+    g.shiftObservations(0.02)
+    g.advanceMpcAsync()
+    during = g.getPolicy(3, 1)            # the tick is (almost certainly) still running: previous policy, complete
+    assert any(np.array_equal(during["x"][0], r["x"]) and np.array_equal(during["K"][0], r["K"]) for r in ref[:2])
+    g.synchronize()
+    assert not g.poll()
+    after = g.getPolicy(3, 1)
+    assert np.array_equal(after["x"][0], ref[1]["x"]) and not np.array_equal(after["x"][0], first["x"][0])
+    # reader thread against the MPC thread
+    stop = threading.Event(); seen = []; errors = []
+
+    def reader():
+        try:
+            while not stop.is_set():
+                p = g.getPolicy(3, 1)
+                hits = [i for i, r in enumerate(ref) if np.array_equal(p["t"][0], r["t"])]
+                if len(hits) != 1:
+                    errors.append("time grid of no tick"); return
+                r = ref[hits[0]]
+                if not all(np.array_equal(p[k][0], r[k]) for k in ("x", "u", "uff", "K")):
+                    errors.append(f"torn policy at tick {hits[0]}"); return
+                seen.append(hits[0])
+                xo, uo, mo = g.evaluatePolicy(r["t"][0] + 0.004, x0)
+                if not (np.isfinite(xo).all() and np.isfinite(uo).all()):
+                    errors.append("non-finite evaluatePolicy"); return
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+    th = threading.Thread(target=reader); th.start()
+    for tick in range(2, 6):
+        g.shiftObservations(0.02)
+        g.advanceMpcAsync()
+        while g.poll():
+            pass
+    stop.set(); th.join(timeout=30)
+    assert not errors, errors
+    assert len(seen) > 0 and seen == sorted(seen)      # complete policies only, never an older one after a newer one
+    final = g.getPolicy(3, 1)
+    assert np.array_equal(final["K"][0], ref[5]["K"])
+    g.close()
+
+
+def test_reset_of_one_instance():
+    """bmpc_reset(h, instance): that instance cold-starts on the next tick (and has no policy in between), the others continue warm."""
+    import helpers
+    G = _gpu()
+    m = _mdl()
+    x0 = np.asarray(m["initial_state"]).copy(); x0[0] = 0.15
+    et, ms = helpers.config2(22, x0, None, None)
+    tt, ts = helpers.cmd_vel_target(x0, 0.0, (0.3, 0, 0, 0.1), 1.0, m["com_height"], m["default_joint_state"])
+    g = G(4, model_file=MODEL, dt=0.01, time_horizon=0.4)
+    g.setCurrentObservation(0.0, x0); g.setTargetTrajectories(tt, ts); g.setModeSchedule(et, ms)
+    g.advanceMpc(); cold = g.getPolicy(0, 1)["x"][0].copy()
+    g.advanceMpc(); warm2 = g.getPolicy(0, 1)["x"][0].copy()
+    assert np.abs(cold - warm2).max() > 1e-7
+    g.reset(2)
+    assert list(g.getPolicy(0, 4, with_gains=False)["n_nodes"] > 0) == [True, True, False, True]
+    xo, uo, _ = g.evaluatePolicy(0.0, x0)
+    assert np.array_equal(xo[2], x0) and not uo[2].any() and uo[1].any()
+    g.advanceMpc()
+    p = g.getPolicy(0, 4)
+    assert np.array_equal(p["x"][2], cold)                          # cold start again
+    assert np.array_equal(p["x"][0], p["x"][1]) and np.array_equal(p["x"][0], p["x"][3]) and not np.array_equal(p["x"][0], cold)
+    g.close()
+
+
+def test_time_grid_capacity_is_reported():
+    """More event nodes inside the horizon than max_event_nodes: status bit 32 and BMPC_ERR_CAPACITY instead of a silently distorted grid; a
+    larger max_event_nodes solves the same problem."""
+    import helpers
+    from bipedal_control_b200 import BmpcError
+    G = _gpu()
+    m = _mdl()
+    x0 = np.asarray(m["initial_state"])
+    et = np.array([-0.5, 0.033, 0.071, 0.112, 0.155, 0.9])     # four switches off the grid inside a 0.2 s horizon: 8 extra nodes
+    ms = np.array([3, 1, 3, 2, 3, 1, 3], dtype=np.int32)
+    tt, ts = helpers.cmd_vel_target(x0, 0.0, (0.1, 0, 0, 0), 1.0, m["com_height"], m["default_joint_state"])
+    g = G(2, model_file=MODEL, dt=0.01, time_horizon=0.2, max_event_nodes=4)
+    g.setCurrentObservation(0.0, x0); g.setTargetTrajectories(tt, ts); g.setModeSchedule(et, ms)
+    with pytest.raises(BmpcError) as ei:
+        g.advanceMpc()
+    assert ei.value.code == -4 and (g.getStatus() & 32).all()
+    g.close()
+    g = G(2, model_file=MODEL, dt=0.01, time_horizon=0.2, max_event_nodes=8)
+    g.setCurrentObservation(0.0, x0); g.setTargetTrajectories(tt, ts); g.setModeSchedule(et, ms)
+    g.advanceMpc()
+    assert not g.getStatus().any() and g.getPolicy(0, 1, with_gains=False)["n_nodes"][0] == 21 + 8
+    g.close()

@@ -52,8 +52,8 @@ def test_create_fails_loudly_without_gpu(lib):
 
     class Cfg(C.Structure):
         _fields_ = [("model_file", C.c_char_p), ("task_file", C.c_char_p), ("reference_file", C.c_char_p), ("gait_file", C.c_char_p), ("urdf_file", C.c_char_p),
-                    ("batch", C.c_int), ("device", C.c_int), ("dt", C.c_double), ("time_horizon", C.c_double), ("max_events", C.c_int), ("max_target_points", C.c_int), ("sqp_iterations", C.c_int)]
-    cfg = Cfg(os.path.join(ROOT, "configs", "h1.model").encode(), None, None, None, None, 4, 0, 0.0, 0.0, 0, 0, 0)
+                    ("batch", C.c_int), ("device", C.c_int), ("dt", C.c_double), ("time_horizon", C.c_double), ("max_events", C.c_int), ("max_target_points", C.c_int), ("sqp_iterations", C.c_int), ("max_event_nodes", C.c_int)]
+    cfg = Cfg(os.path.join(ROOT, "configs", "h1.model").encode(), None, None, None, None, 4, 0, 0.0, 0.0, 0, 0, 0, 0)
     h = C.c_void_p()
     rc = lib.bmpc_create(C.byref(cfg), C.byref(h))
     assert rc == -2 and not h.value

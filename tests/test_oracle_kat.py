@@ -203,7 +203,11 @@ def test_projection_rank_and_pseudo_inverse(o, mode, rows, rank):
     L = _mode_constraints(o, mode, rng)
     assert L["nc_rows"] == rows and L["rank"] == rank and L["m"] == o.nu - rank
     assert np.linalg.matrix_rank(L["D"], tol=1e-9) == rank
-    Px, Pu, Pe, rk = pyoracle.project(L["C"], L["D"], L["e"])
+    pyoracle.set_projection_mode(0)   # the Moore-Penrose variant ("projection_mode" 0 of the product)
+    try:
+        Px, Pu, Pe, rk = pyoracle.project(L["C"], L["D"], L["e"])
+    finally:
+        pyoracle.set_projection_mode(pyoracle.DEFAULT_PROJECTION_MODE)
     assert rk == rank
     assert np.abs(L["D"] @ Pu).max() < 1e-12
     np.testing.assert_allclose(Pu.T @ Pu, np.eye(o.nu - rank), atol=1e-12)
@@ -436,12 +440,13 @@ def test_fullpivlu_emulation_properties(o, mode, rank):
     exactly while ignoring the dependent stance-foot row."""
     from oracle import pyoracle
     Cm, D, e = _random_stage_constraints(o, mode, seed=11 + mode)
-    Px0, Pu0, Pe0, r0 = pyoracle.project(Cm, D, e)
-    pyoracle.set_projection_mode(1)
+    pyoracle.set_projection_mode(0)
     try:
+        Px0, Pu0, Pe0, r0 = pyoracle.project(Cm, D, e)
+        pyoracle.set_projection_mode(1)
         Px1, Pu1, Pe1, r1 = pyoracle.project(Cm, D, e)
     finally:
-        pyoracle.set_projection_mode(0)
+        pyoracle.set_projection_mode(pyoracle.DEFAULT_PROJECTION_MODE)
     assert r0 == r1 == rank == np.linalg.matrix_rank(D, tol=1e-9 * np.abs(D).max())
     assert np.abs(D @ Pu1).max() < 1e-10 * max(1.0, np.abs(D).max())
     # same null space: the orthogonal projector onto it is the same
@@ -457,7 +462,7 @@ def test_fullpivlu_emulation_properties(o, mode, rank):
 
 
 def test_projection_choice_identical_at_consistent_points_and_small_near_feasibility(h1_model_path):
-    """Quantifies deliberate deviation 1 of DESIGN.md: with the stance feet at rest (config 2, cold start from the initial state) the
+    """Quantifies the difference between upstream's projection (default) and the selectable Moore-Penrose variant: with the stance feet at rest (config 2, cold start from the initial state) the
     equality constraints are consistent and both projections give the same solution to rounding; one warm tick later the stance-foot rows are
     inconsistent at second order only (foot angular velocity x dx) and the solutions agree to 1e-4 relative on cost and to 1e-3 on the inputs."""
     import helpers
@@ -480,7 +485,7 @@ def test_projection_choice_identical_at_consistent_points_and_small_near_feasibi
                 ticks.append((np.array(so["x"]), np.array(so["u"]), np.array(so["K"]), np.array(io["after"])))
             sols[pm] = ticks
         finally:
-            pyoracle.set_projection_mode(0)
+            pyoracle.set_projection_mode(pyoracle.DEFAULT_PROJECTION_MODE)
     (xa, ua, Ka, pa), (xb, ub, Kb, pb) = sols[0][0], sols[1][0]
     assert np.abs(xa - xb).max() < 1e-10 and np.abs(ua - ub).max() < 1e-9 * np.abs(ua).max() and np.abs(Ka - Kb).max() < 1e-9 * np.abs(Ka).max()
     (xa, ua, Ka, pa), (xb, ub, Kb, pb) = sols[0][1], sols[1][1]
@@ -490,7 +495,7 @@ def test_projection_choice_identical_at_consistent_points_and_small_near_feasibi
 
 @pytest.mark.parametrize("mode", [3, 1, 2, 0])
 def test_complete_pivoting_on_joint_block_equals_fullpivlu_on_stacked_rows(o, mode):
-    """Design check for the CUDA FullPivLU projection (tools/candidates/r2_fullpivlu.patch): the zero-force rows of open contacts are identity
+    """Design check for the CUDA FullPivLU projection (k_project<NJ, true>): the zero-force rows of open contacts are identity
     rows on columns the velocity rows never touch, so Gaussian elimination with complete pivoting of the joint block Dv alone (what one warp does:
     lane = joint column) gives the same Px / Pe joint rows as the oracle's FullPivLU emulation on the full stacked D of the stage."""
     from oracle import pyoracle
@@ -545,7 +550,94 @@ def test_complete_pivoting_on_joint_block_equals_fullpivlu_on_stacked_rows(o, mo
     try:
         Px1, Pu1, Pe1, r1 = pyoracle.project(Cm, D, e)
     finally:
-        pyoracle.set_projection_mode(0)
+        pyoracle.set_projection_mode(pyoracle.DEFAULT_PROJECTION_MODE)
     assert r1 == rank + 3 * n_open
     scale = max(1.0, np.abs(Px1).max())
     assert np.abs(Px1[12:] - Pxj).max() < 1e-11 * scale and np.abs(Pe1[12:] - Pej).max() < 1e-11 * max(1.0, np.abs(Pe1).max())
+
+
+def _gauss_jordan_lanes(Cv, Dv, ev, n_open, nu_full):
+    """numpy restatement of lu_project (csrc/bmpc_kernels_project.cuh), lane by lane: Gauss-Jordan with complete pivoting on the augmented
+    columns [Dv | Cv | ev], rows never swapped, scatter -col[row(k)] / pivot(k) into W at the pivot column's joint index."""
+    nr, nj = Dv.shape
+    nxa = Cv.shape[1]
+    cols = np.concatenate([Dv, Cv, ev[:, None]], axis=1).astype(float)    # column j = lane j
+    ncols = cols.shape[1]
+    rowdone = [False] * nr
+    used = [False] * nj
+    spc, sip = [-1] * nr, [0.0] * nr
+    maxpiv = 1.0 if n_open > 0 else 0.0
+    epsd = np.finfo(float).eps * min(nr + 3 * n_open, nu_full)
+    rank = 0
+    for kk in range(min(nr, nj)):
+        best, bl, prow = 0.0, None, None
+        for lane in range(nj):           # warp arg-max: first maximum in lane order; inside a lane the first maximum over the unused rows
+            if used[lane]:
+                continue
+            lb, li = -1.0, 0
+            for i in range(nr):
+                if not rowdone[i] and abs(cols[i, lane]) > lb:
+                    lb, li = abs(cols[i, lane]), i
+            if lb > best:
+                best, bl, prow = lb, lane, li
+        if bl is None:
+            break
+        p = cols[prow, bl]
+        mp = max(maxpiv, abs(p))
+        if not abs(p) > epsd * mp:
+            break
+        maxpiv = mp
+        ip = 1.0 / p
+        f = cols[:, bl] * ip
+        f[prow] = 0.0
+        cp = cols[prow, :].copy()
+        cols -= np.outer(f, cp)
+        used[bl] = True; rowdone[prow] = True; spc[prow] = bl; sip[prow] = ip; rank += 1
+    W = np.zeros((nj, 32))
+    free = [l for l in range(nj) if not used[l]]
+    for lane in range(ncols):
+        if lane < nj:
+            if used[lane]:
+                continue
+            wl = 24 + free.index(lane)
+        elif lane < nj + nxa:
+            c = lane - nj
+            wl = c if c < 6 else c + 3
+        else:
+            wl = 6
+        for i in range(nr):
+            if spc[i] >= 0:
+                W[spc[i], wl] = -cols[i, lane] * sip[i]
+        if lane < nj:
+            W[lane, wl] = 1.0
+    return W, rank
+
+
+@pytest.mark.parametrize("mode", [3, 1, 2, 0])
+@pytest.mark.parametrize("robot", ["h1", "g1"])
+def test_in_warp_gauss_jordan_equals_fullpivlu_emulation(mode, robot):
+    """The algorithm the CUDA projection runs (Gauss-Jordan on augmented columns, no row swaps, scatter by pivot column) gives the Px / Pe joint
+    rows and a kernel basis that agree with the oracle's Eigen::FullPivLU emulation on the full stacked D, for every contact mode and both robots."""
+    import os
+    oo = Oracle(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs", f"{robot}.model"))
+    Cm, D, e = _random_stage_constraints(oo, mode, seed=21 + mode)
+    nu = D.shape[1]; nj = nu - 12
+    vel = [i for i in range(D.shape[0]) if np.abs(D[i, :12]).max() == 0.0]
+    n_open = (D.shape[0] - len(vel)) // 3
+    X = list(range(6)) + list(range(9, nu))
+    assert np.abs(Cm[vel][:, 6:9]).max() == 0.0           # translation invariance: the base-position columns vanish
+    W, rank = _gauss_jordan_lanes(Cm[vel][:, X], D[vel][:, 12:], e[vel], n_open, nu)
+    Px1, Pu1, Pe1, r1 = pyoracle.project(Cm, D, e)        # default = FullPivLU emulation
+    assert r1 == rank + 3 * n_open
+    cols = [c if c < 6 else c + 3 for c in range(len(X))]
+    scale = max(1.0, np.abs(Px1).max())
+    assert np.abs(W[:, cols] - Px1[12:][:, X]).max() < 1e-11 * scale
+    assert np.abs(W[:, 6] - Pe1[12:]).max() < 1e-11 * max(1.0, np.abs(Pe1).max())
+    mj = nj - rank
+    N = W[:, 24:24 + mj]
+    assert mj == 0 or np.abs(D[vel][:, 12:] @ N).max() < 1e-10
+    # same null space of the joint block as upstream's kernel() restricted to the joint rows (force columns of closed contacts are free there)
+    if mj > 0:
+        Nj = Pu1[12:, :]
+        Nj = Nj[:, np.abs(Nj).max(axis=0) > 0]
+        assert Nj.shape[1] == mj and np.linalg.matrix_rank(np.concatenate([N, Nj], axis=1), tol=1e-9) == mj
