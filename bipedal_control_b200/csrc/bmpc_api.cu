@@ -90,6 +90,7 @@ struct bmpc_handle {
   double *s_t[2] = {nullptr, nullptr}, *s_x[2] = {nullptr, nullptr}, *s_u[2] = {nullptr, nullptr}, *s_uff[2] = {nullptr, nullptr}, *s_K[2] = {nullptr, nullptr};
   int* s_nev[2] = {nullptr, nullptr}; double* s_evt[2] = {nullptr, nullptr}; int* s_evm[2] = {nullptr, nullptr};
   double* s_perf[2] = {nullptr, nullptr}; int* s_status[2] = {nullptr, nullptr};
+  double* slab[2] = {nullptr, nullptr}; size_t slab_doubles = 0;
   int cur = 0; bool have_solution = false;
   // work
   double *d_lq = nullptr, *d_proj = nullptr, *d_stage = nullptr, *d_ric = nullptr, *d_dx = nullptr, *d_du = nullptr, *d_norms = nullptr;
@@ -340,9 +341,14 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     h->d_st_t = P.d<double>(B * NS); h->d_st_dt = P.d<double>(B * NS); h->d_st_mode = P.d<int>(B * NS);
     h->d_xref = P.d<double>(B * NS * nx); h->d_zref = P.d<double>(B * NS * 2);
     for (int i = 0; i < 2; ++i) {
-      h->s_n[i] = P.d<int>(B); h->s_ev[i] = P.d<int>(B * NS); h->s_t[i] = P.d<double>(B * NS);
-      h->s_x[i] = P.d<double>(B * NS * nx); h->s_u[i] = P.d<double>(B * NS * nu); h->s_uff[i] = P.d<double>(B * NS * nu);
-      h->s_K[i] = P.d<double>(B * NS * nu * nx);
+      // one contiguous slab per policy buffer: [K | uff | x | u | t | events | n_nodes], so that the multi-GPU exchange is ONE collective
+      const size_t nK = B * NS * nu * nx, nU = B * NS * nu, nX = B * NS * nx, nT = B * NS;
+      const size_t ints = (B * NS + B + 1) / 2;   // events + n_nodes, in units of doubles
+      h->slab_doubles = nK + 2 * nU + nX + nT + ints;
+      double* slab = P.d<double>(h->slab_doubles);
+      h->slab[i] = slab;
+      h->s_K[i] = slab; h->s_uff[i] = slab + nK; h->s_x[i] = h->s_uff[i] + nU; h->s_u[i] = h->s_x[i] + nX; h->s_t[i] = h->s_u[i] + nU;
+      h->s_ev[i] = reinterpret_cast<int*>(h->s_t[i] + nT); h->s_n[i] = h->s_ev[i] + B * NS;
       h->s_nev[i] = P.d<int>(B); h->s_evt[i] = P.d<double>(B * h->ME); h->s_evm[i] = P.d<int>(B * (h->ME + 1));
       h->s_perf[i] = P.d<double>(B * 8); h->s_status[i] = P.d<int>(B);
     }
@@ -580,7 +586,7 @@ int bmpc_get_device_view(bmpc_handle* h, bmpc_device_view* v) {
   if (!h->have_solution) return BMPC_ERR_INVALID;
   const int c = h->cur;
   v->n_nodes = h->s_n[c]; v->times = h->s_t[c]; v->events = h->s_ev[c]; v->x = h->s_x[c]; v->u = h->s_u[c]; v->uff = h->s_uff[c]; v->K = h->s_K[c];
-  v->max_nodes = h->NS; v->nx = h->nx; v->nu = h->nu; v->batch = h->B;
+  v->max_nodes = h->NS; v->nx = h->nx; v->nu = h->nu; v->batch = h->B; v->slab = h->slab[c]; v->slab_bytes = h->slab_doubles * sizeof(double);
   return BMPC_OK;
 }
 int bmpc_get_device_view_inflight(bmpc_handle* h, bmpc_device_view* v) {
@@ -590,7 +596,7 @@ int bmpc_get_device_view_inflight(bmpc_handle* h, bmpc_device_view* v) {
   if (!h->have_solution && !h->pending) return BMPC_ERR_INVALID;
   const int c = h->pending ? 1 - h->cur : h->cur;
   v->n_nodes = h->s_n[c]; v->times = h->s_t[c]; v->events = h->s_ev[c]; v->x = h->s_x[c]; v->u = h->s_u[c]; v->uff = h->s_uff[c]; v->K = h->s_K[c];
-  v->max_nodes = h->NS; v->nx = h->nx; v->nu = h->nu; v->batch = h->B;
+  v->max_nodes = h->NS; v->nx = h->nx; v->nu = h->nu; v->batch = h->B; v->slab = h->slab[c]; v->slab_bytes = h->slab_doubles * sizeof(double);
   return BMPC_OK;
 }
 int bmpc_get_performance(bmpc_handle* h, double* perf) {

@@ -43,7 +43,8 @@ class _Config(C.Structure):
 
 class DeviceView(C.Structure):
     _fields_ = [("n_nodes", C.c_void_p), ("times", C.c_void_p), ("events", C.c_void_p), ("x", C.c_void_p), ("u", C.c_void_p),
-                ("uff", C.c_void_p), ("K", C.c_void_p), ("max_nodes", C.c_int), ("nx", C.c_int), ("nu", C.c_int), ("batch", C.c_int)]
+                ("uff", C.c_void_p), ("K", C.c_void_p), ("max_nodes", C.c_int), ("nx", C.c_int), ("nu", C.c_int), ("batch", C.c_int),
+                ("slab", C.c_void_p), ("slab_bytes", C.c_ulonglong)]
 
 
 _dp = C.POINTER(C.c_double)

@@ -29,3 +29,104 @@ def all_gather_policies(local: dict, batch_total: int, world: int):
             full = torch.cat(parts, dim=0)
         out[name] = full
     return out
+
+
+class PolicyExchange:
+    """The north star's "one all-gather of the solved feedback policies per MPC tick" for one shard (one process per GPU).
+
+    Every policy buffer of the library is ONE contiguous slab [K | uff | x | u | times | events | n_nodes] (bmpc_device_view.slab), so the
+    exchange is a single collective per tick.  It runs on a side stream and overlaps with the next tick: the library double-buffers its
+    policies, so the slab being gathered is only overwritten two ticks later, and that tick first waits for the gather (`before_tick`).
+    `window=True` gathers only the nodes consumers read before the next tick (evaluatePolicy is called for t in [t0, t0 + 1/50 s],
+    bipedal_controllers/src/BipedalController.cpp:200): the first `window_nodes` nodes of every instance.
+
+    `slab_provider()` returns the newest policy slab as a 1-D float64 tensor (GPU: an alias of library memory, ordered after the tick in flight
+    on `compute_stream`); tests on CPU pass plain tensors and the gloo backend through the same code.
+    """
+
+    def __init__(self, mpc, dist, rank, world, window=False, window_nodes=4, slab_provider=None, compute_stream=None):
+        import torch
+        self.torch, self.dist, self.mpc, self.rank, self.world = torch, dist, mpc, rank, world
+        self.window, self.window_nodes = window, window_nodes
+        self.slab_provider = slab_provider or self._library_slab
+        self.cuda = slab_provider is None
+        self.out = [None, None]
+        self.events = []
+        self.ticks = 0
+        self.bytes_per_tick = 0
+        self._keep = []
+        if self.cuda:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+            self.compute_stream = compute_stream or torch.cuda.ExternalStream(mpc.stream(), device=self.device)
+            self.side = torch.cuda.Stream(device=self.device)
+
+    # -- newest policy slab of the library as a tensor (no copy)
+    def _library_slab(self):
+        v = self.mpc.getDeviceView(inflight=True)
+        n = int(v.slab_bytes) // 8
+
+        class _Arr:
+            pass
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(v.slab), False), "version": 3, "strides": None}
+        t = self.torch.as_tensor(a, device=self.device)
+        self._keep = self._keep[-8:] + [a]
+        return t
+
+    def _window_of(self, slab):
+        """First `window_nodes` nodes of K, uff, x, u, times of every instance, packed into one send buffer."""
+        m = self.mpc
+        B, NS, nx, nu, k = m.batch, m.max_nodes, m.nx, m.nu, self.window_nodes
+        sizes = [B * NS * nu * nx, B * NS * nu, B * NS * nx, B * NS * nu, B * NS]
+        parts, o = [], 0
+        for sz in sizes:
+            parts.append(slab[o:o + sz].view(B, NS, -1)[:, :k].reshape(-1))
+            o += sz
+        return self.torch.cat(parts)
+
+    def _gather(self, slab):
+        src = self._window_of(slab) if self.window else slab
+        i = self.ticks & 1
+        if self.out[i] is None or self.out[i].numel() != self.world * src.numel():
+            self.out[i] = self.torch.empty(self.world * src.numel(), dtype=src.dtype, device=src.device)
+        self.dist.all_gather_into_tensor(self.out[i], src)
+        self.bytes_per_tick = src.numel() * 8 * self.world
+        return self.out[i]
+
+    def after_tick(self):
+        """Call right after bmpc_advance_async: enqueues the all-gather of the policy that tick produces."""
+        torch = self.torch
+        if not self.cuda:
+            res = self._gather(self.slab_provider())
+            self.ticks += 1
+            return res
+        slab = self.slab_provider()
+        ready = torch.cuda.Event()
+        ready.record(self.compute_stream)
+        self.side.wait_event(ready)
+        with torch.cuda.stream(self.side):
+            res = self._gather(slab)
+            done = torch.cuda.Event()
+            done.record(self.side)
+        self.events.append(done)
+        self.events = self.events[-4:]
+        self.ticks += 1
+        return res
+
+    def before_tick(self):
+        """Call before bmpc_advance_async: the tick about to start overwrites the slab that was gathered two ticks ago."""
+        if self.cuda and len(self.events) >= 2:
+            self.compute_stream.wait_event(self.events[-2])
+
+    def join(self, stream=None):
+        if self.cuda:
+            (stream or self.compute_stream).wait_stream(self.side)
+
+    def shard(self, gathered, r):
+        """View of rank r's part of a gathered buffer."""
+        n = gathered.numel() // self.world
+        return gathered[r * n:(r + 1) * n]
+
+    def describe(self):
+        return {"collectives_per_tick": 1, "bytes_received_per_rank_per_tick": int(self.bytes_per_tick), "what": "first %d nodes of every instance" % self.window_nodes if self.window else "whole policy slab [K | uff | x | u | times | events | n_nodes], node slots sized to the workload",
+                "backend": "torch.distributed all_gather_into_tensor (NCCL)" if self.cuda else "gloo"}

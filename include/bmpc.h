@@ -149,6 +149,9 @@ typedef struct bmpc_device_view {
   const int* n_nodes; const double* times; const int* events;
   const double* x; const double* u; const double* uff; const double* K;
   int max_nodes, nx, nu, batch;
+  /* the arrays above live in ONE contiguous allocation [K | uff | x | u | times | events | n_nodes] of slab_bytes bytes starting at slab (= K):
+   * the multi-GPU exchange of a whole shard's policies is a single all-gather of this range */
+  const void* slab; unsigned long long slab_bytes;
 } bmpc_device_view;
 int bmpc_get_device_view(bmpc_handle* h, bmpc_device_view* v);
 int bmpc_get_device_view_inflight(bmpc_handle* h, bmpc_device_view* v);

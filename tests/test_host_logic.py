@@ -176,6 +176,54 @@ def test_policy_all_gather_world_size_2_gloo():
     assert all(ok for _, ok in res)
 
 
+def _exchange_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from bipedal_control_b200.sharding import PolicyExchange
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+
+    class FakeMpc:   # geometry of a shard; the slab layout is the library's: [K | uff | x | u | times | events | n_nodes]
+        batch, max_nodes, nx, nu = 3, 6, 22, 22
+    m = FakeMpc()
+    nK, nU, nX, nT = m.batch * m.max_nodes * m.nu * m.nx, m.batch * m.max_nodes * m.nu, m.batch * m.max_nodes * m.nx, m.batch * m.max_nodes
+    n = nK + 2 * nU + nX + nT + (nT + m.batch + 1) // 2
+    tick = {"i": 0}
+    slab = lambda: torch.arange(n, dtype=torch.float64) + 1e6 * rank + 1e3 * tick["i"]
+    ok = True
+    for window in (False, True):
+        ex = PolicyExchange(m, dist, rank, world, window=window, window_nodes=2, slab_provider=slab)
+        for t in range(3):
+            tick["i"] = t
+            ex.before_tick()
+            out = ex.after_tick()
+            for r in range(world):
+                part = ex.shard(out, r)
+                expect = torch.arange(n, dtype=torch.float64) + 1e6 * r + 1e3 * t
+                if window:
+                    K = expect[:nK].view(m.batch, m.max_nodes, -1)[:, :2].reshape(-1)
+                    ok = ok and torch.equal(part[:K.numel()], K) and part.numel() == 2 * m.batch * (m.nu * m.nx + 2 * m.nu + m.nx + 1)
+                else:
+                    ok = ok and torch.equal(part, expect)
+        ok = ok and ex.describe()["collectives_per_tick"] == 1
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_policy_exchange_world_size_2_gloo():
+    """The exchange object bench.py uses at N > 1 (one collective per tick over the policy slab; consumed-window variant), on CPU with gloo."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res)
+
+
 def test_shard_range_covers_batch():
     from bipedal_control_b200.sharding import shard_range
     for B in (1, 7, 4096, 32768):

@@ -99,9 +99,14 @@ def run(config, ticks=2):
             worst["Px"] = max(worst["Px"], np.abs(Pxj - P["Px"][12:][:, X]).max(), np.abs(P["Px"][12:, 6:9]).max())
             worst["Pe"] = max(worst["Pe"], np.abs(Pej - P["Pe"][12:]).max())
             Pu_j = P["Pu"][12:, :]
-            projector_o = Pu_j @ Pu_j.T
-            projector_g = Nn[:, :mj] @ Nn[:, :mj].T
-            worst["PN"] = max(worst["PN"], np.abs(projector_o - projector_g).max())
+            Pu_j = Pu_j[:, np.abs(Pu_j).max(axis=0) > 0] if Pu_j.size else Pu_j
+            if mj > 0:   # the bases need not be orthonormal (FullPivLU kernel): compare the orthogonal projectors onto their spans
+                qo, _ = np.linalg.qr(Pu_j); qg, _ = np.linalg.qr(Nn[:, :mj])
+                worst["PN"] = max(worst["PN"], np.abs(qo @ qo.T - qg @ qg.T).max() if qo.shape[1] == mj else 9.9)
+            # raw constraint rows of the contact velocities (upstream stacking order, zero-force rows skipped)
+            vel = [i for i in range(L["D"].shape[0]) if np.abs(L["D"][i, :12]).max() == 0.0]
+            if e["nrows"] == len(vel):
+                worst["CD"] = max(worst.get("CD", 0), np.abs(e["Cv"] - L["C"][vel][:, X]).max(), np.abs(e["Dv"] - L["D"][vel][:, 12:]).max(), np.abs(e["ev"] - L["e"][vel]).max())
             worst["K"] = max(worst["K"], np.abs(pol["K"][1][k] - P["K"]).max())
         for kk, v in worst.items():
             print(f"  LQ worst {kk:3s} {v:10.3e}")
