@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
     const bool is_null = lane >= 24 && lane - 24 < mj;
     if (is_x) { for (int i = 0; i < NJ; ++i) out[D::P_PX + i * NXA + gc] = y[i]; }
     else if (is_aff) { for (int i = 0; i < NJ; ++i) out[D::P_PE + i] = y[i]; }
-    else if (is_null) { for (int i = 0; i < NJ; ++i) out[D::P_N + i * 8 + lane - 24] = y[i]; }
+    else if (lane >= 24) { for (int i = 0; i < NJ; ++i) out[D::P_N + i * 8 + lane - 24] = y[i]; }   // columns beyond mj are zero
   } else {
   double (*Mt)[12] = sM[warp]; double (*V)[NJ] = sV[warp]; double* beta = sBeta[warp]; double* rinv = sBeta[warp] + 10;
   {   // stage Dv^T, [Cv | ev] and B_d rows 3..11: all global loads are issued before the first shared-memory store (fixed trip counts;
@@ -336,6 +336,9 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
 #pragma unroll
       for (int i = 0; i < NJ; ++i) out[D::P_N + i * 8 + t] = y[i];
     }
+  } else if (lane >= 24) {
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) out[D::P_N + i * 8 + lane - 24] = 0.0;   // unused null-space columns: never leave stale data behind
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) W[i][lane] = (i < NJ) ? y[i < NJ ? i : 0] : 0.0;   // idle lanes hold y = 0
