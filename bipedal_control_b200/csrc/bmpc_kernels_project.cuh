@@ -85,9 +85,9 @@ __device__ __forceinline__ int lu_project(const double* __restrict__ rec, double
 #pragma unroll
   for (int kk = 0; kk < SD; ++kk) {
     if (!stop) {   // warp uniform
-      double best = -1.0; int bi = 0;
+      double best = -1.0;
 #pragma unroll
-      for (int i = 0; i < NR; ++i) { const double a_ = fabs(c0[i]); if (!((rowdone >> i) & 1u) && a_ > best) { best = a_; bi = i; } }
+      for (int i = 0; i < NR; ++i) { const double a_ = fabs(c0[i]); if (!((rowdone >> i) & 1u) && a_ > best) best = a_; }
       const bool cand = lane < NJ && !used;
       const unsigned long long key = cand ? (unsigned long long)__double_as_longlong(best) : 0ull;
       const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
@@ -95,7 +95,13 @@ __device__ __forceinline__ int lu_project(const double* __restrict__ rec, double
       const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
       if ((mhi | mlo) == 0u) stop = true;   // the remaining block is exactly zero (Eigen: m_nonzero_pivots = k)
       else {
-        const unsigned win = __ballot_sync(0xffffffffu, cand && hi == mhi && lo == mlo);
+        // coefficients within PIVOT_TIE of the maximum are tied (the last pivot of a stance foot's block is an exact tie between two rows that
+        // rounding noise would decide): the first one in (column, row) order wins -- same rule as the oracle's emulation
+        const double tie = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo)) * (1.0 - 1e-10);
+        int bi = NR;
+#pragma unroll
+        for (int i = NR - 1; i >= 0; --i) if (!((rowdone >> i) & 1u) && fabs(c0[i]) >= tie) bi = i;
+        const unsigned win = __ballot_sync(0xffffffffu, cand && bi < NR);
         const int bl = __ffs(win) - 1;
         const int prow = __shfl_sync(0xffffffffu, bi, bl);
         double cp0 = 0.0, cp1 = 0.0;   // own elements of the pivot row (dynamic row index -> predicated moves)

@@ -190,6 +190,17 @@ void orc_spline(double ts, double ps, double vs, double mid, double tf, double p
 }
 // 0: Moore-Penrose projection (default = the CUDA product), 1: emulation of upstream's Eigen::FullPivLU projection (process-wide switch, tests only)
 void orc_set_projection_mode(int mode) { projection_mode() = mode; }
+// exact operation counts of ONE evaluation of the flow map + contact kinematics at (x, u): out = {add, mul, div, trig} (counting scalar)
+void orc_count_flow_map(void* h, const double* x, const double* u, unsigned long long* out) {
+  auto* s = static_cast<Solver*>(h); const Model& M = s->M;
+  Counted xc[MAXX], uc[MAXU], fc[MAXX]; V3<Counted> pc[NC], vc[NC];
+  for (int i = 0; i < M.nx; ++i) xc[i] = Counted(x[i]);
+  for (int i = 0; i < M.nu; ++i) uc[i] = Counted(u[i]);
+  flop_counter() = FlopCount();
+  flow_map<Counted>(M, xc, uc, fc, pc, vc);
+  const FlopCount c = flop_counter();
+  out[0] = c.add; out[1] = c.mul; out[2] = c.div; out[3] = c.trig;
+}
 int orc_project(int nr, int nu, int nx, const double* C, const double* D, const double* e, double* Px, double* Pu, double* Pe) {
   ORC_TRY Mat Cm(nr, nx), Dm(nr, nu); Cm.a.assign(C, C + nr * nx); Dm.a.assign(D, D + nr * nu);
   std::vector<double> ev(e, e + nr), pe; Mat px, pu; int rank = 0;

@@ -59,6 +59,32 @@ template <int N> inline Dual<N>& operator+=(Dual<N>& a, const Dual<N>& b) { a.v 
 template <int N> inline Dual<N>& operator-=(Dual<N>& a, const Dual<N>& b) { a.v -= b.v; for (int i = 0; i < N; ++i) a.d[i] -= b.d[i]; return a; }
 template <int N> inline Dual<N> sin(const Dual<N>& a) { Dual<N> r; r.v = std::sin(a.v); const double c = std::cos(a.v); for (int i = 0; i < N; ++i) r.d[i] = c * a.d[i]; return r; }
 template <int N> inline Dual<N> cos(const Dual<N>& a) { Dual<N> r; r.v = std::cos(a.v); const double s = -std::sin(a.v); for (int i = 0; i < N; ++i) r.d[i] = s * a.d[i]; return r; }
+// ---------------------------------------------------------------- counting scalar (exact flop counts instead of estimates)
+// A double that counts the arithmetic it takes part in.  flow_map<Counted> gives the exact operation count of one evaluation of the model;
+// the count of the forward-mode linearisation follows from it (every + / - costs 1 + N, every * costs 1 + 3N flops with N tangent directions).
+struct FlopCount { unsigned long long add = 0, mul = 0, div = 0, trig = 0; };
+inline FlopCount& flop_counter() { static thread_local FlopCount c; return c; }
+struct Counted {
+  double v;
+  Counted() : v(0.0) {}
+  Counted(double a) : v(a) {}
+};
+inline Counted operator+(const Counted& a, const Counted& b) { ++flop_counter().add; return Counted(a.v + b.v); }
+inline Counted operator-(const Counted& a, const Counted& b) { ++flop_counter().add; return Counted(a.v - b.v); }
+inline Counted operator-(const Counted& a) { return Counted(-a.v); }
+inline Counted operator*(const Counted& a, const Counted& b) { ++flop_counter().mul; return Counted(a.v * b.v); }
+inline Counted operator/(const Counted& a, const Counted& b) { ++flop_counter().div; return Counted(a.v / b.v); }
+inline Counted operator*(double a, const Counted& b) { ++flop_counter().mul; return Counted(a * b.v); }
+inline Counted operator*(const Counted& b, double a) { ++flop_counter().mul; return Counted(a * b.v); }
+inline Counted operator+(const Counted& a, double b) { ++flop_counter().add; return Counted(a.v + b); }
+inline Counted operator+(double b, const Counted& a) { ++flop_counter().add; return Counted(a.v + b); }
+inline Counted operator-(const Counted& a, double b) { ++flop_counter().add; return Counted(a.v - b); }
+inline Counted operator/(const Counted& a, double b) { ++flop_counter().mul; return Counted(a.v * (1.0 / b)); }
+inline Counted& operator+=(Counted& a, const Counted& b) { ++flop_counter().add; a.v += b.v; return a; }
+inline Counted& operator-=(Counted& a, const Counted& b) { ++flop_counter().add; a.v -= b.v; return a; }
+inline Counted sin(const Counted& a) { ++flop_counter().trig; return Counted(std::sin(a.v)); }
+inline Counted cos(const Counted& a) { ++flop_counter().trig; return Counted(std::cos(a.v)); }
+inline double value_of(const Counted& a) { return a.v; }
 inline double sin(double a) { return std::sin(a); }
 inline double cos(double a) { return std::cos(a); }
 inline double value_of(double a) { return a; }

@@ -420,6 +420,7 @@ inline void project_constraints(const Mat& C, const Mat& D, const std::vector<do
 // |pivot| > eps * min(rows, cols) * |largest pivot|; solve() forward-substitutes with the unit-lower factor, back-substitutes the leading
 // rank x rank block of U and sets the free unknowns to zero, i.e. it satisfies the first `rank` pivot rows and silently ignores the rest.
 // This is the oracle's default since round 2 (the CUDA product implements the same elimination in-warp, k_project<NJ, true>).
+constexpr double PIVOT_TIE = 1e-10;
 inline void project_constraints_fullpivlu(const Mat& C, const Mat& D, const std::vector<double>& e, Mat& Px, Mat& Pu, std::vector<double>& Pe, int& rank) {
   const int nr = D.r, nu = D.c, nx = C.c, sd = std::min(nr, nu);
   Mat lu = D;
@@ -429,8 +430,20 @@ inline void project_constraints_fullpivlu(const Mat& C, const Mat& D, const std:
   double maxpivot = 0.0; int nonzero = sd;
   for (int k = 0; k < sd; ++k) {
     int br = k, bc = k; double big = -1.0;
-    for (int j = k; j < nu; ++j) for (int i = k; i < nr; ++i) if (std::fabs(lu(i, j)) > big) { big = std::fabs(lu(i, j)); br = i; bc = j; }   // first maximum in column-major order, as Eigen's maxCoeff visitor on a column-major matrix
+    for (int j = k; j < nu; ++j) for (int i = k; i < nr; ++i) big = std::max(big, std::fabs(lu(i, j)));
     if (big == 0.0) { nonzero = k; break; }
+    // Pivot = the largest remaining coefficient (Eigen: maxCoeff visitor).  The two sole points of a stance foot make the LAST pivot of that
+    // foot's block a mathematically exact tie between two rows (their residuals along the dependent direction have equal magnitude), which
+    // floating-point noise would decide -- in Eigen as well.  To make the choice reproducible across implementations, coefficients within
+    // PIVOT_TIE of the maximum count as tied and the first one in (original column, original row) order wins (the CUDA kernel applies the same rule).
+    {
+      const double tie = big * (1.0 - PIVOT_TIE);
+      long bestkey = -1;
+      for (int j = k; j < nu; ++j) for (int i = k; i < nr; ++i) if (std::fabs(lu(i, j)) >= tie) {
+        const long key = (long)colp[j] * 4096 + rowp[i];
+        if (bestkey < 0 || key < bestkey) { bestkey = key; br = i; bc = j; }
+      }
+    }
     maxpivot = std::max(maxpivot, big);
     if (br != k) { for (int j = 0; j < nu; ++j) std::swap(lu(k, j), lu(br, j)); std::swap(rowp[k], rowp[br]); }
     if (bc != k) { for (int i = 0; i < nr; ++i) std::swap(lu(i, k), lu(i, bc)); std::swap(colp[k], colp[bc]); }

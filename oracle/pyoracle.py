@@ -225,6 +225,13 @@ class Oracle:
         self.L.orc_flow_map(self.h, _p(x), _p(u), _p(f), _p(pos), _p(vel))
         return f, pos, vel
 
+    def count_flow_map(self, x, u):
+        """Exact operation counts {add, mul, div, trig} of one flow-map + contact-kinematics evaluation (counting scalar)."""
+        x, u = _d(x), _d(u)
+        out = (C.c_ulonglong * 4)()
+        self.L.orc_count_flow_map(self.h, _p(x), _p(u), out)
+        return dict(add=int(out[0]), mul=int(out[1]), div=int(out[2]), trig=int(out[3]))
+
     def linearize(self, x, u):
         x, u = _d(x), _d(u)
         nx, nu = self.nx, self.nu

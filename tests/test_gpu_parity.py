@@ -557,6 +557,9 @@ def test_time_grid_capacity_is_reported():
     et = np.array([-0.5, 0.033, 0.071, 0.112, 0.155, 0.9])     # four switches off the grid inside a 0.2 s horizon: 8 extra nodes
     ms = np.array([3, 1, 3, 2, 3, 1, 3], dtype=np.int32)
     tt, ts = helpers.cmd_vel_target(x0, 0.0, (0.1, 0, 0, 0), 1.0, m["com_height"], m["default_joint_state"])
+    from oracle import pyoracle
+    nodes_expected = len(pyoracle.time_discretization(0.0, 0.2, 0.01, et)[0])     # the grid restarts at every event: 20 intervals become 20 + 8 nodes
+    assert nodes_expected > 21 + 4
     g = G(2, model_file=MODEL, dt=0.01, time_horizon=0.2, max_event_nodes=4)
     g.setCurrentObservation(0.0, x0); g.setTargetTrajectories(tt, ts); g.setModeSchedule(et, ms)
     with pytest.raises(BmpcError) as ei:
@@ -566,5 +569,5 @@ def test_time_grid_capacity_is_reported():
     g = G(2, model_file=MODEL, dt=0.01, time_horizon=0.2, max_event_nodes=8)
     g.setCurrentObservation(0.0, x0); g.setTargetTrajectories(tt, ts); g.setModeSchedule(et, ms)
     g.advanceMpc()
-    assert not g.getStatus().any() and g.getPolicy(0, 1, with_gains=False)["n_nodes"][0] == 21 + 8
+    assert not g.getStatus().any() and g.getPolicy(0, 1, with_gains=False)["n_nodes"][0] == nodes_expected
     g.close()

@@ -571,15 +571,20 @@ def _gauss_jordan_lanes(Cv, Dv, ev, n_open, nu_full):
     rank = 0
     for kk in range(min(nr, nj)):
         best, bl, prow = 0.0, None, None
-        for lane in range(nj):           # warp arg-max: first maximum in lane order; inside a lane the first maximum over the unused rows
-            if used[lane]:
-                continue
-            lb, li = -1.0, 0
-            for i in range(nr):
-                if not rowdone[i] and abs(cols[i, lane]) > lb:
-                    lb, li = abs(cols[i, lane]), i
-            if lb > best:
-                best, bl, prow = lb, lane, li
+        for lane in range(nj):           # warp maximum over the unused rows of the unused columns
+            if not used[lane]:
+                for i in range(nr):
+                    if not rowdone[i]:
+                        best = max(best, abs(cols[i, lane]))
+        if best > 0.0:                   # first coefficient within 1e-10 of the maximum in (column, row) order
+            tie = best * (1.0 - 1e-10)
+            for lane in range(nj):
+                if used[lane] or bl is not None:
+                    continue
+                for i in range(nr):
+                    if not rowdone[i] and abs(cols[i, lane]) >= tie:
+                        bl, prow = lane, i
+                        break
         if bl is None:
             break
         p = cols[prow, bl]
