@@ -93,7 +93,7 @@ struct bmpc_handle {
   double* slab[2] = {nullptr, nullptr}; size_t slab_doubles = 0;
   int cur = 0; bool have_solution = false;
   // work
-  double *d_lq = nullptr, *d_proj = nullptr, *d_stage = nullptr, *d_ric = nullptr, *d_dx = nullptr, *d_du = nullptr, *d_norms = nullptr;
+  double *d_lq = nullptr, *d_proj = nullptr, *d_stage = nullptr, *d_ric = nullptr, *d_dx = nullptr, *d_du = nullptr, *d_norms = nullptr, *d_alpha = nullptr;
   int* d_counters = nullptr;
   int* h_counters = nullptr;
   size_t rec = 0, prec = 0, krec = 0, srec = 0;
@@ -123,7 +123,7 @@ Dev make_dev(bmpc_handle* h) {
   d.p_ev = h->s_ev[h->cur]; d.p_uff = h->s_uff[h->cur]; d.p_K = h->s_K[h->cur];
   d.s_x = h->s_x[w]; d.s_u = h->s_u[w]; d.s_uff = h->s_uff[w]; d.s_K = h->s_K[w];
   d.lq = h->d_lq; d.proj = h->d_proj; d.stage = h->d_stage; d.ric = h->d_ric; d.jc = h->d_jc; d.dx = h->d_dx; d.du = h->d_du;
-  d.perf = h->s_perf[w]; d.norms = h->d_norms; d.status = h->s_status[w]; d.counters = h->d_counters;
+  d.perf = h->s_perf[w]; d.alpha = h->d_alpha; d.norms = h->d_norms; d.status = h->s_status[w]; d.counters = h->d_counters;
   return d;
 }
 
@@ -201,10 +201,12 @@ void tick(bmpc_handle* h) {
     if (iter == 0) mark(5);
     k_forward<NJ><<<(B + 3) / 4, 128, 4 * sizeof(FwdSmem<NJ>), st>>>(d); ++h->launches;
     if (iter == 0) mark(6);
-    // filter line search (device-side backtracking loop, one CTA per instance) + step + policy completion
-    k_linesearch<NJ><<<B, LS_THREADS, 0, st>>>(d, iter == h->sqp_iterations - 1 ? 1 : 0); ++h->launches;
+    // filter line search: device-side backtracking loop, one CTA per instance; then the accepted step
+    k_linesearch<NJ><<<B, LS_THREADS, 0, st>>>(d); ++h->launches;
+    k_update<NJ><<<(unsigned)(((size_t)nodes * Dims<NJ>::NX + 255) / 256), 256, 0, st>>>(d); ++h->launches;
     if (iter == 0) mark(7);
   }
+  k_policy_fill<NJ><<<B, 128, 0, st>>>(d); ++h->launches;
   mark(8);
   CK(cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int) * CNT_N, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(h->ev_done, st));
@@ -354,7 +356,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     }
     h->d_lq = P.d<double>(B * NS * h->rec); h->d_proj = P.d<double>(B * NS * h->prec); h->d_stage = P.d<double>(B * NS * h->srec); h->d_ric = P.d<double>(B * NS * h->krec);
     h->d_dx = P.d<double>(B * NS * nx); h->d_du = P.d<double>(B * NS * nu);
-    h->d_norms = P.d<double>(B * 2);
+    h->d_norms = P.d<double>(B * 2); h->d_alpha = P.d<double>(B);
     h->d_counters = P.d<int>(CNT_N); h->h_counters = P.h<int>(CNT_N);
     {  // static entries of the projected stage records (identity rows / columns of At); everything else was zeroed by the pool
       const size_t nrec = B * NS;

@@ -40,7 +40,7 @@ struct Dev {
   double* s_x; double* s_u; double* s_uff; double* s_K;                      // new primal solution / linearisation point
   double* lq; double* proj; double* stage; double* ric; const double* jc;
   double* dx; double* du;
-  double* perf; double* norms; int* status; int* counters;
+  double* perf; double* alpha; double* norms; int* status; int* counters;
 };
 
 // ------------------------------------------------------------------------------------------------ helpers

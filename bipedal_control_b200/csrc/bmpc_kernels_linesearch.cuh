@@ -8,9 +8,8 @@ namespace bmpc {
 // ONE CTA PER INSTANCE: thread = stage.  The backtracking loop of FilterLinesearch runs inside the CTA (instances are independent, so no
 // global synchronisation, no host round trip, no per-trial launches): every trial evaluates the RK2 defect, the cost and the constraint
 // violation at (x + alpha dx, u + alpha du) for all stages of the instance on the streaming, register-only flow map (model_values: no per-joint
-// arrays, no local memory), reduces them over the block and lets thread 0 take the accept / halve decision.  The accepted step is then applied
-// (x += alpha dx, u += alpha du, uff = uff0 + alpha kappa) and, on the last SQP iteration, event nodes and the terminal node copy the policy of
-// the previous node ([UPSTREAM] incrementTrajectory + multiple_shooting::toPrimalSolution).
+// arrays, no local memory), reduces them over the block and lets thread 0 take the accept / halve decision.  The accepted step size is applied by
+// the wide kernels below (k_update: x += alpha dx, u += alpha du, uff = uff0 + alpha kappa; k_policy_fill: [UPSTREAM] toPrimalSolution).
 // [UPSTREAM] FilterLinesearch::acceptStep (g_max, g_min: task.info:72-73; gamma_c 1e-6, armijoFactor 1e-4, alpha_decay 0.5, alpha_min 1e-4)
 //
 // Instances whose solve failed numerically (Riccati lost positive definiteness, rank anomaly of the constraint Jacobian, NaN) store nothing of
@@ -94,9 +93,8 @@ __device__ __forceinline__ void stage_trial(const Dev& d, size_t nb, int k, doub
 }
 
 template <int NJ>
-__global__ void __launch_bounds__(LS_THREADS, LS2_BLOCKS) k_linesearch(Dev d, int last_iteration) {
-  using R = RDims<NJ>;
-  constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU, NWARP = LS_THREADS / 32;
+__global__ void __launch_bounds__(LS_THREADS, LS2_BLOCKS) k_linesearch(Dev d) {
+  constexpr int NX = Dims<NJ>::NX, NWARP = LS_THREADS / 32;
   __shared__ double sred[NWARP][3];
   __shared__ double s_alpha;
   __shared__ int s_done;
@@ -146,42 +144,59 @@ __global__ void __launch_bounds__(LS_THREADS, LS2_BLOCKS) k_linesearch(Dev d, in
     al = s_alpha;
     if (s_done) break;
   }
-  // ---- take the step
-  const int st = d.status[b];   // written by thread 0 before the barrier above (same CTA) or by earlier kernels
-  const bool fail = (st & FAIL_MASK) != 0;
   if (tid == 0) {
+    d.alpha[b] = al;
     atomicAdd(&d.counters[CNT_TRIALS], trials); atomicMax(&d.counters[CNT_MAXTRIALS], trials);
-    if (st) atomicOr(&d.counters[CNT_STATUS], st);
-    if (fail) atomicAdd(&d.counters[CNT_FAIL], 1);
   }
-  if (fail) {
+}
+
+// ------------------------------------------------------------------------------------------------ K6: take the step, finish the policy
+template <int NJ>
+__global__ void k_update(Dev d) {   // one thread per (instance, node, component): coalesced x += alpha dx, u += alpha du, uff += alpha kappa
+  using R = RDims<NJ>;
+  constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU;
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t node = gid / NX; const int i = (int)(gid % NX);
+  const int b = (int)(node / d.NS), k = (int)(node % d.NS);
+  if (b >= d.B) return;
+  const int n = d.n_nodes[b];
+  if (k >= n) return;
+  const double al = d.alpha[b];
+  if (al == 0.0 || (d.status[b] & FAIL_MASK) != 0) return;   // rejected step / failed instance: nothing is taken
+  const size_t nb = (size_t)b * d.NS;
+  d.s_x[(nb + k) * NX + i] += al * d.dx[(nb + k) * NX + i];
+  if (i < NU && k < n - 1 && d.node_ev[nb + k] != 1) {
+    d.s_u[(nb + k) * NU + i] += al * d.du[(nb + k) * NU + i];
+    d.s_uff[(nb + k) * NU + i] += al * d.ric[(nb + k) * R::KREC + R::K_KAP + i];
+  }
+}
+// once per tick, one CTA per instance: event nodes and the terminal node copy input / feedforward / gain of the previous node
+// ([UPSTREAM] toPrimalSolution); a failed instance gets its previous policy back (see above); per-tick status summary for the host
+template <int NJ>
+__global__ void k_policy_fill(Dev d) {
+  constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU;
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const size_t nb = (size_t)b * d.NS;
+  const int st = d.status[b];
+  if (tid == 0 && st) { atomicOr(&d.counters[CNT_STATUS], st); if (st & FAIL_MASK) atomicAdd(&d.counters[CNT_FAIL], 1); }
+  if ((st & FAIL_MASK) != 0) {
     // the instance keeps its previous policy (time grid included), or has none (n_nodes = 0) if there is no previous one: the next tick then
     // cold-starts it from the initializer.  Nothing computed by this tick is stored.
     const int pn = d.p_n ? d.p_n[b] : 0;
-    for (int i = tid; i < pn; i += LS_THREADS) { d.node_t[nb + i] = d.p_t[nb + i]; d.node_ev[nb + i] = d.p_ev[nb + i]; }
-    for (int i = tid; i < pn * NX; i += LS_THREADS) d.s_x[nb * NX + i] = d.p_x[nb * NX + i];
-    for (int i = tid; i < pn * NU; i += LS_THREADS) { d.s_u[nb * NU + i] = d.p_u[nb * NU + i]; d.s_uff[nb * NU + i] = d.p_uff[nb * NU + i]; }
-    for (size_t i = tid; i < (size_t)pn * NU * NX; i += LS_THREADS) d.s_K[nb * (size_t)(NU * NX) + i] = d.p_K[nb * (size_t)(NU * NX) + i];
+    for (int i = tid; i < pn; i += nt) { d.node_t[nb + i] = d.p_t[nb + i]; d.node_ev[nb + i] = d.p_ev[nb + i]; }
+    for (int i = tid; i < pn * NX; i += nt) d.s_x[nb * NX + i] = d.p_x[nb * NX + i];
+    for (int i = tid; i < pn * NU; i += nt) { d.s_u[nb * NU + i] = d.p_u[nb * NU + i]; d.s_uff[nb * NU + i] = d.p_uff[nb * NU + i]; }
+    for (size_t i = tid; i < (size_t)pn * NU * NX; i += nt) d.s_K[nb * (size_t)(NU * NX) + i] = d.p_K[nb * (size_t)(NU * NX) + i];
     __syncthreads();
     if (tid == 0) d.n_nodes[b] = pn;
     return;
   }
-  if (al != 0.0) {
-    for (int i = tid; i < n * NX; i += LS_THREADS) d.s_x[nb * NX + i] += al * d.dx[nb * NX + i];
-    for (int i = tid; i < N * NU; i += LS_THREADS) {
-      const int k = i / NU, c = i - k * NU;
-      if (d.node_ev[nb + k] == 1) continue;
-      d.s_u[nb * NU + i] += al * d.du[nb * NU + i]; d.s_uff[nb * NU + i] += al * d.ric[(nb + k) * R::KREC + R::K_KAP + c];
-    }
-  }
-  if (!last_iteration) return;
-  __syncthreads();
-  // ---- event nodes and the terminal node copy input / feedforward / gain of the previous node
+  const int n = d.n_nodes[b];
   for (int k = 1; k < n; ++k) {
     const bool copy = (k == n - 1) || d.node_ev[nb + k] == 1;
     if (!copy) continue;
-    for (int i = tid; i < NU; i += LS_THREADS) { d.s_u[(nb + k) * NU + i] = d.s_u[(nb + k - 1) * NU + i]; d.s_uff[(nb + k) * NU + i] = d.s_uff[(nb + k - 1) * NU + i]; }
-    for (int i = tid; i < NU * NX; i += LS_THREADS) d.s_K[(nb + k) * (size_t)(NU * NX) + i] = d.s_K[(nb + k - 1) * (size_t)(NU * NX) + i];
+    for (int i = tid; i < NU; i += nt) { d.s_u[(nb + k) * NU + i] = d.s_u[(nb + k - 1) * NU + i]; d.s_uff[(nb + k) * NU + i] = d.s_uff[(nb + k - 1) * NU + i]; }
+    for (int i = tid; i < NU * NX; i += nt) d.s_K[(nb + k) * (size_t)(NU * NX) + i] = d.s_K[(nb + k - 1) * (size_t)(NU * NX) + i];
     __syncthreads();
   }
 }

@@ -54,17 +54,16 @@ __global__ void __launch_bounds__(128, 4) k_policy_expand(Dev d) {
   const int m = (int)meta[S::T_M], mj = (int)meta[S::T_MJ], nclosed = (int)meta[S::T_NCLOSED], mode = (int)meta[S::T_MODE];
   const double dt = meta[S::T_DT];
   const bool st0 = leg_in_stance(mode, 0), st1 = leg_in_stance(mode, 1);
-  const double imass = 1.0 / c_model.total_mass;
   const double* __restrict__ prj = d.proj + (nb + k) * D::PREC;
   const int lr = lane >> 2, lc = lane & 3;
   // ---- issue every global load up front (independent: their latency overlaps with the back substitution below)
   const bool active = lane <= NX;
   double z[MP];
 #pragma unroll
-  for (int i = 0; i < MP; ++i) z[i] = active ? (lane < NX ? ric[R::K_Y + i * NX + lane] : ric[R::K_YG + i]) : 0.0;
+  for (int i = 0; i < MP; ++i) z[i] = (active && i < m) ? (lane < NX ? ric[R::K_Y + i * NX + lane] : ric[R::K_YG + i]) : 0.0;   // rows >= m: padding, not stored
   double lreg[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) lreg[i] = ric[R::K_L + lane + 32 * i];
+  for (int i = 0; i < 8; ++i) lreg[i] = (((lane + 32 * i) >> 4) < m) ? ric[R::K_L + lane + 32 * i] : 0.0;
   // accumulators of the 9 output tiles initialised with [At | bt | 0]; A fragments of Bt (24 x 16)
   double c0[NTILES], c1[NTILES], af[3][4];
 #pragma unroll

@@ -59,6 +59,25 @@ __global__ void k_stage_static(double* stage, size_t nrec) {
 // column are broadcast through a double-buffered shared-memory vector, every lane eliminates its own column (above AND below the pivot, so
 // no back substitution is needed: afterwards row r of column c holds U11^-1 L^-1 P c up to the pivot scale).  The result columns
 // -col[row(k)] / pivot(k) are scattered into W (shared memory) at the pivot column's joint index.
+// c[r] for a warp-uniform r
+template <int NR>
+__device__ __forceinline__ void pick_row(const double (&c)[NR], int r, double& out) {
+  switch (r) {
+    case 0: out = c[0]; break;
+    case 1: out = c[1]; break;
+    case 2: out = c[2]; break;
+    case 3: out = c[3]; break;
+    case 4: if constexpr (NR > 4) out = c[4]; break;
+    case 5: if constexpr (NR > 5) out = c[5]; break;
+    case 6: if constexpr (NR > 6) out = c[6]; break;
+    case 7: if constexpr (NR > 7) out = c[7]; break;
+    case 8: if constexpr (NR > 8) out = c[8]; break;
+    case 9: if constexpr (NR > 9) out = c[9]; break;
+    case 10: if constexpr (NR > 10) out = c[10]; break;
+    default: if constexpr (NR > 11) out = c[11]; break;
+  }
+}
+
 template <int NJ, int NR>
 __device__ __forceinline__ int lu_project(const double* __restrict__ rec, double* __restrict__ W, int ldw, double* __restrict__ sF, int* __restrict__ sPc, double* __restrict__ sIp,
                                           int lane, int n_open) {
@@ -69,12 +88,18 @@ __device__ __forceinline__ int lu_project(const double* __restrict__ rec, double
   double c0[NR], c1[TWO ? NR : 1];
   {
     const int j = lane;
+    const double* src = j < NJ ? rec + D::R_DV + j : (j < NJ + NXA ? rec + D::R_CV + (j - NJ) : rec + D::R_EV);
+    const int stride = j < NJ ? NJ : (j < NJ + NXA ? NXA : 1);
+    const bool on = j < NCOLS;
 #pragma unroll
-    for (int i = 0; i < NR; ++i) c0[i] = j < NJ ? rec[D::R_DV + i * NJ + j] : (j < NJ + NXA ? rec[D::R_CV + i * NXA + (j - NJ)] : (j == NJ + NXA ? rec[D::R_EV + i] : 0.0));
+    for (int i = 0; i < NR; ++i) c0[i] = on ? src[i * stride] : 0.0;
     if constexpr (TWO) {
       const int j2 = lane + 32;
+      const double* src2 = j2 < NJ + NXA ? rec + D::R_CV + (j2 - NJ) : rec + D::R_EV;
+      const int stride2 = j2 < NJ + NXA ? NXA : 1;
+      const bool on2 = j2 < NCOLS;
 #pragma unroll
-      for (int i = 0; i < NR; ++i) c1[i] = j2 < NJ + NXA ? rec[D::R_CV + i * NXA + (j2 - NJ)] : (j2 == NJ + NXA ? rec[D::R_EV + i] : 0.0);
+      for (int i = 0; i < NR; ++i) c1[i] = on2 ? src2[i * stride2] : 0.0;
     }
   }
   if (lane < NR) sPc[lane] = -1;
@@ -104,9 +129,10 @@ __device__ __forceinline__ int lu_project(const double* __restrict__ rec, double
         const unsigned win = __ballot_sync(0xffffffffu, cand && bi < NR);
         const int bl = __ffs(win) - 1;
         const int prow = __shfl_sync(0xffffffffu, bi, bl);
-        double cp0 = 0.0, cp1 = 0.0;   // own elements of the pivot row (dynamic row index -> predicated moves)
-#pragma unroll
-        for (int i = 0; i < NR; ++i) if (i == prow) { cp0 = c0[i]; if constexpr (TWO) cp1 = c1[i]; }
+        // own elements of the pivot row: prow is warp uniform, so a switch (one uniform branch) replaces a chain of selects
+        double cp0 = 0.0, cp1 = 0.0;
+        pick_row<NR>(c0, prow, cp0);
+        if constexpr (TWO) pick_row<NR>(c1, prow, cp1);
         const double p = __shfl_sync(0xffffffffu, cp0, bl);
         const double ap = fabs(p), mp = fmax(maxpiv, ap);
         if (!(ap > epsd * mp)) stop = true;   // below Eigen's rank threshold: with complete pivoting everything that follows is, too
@@ -114,9 +140,10 @@ __device__ __forceinline__ int lu_project(const double* __restrict__ rec, double
           maxpiv = mp;
           const double ip = 1.0 / p;
           double* F = sF + (kk & 1) * 16;
-          if (lane == bl) {
+          if (lane == bl) {   // multipliers of the pivot column; the pivot row itself is not eliminated (its multiplier is overwritten with 0)
 #pragma unroll
-            for (int i = 0; i < NR; i += 2) reinterpret_cast<double2*>(F)[i >> 1] = make_double2(i == prow ? 0.0 : c0[i] * ip, i + 1 == prow ? 0.0 : c0[i + 1] * ip);
+            for (int i = 0; i < NR; ++i) F[i] = c0[i] * ip;
+            F[prow] = 0.0;
             used = true;
           }
           if (lane == 0) { sPc[prow] = bl; sIp[prow] = ip; }
@@ -180,7 +207,7 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
   __shared__ double sMisc[WPB][32];          // r_j (16) | open-contact correction of bt rows 3..11 (16)
   __shared__ double sRjP[16][LDR];           // joint block of R (model constant), zero padded
   __shared__ double sQd[24];
-  for (int i = threadIdx.x; i < 16 * LDR; i += 128) { const int rr_ = i / LDR, cc_ = i % LDR; sRjP[rr_][cc_] = (rr_ < NJ && cc_ < NJ) ? c_model.Rjoint[rr_ * NJ + cc_] : 0.0; }
+  for (int rr_ = threadIdx.x >> 5; rr_ < 16; rr_ += 4) { const int cc_ = threadIdx.x & 31; if (cc_ < LDR) sRjP[rr_][cc_] = (rr_ < NJ && cc_ < NJ) ? c_model.Rjoint[rr_ * NJ + cc_] : 0.0; }
   if (threadIdx.x < 24) sQd[threadIdx.x] = threadIdx.x < NX ? c_model.Qdiag[threadIdx.x] : 0.0;
   __syncthreads();
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // broadcast: lets the compiler treat the warp index as warp-uniform
@@ -366,7 +393,10 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
   // joint block of B_d rows 3..11 (columns zero padded to 16; fragment rows beyond 8 re-read row 8, results discarded) in the storage of [Cv | ev]
   static_assert(9 * LDJ <= 10 * (NXA + 1), "Bj must fit into the [Cv | ev] buffer");
   double (*Bj)[LDJ] = reinterpret_cast<double (*)[LDJ]>(&G[0][0]);
-  for (int i = lane; i < 9 * LDJ; i += 32) { const int rr_ = i / LDJ, cc_ = i % LDJ; Bj[rr_][cc_] = (cc_ < NJ) ? Bd[rr_ * NU + 12 + cc_] : 0.0; }
+  if (lane < LDJ) {
+#pragma unroll
+    for (int rr_ = 0; rr_ < 9; ++rr_) Bj[rr_][lane] = (lane < NJ) ? Bd[rr_ * NU + 12 + lane] : 0.0;
+  }
   // contribution of the fixed open-contact forces (du_F = -F) to rows 3..11 of bt, one row per lane 0..8
   if (lane < 16) {
     double open_corr = 0.0;
@@ -467,7 +497,9 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
         double v0 = (R == 6 || C0 == 6) ? 0.0 : c0, v1 = (R == 6) ? 0.0 : c1;
         if (R == C0 && R < NX) v0 += dt * sQd[R] + dq;
         if (R == C0 + 1 && R < NX) v1 += dt * sQd[R] + dq;
-        *reinterpret_cast<double2*>(so + S::S_QF + (mt * 3 + nt) * 64 + 2 * lane) = make_double2(v0, v1);
+        // Qt is symmetric: tiles below the diagonal are not stored, the ones above it are stored doubled (k_riccati_warp symmetrises S' + S'^T)
+        if (mt == nt) *reinterpret_cast<double2*>(so + S::S_QF + (mt * 3 + nt) * 64 + 2 * lane) = make_double2(v0, v1);
+        else if (mt < nt) *reinterpret_cast<double2*>(so + S::S_QF + (mt * 3 + nt) * 64 + 2 * lane) = make_double2(2.0 * v0, 2.0 * v1);
       } else if (nt < 3) {             // mt == 3: Pt rows t = g (zero beyond mj); column 6 is the rt correction of the null-space inputs
         if (nt == 0 && q == 3 && g < mj) so[S::S_R + g] = c0;
         *reinterpret_cast<double2*>(so + S::S_PRF + (0 * 5 + nt) * 64 + 2 * lane) = make_double2((C0 == 6) ? 0.0 : c0, c1);

@@ -163,7 +163,12 @@ __global__ void __launch_bounds__(32 * RIC_WPC, RIC_BLOCKS) k_riccati_warp(Dev d
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) { const double2 v = *reinterpret_cast<const double2*>(grec + S::S_QF + (a * 3 + c) * 64 + 2 * lane); Sn[a][c][0] = v.x; Sn[a][c][1] = v.y; }
+      for (int c = 0; c < 3; ++c) {
+        // Qt is symmetric: only the tiles on and above the diagonal are stored (the off-diagonal ones doubled); the symmetrisation at the end
+        // of the stage, S = (S' + S'^T) / 2, restores both halves
+        if (c >= a) { const double2 v = *reinterpret_cast<const double2*>(grec + S::S_QF + (a * 3 + c) * 64 + 2 * lane); Sn[a][c][0] = v.x; Sn[a][c][1] = v.y; }
+        else { Sn[a][c][0] = 0.0; Sn[a][c][1] = 0.0; }
+      }
     __syncwarp();   // sb visible to every lane
     // ---- step B: [H | G] += Bt^T Z ; g = rt + Bt^T sb
 #pragma unroll
@@ -218,9 +223,11 @@ __global__ void __launch_bounds__(32 * RIC_WPC, RIC_BLOCKS) k_riccati_warp(Dev d
 #pragma unroll
       for (int i = 0; i < MP; ++i) {
         if (lane < 24) sm.HG[i * LDH + lane] = hc[i];                       // Y
-        if (lane < NX) ric[R::K_Y + i * NX + lane] = hc[i];
-        if (lane < MP) ric[R::K_L + i * MP + lane] = (i >= lane) ? gc[i] : 0.0;   // L (reciprocal pivots on the diagonal)
-        if (lane == 24) { sm.gv[i] = hc[i]; ric[R::K_YG + i] = hc[i]; }       // yg
+        if (i < m) {   // rows >= m are padding: never written, never read (k_policy_expand)
+          if (lane < NX) ric[R::K_Y + i * NX + lane] = hc[i];
+          if (lane < MP) ric[R::K_L + i * MP + lane] = (i >= lane) ? gc[i] : 0.0;   // L (reciprocal pivots on the diagonal)
+        }
+        if (lane == 24) { sm.gv[i] = hc[i]; if (i < m) ric[R::K_YG + i] = hc[i]; }       // yg
       }
       __syncwarp();
       if (lane < 24) {   // s' -= Y^T yg
@@ -250,13 +257,9 @@ __global__ void __launch_bounds__(32 * RIC_WPC, RIC_BLOCKS) k_riccati_warp(Dev d
       for (int nt = 0; nt < 3; ++nt)
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl) {
-#ifdef RIC_NOSYM
-          Sf[mt][nt][sl] = Sn[mt][nt][sl];
-#else
           const int src = (2 * q + sl) * 4 + (g >> 1);
           const double t0 = __shfl_sync(0xffffffffu, Sn[nt][mt][0], src), t1 = __shfl_sync(0xffffffffu, Sn[nt][mt][1], src);
           Sf[mt][nt][sl] = 0.5 * (Sn[mt][nt][sl] + ((g & 1) ? t1 : t0));
-#endif
         }
     __syncwarp();   // HG / gv / sb are rewritten by the next stage
   }

@@ -280,7 +280,7 @@ class BatchedMpcMrtInterface:
     def phaseTimes(self):
         ms = (C.c_float * 9)()
         self._ck(self.L.bmpc_get_phase_times(self.h, ms))
-        names = ["setup", "lq", "projection", "riccati", "policy_expand", "forward", "linesearch"]
+        names = ["setup", "lq", "projection", "riccati", "policy_expand", "forward", "linesearch", "finalize"]
         out = {k: float(ms[i]) for i, k in enumerate(names)}
         out["linesearch_trials"] = int(ms[8])   # largest number of trials any instance needed
         return out

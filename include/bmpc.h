@@ -166,7 +166,7 @@ int bmpc_get_status(bmpc_handle* h, int* status /* B */);
 int bmpc_evaluate_policy(bmpc_handle* h, const double* t, const double* x, double* x_opt, double* u_opt, int* mode);
 
 /* number of kernels launched by the last bmpc_advance (for bench.py's gpu_launches) and per-phase device times in
- * milliseconds of the last tick: ms[0..7] = {setup, lq, projection, riccati, policy_expand, forward, linesearch+step, (unused)}, ms[8] = largest number of
+ * milliseconds of the last tick: ms[0..7] = {setup, lq, projection, riccati, policy_expand, forward, linesearch + step, policy completion}, ms[8] = largest number of
  * line-search trials any instance needed */
 int bmpc_get_launch_count(const bmpc_handle* h);
 int bmpc_get_phase_times(bmpc_handle* h, float* ms /* 9 */);

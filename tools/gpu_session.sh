@@ -15,7 +15,7 @@ if [[ " $* " != *" notest "* ]]; then
 fi
 timeout 900 python bench.py --steps 10 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; tail -c 4000 $OUT/${TAG}_bench.json; tail -5 $OUT/${TAG}_bench.err
 if [[ " $* " != *" noprof "* ]]; then
-  timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 200 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra > $OUT/${TAG}_ncu_launch.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__inst_executed.sum --clock-control none -c 200 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra > $OUT/${TAG}_ncu_launch.log 2>&1
   KREG='regex:k_lq_pack|k_riccati_warp|k_project|k_policy_expand|k_linesearch|k_forward'
   timeout 900 ncu --set full --clock-control none --import-source on -k "$KREG" --launch-skip 12 --launch-count 6 -o $OUT/${TAG}_full -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra > $OUT/${TAG}_ncu_full.log 2>&1
   ncu -i $OUT/${TAG}_full.ncu-rep --page raw --csv > $OUT/${TAG}_full_raw.csv 2>/dev/null
