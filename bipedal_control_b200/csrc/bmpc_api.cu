@@ -67,6 +67,7 @@ struct bmpc_handle {
   HostModel model; unsigned long long model_id = 0;
   int B = 0, NS = 0, ME = 0, TP = 0, nj = 0, nx = 0, nu = 0, device = 0, sqp_iterations = 1;
   double dt = 0, horizon = 0;
+  double rollout_abs = 1e-5, rollout_rel = 1e-3, rollout_dt = 0.015;   // task.info:159-167 (AbsTolODE, RelTolODE, timeStep)
   cudaStream_t stream = nullptr, io_stream = nullptr;
   cudaEvent_t ev_done = nullptr, ev_inputs = nullptr;
   std::string err;
@@ -99,7 +100,7 @@ struct bmpc_handle {
   size_t rec = 0, prec = 0, krec = 0, srec = 0;
   int projection_mode = 1;   // 1: upstream's FullPivLU projection (default), 0: Moore-Penrose (Householder QR on per-foot compressed rows)
   // gait bookkeeping
-  std::vector<GaitSchedule> gaits; bool use_gait = false;
+  GaitDev gait{}; int* d_gait_rc = nullptr; bool use_gait = false;
   // stats
   int launches = 0; bool timing = false; cudaEvent_t tev[10] = {}; float phase_ms[9] = {};
   int linesearch_trials = 0, max_trials = 0, failed_instances = 0, status_or = 0;
@@ -174,13 +175,14 @@ void tick(bmpc_handle* h) {
   upload_inputs(h);
   CK(cudaMemsetAsync(h->s_status[w], 0, sizeof(int) * B, st));
   CK(cudaMemsetAsync(h->d_counters, 0, sizeof(int) * CNT_N, st));
+  Dev d = make_dev(h);
+  const int nodes = B * NS;
+  mark(0);
+  if (h->use_gait) { k_gait_schedule<<<(B + 127) / 128, 128, 0, st>>>(h->gait, d); ++h->launches; }   // modifyReferences: per-instance gait tiling on the device
   // the mode schedule this policy is solved with travels with the policy buffer (evaluatePolicy reports the mode from it)
   CK(cudaMemcpyAsync(h->s_nev[w], h->d_n_ev, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(h->s_evt[w], h->d_ev_t, sizeof(double) * B * h->ME, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(h->s_evm[w], h->d_ev_mode, sizeof(int) * B * (h->ME + 1), cudaMemcpyDeviceToDevice, st));
-  Dev d = make_dev(h);
-  const int nodes = B * NS;
-  mark(0);
   k_time_grid<<<(B + 127) / 128, 128, 0, st>>>(d); ++h->launches;
   k_node_setup<NJ><<<(nodes + 127) / 128, 128, 0, st>>>(d); ++h->launches;
   mark(1);
@@ -248,28 +250,25 @@ struct ReadGuard {   // pins the current policy buffer while a getter copies fro
   ~ReadGuard() { { std::lock_guard<std::mutex> lk(h->mtx); --h->readers[c]; } h->cv.notify_all(); }
 };
 
-void compute_gait_schedules(bmpc_handle* h) {
-  if (!h->have_obs) throw std::invalid_argument("[bmpc] gait schedule mode needs host observations (bmpc_set_observations)");
-  staging_ready(h);
-  const int B = h->B, ME = h->ME;
-  for (int b = 0; b < B; ++b) {
-    const double t0 = h->h_t0[b], tf = t0 + h->horizon;
-    // SwitchedModelReferenceManager::modifyReferences (SwitchedModelReferenceManager.cpp:62-69)
-    const ModeSchedule& ms = h->gaits[b].getModeSchedule(t0 - h->horizon, tf + h->horizon);
-    const int ne = (int)ms.eventTimes.size();
-    if (ne > ME) throw std::length_error("[bmpc] mode schedule exceeds max_events");
-    h->h_n_ev[b] = ne;
-    for (int i = 0; i < ne; ++i) h->h_ev_t[(size_t)b * ME + i] = ms.eventTimes[i];
-    for (int i = 0; i <= ne; ++i) h->h_ev_mode[(size_t)b * (ME + 1) + i] = ms.modeSequence[i];
-  }
-  h->sched_dirty = true; h->have_sched = true;
+GaitTemplateArrays to_template_arrays(const std::vector<int>& modes, const std::vector<double>& times) {
+  if (modes.size() > (size_t)GAIT_TMAX || times.size() != modes.size() + 1) throw std::invalid_argument("[bmpc] mode-sequence template: at most 8 phases, n + 1 switching times");
+  GaitTemplateArrays t{}; t.n = (int)modes.size();
+  for (size_t i = 0; i < modes.size(); ++i) t.modes[i] = modes[i];
+  for (size_t i = 0; i < times.size(); ++i) t.times[i] = times[i];
+  return t;
 }
-
-GaitSchedule initial_gait(const bmpc_handle* h) {
-  // per-instance gait schedules start from reference.info's initialModeSchedule / defaultModeSequenceTemplate (BipedalRobotInterface.cpp:209-234)
-  GaitSchedule g0; g0.ms.eventTimes = h->model.init_events; g0.ms.modeSequence = h->model.init_modes; g0.tmpl = h->model.default_template;
-  g0.phaseTransitionStanceTime = h->model.phase_transition_stance_time;
-  return g0;
+// (re)initialises the gait bookkeeping of instances [first, first + count) from reference.info's initialModeSchedule /
+// defaultModeSequenceTemplate (BipedalRobotInterface.cpp:209-234); caller holds h->mtx
+void init_gaits(bmpc_handle* h, int first, int count) {
+  const auto& ev = h->model.init_events; const auto& ms = h->model.init_modes;
+  if ((int)ev.size() > h->ME || ms.size() != ev.size() + 1) throw std::invalid_argument("[bmpc] initialModeSchedule does not fit max_events");
+  double* d_ev = nullptr; int* d_ms = nullptr;
+  CK(cudaMalloc(&d_ev, sizeof(double) * std::max<size_t>(ev.size(), 1))); CK(cudaMalloc(&d_ms, sizeof(int) * ms.size()));
+  CK(cudaMemcpyAsync(d_ev, ev.data(), sizeof(double) * ev.size(), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_ms, ms.data(), sizeof(int) * ms.size(), cudaMemcpyHostToDevice, h->stream));
+  k_gait_init<<<(count + 127) / 128, 128, 0, h->stream>>>(h->gait, first, count, (int)ev.size(), d_ev, d_ms, to_template_arrays(h->model.default_template.modes, h->model.default_template.times));
+  CK(cudaGetLastError()); CK(cudaStreamSynchronize(h->stream));
+  cudaFree(d_ev); cudaFree(d_ms);
 }
 
 int fail(bmpc_handle* h, int code, const std::string& msg) {
@@ -378,7 +377,10 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
       CK(cudaMemcpy(h->d_jc, jc.data(), sizeof(double) * jc.size(), cudaMemcpyHostToDevice));
     }
     h->d_eval_t = P.d<double>(B); h->d_eval_x = P.d<double>(B * nx); h->d_eval_xo = P.d<double>(B * nx); h->d_eval_uo = P.d<double>(B * nu); h->d_eval_m = P.d<int>(B);
-    h->gaits.assign(B, initial_gait(h));
+    h->gait.B = h->B; h->gait.cap = h->ME;
+    h->gait.n = P.d<int>(B); h->gait.ev = P.d<double>(B * h->ME); h->gait.modes = P.d<int>(B * (h->ME + 1)); h->gait.tmpl = P.d<GaitTemplateArrays>(B);
+    h->d_gait_rc = P.d<int>(1);
+    init_gaits(h, 0, h->B);
     *out = h;
     return BMPC_OK;
   } catch (const CudaError& e) { destroy_impl(h); return fail(nullptr, BMPC_ERR_CUDA, e.what()); }
@@ -415,11 +417,11 @@ int bmpc_reset(bmpc_handle* h, int instance) {
   CK(cudaSetDevice(h->device));
   std::unique_lock<std::mutex> lk(h->mtx);
   wait_and_publish(h, lk);
-  if (instance < 0) { h->have_solution = false; h->gaits.assign(h->B, initial_gait(h)); }
+  if (instance < 0) { h->have_solution = false; init_gaits(h, 0, h->B); }
   else {
     // one instance: its warm start is dropped by emptying its previous solution (the initializer is used for every node of the next tick)
     if (h->have_solution) { CK(cudaMemsetAsync(h->s_n[h->cur] + instance, 0, sizeof(int), h->stream)); CK(cudaStreamSynchronize(h->stream)); }
-    h->gaits[instance] = initial_gait(h);
+    init_gaits(h, instance, 1);
   }
   return BMPC_OK; API_END(h)
 }
@@ -510,10 +512,19 @@ int bmpc_set_mode_schedules_device(bmpc_handle* h, int stride, const int* n_even
 int bmpc_gait_insert(bmpc_handle* h, int instance, int n_modes, const int* modes, const double* switching_times, double start_time, double final_time) {
   API_BEGIN if (!h || !modes || !switching_times || n_modes <= 0) throw std::invalid_argument("[bmpc] null argument");
   if (instance >= h->B) throw std::invalid_argument("[bmpc] instance out of range");
-  GaitTemplate t; t.modes.assign(modes, modes + n_modes); t.times.assign(switching_times, switching_times + n_modes + 1);
-  std::lock_guard<std::mutex> lk(h->mtx);   // GaitReceiver's receivedGaitMutex_ (GaitReceiver.cpp:52,65)
-  const int b0 = instance < 0 ? 0 : instance, b1 = instance < 0 ? h->B : instance + 1;
-  for (int b = b0; b < b1; ++b) h->gaits[b].insertModeSequenceTemplate(t, start_time, final_time);
+  const GaitTemplateArrays t = to_template_arrays(std::vector<int>(modes, modes + n_modes), std::vector<double>(switching_times, switching_times + n_modes + 1));
+  CK(cudaSetDevice(h->device));
+  std::unique_lock<std::mutex> lk(h->mtx);   // GaitReceiver's receivedGaitMutex_ (GaitReceiver.cpp:52,65); stream order puts it after the tick in flight
+  const int first = instance < 0 ? 0 : instance, count = instance < 0 ? h->B : 1;
+  int rc = 0;
+  CK(cudaMemsetAsync(h->d_gait_rc, 0, sizeof(int), h->stream));
+  k_gait_insert<<<(count + 127) / 128, 128, 0, h->stream>>>(h->gait, first, count, t, start_time, final_time, h->model.phase_transition_stance_time, h->d_gait_rc);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(&rc, h->d_gait_rc, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  lk.unlock();                               // getters are not held up while the stream drains
+  CK(cudaStreamSynchronize(h->stream));
+  if (rc == GAIT_CAPACITY) throw std::length_error("[bmpc] gait schedule exceeds max_events");
+  if (rc == GAIT_TILING_ORDER) throw std::invalid_argument("[bmpc] The initial time for template-tiling is not greater than the last event time.");   // GaitSchedule.cpp:118-120 throws the same
   return BMPC_OK; API_END(h)
 }
 int bmpc_gait_insert_named(bmpc_handle* h, int instance, const char* gait_name, double start_time, double final_time) {
@@ -522,17 +533,23 @@ int bmpc_gait_insert_named(bmpc_handle* h, int instance, const char* gait_name, 
     if (g.name == gait_name) return bmpc_gait_insert(h, instance, (int)g.modes.size(), g.modes.data(), g.times.data(), start_time, final_time);
   return fail(h, BMPC_ERR_INVALID, std::string("[bmpc] unknown gait '") + gait_name + "'");
 }
-int bmpc_use_gait_schedule(bmpc_handle* h, int enable) { if (!h) return BMPC_ERR_INVALID; std::lock_guard<std::mutex> lk(h->mtx); h->use_gait = enable != 0; return BMPC_OK; }
+int bmpc_use_gait_schedule(bmpc_handle* h, int enable) { if (!h) return BMPC_ERR_INVALID; std::lock_guard<std::mutex> lk(h->mtx); h->use_gait = enable != 0; if (h->use_gait) h->sched_dirty = false; return BMPC_OK; }
 int bmpc_gait_peek(const bmpc_handle* hc, int instance, int cap, double* event_times, int* mode_sequence) {
   bmpc_handle* h = const_cast<bmpc_handle*>(hc);
-  if (!h || instance < 0 || instance >= h->B) return BMPC_ERR_INVALID;
-  std::lock_guard<std::mutex> lk(h->mtx);
-  const ModeSchedule& ms = h->gaits[instance].ms;
-  const int n = (int)ms.eventTimes.size();
+  API_BEGIN if (!h || instance < 0 || instance >= h->B || !event_times || !mode_sequence) return BMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  std::unique_lock<std::mutex> lk(h->mtx);
+  int n = 0;
+  std::vector<double> ev(h->ME); std::vector<int> ms(h->ME + 1);
+  CK(cudaMemcpyAsync(&n, h->gait.n + instance, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(ev.data(), h->gait.ev + (size_t)instance * h->ME, sizeof(double) * h->ME, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(ms.data(), h->gait.modes + (size_t)instance * (h->ME + 1), sizeof(int) * (h->ME + 1), cudaMemcpyDeviceToHost, h->stream));
+  lk.unlock();
+  CK(cudaStreamSynchronize(h->stream));
   if (n > cap) return BMPC_ERR_CAPACITY;
-  for (int i = 0; i < n; ++i) event_times[i] = ms.eventTimes[i];
-  for (int i = 0; i <= n; ++i) mode_sequence[i] = ms.modeSequence[i];
-  return n;
+  for (int i = 0; i < n; ++i) event_times[i] = ev[i];
+  for (int i = 0; i <= n; ++i) mode_sequence[i] = ms[i];
+  return n; API_END(h)
 }
 
 int bmpc_advance_async(bmpc_handle* h) {
@@ -540,9 +557,8 @@ int bmpc_advance_async(bmpc_handle* h) {
   CK(cudaSetDevice(h->device));
   std::unique_lock<std::mutex> lk(h->mtx);
   wait_and_publish(h, lk);                                         // one tick at a time (MPC_BASE::run is not re-entrant either)
-  if (h->use_gait) compute_gait_schedules(h);
   if (!h->have_tgt) throw std::invalid_argument("[bmpc] target trajectories not set");
-  if (!h->have_sched) throw std::invalid_argument("[bmpc] mode schedules not set (bmpc_set_mode_schedules or bmpc_use_gait_schedule)");
+  if (!h->have_sched && !h->use_gait) throw std::invalid_argument("[bmpc] mode schedules not set (bmpc_set_mode_schedules or bmpc_use_gait_schedule)");
   const int w = 1 - h->cur;
   h->cv.wait(lk, [&] { return h->readers[w] == 0; });              // nobody is still copying the buffer this tick overwrites
   if (h->nj == 10) tick<10>(h); else tick<12>(h);
@@ -647,6 +663,27 @@ int bmpc_shift_observations(bmpc_handle* h, double dt) {
   else k_shift_observations<12><<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->NS, dt, h->s_n[c], h->s_t[c], h->s_x[c], h->d_t0, h->d_x0);
   h->have_obs = false; CK(cudaGetLastError());
   return BMPC_OK; API_END(h)
+}
+// MRT_BASE::rolloutPolicy [UPSTREAM] (BipedalController.cpp:322, task.info:159-167), batched and device resident: see k_rollout
+int bmpc_rollout_observations(bmpc_handle* h, double time_step, int substeps) {
+  API_BEGIN if (!h) return BMPC_ERR_INVALID;
+  if (!(time_step > 0.0) || substeps < 1) throw std::invalid_argument("[bmpc] rollout needs time_step > 0 and substeps >= 1");
+  CK(cudaSetDevice(h->device));
+  std::lock_guard<std::mutex> lk(h->mtx);
+  if (!h->have_solution && !h->pending) throw std::invalid_argument("[bmpc] no solution yet");
+  ensure_model_image(h);
+  upload_inputs(h);
+  const int c = h->pending ? 1 - h->cur : h->cur, B = h->B;
+  if (h->nj == 10) k_rollout<10><<<(B + 3) / 4, 128, 0, h->stream>>>(B, h->NS, h->ME, h->s_n[c], h->s_t[c], h->s_uff[c], h->s_K[c], h->s_nev[c], h->s_evt[c], h->d_t0, h->d_x0, time_step, substeps, h->rollout_abs, h->rollout_rel, h->rollout_dt, h->s_status[c]);
+  else k_rollout<12><<<(B + 3) / 4, 128, 0, h->stream>>>(B, h->NS, h->ME, h->s_n[c], h->s_t[c], h->s_uff[c], h->s_K[c], h->s_nev[c], h->s_evt[c], h->d_t0, h->d_x0, time_step, substeps, h->rollout_abs, h->rollout_rel, h->rollout_dt, h->s_status[c]);
+  h->have_obs = false; CK(cudaGetLastError());
+  return BMPC_OK; API_END(h)
+}
+int bmpc_set_rollout_settings(bmpc_handle* h, double abs_tol, double rel_tol, double initial_time_step) {
+  if (!h || !(abs_tol > 0.0) || !(rel_tol >= 0.0) || !(initial_time_step > 0.0)) return BMPC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mtx);
+  h->rollout_abs = abs_tol; h->rollout_rel = rel_tol; h->rollout_dt = initial_time_step;
+  return BMPC_OK;
 }
 int bmpc_set_targets_from_cmd_vel_device(bmpc_handle* h, const double* cmd_dev, double time_to_target) {
   API_BEGIN if (!h || !cmd_dev) return BMPC_ERR_INVALID;

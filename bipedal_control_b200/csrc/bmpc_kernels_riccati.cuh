@@ -61,6 +61,21 @@ struct RDims {
                        K_MISC = K_G + NX, KREC = ((K_MISC + 2 + 3) / 4) * 4;
 };
 
+// chol_forward + the record of the stage for k_policy_expand: Y (M x NX), yg (M), L (M x MP, reciprocal pivots on the diagonal).  Rows >= M are
+// padding: never written, never read.  The trip counts are compile-time constants, so the stores stay one straight-line batch.
+template <int M, int MP, int NX>
+__device__ __forceinline__ bool chol_forward_store(double (&gc)[MP], double (&hc)[MP], int lane, double* __restrict__ ric) {
+  using R = RDims<NX - 12>;
+  const bool not_pd = chol_forward<M, MP>(gc, hc, lane);
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    if (lane < NX) ric[R::K_Y + i * NX + lane] = hc[i];
+    if (lane < MP) ric[R::K_L + i * MP + lane] = (i >= lane) ? gc[i] : 0.0;
+    if (lane == 24) ric[R::K_YG + i] = hc[i];
+  }
+  return not_pd;
+}
+
 // ------------------------------------------------------------------------------------------------ K2 (default): backward Riccati recursion, ONE WARP PER INSTANCE
 // No block-level barrier anywhere: the 4 warps of a CTA run 4 independent instances.  The value function S (24 x 24) never leaves the
 // warp's registers: it is held as the 3 x 3 accumulator fragments of mma.sync.m8n8k4.f64 (lane (g, q) = (lane >> 2, lane & 3) owns
@@ -211,23 +226,19 @@ __global__ void __launch_bounds__(32 * RIC_WPC, RIC_BLOCKS) k_riccati_warp(Dev d
       __syncwarp();
       bool not_pd;
       switch (m) {   // reduced input dimensions that occur: H1 6 / 9 / 12 (FLY / single stance / double stance), G1 8 / 11 / 14
-        case 6: not_pd = chol_forward<6, MP>(gc, hc, lane); break;
-        case 9: not_pd = chol_forward<9, MP>(gc, hc, lane); break;
-        case 12: not_pd = chol_forward<12, MP>(gc, hc, lane); break;
-        case 8: not_pd = chol_forward<8, MP>(gc, hc, lane); break;
-        case 11: not_pd = chol_forward<11, MP>(gc, hc, lane); break;
-        case 14: not_pd = chol_forward<14, MP>(gc, hc, lane); break;
-        default: not_pd = chol_forward<MP, MP>(gc, hc, lane); break;   // padded pivots are identity rows
+        case 6: not_pd = chol_forward_store<6, MP, NX>(gc, hc, lane, ric); break;
+        case 9: not_pd = chol_forward_store<9, MP, NX>(gc, hc, lane, ric); break;
+        case 12: not_pd = chol_forward_store<12, MP, NX>(gc, hc, lane, ric); break;
+        case 8: not_pd = chol_forward_store<8, MP, NX>(gc, hc, lane, ric); break;
+        case 11: not_pd = chol_forward_store<11, MP, NX>(gc, hc, lane, ric); break;
+        case 14: not_pd = chol_forward_store<14, MP, NX>(gc, hc, lane, ric); break;
+        default: not_pd = chol_forward_store<MP, MP, NX>(gc, hc, lane, ric); break;   // padded pivots are identity rows
       }
       if (not_pd && lane == 0) atomicOr(&d.status[b], 1);
 #pragma unroll
       for (int i = 0; i < MP; ++i) {
         if (lane < 24) sm.HG[i * LDH + lane] = hc[i];                       // Y
-        if (i < m) {   // rows >= m are padding: never written, never read (k_policy_expand)
-          if (lane < NX) ric[R::K_Y + i * NX + lane] = hc[i];
-          if (lane < MP) ric[R::K_L + i * MP + lane] = (i >= lane) ? gc[i] : 0.0;   // L (reciprocal pivots on the diagonal)
-        }
-        if (lane == 24) { sm.gv[i] = hc[i]; if (i < m) ric[R::K_YG + i] = hc[i]; }       // yg
+        if (lane == 24) sm.gv[i] = hc[i];                                   // yg
       }
       __syncwarp();
       if (lane < 24) {   // s' -= Y^T yg

@@ -4,6 +4,42 @@
 
 namespace bmpc {
 
+// ------------------------------------------------------------------------------------------------ gait bookkeeping on the device (one thread per instance)
+struct GaitDev { int B, cap; int* n; double* ev; int* modes; GaitTemplateArrays* tmpl; };
+__device__ __forceinline__ GaitView gait_view(const GaitDev& g, int b) { return GaitView{g.cap, g.n + b, g.ev + (size_t)b * g.cap, g.modes + (size_t)b * (g.cap + 1), g.tmpl + b}; }
+// reference.info initialModeSchedule / defaultModeSequenceTemplate for instances [first, first + count) (BipedalRobotInterface.cpp:209-234)
+__global__ void k_gait_init(GaitDev g, int first, int count, int n0, const double* ev0, const int* modes0, GaitTemplateArrays t0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const GaitView v = gait_view(g, first + i);
+  *v.n = n0;
+  for (int k = 0; k < n0; ++k) v.ev[k] = ev0[k];
+  for (int k = 0; k <= n0; ++k) v.modes[k] = modes0[k];
+  *v.tmpl = t0;
+}
+// GaitSchedule::insertModeSequenceTemplate for instances [first, first + count): status[] gets GaitStatus codes (0 = ok)
+__global__ void k_gait_insert(GaitDev g, int first, int count, GaitTemplateArrays t, double start, double fin, double transition, int* result) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int rc = gait_insert(gait_view(g, first + i), t, start, fin, transition);
+  if (rc != GAIT_OK) atomicMax(result, rc);
+}
+// SwitchedModelReferenceManager::modifyReferences (SwitchedModelReferenceManager.cpp:62-69): modeSchedule = gaitSchedule.getModeSchedule(t0 - T, tf + T),
+// written straight into the solver's mode-schedule inputs
+__global__ void k_gait_schedule(GaitDev g, Dev d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  const GaitView v = gait_view(g, b);
+  const double t0 = d.t0[b], tf = t0 + d.horizon;
+  const int rc = gait_get_mode_schedule(v, t0 - d.horizon, tf + d.horizon);
+  int n = *v.n;
+  if (rc != GAIT_OK || n > d.ME) { atomicOr(&d.status[b], 32); n = n < d.ME ? n : d.ME; }
+  int* nev = const_cast<int*>(d.n_ev); double* evt = const_cast<double*>(d.ev_t) + (size_t)b * d.ME; int* evm = const_cast<int*>(d.ev_mode) + (size_t)b * (d.ME + 1);
+  nev[b] = n;
+  for (int k = 0; k < n; ++k) evt[k] = v.ev[k];
+  for (int k = 0; k <= n; ++k) evm[k] = v.modes[k];
+}
+
 // ------------------------------------------------------------------------------------------------ K0a: time grid
 __global__ void k_time_grid(Dev d) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;

@@ -72,7 +72,7 @@ def load_library(path: str | None = None):
                  "bmpc_set_mode_schedules_device", "bmpc_gait_insert", "bmpc_gait_insert_named", "bmpc_use_gait_schedule", "bmpc_gait_peek",
                  "bmpc_advance", "bmpc_advance_async", "bmpc_synchronize", "bmpc_get_policy", "bmpc_get_device_view", "bmpc_get_performance",
                  "bmpc_get_status", "bmpc_evaluate_policy", "bmpc_get_launch_count", "bmpc_get_phase_times", "bmpc_enable_phase_timing",
-                 "bmpc_poll", "bmpc_get_device_view_inflight", "bmpc_get_tick_stats",
+                 "bmpc_poll", "bmpc_get_device_view_inflight", "bmpc_get_tick_stats", "bmpc_rollout_observations", "bmpc_set_rollout_settings",
                  "bmpc_debug_copy", "bmpc_debug_record_sizes", "bmpc_debug_set_option"):
         getattr(L, name).restype = C.c_int
     if path is None:
@@ -176,6 +176,13 @@ class BatchedMpcMrtInterface:
     def shiftObservations(self, dt: float):
         """t0 += dt, x0 = optimized state at the new time (device side, perfect-model closed loop)."""
         self._ck(self.L.bmpc_shift_observations(self.h, C.c_double(dt)))
+
+    def rolloutObservations(self, time_step: float, substeps: int = 1):
+        """MRT_BASE::rolloutPolicy for the batch: the observations advance by `time_step` under the feedback policy u = uff(t) + K(t) x (device side)."""
+        self._ck(self.L.bmpc_rollout_observations(self.h, C.c_double(time_step), C.c_int(substeps)))
+
+    def setRolloutSettings(self, abs_tol=1e-5, rel_tol=1e-3, initial_time_step=0.015):
+        self._ck(self.L.bmpc_set_rollout_settings(self.h, C.c_double(abs_tol), C.c_double(rel_tol), C.c_double(initial_time_step)))
 
     def getObservations(self):
         t, x = np.zeros(self.batch), np.zeros((self.batch, self.nx))

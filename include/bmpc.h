@@ -101,6 +101,15 @@ int bmpc_set_targets_from_cmd_vel_device(bmpc_handle* h, const double* cmd_dev, 
  * flight, in stream order) interpolated at the new time (perfect-model stand-in for the MRT_ROS_Dummy_Loop rollout [UPSTREAM] that
  * ocs2_bipedal_robot_ros/src/BipedalRobotDummyNode.cpp:72-86 runs between MPC ticks).  bmpc_get_observations reads them back. */
 int bmpc_shift_observations(bmpc_handle* h, double dt);
+/* MRT_BASE::rolloutPolicy [UPSTREAM] for the whole batch, device resident (mpcMrtInterface_->initRollout(&interface.getRollout()),
+ * BipedalController.cpp:322; the dummy loop of ocs2_bipedal_robot_ros/src/BipedalRobotDummyNode.cpp:72-86 advances the observation with it):
+ * integrates the closed loop xdot = f(x, uff(t) + K(t) x) of the newest policy from each instance's observation (t0, x0) over `substeps`
+ * consecutive periods of time_step / substeps and stores the result as the new observation.  Integrator = upstream's rollout settings
+ * (task.info:159-167: ODE45 = Dormand-Prince 5(4) with odeint's step-size control, AbsTolODE 1e-5, RelTolODE 1e-3, initial step `timeStep` 0.015;
+ * sub-intervals split at the policy's mode switches); bmpc_set_rollout_settings overrides the three numbers.  Instances without a policy only
+ * advance in time; an instance whose integration fails keeps its observation and gets status bit 8. */
+int bmpc_rollout_observations(bmpc_handle* h, double time_step, int substeps);
+int bmpc_set_rollout_settings(bmpc_handle* h, double abs_tol, double rel_tol, double initial_time_step);
 int bmpc_get_observations(bmpc_handle* h, double* t, double* x);
 
 /* ReferenceManager::setModeSchedule [UPSTREAM]: explicit ModeSchedule per instance; n_events[B],
@@ -109,7 +118,8 @@ int bmpc_get_observations(bmpc_handle* h, double* t, double* x);
 int bmpc_set_mode_schedules(bmpc_handle* h, int stride, const int* n_events, const double* event_times, const int* mode_sequence);
 int bmpc_set_mode_schedules_device(bmpc_handle* h, int stride, const int* n_events_dev, const double* event_times_dev, const int* mode_sequence_dev);
 
-/* GaitSchedule (ocs2_bipedal_robot/src/gait/GaitSchedule.cpp): per-instance gait bookkeeping on the host.
+/* GaitSchedule (ocs2_bipedal_robot/src/gait/GaitSchedule.cpp): per-instance gait bookkeeping, device resident (one thread per instance; a tick
+ * has no per-instance host work, and the observations may be host or device resident).
  * bmpc_gait_insert == GaitSchedule::insertModeSequenceTemplate (GaitSchedule.cpp:46-73; called from
  * GaitReceiver::preSolverRun, ocs2_bipedal_robot_ros/src/gait/GaitReceiver.cpp:49-59); instance < 0 applies to all.
  * bmpc_use_gait_schedule(1) makes bmpc_advance derive each instance's ModeSchedule with

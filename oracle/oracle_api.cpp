@@ -136,6 +136,13 @@ int orc_get_node_projection(void* h, int k, double* Px, double* Pu, double* Pe, 
   return 0;
 }
 void orc_evaluate_policy(void* h, double t, const double* xm, double* xOpt, double* uOpt, int* mode) { static_cast<Solver*>(h)->evaluatePolicy(t, xm, xOpt, uOpt, mode); }
+// MRT_BASE::rolloutPolicy: x <- closed-loop state at t + time_step under the current policy; `substeps` consecutive calls of time_step / substeps
+int orc_rollout_policy(void* h, double t, double* x, double time_step, int substeps) {
+  ORC_TRY auto* s = static_cast<Solver*>(h); int steps = 0;
+  const double hstep = time_step / substeps;
+  for (int i = 0; i < substeps; ++i) steps += s->rolloutPolicy(t + i * hstep, x, hstep);
+  return steps; ORC_CATCH(-1)
+}
 
 // ---- model maths
 void orc_flow_map(void* h, const double* x, const double* u, double* f, double* pos, double* vel) {

@@ -790,6 +790,77 @@ struct Solver {
     }
     *mode = sol.modeSchedule.modeAtTime(t);
   }
+
+  // ---- feedback-policy rollout between MPC ticks
+  // [UPSTREAM MRT_BASE::rolloutPolicy -> TimeTriggeredRollout::run] (installed by mpcMrtInterface_->initRollout(&interface.getRollout()),
+  // bipedal_controllers/src/BipedalController.cpp:322; settings task.info:159-167: ODE45, AbsTolODE 1e-5, RelTolODE 1e-3, timeStep 0.015).
+  // The closed-loop system xdot = f(x, uff(t) + K(t) x) is integrated from t to t + timeStep.  Restated from OCS2 / boost::odeint:
+  //  * RolloutBase::findActiveModesTimeInterval splits [t, t + timeStep] at the event times of the policy's mode schedule and starts every
+  //    sub-interval weakEpsilon late (the state is carried over unchanged; the jump map is the identity);
+  //  * each sub-interval runs odeint::integrate_adaptive(make_controlled<runge_kutta_dopri5>(AbsTol, RelTol), sys, x, begin, end, dtInitial = timeStep):
+  //    Dormand-Prince 5(4) with the default error checker  err = max_i |xerr_i| / (abs + rel (|x_i| + dt |dxdt_i|))  and the default step
+  //    adjuster  (reject: dt *= max(0.9 err^(-1/3), 0.2); accept with err < 0.5: dt *= 0.9 max(err, 5^-5)^(-1/5)), a fresh stepper per interval.
+  struct RolloutSettings { double absTol = 1e-5, relTol = 1e-3, timeStep = 0.015; int maxTrials = 500; };
+  RolloutSettings rollout;
+  void closedLoopFlow(double t, const double* x, double* f) const {
+    double xo[MAXX], u[MAXU]; int mode;
+    evaluatePolicy(t, x, xo, u, &mode);
+    flow_map<double>(M, x, u, f);
+  }
+  int integrateAdaptiveDopri5(double* x, double t0, double t1, double dtInit) const {
+    static const double a21 = 1.0 / 5, a31 = 3.0 / 40, a32 = 9.0 / 40, a41 = 44.0 / 45, a42 = -56.0 / 15, a43 = 32.0 / 9, a51 = 19372.0 / 6561, a52 = -25360.0 / 2187,
+                        a53 = 64448.0 / 6561, a54 = -212.0 / 729, a61 = 9017.0 / 3168, a62 = -355.0 / 33, a63 = 46732.0 / 5247, a64 = 49.0 / 176, a65 = -5103.0 / 18656,
+                        c1 = 35.0 / 384, c3 = 500.0 / 1113, c4 = 125.0 / 192, c5 = -2187.0 / 6784, c6 = 11.0 / 84;
+    static const double dc1 = c1 - 5179.0 / 57600, dc3 = c3 - 7571.0 / 16695, dc4 = c4 - 393.0 / 640, dc5 = c5 + 92097.0 / 339200, dc6 = c6 - 187.0 / 2100, dc7 = -1.0 / 40;
+    const int nx = M.nx;
+    double k1[MAXX], k2[MAXX], k3[MAXX], k4[MAXX], k5[MAXX], k6[MAXX], k7[MAXX], xt[MAXX], xn[MAXX];
+    double t = t0, dt = dtInit; int steps = 0;
+    closedLoopFlow(t, x, k1);   // first call of the FSAL stepper
+    while (t < t1 && (t1 - t) > 1e-15 * std::max(1.0, std::fabs(t1))) {
+      if (t + dt > t1) dt = t1 - t;
+      int trials = 0; bool ok = false;
+      while (!ok && trials < rollout.maxTrials) {
+        ++trials;
+        for (int i = 0; i < nx; ++i) xt[i] = x[i] + dt * a21 * k1[i];
+        closedLoopFlow(t + dt * (1.0 / 5), xt, k2);
+        for (int i = 0; i < nx; ++i) xt[i] = x[i] + dt * (a31 * k1[i] + a32 * k2[i]);
+        closedLoopFlow(t + dt * (3.0 / 10), xt, k3);
+        for (int i = 0; i < nx; ++i) xt[i] = x[i] + dt * (a41 * k1[i] + a42 * k2[i] + a43 * k3[i]);
+        closedLoopFlow(t + dt * (4.0 / 5), xt, k4);
+        for (int i = 0; i < nx; ++i) xt[i] = x[i] + dt * (a51 * k1[i] + a52 * k2[i] + a53 * k3[i] + a54 * k4[i]);
+        closedLoopFlow(t + dt * (8.0 / 9), xt, k5);
+        for (int i = 0; i < nx; ++i) xt[i] = x[i] + dt * (a61 * k1[i] + a62 * k2[i] + a63 * k3[i] + a64 * k4[i] + a65 * k5[i]);
+        closedLoopFlow(t + dt, xt, k6);
+        for (int i = 0; i < nx; ++i) xn[i] = x[i] + dt * (c1 * k1[i] + c3 * k3[i] + c4 * k4[i] + c5 * k5[i] + c6 * k6[i]);
+        closedLoopFlow(t + dt, xn, k7);
+        double err = 0.0;
+        for (int i = 0; i < nx; ++i) {
+          const double xe = dt * (dc1 * k1[i] + dc3 * k3[i] + dc4 * k4[i] + dc5 * k5[i] + dc6 * k6[i] + dc7 * k7[i]);
+          err = std::max(err, std::fabs(xe) / (rollout.absTol + rollout.relTol * (std::fabs(x[i]) + std::fabs(dt) * std::fabs(k1[i]))));
+        }
+        if (err > 1.0) { dt *= std::max(0.9 * std::pow(err, -1.0 / 3.0), 0.2); continue; }
+        ok = true; t += dt; ++steps;
+        for (int i = 0; i < nx; ++i) { x[i] = xn[i]; k1[i] = k7[i]; }
+        if (err < 0.5) { err = std::max(std::pow(5.0, -5.0), err); dt *= 0.9 * std::pow(err, -1.0 / 5.0); }
+      }
+      if (!ok) throw std::runtime_error("[oracle] rollout: step size underflow");
+    }
+    return steps;
+  }
+  // x <- state after the closed-loop rollout from t to t + timeStep; returns the number of accepted integration steps
+  int rolloutPolicy(double t, double* x, double timeStep) const {
+    const double tf = t + timeStep;
+    const auto& ev = sol.modeSchedule.eventTimes;
+    std::vector<double> sw; sw.push_back(t);
+    for (auto it = std::upper_bound(ev.begin(), ev.end(), t); it != ev.end() && *it < tf; ++it) sw.push_back(*it);   // events inside (t, tf)
+    sw.push_back(tf);
+    int steps = 0;
+    for (size_t i = 0; i + 1 < sw.size(); ++i) {
+      const double begin = std::min(sw[i] + WEAK_EPS, sw[i + 1]), end = sw[i + 1];
+      if (end > begin) steps += integrateAdaptiveDopri5(x, begin, end, rollout.timeStep);
+    }
+    return steps;
+  }
 };
 
 }  // namespace orc

@@ -219,6 +219,14 @@ class Oracle:
         return xo, uo, mode.value
 
     # ---- model maths
+    def rollout_policy(self, t, x, time_step, substeps=1):
+        """MRT_BASE::rolloutPolicy [UPSTREAM]: state after integrating the closed loop (u = uff(t) + K(t) x) from t to t + time_step."""
+        x = _d(x).copy()
+        steps = self.L.orc_rollout_policy(self.h, C.c_double(t), _p(x), C.c_double(time_step), C.c_int(substeps))
+        if steps < 0:
+            raise RuntimeError(self.L.orc_last_error().decode())
+        return x, steps
+
     def flow_map(self, x, u):
         x, u = _d(x), _d(u)
         f, pos, vel = np.zeros(self.nx), np.zeros((4, 3)), np.zeros((4, 3))

@@ -1,20 +1,36 @@
-// Test-only shim: exposes the product's host-side GaitSchedule (bipedal_control_b200/csrc/bmpc_gait.h) to ctypes so that the
-// CPU test-suite can compare it with the oracle's restatement without a GPU.  Built on demand by tests/test_host_logic.py.
+// Test-only shim: exposes the product's gait bookkeeping (bipedal_control_b200/csrc/bmpc_gait.h: the same functions the device kernels
+// k_gait_insert / k_gait_schedule call, compiled here for the host) to ctypes so that the CPU test-suite can compare it with the oracle's
+// restatement of GaitSchedule.cpp without a GPU.  Built on demand by tests/test_host_logic.py.
+#include <vector>
 #include "../bipedal_control_b200/csrc/bmpc_gait.h"
 using namespace bmpc;
+namespace {
+struct Shim { int cap, n; std::vector<double> ev; std::vector<int> modes; GaitTemplateArrays tmpl; double pts;
+  GaitView view() { return GaitView{cap, &n, ev.data(), modes.data(), &tmpl}; } };
+GaitTemplateArrays make_template(int n, const int* modes, const double* times) {
+  GaitTemplateArrays t{}; t.n = n; for (int i = 0; i < n; ++i) t.modes[i] = modes[i]; for (int i = 0; i <= n; ++i) t.times[i] = times[i]; return t;
+}
+}  // namespace
 extern "C" {
 void* shim_gait_create(int n_modes, const int* modes, int n_events, const double* events, int nt, const int* tmodes, const double* ttimes, double pts) {
-  auto* g = new GaitSchedule();
-  g->ms.modeSequence.assign(modes, modes + n_modes); g->ms.eventTimes.assign(events, events + n_events);
-  g->tmpl.modes.assign(tmodes, tmodes + nt); g->tmpl.times.assign(ttimes, ttimes + nt + 1); g->phaseTransitionStanceTime = pts;
+  auto* g = new Shim(); g->cap = 64; g->ev.assign(g->cap, 0.0); g->modes.assign(g->cap + 1, 0);
+  g->n = n_events; for (int i = 0; i < n_events; ++i) g->ev[i] = events[i]; for (int i = 0; i < n_modes; ++i) g->modes[i] = modes[i];
+  g->tmpl = make_template(nt, tmodes, ttimes); g->pts = pts;
   return g;
 }
-void shim_gait_destroy(void* h) { delete static_cast<GaitSchedule*>(h); }
+void shim_gait_destroy(void* h) { delete static_cast<Shim*>(h); }
 int shim_gait_insert(void* h, int n, const int* modes, const double* times, double start, double fin) {
-  try { GaitTemplate t; t.modes.assign(modes, modes + n); t.times.assign(times, times + n + 1); static_cast<GaitSchedule*>(h)->insertModeSequenceTemplate(t, start, fin); return 0; } catch (...) { return -1; }
+  auto* g = static_cast<Shim*>(h);
+  if (n > GAIT_TMAX) return -3;
+  return -gait_insert(g->view(), make_template(n, modes, times), start, fin, g->pts);
 }
 int shim_gait_get(void* h, double lo, double hi, int cap, double* et, int* ms) {
-  try { const ModeSchedule& s = static_cast<GaitSchedule*>(h)->getModeSchedule(lo, hi); const int n = (int)s.eventTimes.size(); if (n > cap) return -2;
-    for (int i = 0; i < n; ++i) et[i] = s.eventTimes[i]; for (int i = 0; i <= n; ++i) ms[i] = s.modeSequence[i]; return n; } catch (...) { return -1; }
+  auto* g = static_cast<Shim*>(h);
+  const int rc = gait_get_mode_schedule(g->view(), lo, hi);
+  if (rc != GAIT_OK) return -rc;
+  if (g->n > cap) return -9;
+  for (int i = 0; i < g->n; ++i) et[i] = g->ev[i];
+  for (int i = 0; i <= g->n; ++i) ms[i] = g->modes[i];
+  return g->n;
 }
 }

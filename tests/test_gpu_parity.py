@@ -571,3 +571,50 @@ def test_time_grid_capacity_is_reported():
     g.advanceMpc()
     assert not g.getStatus().any() and g.getPolicy(0, 1, with_gains=False)["n_nodes"][0] == nodes_expected
     g.close()
+
+
+def test_feedback_policy_rollout_matches_oracle(oracle_h1):
+    """SURVEY 8(f)-1: the device-side closed-loop rollout between MPC ticks (MRT_BASE::rolloutPolicy, Dormand-Prince 5(4) with odeint's step control,
+    sub-intervals split at mode switches) against the oracle's restatement: from a perturbed observation, over 8 MRT periods, and across an event."""
+    import helpers
+    G = _gpu()
+    m = _mdl()
+    o = oracle_h1
+    x0 = o.initial_state()
+    et, ms = helpers.config2(o.nx, x0, None, None)
+    tt, ts = helpers.cmd_vel_target(x0, 0.0, (0.3, 0, 0, 0.1), 1.0, m["com_height"], m["default_joint_state"])
+    o.reset(); o.set_dt_horizon(0.01, 1.0); o.set_mode_schedule(et, ms); o.set_target(tt, ts)
+    B = 5
+    g = G(B, model_file=MODEL, dt=0.01, time_horizon=1.0)
+    g.setCurrentObservation(0.0, x0); g.setTargetTrajectories(tt, ts); g.setModeSchedule(et, ms)
+    for _ in range(2):
+        o.run(0.0, x0); g.advanceMpc()
+    # (1) perturbed observations at t = 0, 8 MRT periods of 2.5 ms
+    X = np.tile(x0, (B, 1)) + 0.01 * np.cos(np.arange(B * len(x0))).reshape(B, -1)
+    g.setCurrentObservation(np.zeros(B), X)
+    g.rolloutObservations(0.02, 8)
+    t2, X2 = g.getObservations()
+    np.testing.assert_allclose(t2, 0.02)
+    for b in range(B):
+        xr, steps = o.rollout_policy(0.0, X[b], 0.02, 8)
+        assert steps >= 8
+        _close(X2[b], xr, 1e-7, "rollout state")
+    assert np.abs(X2 - X).max() > 1e-3 and not (g.getStatus() & 8).any()
+    # (2) one period across the mode switch at t = 0.10 (two sub-intervals, the second one started weakEpsilon late)
+    xs, _, _ = g.evaluatePolicy(np.full(B, 0.09), X)
+    g.setCurrentObservation(np.full(B, 0.09), xs)
+    g.rolloutObservations(0.02, 1)
+    t3, X3 = g.getObservations()
+    np.testing.assert_allclose(t3, 0.11)
+    for b in (0, B - 1):
+        xr, steps = o.rollout_policy(0.09, xs[b], 0.02, 1)
+        assert steps >= 2
+        _close(X3[b], xr, 1e-7, "rollout state across an event")
+    # (3) the rollout differs from the perfect-model shift by the discretisation error of the plan, not by more
+    g.setCurrentObservation(np.zeros(B), np.tile(x0, (B, 1)))
+    g.rolloutObservations(0.02, 8)
+    _, Xr = g.getObservations()
+    xe, _, _ = g.evaluatePolicy(np.full(B, 0.02), np.tile(x0, (B, 1)))
+    assert 1e-6 < np.abs(Xr - xe).max() < 2e-2
+    g.close()
+    o.reset()
