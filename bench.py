@@ -336,6 +336,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--probe", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--gather", default="full", choices=["full", "window", "none"])
+    ap.add_argument("--gather-impl", default="native", choices=["native", "torch"], help="policy all-gather: libbmpc's own NCCL exchange (bmpc_exchange_*) or torch.distributed")
+    ap.add_argument("--gather-ctas", type=int, default=16, help="cap on the SMs NCCL may use for the policy all-gather (0: NCCL default)")
+    ap.add_argument("--gather-ce", type=int, default=0, help="1: ask NCCL for the copy-engine all-gather (NCCL >= 2.28, no SM at all)")
     ap.add_argument("--opt", action="append", default=[], help="debug option name=value passed to bmpc_debug_set_option (not for reported numbers)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -370,12 +373,16 @@ def main():
         mpc.setOption(name, int(val))
 
     # ---- multi-GPU: one all-gather of the solved policies per tick (north star), behind the library's exchange API
-    exchange = None
-    if world > 1 and args.gather != "none":
+    def attach_exchange(r, window):
         from bipedal_control_b200.sharding import PolicyExchange
-        exchange = PolicyExchange(mpc, dist, rank, world, window=(args.gather == "window"))
-        run.after_tick = exchange.after_tick
-        run.before_tick = exchange.before_tick
+        r.exchange = PolicyExchange(r.mpc, dist, rank, world, window=window, impl=args.gather_impl, max_ctas=args.gather_ctas, copy_engines=bool(args.gather_ce))
+        r.after_tick = r.exchange.after_tick
+        r.before_tick = r.exchange.before_tick
+
+    run.exchange = None
+    if world > 1 and args.gather != "none":
+        attach_exchange(run, args.gather == "window")
+    exchange = run.exchange
 
     def barrier():
         if world > 1:
@@ -393,8 +400,8 @@ def main():
             if collect_phases:
                 r.mpc.synchronize()
                 phases.append(r.mpc.phaseTimes())
-        if exchange is not None and r is run:
-            exchange.join(r.stream)   # the timed region ends when the last policy all-gather has finished, not only the last tick
+        if getattr(r, "exchange", None) is not None:
+            r.exchange.join(r.stream)   # the timed region ends when the last policy all-gather has finished, not only the last tick
         e1.record(r.stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -487,6 +494,32 @@ def main():
     }
     if exchange is not None:
         line["policy_exchange"] = exchange.describe()
+        # extra keys at N > 1: the consumed-window exchange (only the nodes consumers read before the next tick) and the
+        # randomised distribution of BASELINE configs[4] (seed = rank), both with the same closed loop; shorter runs, every rank takes part
+        extra = {}
+        try:
+            if args.gather == "full":
+                attach_exchange(run, True)
+                for _ in range(2):
+                    run.device_step()
+                msw, _, _ = timed(run, run.device_step, 8)
+                extra["consumed_window"] = {"value": world * B * 8 / (msw * 1e-3), "unit": UNIT, "ms_per_step": msw / 8, "steps": 8, "policy_exchange": run.exchange.describe()}
+            run.mpc.close()
+            r2 = Runner(torch, args.robot, "randomized", B, rank, local_rank)
+            r2.exchange = None
+            attach_exchange(r2, False)
+            r2.cold_start()
+            for _ in range(3):
+                r2.device_step()
+            ms2, _, _ = timed(r2, r2.device_step, 8)
+            nz = torch.tensor([int(np.count_nonzero(r2.mpc.getStatus() & ~16))], device=dev)
+            dist.all_reduce(nz)
+            extra["configs[4] randomized"] = {"value": world * B * 8 / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / 8, "steps": 8, "status_nonzero": int(nz.item()),
+                                              "workload": bench_config(args.robot, "randomized", B, world, args.gather)["workload"], "policy_exchange": r2.exchange.describe()}
+            r2.mpc.close()
+        except Exception as e:   # noqa: BLE001
+            extra["error"] = str(e)[:200]
+        line["other_configs"] = extra
     if rank == 0 and world == 1 and not args.no_extra:
         # the other single-GPU configs of BASELINE.json, shorter runs (extra keys; the headline stays configs[1])
         extra = {}

@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "../../include/bmpc.h"
+#include "bmpc_exchange.h"
 #include "bmpc_gait.h"
 #include "bmpc_kernels.cuh"
 
@@ -104,6 +105,14 @@ struct bmpc_handle {
   // stats
   int launches = 0; bool timing = false; cudaEvent_t tev[10] = {}; float phase_ms[9] = {};
   int linesearch_trials = 0, max_trials = 0, failed_instances = 0, status_or = 0;
+  // multi-GPU policy exchange (bmpc_exchange_*)
+  struct Exchange {
+    NcclApi::Comm comm = nullptr; int rank = 0, nranks = 1; bool copy_engines = false; int max_ctas = 0;
+    cudaStream_t stream = nullptr; cudaEvent_t ready = nullptr, done[2] = {nullptr, nullptr}; bool started[2] = {false, false};
+    void* recv[2] = {nullptr, nullptr}; void* send = nullptr; bool nccl_mem = false;
+    NcclApi::Window win_recv[2] = {nullptr, nullptr}, win_send = nullptr;
+    int last = -1; long count = 0;
+  } ex;
   // scratch for policy evaluation / rollout
   double *d_default_joints = nullptr, *d_jc = nullptr;
   double *d_eval_t = nullptr, *d_eval_x = nullptr, *d_eval_xo = nullptr, *d_eval_uo = nullptr; int* d_eval_m = nullptr;
@@ -172,6 +181,7 @@ void tick(bmpc_handle* h) {
   auto mark = [&](int i) { if (h->timing) CK(cudaEventRecord(h->tev[i], st)); };
   h->launches = 0;
   ensure_model_image(h);
+  if (h->ex.comm && h->ex.started[w]) CK(cudaStreamWaitEvent(st, h->ex.done[w], 0));   // the all-gather that reads the slab this tick overwrites
   upload_inputs(h);
   CK(cudaMemsetAsync(h->s_status[w], 0, sizeof(int) * B, st));
   CK(cudaMemsetAsync(h->d_counters, 0, sizeof(int) * CNT_N, st));
@@ -282,11 +292,28 @@ int fail(bmpc_handle* h, int code, const std::string& msg) {
   catch (const std::length_error& e) { return fail(h, BMPC_ERR_CAPACITY, e.what()); } \
   catch (const std::exception& e) { return fail(h, BMPC_ERR_INVALID, e.what()); }
 
+void exchange_release(bmpc_handle* h) {
+  auto& ex = h->ex; NcclApi& N = nccl_api();
+  if (ex.stream) cudaStreamSynchronize(ex.stream);
+  if (ex.comm) {
+    for (int i = 0; i < 2; ++i) if (ex.win_recv[i] && N.CommWindowDeregister) N.CommWindowDeregister(ex.comm, ex.win_recv[i]);
+    if (ex.win_send && N.CommWindowDeregister) N.CommWindowDeregister(ex.comm, ex.win_send);
+  }
+  for (int i = 0; i < 2; ++i) if (ex.recv[i]) { if (ex.nccl_mem) N.MemFree(ex.recv[i]); else cudaFree(ex.recv[i]); ex.recv[i] = nullptr; }
+  if (ex.send) { if (ex.nccl_mem) N.MemFree(ex.send); else cudaFree(ex.send); ex.send = nullptr; }
+  if (ex.comm) { N.CommDestroy(ex.comm); ex.comm = nullptr; }
+  if (ex.ready) cudaEventDestroy(ex.ready);
+  for (auto& e : ex.done) if (e) cudaEventDestroy(e);
+  if (ex.stream) cudaStreamDestroy(ex.stream);
+  ex = bmpc_handle::Exchange();
+}
+
 void destroy_impl(bmpc_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->io_stream) cudaStreamSynchronize(h->io_stream);
+  exchange_release(h);
   h->pool.release();
   for (auto& e : h->tev) if (e) cudaEventDestroy(e);
   if (h->ev_done) cudaEventDestroy(h->ev_done);
@@ -706,6 +733,94 @@ int bmpc_get_observations(bmpc_handle* h, double* t, double* x) {
   if (x) CK(cudaMemcpyAsync(x, h->d_x0, sizeof(double) * h->B * h->nx, cudaMemcpyDeviceToHost, h->stream));
   lk.unlock();
   CK(cudaStreamSynchronize(h->stream));
+  return BMPC_OK; API_END(h)
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU policy exchange
+int bmpc_exchange_create_id(bmpc_exchange_id* id) {
+  try {
+    if (!id) throw std::invalid_argument("[bmpc] null argument");
+    NcclApi& N = nccl_api(); N.load();
+    static_assert(sizeof(bmpc_exchange_id) == sizeof(NcclApi::UniqueId), "id size");
+    N.check(N.GetUniqueId(reinterpret_cast<NcclApi::UniqueId*>(id)), "ncclGetUniqueId");
+    return BMPC_OK;
+  } catch (const std::exception& e) { return fail(nullptr, BMPC_ERR_INVALID, e.what()); }
+}
+int bmpc_exchange_init(bmpc_handle* h, int rank, int nranks, const bmpc_exchange_id* id, int max_ctas, int use_copy_engines) {
+  API_BEGIN if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) throw std::invalid_argument("[bmpc] bad exchange arguments");
+  CK(cudaSetDevice(h->device));
+  std::unique_lock<std::mutex> lk(h->mtx);
+  wait_and_publish(h, lk);
+  exchange_release(h);
+  NcclApi& N = nccl_api(); N.load();
+  auto& ex = h->ex;
+  ex.rank = rank; ex.nranks = nranks; ex.max_ctas = max_ctas;
+  NcclApi::UniqueId uid; std::memcpy(&uid, id, sizeof(uid));
+  const bool can_config = N.CommInitRankConfig && N.version >= 22800;
+  // copy-engine collectives (NCCL >= 2.28: CTA policy "zero" + symmetric windows): the all-gather then uses no SM at all
+  ex.copy_engines = use_copy_engines && can_config && N.MemAlloc && N.CommWindowRegister;
+  if (can_config) {
+    NcclApi::ConfigV22800 cfg = N.default_config();
+    if (max_ctas > 0) { cfg.maxCTAs = max_ctas; cfg.minCTAs = 1; }
+    if (ex.copy_engines) cfg.CTAPolicy = NcclApi::kCtaPolicyZero;
+    N.check(N.CommInitRankConfig(&ex.comm, nranks, uid, rank, &cfg), "ncclCommInitRankConfig");
+  } else N.check(N.CommInitRank(&ex.comm, nranks, uid, rank), "ncclCommInitRank");
+  CK(cudaStreamCreateWithFlags(&ex.stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ex.ready, cudaEventDisableTiming));
+  for (auto& e : ex.done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  const size_t bytes = h->slab_doubles * sizeof(double);
+  ex.nccl_mem = ex.copy_engines;
+  for (int i = 0; i < 2; ++i) {
+    if (ex.nccl_mem) N.check(N.MemAlloc(&ex.recv[i], bytes * nranks), "ncclMemAlloc"); else CK(cudaMalloc(&ex.recv[i], bytes * nranks));
+  }
+  if (ex.copy_engines) {
+    N.check(N.MemAlloc(&ex.send, bytes), "ncclMemAlloc");
+    N.check(N.CommWindowRegister(ex.comm, ex.send, bytes, &ex.win_send, NcclApi::kWinCollSymmetric), "ncclCommWindowRegister");
+    for (int i = 0; i < 2; ++i) N.check(N.CommWindowRegister(ex.comm, ex.recv[i], bytes * nranks, &ex.win_recv[i], NcclApi::kWinCollSymmetric), "ncclCommWindowRegister");
+  }
+  return BMPC_OK; API_END(h)
+}
+// all-gather of the newest policy slab (the one the tick in flight writes), ordered after that tick, on the exchange stream
+int bmpc_exchange_start(bmpc_handle* h) {
+  API_BEGIN if (!h) return BMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  std::lock_guard<std::mutex> lk(h->mtx);
+  auto& ex = h->ex;
+  if (!ex.comm) throw std::invalid_argument("[bmpc] bmpc_exchange_init has not been called");
+  if (!h->have_solution && !h->pending) throw std::invalid_argument("[bmpc] no solution yet");
+  NcclApi& N = nccl_api();
+  const int c = h->pending ? 1 - h->cur : h->cur;
+  CK(cudaEventRecord(ex.ready, h->stream));
+  CK(cudaStreamWaitEvent(ex.stream, ex.ready, 0));
+  const void* src = h->slab[c];
+  if (ex.copy_engines) { CK(cudaMemcpyAsync(ex.send, h->slab[c], h->slab_doubles * sizeof(double), cudaMemcpyDeviceToDevice, ex.stream)); src = ex.send; }
+  N.check(N.AllGather(src, ex.recv[c], h->slab_doubles, NcclApi::kFloat64, ex.comm, ex.stream), "ncclAllGather");
+  CK(cudaEventRecord(ex.done[c], ex.stream));
+  ex.started[c] = true; ex.last = c; ++ex.count;
+  return BMPC_OK; API_END(h)
+}
+int bmpc_exchange_wait(bmpc_handle* h) {
+  API_BEGIN if (!h) return BMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  if (h->ex.stream) CK(cudaStreamSynchronize(h->ex.stream));
+  return BMPC_OK; API_END(h)
+}
+// device pointer of the gathered slabs of the last started exchange: nranks consecutive slabs of slab_bytes (rank r at offset r * slab_bytes);
+// valid after bmpc_exchange_wait (or for work ordered after it) until the exchange after the next one starts
+int bmpc_exchange_view(bmpc_handle* h, const void** gathered, unsigned long long* slab_bytes, int* nranks) {
+  if (!h || !h->ex.comm || h->ex.last < 0) return BMPC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(h->mtx);
+  if (gathered) *gathered = h->ex.recv[h->ex.last];
+  if (slab_bytes) *slab_bytes = h->slab_doubles * sizeof(double);
+  if (nranks) *nranks = h->ex.nranks;
+  return h->ex.copy_engines ? 1 : 0;
+}
+int bmpc_exchange_destroy(bmpc_handle* h) {
+  API_BEGIN if (!h) return BMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  std::unique_lock<std::mutex> lk(h->mtx);
+  wait_and_publish(h, lk);
+  exchange_release(h);
   return BMPC_OK; API_END(h)
 }
 

@@ -73,6 +73,7 @@ def load_library(path: str | None = None):
                  "bmpc_advance", "bmpc_advance_async", "bmpc_synchronize", "bmpc_get_policy", "bmpc_get_device_view", "bmpc_get_performance",
                  "bmpc_get_status", "bmpc_evaluate_policy", "bmpc_get_launch_count", "bmpc_get_phase_times", "bmpc_enable_phase_timing",
                  "bmpc_poll", "bmpc_get_device_view_inflight", "bmpc_get_tick_stats", "bmpc_rollout_observations", "bmpc_set_rollout_settings",
+                 "bmpc_exchange_create_id", "bmpc_exchange_init", "bmpc_exchange_start", "bmpc_exchange_wait", "bmpc_exchange_view", "bmpc_exchange_destroy",
                  "bmpc_debug_copy", "bmpc_debug_record_sizes", "bmpc_debug_set_option"):
         getattr(L, name).restype = C.c_int
     if path is None:
@@ -276,6 +277,37 @@ class BatchedMpcMrtInterface:
         xo, uo, mo = np.zeros((self.batch, self.nx)), np.zeros((self.batch, self.nu)), np.zeros(self.batch, dtype=np.int32)
         self._ck(self.L.bmpc_evaluate_policy(self.h, _p(t), _p(x), _p(xo), _p(uo), _pi(mo)))
         return xo, uo, mo
+
+    # ------------------------------------------------------------------ multi-GPU policy exchange (one process per GPU)
+    def exchangeInit(self, dist, rank: int, world: int, max_ctas: int = 0, copy_engines: bool = False):
+        """bmpc_exchange_init: rank 0 creates the NCCL id, `dist` (torch.distributed, any backend) carries its 128 bytes to the other ranks."""
+        import torch
+        buf = (C.c_char * 128)()
+        if rank == 0:
+            rc = self.L.bmpc_exchange_create_id(buf)
+            if rc != 0:
+                raise BmpcError(rc, self.L.bmpc_last_error(None).decode())
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0)
+        raw = bytes(t.cpu().tolist())
+        idb = (C.c_char * 128).from_buffer_copy(raw)
+        self._ck(self.L.bmpc_exchange_init(self.h, C.c_int(rank), C.c_int(world), idb, C.c_int(int(max_ctas)), C.c_int(1 if copy_engines else 0)))
+
+    def exchangeStart(self):
+        self._ck(self.L.bmpc_exchange_start(self.h))
+
+    def exchangeWait(self):
+        self._ck(self.L.bmpc_exchange_wait(self.h))
+
+    def exchangeView(self):
+        """(device pointer of the gathered slabs, bytes per slab, number of ranks, copy-engine mode active)."""
+        p, n, r = C.c_void_p(), C.c_ulonglong(), C.c_int()
+        mode = self._ck(self.L.bmpc_exchange_view(self.h, C.byref(p), C.byref(n), C.byref(r)))
+        return int(p.value or 0), int(n.value), int(r.value), bool(mode)
+
+    def exchangeDestroy(self):
+        self._ck(self.L.bmpc_exchange_destroy(self.h))
 
     # ------------------------------------------------------------------ instrumentation
     def launchCount(self):

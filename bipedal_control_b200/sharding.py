@@ -44,10 +44,32 @@ class PolicyExchange:
     on `compute_stream`); tests on CPU pass plain tensors and the gloo backend through the same code.
     """
 
-    def __init__(self, mpc, dist, rank, world, window=False, window_nodes=4, slab_provider=None, compute_stream=None):
+    def __init__(self, mpc, dist, rank, world, window=False, window_nodes=4, slab_provider=None, compute_stream=None, impl="native", max_ctas=0, copy_engines=False):
+        """impl "native": the library's own exchange (bmpc_exchange_*: ncclAllGather issued by libbmpc on its exchange stream, optional SM cap /
+        copy-engine mode); "torch": torch.distributed all_gather_into_tensor on a side stream (own NCCL group when max_ctas > 0).  The consumed-window
+        variant and the CPU tests always use the torch path; a native initialisation failure falls back to it and is reported by describe()."""
         import torch
         self.torch, self.dist, self.mpc, self.rank, self.world = torch, dist, mpc, rank, world
         self.window, self.window_nodes = window, window_nodes
+        self.impl, self.max_ctas, self.copy_engines, self.note, self.group = impl, max_ctas, copy_engines, "", None
+        if slab_provider is not None or window:
+            self.impl = "torch"
+        if self.impl == "native":
+            try:
+                mpc.exchangeInit(dist, rank, world, max_ctas=max_ctas, copy_engines=copy_engines)
+            except Exception as e:   # noqa: BLE001
+                self.impl, self.note = "torch", "native exchange unavailable: " + str(e).splitlines()[0][:120]
+            ok = torch.tensor([1 if self.impl == "native" else 0], device=torch.device("cuda", torch.cuda.current_device()))
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks or none
+            if int(ok.item()) == 0 and self.impl == "native":
+                mpc.exchangeDestroy(); self.impl, self.note = "torch", "native exchange unavailable on another rank"
+        if self.impl == "torch" and slab_provider is None and max_ctas > 0:
+            try:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = int(max_ctas); opts.config.min_ctas = 1
+                self.group = dist.new_group(ranks=list(range(world)), backend="nccl", pg_options=opts)
+            except Exception as e:   # noqa: BLE001
+                self.note += " (no CTA cap: %s)" % str(e).splitlines()[0][:80]
         self.slab_provider = slab_provider or self._library_slab
         self.cuda = slab_provider is None
         self.out = [None, None]
@@ -89,13 +111,18 @@ class PolicyExchange:
         i = self.ticks & 1
         if self.out[i] is None or self.out[i].numel() != self.world * src.numel():
             self.out[i] = self.torch.empty(self.world * src.numel(), dtype=src.dtype, device=src.device)
-        self.dist.all_gather_into_tensor(self.out[i], src)
+        self.dist.all_gather_into_tensor(self.out[i], src, group=self.group)
         self.bytes_per_tick = src.numel() * 8 * self.world
         return self.out[i]
 
     def after_tick(self):
         """Call right after bmpc_advance_async: enqueues the all-gather of the policy that tick produces."""
         torch = self.torch
+        if self.impl == "native":
+            self.mpc.exchangeStart()
+            self.ticks += 1
+            self.bytes_per_tick = self.mpc.getDeviceView(inflight=True).slab_bytes * self.world
+            return None
         if not self.cuda:
             res = self._gather(self.slab_provider())
             self.ticks += 1
@@ -115,11 +142,15 @@ class PolicyExchange:
 
     def before_tick(self):
         """Call before bmpc_advance_async: the tick about to start overwrites the slab that was gathered two ticks ago."""
+        if self.impl == "native":
+            return   # the library orders the tick after the gather that still reads its slab
         if self.cuda and len(self.events) >= 2:
             self.compute_stream.wait_event(self.events[-2])
 
     def join(self, stream=None):
-        if self.cuda:
+        if self.impl == "native":
+            self.mpc.exchangeWait()
+        elif self.cuda:
             (stream or self.compute_stream).wait_stream(self.side)
 
     def shard(self, gathered, r):
@@ -129,4 +160,6 @@ class PolicyExchange:
 
     def describe(self):
         return {"collectives_per_tick": 1, "bytes_received_per_rank_per_tick": int(self.bytes_per_tick), "what": "first %d nodes of every instance" % self.window_nodes if self.window else "whole policy slab [K | uff | x | u | times | events | n_nodes], node slots sized to the workload",
-                "backend": "torch.distributed all_gather_into_tensor (NCCL)" if self.cuda else "gloo"}
+                "backend": ("libbmpc bmpc_exchange_* (ncclAllGather%s)" % (", copy engines" if self.mpc.exchangeView()[3] else "") if self.impl == "native"
+                            else ("torch.distributed all_gather_into_tensor (NCCL)" if self.cuda else "gloo")),
+                "max_ctas": self.max_ctas, "note": self.note}

@@ -166,6 +166,25 @@ typedef struct bmpc_device_view {
 int bmpc_get_device_view(bmpc_handle* h, bmpc_device_view* v);
 int bmpc_get_device_view_inflight(bmpc_handle* h, bmpc_device_view* v);
 
+/* Multi-GPU: one process per GPU, each with its own handle over a contiguous shard of the batch (instances are independent: the data path needs
+ * no collective).  The only exchange is the all-gather of the solved policies once per tick (every rank then holds every robot's policy):
+ *   rank 0: bmpc_exchange_create_id(&id); broadcast the 128 bytes to the other ranks (MPI, torch.distributed, a file ...);
+ *   every rank: bmpc_exchange_init(h, rank, nranks, &id, max_ctas, use_copy_engines);
+ *   every tick: bmpc_advance_async(h); bmpc_exchange_start(h);   -> ONE ncclAllGather of the policy slab on its own stream, overlapped with the
+ *               next tick (the slab is double buffered; the tick that overwrites it waits for the gather by itself);
+ *   consumers: bmpc_exchange_wait(h); bmpc_exchange_view(h, &ptr, &slab_bytes, &nranks)  (rank r's slab at ptr + r * slab_bytes, laid out as
+ *              bmpc_device_view describes).
+ * max_ctas > 0 caps the SMs NCCL may use (the solver keeps the rest); use_copy_engines = 1 asks for NCCL's copy-engine all-gather (NCCL >= 2.28,
+ * symmetric windows, CTA policy "zero": no SM at all); bmpc_exchange_view returns 1 if that mode is active, 0 otherwise.  NCCL is loaded at run
+ * time (libnccl.so.2) only when these functions are used. */
+typedef struct bmpc_exchange_id { char bytes[128]; } bmpc_exchange_id;
+int bmpc_exchange_create_id(bmpc_exchange_id* id);
+int bmpc_exchange_init(bmpc_handle* h, int rank, int nranks, const bmpc_exchange_id* id, int max_ctas, int use_copy_engines);
+int bmpc_exchange_start(bmpc_handle* h);
+int bmpc_exchange_wait(bmpc_handle* h);
+int bmpc_exchange_view(bmpc_handle* h, const void** gathered, unsigned long long* slab_bytes, int* nranks);
+int bmpc_exchange_destroy(bmpc_handle* h);
+
 /* PerformanceIndex [UPSTREAM] per instance: perf[B*8] = {cost, dynamicsViolationSSE, equalityConstraintsSSE} before the
  * step, the same three after the accepted step, step size alpha, armijo descent metric. */
 int bmpc_get_performance(bmpc_handle* h, double* perf);

@@ -205,6 +205,19 @@ def test_closed_loop_shift_and_gait_schedule(h1_model_path):
             xb, _, _ = ob.inst[b].evaluate_policy(t[b] + 0.05, X[b])
             _close(X2[b], xb, 1e-6, "shifted observation")
         t, X = t2, X2
+    # device-resident continuation: observations stay in HBM (bmpc_shift_observations), the gait schedules are tiled on the device from them
+    import torch
+    d_cmd = torch.tensor(cmds, device="cuda")
+    g.setCurrentObservation(t, X)
+    for tick in range(3):
+        g.setTargetsFromCmdVelDevice(d_cmd.data_ptr(), 1.0)
+        g.advanceMpc()
+        ob.run(threads=1, shift_dt=0.05)
+        for b in range(B):
+            _compare_tick(g, ob.inst[b], b, rel=1e-6)
+            eg, mg = g.gaitPeek(b); eo, mo = ob.inst[b].gait_peek()
+            np.testing.assert_allclose(eg, eo, atol=1e-12); assert list(mg) == list(mo)
+        g.shiftObservations(0.05)
     g.close()
 
 
@@ -618,3 +631,48 @@ def test_feedback_policy_rollout_matches_oracle(oracle_h1):
     assert 1e-6 < np.abs(Xr - xe).max() < 2e-2
     g.close()
     o.reset()
+
+
+def test_native_policy_exchange_single_rank():
+    """bmpc_exchange_* (NCCL bound at run time, one all-gather of the policy slab per tick) with a one-rank communicator: the gathered slab is the
+    policy the getters return, for two consecutive ticks (double-buffered slabs); with and without an SM cap."""
+    import torch
+    import torch.distributed as dist
+    import helpers
+    G = _gpu()
+    m = _mdl()
+    x0 = np.asarray(m["initial_state"])
+    et, ms = helpers.config2(22, x0, None, None)
+    tt, ts = helpers.cmd_vel_target(x0, 0.0, (0.3, 0, 0, 0), 1.0, m["com_height"], m["default_joint_state"])
+    own_pg = not dist.is_initialized()
+    if own_pg:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{33500 + os.getpid() % 2000}", rank=0, world_size=1)
+    try:
+        for max_ctas in (0, 8):
+            B = 6
+            g = G(B, model_file=MODEL, dt=0.01, time_horizon=0.3, max_event_nodes=3)
+            g.setCurrentObservation(0.0, x0); g.setTargetTrajectories(tt, ts); g.setModeSchedule(et, ms)
+            g.exchangeInit(dist, 0, 1, max_ctas=max_ctas)
+            for tick in range(3):
+                g.advanceMpcAsync()
+                g.exchangeStart()
+                g.exchangeWait()
+                g.synchronize()
+                ptr, nbytes, nranks, ce = g.exchangeView()
+                assert nranks == 1 and ptr and nbytes == g.getDeviceView().slab_bytes
+
+                class _Arr:
+                    pass
+                a = _Arr()
+                a.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<f8", "data": (ptr, False), "version": 3, "strides": None}
+                slab = torch.as_tensor(a, device="cuda").cpu().numpy()
+                pol = g.getPolicy()
+                nK = B * g.max_nodes * g.nu * g.nx
+                assert np.array_equal(slab[:nK].reshape(pol["K"].shape), pol["K"])
+                nU = B * g.max_nodes * g.nu
+                assert np.array_equal(slab[nK:nK + nU].reshape(pol["uff"].shape), pol["uff"])
+            g.exchangeDestroy()
+            g.close()
+    finally:
+        if own_pg:
+            dist.destroy_process_group()

@@ -33,6 +33,16 @@ def test_library_exports_every_declared_symbol(lib):
     assert not missing, f"declared in include/bmpc.h but not exported: {sorted(missing)}"
 
 
+def test_exchange_binds_nccl_at_run_time(lib):
+    """bmpc_exchange_create_id dlopens libnccl.so.2 and returns a 128-byte id: no link-time NCCL dependency, no GPU needed for this step."""
+    out = subprocess.run(["ldd", LIB], capture_output=True, text=True).stdout
+    assert "nccl" not in out
+    buf = (C.c_char * 128)()
+    rc = lib.bmpc_exchange_create_id(buf)
+    assert rc == 0, lib.bmpc_last_error(None)
+    assert any(bytes(buf))
+
+
 def test_library_is_sm100a_only():
     out = subprocess.run(["cuobjdump", "-lelf", LIB], capture_output=True, text=True).stdout
     assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
