@@ -498,6 +498,8 @@ def main():
         # randomised distribution of BASELINE configs[4] (seed = rank), both with the same closed loop; shorter runs, every rank takes part
         extra = {}
         try:
+            if args.no_extra:
+                raise StopIteration
             if args.gather == "full":
                 attach_exchange(run, True)
                 for _ in range(2):
@@ -517,6 +519,8 @@ def main():
             extra["configs[4] randomized"] = {"value": world * B * 8 / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / 8, "steps": 8, "status_nonzero": int(nz.item()),
                                               "workload": bench_config(args.robot, "randomized", B, world, args.gather)["workload"], "policy_exchange": r2.exchange.describe()}
             r2.mpc.close()
+        except StopIteration:
+            pass
         except Exception as e:   # noqa: BLE001
             extra["error"] = str(e)[:200]
         line["other_configs"] = extra
