@@ -89,14 +89,58 @@ __device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k,
   const double dt = d.st_dt[nb + k];
   const int mode = d.st_mode[nb + k];
   const double hdt = 0.5 * dt, imass = 1.0 / M.total_mass;
-  // ---- Jacobian columns (lane = column)
-  double a1[9], a2[9], bj1[6], bj2[6], bf1[3], bf2[3];
-  if (lane < NXA) { lq_x_column<NJ>(b1, us, lane, a1); lq_x_column<NJ>(b2, us, lane, a2); }
-  if (lane < NJ) { lq_bj_column<NJ>(b1, lane, bj1); lq_bj_column<NJ>(b2, lane, bj2); }
-  if (lane < 12) { lq_bf_column<NJ>(b1, lane, bf1); lq_bf_column<NJ>(b2, lane, bf2); }
-  if (lane < NXA) {
+  // ---- Jacobian columns.  Lanes 0..15 work on the first Heun evaluation (b1), lanes 16..31 on the second (b2), with the same instructions:
+  //   heavy pass : half-lane cl < NH = NXA - 6 -> state column 6 + cl (base Euler angles, leg joints), lq_dq_column
+  //   cheap pass : the angular-momentum columns 3..5 (lanes NH..NH+2 for b1, lanes 24..26 for b2); columns 0..2 are constant
+  // Everything below addresses the state columns through xcl = xc_of(lane): lanes 0..NH-1 -> columns 6.., NH..NH+2 -> 3..5, NH+3..NXA-1 -> 0..2,
+  // so the columns of the first evaluation (a1) are already in the lane that consumes them; the second evaluation's go through sA2w.
+  constexpr int NH = NXA - 6;
+  static_assert(NH <= 16 && NH + 6 <= 32, "half-warp split of the Jacobian columns");
+  const int half = lane >> 4, cl = lane & 15;
+  const double* __restrict__ bsel = half ? b2 : b1;
+  const int xcl = lane < NH ? 6 + lane : (lane < NH + 3 ? 3 + (lane - NH) : lane - (NH + 3));   // state column (active-x index) of this lane, lane < NXA
+  double a1[9], bj1[6], bj2[6], bf1[3], bf2[3];
 #pragma unroll
-    for (int r = 0; r < 9; ++r) sA2w[r][lane] = a2[r];
+  for (int r = 0; r < 9; ++r) a1[r] = 0.0;
+  if (cl < NH) {
+    double col[9];
+    lq_dq_column<NJ>(bsel, us, 6 + cl, col);
+    if (half == 0) {
+#pragma unroll
+      for (int r = 0; r < 9; ++r) a1[r] = col[r];
+    } else {
+#pragma unroll
+      for (int r = 0; r < 9; ++r) sA2w[r][6 + cl] = col[r];
+    }
+  }
+  {
+    const bool c1 = lane >= NH && lane < NH + 3, c2 = lane >= 24 && lane < 27;
+    if (c1 || c2) {
+      double col[9];
+      lq_x_column<NJ>(c1 ? b1 : b2, us, 3 + (c1 ? lane - NH : lane - 24), col);
+      if (c1) {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) a1[r] = col[r];
+      } else {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) sA2w[r][3 + lane - 24] = col[r];
+      }
+    }
+    if (lane >= NH + 3 && lane < NXA) {   // d f / d (normalised linear momentum): identity block, both evaluations
+      const int c = lane - (NH + 3);
+      a1[3 + c] = 1.0;
+#pragma unroll
+      for (int r = 0; r < 9; ++r) sA2w[r][c] = (r == 3 + c) ? 1.0 : 0.0;
+    }
+  }
+  {
+    double bjv[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, bfv[3] = {0.0, 0.0, 0.0};
+    if (cl < NJ) lq_bj_column<NJ>(bsel, cl, bjv);
+    if (cl < 12) lq_bf_column<NJ>(bsel, cl, bfv);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { bj1[i] = bjv[i]; bj2[i] = __shfl_sync(0xffffffffu, bjv[i], (lane + 16) & 31); }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { bf1[i] = bfv[i]; bf2[i] = __shfl_sync(0xffffffffu, bfv[i], (lane + 16) & 31); }
   }
   __syncwarp();
   // ---- dynamics: b, (A_d - I), B_d   [UPSTREAM SensitivityIntegrator RK2]
@@ -109,7 +153,7 @@ __device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k,
       double s = 0.0;
 #pragma unroll
       for (int t = 0; t < 3; ++t) s += sA2w[r][3 + t] * a1[t] + sA2w[r][6 + t] * a1[6 + t];
-      rec[D::R_AD + r * NXA + lane] = hdt * (a1[r] + a2[r] + dt * s);
+      rec[D::R_AD + r * NXA + xcl] = hdt * (a1[r] + sA2w[r][xcl] + dt * s);
     }
   }
   if (lane < 12) {
@@ -189,8 +233,8 @@ __device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k,
       if (lane < NXA) {
         v3 t = mk(a1[3], a1[4], a1[5]) + a1[6] * Jb[0] + a1[7] * Jb[1] + a1[8] * Jb[2];
         bool direct = false; v3 ak, ok, wk, vk;
-        if (lane >= 6 && lane < 9) { const int kk = lane - 6; direct = true; ak = ld3(b1 + BD::B_BAX + 3 * kk); ok = pb; wk = ld3(b1 + BD::B_WE + 3 * (kk + 1)); vk = ld3(b1 + BD::B_VE + 3 * (kk + 1)); }
-        else if (lane >= 9 && (lane - 9) / NL == leg) { const double* J = b1 + BD::B_J + BD::JS * (lane - 9); direct = true; ak = ld3(J + BD::J_A); ok = ld3(J + BD::J_O); wk = ld3(J + BD::J_W); vk = ld3(J + BD::J_V); }
+        if (xcl >= 6 && xcl < 9) { const int kk = xcl - 6; direct = true; ak = ld3(b1 + BD::B_BAX + 3 * kk); ok = pb; wk = ld3(b1 + BD::B_WE + 3 * (kk + 1)); vk = ld3(b1 + BD::B_VE + 3 * (kk + 1)); }
+        else if (xcl >= 9 && (xcl - 9) / NL == leg) { const double* J = b1 + BD::B_J + BD::JS * (xcl - 9); direct = true; ak = ld3(J + BD::J_A); ok = ld3(J + BD::J_O); wk = ld3(J + BD::J_W); vk = ld3(J + BD::J_V); }
         if (direct) { const v3 uw = vcp - (cross(wk, p) + vk); t = t + cross(ak, uw) + cross(wk, cross(ak, p - ok)); }
         jx[c] = t;
       }
@@ -212,13 +256,13 @@ __device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k,
       const v3 vcc = ld3(b1 + BD::B_VC + 3 * c);
       if (st) {
         peq += dot(vcc, vcc);
-        if (lane < NXA) { rec[D::R_CV + (nrows + 0) * NXA + lane] = jx[c].x; rec[D::R_CV + (nrows + 1) * NXA + lane] = jx[c].y; rec[D::R_CV + (nrows + 2) * NXA + lane] = jx[c].z; }
+        if (lane < NXA) { rec[D::R_CV + (nrows + 0) * NXA + xcl] = jx[c].x; rec[D::R_CV + (nrows + 1) * NXA + xcl] = jx[c].y; rec[D::R_CV + (nrows + 2) * NXA + xcl] = jx[c].z; }
         if (lane < NJ) { rec[D::R_DV + (nrows + 0) * NJ + lane] = ju[c].x; rec[D::R_DV + (nrows + 1) * NJ + lane] = ju[c].y; rec[D::R_DV + (nrows + 2) * NJ + lane] = ju[c].z; }
         if (lane == 0) { rec[D::R_EV + nrows] = vcc.x; rec[D::R_EV + nrows + 1] = vcc.y; rec[D::R_EV + nrows + 2] = vcc.z; }
         nrows += 3;
       } else {
         const double ev = vcc.z - d.zref[(nb + k) * 2 + c / 2];
-        if (lane < NXA) rec[D::R_CV + nrows * NXA + lane] = jx[c].z;
+        if (lane < NXA) rec[D::R_CV + nrows * NXA + xcl] = jx[c].z;
         if (lane < NJ) rec[D::R_DV + nrows * NJ + lane] = ju[c].z;
         if (lane == 0) rec[D::R_EV + nrows] = ev;
         peq += ev * ev + us[3 * c] * us[3 * c] + us[3 * c + 1] * us[3 * c + 1] + us[3 * c + 2] * us[3 * c + 2];
@@ -242,8 +286,8 @@ __device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k,
       const v3 n2 = cross(r, n1);
       const v3 sx_ = is2 * (jx[ca] + jx[cb]), dx_ = is2 * (jx[ca] - jx[cb]), su_ = is2 * (ju[ca] + ju[cb]), du_ = is2 * (ju[ca] - ju[cb]);
       if (lane < NXA) {
-        rec[D::R_CV + (nrows + 0) * NXA + lane] = sx_.x; rec[D::R_CV + (nrows + 1) * NXA + lane] = sx_.y; rec[D::R_CV + (nrows + 2) * NXA + lane] = sx_.z;
-        rec[D::R_CV + (nrows + 3) * NXA + lane] = dot(n1, dx_); rec[D::R_CV + (nrows + 4) * NXA + lane] = dot(n2, dx_);
+        rec[D::R_CV + (nrows + 0) * NXA + xcl] = sx_.x; rec[D::R_CV + (nrows + 1) * NXA + xcl] = sx_.y; rec[D::R_CV + (nrows + 2) * NXA + xcl] = sx_.z;
+        rec[D::R_CV + (nrows + 3) * NXA + xcl] = dot(n1, dx_); rec[D::R_CV + (nrows + 4) * NXA + xcl] = dot(n2, dx_);
       }
       if (lane < NJ) {
         rec[D::R_DV + (nrows + 0) * NJ + lane] = su_.x; rec[D::R_DV + (nrows + 1) * NJ + lane] = su_.y; rec[D::R_DV + (nrows + 2) * NJ + lane] = su_.z;
@@ -259,7 +303,7 @@ __device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k,
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int c0 = t == 0 ? ca : cb;
-        if (lane < NXA) rec[D::R_CV + nrows * NXA + lane] = jx[c0].z;
+        if (lane < NXA) rec[D::R_CV + nrows * NXA + xcl] = jx[c0].z;
         if (lane < NJ) rec[D::R_DV + nrows * NJ + lane] = ju[c0].z;
         const double ev = (t == 0 ? va.z : vb.z) - zr;
         if (lane == 0) rec[D::R_EV + nrows] = ev;
