@@ -107,10 +107,10 @@ struct bmpc_handle {
   int linesearch_trials = 0, max_trials = 0, failed_instances = 0, status_or = 0;
   // multi-GPU policy exchange (bmpc_exchange_*)
   struct Exchange {
-    NcclApi::Comm comm = nullptr; int rank = 0, nranks = 1; bool copy_engines = false; int max_ctas = 0;
+    NcclApi::Comm comm = nullptr; int rank = 0, nranks = 1; bool copy_engines = false, symmetric = false; int max_ctas = 0;
     cudaStream_t stream = nullptr; cudaEvent_t ready = nullptr, done[2] = {nullptr, nullptr}; bool started[2] = {false, false};
-    void* recv[2] = {nullptr, nullptr}; void* send = nullptr; bool nccl_mem = false;
-    NcclApi::Window win_recv[2] = {nullptr, nullptr}, win_send = nullptr;
+    void* recv[2] = {nullptr, nullptr}; void* send_slab[2] = {nullptr, nullptr}; bool nccl_mem = false;
+    NcclApi::Window win_recv[2] = {nullptr, nullptr}, win_send[2] = {nullptr, nullptr};
     int last = -1; long count = 0;
   } ex;
   // scratch for policy evaluation / rollout
@@ -193,8 +193,7 @@ void tick(bmpc_handle* h) {
   CK(cudaMemcpyAsync(h->s_nev[w], h->d_n_ev, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(h->s_evt[w], h->d_ev_t, sizeof(double) * B * h->ME, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(h->s_evm[w], h->d_ev_mode, sizeof(int) * B * (h->ME + 1), cudaMemcpyDeviceToDevice, st));
-  k_time_grid<<<(B + 127) / 128, 128, 0, st>>>(d); ++h->launches;
-  k_node_setup<NJ><<<(nodes + 7) / 8, 256, 0, st>>>(d); ++h->launches;   // one warp per node
+  k_setup<NJ><<<B, SETUP_THREADS, setup_smem_bytes(NS, h->ME, h->TP), st>>>(d); ++h->launches;   // time grid + references + warm start, one CTA per instance
   mark(1);
   for (int iter = 0; iter < h->sqp_iterations; ++iter) {
     constexpr int G = LqPackSmem<NJ>::G;
@@ -292,15 +291,30 @@ int fail(bmpc_handle* h, int code, const std::string& msg) {
   catch (const std::length_error& e) { return fail(h, BMPC_ERR_CAPACITY, e.what()); } \
   catch (const std::exception& e) { return fail(h, BMPC_ERR_INVALID, e.what()); }
 
+void set_slab_pointers(bmpc_handle* h, int i, double* slab) {
+  const size_t B = h->B, NS = h->NS, nx = h->nx, nu = h->nu;
+  const size_t nK = B * NS * nu * nx, nU = B * NS * nu, nX = B * NS * nx, nT = B * NS;
+  h->slab[i] = slab;
+  h->s_K[i] = slab; h->s_uff[i] = slab + nK; h->s_x[i] = h->s_uff[i] + nU; h->s_u[i] = h->s_x[i] + nX; h->s_t[i] = h->s_u[i] + nU;
+  h->s_ev[i] = reinterpret_cast<int*>(h->s_t[i] + nT); h->s_n[i] = h->s_ev[i] + B * NS;
+}
 void exchange_release(bmpc_handle* h) {
   auto& ex = h->ex; NcclApi& N = nccl_api();
   if (ex.stream) cudaStreamSynchronize(ex.stream);
   if (ex.comm) {
-    for (int i = 0; i < 2; ++i) if (ex.win_recv[i] && N.CommWindowDeregister) N.CommWindowDeregister(ex.comm, ex.win_recv[i]);
-    if (ex.win_send && N.CommWindowDeregister) N.CommWindowDeregister(ex.comm, ex.win_send);
+    for (int i = 0; i < 2; ++i) {
+      if (ex.win_recv[i] && N.CommWindowDeregister) N.CommWindowDeregister(ex.comm, ex.win_recv[i]);
+      if (ex.win_send[i] && N.CommWindowDeregister) N.CommWindowDeregister(ex.comm, ex.win_send[i]);
+    }
   }
   for (int i = 0; i < 2; ++i) if (ex.recv[i]) { if (ex.nccl_mem) N.MemFree(ex.recv[i]); else cudaFree(ex.recv[i]); ex.recv[i] = nullptr; }
-  if (ex.send) { if (ex.nccl_mem) N.MemFree(ex.send); else cudaFree(ex.send); ex.send = nullptr; }
+  for (int i = 0; i < 2; ++i) if (ex.send_slab[i]) {
+    // the policy slabs live in NCCL memory: move them back into plain device memory before it is released
+    const size_t bytes = h->slab_doubles * sizeof(double);
+    double* p = nullptr;
+    if (cudaMalloc(&p, bytes) == cudaSuccess) { cudaMemcpy(p, ex.send_slab[i], bytes, cudaMemcpyDeviceToDevice); h->pool.dev.push_back(p); set_slab_pointers(h, i, p); }
+    N.MemFree(ex.send_slab[i]); ex.send_slab[i] = nullptr;
+  }
   if (ex.comm) { N.CommDestroy(ex.comm); ex.comm = nullptr; }
   if (ex.ready) cudaEventDestroy(ex.ready);
   for (auto& e : ex.done) if (e) cudaEventDestroy(e);
@@ -373,10 +387,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
       const size_t nK = B * NS * nu * nx, nU = B * NS * nu, nX = B * NS * nx, nT = B * NS;
       const size_t ints = (B * NS + B + 1) / 2;   // events + n_nodes, in units of doubles
       h->slab_doubles = nK + 2 * nU + nX + nT + ints;
-      double* slab = P.d<double>(h->slab_doubles);
-      h->slab[i] = slab;
-      h->s_K[i] = slab; h->s_uff[i] = slab + nK; h->s_x[i] = h->s_uff[i] + nU; h->s_u[i] = h->s_x[i] + nX; h->s_t[i] = h->s_u[i] + nU;
-      h->s_ev[i] = reinterpret_cast<int*>(h->s_t[i] + nT); h->s_n[i] = h->s_ev[i] + B * NS;
+      set_slab_pointers(h, i, P.d<double>(h->slab_doubles));
       h->s_nev[i] = P.d<int>(B); h->s_evt[i] = P.d<double>(B * h->ME); h->s_evm[i] = P.d<int>(B * (h->ME + 1));
       h->s_perf[i] = P.d<double>(B * 8); h->s_status[i] = P.d<int>(B);
     }
@@ -757,8 +768,11 @@ int bmpc_exchange_init(bmpc_handle* h, int rank, int nranks, const bmpc_exchange
   ex.rank = rank; ex.nranks = nranks; ex.max_ctas = max_ctas;
   NcclApi::UniqueId uid; std::memcpy(&uid, id, sizeof(uid));
   const bool can_config = N.CommInitRankConfig && N.version >= 22800;
-  // copy-engine collectives (NCCL >= 2.28: CTA policy "zero" + symmetric windows): the all-gather then uses no SM at all
-  ex.copy_engines = use_copy_engines && can_config && N.MemAlloc && N.CommWindowRegister;
+  // mode 1: copy-engine collectives (NCCL >= 2.28: CTA policy "zero" + symmetric windows): the all-gather then uses no SM at all;
+  // mode 2: symmetric windows with NCCL's SM kernels (fewer CTAs reach the same bandwidth than with unregistered buffers)
+  const bool windows = use_copy_engines != 0 && can_config && N.MemAlloc && N.CommWindowRegister;
+  ex.copy_engines = windows && use_copy_engines == 1;
+  ex.symmetric = windows;
   if (can_config) {
     NcclApi::ConfigV22800 cfg = N.default_config();
     if (max_ctas > 0) { cfg.maxCTAs = max_ctas; cfg.minCTAs = 1; }
@@ -769,14 +783,24 @@ int bmpc_exchange_init(bmpc_handle* h, int rank, int nranks, const bmpc_exchange
   CK(cudaEventCreateWithFlags(&ex.ready, cudaEventDisableTiming));
   for (auto& e : ex.done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   const size_t bytes = h->slab_doubles * sizeof(double);
-  ex.nccl_mem = ex.copy_engines;
+  ex.nccl_mem = windows;
   for (int i = 0; i < 2; ++i) {
     if (ex.nccl_mem) N.check(N.MemAlloc(&ex.recv[i], bytes * nranks), "ncclMemAlloc"); else CK(cudaMalloc(&ex.recv[i], bytes * nranks));
   }
-  if (ex.copy_engines) {
-    N.check(N.MemAlloc(&ex.send, bytes), "ncclMemAlloc");
-    N.check(N.CommWindowRegister(ex.comm, ex.send, bytes, &ex.win_send, NcclApi::kWinCollSymmetric), "ncclCommWindowRegister");
-    for (int i = 0; i < 2; ++i) N.check(N.CommWindowRegister(ex.comm, ex.recv[i], bytes * nranks, &ex.win_recv[i], NcclApi::kWinCollSymmetric), "ncclCommWindowRegister");
+  if (windows) {
+    // the policy slabs themselves move into NCCL-allocated, window-registered memory: the all-gather reads them in place (no staging copy)
+    for (int i = 0; i < 2; ++i) {
+      void* p = nullptr;
+      N.check(N.MemAlloc(&p, bytes), "ncclMemAlloc");
+      CK(cudaMemcpy(p, h->slab[i], bytes, cudaMemcpyDeviceToDevice));
+      auto& dv = h->pool.dev;
+      dv.erase(std::remove(dv.begin(), dv.end(), (void*)h->slab[i]), dv.end());
+      CK(cudaFree(h->slab[i]));
+      set_slab_pointers(h, i, static_cast<double*>(p));
+      ex.send_slab[i] = p;
+      N.check(N.CommWindowRegister(ex.comm, p, bytes, &ex.win_send[i], NcclApi::kWinCollSymmetric), "ncclCommWindowRegister");
+      N.check(N.CommWindowRegister(ex.comm, ex.recv[i], bytes * nranks, &ex.win_recv[i], NcclApi::kWinCollSymmetric), "ncclCommWindowRegister");
+    }
   }
   return BMPC_OK; API_END(h)
 }
@@ -792,9 +816,7 @@ int bmpc_exchange_start(bmpc_handle* h) {
   const int c = h->pending ? 1 - h->cur : h->cur;
   CK(cudaEventRecord(ex.ready, h->stream));
   CK(cudaStreamWaitEvent(ex.stream, ex.ready, 0));
-  const void* src = h->slab[c];
-  if (ex.copy_engines) { CK(cudaMemcpyAsync(ex.send, h->slab[c], h->slab_doubles * sizeof(double), cudaMemcpyDeviceToDevice, ex.stream)); src = ex.send; }
-  N.check(N.AllGather(src, ex.recv[c], h->slab_doubles, NcclApi::kFloat64, ex.comm, ex.stream), "ncclAllGather");
+  N.check(N.AllGather(h->slab[c], ex.recv[c], h->slab_doubles, NcclApi::kFloat64, ex.comm, ex.stream), "ncclAllGather");
   CK(cudaEventRecord(ex.done[c], ex.stream));
   ex.started[c] = true; ex.last = c; ++ex.count;
   return BMPC_OK; API_END(h)
@@ -813,7 +835,7 @@ int bmpc_exchange_view(bmpc_handle* h, const void** gathered, unsigned long long
   if (gathered) *gathered = h->ex.recv[h->ex.last];
   if (slab_bytes) *slab_bytes = h->slab_doubles * sizeof(double);
   if (nranks) *nranks = h->ex.nranks;
-  return h->ex.copy_engines ? 1 : 0;
+  return h->ex.copy_engines ? 1 : (h->ex.symmetric ? 2 : 0);
 }
 int bmpc_exchange_destroy(bmpc_handle* h) {
   API_BEGIN if (!h) return BMPC_ERR_INVALID;

@@ -279,8 +279,10 @@ class BatchedMpcMrtInterface:
         return xo, uo, mo
 
     # ------------------------------------------------------------------ multi-GPU policy exchange (one process per GPU)
-    def exchangeInit(self, dist, rank: int, world: int, max_ctas: int = 0, copy_engines: bool = False):
-        """bmpc_exchange_init: rank 0 creates the NCCL id, `dist` (torch.distributed, any backend) carries its 128 bytes to the other ranks."""
+    def exchangeInit(self, dist, rank: int, world: int, max_ctas: int = 0, copy_engines: int = 0):
+        """bmpc_exchange_init: rank 0 creates the NCCL id, `dist` (torch.distributed, any backend) carries its 128 bytes to the other ranks.
+        copy_engines: 0 plain buffers, 1 NCCL copy-engine all-gather (no SM), 2 symmetric windows with NCCL's SM kernels.  Device views obtained
+        before this call are stale afterwards (modes 1 and 2 move the policy slabs into NCCL-registered memory)."""
         import torch
         buf = (C.c_char * 128)()
         if rank == 0:
@@ -292,7 +294,7 @@ class BatchedMpcMrtInterface:
         dist.broadcast(t, src=0)
         raw = bytes(t.cpu().tolist())
         idb = (C.c_char * 128).from_buffer_copy(raw)
-        self._ck(self.L.bmpc_exchange_init(self.h, C.c_int(rank), C.c_int(world), idb, C.c_int(int(max_ctas)), C.c_int(1 if copy_engines else 0)))
+        self._ck(self.L.bmpc_exchange_init(self.h, C.c_int(rank), C.c_int(world), idb, C.c_int(int(max_ctas)), C.c_int(int(copy_engines))))
 
     def exchangeStart(self):
         self._ck(self.L.bmpc_exchange_start(self.h))
@@ -301,10 +303,10 @@ class BatchedMpcMrtInterface:
         self._ck(self.L.bmpc_exchange_wait(self.h))
 
     def exchangeView(self):
-        """(device pointer of the gathered slabs, bytes per slab, number of ranks, copy-engine mode active)."""
+        """(device pointer of the gathered slabs, bytes per slab, number of ranks, active mode: 0 plain, 1 copy engines, 2 symmetric windows)."""
         p, n, r = C.c_void_p(), C.c_ulonglong(), C.c_int()
         mode = self._ck(self.L.bmpc_exchange_view(self.h, C.byref(p), C.byref(n), C.byref(r)))
-        return int(p.value or 0), int(n.value), int(r.value), bool(mode)
+        return int(p.value or 0), int(n.value), int(r.value), int(mode)
 
     def exchangeDestroy(self):
         self._ck(self.L.bmpc_exchange_destroy(self.h))

@@ -44,7 +44,7 @@ class PolicyExchange:
     on `compute_stream`); tests on CPU pass plain tensors and the gloo backend through the same code.
     """
 
-    def __init__(self, mpc, dist, rank, world, window=False, window_nodes=4, slab_provider=None, compute_stream=None, impl="native", max_ctas=0, copy_engines=False):
+    def __init__(self, mpc, dist, rank, world, window=False, window_nodes=4, slab_provider=None, compute_stream=None, impl="native", max_ctas=0, copy_engines=0):
         """impl "native": the library's own exchange (bmpc_exchange_*: ncclAllGather issued by libbmpc on its exchange stream, optional SM cap /
         copy-engine mode); "torch": torch.distributed all_gather_into_tensor on a side stream (own NCCL group when max_ctas > 0).  The consumed-window
         variant and the CPU tests always use the torch path; a native initialisation failure falls back to it and is reported by describe()."""
@@ -160,6 +160,6 @@ class PolicyExchange:
 
     def describe(self):
         return {"collectives_per_tick": 1, "bytes_received_per_rank_per_tick": int(self.bytes_per_tick), "what": "first %d nodes of every instance" % self.window_nodes if self.window else "whole policy slab [K | uff | x | u | times | events | n_nodes], node slots sized to the workload",
-                "backend": ("libbmpc bmpc_exchange_* (ncclAllGather%s)" % (", copy engines" if self.mpc.exchangeView()[3] else "") if self.impl == "native"
+                "backend": ("libbmpc bmpc_exchange_* (ncclAllGather%s)" % ["", ", copy engines, zero SMs", ", symmetric windows"][self.mpc.exchangeView()[3]] if self.impl == "native"
                             else ("torch.distributed all_gather_into_tensor (NCCL)" if self.cuda else "gloo")),
                 "max_ctas": self.max_ctas, "note": self.note}

@@ -648,11 +648,11 @@ def test_native_policy_exchange_single_rank():
     if own_pg:
         dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{33500 + os.getpid() % 2000}", rank=0, world_size=1)
     try:
-        for max_ctas in (0, 8):
+        for max_ctas, mode in ((0, 0), (8, 0), (0, 1), (16, 2)):   # plain / SM cap / copy engines / symmetric windows (the latter two fall back to plain on old NCCL)
             B = 6
             g = G(B, model_file=MODEL, dt=0.01, time_horizon=0.3, max_event_nodes=3)
             g.setCurrentObservation(0.0, x0); g.setTargetTrajectories(tt, ts); g.setModeSchedule(et, ms)
-            g.exchangeInit(dist, 0, 1, max_ctas=max_ctas)
+            g.exchangeInit(dist, 0, 1, max_ctas=max_ctas, copy_engines=mode)
             for tick in range(3):
                 g.advanceMpcAsync()
                 g.exchangeStart()

@@ -26,6 +26,10 @@ for v in "${VARIANTS[@]}"; do
     native32) run $v --gather-impl native --gather-ctas 32 --no-extra ;;
     native0) run $v --gather-impl native --gather-ctas 0 --no-extra ;;
     nativece) run $v --gather-impl native --gather-ctas 0 --gather-ce 1 --no-extra ;;
+    sym8) run $v --gather-impl native --gather-ctas 8 --gather-ce 2 --no-extra ;;
+    sym16) run $v --gather-impl native --gather-ctas 16 --gather-ce 2 --no-extra ;;
+    sym32) run $v --gather-impl native --gather-ctas 32 --gather-ce 2 --no-extra ;;
+    sym0) run $v --gather-impl native --gather-ctas 0 --gather-ce 2 --no-extra ;;
     torch0) run $v --gather-impl torch --gather-ctas 0 --no-extra ;;
     torch16) run $v --gather-impl torch --gather-ctas 16 --no-extra ;;
     none) run $v --gather none --no-extra ;;
