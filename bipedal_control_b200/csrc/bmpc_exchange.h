@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 
 #include <climits>
+#include <cstdlib>
 #include <cstddef>
 #include <stdexcept>
 #include <string>
@@ -44,7 +45,12 @@ struct NcclApi {
   }
   void load() {
     if (lib) return;
-    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    // a copy that is already in the process (e.g. the one PyTorch ships and loaded) must be the one we use: two different libnccl.so.2 in one
+    // process do not work.  Otherwise BMPC_NCCL_LIBRARY (full path) or the system library.  A process that also uses PyTorch has to import torch
+    // BEFORE the first bmpc_exchange_* call for the same reason.
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!lib) { const char* path = getenv("BMPC_NCCL_LIBRARY"); if (path && path[0]) lib = dlopen(path, RTLD_NOW | RTLD_LOCAL); }
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
     if (!lib) throw std::runtime_error(std::string("[bmpc] cannot load libnccl.so.2 (needed only for bmpc_exchange_*): ") + dlerror());
     bind(GetVersion, "ncclGetVersion", true); bind(GetUniqueId, "ncclGetUniqueId", true); bind(CommInitRank, "ncclCommInitRank", true);
     bind(CommInitRankConfig, "ncclCommInitRankConfig", false); bind(CommDestroy, "ncclCommDestroy", true); bind(AllGather, "ncclAllGather", true);

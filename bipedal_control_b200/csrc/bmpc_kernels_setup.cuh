@@ -40,6 +40,36 @@ __global__ void k_gait_schedule(GaitDev g, Dev d) {
   for (int k = 0; k <= n; ++k) evm[k] = v.modes[k];
 }
 
+// ------------------------------------------------------------------------------------------------ K0a: time grid
+__global__ void k_time_grid(Dev d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  const double t0 = d.t0[b], tf = t0 + d.horizon, dt = d.dt_nom;
+  const double* ev = d.ev_t + (size_t)b * d.ME; const int ne = d.n_ev[b];
+  double* nt = d.node_t + (size_t)b * d.NS; int* nev = d.node_ev + (size_t)b * d.NS;
+  const double dt_min = 10.0 * WEAK_EPS;
+  int n = 0; bool overflow = false;
+  nt[0] = t0; nev[0] = 0; n = 1;
+  int nextEvent = lower_bound_d(ev, ne, t0);
+  double nextT = t0; int nextE = 0;
+  while (nt[n - 1] < tf) {
+    nextT = nextT + dt; nextE = 0;
+    if (nextEvent < ne && nextT >= ev[nextEvent]) { nextT = ev[nextEvent]; nextE = 1; ++nextEvent; }
+    if (nextT >= tf) { nextT = tf; nextE = 0; }
+    if (nextT > nt[n - 1] + dt_min) { if (n >= d.NS) { overflow = true; break; } nt[n] = nextT; nev[n] = nextE; ++n; }
+    else { nt[n - 1] = nextT; nev[n - 1] = nextE; }
+    if (nextE == 1) { if (n >= d.NS) { overflow = true; break; } nt[n] = nextT; nev[n] = 2; ++n; }
+  }
+  if (overflow) { atomicOr(&d.status[b], 32); nt[n - 1] = tf; nev[n - 1] = 0; }
+  d.n_nodes[b] = n;
+  double* stt = d.st_t + (size_t)b * d.NS; double* std_ = d.st_dt + (size_t)b * d.NS;
+  for (int i = 0; i + 1 < n; ++i) {
+    const double ts = nev[i] == 2 ? nt[i] + WEAK_EPS : nt[i];
+    const double te = nev[i + 1] == 1 ? nt[i + 1] - WEAK_EPS : nt[i + 1];
+    stt[i] = ts; std_[i] = (nev[i] == 1) ? 0.0 : te - ts;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ K0b: per-node references + warm start
 // swing height velocity of leg `leg` at time t (foot_planner/SwingTrajectoryPlanner.cpp:50-118, SplineCpg.cpp:38-60, CubicSpline.cpp:38-75)
 __device__ inline double swing_zvel(const double* ev, const int* modes, int ne, int leg, double t, int* status) {
@@ -70,100 +100,66 @@ __device__ __forceinline__ double interp_lane(const double* ta, const double* da
   return al * a[lane] + (1.0 - al) * a[dim + lane];
 }
 
-// K0: one CTA per instance.  (a) thread 0 builds the time grid with event nodes in shared memory ([UPSTREAM] timeDiscretizationWithEvents), the CTA
-// writes it out coalesced; (b) every warp then takes nodes k = warp, warp + 4, ...: lane = state / input component, the scalar logic (mode lookup,
-// swing reference, source of the initial guess) is evaluated by all lanes on the shared-memory copies of the instance's schedule, grid and previous
-// time trajectory, so no lookup chain goes through global memory; the 22-wide reads and writes are coalesced.
-constexpr int SETUP_THREADS = 128;
-__host__ __device__ inline size_t setup_smem_bytes(int NS, int ME, int TP) { return sizeof(double) * (size_t)(4 * NS + ME + TP + 2) + sizeof(int) * (size_t)(NS + ME + 2); }
-
+// one WARP per node, lane = state / input component: the scalar logic (mode lookup, swing reference, which source the initial guess comes from)
+// is evaluated redundantly by the lanes, the 22-wide reads and writes are coalesced
 template <int NJ>
-__global__ void __launch_bounds__(SETUP_THREADS) k_setup(Dev d) {
+__global__ void __launch_bounds__(256) k_node_setup(Dev d) {
   constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* nt = reinterpret_cast<double*>(smem_raw); double* stt = nt + d.NS; double* std_ = stt + d.NS; double* pt = std_ + d.NS;
-  double* ev = pt + d.NS; double* tg = ev + d.ME;
-  int* nev = reinterpret_cast<int*>(tg + d.TP + 2); int* modes = nev + d.NS;
-  __shared__ int s_n;
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gw = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  const int b = gw / d.NS, k = gw % d.NS;
+  if (b >= d.B) return;
+  const int n = d.n_nodes[b];
+  if (k >= n) return;
+  const int N = n - 1;
   const size_t nb = (size_t)b * d.NS;
-  const int ne = d.n_ev[b];
-  const int pn = d.p_n ? d.p_n[b] : 0;
-  for (int i = tid; i < ne; i += SETUP_THREADS) ev[i] = d.ev_t[(size_t)b * d.ME + i];
-  for (int i = tid; i <= ne; i += SETUP_THREADS) modes[i] = d.ev_mode[(size_t)b * (d.ME + 1) + i];
-  for (int i = tid; i < pn; i += SETUP_THREADS) pt[i] = d.p_t[nb + i];
-  for (int i = tid; i < d.npts; i += SETUP_THREADS) tg[i] = d.tgt_t[(size_t)b * d.TP + i];
-  __syncthreads();
-  if (tid == 0) {   // ---- (a) time grid
-    const double t0 = d.t0[b], tf = t0 + d.horizon, dt = d.dt_nom;
-    const double dt_min = 10.0 * WEAK_EPS;
-    int n = 0; bool overflow = false;
-    nt[0] = t0; nev[0] = 0; n = 1;
-    int nextEvent = lower_bound_d(ev, ne, t0);
-    double nextT = t0; int nextE = 0;
-    while (nt[n - 1] < tf) {
-      nextT = nextT + dt; nextE = 0;
-      if (nextEvent < ne && nextT >= ev[nextEvent]) { nextT = ev[nextEvent]; nextE = 1; ++nextEvent; }
-      if (nextT >= tf) { nextT = tf; nextE = 0; }
-      if (nextT > nt[n - 1] + dt_min) { if (n >= d.NS) { overflow = true; break; } nt[n] = nextT; nev[n] = nextE; ++n; }
-      else { nt[n - 1] = nextT; nev[n - 1] = nextE; }
-      if (nextE == 1) { if (n >= d.NS) { overflow = true; break; } nt[n] = nextT; nev[n] = 2; ++n; }
+  const double* ev = d.ev_t + (size_t)b * d.ME; const int* modes = d.ev_mode + (size_t)b * (d.ME + 1); const int ne = d.n_ev[b];
+  const int* nev = d.node_ev + nb;
+  const double* nt = d.node_t + nb;
+  const double* stt = d.st_t + nb; const double* std_ = d.st_dt + nb;
+  // ---- stage references
+  if (k < N) {
+    int mode = -1;
+    if (nev[k] != 1) {
+      const double t = stt[k];
+      mode = modes[lower_bound_d(ev, ne, t)];
+      if (lane < NX) d.xref[(nb + k) * NX + lane] = interp_lane(d.tgt_t + (size_t)b * d.TP, d.tgt_x + (size_t)b * d.TP * NX, d.npts, NX, t, lane);
+      if (lane < 2) d.zref[(nb + k) * 2 + lane] = leg_in_stance(mode, lane) ? 0.0 : swing_zvel(ev, modes, ne, lane, t, &d.status[b]);
     }
-    if (overflow) { atomicOr(&d.status[b], 32); nt[n - 1] = tf; nev[n - 1] = 0; }
-    d.n_nodes[b] = n; s_n = n;
-    for (int i = 0; i + 1 < n; ++i) {
-      const double ts = nev[i] == 2 ? nt[i] + WEAK_EPS : nt[i];
-      const double te = nev[i + 1] == 1 ? nt[i + 1] - WEAK_EPS : nt[i + 1];
-      stt[i] = ts; std_[i] = (nev[i] == 1) ? 0.0 : te - ts;
-    }
+    if (lane == 0) d.st_mode[nb + k] = mode;
   }
-  __syncthreads();
-  const int n = s_n, N = n - 1;
-  for (int i = tid; i < n; i += SETUP_THREADS) { d.node_t[nb + i] = nt[i]; d.node_ev[nb + i] = nev[i]; }
-  for (int i = tid; i < N; i += SETUP_THREADS) { d.st_t[nb + i] = stt[i]; d.st_dt[nb + i] = std_[i]; }
-  // ---- (b) per-node references + warm start
+  // ---- initial guess: [UPSTREAM] multiple_shooting::initializeStateInputTrajectories
+  const int pn = d.p_n ? d.p_n[b] : 0;
+  const double* pt = d.p_t + nb; const double* px = d.p_x + nb * NX; const double* pu = d.p_u + nb * NU;
   double stateTill = nt[0], inputTill = nt[0];
   if (pn >= 2) { stateTill = pt[pn - 1]; inputTill = pt[pn - 2]; }
-  const double* px = d.p_x + nb * NX; const double* pu = d.p_u + nb * NU;
   auto interval_uses_initializer = [&](int i) {   // interval i = [node i, node i+1]; true also for event nodes (state copied)
     if (nev[i] == 1) return true;
     const double ti = stt[i], tn = stt[i] + std_[i];
     return (ti > inputTill || tn > stateTill);
   };
-  for (int k = warp; k < n; k += SETUP_THREADS / 32) {
-    if (k < N) {   // stage references
-      int mode = -1;
-      if (nev[k] != 1) {
-        const double t = stt[k];
-        mode = modes[lower_bound_d(ev, ne, t)];
-        if (lane < NX) d.xref[(nb + k) * NX + lane] = interp_lane(tg, d.tgt_x + (size_t)b * d.TP * NX, d.npts, NX, t, lane);
-        if (lane < 2) d.zref[(nb + k) * 2 + lane] = leg_in_stance(mode, lane) ? 0.0 : swing_zvel(ev, modes, ne, lane, t, &d.status[b]);
-      }
-      if (lane == 0) d.st_mode[nb + k] = mode;
-    }
-    // initial guess: [UPSTREAM] multiple_shooting::initializeStateInputTrajectories
-    int j = k;
-    while (j > 0 && interval_uses_initializer(j - 1)) --j;
-    if (lane < NX) {
-      double xv;
-      if (j == 0) {
-        const double tinit = nev[0] == 2 ? nt[0] + WEAK_EPS : nt[0];
-        xv = (tinit < stateTill) ? interp_lane(pt, px, pn, NX, tinit, lane) : d.x0[(size_t)b * NX + lane];
-      } else xv = interp_lane(pt, px, pn, NX, stt[j - 1] + std_[j - 1], lane);
-      d.s_x[(nb + k) * NX + lane] = xv;
-    }
-    if (k < N && lane < NU) {
-      double uv = 0.0;
-      if (nev[k] == 1) uv = 0.0;
-      else if (interval_uses_initializer(k)) {   // initialization/BipedalRobotInitializer.cpp:56-63 + common/utils.h:63-77
-        const int mode = modes[lower_bound_d(ev, ne, stt[k])];
-        const bool s0 = leg_in_stance(mode, 0), s1 = leg_in_stance(mode, 1);
-        const int ns = 2 * (int(s0) + int(s1));
-        const double fz = ns > 0 ? c_model.total_mass * 9.81 / ns : 0.0;
-        if ((s0 && (lane == 2 || lane == 5)) || (s1 && (lane == 8 || lane == 11))) uv = fz;
-      } else uv = interp_lane(pt, pu, pn, NU, stt[k], lane);
-      d.s_u[(nb + k) * NU + lane] = uv;
-    }
+  // state of node k
+  int j = k;
+  while (j > 0 && interval_uses_initializer(j - 1)) --j;
+  if (lane < NX) {
+    double xv;
+    if (j == 0) {
+      const double tinit = nev[0] == 2 ? nt[0] + WEAK_EPS : nt[0];
+      xv = (tinit < stateTill) ? interp_lane(pt, px, pn, NX, tinit, lane) : d.x0[(size_t)b * NX + lane];
+    } else xv = interp_lane(pt, px, pn, NX, stt[j - 1] + std_[j - 1], lane);
+    d.s_x[(nb + k) * NX + lane] = xv;
+  }
+  // input of stage k
+  if (k < N && lane < NU) {
+    double uv = 0.0;
+    if (nev[k] == 1) uv = 0.0;
+    else if (interval_uses_initializer(k)) {   // initialization/BipedalRobotInitializer.cpp:56-63 + common/utils.h:63-77
+      const int mode = modes[lower_bound_d(ev, ne, stt[k])];
+      const bool s0 = leg_in_stance(mode, 0), s1 = leg_in_stance(mode, 1);
+      const int ns = 2 * (int(s0) + int(s1));
+      const double fz = ns > 0 ? c_model.total_mass * 9.81 / ns : 0.0;
+      if ((s0 && (lane == 2 || lane == 5)) || (s1 && (lane == 8 || lane == 11))) uv = fz;
+    } else uv = interp_lane(pt, pu, pn, NU, stt[k], lane);
+    d.s_u[(nb + k) * NU + lane] = uv;
   }
 }
 

@@ -33,14 +33,15 @@ def test_library_exports_every_declared_symbol(lib):
     assert not missing, f"declared in include/bmpc.h but not exported: {sorted(missing)}"
 
 
-def test_exchange_binds_nccl_at_run_time(lib):
-    """bmpc_exchange_create_id dlopens libnccl.so.2 and returns a 128-byte id: no link-time NCCL dependency, no GPU needed for this step."""
+def test_exchange_binds_nccl_at_run_time():
+    """bmpc_exchange_create_id dlopens libnccl.so.2 and returns a 128-byte id: no link-time NCCL dependency, no GPU needed for this step.
+    (In a subprocess: a process that loads the system NCCL first can no longer import a PyTorch that ships a newer one.)"""
     out = subprocess.run(["ldd", LIB], capture_output=True, text=True).stdout
     assert "nccl" not in out
-    buf = (C.c_char * 128)()
-    rc = lib.bmpc_exchange_create_id(buf)
-    assert rc == 0, lib.bmpc_last_error(None)
-    assert any(bytes(buf))
+    code = ("import ctypes as C; L = C.CDLL(%r); L.bmpc_last_error.restype = C.c_char_p; L.bmpc_last_error.argtypes = [C.c_void_p]; "
+            "b = (C.c_char * 128)(); rc = L.bmpc_exchange_create_id(b); print(rc, any(bytes(b)), L.bmpc_last_error(None))" % LIB)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.stdout.split()[:2] == ["0", "True"], r.stdout + r.stderr
 
 
 def test_library_is_sm100a_only():
