@@ -338,7 +338,7 @@ def main():
     ap.add_argument("--gather", default="full", choices=["full", "window", "none"])
     ap.add_argument("--gather-impl", default="native", choices=["native", "torch"], help="policy all-gather: libbmpc's own NCCL exchange (bmpc_exchange_*) or torch.distributed")
     ap.add_argument("--gather-ctas", type=int, default=16, help="cap on the SMs NCCL may use for the policy all-gather (0: NCCL default)")
-    ap.add_argument("--gather-ce", type=int, default=0, help="1: NCCL copy-engine all-gather (NCCL >= 2.28, symmetric windows, no SM at all); 2: symmetric windows with NCCL's SM kernels")
+    ap.add_argument("--gather-ce", type=int, default=2, help="1: NCCL copy-engine all-gather (NCCL >= 2.28, symmetric windows, no SM at all); 2: symmetric windows with NCCL's SM kernels")
     ap.add_argument("--opt", action="append", default=[], help="debug option name=value passed to bmpc_debug_set_option (not for reported numbers)")
     args = ap.parse_args()
     if args.impl == "reference":
