@@ -382,7 +382,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     h->h_t0 = P.h<double>(B); h->h_x0 = P.h<double>(B * nx); h->h_tgt_t = P.h<double>(B * h->TP); h->h_tgt_x = P.h<double>(B * h->TP * nx);
     h->h_n_ev = P.h<int>(B); h->h_ev_t = P.h<double>(B * h->ME); h->h_ev_mode = P.h<int>(B * (h->ME + 1));
     h->d_st_t = P.d<double>(B * NS); h->d_st_dt = P.d<double>(B * NS); h->d_st_mode = P.d<int>(B * NS);
-    h->d_xref = P.d<double>(B * NS * nx); h->d_zref = P.d<double>(B * NS * 2);
+    h->d_xref = P.d<double>(B * NS * nx); h->d_zref = P.d<double>(B * NS * 4);
     for (int i = 0; i < 2; ++i) {
       // one contiguous slab per policy buffer: [K | uff | x | u | t | events | n_nodes], so that the multi-GPU exchange is ONE collective
       const size_t nK = B * NS * nu * nx, nU = B * NS * nu, nX = B * NS * nx, nT = B * NS;
@@ -851,7 +851,11 @@ int bmpc_get_launch_count(const bmpc_handle* h) { return h ? h->launches : 0; }
 int bmpc_debug_set_option(bmpc_handle* h, const char* name, int value) {
   if (!h || !name) return BMPC_ERR_INVALID;
   std::lock_guard<std::mutex> lk(h->mtx);
-  if (std::string(name) == "projection_mode") { if (value < 0 || value > 1) return BMPC_ERR_INVALID; h->projection_mode = value; return BMPC_OK; }
+  if (std::string(name) == "projection_mode") {
+    if (value < 0 || value > 1) return BMPC_ERR_INVALID;
+    if (value == 0 && h->model.dev.gain != 0.0) return fail(h, BMPC_ERR_INVALID, "[bmpc] the Moore-Penrose projection option does not support positionErrorGain != 0");
+    h->projection_mode = value; return BMPC_OK;
+  }
   return BMPC_ERR_INVALID;
 }
 int bmpc_enable_phase_timing(bmpc_handle* h, int enable) { if (!h) return BMPC_ERR_INVALID; std::lock_guard<std::mutex> lk(h->mtx); h->timing = enable != 0; return BMPC_OK; }
@@ -893,7 +897,7 @@ int bmpc_debug_copy(bmpc_handle* h, const char* name, int instance, double* dst,
   else if (n == "dx") { src = h->d_dx + b * NS * h->nx; cnt = NS * h->nx; }
   else if (n == "du") { src = h->d_du + b * NS * h->nu; cnt = NS * h->nu; }
   else if (n == "xref") { src = h->d_xref + b * NS * h->nx; cnt = NS * h->nx; }
-  else if (n == "zref") { src = h->d_zref + b * NS * 2; cnt = NS * 2; }
+  else if (n == "zref") { src = h->d_zref + b * NS * 4; cnt = NS * 4; }
   else if (n == "st_t") { src = h->d_st_t + b * NS; cnt = NS; }
   else if (n == "st_dt") { src = h->d_st_dt + b * NS; cnt = NS; }
   else if (n == "x") { src = h->s_x[c] + b * NS * h->nx; cnt = NS * h->nx; }

@@ -109,8 +109,9 @@ struct Dims {
                        REC = ((R_FO + 12 + 3) / 4) * 4;
   // misc slots
   static constexpr int M_DT = 0, M_DQ = 1, M_DR = 2, M_MODE = 3, M_NROWS = 4, M_TYPE = 5, M_PCOST = 6, M_PDYN = 7, M_PEQ = 8;
-  // projection record: Pxj[NJ][NXA], Pej[NJ], N[NJ][8], meta (mj, rank_flag)
-  static constexpr int P_PX = 0, P_PE = P_PX + NJ * NXA, P_N = P_PE + NJ, P_FO = P_N + NJ * 8, P_META = P_FO + 12, PREC = ((P_META + 4 + 3) / 4) * 4;
+  // projection record: Pxj[NJ][NXA], Pej[NJ], N[NJ][8], meta (mj, rank_flag), Pxj[:, base height]
+  // P_PX8: the base-height column (state 8) of Pxj; non-zero only with positionErrorGain != 0 (the other base-position columns vanish always)
+  static constexpr int P_PX = 0, P_PE = P_PX + NJ * NXA, P_N = P_PE + NJ, P_FO = P_N + NJ * 8, P_META = P_FO + 12, P_PX8 = P_META + 4, PREC = ((P_PX8 + NJ + 3) / 4) * 4;
 };
 
 // map a state index (0..NX-1, not 6..8) to its column in the "active x" set X = {0..5, 9..NX-1}
@@ -123,7 +124,7 @@ __device__ __forceinline__ int xcol(int s) { return s < 6 ? s : s - 3; }
 // inertias, no per-joint arrays, no local memory.  xb = x[0:12], qj = x[12:], uf = u[0:12], qd = u[12:]; f = rows 0..11 of the flow map
 // (rows 12.. are qd).  Fully unrolled: the model constants become immediate constant-bank operands.
 template <int NJ>
-__device__ __noinline__ void model_values(const double (&xb)[12], const double (&qj)[NJ], const double (&uf)[12], const double (&qd)[NJ], double (&f)[12], v3 (&vc)[NCON]) {
+__device__ __noinline__ void model_values(const double (&xb)[12], const double (&qj)[NJ], const double (&uf)[12], const double (&qd)[NJ], double (&f)[12], v3 (&vc)[NCON], v3* pc_out = nullptr) {
   constexpr int NL = Dims<NJ>::NL;
   const DevModel& M = c_model;
   const double mass = M.total_mass, imass = 1.0 / mass;
@@ -182,6 +183,10 @@ __device__ __noinline__ void model_values(const double (&xb)[12], const double (
   const v3 ve3 = vlin + w.x * cross(pb, bax[0]) + w.y * cross(pb, bax[1]) + w.z * cross(pb, bax[2]);
 #pragma unroll
   for (int c = 0; c < NCON; ++c) vc[c] = cross(we3 + wtip[c / 2], pc[c]) + ve3 + vtip[c / 2];
+  if (pc_out) {
+#pragma unroll
+    for (int c = 0; c < NCON; ++c) pc_out[c] = pc[c];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ base record (values only)

@@ -68,17 +68,15 @@ __device__ __forceinline__ void stage_trial(const Dev& d, size_t nb, int k, doub
   double sdef = 0.0;
 #pragma unroll
   for (int j = 0; j < NJ; ++j) { const double e = qj[j] + dt * qd[j] - (gx[NX + 12 + j] + al * gdx[NX + 12 + j]); sdef += e * e; }
-  double k1[12], k2[12]; v3 vc[NCON], vc2[NCON];
-  model_values<NJ>(xb, qj, uf, qd, k1, vc);
+  double k1[12], k2[12]; v3 vc[NCON], vc2[NCON], pc[NCON];
+  model_values<NJ>(xb, qj, uf, qd, k1, vc, pc);
   double peq = 0.0;
 #pragma unroll
-  for (int leg = 0; leg < 2; ++leg) {
-    const int ca = 2 * leg, cb = 2 * leg + 1;
-    if (leg == 0 ? st0 : st1) peq += dot(vc[ca], vc[ca]) + dot(vc[cb], vc[cb]);
+  for (int c = 0; c < NCON; ++c) {   // ZeroVelocityConstraintCppAd / NormalVelocityConstraintCppAd + ZeroForceConstraint, incl. positionErrorGain
+    if ((c / 2 == 0) ? st0 : st1) { const double ez = vc[c].z + M.gain * pc[c].z; peq += vc[c].x * vc[c].x + vc[c].y * vc[c].y + ez * ez; }
     else {
-      const double zr = d.zref[(nb + k) * 2 + leg];
-#pragma unroll
-      for (int t = 0; t < 2; ++t) { const int c0 = t == 0 ? ca : cb; const double ev = vc[c0].z - zr; peq += ev * ev + uf[3 * c0] * uf[3 * c0] + uf[3 * c0 + 1] * uf[3 * c0 + 1] + uf[3 * c0 + 2] * uf[3 * c0 + 2]; }
+      const double ev = vc[c].z - d.zref[(nb + k) * 4 + c / 2] + M.gain * (pc[c].z - d.zref[(nb + k) * 4 + 2 + c / 2]);
+      peq += ev * ev + uf[3 * c] * uf[3 * c] + uf[3 * c + 1] * uf[3 * c + 1] + uf[3 * c + 2] * uf[3 * c + 2];
     }
   }
   double xb2[12], qj2[NJ];
@@ -86,7 +84,7 @@ __device__ __forceinline__ void stage_trial(const Dev& d, size_t nb, int k, doub
   for (int i = 0; i < 12; ++i) xb2[i] = xb[i] + dt * k1[i];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) qj2[j] = qj[j] + dt * qd[j];
-  model_values<NJ>(xb2, qj2, uf, qd, k2, vc2);
+  model_values<NJ>(xb2, qj2, uf, qd, k2, vc2, nullptr);
 #pragma unroll
   for (int i = 0; i < 12; ++i) { const double e = xb[i] + 0.5 * dt * (k1[i] + k2[i]) - (gx[NX + i] + al * gdx[NX + i]); sdef += e * e; }
   out[0] = dt * cost; out[1] = dt * sdef; out[2] = dt * peq;

@@ -235,7 +235,11 @@ __device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k,
         bool direct = false; v3 ak, ok, wk, vk;
         if (xcl >= 6 && xcl < 9) { const int kk = xcl - 6; direct = true; ak = ld3(b1 + BD::B_BAX + 3 * kk); ok = pb; wk = ld3(b1 + BD::B_WE + 3 * (kk + 1)); vk = ld3(b1 + BD::B_VE + 3 * (kk + 1)); }
         else if (xcl >= 9 && (xcl - 9) / NL == leg) { const double* J = b1 + BD::B_J + BD::JS * (xcl - 9); direct = true; ak = ld3(J + BD::J_A); ok = ld3(J + BD::J_O); wk = ld3(J + BD::J_W); vk = ld3(J + BD::J_V); }
-        if (direct) { const v3 uw = vcp - (cross(wk, p) + vk); t = t + cross(ak, uw) + cross(wk, cross(ak, p - ok)); }
+        if (direct) {
+          const v3 uw = vcp - (cross(wk, p) + vk), apo = cross(ak, p - ok);   // apo = d p / d q_k
+          t = t + cross(ak, uw) + cross(wk, apo);
+          t.z += M.gain * apo.z;   // positionErrorGain (BipedalRobotInterface.cpp:350-359, BipedalRobotPreComputation.cpp:71-80): the z rows also see gain * p_z
+        }
         jx[c] = t;
       }
       if (lane < NJ) {
@@ -254,14 +258,16 @@ __device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k,
     for (int c = 0; c < NCON; ++c) {
       const bool st = (c / 2 == 0) ? st0 : st1;
       const v3 vcc = ld3(b1 + BD::B_VC + 3 * c);
+      const double pz = b1[BD::B_PC + 3 * c + 2];   // contact height (terrain height 0, SwitchedModelReferenceManager.cpp:67)
       if (st) {
-        peq += dot(vcc, vcc);
+        const double ez = vcc.z + M.gain * pz;
+        peq += vcc.x * vcc.x + vcc.y * vcc.y + ez * ez;
         if (lane < NXA) { rec[D::R_CV + (nrows + 0) * NXA + xcl] = jx[c].x; rec[D::R_CV + (nrows + 1) * NXA + xcl] = jx[c].y; rec[D::R_CV + (nrows + 2) * NXA + xcl] = jx[c].z; }
         if (lane < NJ) { rec[D::R_DV + (nrows + 0) * NJ + lane] = ju[c].x; rec[D::R_DV + (nrows + 1) * NJ + lane] = ju[c].y; rec[D::R_DV + (nrows + 2) * NJ + lane] = ju[c].z; }
-        if (lane == 0) { rec[D::R_EV + nrows] = vcc.x; rec[D::R_EV + nrows + 1] = vcc.y; rec[D::R_EV + nrows + 2] = vcc.z; }
+        if (lane == 0) { rec[D::R_EV + nrows] = vcc.x; rec[D::R_EV + nrows + 1] = vcc.y; rec[D::R_EV + nrows + 2] = ez; }
         nrows += 3;
       } else {
-        const double ev = vcc.z - d.zref[(nb + k) * 2 + c / 2];
+        const double ev = vcc.z - d.zref[(nb + k) * 4 + c / 2] + M.gain * (pz - d.zref[(nb + k) * 4 + 2 + c / 2]);
         if (lane < NXA) rec[D::R_CV + nrows * NXA + xcl] = jx[c].z;
         if (lane < NJ) rec[D::R_DV + nrows * NJ + lane] = ju[c].z;
         if (lane == 0) rec[D::R_EV + nrows] = ev;
@@ -299,7 +305,7 @@ __device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k,
       }
       nrows += 5;
     } else {
-      const double zr = d.zref[(nb + k) * 2 + leg];
+      const double zr = d.zref[(nb + k) * 4 + leg];
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int c0 = t == 0 ? ca : cb;

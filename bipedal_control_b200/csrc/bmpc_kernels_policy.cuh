@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(128, 4) k_policy_expand(Dev d) {
     const int xc = xcol(lane);
     double pxv[NJ];
 #pragma unroll
-    for (int l = 0; l < NJ; ++l) pxv[l] = (lane < NX) ? (xact ? prj[D::P_PX + l * NXA + xc] : 0.0) : prj[D::P_PE + l];
+    for (int l = 0; l < NJ; ++l) pxv[l] = (lane < NX) ? (xact ? prj[D::P_PX + l * NXA + xc] : (lane == 8 ? prj[D::P_PX8 + l] : 0.0)) : prj[D::P_PE + l];
 #pragma unroll
     for (int l = 0; l < NJ; ++l) {
       double a = pxv[l];

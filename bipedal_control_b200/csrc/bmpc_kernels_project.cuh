@@ -80,9 +80,10 @@ __device__ __forceinline__ void pick_row(const double (&c)[NR], int r, double& o
 
 template <int NJ, int NR>
 __device__ __forceinline__ int lu_project(const double* __restrict__ rec, double* __restrict__ W, int ldw, double* __restrict__ sF, int* __restrict__ sPc, double* __restrict__ sIp,
-                                          int lane, int n_open) {
+                                          int lane, int n_open, unsigned zrows, double gain) {
   using D = Dims<NJ>;
-  constexpr int NXA = D::NXA, NU = D::NU, NCOLS = NJ + NXA + 1, SD = NR < NJ ? NR : NJ;
+  // columns: Dv (NJ) | Cv (NXA active state columns) | ev | C[:, base height] = gain on the z rows (zero, and skipped, without positionErrorGain)
+  constexpr int NXA = D::NXA, NU = D::NU, NCOLS = NJ + NXA + 2, SD = NR < NJ ? NR : NJ;
   constexpr bool TWO = NCOLS > 32;
   static_assert(NCOLS <= 64 && NR % 2 == 0 && NR <= D::MAXROWS, "column / row capacity of the in-warp elimination");
   double c0[NR], c1[TWO ? NR : 1];
@@ -90,16 +91,16 @@ __device__ __forceinline__ int lu_project(const double* __restrict__ rec, double
     const int j = lane;
     const double* src = j < NJ ? rec + D::R_DV + j : (j < NJ + NXA ? rec + D::R_CV + (j - NJ) : rec + D::R_EV);
     const int stride = j < NJ ? NJ : (j < NJ + NXA ? NXA : 1);
-    const bool on = j < NCOLS;
+    const bool on = j <= NJ + NXA, z8 = j == NJ + NXA + 1;
 #pragma unroll
-    for (int i = 0; i < NR; ++i) c0[i] = on ? src[i * stride] : 0.0;
+    for (int i = 0; i < NR; ++i) c0[i] = on ? src[i * stride] : ((z8 && ((zrows >> i) & 1u)) ? gain : 0.0);
     if constexpr (TWO) {
       const int j2 = lane + 32;
       const double* src2 = j2 < NJ + NXA ? rec + D::R_CV + (j2 - NJ) : rec + D::R_EV;
       const int stride2 = j2 < NJ + NXA ? NXA : 1;
-      const bool on2 = j2 < NCOLS;
+      const bool on2 = j2 <= NJ + NXA, z82 = j2 == NJ + NXA + 1;
 #pragma unroll
-      for (int i = 0; i < NR; ++i) c1[i] = on2 ? src2[i * stride2] : 0.0;
+      for (int i = 0; i < NR; ++i) c1[i] = on2 ? src2[i * stride2] : ((z82 && ((zrows >> i) & 1u)) ? gain : 0.0);
     }
   }
   if (lane < NR) sPc[lane] = -1;
@@ -165,7 +166,7 @@ __device__ __forceinline__ int lu_project(const double* __restrict__ rec, double
   auto wcol = [&](int j) {
     if (j < NJ) { const int w = 24 + __popc(free_mask & ((1u << j) - 1u)); return (used || w >= 32) ? -1 : w; }
     if (j < NJ + NXA) { const int c = j - NJ; return c < 6 ? c : c + 3; }
-    return j == NJ + NXA ? 6 : -1;
+    return j == NJ + NXA ? 6 : (j == NJ + NXA + 1 ? 8 : -1);
   };
   const int wl0 = wcol(lane);
 #pragma unroll
@@ -251,11 +252,13 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
       if (lane < 16) sMisc[warp][lane] = trj;
     }
     const int n_open = 4 - 2 * (int(st0) + int(st1));
+    // z rows of the raw stack (contact 0..3: closed -> third of its three rows, open -> its single row): where positionErrorGain enters C[:, base height]
+    unsigned zrows; { const unsigned z0 = st0 ? 0x24u : 0x3u; const int n0 = st0 ? 6 : 2; zrows = z0 | ((st1 ? 0x24u : 0x3u) << n0); }
     int rank;
     switch (r) {   // raw velocity rows: 3 per closed contact, 1 per open contact
-      case 4: rank = lu_project<NJ, 4>(rec, &W[0][0], LDW, sBeta[warp], sPcl[warp], sIpv[warp], lane, n_open); break;
-      case 8: rank = lu_project<NJ, 8>(rec, &W[0][0], LDW, sBeta[warp], sPcl[warp], sIpv[warp], lane, n_open); break;
-      default: rank = lu_project<NJ, 12>(rec, &W[0][0], LDW, sBeta[warp], sPcl[warp], sIpv[warp], lane, n_open); break;
+      case 4: rank = lu_project<NJ, 4>(rec, &W[0][0], LDW, sBeta[warp], sPcl[warp], sIpv[warp], lane, n_open, zrows, M.gain); break;
+      case 8: rank = lu_project<NJ, 8>(rec, &W[0][0], LDW, sBeta[warp], sPcl[warp], sIpv[warp], lane, n_open, zrows, M.gain); break;
+      default: rank = lu_project<NJ, 12>(rec, &W[0][0], LDW, sBeta[warp], sPcl[warp], sIpv[warp], lane, n_open, zrows, M.gain); break;
     }
     const int expect = (st0 ? 5 : 2) + (st1 ? 5 : 2);
     anomaly = rank < (expect < NJ ? expect : NJ);
@@ -268,6 +271,7 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
     if (is_x) { for (int i = 0; i < NJ; ++i) out[D::P_PX + i * NXA + gc] = y[i]; }
     else if (is_aff) { for (int i = 0; i < NJ; ++i) out[D::P_PE + i] = y[i]; }
     else if (lane >= 24) { for (int i = 0; i < NJ; ++i) out[D::P_N + i * 8 + lane - 24] = y[i]; }   // columns beyond mj are zero
+    else if (lane == 8) { for (int i = 0; i < NJ; ++i) out[D::P_PX8 + i] = y[i]; }                  // zero without positionErrorGain
   } else {
   double (*Mt)[12] = sM[warp]; double (*V)[NJ] = sV[warp]; double* beta = sBeta[warp]; double* rinv = sBeta[warp] + 10;
   {   // stage Dv^T, [Cv | ev] and B_d rows 3..11: all global loads are issued before the first shared-memory store (fixed trip counts;
@@ -372,6 +376,9 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
   } else if (lane >= 24) {
 #pragma unroll
     for (int i = 0; i < NJ; ++i) out[D::P_N + i * 8 + lane - 24] = 0.0;   // unused null-space columns: never leave stale data behind
+  } else if (lane == 8) {
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) out[D::P_PX8 + i] = 0.0;
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) W[i][lane] = (i < NJ) ? y[i < NJ ? i : 0] : 0.0;   // idle lanes hold y = 0
@@ -407,7 +414,7 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
     sMisc[warp][16 + lane] = open_corr;
   }
   // ---- element-wise parts (lane = column of W, values in y[]; done first so that y[] is dead during the tile products)
-  if (is_x) {
+  if (is_x || lane == 8) {   // lane 8: the base-height column (zero without positionErrorGain)
 #pragma unroll
     for (int l = 0; l < NJ; ++l) so[S::S_AB + (12 + l) * LDA + lane] = dt * y[l] + ((12 + l == lane) ? 1.0 : 0.0);   // At rows 12..: I + dt Pxj
   } else if (is_aff) {
@@ -493,7 +500,7 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
         for (int sl = 0; sl < 2; ++sl) dmma884(c0, c1, a[kb][sl][mt], Z[nt][kb][sl]);
       const int R = 8 * mt + g, C0 = 8 * nt + 2 * q;
       if (mt < 3 && nt < 3) {          // Qt tile (R, C0 .. C0+1): row / column 6 carry the affine terms, the diagonal gets dt Q + dq
-        if (nt == 0 && q == 3 && R < NX && R != 6) so[S::S_Q + R] = rec[D::R_Q + R] + ((R == 7 || R == 8) ? 0.0 : c0);   // qt = q + Px^T t1
+        if (nt == 0 && q == 3 && R < NX && R != 6) so[S::S_Q + R] = rec[D::R_Q + R] + ((R == 7) ? 0.0 : c0);   // qt = q + Px^T t1 (row 8: non-zero only with positionErrorGain)
         double v0 = (R == 6 || C0 == 6) ? 0.0 : c0, v1 = (R == 6) ? 0.0 : c1;
         if (R == C0 && R < NX) v0 += dt * sQd[R] + dq;
         if (R == C0 + 1 && R < NX) v1 += dt * sQd[R] + dq;
@@ -563,8 +570,8 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
         const int sr_ = 3 + rr;
         if (nt < 3) {     // At row 3 + rr, state columns C0, C0 + 1 (columns 6..8: identity entries; column 6 of the product is bt)
           if (C0 == 6) so[S::S_B + sr_] = c0;
-          const double v0 = ((C0 >= 6 && C0 <= 8) ? 0.0 : c0) + ((sr_ == C0) ? 1.0 : 0.0);
-          const double v1 = ((C0 + 1 >= 6 && C0 + 1 <= 8) ? 0.0 : c1) + ((sr_ == C0 + 1) ? 1.0 : 0.0);
+          const double v0 = ((C0 == 6) ? 0.0 : c0) + ((sr_ == C0) ? 1.0 : 0.0);   // column 6 carries bt; column 8 (base height) is zero without positionErrorGain
+          const double v1 = ((C0 + 1 == 7) ? 0.0 : c1) + ((sr_ == C0 + 1) ? 1.0 : 0.0);
           *reinterpret_cast<double2*>(so + S::S_AB + sr_ * LDA + C0) = make_double2(v0, v1);
         } else {          // Bt row 3 + rr, reduced columns 2q, 2q + 1: null-space columns, then closed-contact force columns, then zero
           double v[2] = {c0, c1};
@@ -576,7 +583,7 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
     }
   }
   // qt of the base-position rows and the rows the tiles do not reach
-  if (lane >= 6 && lane < 9) so[S::S_Q + lane] = rec[D::R_Q + lane];
+  if (lane == 6) so[S::S_Q + 6] = rec[D::R_Q + 6];
 }
 
 }  // namespace bmpc

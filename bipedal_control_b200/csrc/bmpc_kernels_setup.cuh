@@ -71,14 +71,16 @@ __global__ void k_time_grid(Dev d) {
 }
 
 // ------------------------------------------------------------------------------------------------ K0b: per-node references + warm start
-// swing height velocity of leg `leg` at time t (foot_planner/SwingTrajectoryPlanner.cpp:50-118, SplineCpg.cpp:38-60, CubicSpline.cpp:38-75)
-__device__ inline double swing_zvel(const double* ev, const int* modes, int ne, int leg, double t, int* status) {
+// swing height reference of leg `leg` at time t: velocity (returned) and position (*zpos)
+// (foot_planner/SwingTrajectoryPlanner.cpp:50-118, SplineCpg.cpp:38-60, CubicSpline.cpp:38-75; the position enters only with positionErrorGain != 0)
+__device__ inline double swing_zref(const double* ev, const int* modes, int ne, int leg, double t, int* status, double* zpos) {
   const int np = ne + 1;
   const int p = lower_bound_d(ev, ne, t);
   int start = -1;
   for (int ip = p - 1; ip >= 0; --ip) if (leg_in_stance(modes[ip], leg)) { start = ip; break; }
   int fin = np - 1;
   for (int ip = p + 1; ip < np; ++ip) if (leg_in_stance(modes[ip], leg)) { fin = ip - 1; break; }
+  *zpos = 0.0;
   if (start < 0 || fin >= np - 1) { atomicOr(status, 4); return 0.0; }
   const double ts = ev[start], tf = ev[fin];
   const double scaling = fmin(1.0, (tf - ts) / c_model.swing_time_scale);
@@ -89,6 +91,7 @@ __device__ inline double swing_zvel(const double* ev, const int* modes, int ne, 
   const double dts = t_b - t_a, dp = p_b - p_a, dv = v_b - v_a;
   const double c1 = v_a * dts, c2 = -(3.0 * v_a + dv) * dts + 3.0 * dp, c3 = (2.0 * v_a + dv) * dts - 2.0 * dp;
   const double tn = (t - t_a) / dts;
+  *zpos = ((c3 * tn + c2) * tn + c1) * tn + p_a;
   return (3.0 * c3 * tn * tn + 2.0 * c2 * tn + c1) / dts;
 }
 
@@ -123,7 +126,11 @@ __global__ void __launch_bounds__(256) k_node_setup(Dev d) {
       const double t = stt[k];
       mode = modes[lower_bound_d(ev, ne, t)];
       if (lane < NX) d.xref[(nb + k) * NX + lane] = interp_lane(d.tgt_t + (size_t)b * d.TP, d.tgt_x + (size_t)b * d.TP * NX, d.npts, NX, t, lane);
-      if (lane < 2) d.zref[(nb + k) * 2 + lane] = leg_in_stance(mode, lane) ? 0.0 : swing_zvel(ev, modes, ne, lane, t, &d.status[b]);
+      if (lane < 2) {   // per leg: reference height velocity, and position (used only with positionErrorGain != 0); terrain height 0 in stance
+        double zp = 0.0;
+        const double zv = leg_in_stance(mode, lane) ? 0.0 : swing_zref(ev, modes, ne, lane, t, &d.status[b], &zp);
+        d.zref[(nb + k) * 4 + lane] = zv; d.zref[(nb + k) * 4 + 2 + lane] = zp;
+      }
     }
     if (lane == 0) d.st_mode[nb + k] = mode;
   }

@@ -55,7 +55,6 @@ void finalize_model(HostModel& m) {
   }
   for (int c = 0; c < NCON; ++c)
     if (m.contact_parent[c] != (c / 2) * nl + nl - 1) throw std::invalid_argument("[bmpc] contact points must be attached to the last link of each leg (two per foot)");
-  if (m.dev.gain != 0.0) throw std::invalid_argument("[bmpc] positionErrorGain != 0 is not supported by the CUDA path yet");
   m.nx = 12 + nj; m.nu = 12 + nj;
   if ((int)m.initial_state.size() != m.nx) throw std::invalid_argument("[bmpc] initial_state must have 12 + nj entries");
   if ((int)m.default_joint_state.size() != nj) throw std::invalid_argument("[bmpc] default_joint_state must have nj entries");

@@ -676,3 +676,38 @@ def test_native_policy_exchange_single_rank():
     finally:
         if own_pg:
             dist.destroy_process_group()
+
+
+def test_position_error_gain_variant(tmp_path):
+    """positionErrorGain != 0 (legged_hunter_config/config/task/task.info:12 uses 20.0; BipedalRobotInterface.cpp:350-359,
+    BipedalRobotPreComputation.cpp:71-80): the z rows of the zero-velocity / normal-velocity constraints also see gain * (p_z - z_ref), which puts
+    the base height into the constraint Jacobian.  H1 with the gain switched on, trot with swing phases, against the oracle."""
+    import helpers
+    from oracle.pyoracle import Oracle
+    G = _gpu()
+    model = str(tmp_path / "h1_gain20.model")
+    txt = open(MODEL).read()
+    assert "position_error_gain d 1 0.0" in txt
+    open(model, "w").write(txt.replace("position_error_gain d 1 0.0", "position_error_gain d 1 20.0", 1))
+    m = _mdl()
+    o = Oracle(model)
+    x0 = o.initial_state().copy()
+    x0[8] += 0.01; x0[0] = 0.1; x0[13] += 0.05
+    et, ms = helpers.config2(22, x0, None, None)
+    tt, ts = helpers.cmd_vel_target(x0, 0.0, (0.3, 0.05, 0, 0.1), 1.0, m["com_height"], m["default_joint_state"])
+    o.set_dt_horizon(0.01, 0.6); o.set_mode_schedule(et, ms); o.set_target(tt, ts)
+    g = G(3, model_file=model, dt=0.01, time_horizon=0.6)
+    g.setCurrentObservation(0.0, x0); g.setTargetTrajectories(tt, ts); g.setModeSchedule(et, ms)
+    for tick in range(3):
+        o.run(0.0, x0); g.advanceMpc()
+        assert not (g.getStatus() & ~16).any()
+        _compare_tick(g, o, 1, rel=1e-7 if tick else REL)
+    # the gain really changes the problem: base-height column of the gains differs from the gain-free solve
+    g0 = G(1, model_file=MODEL, dt=0.01, time_horizon=0.6)
+    g0.setCurrentObservation(0.0, x0); g0.setTargetTrajectories(tt, ts); g0.setModeSchedule(et, ms); g0.advanceMpc()
+    g.reset(); g.advanceMpc()
+    assert np.abs(g.getPolicy(0, 1)["K"][0][:, :, 8] - g0.getPolicy(0, 1)["K"][0][:, :, 8]).max() > 1e-3
+    from bipedal_control_b200 import BmpcError
+    with pytest.raises(BmpcError):
+        g.setOption("projection_mode", 0)     # the Moore-Penrose option does not carry the position rows
+    g.close(); g0.close()
