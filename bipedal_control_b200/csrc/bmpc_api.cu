@@ -194,7 +194,7 @@ void tick(bmpc_handle* h) {
   CK(cudaMemcpyAsync(h->s_evt[w], h->d_ev_t, sizeof(double) * B * h->ME, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(h->s_evm[w], h->d_ev_mode, sizeof(int) * B * (h->ME + 1), cudaMemcpyDeviceToDevice, st));
   k_time_grid<<<(B + 127) / 128, 128, 0, st>>>(d); ++h->launches;
-  k_node_setup<NJ><<<(nodes + 7) / 8, 256, 0, st>>>(d); ++h->launches;   // one warp per node
+  k_node_setup<NJ><<<(nodes + 127) / 128, 128, 0, st>>>(d); ++h->launches;
   mark(1);
   for (int iter = 0; iter < h->sqp_iterations; ++iter) {
     constexpr int G = LqPackSmem<NJ>::G;

@@ -95,21 +95,13 @@ __device__ inline double swing_zref(const double* ev, const int* modes, int ne, 
   return (3.0 * c3 * tn * tn + 2.0 * c2 * tn + c1) / dts;
 }
 
-// linear interpolation of a trajectory at time t, one component per lane (LinearInterpolation::interpolate [UPSTREAM])
-__device__ __forceinline__ double interp_lane(const double* ta, const double* data, int n, int dim, double t, int lane) {
-  if (n <= 1) return data[lane];
-  int idx; double al; time_segment(ta, n, t, idx, al);
-  const double* a = data + (size_t)idx * dim;
-  return al * a[lane] + (1.0 - al) * a[dim + lane];
-}
-
-// one WARP per node, lane = state / input component: the scalar logic (mode lookup, swing reference, which source the initial guess comes from)
-// is evaluated redundantly by the lanes, the 22-wide reads and writes are coalesced
+// one thread per node (a warp-per-node variant with coalesced 22-wide accesses was 2.7x slower: the kernel is bound by the scalar lookup
+// chains, which every lane of a warp would repeat)
 template <int NJ>
-__global__ void __launch_bounds__(256) k_node_setup(Dev d) {
+__global__ void k_node_setup(Dev d) {
   constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU;
-  const int gw = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  const int b = gw / d.NS, k = gw % d.NS;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = gid / d.NS, k = gid % d.NS;
   if (b >= d.B) return;
   const int n = d.n_nodes[b];
   if (k >= n) return;
@@ -125,14 +117,14 @@ __global__ void __launch_bounds__(256) k_node_setup(Dev d) {
     if (nev[k] != 1) {
       const double t = stt[k];
       mode = modes[lower_bound_d(ev, ne, t)];
-      if (lane < NX) d.xref[(nb + k) * NX + lane] = interp_lane(d.tgt_t + (size_t)b * d.TP, d.tgt_x + (size_t)b * d.TP * NX, d.npts, NX, t, lane);
-      if (lane < 2) {   // per leg: reference height velocity, and position (used only with positionErrorGain != 0); terrain height 0 in stance
+      interp_vec(d.tgt_t + (size_t)b * d.TP, d.tgt_x + (size_t)b * d.TP * NX, d.npts, NX, t, d.xref + (nb + k) * NX);
+      for (int leg = 0; leg < 2; ++leg) {   // per leg: reference height velocity, and position (used only with positionErrorGain != 0); terrain height 0 in stance
         double zp = 0.0;
-        const double zv = leg_in_stance(mode, lane) ? 0.0 : swing_zref(ev, modes, ne, lane, t, &d.status[b], &zp);
-        d.zref[(nb + k) * 4 + lane] = zv; d.zref[(nb + k) * 4 + 2 + lane] = zp;
+        const double zv = leg_in_stance(mode, leg) ? 0.0 : swing_zref(ev, modes, ne, leg, t, &d.status[b], &zp);
+        d.zref[(nb + k) * 4 + leg] = zv; d.zref[(nb + k) * 4 + 2 + leg] = zp;
       }
     }
-    if (lane == 0) d.st_mode[nb + k] = mode;
+    d.st_mode[nb + k] = mode;
   }
   // ---- initial guess: [UPSTREAM] multiple_shooting::initializeStateInputTrajectories
   const int pn = d.p_n ? d.p_n[b] : 0;
@@ -147,26 +139,27 @@ __global__ void __launch_bounds__(256) k_node_setup(Dev d) {
   // state of node k
   int j = k;
   while (j > 0 && interval_uses_initializer(j - 1)) --j;
-  if (lane < NX) {
-    double xv;
-    if (j == 0) {
-      const double tinit = nev[0] == 2 ? nt[0] + WEAK_EPS : nt[0];
-      xv = (tinit < stateTill) ? interp_lane(pt, px, pn, NX, tinit, lane) : d.x0[(size_t)b * NX + lane];
-    } else xv = interp_lane(pt, px, pn, NX, stt[j - 1] + std_[j - 1], lane);
-    d.s_x[(nb + k) * NX + lane] = xv;
+  double* xo = d.s_x + (nb + k) * NX;
+  if (j == 0) {
+    const double tinit = nev[0] == 2 ? nt[0] + WEAK_EPS : nt[0];
+    if (tinit < stateTill) interp_vec(pt, px, pn, NX, tinit, xo);
+    else for (int i = 0; i < NX; ++i) xo[i] = d.x0[(size_t)b * NX + i];
+  } else {
+    interp_vec(pt, px, pn, NX, stt[j - 1] + std_[j - 1], xo);
   }
   // input of stage k
-  if (k < N && lane < NU) {
-    double uv = 0.0;
-    if (nev[k] == 1) uv = 0.0;
+  if (k < N) {
+    double* uo = d.s_u + (nb + k) * NU;
+    if (nev[k] == 1) { for (int i = 0; i < NU; ++i) uo[i] = 0.0; }
     else if (interval_uses_initializer(k)) {   // initialization/BipedalRobotInitializer.cpp:56-63 + common/utils.h:63-77
       const int mode = modes[lower_bound_d(ev, ne, stt[k])];
       const bool s0 = leg_in_stance(mode, 0), s1 = leg_in_stance(mode, 1);
       const int ns = 2 * (int(s0) + int(s1));
       const double fz = ns > 0 ? c_model.total_mass * 9.81 / ns : 0.0;
-      if ((s0 && (lane == 2 || lane == 5)) || (s1 && (lane == 8 || lane == 11))) uv = fz;
-    } else uv = interp_lane(pt, pu, pn, NU, stt[k], lane);
-    d.s_u[(nb + k) * NU + lane] = uv;
+      for (int i = 0; i < NU; ++i) uo[i] = 0.0;
+      if (s0) { uo[2] = fz; uo[5] = fz; }
+      if (s1) { uo[8] = fz; uo[11] = fz; }
+    } else interp_vec(pt, pu, pn, NU, stt[k], uo);
   }
 }
 
