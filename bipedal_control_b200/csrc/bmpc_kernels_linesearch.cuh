@@ -69,13 +69,14 @@ __device__ __forceinline__ void stage_trial(const Dev& d, size_t nb, int k, doub
 #pragma unroll
   for (int j = 0; j < NJ; ++j) { const double e = qj[j] + dt * qd[j] - (gx[NX + 12 + j] + al * gdx[NX + 12 + j]); sdef += e * e; }
   double k1[12], k2[12]; v3 vc[NCON], vc2[NCON], pc[NCON];
-  model_values<NJ>(xb, qj, uf, qd, k1, vc, pc);
+  const bool pg = M.gain != 0.0;   // positionErrorGain: the z rows also see gain * (p_z - z_ref)
+  model_values<NJ>(xb, qj, uf, qd, k1, vc, pg ? pc : nullptr);
   double peq = 0.0;
 #pragma unroll
   for (int c = 0; c < NCON; ++c) {   // ZeroVelocityConstraintCppAd / NormalVelocityConstraintCppAd + ZeroForceConstraint, incl. positionErrorGain
-    if ((c / 2 == 0) ? st0 : st1) { const double ez = vc[c].z + M.gain * pc[c].z; peq += vc[c].x * vc[c].x + vc[c].y * vc[c].y + ez * ez; }
+    if ((c / 2 == 0) ? st0 : st1) { const double ez = vc[c].z + (pg ? M.gain * pc[c].z : 0.0); peq += vc[c].x * vc[c].x + vc[c].y * vc[c].y + ez * ez; }
     else {
-      const double ev = vc[c].z - d.zref[(nb + k) * 4 + c / 2] + M.gain * (pc[c].z - d.zref[(nb + k) * 4 + 2 + c / 2]);
+      const double ev = vc[c].z - d.zref[(nb + k) * 4 + c / 2] + (pg ? M.gain * (pc[c].z - d.zref[(nb + k) * 4 + 2 + c / 2]) : 0.0);
       peq += ev * ev + uf[3 * c] * uf[3 * c] + uf[3 * c + 1] * uf[3 * c + 1] + uf[3 * c + 2] * uf[3 * c + 2];
     }
   }

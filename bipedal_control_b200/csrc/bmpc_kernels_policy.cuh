@@ -25,6 +25,18 @@ __device__ __forceinline__ double stage_At_aug(const double* __restrict__ sr, in
   return c == NX ? sr[S::S_B + r] : 0.0;
 }
 
+// z <- L^-T z for the leading M x M block (the record stores 1 / L[i][i] on the diagonal); rows >= M are left as they are (zero)
+template <int M, int MP>
+__device__ __forceinline__ void back_substitute(double (&z)[MP], const double (&L)[MP][MP + 1]) {
+#pragma unroll
+  for (int i = M - 1; i >= 0; --i) {
+    double a = z[i];
+#pragma unroll
+    for (int l = i + 1; l < M; ++l) a -= L[l][i] * z[l];
+    z[i] = a * L[i][i];
+  }
+}
+
 template <int NJ>
 __global__ void __launch_bounds__(128, 4) k_policy_expand(Dev d) {
   using D = Dims<NJ>; using R = RDims<NJ>; using S = SDims<NJ>; using PS = PolSmem<NJ>;
@@ -88,13 +100,15 @@ __global__ void __launch_bounds__(128, 4) k_policy_expand(Dev d) {
 #pragma unroll
   for (int i = 0; i < (NJ * 8 + 31) / 32; ++i) if (lane + 32 * i < NJ * 8) sm.Nn[lane + 32 * i] = nn[i];
   __syncwarp();
-  // ---- back substitution Kt = -L^-T Y (lane c < NX: column c; lane NX: kt from yg)
-#pragma unroll
-  for (int i = MP - 1; i >= 0; --i) {
-    double a = z[i];
-#pragma unroll
-    for (int l = i + 1; l < MP; ++l) a -= sm.L[l][i] * z[l];
-    z[i] = (i < m) ? a * sm.L[i][i] : 0.0;   // the record stores 1 / L[i][i] on the diagonal
+  // ---- back substitution Kt = -L^-T Y (lane c < NX: column c; lane NX: kt from yg); trip counts fixed by the reduced input dimension m
+  switch (m) {   // H1: 6 / 9 / 12 (FLY / single stance / double stance), G1: 8 / 11 / 14
+    case 6: back_substitute<6, MP>(z, sm.L); break;
+    case 9: back_substitute<9, MP>(z, sm.L); break;
+    case 12: back_substitute<12, MP>(z, sm.L); break;
+    case 8: back_substitute<8, MP>(z, sm.L); break;
+    case 11: back_substitute<11, MP>(z, sm.L); break;
+    case 14: back_substitute<14, MP>(z, sm.L); break;
+    default: back_substitute<MP, MP>(z, sm.L); break;   // rows >= m of z and of L (incl. the reciprocal pivots) were loaded as zero
   }
 #pragma unroll
   for (int i = 0; i < MP; ++i) { z[i] = -z[i]; if (lane < LDK) sm.Kt[i * LDK + lane] = z[i]; }
@@ -102,8 +116,10 @@ __global__ void __launch_bounds__(128, 4) k_policy_expand(Dev d) {
   // ---- [Phi | phi] = [At | bt] + Bt [Kt | kt] on the FP64 tensor cores: 9 tiles x 4 k-steps, results stored straight from the fragments
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk)
+    if (4 * kk < m) {   // rows >= m of [Kt | kt] are zero (warp-uniform skip)
 #pragma unroll
-    for (int t = 0; t < NTILES; ++t) dmma884(c0[t], c1[t], af[t / NT][kk], sm.Kt[(4 * kk + lc) * LDK + 8 * (t % NT) + lr]);
+      for (int t = 0; t < NTILES; ++t) dmma884(c0[t], c1[t], af[t / NT][kk], sm.Kt[(4 * kk + lc) * LDK + 8 * (t % NT) + lr]);
+    }
 #pragma unroll
   for (int t = 0; t < NTILES; ++t) {
     const int r = 8 * (t / NT) + lr, c = 8 * (t % NT) + 2 * lc;
@@ -136,7 +152,11 @@ __global__ void __launch_bounds__(128, 4) k_policy_expand(Dev d) {
     const int xc = xcol(lane);
     double pxv[NJ];
 #pragma unroll
-    for (int l = 0; l < NJ; ++l) pxv[l] = (lane < NX) ? (xact ? prj[D::P_PX + l * NXA + xc] : (lane == 8 ? prj[D::P_PX8 + l] : 0.0)) : prj[D::P_PE + l];
+    for (int l = 0; l < NJ; ++l) pxv[l] = (lane < NX) ? (xact ? prj[D::P_PX + l * NXA + xc] : 0.0) : prj[D::P_PE + l];
+    if (c_model.gain != 0.0 && lane == 8) {   // positionErrorGain: the base-height column of Pxj is not structurally zero
+#pragma unroll
+      for (int l = 0; l < NJ; ++l) pxv[l] = prj[D::P_PX8 + l];
+    }
 #pragma unroll
     for (int l = 0; l < NJ; ++l) {
       double a = pxv[l];

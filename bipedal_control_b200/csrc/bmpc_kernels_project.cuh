@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
     if (is_x) { for (int i = 0; i < NJ; ++i) out[D::P_PX + i * NXA + gc] = y[i]; }
     else if (is_aff) { for (int i = 0; i < NJ; ++i) out[D::P_PE + i] = y[i]; }
     else if (lane >= 24) { for (int i = 0; i < NJ; ++i) out[D::P_N + i * 8 + lane - 24] = y[i]; }   // columns beyond mj are zero
-    else if (lane == 8) { for (int i = 0; i < NJ; ++i) out[D::P_PX8 + i] = y[i]; }                  // zero without positionErrorGain
+    else if (lane == 8 && M.gain != 0.0) { for (int i = 0; i < NJ; ++i) out[D::P_PX8 + i] = y[i]; }   // read only with positionErrorGain
   } else {
   double (*Mt)[12] = sM[warp]; double (*V)[NJ] = sV[warp]; double* beta = sBeta[warp]; double* rinv = sBeta[warp] + 10;
   {   // stage Dv^T, [Cv | ev] and B_d rows 3..11: all global loads are issued before the first shared-memory store (fixed trip counts;
@@ -376,9 +376,6 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
   } else if (lane >= 24) {
 #pragma unroll
     for (int i = 0; i < NJ; ++i) out[D::P_N + i * 8 + lane - 24] = 0.0;   // unused null-space columns: never leave stale data behind
-  } else if (lane == 8) {
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) out[D::P_PX8 + i] = 0.0;
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) W[i][lane] = (i < NJ) ? y[i < NJ ? i : 0] : 0.0;   // idle lanes hold y = 0
@@ -414,7 +411,7 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
     sMisc[warp][16 + lane] = open_corr;
   }
   // ---- element-wise parts (lane = column of W, values in y[]; done first so that y[] is dead during the tile products)
-  if (is_x || lane == 8) {   // lane 8: the base-height column (zero without positionErrorGain)
+  if (is_x || (lane == 8 && M.gain != 0.0)) {   // lane 8: the base-height column (structurally zero, and static, without positionErrorGain)
 #pragma unroll
     for (int l = 0; l < NJ; ++l) so[S::S_AB + (12 + l) * LDA + lane] = dt * y[l] + ((12 + l == lane) ? 1.0 : 0.0);   // At rows 12..: I + dt Pxj
   } else if (is_aff) {
