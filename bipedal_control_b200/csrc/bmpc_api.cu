@@ -160,7 +160,7 @@ void set_kernel_attributes() {
   CK(cudaFuncSetAttribute(k_lq_pack<NJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LqPackSmem<NJ>)));
   CK(cudaFuncSetAttribute(k_lq_pack<NJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LqPackSmem<NJ>)));
   CK(cudaFuncSetAttribute(k_policy_expand<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(PolSmem<NJ>))));
-  CK(cudaFuncSetAttribute(k_forward<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(FwdSmem<NJ>))));
+  CK(cudaFuncSetAttribute(k_forward<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FWD_WPC * sizeof(FwdSmem<NJ>))));
 }
 
 // the model image this handle's kernels read (see g_image_mtx)
@@ -211,7 +211,7 @@ void tick(bmpc_handle* h) {
     if (iter == 0) mark(4);
     k_policy_expand<NJ><<<(nodes + 3) / 4, 128, 4 * sizeof(PolSmem<NJ>), st>>>(d); ++h->launches;
     if (iter == 0) mark(5);
-    k_forward<NJ><<<(B + 3) / 4, 128, 4 * sizeof(FwdSmem<NJ>), st>>>(d); ++h->launches;
+    k_forward<NJ><<<(B + FWD_WPC - 1) / FWD_WPC, 32 * FWD_WPC, FWD_WPC * sizeof(FwdSmem<NJ>), st>>>(d); ++h->launches;
     if (iter == 0) mark(6);
     // filter line search: device-side backtracking loop, one CTA per instance; then the accepted step
     k_linesearch<NJ><<<B, LS_THREADS, 0, st>>>(d); ++h->launches;

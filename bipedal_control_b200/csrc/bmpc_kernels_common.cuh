@@ -24,6 +24,13 @@ constexpr int CNT_TRIALS = 0, CNT_MAXTRIALS = 1, CNT_FAIL = 2, CNT_STATUS = 3, C
 #define RIC_WPC 4   // independent instances (warps) per CTA of k_riccati_warp
 #endif
 
+#ifndef FWD_WPC
+#define FWD_WPC 7      // independent instances (warps) per CTA of k_forward
+#endif
+#ifndef FWD_BLOCKS
+#define FWD_BLOCKS 2
+#endif
+
 template <int NJ> struct RDims;
 template <int NJ> struct SDims;
 

@@ -56,8 +56,8 @@ __device__ __forceinline__ bool chol_forward(double (&gc)[MP], double (&hc)[MP],
 template <int NJ>
 struct RDims {
   static constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU, MP = 16;
-  // written by k_riccati: Y[MP][NX], yg[MP], L[MP][MP];  written by k_policy_expand: kappa, Phi, phi, ghat, misc
-  static constexpr int K_Y = 0, K_YG = K_Y + MP * NX, K_L = K_YG + MP, K_KAP = K_L + MP * MP, K_PHI = K_KAP + NU, K_SPHI = K_PHI + NX * NX, K_G = K_SPHI + NX,
+  // written by k_riccati: Y[MP][NX], yg[MP], L[MP][MP];  written by k_policy_expand: kappa, ghat, misc (armijo term, event flag)
+  static constexpr int K_Y = 0, K_YG = K_Y + MP * NX, K_L = K_YG + MP, K_KAP = K_L + MP * MP, K_G = K_KAP + NU,
                        K_MISC = K_G + NX, KREC = ((K_MISC + 2 + 3) / 4) * 4;
 };
 
