@@ -31,8 +31,24 @@ constexpr int CNT_TRIALS = 0, CNT_MAXTRIALS = 1, CNT_FAIL = 2, CNT_STATUS = 3, C
 #define FWD_BLOCKS 2
 #endif
 
+#ifndef PF_AHEAD
+#define PF_AHEAD 296   // warp-per-stage kernels first ask L2 for the whole input record of the stage PF_AHEAD warps ahead (same wave): the dependent rounds of cold DRAM loads at the start of a warp then hit L2
+#endif
+
 template <int NJ> struct RDims;
 template <int NJ> struct SDims;
+
+// L2 prefetch of a contiguous record (16-byte aligned address, size a multiple of 16 bytes), one lane issues it.  The warp-per-stage kernels are
+// latency bound by dependent rounds of cold DRAM loads at the start of every warp; CTAs are dispatched in blockIdx order, so the warp that starts
+// one wave later finds its records in the 126 MB L2 instead.
+__device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p) : "memory"); }
+#ifndef PF_AHEAD_LQ
+#define PF_AHEAD_LQ 296
+#endif
 
 struct Dev {
   int B, NS, ME, TP, npts;   // NS: node slots per instance = nominal grid + 1 + max_event_nodes

@@ -353,6 +353,20 @@ __global__ void __launch_bounds__(128, LQ_PAIR_BLOCKS) k_lq_pack(Dev d) {
   const int gw = blockIdx.x * WPB + warp;
   const int b = gw / NP, k0 = G * (gw % NP);
   if (b >= d.B) return;
+  if (PF_AHEAD_LQ >= 0 && lane < 8) {   // inputs of the warp one wave ahead -> L2
+    const int ga = gw + PF_AHEAD_LQ, ba = ga / NP, ka = G * (ga % NP);
+    if (ba < d.B && ka + G < d.NS) {
+      const size_t na = (size_t)ba * d.NS + ka;
+      if (lane == 0) prefetch_l2(d.s_x + na * NX, (G + 1) * NX * sizeof(double));
+      else if (lane == 1) prefetch_l2(d.s_u + na * NU, G * NU * sizeof(double));
+      else if (lane == 2) prefetch_l2(d.xref + na * NX, G * NX * sizeof(double));
+      else if (lane == 3) prefetch_l2_line(d.zref + na * 4);
+      else if (lane == 4) prefetch_l2_line(d.zref + na * 4 + 4 * G - 1);
+      else if (lane == 5) prefetch_l2_line(d.st_dt + na);
+      else if (lane == 6) prefetch_l2_line(d.st_mode + na);
+      else prefetch_l2_line(d.node_ev + na);
+    }
+  }
   const int N = d.n_nodes[b] - 1;
   if (k0 >= N) return;
   const size_t nb = (size_t)b * d.NS;

@@ -56,7 +56,14 @@ __global__ void __launch_bounds__(128, 4) k_policy_expand(Dev d) {
     return;
   }
   const int m = (int)meta[S::T_M], mj = (int)meta[S::T_MJ], nclosed = (int)meta[S::T_NCLOSED], mode = (int)meta[S::T_MODE];
-  const double dt = meta[S::T_DT];
+  if (PF_AHEAD >= 0 && (size_t)gw + PF_AHEAD < (size_t)d.B * d.NS) {   // inputs of the stage one wave ahead -> L2 (its m is guessed to be this stage's)
+    const size_t ga = (size_t)gw + PF_AHEAD;
+    const int mg = m > 0 ? m : 9;
+    if (lane == 0) prefetch_l2(d.ric + ga * R::KREC + R::K_Y, (unsigned)(mg * NX * sizeof(double)));
+    if (lane == 1) prefetch_l2(d.ric + ga * R::KREC + R::K_YG, (unsigned)((MP + mg * MP) * sizeof(double)));
+    if (lane == 2) prefetch_l2(d.proj + ga * D::PREC, (unsigned)(D::PREC * sizeof(double)));
+    if (lane == 3) prefetch_l2(d.stage + ga * S::SREC + S::S_B, (unsigned)((S::TMA_DOUBLES - S::S_B) * sizeof(double)));
+  }
   const bool st0 = leg_in_stance(mode, 0), st1 = leg_in_stance(mode, 1);
   const double* __restrict__ prj = d.proj + (nb + k) * D::PREC;
   // ---- issue every global load up front (independent: their latency overlaps with the back substitution below)

@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
   const int gw = blockIdx.x * WPB + warp;
   const int b = gw / d.NS, k = gw % d.NS;
   if (b >= d.B) return;
+  if (PF_AHEAD >= 0 && lane == 0 && (size_t)gw + PF_AHEAD < (size_t)d.B * d.NS) prefetch_l2(d.lq + ((size_t)gw + PF_AHEAD) * D::REC, D::REC * sizeof(double));
   const int N = d.n_nodes[b] - 1;
   if (k >= N) return;
   const size_t nb = (size_t)b * d.NS;
