@@ -48,8 +48,10 @@ __device__ __forceinline__ void lq_x_column(const double* __restrict__ bs, const
   using BD = BaseDims<NJ>;
 #pragma unroll
   for (int i = 0; i < 9; ++i) col[i] = 0.0;
-  if (c < 3) col[3 + c] = 1.0;
-  else if (c < 6) {
+  if (c < 3) {   // (no dynamic register-array index: it would push col[] into local memory)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) col[3 + i] = (c == i) ? 1.0 : 0.0;
+  } else if (c < 6) {
     const double* A22i = bs + BD::B_A22I; const double* A12 = bs + BD::B_A12; const int cc = c - 3;
 #pragma unroll
     for (int r = 0; r < 3; ++r) { col[3 + r] = -(A12[3 * r] * A22i[cc] + A12[3 * r + 1] * A22i[3 + cc] + A12[3 * r + 2] * A22i[6 + cc]); col[6 + r] = c_model.total_mass * A22i[3 * r + cc]; }
@@ -128,7 +130,8 @@ __device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k,
     }
     if (lane >= NH + 3 && lane < NXA) {   // d f / d (normalised linear momentum): identity block, both evaluations
       const int c = lane - (NH + 3);
-      a1[3 + c] = 1.0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) a1[3 + i] = (c == i) ? 1.0 : 0.0;   // (no dynamic register-array index: it would push a1[] into local memory)
 #pragma unroll
       for (int r = 0; r < 9; ++r) sA2w[r][c] = (r == 3 + c) ? 1.0 : 0.0;
     }
