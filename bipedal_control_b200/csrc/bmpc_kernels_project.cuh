@@ -78,6 +78,25 @@ __device__ __forceinline__ void pick_row(const double (&c)[NR], int r, double& o
   }
 }
 
+// c[r] = v for a warp-uniform r
+template <int NR>
+__device__ __forceinline__ void put_row(double (&c)[NR], int r, double v) {
+  switch (r) {
+    case 0: c[0] = v; break;
+    case 1: c[1] = v; break;
+    case 2: c[2] = v; break;
+    case 3: c[3] = v; break;
+    case 4: if constexpr (NR > 4) c[4] = v; break;
+    case 5: if constexpr (NR > 5) c[5] = v; break;
+    case 6: if constexpr (NR > 6) c[6] = v; break;
+    case 7: if constexpr (NR > 7) c[7] = v; break;
+    case 8: if constexpr (NR > 8) c[8] = v; break;
+    case 9: if constexpr (NR > 9) c[9] = v; break;
+    case 10: if constexpr (NR > 10) c[10] = v; break;
+    default: if constexpr (NR > 11) c[11] = v; break;
+  }
+}
+
 template <int NJ, int NR>
 __device__ __forceinline__ int lu_project(const double* __restrict__ rec, double* __restrict__ W, int ldw, double* __restrict__ sF, int* __restrict__ sPc, double* __restrict__ sIp,
                                           int lane, int n_open, unsigned zrows, double gain) {
@@ -104,7 +123,10 @@ __device__ __forceinline__ int lu_project(const double* __restrict__ rec, double
     }
   }
   if (lane < NR) sPc[lane] = -1;
-  unsigned rowdone = 0u; bool used = false, stop = false; int rank = 0;
+  // Rows are swapped physically (as Eigen does): after step kk the pivot rows sit in positions 0..kk, so the search runs over the static
+  // range i >= kk.  perm holds the ORIGINAL row number of every position (4 bits each, warp uniform): the tie rule is stated in original order.
+  unsigned long long perm = 0xBA9876543210ull;
+  bool used = false, stop = false; int rank = 0;
   double maxpiv = n_open > 0 ? 1.0 : 0.0;
   const int sdfull = (NR + 3 * n_open) < NU ? (NR + 3 * n_open) : NU;
   const double epsd = 2.220446049250313e-16 * (double)sdfull;
@@ -113,7 +135,7 @@ __device__ __forceinline__ int lu_project(const double* __restrict__ rec, double
     if (!stop) {   // warp uniform
       double best = -1.0;
 #pragma unroll
-      for (int i = 0; i < NR; ++i) { const double a_ = fabs(c0[i]); if (!((rowdone >> i) & 1u) && a_ > best) best = a_; }
+      for (int i = kk; i < NR; ++i) { const double a_ = fabs(c0[i]); if (a_ > best) best = a_; }
       const bool cand = lane < NJ && !used;
       const unsigned long long key = cand ? (unsigned long long)__double_as_longlong(best) : 0ull;
       const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
@@ -122,14 +144,14 @@ __device__ __forceinline__ int lu_project(const double* __restrict__ rec, double
       if ((mhi | mlo) == 0u) stop = true;   // the remaining block is exactly zero (Eigen: m_nonzero_pivots = k)
       else {
         // coefficients within PIVOT_TIE of the maximum are tied (the last pivot of a stance foot's block is an exact tie between two rows that
-        // rounding noise would decide): the first one in (column, row) order wins -- same rule as the oracle's emulation
+        // rounding noise would decide): the first one in (original column, original row) order wins -- same rule as the oracle's emulation
         const double tie = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo)) * (1.0 - 1e-10);
-        int bi = NR;
+        int bo = 16, bi = NR;   // smallest original row number among the tied rows of the own column, and its position
 #pragma unroll
-        for (int i = NR - 1; i >= 0; --i) if (!((rowdone >> i) & 1u) && fabs(c0[i]) >= tie) bi = i;
+        for (int i = kk; i < NR; ++i) { const int o_ = (int)((perm >> (4 * i)) & 15ull); if (fabs(c0[i]) >= tie && o_ < bo) { bo = o_; bi = i; } }
         const unsigned win = __ballot_sync(0xffffffffu, cand && bi < NR);
         const int bl = __ffs(win) - 1;
-        const int prow = __shfl_sync(0xffffffffu, bi, bl);
+        const int prow = __shfl_sync(0xffffffffu, bi, bl);   // position of the pivot row (>= kk)
         // own elements of the pivot row: prow is warp uniform, so a switch (one uniform branch) replaces a chain of selects
         double cp0 = 0.0, cp1 = 0.0;
         pick_row<NR>(c0, prow, cp0);
@@ -139,15 +161,21 @@ __device__ __forceinline__ int lu_project(const double* __restrict__ rec, double
         if (!(ap > epsd * mp)) stop = true;   // below Eigen's rank threshold: with complete pivoting everything that follows is, too
         else {
           maxpiv = mp;
+          // swap positions kk <-> prow
+          put_row<NR>(c0, prow, c0[kk]); c0[kk] = cp0;
+          if constexpr (TWO) { put_row<NR>(c1, prow, c1[kk]); c1[kk] = cp1; }
+          {
+            const unsigned long long ok_ = (perm >> (4 * kk)) & 15ull, op_ = (perm >> (4 * prow)) & 15ull;
+            perm = (perm & ~((15ull << (4 * kk)) | (15ull << (4 * prow)))) | (op_ << (4 * kk)) | (ok_ << (4 * prow));
+          }
           const double ip = 1.0 / p;
           double* F = sF + (kk & 1) * 16;
-          if (lane == bl) {   // multipliers of the pivot column; the pivot row itself is not eliminated (its multiplier is overwritten with 0)
+          if (lane == bl) {   // multipliers of the pivot column; the pivot row itself is not eliminated (multiplier 0)
 #pragma unroll
-            for (int i = 0; i < NR; ++i) F[i] = c0[i] * ip;
-            F[prow] = 0.0;
+            for (int i = 0; i < NR; ++i) F[i] = (i == kk) ? 0.0 : c0[i] * ip;
             used = true;
           }
-          if (lane == 0) { sPc[prow] = bl; sIp[prow] = ip; }
+          if (lane == 0) { sPc[kk] = bl; sIp[kk] = ip; }
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < NR; i += 2) {
@@ -155,7 +183,7 @@ __device__ __forceinline__ int lu_project(const double* __restrict__ rec, double
             c0[i] = fma(-f.x, cp0, c0[i]); c0[i + 1] = fma(-f.y, cp0, c0[i + 1]);
             if constexpr (TWO) { c1[i] = fma(-f.x, cp1, c1[i]); c1[i + 1] = fma(-f.y, cp1, c1[i + 1]); }
           }
-          rowdone |= 1u << prow; ++rank;
+          ++rank;
         }
       }
     }
