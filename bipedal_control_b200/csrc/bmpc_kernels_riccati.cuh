@@ -61,18 +61,39 @@ struct RDims {
                        K_MISC = K_G + NX, KREC = ((K_MISC + 2 + 3) / 4) * 4;
 };
 
-// chol_forward + the record of the stage for k_policy_expand: Y (M x NX), yg (M), L (M x MP, reciprocal pivots on the diagonal).  Rows >= M are
-// padding: never written, never read.  The trip counts are compile-time constants, so the stores stay one straight-line batch.
-template <int M, int MP, int NX>
-__device__ __forceinline__ bool chol_forward_store(double (&gc)[MP], double (&hc)[MP], int lane, double* __restrict__ ric) {
+// Step C of a Riccati stage for a compile-time reduced input dimension M: [H | G | g] (rows < M) from the staged fragments -> one column per lane,
+// chol_forward, the record of the stage for k_policy_expand (Y (M x NX), yg (M), L (M x MP, reciprocal pivots on the diagonal); rows >= M are
+// padding: never written, never read) and [Y | yg] back into shared memory for the S' update (rows M .. 4 ceil(M / 4) - 1 zero).
+// Every lane runs the same straight-line code: one clamped column index per lane and predicated stores, no divergent branches.
+// HG layout per row: H (24) | G (16) | g (column 40).  Returns s' correction sum_i Y[i][lane] yg[i] for lane < 24.
+template <int M, int MP, int NX, int LDH>
+__device__ __forceinline__ bool chol_stage(double* __restrict__ HG, int lane, double* __restrict__ ric, double& ytyg) {
   using R = RDims<NX - 12>;
+  constexpr int M4 = ((M + 3) / 4) * 4;
+  const int hcol = lane < 24 ? lane : 40;          // lane 24 carries g / yg
+  const int gcol = 24 + (lane & (MP - 1));
+  const bool hon = lane <= 24, gon = lane < MP;
+  double gc[MP], hc[MP];
+#pragma unroll
+  for (int i = 0; i < M; ++i) { const double gv_ = HG[i * LDH + gcol], hv_ = HG[i * LDH + hcol]; gc[i] = gon ? gv_ : 0.0; hc[i] = hon ? hv_ : 0.0; }
+#pragma unroll
+  for (int i = M; i < MP; ++i) { gc[i] = 0.0; hc[i] = 0.0; }
+  __syncwarp();
   const bool not_pd = chol_forward<M, MP>(gc, hc, lane);
+  const bool yst = lane < NX || lane == 24;
+  const int yoff = lane < NX ? R::K_Y + lane : R::K_YG, ystr = lane < NX ? NX : 1;
 #pragma unroll
   for (int i = 0; i < M; ++i) {
-    if (lane < NX) ric[R::K_Y + i * NX + lane] = hc[i];
-    if (lane < MP) ric[R::K_L + i * MP + lane] = (i >= lane) ? gc[i] : 0.0;
-    if (lane == 24) ric[R::K_YG + i] = hc[i];
+    if (yst) ric[yoff + i * ystr] = hc[i];
+    if (gon) ric[R::K_L + i * MP + lane] = (i >= lane) ? gc[i] : 0.0;
   }
+#pragma unroll
+  for (int i = 0; i < M4; ++i) if (hon) HG[i * LDH + hcol] = (i < M) ? hc[i] : 0.0;   // Y | yg
+  __syncwarp();
+  double a = 0.0;
+#pragma unroll
+  for (int i = 0; i < M; ++i) a += hc[i] * HG[i * LDH + 40];
+  ytyg = a;
   return not_pd;
 }
 
@@ -93,7 +114,7 @@ struct RicWarpSmem {
   static constexpr int LDH = 44;
   alignas(16) double rec[SDims<NJ>::TMA_DOUBLES];   // AB | bt | qt | rt | meta (TMA destination)
   alignas(16) double HG[16 * LDH];                   // [H | G] fragments -> column layout for the Cholesky; afterwards [Y | L]
-  double sb[24], gv[16];
+  double sb[24];
   alignas(16) unsigned long long bar;
 };
 
@@ -200,7 +221,7 @@ __global__ void __launch_bounds__(32 * RIC_WPC, RIC_BLOCKS) k_riccati_warp(Dev d
       // ---- step D1: S' = Qt + At^T Z[:, :24] ; s' = qt + At^T sb
       if (lane < 24) { sn = sr[S::S_Q + lane]; for (int r = 0; r < 24; ++r) sn += AB[r * LDA + lane] * sm.sb[r]; }
       s_l = sn;
-      if (lane < MP) sm.gv[lane] = gval;
+      if (lane < MP) sm.HG[lane * LDH + 40] = gval;   // g: column 40 of the staged [H | G]
     }
 #pragma unroll
     for (int kb = 0; kb < 3; ++kb)
@@ -220,33 +241,18 @@ __global__ void __launch_bounds__(32 * RIC_WPC, RIC_BLOCKS) k_riccati_warp(Dev d
       for (int c = 0; c < 5; ++c) *reinterpret_cast<double2*>(&sm.HG[(8 * a + g) * LDH + 8 * c + 2 * q]) = make_double2(HGf[a][c][0], HGf[a][c][1]);
     __syncwarp();
     {
-      double gc[MP], hc[MP];
-#pragma unroll
-      for (int i = 0; i < MP; ++i) { gc[i] = (lane < MP) ? sm.HG[i * LDH + 24 + lane] : 0.0; hc[i] = (lane < 24) ? sm.HG[i * LDH + lane] : ((lane == 24) ? sm.gv[i] : 0.0); }
-      __syncwarp();
-      bool not_pd;
+      bool not_pd; double ytyg;
       switch (m) {   // reduced input dimensions that occur: H1 6 / 9 / 12 (FLY / single stance / double stance), G1 8 / 11 / 14
-        case 6: not_pd = chol_forward_store<6, MP, NX>(gc, hc, lane, ric); break;
-        case 9: not_pd = chol_forward_store<9, MP, NX>(gc, hc, lane, ric); break;
-        case 12: not_pd = chol_forward_store<12, MP, NX>(gc, hc, lane, ric); break;
-        case 8: not_pd = chol_forward_store<8, MP, NX>(gc, hc, lane, ric); break;
-        case 11: not_pd = chol_forward_store<11, MP, NX>(gc, hc, lane, ric); break;
-        case 14: not_pd = chol_forward_store<14, MP, NX>(gc, hc, lane, ric); break;
-        default: not_pd = chol_forward_store<MP, MP, NX>(gc, hc, lane, ric); break;   // padded pivots are identity rows
+        case 6: not_pd = chol_stage<6, MP, NX, LDH>(sm.HG, lane, ric, ytyg); break;
+        case 9: not_pd = chol_stage<9, MP, NX, LDH>(sm.HG, lane, ric, ytyg); break;
+        case 12: not_pd = chol_stage<12, MP, NX, LDH>(sm.HG, lane, ric, ytyg); break;
+        case 8: not_pd = chol_stage<8, MP, NX, LDH>(sm.HG, lane, ric, ytyg); break;
+        case 11: not_pd = chol_stage<11, MP, NX, LDH>(sm.HG, lane, ric, ytyg); break;
+        case 14: not_pd = chol_stage<14, MP, NX, LDH>(sm.HG, lane, ric, ytyg); break;
+        default: not_pd = chol_stage<MP, MP, NX, LDH>(sm.HG, lane, ric, ytyg); break;   // padded pivots are identity rows
       }
       if (not_pd && lane == 0) atomicOr(&d.status[b], 1);
-#pragma unroll
-      for (int i = 0; i < MP; ++i) {
-        if (lane < 24) sm.HG[i * LDH + lane] = hc[i];                       // Y
-        if (lane == 24) sm.gv[i] = hc[i];                                   // yg
-      }
-      __syncwarp();
-      if (lane < 24) {   // s' -= Y^T yg
-        double a = 0.0;
-#pragma unroll
-        for (int i = 0; i < MP; ++i) a += hc[i] * sm.gv[i];
-        s_l -= a;
-      }
+      if (lane < 24) s_l -= ytyg;   // s' -= Y^T yg
     }
     // ---- step E: S' -= Y^T Y  (natural k order: both operands come from the staged Y)
 #pragma unroll
