@@ -9,18 +9,20 @@ template <int NJ>
 __device__ __forceinline__ void lq_dq_column(const double* __restrict__ bs, const double* __restrict__ u, int c, double* col) {
   using BD = BaseDims<NJ>; constexpr int NL = Dims<NJ>::NL;
   const double imass = 1.0 / c_model.total_mass;
-  v3 ak, ok, wp, vp, AlinK; SI sub; Mom hsub; int leg_first, leg_last;
-  if (c < 9) {
-    const int k = c - 6;
-    ak = ld3(bs + BD::B_BAX + 3 * k); ok = ld3(bs + BD::B_PB); sub = ld_si(bs + BD::B_TOT);
-    hsub.n = ld3(bs + BD::B_HTOT); hsub.p = ld3(bs + BD::B_HTOT + 3);
-    wp = ld3(bs + BD::B_WE + 3 * k); vp = ld3(bs + BD::B_VE + 3 * k); AlinK = ld3(bs + BD::B_ALE + 3 * k); leg_first = 0; leg_last = 1;
-  } else {
-    const int j = c - 9; const double* J = bs + BD::B_J + BD::JS * j;
-    ak = ld3(J + BD::J_A); ok = ld3(J + BD::J_O); sub = ld_si(J + BD::J_SI); hsub.n = ld3(J + BD::J_HN); hsub.p = ld3(J + BD::J_HP);
-    if (j % NL == 0) { wp = ld3(bs + BD::B_WE + 9); vp = ld3(bs + BD::B_VE + 9); } else { wp = ld3(J - BD::JS + BD::J_W); vp = ld3(J - BD::JS + BD::J_V); }
-    AlinK = ld3(J + BD::J_AL); leg_first = leg_last = j / NL;
-  }
+  // operands through one pointer set per lane (base Euler-angle columns 6..8: the whole tree moves; joint columns: the joint's subtree):
+  // the same straight-line code for every lane, no lane-dependent branch
+  const bool isb = c < 9;
+  const int kq = isb ? c - 6 : 0, j = isb ? 0 : c - 9;
+  const double* J = bs + BD::B_J + BD::JS * j;
+  const bool root = (j % NL) == 0;
+  const v3 ak = ld3(isb ? bs + BD::B_BAX + 3 * kq : J + BD::J_A), ok = ld3(isb ? bs + BD::B_PB : J + BD::J_O);
+  const SI sub = ld_si(isb ? bs + BD::B_TOT : J + BD::J_SI);
+  Mom hsub; { const double* ph = isb ? bs + BD::B_HTOT : J + BD::J_HN; hsub.n = ld3(ph); hsub.p = ld3(ph + 3); }
+  static_assert(BD::J_HP == BD::J_HN + 3, "subtree momentum: moment then linear part");
+  const v3 wp = ld3(isb ? bs + BD::B_WE + 3 * kq : (root ? bs + BD::B_WE + 9 : J - BD::JS + BD::J_W));
+  const v3 vp = ld3(isb ? bs + BD::B_VE + 3 * kq : (root ? bs + BD::B_VE + 9 : J - BD::JS + BD::J_V));
+  const v3 AlinK = ld3(isb ? bs + BD::B_ALE + 3 * kq : J + BD::J_AL);
+  const int leg_first = isb ? 0 : j / NL, leg_last = isb ? 1 : j / NL;
   const v3 com = ld3(bs + BD::B_COM), ptot = ld3(bs + BD::B_HTOT + 3), Ftot = ld3(bs + BD::B_FTOT);
   const double* A22i = bs + BD::B_A22I; const double* A12 = bs + BD::B_A12;
   const v3 s = cross(ok, ak);
@@ -38,8 +40,10 @@ __device__ __forceinline__ void lq_dq_column(const double* __restrict__ bs, cons
   col[3] = -l.x; col[4] = -l.y; col[5] = -l.z; col[6] = -e.x; col[7] = -e.y; col[8] = -e.z;
   v3 t = mk(0.0, 0.0, 0.0);
 #pragma unroll
-  for (int cc = 0; cc < NCON; ++cc)
-    if (cc / 2 >= leg_first && cc / 2 <= leg_last) t = t + cross(cross(ak, ld3(bs + BD::B_PC + 3 * cc) - ok), mk(u[3 * cc], u[3 * cc + 1], u[3 * cc + 2]));
+  for (int cc = 0; cc < NCON; ++cc) {
+    const v3 e = cross(cross(ak, ld3(bs + BD::B_PC + 3 * cc) - ok), mk(u[3 * cc], u[3 * cc + 1], u[3 * cc + 2]));
+    if (cc / 2 >= leg_first && cc / 2 <= leg_last) t = t + e;
+  }
   t = imass * (t - cross(dcom, Ftot));
   col[0] = t.x; col[1] = t.y; col[2] = t.z;
 }
@@ -224,31 +228,41 @@ __device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k,
   // ---- contact velocity Jacobians of the first evaluation and the compressed constraint rows
   v3 jx[NCON], ju[NCON];
   {
+    // The "direct" term of d v_c / d q_k (the column's own joint moves the contact) is the same straight-line code for every lane: its operands
+    // come through one clamped pointer set per lane (base Euler-angle columns 6..8: base axes / partial base twists; joint columns: the joint's
+    // record), chosen once per stage, and the result is selected in -- no lane-dependent branches inside the contact loop.
     const v3 pb = ld3(b1 + BD::B_PB);
+    const bool xb_ = xcl >= 6 && xcl < 9 && lane < NXA, xj_ = xcl >= 9 && lane < NXA;
+    const int jq = xj_ ? xcl - 9 : 0, kq = xb_ ? xcl - 6 : 0;
+    const double* Jq = b1 + BD::B_J + BD::JS * jq;
+    const v3 ak = ld3(xb_ ? b1 + BD::B_BAX + 3 * kq : Jq + BD::J_A), ok = ld3(xb_ ? b1 + BD::B_PB : Jq + BD::J_O);
+    const v3 wk = ld3(xb_ ? b1 + BD::B_WE + 3 * (kq + 1) : Jq + BD::J_W), vk = ld3(xb_ ? b1 + BD::B_VE + 3 * (kq + 1) : Jq + BD::J_V);
+    const int xleg = jq / NL;
+    const int ju_ = lane < NJ ? lane : 0, uleg = ju_ / NL;
+    const double* Ju = b1 + BD::B_J + BD::JS * ju_;
+    const v3 aj = ld3(Ju + BD::J_A), oj = ld3(Ju + BD::J_O);
+    v3 bax3[3];
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) bax3[kk] = ld3(b1 + BD::B_BAX + 3 * kk);
 #pragma unroll
     for (int c = 0; c < NCON; ++c) {
       const int leg = c / 2;
       const v3 p = ld3(b1 + BD::B_PC + 3 * c), vcp = ld3(b1 + BD::B_VC + 3 * c);
       v3 Jb[3];
 #pragma unroll
-      for (int kk = 0; kk < 3; ++kk) Jb[kk] = cross(ld3(b1 + BD::B_BAX + 3 * kk), p - pb);
-      jx[c] = mk(0.0, 0.0, 0.0); ju[c] = mk(0.0, 0.0, 0.0);
-      if (lane < NXA) {
-        v3 t = mk(a1[3], a1[4], a1[5]) + a1[6] * Jb[0] + a1[7] * Jb[1] + a1[8] * Jb[2];
-        bool direct = false; v3 ak, ok, wk, vk;
-        if (xcl >= 6 && xcl < 9) { const int kk = xcl - 6; direct = true; ak = ld3(b1 + BD::B_BAX + 3 * kk); ok = pb; wk = ld3(b1 + BD::B_WE + 3 * (kk + 1)); vk = ld3(b1 + BD::B_VE + 3 * (kk + 1)); }
-        else if (xcl >= 9 && (xcl - 9) / NL == leg) { const double* J = b1 + BD::B_J + BD::JS * (xcl - 9); direct = true; ak = ld3(J + BD::J_A); ok = ld3(J + BD::J_O); wk = ld3(J + BD::J_W); vk = ld3(J + BD::J_V); }
-        if (direct) {
-          const v3 uw = vcp - (cross(wk, p) + vk), apo = cross(ak, p - ok);   // apo = d p / d q_k
-          t = t + cross(ak, uw) + cross(wk, apo);
-          t.z += M.gain * apo.z;   // positionErrorGain (BipedalRobotInterface.cpp:350-359, BipedalRobotPreComputation.cpp:71-80): the z rows also see gain * p_z
-        }
-        jx[c] = t;
+      for (int kk = 0; kk < 3; ++kk) Jb[kk] = cross(bax3[kk], p - pb);
+      {
+        v3 t = mk(a1[3], a1[4], a1[5]) + a1[6] * Jb[0] + a1[7] * Jb[1] + a1[8] * Jb[2];   // a1 = 0 on lanes >= NXA
+        const v3 uw = vcp - (cross(wk, p) + vk), apo = cross(ak, p - ok);   // apo = d p / d q_k
+        v3 e = cross(ak, uw) + cross(wk, apo);
+        e.z += M.gain * apo.z;   // positionErrorGain (BipedalRobotInterface.cpp:350-359, BipedalRobotPreComputation.cpp:71-80): the z rows also see gain * p_z
+        const bool direct = xb_ || (xj_ && xleg == leg);
+        jx[c] = direct ? t + e : t;
       }
-      if (lane < NJ) {
+      {
         v3 t = mk(bj1[0], bj1[1], bj1[2]) + bj1[3] * Jb[0] + bj1[4] * Jb[1] + bj1[5] * Jb[2];
-        if (lane / NL == leg) { const double* J = b1 + BD::B_J + BD::JS * lane; t = t + cross(ld3(J + BD::J_A), p - ld3(J + BD::J_O)); }
-        ju[c] = t;
+        const v3 e = cross(aj, p - oj);
+        ju[c] = (lane < NJ && uleg == leg) ? t + e : t;
       }
     }
   }
