@@ -45,11 +45,6 @@ __device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-__device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p) : "memory"); }
-#ifndef PF_AHEAD_LQ
-#define PF_AHEAD_LQ -1   // k_lq_pack: off (its inputs are three short rows; measured no gain, the extra branches cost 1 %)
-#endif
-
 struct Dev {
   int B, NS, ME, TP, npts;   // NS: node slots per instance = nominal grid + 1 + max_event_nodes
   double dt_nom, horizon;

@@ -88,12 +88,13 @@ __device__ __forceinline__ void lq_bf_column(const double* __restrict__ bs, int 
 // cost gradient, soft friction-cone barrier, compressed constraint rows -> compact LQ record `rec`.  xs/us/xns/xrs: x_k, u_k, x_{k+1}, x_ref.
 template <int NJ, bool RAW>
 __device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k, double* __restrict__ rec, const double* __restrict__ b1, const double* __restrict__ b2,
-                                                 const double* xs, const double* us, const double* xns, const double* xrs, double (*sA2w)[Dims<NJ>::NXA + 1], int lane) {
+                                                 const double* xs, const double* us, const double* xns, const double* xrs, double (*sA2w)[Dims<NJ>::NXA + 1], const double* __restrict__ mt, int lane) {
   using D = Dims<NJ>; using BD = BaseDims<NJ>;
   constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, NL = D::NL;
   const DevModel& M = c_model;
-  const double dt = d.st_dt[nb + k];
-  const int mode = d.st_mode[nb + k];
+  // per-stage scalars staged by the kernel prologue (mt = [zref 4 | dt | mode | event flag]): no global load inside the column pass
+  const double dt = mt[4];
+  const int mode = (int)mt[5];
   const double hdt = 0.5 * dt, imass = 1.0 / M.total_mass;
   // ---- Jacobian columns.  Lanes 0..15 work on the first Heun evaluation (b1), lanes 16..31 on the second (b2), with the same instructions:
   //   heavy pass : half-lane cl < NH = NXA - 6 -> state column 6 + cl (base Euler angles, leg joints), lq_dq_column
@@ -284,7 +285,7 @@ __device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k,
         if (lane == 0) { rec[D::R_EV + nrows] = vcc.x; rec[D::R_EV + nrows + 1] = vcc.y; rec[D::R_EV + nrows + 2] = ez; }
         nrows += 3;
       } else {
-        const double ev = vcc.z - d.zref[(nb + k) * 4 + c / 2] + M.gain * (pz - d.zref[(nb + k) * 4 + 2 + c / 2]);
+        const double ev = vcc.z - mt[c / 2] + M.gain * (pz - mt[2 + c / 2]);
         if (lane < NXA) rec[D::R_CV + nrows * NXA + xcl] = jx[c].z;
         if (lane < NJ) rec[D::R_DV + nrows * NJ + lane] = ju[c].z;
         if (lane == 0) rec[D::R_EV + nrows] = ev;
@@ -322,7 +323,7 @@ __device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k,
       }
       nrows += 5;
     } else {
-      const double zr = d.zref[(nb + k) * 4 + leg];
+      const double zr = mt[leg];
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int c0 = t == 0 ? ca : cb;
@@ -355,6 +356,7 @@ struct LqPackSmem {
   double base[WPB][G][2 * BASE];
   double A2[WPB][9][NXA + 1];
   double xu[WPB][G][4 * 24];   // per stage: x, u, xnext, xref
+  double mt[WPB][G][8];        // per stage: zref (4), dt, mode, event flag
 };
 template <int NJ, bool RAW>
 __global__ void __launch_bounds__(128, LQ_PAIR_BLOCKS) k_lq_pack(Dev d) {
@@ -370,39 +372,35 @@ __global__ void __launch_bounds__(128, LQ_PAIR_BLOCKS) k_lq_pack(Dev d) {
   const int gw = blockIdx.x * WPB + warp;
   const int b = gw / NP, k0 = G * (gw % NP);
   if (b >= d.B) return;
-  if (PF_AHEAD_LQ >= 0 && lane < 8) {   // inputs of the warp one wave ahead -> L2
-    const int ga = gw + PF_AHEAD_LQ, ba = ga / NP, ka = G * (ga % NP);
-    if (ba < d.B && ka + G < d.NS) {
-      const size_t na = (size_t)ba * d.NS + ka;
-      if (lane == 0) prefetch_l2(d.s_x + na * NX, (G + 1) * NX * sizeof(double));
-      else if (lane == 1) prefetch_l2(d.s_u + na * NU, G * NU * sizeof(double));
-      else if (lane == 2) prefetch_l2(d.xref + na * NX, G * NX * sizeof(double));
-      else if (lane == 3) prefetch_l2_line(d.zref + na * 4);
-      else if (lane == 4) prefetch_l2_line(d.zref + na * 4 + 4 * G - 1);
-      else if (lane == 5) prefetch_l2_line(d.st_dt + na);
-      else if (lane == 6) prefetch_l2_line(d.st_mode + na);
-      else prefetch_l2_line(d.node_ev + na);
-    }
-  }
-  const int N = d.n_nodes[b] - 1;
-  if (k0 >= N) return;
+  // ---- one round of global loads: everything the G stages need is requested before the first dependent use (rows are clamped into the
+  //      instance's node slots, so no load waits for n_nodes / node_ev); the per-stage scalars travel through shared memory as well
   const size_t nb = (size_t)b * d.NS;
+  const int Nn = d.n_nodes[b];
+  int evv[G];
+#pragma unroll
+  for (int s = 0; s < G; ++s) {
+    const int kc = (k0 + s < d.NS - 1) ? k0 + s : d.NS - 2;
+    double* xs = sm.xu[warp][s];
+    evv[s] = d.node_ev[nb + kc];
+    const double v0 = lane < NX ? d.s_x[(nb + kc) * NX + lane] : 0.0, v1 = lane < NX ? d.s_x[(nb + kc + 1) * NX + lane] : 0.0;
+    const double v2 = lane < NX ? d.xref[(nb + kc) * NX + lane] : 0.0, v3_ = lane < NU ? d.s_u[(nb + kc) * NU + lane] : 0.0;
+    double v4 = 0.0;
+    if (lane < 4) v4 = d.zref[(nb + kc) * 4 + lane]; else if (lane == 4) v4 = d.st_dt[nb + kc]; else if (lane == 5) v4 = (double)d.st_mode[nb + kc];
+    if (lane < NX) { xs[lane] = v0; xs[48 + lane] = v1; xs[72 + lane] = v2; }
+    if (lane < NU) xs[24 + lane] = v3_;
+    if (lane < 6) sm.mt[warp][s][lane] = v4;
+  }
+  const int N = Nn - 1;
+  if (k0 >= N) return;
   bool has[G], ev[G], comp[G];   // stage exists / is an event node / needs the model
   int first_comp = -1;
 #pragma unroll
   for (int s = 0; s < G; ++s) {
     has[s] = k0 + s < N;
-    ev[s] = has[s] && d.node_ev[nb + k0 + s] == 1;
+    ev[s] = has[s] && evv[s] == 1;
     comp[s] = has[s] && !ev[s];
     if (comp[s] && first_comp < 0) first_comp = s;
-  }
-#pragma unroll
-  for (int s = 0; s < G; ++s) {
-    if (!has[s]) continue;
-    const int k = k0 + s;
-    double* xs = sm.xu[warp][s];
-    if (lane < NX) { xs[lane] = d.s_x[(nb + k) * NX + lane]; xs[48 + lane] = d.s_x[(nb + k + 1) * NX + lane]; xs[72 + lane] = d.xref[(nb + k) * NX + lane]; }
-    if (lane < NU) xs[24 + lane] = d.s_u[(nb + k) * NU + lane];
+    if (lane == 6) sm.mt[warp][s][6] = ev[s] ? 1.0 : 0.0;
   }
   __syncwarp();
   if (first_comp >= 0) {
@@ -424,7 +422,7 @@ __global__ void __launch_bounds__(128, LQ_PAIR_BLOCKS) k_lq_pack(Dev d) {
       if (ev_ == 0) {
 #pragma unroll
         for (int s = 0; s < G; ++s)
-          if (lane < NX) x2[24 * s + lane] = comp[s] ? sm.xu[warp][s][lane] + d.st_dt[nb + k0 + s] * sm.base[warp][s][BD::B_F + lane] : 0.0;
+          if (lane < NX) x2[24 * s + lane] = comp[s] ? sm.xu[warp][s][lane] + sm.mt[warp][s][4] * sm.base[warp][s][BD::B_F + lane] : 0.0;
         __syncwarp();
       }
     }
@@ -435,7 +433,7 @@ __global__ void __launch_bounds__(128, LQ_PAIR_BLOCKS) k_lq_pack(Dev d) {
     const int k = k0 + s;
     double* __restrict__ rec = d.lq + (nb + k) * D::REC;
     const double* xs = sm.xu[warp][s];
-    if (d.node_ev[nb + k] == 1) {   // [UPSTREAM] setupEventNode
+    if (sm.mt[warp][s][6] != 0.0) {   // [UPSTREAM] setupEventNode
       double sq = 0.0;
       if (lane < NX) { const double bi = xs[lane] - xs[48 + lane]; rec[D::R_B + lane] = bi; sq = bi * bi; }
       for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
@@ -445,7 +443,7 @@ __global__ void __launch_bounds__(128, LQ_PAIR_BLOCKS) k_lq_pack(Dev d) {
       }
       continue;
     }
-    lq_stage_columns<NJ, RAW>(d, nb, k, rec, sm.base[warp][s], sm.base[warp][s] + BASE, xs, xs + 24, xs + 48, xs + 72, sm.A2[warp], lane);
+    lq_stage_columns<NJ, RAW>(d, nb, k, rec, sm.base[warp][s], sm.base[warp][s] + BASE, xs, xs + 24, xs + 48, xs + 72, sm.A2[warp], sm.mt[warp][s], lane);
     __syncwarp();   // A2 is reused by the next stage
   }
 }
