@@ -106,83 +106,86 @@ __device__ __forceinline__ void lq_stage_columns(const Dev& d, size_t nb, int k,
   const int half = lane >> 4, cl = lane & 15;
   const double* __restrict__ bsel = half ? b2 : b1;
   const int xcl = lane < NH ? 6 + lane : (lane < NH + 3 ? 3 + (lane - NH) : lane - (NH + 3));   // state column (active-x index) of this lane, lane < NXA
+  // All of this is straight-line code executed by every lane (idle lanes work on a clamped column and their results are masked): one large basic
+  // block lets the compiler interleave the independent chains, which is what hides latency at two warps per scheduler.
   double a1[9], bj1[6], bj2[6], bf1[3], bf2[3];
-#pragma unroll
-  for (int r = 0; r < 9; ++r) a1[r] = 0.0;
-  if (cl < NH) {
+  {
     double col[9];
-    lq_dq_column<NJ>(bsel, us, 6 + cl, col);
-    if (half == 0) {
+    lq_dq_column<NJ>(bsel, us, cl < NH ? 6 + cl : 6, col);
+    const bool own1 = half == 0 && cl < NH, own2 = half == 1 && cl < NH;
 #pragma unroll
-      for (int r = 0; r < 9; ++r) a1[r] = col[r];
-    } else {
+    for (int r = 0; r < 9; ++r) a1[r] = own1 ? col[r] : 0.0;
+    if (own2) {
 #pragma unroll
       for (int r = 0; r < 9; ++r) sA2w[r][6 + cl] = col[r];
     }
   }
   {
-    const bool c1 = lane >= NH && lane < NH + 3, c2 = lane >= 24 && lane < 27;
-    if (c1 || c2) {
-      double col[9];
-      lq_x_column<NJ>(c1 ? b1 : b2, us, 3 + (c1 ? lane - NH : lane - 24), col);
-      if (c1) {
+    // cheap columns: angular momentum 3..5 (lanes NH..NH+2 for b1, lanes 24..26 for b2): -A12 A22i e_c / m A22i e_c; linear momentum 0..2: identity
+    const bool c1 = lane >= NH && lane < NH + 3, c2 = lane >= 24 && lane < 27, c3 = lane >= NH + 3 && lane < NXA;
+    const int cc = c1 ? lane - NH : (c2 ? lane - 24 : 0), ci = c3 ? lane - (NH + 3) : 0;
+    const double* bq = c2 ? b2 : b1;
+    const double* A22i = bq + BD::B_A22I; const double* A12 = bq + BD::B_A12;
+    const double i0 = A22i[cc], i1 = A22i[3 + cc], i2 = A22i[6 + cc];
+    double col[6];
 #pragma unroll
-        for (int r = 0; r < 9; ++r) a1[r] = col[r];
-      } else {
+    for (int r = 0; r < 3; ++r) { col[r] = -(A12[3 * r] * i0 + A12[3 * r + 1] * i1 + A12[3 * r + 2] * i2); col[3 + r] = M.total_mass * (r == 0 ? i0 : (r == 1 ? i1 : i2)); }
 #pragma unroll
-        for (int r = 0; r < 9; ++r) sA2w[r][3 + lane - 24] = col[r];
-      }
+    for (int r = 0; r < 6; ++r) a1[3 + r] = c1 ? col[r] : a1[3 + r];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) a1[3 + i] = (c3 && ci == i) ? 1.0 : a1[3 + i];
+    if (c2) {
+#pragma unroll
+      for (int r = 0; r < 9; ++r) sA2w[r][3 + cc] = r < 3 ? 0.0 : col[r - 3];
     }
-    if (lane >= NH + 3 && lane < NXA) {   // d f / d (normalised linear momentum): identity block, both evaluations
-      const int c = lane - (NH + 3);
+    if (c3) {
 #pragma unroll
-      for (int i = 0; i < 3; ++i) a1[3 + i] = (c == i) ? 1.0 : 0.0;   // (no dynamic register-array index: it would push a1[] into local memory)
-#pragma unroll
-      for (int r = 0; r < 9; ++r) sA2w[r][c] = (r == 3 + c) ? 1.0 : 0.0;
+      for (int r = 0; r < 9; ++r) sA2w[r][ci] = (r == 3 + ci) ? 1.0 : 0.0;
     }
   }
   {
-    double bjv[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, bfv[3] = {0.0, 0.0, 0.0};
-    if (cl < NJ) lq_bj_column<NJ>(bsel, cl, bjv);
-    if (cl < 12) lq_bf_column<NJ>(bsel, cl, bfv);
+    double bjv[6], bfv[3];
+    lq_bj_column<NJ>(bsel, cl < NJ ? cl : 0, bjv);
+    lq_bf_column<NJ>(bsel, cl < 12 ? cl : 0, bfv);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { bj1[i] = bjv[i]; bj2[i] = __shfl_sync(0xffffffffu, bjv[i], (lane + 16) & 31); }
+    for (int i = 0; i < 6; ++i) { bjv[i] = cl < NJ ? bjv[i] : 0.0; bj1[i] = bjv[i]; bj2[i] = __shfl_sync(0xffffffffu, bjv[i], (lane + 16) & 31); }
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { bf1[i] = bfv[i]; bf2[i] = __shfl_sync(0xffffffffu, bfv[i], (lane + 16) & 31); }
+    for (int i = 0; i < 3; ++i) { bfv[i] = cl < 12 ? bfv[i] : 0.0; bf1[i] = bfv[i]; bf2[i] = __shfl_sync(0xffffffffu, bfv[i], (lane + 16) & 31); }
   }
   __syncwarp();
   // ---- dynamics: b, (A_d - I), B_d   [UPSTREAM SensitivityIntegrator RK2]
-  double pdyn = 0.0;
-  if (lane < NX) { const double bi = xs[lane] + hdt * (b1[BD::B_F + lane] + b2[BD::B_F + lane]) - xns[lane]; rec[D::R_B + lane] = bi; pdyn = bi * bi; }
+  double pdyn;
+  {
+    const int li = lane < NX ? lane : 0;
+    const double bi = xs[li] + hdt * (b1[BD::B_F + li] + b2[BD::B_F + li]) - xns[li];
+    if (lane < NX) rec[D::R_B + lane] = bi;
+    pdyn = lane < NX ? bi * bi : 0.0;
+  }
   for (int o = 16; o > 0; o >>= 1) pdyn += __shfl_xor_sync(0xffffffffu, pdyn, o);
-  if (lane < NXA) {
+  {
+    const int xc_ = lane < NXA ? xcl : 0, fl = lane < 12 ? lane : 0, jl = lane < NJ ? lane : 0, a = fl % 3;
+    double vA[9], vF[9], vJ[9];
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
-      double s = 0.0;
-#pragma unroll
-      for (int t = 0; t < 3; ++t) s += sA2w[r][3 + t] * a1[t] + sA2w[r][6 + t] * a1[6 + t];
-      rec[D::R_AD + r * NXA + xcl] = hdt * (a1[r] + sA2w[r][xcl] + dt * s);
+      const double a3 = sA2w[r][3], a4 = sA2w[r][4], a5 = sA2w[r][5], a6 = sA2w[r][6], a7 = sA2w[r][7], a8 = sA2w[r][8];
+      const double sA = (a3 * a1[0] + a6 * a1[6]) + (a4 * a1[1] + a7 * a1[7]) + (a5 * a1[2] + a8 * a1[8]);
+      vA[r] = hdt * (a1[r] + sA2w[r][xc_] + dt * sA);
+      const double sF = sA2w[r][a] * imass + a3 * bf1[0] + a4 * bf1[1] + a5 * bf1[2];
+      vF[r] = hdt * ((r < 3 ? (bf1[r < 3 ? r : 0] + bf2[r < 3 ? r : 0]) : 0.0) + dt * sF);
+      const double sJ = sA2w[r][9 + jl] + a6 * bj1[3] + a7 * bj1[4] + a8 * bj1[5];
+      vJ[r] = hdt * ((r >= 3 ? (bj1[r >= 3 ? r - 3 : 0] + bj2[r >= 3 ? r - 3 : 0]) : 0.0) + dt * sJ);
     }
-  }
-  if (lane < 12) {
-    const int a = lane % 3;
+    if (lane < NXA) {
 #pragma unroll
-    for (int r = 0; r < 9; ++r) {
-      double s = sA2w[r][a] * imass;
-#pragma unroll
-      for (int t = 0; t < 3; ++t) s += sA2w[r][3 + t] * bf1[t];
-      const double b12 = r < 3 ? (bf1[r] + bf2[r]) : 0.0;
-      rec[D::R_BD + r * NU + lane] = hdt * (b12 + dt * s);
+      for (int r = 0; r < 9; ++r) rec[D::R_AD + r * NXA + xcl] = vA[r];
     }
-  }
-  if (lane < NJ) {
+    if (lane < 12) {
 #pragma unroll
-    for (int r = 0; r < 9; ++r) {
-      double s = sA2w[r][9 + lane];
+      for (int r = 0; r < 9; ++r) rec[D::R_BD + r * NU + lane] = vF[r];
+    }
+    if (lane < NJ) {
 #pragma unroll
-      for (int t = 0; t < 3; ++t) s += sA2w[r][6 + t] * bj1[3 + t];
-      const double b12 = r >= 3 ? (bj1[r - 3] + bj2[r - 3]) : 0.0;
-      rec[D::R_BD + r * NU + 12 + lane] = hdt * (b12 + dt * s);
+      for (int r = 0; r < 9; ++r) rec[D::R_BD + r * NU + 12 + lane] = vJ[r];
     }
   }
   // ---- cost gradient / barrier blocks (one contact per lane 0..3, one joint per lane for the joint part)
