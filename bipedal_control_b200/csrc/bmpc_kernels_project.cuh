@@ -296,11 +296,15 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < NJ; ++i) y[i] = W[i][lane];
-    const bool is_null = lane >= 24 && lane - 24 < mj;
-    if (is_x) { for (int i = 0; i < NJ; ++i) out[D::P_PX + i * NXA + gc] = y[i]; }
-    else if (is_aff) { for (int i = 0; i < NJ; ++i) out[D::P_PE + i] = y[i]; }
-    else if (lane >= 24) { for (int i = 0; i < NJ; ++i) out[D::P_N + i * 8 + lane - 24] = y[i]; }   // columns beyond mj are zero
-    else if (lane == 8 && M.gain != 0.0) { for (int i = 0; i < NJ; ++i) out[D::P_PX8 + i] = y[i]; }   // read only with positionErrorGain
+    {   // projection record: one destination pointer / stride per lane (Pxj column | Pej | null-space column (zero beyond mj) | Pxj[:, base height]), one store loop
+      const bool g8 = lane == 8 && M.gain != 0.0;   // read only with positionErrorGain
+      double* pd = is_x ? out + D::P_PX + gc : (is_aff ? out + D::P_PE : (lane >= 24 ? out + D::P_N + (lane - 24) : out + D::P_PX8));
+      const int ps = is_x ? NXA : (lane >= 24 ? 8 : 1);
+      if (is_x || is_aff || lane >= 24 || g8) {
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) pd[i * ps] = y[i];
+      }
+    }
   } else {
   double (*Mt)[12] = sM[warp]; double (*V)[NJ] = sV[warp]; double* beta = sBeta[warp]; double* rinv = sBeta[warp] + 10;
   {   // stage Dv^T, [Cv | ev] and B_d rows 3..11: all global loads are issued before the first shared-memory store (fixed trip counts;
@@ -440,21 +444,25 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
     sMisc[warp][16 + lane] = open_corr;
   }
   // ---- element-wise parts (lane = column of W, values in y[]; done first so that y[] is dead during the tile products)
-  if (is_x || (lane == 8 && M.gain != 0.0)) {   // lane 8: the base-height column (structurally zero, and static, without positionErrorGain)
+  {   // At rows 12.. = I + dt Pxj (lane = state column; lane 8, the base-height column, only with positionErrorGain), Bt rows 12.. = dt N (lanes 24..: reduced
+      // columns 0..7, zero beyond mj) and bt rows 12.. (affine lane): the same row of [At | Bt] for the first two, so one destination pointer / stride per lane
+    const bool rowst = is_x || (lane == 8 && M.gain != 0.0) || lane >= 24;
+    double* pd = is_aff ? so + S::S_B + 12 : so + S::S_AB + 12 * LDA + lane;
+    const int ps = is_aff ? 1 : LDA;
 #pragma unroll
-    for (int l = 0; l < NJ; ++l) so[S::S_AB + (12 + l) * LDA + lane] = dt * y[l] + ((12 + l == lane) ? 1.0 : 0.0);   // At rows 12..: I + dt Pxj
-  } else if (is_aff) {
-#pragma unroll
-    for (int l = 0; l < NJ; ++l) so[S::S_B + 12 + l] = rec[D::R_B + 12 + l] + dt * y[l];                              // bt rows 12..
+    for (int l = 0; l < NJ; ++l) {
+      const double bl = rec[D::R_B + 12 + l];
+      const double v = dt * y[l] + (is_aff ? bl : ((12 + l == lane) ? 1.0 : 0.0));
+      if (rowst || is_aff) pd[l * ps] = v;
+    }
+  }
+  if (is_aff) {
     const double f = dt / M.total_mass;
     for (int qq = 0; qq < 3; ++qq) {   // rows 0..2 of bt: B_d rows 0..2 = dt/m on the force columns
       double bb = rec[D::R_B + qq];
       for (int cn = 0; cn < NCON; ++cn) if (!(cn / 2 == 0 ? st0 : st1)) bb -= f * rec[D::R_FO + 3 * cn + qq];
       so[S::S_B + qq] = bb;
     }
-  } else if (lane >= 24) {
-#pragma unroll
-    for (int l = 0; l < NJ; ++l) so[S::S_AB + (12 + l) * LDA + lane] = dt * y[l];   // Bt rows 12.., reduced columns 0..7: dt N (zero beyond mj)
   }
   // Bt rows 0..2 (dt/m on the closed-contact force columns) and rows 3..11 of the reduced columns 8..15 (force columns or zero)
   for (int i = lane; i < 3 * MP + 9 * 8; i += 32) {
