@@ -299,24 +299,41 @@ void set_slab_pointers(bmpc_handle* h, int i, double* slab) {
   h->s_K[i] = slab; h->s_uff[i] = slab + nK; h->s_x[i] = h->s_uff[i] + nU; h->s_u[i] = h->s_x[i] + nX; h->s_t[i] = h->s_u[i] + nU;
   h->s_ev[i] = reinterpret_cast<int*>(h->s_t[i] + nT); h->s_n[i] = h->s_ev[i] + B * NS;
 }
+// Tear-down of the policy exchange.  With symmetric windows every rank has the peers' slabs mapped, and NCCL's window / communicator tear-down touches
+// that peer memory: a rank that released its buffers while a slower peer was still deregistering made the peer fault (illegal memory access after
+// bmpc_destroy on the slower rank).  So the release is fenced by two tiny collectives on the same communicator: (1) every rank has entered the release
+// (no exchange in flight anywhere), (2) every rank has deregistered its windows -- only then is memory freed and the communicator destroyed.  Like
+// ncclCommDestroy itself, bmpc_exchange_destroy / bmpc_destroy of a handle with an exchange is therefore a collective call.
+void exchange_fence(bmpc_handle* h) {
+  auto& ex = h->ex; NcclApi& N = nccl_api();
+  if (!ex.comm || !ex.stream || ex.nranks <= 1) return;
+  double* buf = nullptr;
+  if (cudaMalloc(&buf, sizeof(double) * (size_t)(ex.nranks + 1)) != cudaSuccess) return;
+  cudaMemsetAsync(buf, 0, sizeof(double) * (size_t)(ex.nranks + 1), ex.stream);
+  N.AllGather(buf + ex.nranks, buf, 1, NcclApi::kFloat64, ex.comm, ex.stream);
+  cudaStreamSynchronize(ex.stream);
+  cudaFree(buf);
+}
 void exchange_release(bmpc_handle* h) {
   auto& ex = h->ex; NcclApi& N = nccl_api();
   if (ex.stream) cudaStreamSynchronize(ex.stream);
+  if (ex.comm && ex.symmetric) exchange_fence(h);
   if (ex.comm) {
     for (int i = 0; i < 2; ++i) {
       if (ex.win_recv[i] && N.CommWindowDeregister) N.CommWindowDeregister(ex.comm, ex.win_recv[i]);
       if (ex.win_send[i] && N.CommWindowDeregister) N.CommWindowDeregister(ex.comm, ex.win_send[i]);
     }
   }
-  for (int i = 0; i < 2; ++i) if (ex.recv[i]) { if (ex.nccl_mem) N.MemFree(ex.recv[i]); else cudaFree(ex.recv[i]); ex.recv[i] = nullptr; }
+  if (ex.comm && ex.symmetric) exchange_fence(h);
   for (int i = 0; i < 2; ++i) if (ex.send_slab[i]) {
     // the policy slabs live in NCCL memory: move them back into plain device memory before it is released
     const size_t bytes = h->slab_doubles * sizeof(double);
     double* p = nullptr;
     if (cudaMalloc(&p, bytes) == cudaSuccess) { cudaMemcpy(p, ex.send_slab[i], bytes, cudaMemcpyDeviceToDevice); h->pool.dev.push_back(p); set_slab_pointers(h, i, p); }
-    N.MemFree(ex.send_slab[i]); ex.send_slab[i] = nullptr;
   }
-  if (ex.comm) { N.CommDestroy(ex.comm); ex.comm = nullptr; }
+  if (ex.comm) { N.CommDestroy(ex.comm); ex.comm = nullptr; }   // before the NCCL memory goes: the communicator still has it mapped / registered
+  for (int i = 0; i < 2; ++i) if (ex.recv[i]) { if (ex.nccl_mem) N.MemFree(ex.recv[i]); else cudaFree(ex.recv[i]); ex.recv[i] = nullptr; }
+  for (int i = 0; i < 2; ++i) if (ex.send_slab[i]) { N.MemFree(ex.send_slab[i]); ex.send_slab[i] = nullptr; }
   if (ex.ready) cudaEventDestroy(ex.ready);
   for (auto& e : ex.done) if (e) cudaEventDestroy(e);
   if (ex.stream) cudaStreamDestroy(ex.stream);

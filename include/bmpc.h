@@ -177,7 +177,9 @@ int bmpc_get_device_view_inflight(bmpc_handle* h, bmpc_device_view* v);
  * max_ctas > 0 caps the SMs NCCL may use (the solver keeps the rest); use_copy_engines = 1 asks for NCCL's copy-engine all-gather (NCCL >= 2.28,
  * symmetric windows, CTA policy "zero": no SM at all), 2 for symmetric windows with NCCL's SM kernels; in both the policy slabs move into
  * NCCL-registered memory (device views obtained earlier are stale) and are gathered in place.  bmpc_exchange_view returns the active mode
- * (0 plain buffers, 1, 2).  NCCL is loaded at run time (libnccl.so.2) only when these functions are used. */
+ * (0 plain buffers, 1, 2).  NCCL is loaded at run time (libnccl.so.2) only when these functions are used.
+ * Tear-down is collective (as ncclCommDestroy is): bmpc_exchange_destroy, or bmpc_destroy of a handle with an exchange, must be called by every rank;
+ * with symmetric windows the ranks are fenced inside the call so that no rank frees memory a slower peer still has mapped. */
 typedef struct bmpc_exchange_id { char bytes[128]; } bmpc_exchange_id;
 int bmpc_exchange_create_id(bmpc_exchange_id* id);
 int bmpc_exchange_init(bmpc_handle* h, int rank, int nranks, const bmpc_exchange_id* id, int max_ctas, int use_copy_engines);
