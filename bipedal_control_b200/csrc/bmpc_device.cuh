@@ -123,9 +123,15 @@ __device__ __forceinline__ int xcol(int s) { return s < 6 ? s : s - 3; }
 // so one root-to-leaf pass per leg accumulates the total spatial inertia, the joint-induced momentum and the tip twists; no composite
 // inertias, no per-joint arrays, no local memory.  xb = x[0:12], qj = x[12:], uf = u[0:12], qd = u[12:]; f = rows 0..11 of the flow map
 // (rows 12.. are qd).  Fully unrolled: the model constants become immediate constant-bank operands.
+// MODEL_VALUES_UNROLL = 1: the joint loop of a leg stays rolled.  Fully unrolled the function is 7 k instructions of straight-line code that every warp
+// runs through once: k_linesearch then waits for instruction fetch (ncu: 29 % of its stall samples are no_instruction); rolled, the model constants
+// are indexed constant-bank loads instead of immediate operands but the body stays in the instruction cache.
+#ifndef MODEL_VALUES_UNROLL
+#define MODEL_VALUES_UNROLL 1
+#endif
 template <int NJ>
 __device__ __noinline__ void model_values(const double (&xb)[12], const double (&qj)[NJ], const double (&uf)[12], const double (&qd)[NJ], double (&f)[12], v3 (&vc)[NCON], v3* pc_out = nullptr) {
-  constexpr int NL = Dims<NJ>::NL;
+  constexpr int NL = Dims<NJ>::NL, MVU = MODEL_VALUES_UNROLL;
   const DevModel& M = c_model;
   const double mass = M.total_mass, imass = 1.0 / mass;
   double sz, cz, sy, cy, sx, cx;
@@ -144,7 +150,7 @@ __device__ __noinline__ void model_values(const double (&xb)[12], const double (
   for (int leg = 0; leg < 2; ++leg) {
     m3 Rp = Rb; v3 pp = pb;
     v3 wJ = mk(0.0, 0.0, 0.0), vJ = mk(0.0, 0.0, 0.0);
-#pragma unroll
+#pragma unroll MVU
     for (int i = 0; i < NL; ++i) {
       const int j = leg * NL + i;
       const v3 o = mulc(Rp.m, M.pj[j]) + pp;
