@@ -538,9 +538,8 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
         double v0 = (R == 6 || C0 == 6) ? 0.0 : c0, v1 = (R == 6) ? 0.0 : c1;
         if (R == C0 && R < NX) v0 += dt * sQd[R] + dq;
         if (R == C0 + 1 && R < NX) v1 += dt * sQd[R] + dq;
-        // Qt is symmetric: tiles below the diagonal are not stored, the ones above it are stored doubled (k_riccati_warp symmetrises S' + S'^T)
-        if (mt == nt) *reinterpret_cast<double2*>(so + S::S_QF + (mt * 3 + nt) * 64 + 2 * lane) = make_double2(v0, v1);
-        else if (mt < nt) *reinterpret_cast<double2*>(so + S::S_QF + (mt * 3 + nt) * 64 + 2 * lane) = make_double2(2.0 * v0, 2.0 * v1);
+        // Qt is symmetric: tiles below the diagonal are not stored (k_riccati_warp computes the upper tiles of S' only and mirrors them)
+        if (mt <= nt) *reinterpret_cast<double2*>(so + S::S_QF + (mt * 3 + nt) * 64 + 2 * lane) = make_double2(v0, v1);
       } else if (nt < 3) {             // mt == 3: Pt rows t = g (zero beyond mj); column 6 is the rt correction of the null-space inputs
         if (nt == 0 && q == 3 && g < mj) so[S::S_R + g] = c0;
         *reinterpret_cast<double2*>(so + S::S_PRF + (0 * 5 + nt) * 64 + 2 * lane) = make_double2((C0 == 6) ? 0.0 : c0, c1);

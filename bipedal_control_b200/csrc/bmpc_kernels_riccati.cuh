@@ -200,8 +200,8 @@ __global__ void __launch_bounds__(32 * RIC_WPC, RIC_BLOCKS) k_riccati_warp(Dev d
     for (int a = 0; a < 3; ++a)
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        // Qt is symmetric: only the tiles on and above the diagonal are stored (the off-diagonal ones doubled); the symmetrisation at the end
-        // of the stage, S = (S' + S'^T) / 2, restores both halves
+        // S' is symmetric: only its tiles on and above the diagonal are computed (Qt is stored that way too); the end of the stage mirrors the
+        // off-diagonal tiles and symmetrises the diagonal ones
         if (c >= a) { const double2 v = *reinterpret_cast<const double2*>(grec + S::S_QF + (a * 3 + c) * 64 + 2 * lane); Sn[a][c][0] = v.x; Sn[a][c][1] = v.y; }
         else { Sn[a][c][0] = 0.0; Sn[a][c][1] = 0.0; }
       }
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(32 * RIC_WPC, RIC_BLOCKS) k_riccati_warp(Dev d
       for (int mt = 0; mt < 3; ++mt) {
         const double a0 = AB[(8 * kb + 2 * q) * LDA + 8 * mt + g], a1 = AB[(8 * kb + 2 * q + 1) * LDA + 8 * mt + g];
 #pragma unroll
-        for (int nt = 0; nt < 3; ++nt) { dmma884(Sn[mt][nt][0], Sn[mt][nt][1], a0, Z[nt][kb][0]); dmma884(Sn[mt][nt][0], Sn[mt][nt][1], a1, Z[nt][kb][1]); }
+        for (int nt = mt; nt < 3; ++nt) { dmma884(Sn[mt][nt][0], Sn[mt][nt][1], a0, Z[nt][kb][0]); dmma884(Sn[mt][nt][0], Sn[mt][nt][1], a1, Z[nt][kb][1]); }
       }
     // ---- the staged record is free: prefetch the next stage while the Cholesky chain runs
     __syncwarp();
@@ -264,19 +264,22 @@ __global__ void __launch_bounds__(32 * RIC_WPC, RIC_BLOCKS) k_riccati_warp(Dev d
 #pragma unroll
         for (int mt = 0; mt < 3; ++mt)
 #pragma unroll
-          for (int nt = 0; nt < 3; ++nt) dmma884(Sn[mt][nt][0], Sn[mt][nt][1], -y[mt], y[nt]);
+          for (int nt = mt; nt < 3; ++nt) dmma884(Sn[mt][nt][0], Sn[mt][nt][1], -y[mt], y[nt]);
       }
     }
-    // ---- symmetrise: S = (S' + S'^T) / 2.  Element (8 nt + 2q + s, 8 mt + g) of tile (nt, mt) lives in lane (2q + s) * 4 + g / 2, slot g & 1
+    // ---- S from the upper tiles of S'.  Element (8 nt + 2q + s, 8 mt + g) of tile (nt, mt) lives in lane (2q + s) * 4 + g / 2, slot g & 1:
+    //      diagonal tiles are symmetrised, (S' + S'^T) / 2; a tile below the diagonal is the transpose of its mirror image
 #pragma unroll
     for (int mt = 0; mt < 3; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 3; ++nt)
+      for (int nt = mt; nt < 3; ++nt)
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl) {
           const int src = (2 * q + sl) * 4 + (g >> 1);
-          const double t0 = __shfl_sync(0xffffffffu, Sn[nt][mt][0], src), t1 = __shfl_sync(0xffffffffu, Sn[nt][mt][1], src);
-          Sf[mt][nt][sl] = 0.5 * (Sn[mt][nt][sl] + ((g & 1) ? t1 : t0));
+          const double t0 = __shfl_sync(0xffffffffu, Sn[mt][nt][0], src), t1 = __shfl_sync(0xffffffffu, Sn[mt][nt][1], src);
+          const double tr = (g & 1) ? t1 : t0;   // transposed element
+          if (mt == nt) Sf[mt][mt][sl] = 0.5 * (Sn[mt][mt][sl] + tr);
+          else { Sf[mt][nt][sl] = Sn[mt][nt][sl]; Sf[nt][mt][sl] = tr; }
         }
     __syncwarp();   // HG / gv / sb are rewritten by the next stage
   }
