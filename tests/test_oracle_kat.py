@@ -646,3 +646,40 @@ def test_in_warp_gauss_jordan_equals_fullpivlu_emulation(mode, robot):
         Nj = Pu1[12:, :]
         Nj = Nj[:, np.abs(Nj).max(axis=0) > 0]
         assert Nj.shape[1] == mj and np.linalg.matrix_rank(np.concatenate([N, Nj], axis=1), tol=1e-9) == mj
+
+
+# ---------------------------------------------------------------- design check of the CUDA forward sweep (k_forward)
+def test_forward_sweep_with_the_original_dynamics_and_their_structure(h1_model_path):
+    """k_forward never forms the closed-loop map Phi = At + Bt Kt of the projected problem: it applies the ORIGINAL RK2 sensitivities of the compact LQ
+    record, dx+ = A_d dx + B_d du + b with du = K dx + kappa, and relies on their structure (rows 0..2 of A_d - I vanish and B_d rows 0..2 are
+    dt/m [I I I I]; rows 12.. of A_d - I vanish and B_d rows 12.. are dt I; the base-position columns 6..8 of A_d - I vanish).  Checked here on the oracle's
+    dense matrices and its own step (computed in projected coordinates) over cold + warm tick of a trot with an event inside the horizon."""
+    import helpers
+    from tools.ingest import read_model
+    mdl = read_model(h1_model_path)
+    o = Oracle(h1_model_path)
+    x0 = o.initial_state()
+    et, ms = helpers.config2(o.nx, x0, None, None)
+    tt, ts = helpers.cmd_vel_target(x0, 0.0, (0.3, 0.1, 0.0, 0.2), 1.0, mdl["com_height"], mdl["default_joint_state"])
+    o.set_dt_horizon(0.01, 0.25); o.set_mode_schedule(et, ms); o.set_target(tt, ts)
+    nx, nu, mass = o.nx, o.nu, o.total_mass
+    for tick in range(2):
+        o.run(0.0, x0)
+        st = o.step()
+        n = o.info()["n_nodes"]
+        seen_event = False
+        for k in range(n - 1):
+            lq = o.node_lq(k)
+            dx, dxn = st["dx"][k], st["dx"][k + 1]
+            if lq["type"] != 0:                                    # event node: A = I, no input
+                seen_event = True
+                np.testing.assert_allclose(dxn, dx + lq["b"], atol=1e-12)
+                continue
+            A, B, dt = lq["A"], lq["B"], lq["dt"]
+            np.testing.assert_allclose(dxn, A @ dx + B @ st["du"][k] + lq["b"], rtol=0, atol=1e-9 * max(1.0, np.abs(dxn).max()))
+            AmI = A - np.eye(nx)
+            assert np.abs(AmI[0:3]).max() == 0.0 and np.abs(AmI[12:]).max() == 0.0 and np.abs(AmI[:, 6:9]).max() == 0.0
+            np.testing.assert_allclose(B[0:3, 0:12], dt / mass * np.tile(np.eye(3), (1, 4)), rtol=1e-14, atol=0)
+            assert np.abs(B[0:3, 12:]).max() == 0.0 and np.abs(B[12:, 0:12]).max() == 0.0
+            np.testing.assert_allclose(B[12:, 12:], dt * np.eye(nu - 12), rtol=1e-14, atol=0)
+        assert seen_event
