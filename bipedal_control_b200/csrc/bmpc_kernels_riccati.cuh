@@ -111,7 +111,10 @@ __device__ __forceinline__ bool chol_stage(double* __restrict__ HG, int lane, do
 // lands while the warp runs the Cholesky chain.
 template <int NJ>
 struct RicWarpSmem {
-  static constexpr int LDH = 44;
+#ifndef RIC_LDH
+#define RIC_LDH 44
+#endif
+  static constexpr int LDH = RIC_LDH;   // row of the staged [H (24) | G (16) | g]: 41 used; 42 lets 16 warps per SM fit (measured slower)
   alignas(16) double rec[SDims<NJ>::TMA_DOUBLES];   // AB | bt | qt | rt | meta (TMA destination)
   alignas(16) double HG[16 * LDH];                   // [H | G] fragments -> column layout for the Cholesky; afterwards [Y | L]
   double sb[24];
