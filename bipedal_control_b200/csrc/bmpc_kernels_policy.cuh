@@ -31,7 +31,7 @@ __device__ __forceinline__ void back_substitute(double (&z)[MP], const double (&
 }
 
 template <int NJ>
-__global__ void __launch_bounds__(128, 4) k_policy_expand(Dev d) {
+__global__ void __launch_bounds__(128, EXP_BLOCKS) k_policy_expand(Dev d) {
   using D = Dims<NJ>; using R = RDims<NJ>; using S = SDims<NJ>; using PS = PolSmem<NJ>;
   constexpr int NX = D::NX, NU = D::NU, NXA = D::NXA, MP = S::MP, WPB = 4, LDK = PS::LDK;
   extern __shared__ __align__(16) unsigned char smem_raw[];
