@@ -95,71 +95,96 @@ __device__ inline double swing_zref(const double* ev, const int* modes, int ne, 
   return (3.0 * c3 * tn * tn + 2.0 * c2 * tn + c1) / dts;
 }
 
-// one thread per node (a warp-per-node variant with coalesced 22-wide accesses was 2.7x slower: the kernel is bound by the scalar lookup
-// chains, which every lane of a warp would repeat)
+// One thread per node for the scalar lookup chains (a warp-per-node variant was 2.7x slower: every lane of a warp would repeat them), which only
+// DESCRIBE the three vectors a node gets (x_ref, warm-start state, warm-start input) as "alpha * a[] + (1 - alpha) * b[]" with two source rows;
+// the CTA then writes the vectors of its 128 consecutive nodes together, element by element, so the 22-wide rows are read and written coalesced
+// (the per-thread row loops of the first version ran at a quarter of the HBM bandwidth).
+struct VecDesc { const double* a; const double* b; double al; double fz; int kind; };   // kind 0: none, 1: blend, 2: zero, 3: initializer input (fz, stance bits in al)
+__device__ __forceinline__ VecDesc blend_desc(const double* ta, const double* data, int n, int dim, double t) {
+  VecDesc v; v.fz = 0.0; v.kind = 1;
+  if (n <= 1) { v.a = data; v.b = data; v.al = 1.0; return v; }
+  int idx; double al; time_segment(ta, n, t, idx, al);
+  v.a = data + (size_t)idx * dim; v.b = v.a + dim; v.al = al;
+  return v;
+}
 template <int NJ>
-__global__ void k_node_setup(Dev d) {
+__global__ void __launch_bounds__(128) k_node_setup(Dev d) {
   constexpr int NX = Dims<NJ>::NX, NU = Dims<NJ>::NU;
+  __shared__ VecDesc sd[3][128];
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = gid / d.NS, k = gid % d.NS;
-  if (b >= d.B) return;
-  const int n = d.n_nodes[b];
-  if (k >= n) return;
-  const int N = n - 1;
-  const size_t nb = (size_t)b * d.NS;
-  const double* ev = d.ev_t + (size_t)b * d.ME; const int* modes = d.ev_mode + (size_t)b * (d.ME + 1); const int ne = d.n_ev[b];
-  const int* nev = d.node_ev + nb;
-  const double* nt = d.node_t + nb;
-  const double* stt = d.st_t + nb; const double* std_ = d.st_dt + nb;
-  // ---- stage references
-  if (k < N) {
-    int mode = -1;
-    if (nev[k] != 1) {
-      const double t = stt[k];
-      mode = modes[lower_bound_d(ev, ne, t)];
-      interp_vec(d.tgt_t + (size_t)b * d.TP, d.tgt_x + (size_t)b * d.TP * NX, d.npts, NX, t, d.xref + (nb + k) * NX);
-      for (int leg = 0; leg < 2; ++leg) {   // per leg: reference height velocity, and position (used only with positionErrorGain != 0); terrain height 0 in stance
-        double zp = 0.0;
-        const double zv = leg_in_stance(mode, leg) ? 0.0 : swing_zref(ev, modes, ne, leg, t, &d.status[b], &zp);
-        d.zref[(nb + k) * 4 + leg] = zv; d.zref[(nb + k) * 4 + 2 + leg] = zp;
+  VecDesc dr, dx, du; dr.kind = 0; dx.kind = 0; du.kind = 0;
+  dr.a = dr.b = dx.a = dx.b = du.a = du.b = nullptr; dr.al = dx.al = du.al = 0.0; dr.fz = dx.fz = du.fz = 0.0;
+  const int n = b < d.B ? d.n_nodes[b] : 0;
+  if (k < n) {
+    const int N = n - 1;
+    const size_t nb = (size_t)b * d.NS;
+    const double* ev = d.ev_t + (size_t)b * d.ME; const int* modes = d.ev_mode + (size_t)b * (d.ME + 1); const int ne = d.n_ev[b];
+    const int* nev = d.node_ev + nb;
+    const double* nt = d.node_t + nb;
+    const double* stt = d.st_t + nb; const double* std_ = d.st_dt + nb;
+    // ---- stage references
+    if (k < N) {
+      int mode = -1;
+      if (nev[k] != 1) {
+        const double t = stt[k];
+        mode = modes[lower_bound_d(ev, ne, t)];
+        dr = blend_desc(d.tgt_t + (size_t)b * d.TP, d.tgt_x + (size_t)b * d.TP * NX, d.npts, NX, t);
+        for (int leg = 0; leg < 2; ++leg) {   // per leg: reference height velocity, and position (used only with positionErrorGain != 0); terrain height 0 in stance
+          double zp = 0.0;
+          const double zv = leg_in_stance(mode, leg) ? 0.0 : swing_zref(ev, modes, ne, leg, t, &d.status[b], &zp);
+          d.zref[(nb + k) * 4 + leg] = zv; d.zref[(nb + k) * 4 + 2 + leg] = zp;
+        }
       }
+      d.st_mode[nb + k] = mode;
     }
-    d.st_mode[nb + k] = mode;
+    // ---- initial guess: [UPSTREAM] multiple_shooting::initializeStateInputTrajectories
+    const int pn = d.p_n ? d.p_n[b] : 0;
+    const double* pt = d.p_t + nb; const double* px = d.p_x + nb * NX; const double* pu = d.p_u + nb * NU;
+    double stateTill = nt[0], inputTill = nt[0];
+    if (pn >= 2) { stateTill = pt[pn - 1]; inputTill = pt[pn - 2]; }
+    auto interval_uses_initializer = [&](int i) {   // interval i = [node i, node i+1]; true also for event nodes (state copied)
+      if (nev[i] == 1) return true;
+      const double ti = stt[i], tn = stt[i] + std_[i];
+      return (ti > inputTill || tn > stateTill);
+    };
+    // state of node k
+    int j = k;
+    while (j > 0 && interval_uses_initializer(j - 1)) --j;
+    if (j == 0) {
+      const double tinit = nev[0] == 2 ? nt[0] + WEAK_EPS : nt[0];
+      if (tinit < stateTill) dx = blend_desc(pt, px, pn, NX, tinit);
+      else { dx.kind = 1; dx.a = dx.b = d.x0 + (size_t)b * NX; dx.al = 1.0; }
+    } else dx = blend_desc(pt, px, pn, NX, stt[j - 1] + std_[j - 1]);
+    // input of stage k
+    if (k < N) {
+      if (nev[k] == 1) du.kind = 2;
+      else if (interval_uses_initializer(k)) {   // initialization/BipedalRobotInitializer.cpp:56-63 + common/utils.h:63-77
+        const int mode = modes[lower_bound_d(ev, ne, stt[k])];
+        const bool s0 = leg_in_stance(mode, 0), s1 = leg_in_stance(mode, 1);
+        const int ns = 2 * (int(s0) + int(s1));
+        du.kind = 3; du.fz = ns > 0 ? c_model.total_mass * 9.81 / ns : 0.0; du.al = (s0 ? 1.0 : 0.0) + (s1 ? 2.0 : 0.0);
+      } else du = blend_desc(pt, pu, pn, NU, stt[k]);
+    }
   }
-  // ---- initial guess: [UPSTREAM] multiple_shooting::initializeStateInputTrajectories
-  const int pn = d.p_n ? d.p_n[b] : 0;
-  const double* pt = d.p_t + nb; const double* px = d.p_x + nb * NX; const double* pu = d.p_u + nb * NU;
-  double stateTill = nt[0], inputTill = nt[0];
-  if (pn >= 2) { stateTill = pt[pn - 1]; inputTill = pt[pn - 2]; }
-  auto interval_uses_initializer = [&](int i) {   // interval i = [node i, node i+1]; true also for event nodes (state copied)
-    if (nev[i] == 1) return true;
-    const double ti = stt[i], tn = stt[i] + std_[i];
-    return (ti > inputTill || tn > stateTill);
-  };
-  // state of node k
-  int j = k;
-  while (j > 0 && interval_uses_initializer(j - 1)) --j;
-  double* xo = d.s_x + (nb + k) * NX;
-  if (j == 0) {
-    const double tinit = nev[0] == 2 ? nt[0] + WEAK_EPS : nt[0];
-    if (tinit < stateTill) interp_vec(pt, px, pn, NX, tinit, xo);
-    else for (int i = 0; i < NX; ++i) xo[i] = d.x0[(size_t)b * NX + i];
-  } else {
-    interp_vec(pt, px, pn, NX, stt[j - 1] + std_[j - 1], xo);
-  }
-  // input of stage k
-  if (k < N) {
-    double* uo = d.s_u + (nb + k) * NU;
-    if (nev[k] == 1) { for (int i = 0; i < NU; ++i) uo[i] = 0.0; }
-    else if (interval_uses_initializer(k)) {   // initialization/BipedalRobotInitializer.cpp:56-63 + common/utils.h:63-77
-      const int mode = modes[lower_bound_d(ev, ne, stt[k])];
-      const bool s0 = leg_in_stance(mode, 0), s1 = leg_in_stance(mode, 1);
-      const int ns = 2 * (int(s0) + int(s1));
-      const double fz = ns > 0 ? c_model.total_mass * 9.81 / ns : 0.0;
-      for (int i = 0; i < NU; ++i) uo[i] = 0.0;
-      if (s0) { uo[2] = fz; uo[5] = fz; }
-      if (s1) { uo[8] = fz; uo[11] = fz; }
-    } else interp_vec(pt, pu, pn, NU, stt[k], uo);
+  sd[0][threadIdx.x] = dr; sd[1][threadIdx.x] = dx; sd[2][threadIdx.x] = du;
+  __syncthreads();
+  // ---- the CTA's 128 nodes are consecutive rows of xref / s_x / s_u: element e of the block = (node e / dim, component e % dim)
+  const size_t row0 = (size_t)blockIdx.x * blockDim.x;
+  static_assert(NX == NU, "one element loop serves the three vectors");
+  for (int e = threadIdx.x; e < 128 * NX; e += 128) {
+    const int nd = e / NX, c = e - nd * NX;
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      const VecDesc q = sd[v][nd];
+      if (q.kind == 0) continue;
+      double* out = (v == 0 ? d.xref : (v == 1 ? d.s_x : d.s_u)) + (row0 + nd) * NX + c;
+      double val;
+      if (q.kind == 1) val = q.al * q.a[c] + (1.0 - q.al) * q.b[c];
+      else if (q.kind == 2) val = 0.0;
+      else { const int st = (int)q.al; val = ((c == 2 || c == 5) && (st & 1)) || ((c == 8 || c == 11) && (st & 2)) ? q.fz : 0.0; }
+      *out = val;
+    }
   }
 }
 
