@@ -125,7 +125,10 @@ template <int NJ>
 __global__ void __launch_bounds__(32 * RIC_WPC, RIC_BLOCKS) k_riccati_warp(Dev d) {
   using D = Dims<NJ>; using R = RDims<NJ>; using S = SDims<NJ>; using SM = RicWarpSmem<NJ>;
   constexpr int NX = D::NX, MP = S::MP, LDA = S::LDA, LDH = SM::LDH;
-  constexpr unsigned TMA_BYTES = S::TMA_DOUBLES * sizeof(double);
+  // the staged record arrives as two bulk copies on one barrier: rows 0..NX-1 of AB and the tail [bt | qt | rt | meta]; the zero padding rows NX..23 of
+  // AB are written once here and never fetched
+  constexpr unsigned AB_BYTES = NX * LDA * sizeof(double), TAIL_BYTES = (S::TMA_DOUBLES - S::S_B) * sizeof(double);
+  static_assert(AB_BYTES % 16 == 0 && TAIL_BYTES % 16 == 0 && (S::S_B * sizeof(double)) % 16 == 0, "bulk copies need 16-byte multiples");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // broadcast: lets the compiler treat the warp index as warp-uniform
   const int b = blockIdx.x * RIC_WPC + warp;
@@ -141,8 +144,14 @@ __global__ void __launch_bounds__(32 * RIC_WPC, RIC_BLOCKS) k_riccati_warp(Dev d
     for (int c = 0; c < 3; ++c) { Sf[a][c][0] = 0.0; Sf[a][c][1] = 0.0; }   // terminal value function: zero (no terminal cost installed)
   double s_l = 0.0;   // lane r < 24 holds s[r]
   if (lane == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
+  for (int i = lane; i < (S::NXP - NX) * LDA; i += 32) sm.rec[S::S_AB + NX * LDA + i] = 0.0;
   __syncwarp();
-  if (lane == 0 && N >= 1) tma_load_1d(sm.rec, d.stage + (nb + N - 1) * S::SREC, TMA_BYTES, &sm.bar);
+  auto stage_fetch = [&](const double* src) {   // one lane
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm.bar)), "r"(AB_BYTES + TAIL_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm.rec)), "l"(src), "r"(AB_BYTES), "r"(smem_u32(&sm.bar)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm.rec + S::S_B)), "l"(src + S::S_B), "r"(TAIL_BYTES), "r"(smem_u32(&sm.bar)) : "memory");
+  };
+  if (lane == 0 && N >= 1) { fence_proxy_async(); stage_fetch(d.stage + (nb + N - 1) * S::SREC); }
   unsigned phase_bit = 0;
   const double* sr = sm.rec;
   const double* AB = sm.rec + S::S_AB;
@@ -174,16 +183,20 @@ __global__ void __launch_bounds__(32 * RIC_WPC, RIC_BLOCKS) k_riccati_warp(Dev d
       if (is_event) {   // A = I, Q = 0, no input: S unchanged, s <- s + S b
         s_l = sbv;
         __syncwarp();
-        if (lane == 0 && k >= 1) { fence_proxy_async(); tma_load_1d(sm.rec, d.stage + (nb + k - 1) * S::SREC, TMA_BYTES, &sm.bar); }
+        if (lane == 0 && k >= 1) { fence_proxy_async(); stage_fetch(d.stage + (nb + k - 1) * S::SREC); }
         continue;
       }
     }
     // accumulator initialisers, fragment ordered in global memory: [Pt | Rt] now, Qt below (in flight during the products)
+    // (rows 8..15 of Pt belong to closed-contact forces: the state-input cross Hessian vanishes there, k_project never writes those three tiles)
     double HGf[2][5][2];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int c = 0; c < 5; ++c) { const double2 v = *reinterpret_cast<const double2*>(grec + S::S_PRF + (a * 5 + c) * 64 + 2 * lane); HGf[a][c][0] = v.x; HGf[a][c][1] = v.y; }
+      for (int c = 0; c < 5; ++c) {
+        if (a == 1 && c < 3) { HGf[a][c][0] = 0.0; HGf[a][c][1] = 0.0; continue; }
+        const double2 v = *reinterpret_cast<const double2*>(grec + S::S_PRF + (a * 5 + c) * 64 + 2 * lane); HGf[a][c][0] = v.x; HGf[a][c][1] = v.y;
+      }
     // ---- step A: Z^T = AB^T S   (Z[mt][nt] holds (S AB)[8 nt + 2q + slot][8 mt + g])
     double Z[5][3][2];
 #pragma unroll
@@ -236,7 +249,7 @@ __global__ void __launch_bounds__(32 * RIC_WPC, RIC_BLOCKS) k_riccati_warp(Dev d
       }
     // ---- the staged record is free: prefetch the next stage while the Cholesky chain runs
     __syncwarp();
-    if (lane == 0 && k >= 1) { fence_proxy_async(); tma_load_1d(sm.rec, d.stage + (nb + k - 1) * S::SREC, TMA_BYTES, &sm.bar); }
+    if (lane == 0 && k >= 1) { fence_proxy_async(); stage_fetch(d.stage + (nb + k - 1) * S::SREC); }
     // ---- step C: [H | G] fragments -> shared memory -> one column per lane ; Cholesky of G fused with the forward substitution of [H | g]
 #pragma unroll
     for (int a = 0; a < 2; ++a)
