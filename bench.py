@@ -317,7 +317,7 @@ class Runner:
 
     def e2e_bytes(self):
         B, nx, nu = self.B, self.mpc.nx, self.mpc.nu
-        h2d = 2 * B * 8 * (1 + nx) + B * 2 * 8 * (1 + nx) + B * (4 + ME * 8 + (ME + 1) * 4)   # evaluatePolicy query + observation, targets, mode schedules
+        h2d = 2 * B * 8 * (1 + nx) + B * 4 * 8 + B * (4 + ME * 8 + (ME + 1) * 4)   # evaluatePolicy query + observation, velocity commands (targets are built on the device), mode schedules
         d2h = B * 8 * 8 + B * 8 * (nx + nu) + B * 4 + 32                                     # performance indices + evaluatePolicy result + tick counters
         return int(h2d), int(d2h)
 

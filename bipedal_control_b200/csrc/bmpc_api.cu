@@ -80,7 +80,7 @@ struct bmpc_handle {
   // inputs (device) and their pinned staging copies
   double *d_t0 = nullptr, *d_x0 = nullptr, *d_tgt_t = nullptr, *d_tgt_x = nullptr, *d_ev_t = nullptr;
   int *d_n_ev = nullptr, *d_ev_mode = nullptr;
-  double *h_t0 = nullptr, *h_x0 = nullptr, *h_tgt_t = nullptr, *h_tgt_x = nullptr, *h_ev_t = nullptr;
+  double *h_t0 = nullptr, *h_x0 = nullptr, *h_tgt_t = nullptr, *h_tgt_x = nullptr, *h_ev_t = nullptr, *h_cmd = nullptr, *d_cmd = nullptr;
   int *h_n_ev = nullptr, *h_ev_mode = nullptr;
   bool obs_dirty = false, tgt_dirty = false, sched_dirty = false, have_obs = false, have_tgt = false, have_sched = false;
   int npts = 0;
@@ -396,7 +396,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     DevPool& P = h->pool;
     h->d_t0 = P.d<double>(B); h->d_x0 = P.d<double>(B * nx); h->d_tgt_t = P.d<double>(B * h->TP); h->d_tgt_x = P.d<double>(B * h->TP * nx);
     h->d_n_ev = P.d<int>(B); h->d_ev_t = P.d<double>(B * h->ME); h->d_ev_mode = P.d<int>(B * (h->ME + 1));
-    h->h_t0 = P.h<double>(B); h->h_x0 = P.h<double>(B * nx); h->h_tgt_t = P.h<double>(B * h->TP); h->h_tgt_x = P.h<double>(B * h->TP * nx);
+    h->h_cmd = P.h<double>(B * 4); h->d_cmd = P.d<double>(B * 4); h->h_t0 = P.h<double>(B); h->h_x0 = P.h<double>(B * nx); h->h_tgt_t = P.h<double>(B * h->TP); h->h_tgt_x = P.h<double>(B * h->TP * nx);
     h->h_n_ev = P.h<int>(B); h->h_ev_t = P.h<double>(B * h->ME); h->h_ev_mode = P.h<int>(B * (h->ME + 1));
     h->d_st_t = P.d<double>(B * NS); h->d_st_dt = P.d<double>(B * NS); h->d_st_mode = P.d<int>(B * NS);
     h->d_xref = P.d<double>(B * NS * nx); h->d_zref = P.d<double>(B * NS * 4);
@@ -519,27 +519,23 @@ int bmpc_set_target_trajectories_device(bmpc_handle* h, int npts, const double* 
 }
 // TargetTrajectoriesPublisher.cpp:41-99
 int bmpc_set_targets_from_cmd_vel(bmpc_handle* h, const double* cmd, double time_to_target) {
+  // host command buffer -> the same device kernel as bmpc_set_targets_from_cmd_vel_device (k_cmd_vel_targets, cmdVelToTargetTrajectories of
+  // TargetTrajectoriesPublisher.cpp:76-99): only the 4 command values per instance cross PCIe, not two full target states
   API_BEGIN if (!h || !cmd) throw std::invalid_argument("[bmpc] null argument");
+  CK(cudaSetDevice(h->device));
   std::lock_guard<std::mutex> lk(h->mtx);
   if (!h->have_obs) throw std::invalid_argument("[bmpc] set observations (host) before bmpc_set_targets_from_cmd_vel");
   if (h->TP < 2) throw std::length_error("[bmpc] max_target_points < 2");
   staging_ready(h);
-  const int nx = h->nx, nj = h->nj;
-  for (int b = 0; b < h->B; ++b) {
-    const double* x = h->h_x0 + (size_t)b * nx; const double* c = cmd + (size_t)b * 4;
-    const double z = x[9], y = x[10], r = x[11];
-    const double cz = std::cos(z), sz = std::sin(z), cy = std::cos(y), sy = std::sin(y), cx = std::cos(r), sx = std::sin(r);
-    const double R[9] = {cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx, sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx, -sy, cy * sx, cy * cx};
-    const double vr[3] = {R[0] * c[0] + R[1] * c[1] + R[2] * c[2], R[3] * c[0] + R[4] * c[1] + R[5] * c[2], R[6] * c[0] + R[7] * c[1] + R[8] * c[2]};
-    double* s0 = h->h_tgt_x + (size_t)b * h->TP * nx; double* s1 = s0 + nx;
-    std::fill(s0, s0 + 2 * nx, 0.0);
-    s0[0] = s1[0] = vr[0]; s0[1] = s1[1] = vr[1]; s0[2] = s1[2] = vr[2];
-    s0[6] = x[6]; s0[7] = x[7]; s0[8] = h->model.com_height; s0[9] = x[9];
-    s1[6] = x[6] + vr[0] * time_to_target; s1[7] = x[7] + vr[1] * time_to_target; s1[8] = h->model.com_height; s1[9] = x[9] + c[3] * time_to_target;
-    for (int j = 0; j < nj; ++j) { s0[12 + j] = h->model.default_joint_state[j]; s1[12 + j] = h->model.default_joint_state[j]; }
-    h->h_tgt_t[(size_t)b * h->TP] = h->h_t0[b]; h->h_tgt_t[(size_t)b * h->TP + 1] = h->h_t0[b] + time_to_target;
-  }
-  h->npts = 2; h->tgt_dirty = true; h->have_tgt = true; return BMPC_OK; API_END(h)
+  const int B = h->B; cudaStream_t st = h->stream;
+  std::memcpy(h->h_cmd, cmd, sizeof(double) * 4 * (size_t)B);
+  upload_inputs(h);   // the observation the command refers to (as the host version used the observation set before this call)
+  CK(cudaMemcpyAsync(h->d_cmd, h->h_cmd, sizeof(double) * 4 * (size_t)B, cudaMemcpyHostToDevice, st));
+  if (h->nj == 10) k_cmd_vel_targets<10><<<(B + 127) / 128, 128, 0, st>>>(B, h->TP, h->d_t0, h->d_x0, h->d_cmd, time_to_target, h->model.com_height, h->d_default_joints, h->d_tgt_t, h->d_tgt_x);
+  else k_cmd_vel_targets<12><<<(B + 127) / 128, 128, 0, st>>>(B, h->TP, h->d_t0, h->d_x0, h->d_cmd, time_to_target, h->model.com_height, h->d_default_joints, h->d_tgt_t, h->d_tgt_x);
+  CK(cudaEventRecord(h->ev_inputs, st)); h->upload_inflight = true;   // h_cmd is pinned staging like the others
+  h->npts = 2; h->tgt_dirty = false; h->have_tgt = true; CK(cudaGetLastError());
+  return BMPC_OK; API_END(h)
 }
 int bmpc_set_mode_schedules(bmpc_handle* h, int stride, const int* n_events, const double* event_times, const int* mode_sequence) {
   API_BEGIN if (!h || !n_events || !event_times || !mode_sequence) throw std::invalid_argument("[bmpc] null argument");
