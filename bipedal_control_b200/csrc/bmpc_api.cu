@@ -519,29 +519,56 @@ int bmpc_set_target_trajectories_device(bmpc_handle* h, int npts, const double* 
 }
 // TargetTrajectoriesPublisher.cpp:41-99
 int bmpc_set_targets_from_cmd_vel(bmpc_handle* h, const double* cmd, double time_to_target) {
-  // host command buffer -> the same device kernel as bmpc_set_targets_from_cmd_vel_device (k_cmd_vel_targets, cmdVelToTargetTrajectories of
-  // TargetTrajectoriesPublisher.cpp:76-99): only the 4 command values per instance cross PCIe, not two full target states
+  // cmdVelToTargetTrajectories (TargetTrajectoriesPublisher.cpp:76-99) for every instance, from the observation set before this call.
   API_BEGIN if (!h || !cmd) throw std::invalid_argument("[bmpc] null argument");
   CK(cudaSetDevice(h->device));
   std::lock_guard<std::mutex> lk(h->mtx);
   if (!h->have_obs) throw std::invalid_argument("[bmpc] set observations (host) before bmpc_set_targets_from_cmd_vel");
   if (h->TP < 2) throw std::length_error("[bmpc] max_target_points < 2");
   staging_ready(h);
-  const int B = h->B; cudaStream_t st = h->stream;
-  std::memcpy(h->h_cmd, cmd, sizeof(double) * 4 * (size_t)B);
-  upload_inputs(h);   // the observation the command refers to (as the host version used the observation set before this call)
-  CK(cudaMemcpyAsync(h->d_cmd, h->h_cmd, sizeof(double) * 4 * (size_t)B, cudaMemcpyHostToDevice, st));
-  if (h->nj == 10) k_cmd_vel_targets<10><<<(B + 127) / 128, 128, 0, st>>>(B, h->TP, h->d_t0, h->d_x0, h->d_cmd, time_to_target, h->model.com_height, h->d_default_joints, h->d_tgt_t, h->d_tgt_x);
-  else k_cmd_vel_targets<12><<<(B + 127) / 128, 128, 0, st>>>(B, h->TP, h->d_t0, h->d_x0, h->d_cmd, time_to_target, h->model.com_height, h->d_default_joints, h->d_tgt_t, h->d_tgt_x);
-  CK(cudaEventRecord(h->ev_inputs, st)); h->upload_inflight = true;   // h_cmd is pinned staging like the others
-  h->npts = 2; h->tgt_dirty = false; h->have_tgt = true; CK(cudaGetLastError());
-  return BMPC_OK; API_END(h)
+  const int B = h->B;
+  try_publish(h);
+  if (!h->pending) {
+    // no tick in flight: the same device kernel as bmpc_set_targets_from_cmd_vel_device; only the 4 command values per instance cross PCIe
+    cudaStream_t st = h->stream;
+    std::memcpy(h->h_cmd, cmd, sizeof(double) * 4 * (size_t)B);
+    upload_inputs(h);   // the observation the command refers to
+    CK(cudaMemcpyAsync(h->d_cmd, h->h_cmd, sizeof(double) * 4 * (size_t)B, cudaMemcpyHostToDevice, st));
+    if (h->nj == 10) k_cmd_vel_targets<10><<<(B + 127) / 128, 128, 0, st>>>(B, h->TP, h->d_t0, h->d_x0, h->d_cmd, time_to_target, h->model.com_height, h->d_default_joints, h->d_tgt_t, h->d_tgt_x);
+    else k_cmd_vel_targets<12><<<(B + 127) / 128, 128, 0, st>>>(B, h->TP, h->d_t0, h->d_x0, h->d_cmd, time_to_target, h->model.com_height, h->d_default_joints, h->d_tgt_t, h->d_tgt_x);
+    CK(cudaEventRecord(h->ev_inputs, st)); h->upload_inflight = true;   // h_cmd is pinned staging like the others
+    h->npts = 2; h->tgt_dirty = false; h->have_tgt = true; CK(cudaGetLastError());
+    return BMPC_OK;
+  }
+  // a tick is in flight (MRT use: the RT thread feeds the next tick while the MPC thread solves): nothing may queue behind it here, or the next
+  // set_* would wait for the whole tick in staging_ready -- the targets are built on the host into the staging buffers and travel with the next tick
+  const int nx = h->nx, nj = h->nj;
+  for (int b = 0; b < B; ++b) {
+    const double* x = h->h_x0 + (size_t)b * nx; const double* c = cmd + (size_t)b * 4;
+    const double z = x[9], y = x[10], r = x[11];
+    const double cz = std::cos(z), sz = std::sin(z), cy = std::cos(y), sy = std::sin(y), cx = std::cos(r), sx = std::sin(r);
+    const double R[9] = {cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx, sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx, -sy, cy * sx, cy * cx};
+    const double vr[3] = {R[0] * c[0] + R[1] * c[1] + R[2] * c[2], R[3] * c[0] + R[4] * c[1] + R[5] * c[2], R[6] * c[0] + R[7] * c[1] + R[8] * c[2]};
+    double* s0 = h->h_tgt_x + (size_t)b * h->TP * nx; double* s1 = s0 + nx;
+    std::fill(s0, s0 + 2 * nx, 0.0);
+    s0[0] = s1[0] = vr[0]; s0[1] = s1[1] = vr[1]; s0[2] = s1[2] = vr[2];
+    s0[6] = x[6]; s0[7] = x[7]; s0[8] = h->model.com_height; s0[9] = x[9];
+    s1[6] = x[6] + vr[0] * time_to_target; s1[7] = x[7] + vr[1] * time_to_target; s1[8] = h->model.com_height; s1[9] = x[9] + c[3] * time_to_target;
+    for (int j = 0; j < nj; ++j) { s0[12 + j] = h->model.default_joint_state[j]; s1[12 + j] = h->model.default_joint_state[j]; }
+    h->h_tgt_t[(size_t)b * h->TP] = h->h_t0[b]; h->h_tgt_t[(size_t)b * h->TP + 1] = h->h_t0[b] + time_to_target;
+  }
+  h->npts = 2; h->tgt_dirty = true; h->have_tgt = true; return BMPC_OK; API_END(h)
 }
 int bmpc_set_mode_schedules(bmpc_handle* h, int stride, const int* n_events, const double* event_times, const int* mode_sequence) {
   API_BEGIN if (!h || !n_events || !event_times || !mode_sequence) throw std::invalid_argument("[bmpc] null argument");
   std::lock_guard<std::mutex> lk(h->mtx);
   for (int b = 0; b < h->B; ++b) if (n_events[b] < 0 || n_events[b] > h->ME || n_events[b] > stride) throw std::length_error("[bmpc] mode schedule exceeds max_events");
   staging_ready(h);
+  if (stride == h->ME) {   // same row length as the staging arrays: three block copies (entries beyond n_events are never read)
+    std::memcpy(h->h_n_ev, n_events, sizeof(int) * (size_t)h->B);
+    std::memcpy(h->h_ev_t, event_times, sizeof(double) * (size_t)h->B * h->ME);
+    std::memcpy(h->h_ev_mode, mode_sequence, sizeof(int) * (size_t)h->B * (h->ME + 1));
+  } else
   for (int b = 0; b < h->B; ++b) {
     const int ne = n_events[b];
     h->h_n_ev[b] = ne;
