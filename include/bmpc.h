@@ -92,7 +92,9 @@ int bmpc_set_target_trajectories(bmpc_handle* h, int npts, const double* times, 
 int bmpc_set_target_trajectories_device(bmpc_handle* h, int npts, const double* times_dev, const double* states_dev);
 
 /* Batched TargetTrajectoriesPublisher::cmdVelToTargetTrajectories (bipedal_controllers/src/TargetTrajectoriesPublisher.cpp:76-99):
- * builds the 2-knot targets from the current observations and cmd[B*4] = (vx, vy, vz, yaw rate); host side. */
+ * builds the 2-knot targets from the observations set before the call and cmd[B*4] = (vx, vy, vz, yaw rate) in host memory.  Only the commands cross
+ * PCIe (the targets are built by the device kernel of the _device variant) unless a tick is in flight, in which case they are built on the host and
+ * travel with the next tick, so that the call never queues behind the solve. */
 int bmpc_set_targets_from_cmd_vel(bmpc_handle* h, const double* cmd, double time_to_target);
 
 int bmpc_set_targets_from_cmd_vel_device(bmpc_handle* h, const double* cmd_dev, double time_to_target); /* same, observations and cmd in HBM */
