@@ -40,22 +40,25 @@ __global__ void __launch_bounds__(128, EXP_BLOCKS) k_policy_expand(Dev d) {
   const int gw = blockIdx.x * WPB + warp;
   const int b = gw / d.NS, k = gw % d.NS;
   if (b >= d.B) return;
-  const int N = d.n_nodes[b] - 1;
-  if (k >= N) return;
   const size_t nb = (size_t)b * d.NS;
   const double* __restrict__ sr = d.stage + (nb + k) * S::SREC;
+  const double* meta = sr + S::S_META;
+  // one round of loads instead of a chain (n_nodes -> stage meta): a slot beyond the horizon holds stale but valid memory and is dropped below
+  const int Nn = d.n_nodes[b];
+  const double m_type = meta[S::T_TYPE], m_m = meta[S::T_M], m_mj = meta[S::T_MJ], m_nc = meta[S::T_NCLOSED], m_mode = meta[S::T_MODE];
+  const int N = Nn - 1;
+  if (k >= N) return;
   double* __restrict__ ric = d.ric + (nb + k) * R::KREC;
   double* __restrict__ Kg = d.s_K + (nb + k) * (size_t)(NU * NX);
   double* __restrict__ uffg = d.s_uff + (nb + k) * NU;
-  const double* meta = sr + S::S_META;
-  if (meta[S::T_TYPE] != 0.0) {   // event stage: K = 0 (k_forward: dx+ = dx + b, du = 0)
+  if (m_type != 0.0) {   // event stage: K = 0 (k_forward: dx+ = dx + b, du = 0)
     for (int i = lane; i < NU; i += 32) { ric[R::K_KAP + i] = 0.0; uffg[i] = 0.0; }
     for (int i = lane; i < NX; i += 32) ric[R::K_G + i] = 0.0;
     for (int i = lane; i < NU * NX; i += 32) Kg[i] = 0.0;
     if (lane == 0) { ric[R::K_MISC] = 0.0; ric[R::K_MISC + 1] = 1.0; }
     return;
   }
-  const int m = (int)meta[S::T_M], mj = (int)meta[S::T_MJ], nclosed = (int)meta[S::T_NCLOSED], mode = (int)meta[S::T_MODE];
+  const int m = (int)m_m, mj = (int)m_mj, nclosed = (int)m_nc, mode = (int)m_mode;
   if (PF_AHEAD >= 0 && (size_t)gw + PF_AHEAD < (size_t)d.B * d.NS) {   // inputs of the stage one wave ahead -> L2 (its m is guessed to be this stage's)
     const size_t ga = (size_t)gw + PF_AHEAD;
     const int mg = m > 0 ? m : 9;

@@ -244,20 +244,24 @@ __global__ void __launch_bounds__(128, PROJ_BLOCKS) k_project(Dev d) {
   const int b = gw / d.NS, k = gw % d.NS;
   if (b >= d.B) return;
   if (PF_AHEAD >= 0 && lane == 0 && (size_t)gw + PF_AHEAD < (size_t)d.B * d.NS) prefetch_l2(d.lq + ((size_t)gw + PF_AHEAD) * D::REC, D::REC * sizeof(double));
-  const int N = d.n_nodes[b] - 1;
-  if (k >= N) return;
   const size_t nb = (size_t)b * d.NS;
   const double* rec = d.lq + (nb + k) * D::REC;
+  // one round of loads instead of a chain (n_nodes -> node_ev -> row count): the stage type / row count / mode of the LQ record are requested together
+  // with n_nodes (a slot beyond the horizon holds stale but valid memory and is dropped below)
+  const int Nn = d.n_nodes[b];
+  const double m_type = rec[D::R_MISC + D::M_TYPE], m_rows = rec[D::R_MISC + D::M_NROWS], m_mode = rec[D::R_MISC + D::M_MODE];
+  const int N = Nn - 1;
+  if (k >= N) return;
   double* out = d.proj + (nb + k) * D::PREC;
   double* so = d.stage + (nb + k) * S::SREC;
-  if (d.node_ev[nb + k] == 1) {   // event stage: only b is needed
+  if (m_type != 0.0) {   // event stage (k_lq_pack marks it in the record): only b is needed
     for (int i = lane; i < NX; i += 32) so[S::S_B + i] = rec[D::R_B + i];
     if (lane == 0) { so[S::S_META + S::T_TYPE] = 1.0; so[S::S_META + S::T_M] = 0.0; so[S::S_META + S::T_MJ] = 0.0; so[S::S_META + S::T_NCLOSED] = 0.0; so[S::S_META + S::T_DT] = 0.0; so[S::S_META + S::T_MODE] = -1.0; }
     return;
   }
   const DevModel& M = c_model;
-  const int r = (int)rec[D::R_MISC + D::M_NROWS];
-  const int mode = (int)rec[D::R_MISC + D::M_MODE];
+  const int r = (int)m_rows;
+  const int mode = (int)m_mode;
   const bool st0 = leg_in_stance(mode, 0), st1 = leg_in_stance(mode, 1);
   double (*G)[NXA + 1] = sG[warp];
   double (*W)[LDW] = sW[warp];
